@@ -1,0 +1,176 @@
+/*
+ * t41rx.h — C-ABI of the B200-native T41 receive chain (libt41rx.so).
+ *
+ * Drop-in boundary for the reference's per-block receive pipeline
+ *     void ProcessIQData(void)            software/T41_SDR/Process.h:15, Process.cpp:70-944
+ * batched over n_streams independent virtual receivers.  The reference passes
+ * every input and output through globals; each of them becomes an explicit
+ * argument or a field of t41rx_params here (reference location cited per field).
+ * Plain pointers and sizes only; no C++ or torch types cross this boundary.
+ *
+ * Buffer layouts (row-major):
+ *   iq         float  [n_streams][n_blocks][2048][2]   interleaved (I,Q) at 192 kS/s, i.e. what
+ *                                                       arm_q15_to_float produced (Process.cpp:107-108;
+ *                                                       I = Q_in_R, Q = Q_in_L)
+ *   audio      float  [n_streams][n_blocks][2048]      float_buffer_L after the volume scale
+ *                                                       (Process.cpp:929), before arm_float_to_q15
+ *   spec_rows  int16  [n_streams][n_rows][512]         pixelnew[] (FFT.cpp:157,245)
+ *   wf_rows    uint16 [n_streams][n_rows][512]         waterfall[] RGB565 (Display.cpp:459-466);
+ *                                                       element 511 is never written by the reference: 0
+ *   psk_bits   int8   [n_streams][n_blocks]            -1 = no symbol decision in this block, else 0/1
+ *   psk_chars  uint8  [n_streams][n_blocks]            decoded varicode character or 0
+ * A block b of a call is "row-producing" (updateDisplayFlag == 1, Display.cpp:261-267) when
+ * row_every > 0 and b % row_every == 0; n_rows = ceil(n_blocks / row_every).
+ *
+ * Every entry point returns 0 on success or a negative T41RX_E* code; the text of the
+ * last failure on the calling thread is available from t41rx_last_error().  The library
+ * has no CPU fallback: without a CUDA device t41rx_create fails.
+ */
+#ifndef T41RX_H
+#define T41RX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define T41RX_BLOCK_SAMPLES 2048   /* BUFFER_SIZE * N_BLOCKS, T41_SDR.ino:368-369 */
+#define T41RX_SPECTRUM_RES 512     /* SPECTRUM_RES, Display.h:12 */
+
+/* demodulation modes: values of SDT.h:57-68 */
+#define T41RX_DEMOD_USB 0
+#define T41RX_DEMOD_LSB 1
+#define T41RX_DEMOD_AM 2
+#define T41RX_DEMOD_NFM 3
+#define T41RX_DEMOD_PSK31 5
+#define T41RX_DEMOD_SAM 8
+
+#define T41RX_OK 0
+#define T41RX_EINVAL -1    /* bad argument / parameter out of range */
+#define T41RX_ECUDA -2     /* CUDA runtime failure (text in t41rx_last_error) */
+#define T41RX_ENOMEM -3
+#define T41RX_ENODEV -4    /* no usable CUDA device: there is no CPU path */
+
+/* t41rx_process flags */
+#define T41RX_FLAG_EXACT_NCO 1u /* run FreqShift2's FP64 oscillator recurrence step by step (bit-exact
+                                   with the reference, serial); default is the closed-form FP64 phasor */
+
+/* Per-receiver parameters = the globals ProcessIQData() samples at block start. */
+typedef struct t41rx_params {
+  int32_t mode;                 /* bands[currentBand].mode        SDT.h:179-192, Process.cpp:251,615 */
+  int32_t f_lo_cut;             /* bands[].FLoCut (Hz)            Filter.cpp:239                      */
+  int32_t f_hi_cut;             /* bands[].FHiCut (Hz)            Filter.cpp:239                      */
+  int32_t nco_freq;             /* NCOFreq (Hz)                   Freq_Shift.cpp:121                  */
+  int32_t agc_mode;             /* AGCMode 0..4                   DSP_Fn.cpp:373,494                  */
+  int32_t agc_thresh;           /* bands[].AGC_thresh (dB)        DSP_Fn.cpp:408                      */
+  int32_t audio_volume;         /* audioVolume 0..100             Process.cpp:929                     */
+  int32_t rf_gain_all_bands;    /* rfGainAllBands (dB)            Process.cpp:117                     */
+  int32_t rf_gain;              /* bands[].RFgain start value     Process.cpp:133 (then Codec_gain)   */
+  int32_t spectrum_zoom;        /* spectrumZoom index 0..4        Process.cpp:185,212                 */
+  int32_t current_scale;        /* currentScale 0..4              FFT.cpp:157                         */
+  int32_t pixel_offset;         /* bands[].pixel_offset           FFT.cpp:157                         */
+  int32_t current_nf;           /* currentNoiseFloor[band]        Display.cpp:250,343                 */
+  int32_t spectrum_noise_floor; /* spectrumNoiseFloor             Display.cpp:343                     */
+  int32_t nfm_filter_bw;        /* nfmFilterBW (Hz)               Process.cpp:259                     */
+  int32_t psk31_enable;         /* DBPSK + varicode tap on the filtered stream (psk31.cpp:235-310)    */
+  float iq_amp_correction;      /* IQAmpCorrectionFactor[band]    Process.cpp:166,171                 */
+  float iq_phase_correction;    /* IQPhaseCorrectionFactor[band]  Process.cpp:167,172                 */
+} t41rx_params;
+
+/* Discrete / scalar DSP state for state-transition parity checks. */
+typedef struct t41rx_debug {
+  int32_t agc_state;            /* DSP_Fn.cpp:483 */
+  int32_t agc_decay_type;       /* DSP_Fn.cpp:482 */
+  int32_t agc_hang_counter;     /* DSP_Fn.cpp:32  */
+  int32_t agc_action;           /* DSP_Fn.cpp:28  */
+  int32_t rf_gain;              /* bands[].RFgain after Codec_gain, Process.cpp:1005 */
+  int32_t codec_timer;          /* Process.cpp:980 */
+  int32_t zoom_sample_ptr;      /* FFT.cpp:13 */
+  int32_t first_block;          /* Process.cpp:47 */
+  float agc_volts;
+  float agc_ring_max;
+  float agc_save_volts;
+  float agc_fast_backaverage;
+  float agc_hang_backaverage;
+  float sam_phzerror;           /* Demod.cpp:19 */
+  float sam_omega2;             /* Demod.cpp:23 */
+  float sam_fil_out;            /* Demod.cpp:21 */
+  float dc_state[2];            /* HP_DC_Butter_state2, Process.cpp:42 */
+  float am_wold;                /* Process.cpp:73 */
+  double osc_vect_q;            /* Freq_Shift.cpp:13 */
+  double osc_vect_i;            /* Freq_Shift.cpp:14 */
+} t41rx_debug;
+
+/* The control-path tables a receiver currently uses (CalcFilters / AGCLoadValues /
+ * ZoomFFTPrep results), for table-level parity checks. */
+typedef struct t41rx_tables {
+  float dec1[28];               /* FIR_dec1_coeffs  Filter.cpp:412 */
+  float dec2[46];               /* FIR_dec2_coeffs  Filter.cpp:413 */
+  float int1[48];               /* FIR_int1_coeffs  Filter.cpp:415 */
+  float int2[32];               /* FIR_int2_coeffs  Filter.cpp:416 */
+  float mask[1024];             /* FIR_filter_mask  Filter.cpp:260-284 */
+  float am_lp[5];               /* biquad_lowpass1_coeffs T41_SDR.ino:560-566 */
+  float zoom_fir[4];            /* Fir_Zoom_FFT_Decimate_coeffs FFT.cpp:39 */
+  float agc[16];                /* max_gain, attack_mult, decay_mult, fast_decay_mult, fast_backmult,
+                                   onemfast_backmult, out_target, min_volts, slope_constant, inv_max_input,
+                                   hang_level, hang_backmult, onemhang_backmult, hang_decay_mult, hangtime,
+                                   fixed_gain (DSP_Fn.cpp:408-434) */
+  int32_t attack_buffsize;      /* DSP_Fn.cpp:409 */
+  int32_t hang_counter_load;    /* DSP_Fn.cpp:554 */
+} t41rx_tables;
+
+typedef struct t41rx_ctx t41rx_ctx;
+
+/* Reference defaults (gwv.cpp:15-25,70-74; bands[] T41_SDR.ino:163-167). */
+void t41rx_default_params(t41rx_params *p);
+/* FLoCut/FHiCut presets a mode change applies (SetupMode, Filter.cpp:341-385). */
+void t41rx_mode_default_cuts(int32_t mode, int32_t *f_lo_cut, int32_t *f_hi_cut);
+
+/* A context owns n_streams receivers on ONE CUDA device (one process per GPU shards
+ * contiguous stream ranges across contexts).  Every receiver starts in the state
+ * InitializeDataArrays() + SoftReset() leave the firmware in (T41_SDR.ino:473-667,753-795). */
+int t41rx_create(t41rx_ctx **out, int n_streams, int device);
+void t41rx_destroy(t41rx_ctx *ctx);
+int t41rx_num_streams(const t41rx_ctx *ctx);
+
+/* Parameter changes take effect at the next block boundary, like CalcFilters() /
+ * AGCLoadValues() / ZoomFFTPrep() running between two ProcessIQData() calls
+ * (Display.cpp:270-275, MenuProc.cpp:275-284, Display.cpp:1402-1417).
+ * set_params applies *p to streams [first, first+count); set_params_each takes count structs. */
+int t41rx_set_params(t41rx_ctx *ctx, int first, int count, const t41rx_params *p);
+int t41rx_set_params_each(t41rx_ctx *ctx, int first, int count, const t41rx_params *p);
+int t41rx_get_params(const t41rx_ctx *ctx, int stream, t41rx_params *p);
+int t41rx_get_tables(const t41rx_ctx *ctx, int stream, t41rx_tables *t);
+int t41rx_get_debug(t41rx_ctx *ctx, int stream, t41rx_debug *d);
+/* Control path only, no GPU needed: the tables a fresh receiver holds after n_seq successive
+ * t41rx_set_params calls (sticky AGC tuning included, DSP_Fn.cpp:378-402). */
+int t41rx_design_tables(const t41rx_params *seq, int n_seq, t41rx_tables *t);
+
+/* n_blocks ProcessIQData() calls per receiver, HOST buffers (pinned or pageable); copies to and
+ * from the device happen inside.  spec_rows / wf_rows may be NULL when row_every == 0;
+ * psk_bits / psk_chars may be NULL. */
+int t41rx_process(t41rx_ctx *ctx, const float *iq, float *audio, int n_blocks, int row_every,
+                  int16_t *spec_rows, uint16_t *wf_rows, int8_t *psk_bits, uint8_t *psk_chars,
+                  uint32_t flags);
+
+/* Same, with DEVICE pointers (resident in HBM) and an optional cudaStream_t (NULL = the
+ * context's own stream).  Asynchronous: returns after enqueueing. */
+int t41rx_process_device(t41rx_ctx *ctx, const float *iq, float *audio, int n_blocks, int row_every,
+                         int16_t *spec_rows, uint16_t *wf_rows, int8_t *psk_bits, uint8_t *psk_chars,
+                         uint32_t flags, void *cuda_stream);
+int t41rx_synchronize(t41rx_ctx *ctx);
+
+/* Instrumentation for bench.py: kernels launched by this context so far, and the CUDA-event
+ * duration (ms) of the most recent fused RX kernel (valid after t41rx_synchronize). */
+int64_t t41rx_kernel_launches(const t41rx_ctx *ctx);
+int t41rx_last_kernel_ms(t41rx_ctx *ctx, float *ms);
+
+const char *t41rx_last_error(void);
+const char *t41rx_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* T41RX_H */

@@ -1,0 +1,455 @@
+/*
+ * rx_api.cu — libt41rx.so: the fused sm_100a receive-chain kernel and the C-ABI around it
+ * (include/t41rx.h).  Host side = parameter cache + control-path design (rx_design.cpp) +
+ * device memory / stream plumbing.  There is no CPU processing path in this library.
+ */
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <new>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/t41rx.h"
+#include "rx_design.h"
+#include "rx_host.h"
+#include "rx_phases.cuh"
+#include "rx_tables_data.h"
+
+namespace t41rx {
+
+/* ------------------------------------------------------------------ */
+/* the kernel                                                          */
+/* ------------------------------------------------------------------ */
+__global__ void __launch_bounds__(kNT, 2) t41rx_fused_rx_kernel(const LaunchArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  Cta c;
+  c.a = a;
+  c.smem = smem;
+  c.s0 = blockIdx.x * kG;
+  c.ng = min(kG, a.n_streams - c.s0);
+  c.t = 0;
+  c.row = 0;
+  c.row_idx = 0;
+  const int tid = threadIdx.x;
+  PhStateIn(c, tid);
+  __syncthreads();
+  for (int t = 0; t < a.n_blocks; ++t) {
+    c.t = t;
+    c.row = (a.row_every > 0) && (t % a.row_every == 0);
+    c.row_idx = c.row ? t / a.row_every : 0;
+#define T41RX_KPHASE(stmt) \
+  do {                     \
+    stmt;                  \
+    __syncthreads();       \
+  } while (0)
+    T41RX_BLOCK_SCHEDULE(T41RX_KPHASE)
+#undef T41RX_KPHASE
+  }
+  PhStateOut(c, tid);
+}
+
+}  // namespace t41rx
+
+using namespace t41rx;
+
+/* ------------------------------------------------------------------ */
+/* error plumbing                                                      */
+/* ------------------------------------------------------------------ */
+static thread_local std::string g_last_error;
+
+static int Fail(int code, const char *fmt, const char *detail = "") {
+  char buf[512];
+  snprintf(buf, sizeof(buf), fmt, detail);
+  g_last_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                              \
+  do {                                                                              \
+    cudaError_t e_ = (expr);                                                        \
+    if (e_ != cudaSuccess) return Fail(T41RX_ECUDA, #expr ": %s", cudaGetErrorString(e_)); \
+  } while (0)
+
+/* ------------------------------------------------------------------ */
+/* context                                                             */
+/* ------------------------------------------------------------------ */
+struct t41rx_ctx {
+  int device = 0;
+  int n_streams = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool ev_valid = false;
+  int64_t launches = 0;
+
+  HostModel host;          /* parameter cache + host copies of every table */
+  int fset_capacity = 0;
+
+  StreamCfg *d_cfg = nullptr;
+  StreamState *d_state = nullptr;
+  FilterSet *d_fsets = nullptr;
+  double *d_nco_tab = nullptr;
+  float2 *d_twiddle = nullptr;
+  double *d_hann = nullptr;
+  float *d_sin = nullptr;
+  float *d_zoom_iir = nullptr;
+  float *d_sam = nullptr;
+  uint16_t *d_gradient = nullptr;
+  uint32_t *d_varicode = nullptr;
+
+  /* device staging for the host-buffer entry point */
+  void *d_iq = nullptr, *d_audio = nullptr, *d_spec = nullptr, *d_wf = nullptr, *d_bits = nullptr, *d_chars = nullptr;
+  size_t cap_iq = 0, cap_audio = 0, cap_spec = 0, cap_wf = 0, cap_bits = 0, cap_chars = 0;
+};
+
+static int EnsureFsetCapacity(t41rx_ctx *ctx, int need) {
+  if (need <= ctx->fset_capacity) return 0;
+  int cap = ctx->fset_capacity ? ctx->fset_capacity : 16;
+  while (cap < need) cap *= 2;
+  FilterSet *d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, sizeof(FilterSet) * cap));
+  if (ctx->d_fsets) {
+    CUDA_TRY(cudaMemcpy(d, ctx->d_fsets, sizeof(FilterSet) * ctx->fset_capacity, cudaMemcpyDeviceToDevice));
+    CUDA_TRY(cudaFree(ctx->d_fsets));
+  }
+  ctx->d_fsets = d;
+  ctx->fset_capacity = cap;
+  return 0;
+}
+
+static int UploadFset(t41rx_ctx *ctx, int id) {
+  int rc = EnsureFsetCapacity(ctx, id + 1);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpy(ctx->d_fsets + id, &ctx->host.fsets[id], sizeof(FilterSet), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+template <class T, class U>
+static int UploadConst(T **dst, const std::vector<U> &src) {
+  static_assert(sizeof(T) % sizeof(U) == 0, "element size");
+  CUDA_TRY(cudaMalloc(dst, src.size() * sizeof(U)));
+  CUDA_TRY(cudaMemcpy(*dst, src.data(), src.size() * sizeof(U), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+static int UploadConstTables(t41rx_ctx *ctx) {
+  int rc;
+  const HostModel &h = ctx->host;
+  if ((rc = UploadConst(&ctx->d_twiddle, h.twiddle))) return rc;
+  if ((rc = UploadConst(&ctx->d_hann, h.hann))) return rc;
+  if ((rc = UploadConst(&ctx->d_sin, h.sin_table))) return rc;
+  if ((rc = UploadConst(&ctx->d_zoom_iir, h.zoom_iir))) return rc;
+  if ((rc = UploadConst(&ctx->d_sam, h.sam_consts))) return rc;
+  if ((rc = UploadConst(&ctx->d_gradient, h.gradient))) return rc;
+  if ((rc = UploadConst(&ctx->d_varicode, h.varicode))) return rc;
+  return 0;
+}
+
+static int Grow(void **buf, size_t *cap, size_t need) {
+  if (need <= *cap) return 0;
+  if (*buf) CUDA_TRY(cudaFree(*buf));
+  *buf = nullptr;
+  *cap = 0;
+  CUDA_TRY(cudaMalloc(buf, need));
+  *cap = need;
+  return 0;
+}
+
+/* ------------------------------------------------------------------ */
+/* C-ABI                                                               */
+/* ------------------------------------------------------------------ */
+extern "C" {
+
+const char *t41rx_last_error(void) { return g_last_error.c_str(); }
+const char *t41rx_version(void) { return "t41rx-b200 0.1 (sm_100a)"; }
+
+void t41rx_default_params(t41rx_params *p) { DefaultParams(p); }
+
+void t41rx_mode_default_cuts(int32_t mode, int32_t *f_lo_cut, int32_t *f_hi_cut) {
+  switch (mode) {
+    case T41RX_DEMOD_LSB: *f_hi_cut = -200; *f_lo_cut = -3000; break;
+    case T41RX_DEMOD_AM:
+    case T41RX_DEMOD_SAM: *f_hi_cut = 3000; *f_lo_cut = -3000; break;
+    default: *f_hi_cut = 3000; *f_lo_cut = 200; break;
+  }
+}
+
+void t41rx_destroy(t41rx_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  void *bufs[] = {ctx->d_cfg, ctx->d_state, ctx->d_fsets, ctx->d_nco_tab, ctx->d_twiddle, ctx->d_hann, ctx->d_sin,
+                  ctx->d_zoom_iir, ctx->d_sam, ctx->d_gradient, ctx->d_varicode, ctx->d_iq, ctx->d_audio,
+                  ctx->d_spec, ctx->d_wf, ctx->d_bits, ctx->d_chars};
+  for (void *b : bufs)
+    if (b) cudaFree(b);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int t41rx_create(t41rx_ctx **out, int n_streams, int device) {
+  if (!out || n_streams <= 0) return Fail(T41RX_EINVAL, "t41rx_create: bad arguments%s");
+  *out = nullptr;
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0)
+    return Fail(T41RX_ENODEV, "t41rx_create: no CUDA device (this library has no CPU path)%s");
+  if (device < 0 || device >= n_dev) return Fail(T41RX_EINVAL, "t41rx_create: device index out of range%s");
+  CUDA_TRY(cudaSetDevice(device));
+  t41rx_ctx *ctx = new (std::nothrow) t41rx_ctx();
+  if (!ctx) return Fail(T41RX_ENOMEM, "t41rx_create: out of memory%s");
+  ctx->device = device;
+  ctx->n_streams = n_streams;
+  int rc = 0;
+  auto bail = [&](int code) {
+    t41rx_destroy(ctx);
+    return code;
+  };
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess)
+    return bail(Fail(T41RX_ECUDA, "t41rx_create: stream/event creation failed%s"));
+  if (cudaFuncSetAttribute(t41rx_fused_rx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)(kSmemFloats * sizeof(float))) != cudaSuccess)
+    return bail(Fail(T41RX_ECUDA, "t41rx_create: kernel image for this GPU missing (built for sm_100a)%s"));
+  ctx->host.Init(n_streams);
+  if ((rc = UploadConstTables(ctx))) return bail(rc);
+  if (cudaMalloc(&ctx->d_cfg, sizeof(StreamCfg) * n_streams) != cudaSuccess ||
+      cudaMalloc(&ctx->d_state, sizeof(StreamState) * n_streams) != cudaSuccess ||
+      cudaMalloc(&ctx->d_nco_tab, sizeof(double) * 192 * n_streams) != cudaSuccess)
+    return bail(Fail(T41RX_ENOMEM, "t41rx_create: device allocation failed%s"));
+  {
+    std::vector<StreamState> init(n_streams);
+    for (int s = 0; s < n_streams; ++s) HostStateInit(&init[s]);
+    if (cudaMemcpy(ctx->d_state, init.data(), sizeof(StreamState) * n_streams, cudaMemcpyHostToDevice) != cudaSuccess)
+      return bail(Fail(T41RX_ECUDA, "t41rx_create: state upload failed%s"));
+  }
+  if ((rc = UploadFset(ctx, 0))) return bail(rc);
+  if (cudaMemcpy(ctx->d_nco_tab, ctx->host.nco_tab.data(), sizeof(double) * ctx->host.nco_tab.size(),
+                 cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(ctx->d_cfg, ctx->host.cfg.data(), sizeof(StreamCfg) * n_streams, cudaMemcpyHostToDevice) != cudaSuccess)
+    return bail(Fail(T41RX_ECUDA, "t41rx_create: table upload failed%s"));
+  *out = ctx;
+  return T41RX_OK;
+}
+
+int t41rx_num_streams(const t41rx_ctx *ctx) { return ctx ? ctx->n_streams : 0; }
+
+static int SetParamsImpl(t41rx_ctx *ctx, int first, int count, const t41rx_params *p, bool each) {
+  if (!ctx || !p || first < 0 || count <= 0 || first + count > ctx->n_streams)
+    return Fail(T41RX_EINVAL, "t41rx_set_params: bad range%s");
+  for (int i = 0; i < count; ++i)
+    if (!ValidateParams(each ? p[i] : p[0])) return Fail(T41RX_EINVAL, "t41rx_set_params: parameter out of range%s");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));   /* changes apply at a block boundary */
+  for (int i = 0; i < count; ++i) {
+    const int s = first + i;
+    StatePatch patch;
+    int new_fset = -1;
+    if (ctx->host.Apply(s, each ? p[i] : p[0], &patch, &new_fset)) return Fail(T41RX_EINVAL, "t41rx_set_params: rejected%s");
+    if (new_fset >= 0) {
+      int rc = UploadFset(ctx, new_fset);
+      if (rc) return rc;
+    }
+    if (patch.set_rf_gain)
+      CUDA_TRY(cudaMemcpy(&ctx->d_state[s].rf_gain, &patch.rf_gain, sizeof(int32_t), cudaMemcpyHostToDevice));
+    if (patch.reset_zoom_ptr) {
+      const int32_t z = 0;
+      CUDA_TRY(cudaMemcpy(&ctx->d_state[s].zoom_ptr, &z, sizeof(z), cudaMemcpyHostToDevice));
+    }
+  }
+  CUDA_TRY(cudaMemcpy(ctx->d_cfg + first, ctx->host.cfg.data() + first, sizeof(StreamCfg) * count, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(ctx->d_nco_tab + (size_t)192 * first, ctx->host.nco_tab.data() + (size_t)192 * first,
+                      sizeof(double) * 192 * count, cudaMemcpyHostToDevice));
+  return T41RX_OK;
+}
+
+int t41rx_set_params(t41rx_ctx *ctx, int first, int count, const t41rx_params *p) {
+  return SetParamsImpl(ctx, first, count, p, false);
+}
+int t41rx_set_params_each(t41rx_ctx *ctx, int first, int count, const t41rx_params *p) {
+  return SetParamsImpl(ctx, first, count, p, true);
+}
+
+int t41rx_get_params(const t41rx_ctx *ctx, int stream, t41rx_params *p) {
+  if (!ctx || !p || stream < 0 || stream >= ctx->n_streams) return Fail(T41RX_EINVAL, "t41rx_get_params: bad arguments%s");
+  *p = ctx->host.params[stream];
+  return T41RX_OK;
+}
+
+static void FillTables(const HostModel &h, int stream, t41rx_tables *t) {
+  memset(t, 0, sizeof(*t));
+  const StreamCfg &c = h.cfg[stream];
+  const FilterSet &fs = h.fsets[c.filter_id];
+  memcpy(t->dec1, fs.dec1, sizeof(t->dec1));
+  memcpy(t->dec2, fs.dec2, sizeof(t->dec2));
+  memcpy(t->int1, fs.int1, sizeof(t->int1));
+  memcpy(t->int2, fs.int2, sizeof(t->int2));
+  memcpy(t->mask, fs.mask, sizeof(t->mask));
+  memcpy(t->am_lp, c.am_lp, sizeof(t->am_lp));
+  memcpy(t->zoom_fir, c.zoom_fir, sizeof(t->zoom_fir));
+  const AgcConsts &a = c.agc;
+  const float v[16] = {a.max_gain, a.attack_mult, a.decay_mult, a.fast_decay_mult, a.fast_backmult,
+                       a.onemfast_backmult, a.out_target, a.min_volts, a.slope_constant, a.inv_max_input,
+                       a.hang_level, a.hang_backmult, a.onemhang_backmult, a.hang_decay_mult, a.hangtime,
+                       a.fixed_gain};
+  memcpy(t->agc, v, sizeof(v));
+  t->attack_buffsize = h.attack_buffsize[stream];
+  t->hang_counter_load = a.hang_counter_load;
+}
+
+int t41rx_get_tables(const t41rx_ctx *ctx, int stream, t41rx_tables *t) {
+  if (!ctx || !t || stream < 0 || stream >= ctx->n_streams) return Fail(T41RX_EINVAL, "t41rx_get_tables: bad arguments%s");
+  FillTables(ctx->host, stream, t);
+  return T41RX_OK;
+}
+
+int t41rx_design_tables(const t41rx_params *seq, int n_seq, t41rx_tables *t) {
+  if (!t || n_seq < 0 || (n_seq > 0 && !seq)) return Fail(T41RX_EINVAL, "t41rx_design_tables: bad arguments%s");
+  HostModel h;
+  h.Init(1);
+  for (int i = 0; i < n_seq; ++i) {
+    StatePatch patch;
+    int new_fset = -1;
+    if (h.Apply(0, seq[i], &patch, &new_fset)) return Fail(T41RX_EINVAL, "t41rx_design_tables: parameter out of range%s");
+  }
+  FillTables(h, 0, t);
+  return T41RX_OK;
+}
+
+int t41rx_get_debug(t41rx_ctx *ctx, int stream, t41rx_debug *d) {
+  if (!ctx || !d || stream < 0 || stream >= ctx->n_streams) return Fail(T41RX_EINVAL, "t41rx_get_debug: bad arguments%s");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  StreamState st;
+  CUDA_TRY(cudaMemcpy(&st, ctx->d_state + stream, sizeof(st), cudaMemcpyDeviceToHost));
+  memset(d, 0, sizeof(*d));
+  d->agc_state = st.agc_state;
+  d->agc_decay_type = st.agc_decay_type;
+  d->agc_hang_counter = st.agc_hang_counter;
+  d->agc_action = st.agc_action;
+  d->rf_gain = st.rf_gain;
+  d->codec_timer = (int32_t)st.codec_timer;
+  d->zoom_sample_ptr = st.zoom_ptr;
+  d->first_block = st.first_block;
+  d->agc_volts = st.agc_volts;
+  d->agc_ring_max = st.agc_ring_max;
+  d->agc_save_volts = st.agc_save_volts;
+  d->agc_fast_backaverage = st.agc_fast_back;
+  d->agc_hang_backaverage = st.agc_hang_back;
+  d->sam_phzerror = st.sam_phzerror;
+  d->sam_omega2 = st.sam_omega2;
+  d->sam_fil_out = st.sam_fil_out;
+  d->dc_state[0] = st.dc_d1;
+  d->dc_state[1] = st.dc_d2;
+  d->am_wold = st.am_wold;
+  if (st.nco_closed) {
+    const double r = sqrt(st.osc_q * st.osc_q + st.osc_i * st.osc_i);
+    d->osc_vect_q = r * cos(st.nco_phase);
+    d->osc_vect_i = r * sin(st.nco_phase);
+  } else {
+    d->osc_vect_q = st.osc_q;
+    d->osc_vect_i = st.osc_i;
+  }
+  return T41RX_OK;
+}
+
+int t41rx_process_device(t41rx_ctx *ctx, const float *iq, float *audio, int n_blocks, int row_every,
+                         int16_t *spec_rows, uint16_t *wf_rows, int8_t *psk_bits, uint8_t *psk_chars,
+                         uint32_t flags, void *cuda_stream) {
+  if (!ctx || !iq || !audio || n_blocks <= 0 || row_every < 0)
+    return Fail(T41RX_EINVAL, "t41rx_process_device: bad arguments%s");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+  LaunchArgs a;
+  memset(&a, 0, sizeof(a));
+  a.iq = iq;
+  a.audio = audio;
+  a.spec_rows = row_every > 0 ? spec_rows : nullptr;
+  a.wf_rows = row_every > 0 ? wf_rows : nullptr;
+  a.psk_bits = psk_bits;
+  a.psk_chars = psk_chars;
+  a.cfg = ctx->d_cfg;
+  a.st = ctx->d_state;
+  a.fsets = ctx->d_fsets;
+  a.nco_tab = ctx->d_nco_tab;
+  a.twiddle = ctx->d_twiddle;
+  a.hann = ctx->d_hann;
+  a.sin_table = ctx->d_sin;
+  a.zoom_iir = ctx->d_zoom_iir;
+  a.sam_consts = ctx->d_sam;
+  a.gradient = ctx->d_gradient;
+  a.varicode = ctx->d_varicode;
+  a.n_streams = ctx->n_streams;
+  a.n_blocks = n_blocks;
+  a.row_every = row_every;
+  a.n_rows = row_every > 0 ? (n_blocks + row_every - 1) / row_every : 0;
+  a.flags = flags;
+  const int grid = (ctx->n_streams + kG - 1) / kG;
+  CUDA_TRY(cudaEventRecord(ctx->ev0, st));
+  t41rx_fused_rx_kernel<<<grid, kNT, kSmemFloats * sizeof(float), st>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaEventRecord(ctx->ev1, st));
+  ctx->ev_valid = true;
+  ctx->launches += 1;
+  return T41RX_OK;
+}
+
+int t41rx_synchronize(t41rx_ctx *ctx) {
+  if (!ctx) return Fail(T41RX_EINVAL, "t41rx_synchronize: null context%s");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return T41RX_OK;
+}
+
+int t41rx_process(t41rx_ctx *ctx, const float *iq, float *audio, int n_blocks, int row_every,
+                  int16_t *spec_rows, uint16_t *wf_rows, int8_t *psk_bits, uint8_t *psk_chars, uint32_t flags) {
+  if (!ctx || !iq || !audio || n_blocks <= 0 || row_every < 0)
+    return Fail(T41RX_EINVAL, "t41rx_process: bad arguments%s");
+  if (row_every > 0 && !spec_rows && !wf_rows) row_every = 0;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const size_t S = (size_t)ctx->n_streams, T = (size_t)n_blocks;
+  const size_t n_rows = row_every > 0 ? (T + row_every - 1) / row_every : 0;
+  const size_t b_iq = S * T * 2 * kBlock * sizeof(float), b_audio = S * T * kBlock * sizeof(float);
+  const size_t b_spec = S * n_rows * kSpecRes * sizeof(int16_t), b_wf = S * n_rows * kSpecRes * sizeof(uint16_t);
+  const size_t b_psk = S * T;
+  int rc;
+  if ((rc = Grow(&ctx->d_iq, &ctx->cap_iq, b_iq))) return rc;
+  if ((rc = Grow(&ctx->d_audio, &ctx->cap_audio, b_audio))) return rc;
+  if (n_rows && spec_rows && (rc = Grow(&ctx->d_spec, &ctx->cap_spec, b_spec))) return rc;
+  if (n_rows && wf_rows && (rc = Grow(&ctx->d_wf, &ctx->cap_wf, b_wf))) return rc;
+  if (psk_bits && (rc = Grow(&ctx->d_bits, &ctx->cap_bits, b_psk))) return rc;
+  if (psk_chars && (rc = Grow(&ctx->d_chars, &ctx->cap_chars, b_psk))) return rc;
+  cudaStream_t st = ctx->stream;
+  CUDA_TRY(cudaMemcpyAsync(ctx->d_iq, iq, b_iq, cudaMemcpyHostToDevice, st));
+  rc = t41rx_process_device(ctx, (const float *)ctx->d_iq, (float *)ctx->d_audio, n_blocks, row_every,
+                            (n_rows && spec_rows) ? (int16_t *)ctx->d_spec : nullptr,
+                            (n_rows && wf_rows) ? (uint16_t *)ctx->d_wf : nullptr,
+                            psk_bits ? (int8_t *)ctx->d_bits : nullptr, psk_chars ? (uint8_t *)ctx->d_chars : nullptr,
+                            flags, nullptr);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(audio, ctx->d_audio, b_audio, cudaMemcpyDeviceToHost, st));
+  if (n_rows && spec_rows) CUDA_TRY(cudaMemcpyAsync(spec_rows, ctx->d_spec, b_spec, cudaMemcpyDeviceToHost, st));
+  if (n_rows && wf_rows) CUDA_TRY(cudaMemcpyAsync(wf_rows, ctx->d_wf, b_wf, cudaMemcpyDeviceToHost, st));
+  if (psk_bits) CUDA_TRY(cudaMemcpyAsync(psk_bits, ctx->d_bits, b_psk, cudaMemcpyDeviceToHost, st));
+  if (psk_chars) CUDA_TRY(cudaMemcpyAsync(psk_chars, ctx->d_chars, b_psk, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return T41RX_OK;
+}
+
+int64_t t41rx_kernel_launches(const t41rx_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int t41rx_last_kernel_ms(t41rx_ctx *ctx, float *ms) {
+  if (!ctx || !ms) return Fail(T41RX_EINVAL, "t41rx_last_kernel_ms: bad arguments%s");
+  if (!ctx->ev_valid) return Fail(T41RX_EINVAL, "t41rx_last_kernel_ms: no launch yet%s");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  CUDA_TRY(cudaEventSynchronize(ctx->ev1));
+  CUDA_TRY(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+  return T41RX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,234 @@
+"""Host-side mirror of the reference's receive-chain interface over libt41rx.so (ctypes).
+
+The reference exposes `void ProcessIQData(void)` working on globals (Process.h:15); here the
+same call is `Receiver.process(iq)` on a bank of virtual receivers, with the globals the chain
+samples (`bands[].mode/FLoCut/FHiCut`, `NCOFreq`, `AGCMode`, `spectrumZoom`, ...) set through
+`Receiver.set_params`.  This module is plumbing only: every sample is processed by the CUDA
+kernels inside libt41rx.so; if the library or a GPU is missing, construction raises.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libt41rx.so")
+
+DEMOD_USB, DEMOD_LSB, DEMOD_AM, DEMOD_NFM, DEMOD_PSK31, DEMOD_SAM = 0, 1, 2, 3, 5, 8
+BLOCK = 2048
+SPECTRUM_RES = 512
+FLAG_EXACT_NCO = 1
+
+# algorithmic HBM bytes per stream-block
+BYTES_PER_BLOCK = 2 * BLOCK * 4 + BLOCK * 4        # 16 KiB I/Q in + 8 KiB audio out
+BYTES_PER_ROW = SPECTRUM_RES * 2 + SPECTRUM_RES * 2  # int16 spectrum row + RGB565 waterfall row
+
+
+class Params(C.Structure):
+    """t41rx_params (include/t41rx.h)."""
+    _fields_ = [(n, C.c_int32) for n in (
+        "mode", "f_lo_cut", "f_hi_cut", "nco_freq", "agc_mode", "agc_thresh", "audio_volume",
+        "rf_gain_all_bands", "rf_gain", "spectrum_zoom", "current_scale", "pixel_offset",
+        "current_nf", "spectrum_noise_floor", "nfm_filter_bw", "psk31_enable")] + [
+        ("iq_amp_correction", C.c_float), ("iq_phase_correction", C.c_float)]
+
+    def copy(self):
+        p = Params()
+        C.memmove(C.byref(p), C.byref(self), C.sizeof(Params))
+        return p
+
+
+class Debug(C.Structure):
+    """t41rx_debug."""
+    _fields_ = [(n, C.c_int32) for n in (
+        "agc_state", "agc_decay_type", "agc_hang_counter", "agc_action", "rf_gain", "codec_timer",
+        "zoom_sample_ptr", "first_block")] + [(n, C.c_float) for n in (
+        "agc_volts", "agc_ring_max", "agc_save_volts", "agc_fast_backaverage", "agc_hang_backaverage",
+        "sam_phzerror", "sam_omega2", "sam_fil_out")] + [
+        ("dc_state", C.c_float * 2), ("am_wold", C.c_float),
+        ("osc_vect_q", C.c_double), ("osc_vect_i", C.c_double)]
+
+
+class Tables(C.Structure):
+    """t41rx_tables."""
+    _fields_ = [("dec1", C.c_float * 28), ("dec2", C.c_float * 46), ("int1", C.c_float * 48),
+                ("int2", C.c_float * 32), ("mask", C.c_float * 1024), ("am_lp", C.c_float * 5),
+                ("zoom_fir", C.c_float * 4), ("agc", C.c_float * 16),
+                ("attack_buffsize", C.c_int32), ("hang_counter_load", C.c_int32)]
+
+    def as_dict(self):
+        d = {n: np.array(getattr(self, n), dtype=np.float32) for n in
+             ("dec1", "dec2", "int1", "int2", "mask", "am_lp", "zoom_fir", "agc")}
+        d["attack_buffsize"] = int(self.attack_buffsize)
+        d["hang_counter_load"] = int(self.hang_counter_load)
+        return d
+
+
+EXPORTS = (
+    "t41rx_default_params", "t41rx_mode_default_cuts", "t41rx_create", "t41rx_destroy",
+    "t41rx_num_streams", "t41rx_set_params", "t41rx_set_params_each", "t41rx_get_params",
+    "t41rx_get_tables", "t41rx_get_debug", "t41rx_design_tables", "t41rx_process",
+    "t41rx_process_device", "t41rx_synchronize", "t41rx_kernel_launches", "t41rx_last_kernel_ms",
+    "t41rx_last_error", "t41rx_version")
+
+
+def build_library():
+    """Compile libt41rx.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    subprocess.check_call(["make", "-s", "-C", os.path.join(_HERE, "csrc"), "all"])
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("libt41rx.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = C.CDLL(LIB_PATH)
+        vp, ip = C.c_void_p, C.c_int
+        L.t41rx_default_params.argtypes = [C.POINTER(Params)]
+        L.t41rx_mode_default_cuts.argtypes = [C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        L.t41rx_create.argtypes = [C.POINTER(vp), ip, ip]
+        L.t41rx_destroy.argtypes = [vp]
+        L.t41rx_num_streams.argtypes = [vp]
+        L.t41rx_set_params.argtypes = [vp, ip, ip, C.POINTER(Params)]
+        L.t41rx_set_params_each.argtypes = [vp, ip, ip, C.POINTER(Params)]
+        L.t41rx_get_params.argtypes = [vp, ip, C.POINTER(Params)]
+        L.t41rx_get_tables.argtypes = [vp, ip, C.POINTER(Tables)]
+        L.t41rx_get_debug.argtypes = [vp, ip, C.POINTER(Debug)]
+        L.t41rx_design_tables.argtypes = [C.POINTER(Params), ip, C.POINTER(Tables)]
+        L.t41rx_process.argtypes = [vp, vp, vp, ip, ip, vp, vp, vp, vp, C.c_uint32]
+        L.t41rx_process_device.argtypes = [vp, vp, vp, ip, ip, vp, vp, vp, vp, C.c_uint32, vp]
+        L.t41rx_synchronize.argtypes = [vp]
+        L.t41rx_kernel_launches.argtypes = [vp]
+        L.t41rx_kernel_launches.restype = C.c_int64
+        L.t41rx_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
+        L.t41rx_last_error.restype = C.c_char_p
+        L.t41rx_version.restype = C.c_char_p
+        _lib = L
+    return _lib
+
+
+class T41RxError(RuntimeError):
+    pass
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise T41RxError("%s failed (%d): %s" % (what, rc, lib().t41rx_last_error().decode()))
+
+
+def default_params():
+    p = Params()
+    lib().t41rx_default_params(C.byref(p))
+    return p
+
+
+def mode_default_cuts(mode):
+    lo, hi = C.c_int32(), C.c_int32()
+    lib().t41rx_mode_default_cuts(mode, C.byref(lo), C.byref(hi))
+    return lo.value, hi.value
+
+
+def design_tables(param_sequence):
+    """Control path only (no GPU): tables of a fresh receiver after the given set_params calls."""
+    arr = (Params * max(1, len(param_sequence)))(*param_sequence)
+    t = Tables()
+    _check(lib().t41rx_design_tables(arr, len(param_sequence), C.byref(t)), "t41rx_design_tables")
+    return t.as_dict()
+
+
+def _np_ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Receiver:
+    """A bank of n_streams virtual T41 receivers on one CUDA device."""
+
+    def __init__(self, n_streams, device=0):
+        self._h = C.c_void_p()
+        self.n_streams = int(n_streams)
+        self.device = int(device)
+        _check(lib().t41rx_create(C.byref(self._h), self.n_streams, self.device), "t41rx_create")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().t41rx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ---- parameters (the reference's globals) ----
+    def set_params(self, p, first=0, count=None):
+        count = self.n_streams - first if count is None else count
+        _check(lib().t41rx_set_params(self._h, first, count, C.byref(p)), "t41rx_set_params")
+
+    def set_params_each(self, plist, first=0):
+        arr = (Params * len(plist))(*plist)
+        _check(lib().t41rx_set_params_each(self._h, first, len(plist), arr), "t41rx_set_params_each")
+
+    def get_params(self, stream):
+        p = Params()
+        _check(lib().t41rx_get_params(self._h, stream, C.byref(p)), "t41rx_get_params")
+        return p
+
+    def tables(self, stream):
+        t = Tables()
+        _check(lib().t41rx_get_tables(self._h, stream, C.byref(t)), "t41rx_get_tables")
+        return t.as_dict()
+
+    def debug(self, stream):
+        d = Debug()
+        _check(lib().t41rx_get_debug(self._h, stream, C.byref(d)), "t41rx_get_debug")
+        return d
+
+    # ---- ProcessIQData over host buffers ----
+    def process(self, iq, row_every=0, want_psk=False, flags=0, out=None):
+        """iq: float32 [n_streams, n_blocks, 2048, 2] (host).  Returns dict of host arrays."""
+        iq = np.ascontiguousarray(iq, dtype=np.float32)
+        S, T = self.n_streams, iq.shape[1]
+        if iq.shape != (S, T, BLOCK, 2):
+            raise ValueError("iq must have shape [n_streams, n_blocks, 2048, 2]")
+        n_rows = 0 if row_every <= 0 else (T + row_every - 1) // row_every
+        if out is None:
+            out = dict(audio=np.empty((S, T, BLOCK), np.float32),
+                       spec=np.zeros((S, n_rows, SPECTRUM_RES), np.int16),
+                       wf=np.zeros((S, n_rows, SPECTRUM_RES), np.uint16),
+                       psk_bits=np.full((S, T), -1, np.int8) if want_psk else None,
+                       psk_chars=np.zeros((S, T), np.uint8) if want_psk else None)
+        _check(lib().t41rx_process(self._h, _np_ptr(iq), _np_ptr(out["audio"]), T, row_every,
+                                   _np_ptr(out["spec"]) if n_rows else None,
+                                   _np_ptr(out["wf"]) if n_rows else None,
+                                   _np_ptr(out.get("psk_bits")), _np_ptr(out.get("psk_chars")), flags),
+               "t41rx_process")
+        return out
+
+    # ---- ProcessIQData over device buffers (raw pointers, e.g. torch.Tensor.data_ptr()) ----
+    def process_device(self, iq_ptr, audio_ptr, n_blocks, row_every=0, spec_ptr=None, wf_ptr=None,
+                       psk_bits_ptr=None, psk_chars_ptr=None, flags=0, cuda_stream=None):
+        _check(lib().t41rx_process_device(self._h, iq_ptr, audio_ptr, n_blocks, row_every, spec_ptr, wf_ptr,
+                                          psk_bits_ptr, psk_chars_ptr, flags, cuda_stream),
+               "t41rx_process_device")
+
+    def synchronize(self):
+        _check(lib().t41rx_synchronize(self._h), "t41rx_synchronize")
+
+    def kernel_launches(self):
+        return int(lib().t41rx_kernel_launches(self._h))
+
+    def last_kernel_ms(self):
+        ms = C.c_float()
+        _check(lib().t41rx_last_kernel_ms(self._h, C.byref(ms)), "t41rx_last_kernel_ms")
+        return float(ms.value)
