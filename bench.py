@@ -1,0 +1,347 @@
+#!/usr/bin/env python3
+"""bench.py — throughput of the T41 receive-chain hot path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the fused RX chain (ProcessIQData x n_blocks) over the whole bank of
+virtual receivers of a rank.  Workload = BASELINE.json configs[1]: 1024 concurrent receivers per
+GPU, SSB + AM mixed, 192 kS/s, per-receiver NCO frequency, AGC on, one spectrum + waterfall
+row per receiver per step.  With N > 1 (torchrun, one rank per GPU) every rank runs its own 1024
+receivers (receivers are independent: no data-path collective; weak scaling) and the time is
+the max over ranks.
+
+Prints ONE JSON line (rank 0).  `value`  : complex Msamples/s, inputs resident in HBM, CUDA events.
+                                 `e2e`    : same metric through t41rx_process with pinned HOST
+                                            buffers (H2D + kernel + D2H inside the timed region).
+                                 `roofline`: algorithmic bytes / measured kernel time vs measured HBM peak.
+                                 `cpu_baseline`: the CPU oracle on the host cores, bounded sample.
+`--impl reference` times the reference's own CPU implementation of the path (oracle/_ref, the
+reference translation units compiled in place; falls back to the oracle port) on all host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "aggregate IQ Msamples/s (full RX chain)"
+UNIT = "Msamples/s"
+N_DISTINCT = 16
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=1024, help="virtual receivers per GPU")
+    ap.add_argument("--blocks", type=int, default=64, help="2048-sample blocks per receiver per step")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget of the cpu_baseline sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload(n_blocks):
+    """C2: even receivers USB (+300..+3000), odd AM (+-3000), per-receiver tone / NCO."""
+    import cases
+    from t41_sdr_b200 import synth
+    r = np.random.Generator(np.random.PCG64(2024))
+    params, sigs = [], []
+    for k in range(N_DISTINCT):
+        nco = int(r.integers(-20000, 20001))
+        if k % 2 == 0:
+            params.append(cases.P(mode=cases.USB, f_lo_cut=300, f_hi_cut=3000, nco_freq=nco, agc_mode=1))
+            sigs.append(synth.tone(900 + k, n_blocks, float(r.uniform(300, 2700)), mode=cases.USB, nco_freq=nco))
+        else:
+            params.append(cases.P(mode=cases.AM, nco_freq=nco, agc_mode=1))
+            sigs.append(synth.am(900 + k, n_blocks, mode=cases.AM, nco_freq=nco, depth=0.5, f_mod=400.0))
+    return params, sigs
+
+
+def config_dict(args):
+    return {"workload": "C2: %d concurrent virtual receivers per GPU, SSB+AM mixed, 192 kS/s, AGC Long, "
+                        "per-receiver NCO, full RX chain fused" % args.streams,
+            "receivers_per_gpu": args.streams, "blocks_per_step": args.blocks, "block_samples": 2048,
+            "rows_per_receiver_per_step": 1, "distinct_waveforms": N_DISTINCT,
+            "l2_policy": "inputs larger than L2 (%.0f MiB of I/Q per step per GPU)" % (
+                args.streams * args.blocks * 16384 / 2 ** 20),
+            "parallelism": "receivers sharded across GPUs, no data-path collective"}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU legs (the only places bench.py touches oracle/)
+# ---------------------------------------------------------------------------------------------
+def cpu_run(kind, params, sigs, n_blocks, seconds, cores):
+    """Time the CPU chain on `cores` threads (ctypes releases the GIL).  Returns Msamples/s."""
+    import oracle_py as O
+    use_ref = (kind == "reference") and O.tier_a_available()
+    if not use_ref and not os.path.exists(O.TIER_B_PATH):
+        O.build_oracle()
+    mk = (lambda p: O.RefStream(p)) if use_ref else (lambda p: O.OracleStream(p))
+    streams = [mk(params[i % len(params)]) for i in range(cores)]
+    # calibrate on one thread
+    t0 = time.perf_counter()
+    streams[0].process(sigs[0][:min(n_blocks, 32)], 0)
+    per_block = (time.perf_counter() - t0) / min(n_blocks, 32)
+    reps = max(1, int(round(seconds / (per_block * n_blocks))))   # every thread runs ~`seconds` in parallel
+    done = [0] * cores
+
+    def work(i):
+        sig = sigs[i % len(sigs)]
+        for _ in range(reps):
+            streams[i].process(sig, n_blocks)   # one spectrum row per pass, like the GPU step
+            done[i] += n_blocks
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(cores)]
+    t0 = time.perf_counter()
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    dt = time.perf_counter() - t0
+    total_blocks = sum(done)
+    return total_blocks * 2048 / dt / 1e6, ("reference" if use_ref else "port"), total_blocks, dt
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    params, sigs = workload(args.blocks)
+    vals = []
+    kind = "port"
+    total = 0
+    for _ in range(max(1, args.warmup)):
+        cpu_run("reference", params, sigs, args.blocks, 1.0, cores)
+    t_all0 = time.perf_counter()
+    for _ in range(max(1, args.steps)):
+        v, kind, blocks, dt = cpu_run("reference", params, sigs, args.blocks, max(1.0, args.cpu_seconds / max(1, args.steps)), cores)
+        vals.append(v)
+        total += blocks
+    t_all = time.perf_counter() - t_all0
+    value = statistics.median(vals)
+    sample = "%d threads x private receivers, %d stream-blocks in %.1f s (C2 parameter mix)" % (cores, total, t_all)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / max(1, args.steps),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(args),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.path = tempfile.mktemp(prefix="t41rx_clocks_", suffix=".csv")
+        self.proc = None
+
+    def start(self):
+        try:
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.fh,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+            self.fh.close()
+            sm, mx, reasons = [], [], set()
+            for ln in open(self.path):
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            if sm:
+                out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                       "samples": len(sm)}
+        except Exception:
+            pass
+        finally:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+        return out
+
+
+def measured_peak():
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(pk["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def ours(args):
+    import torch
+    import torch.distributed as dist
+    import rx_driver
+    from t41_sdr_b200 import rx
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the RX chain has no CPU path (use --impl reference for the CPU chain)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    S, T = args.streams, args.blocks
+    params, sigs = workload(T)
+    eng = rx.Receiver(S, device=local)
+    eng.set_params_each([rx_driver.to_rx_params(params[s % N_DISTINCT]) for s in range(S)])
+
+    # synthetic input resident in HBM: receiver s gets waveform s % N_DISTINCT
+    base = torch.from_numpy(np.stack(sigs)).to(dev)                       # [D, T, 2048, 2]
+    idx = torch.arange(S, device=dev) % N_DISTINCT
+    iq = base.index_select(0, idx).contiguous()                            # [S, T, 2048, 2]
+    del base
+    audio = torch.empty((S, T, 2048), dtype=torch.float32, device=dev)
+    spec = torch.empty((S, 1, 512), dtype=torch.int16, device=dev)
+    wf = torch.empty((S, 1, 512), dtype=torch.int16, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step():
+        eng.process_device(iq.data_ptr(), audio.data_ptr(), T, T, spec.data_ptr(), wf.data_ptr(),
+                           None, None, 0, stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    launches0 = eng.kernel_launches()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record(stream)
+    for a, b in evs:
+        a.record(stream)
+        step()
+        b.record(stream)
+    t_end.record(stream)
+    barrier()
+    total_ms = t_start.elapsed_time(t_end)
+    launch_ms = [a.elapsed_time(b) for a, b in evs]
+    gpu_launches = eng.kernel_launches() - launches0
+    clk = clocks.stop()
+
+    tm = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    total_ms_max = float(tm.item())
+    samples_per_step = world * S * T * 2048
+    value = samples_per_step * args.steps / (total_ms_max * 1e-3) / 1e6
+
+    # roofline of the fused kernel (the only kernel of a step)
+    bytes_per_launch = S * T * rx.BYTES_PER_BLOCK + S * rx.BYTES_PER_ROW
+    avg_launch_s = statistics.mean(launch_ms) * 1e-3
+    achieved = bytes_per_launch / avg_launch_s / 1e9
+    peak, peak_src = measured_peak()
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "t41rx_fused_rx_kernel", "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": statistics.mean(launch_ms)}
+
+    # end to end through the host-buffer C-ABI call: pinned host I/Q in, audio + rows out
+    e2e = None
+    if not args.no_e2e:
+        h_iq = torch.empty((S, T, 2048, 2), dtype=torch.float32).pin_memory()
+        h_iq.copy_(iq.cpu())
+        h_out = dict(audio=torch.empty((S, T, 2048), dtype=torch.float32).pin_memory().numpy(),
+                     spec=torch.empty((S, 1, 512), dtype=torch.int16).pin_memory().numpy(),
+                     wf=torch.empty((S, 1, 512), dtype=torch.int16).pin_memory().numpy().view(np.uint16),
+                     psk_bits=None, psk_chars=None)
+        h_iq_np = h_iq.numpy()
+        for _ in range(2):
+            eng.process(h_iq_np, row_every=T, out=h_out)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            eng.process(h_iq_np, row_every=T, out=h_out)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        gpu_launches += args.steps
+        e2e = {"value": samples_per_step * args.steps / dt / 1e6, "unit": UNIT,
+               "h2d_bytes_per_step": S * T * 16384, "d2h_bytes_per_step": S * T * 8192 + S * rx.BYTES_PER_ROW,
+               "timed_with": "host wall clock around t41rx_process (blocking), max over ranks",
+               "checksum_audio": float(np.abs(h_out["audio"][::97, -1, ::31]).sum())}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        v, kind, blocks, dt = cpu_run("port", params, sigs, T, args.cpu_seconds, cores)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": "%d stream-blocks of the same C2 mix on %d threads in %.1f s" % (blocks, cores, dt)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config_dict(args), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                "gpu_launches": int(gpu_launches), "clocks": clk}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()

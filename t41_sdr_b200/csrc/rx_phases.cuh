@@ -882,7 +882,16 @@ T41RX_DEV void PhAgcMaxLevel(Cta &c, int tid, int level) {
     const float *src = s + (level == 1 ? vAbs : ((level & 1) ? vLvlB : vLvlA));
     float *dst = s + ((level & 1) ? vLvlA : vLvlB);
     const int d = 1 << (level - 1);
-    for (int e = u; e < n; e += 64) dst[e] = (e >= d) ? fmaxf(src[e], src[e - d]) : src[e];
+    if (level == 1) {
+      /* the reference's `if (abs > ring_max)` never lets a NaN magnitude (NFM discriminator on
+         exact silence: 0/0) become the maximum: NaNs count as 0 here */
+      for (int e = u; e < n; e += 64) {
+        const float a = src[e], b = (e >= 1) ? src[e - 1] : 0.0f;
+        dst[e] = fmaxf((a == a) ? a : 0.0f, (b == b) ? b : 0.0f);
+      }
+    } else {
+      for (int e = u; e < n; e += 64) dst[e] = (e >= d) ? fmaxf(src[e], src[e - d]) : src[e];
+    }
   } else {
     /* level 6 result lives in vLvlB; window [i+1, i+97] = [e-96, e] with e = i + 97 */
     const float *m6 = s + vLvlB;

@@ -1,0 +1,140 @@
+"""Drive a parity Case through a batched engine: the product (t41_sdr_b200.rx.Receiver, CUDA)
+or the host emulation of the kernel phases (tests/devtools, CPU-only logic check)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+import cases
+import oracle_py as O
+from t41_sdr_b200 import rx
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMUL_PATH = os.path.join(HERE, "devtools", "_build", "libt41rx_emul.so")
+
+
+def to_rx_params(p):
+    q = rx.Params()
+    assert C.sizeof(q) == C.sizeof(p)
+    C.memmove(C.byref(q), C.byref(p), C.sizeof(q))
+    return q
+
+
+class EmulReceiver:
+    """Same surface as rx.Receiver, backed by the host build of the kernel phase functions."""
+
+    def __init__(self, n_streams):
+        if not os.path.exists(EMUL_PATH):
+            subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "devtools")])
+        L = C.CDLL(EMUL_PATH)
+        L.emul_create.restype = C.c_void_p
+        L.emul_create.argtypes = [C.c_int]
+        L.emul_destroy.argtypes = [C.c_void_p]
+        L.emul_set_params_each.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(rx.Params)]
+        L.emul_process.argtypes = [C.c_void_p] + [C.c_void_p] * 2 + [C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_uint32]
+        L.emul_get_debug.argtypes = [C.c_void_p, C.c_int, C.POINTER(rx.Debug)]
+        self.L = L
+        self.n_streams = n_streams
+        self.h = L.emul_create(n_streams)
+
+    def close(self):
+        if self.h:
+            self.L.emul_destroy(self.h)
+            self.h = None
+
+    def set_params_each(self, plist, first=0):
+        arr = (rx.Params * len(plist))(*plist)
+        assert self.L.emul_set_params_each(self.h, first, len(plist), arr) == 0
+
+    def process(self, iq, row_every=0, want_psk=False, flags=0):
+        iq = np.ascontiguousarray(iq, np.float32)
+        S, T = iq.shape[:2]
+        n_rows = 0 if row_every <= 0 else (T + row_every - 1) // row_every
+        out = dict(audio=np.empty((S, T, 2048), np.float32), spec=np.zeros((S, n_rows, 512), np.int16),
+                   wf=np.zeros((S, n_rows, 512), np.uint16),
+                   psk_bits=np.full((S, T), -1, np.int8) if want_psk else None,
+                   psk_chars=np.zeros((S, T), np.uint8) if want_psk else None)
+        p = lambda a: None if a is None or a.size == 0 else a.ctypes.data
+        self.L.emul_process(self.h, iq.ctypes.data, out["audio"].ctypes.data, T, row_every, p(out["spec"]),
+                            p(out["wf"]), p(out["psk_bits"]), p(out["psk_chars"]), flags)
+        return out
+
+    def debug(self, stream):
+        d = rx.Debug()
+        self.L.emul_get_debug(self.h, stream, C.byref(d))
+        return d
+
+
+def run_case_batched(case, engine, flags=0):
+    """Returns per-receiver dicts shaped like cases.run_case_on()."""
+    S = case.n_streams
+    iq_all = np.stack(case.iq)            # [S, T, 2048, 2]
+    parts = []
+    b0 = 0
+    for plist, n in case.segments:
+        engine.set_params_each([to_rx_params(p) for p in plist])
+        parts.append(engine.process(iq_all[:, b0:b0 + n], case.row_every, case.psk, flags))
+        b0 += n
+    out = []
+    for s in range(S):
+        r = dict(audio=np.concatenate([p["audio"][s] for p in parts]),
+                 spec=np.concatenate([p["spec"][s] for p in parts]),
+                 wf=np.concatenate([p["wf"][s] for p in parts]))
+        if case.psk:
+            r["psk_bits"] = np.concatenate([p["psk_bits"][s] for p in parts])
+            r["psk_chars"] = np.concatenate([p["psk_chars"][s] for p in parts])
+        r["debug"] = engine.debug(s)
+        out.append(r)
+    return out
+
+
+def assert_identical(case, got, want, check_osc=True):
+    """Bit-exact comparison of everything the boundary returns plus the debug state."""
+    for s, (g, w) in enumerate(zip(got, want)):
+        tag = "%s receiver %d" % (case.name, s)
+        # NaNs (NFM discriminator on exact silence divides 0 by 0, like the reference) compare
+        # equal to NaNs whatever their payload; everything else must match to the bit
+        neq = (g["audio"].view(np.uint32) != w["audio"].view(np.uint32)) & ~(np.isnan(g["audio"]) & np.isnan(w["audio"]))
+        if neq.any():
+            bad = np.argwhere(neq)
+            raise AssertionError("%s: audio differs in %d samples (first at %s), SNR %.1f dB" % (
+                tag, len(bad), bad[0], O.snr_db(w["audio"], g["audio"])))
+        assert np.array_equal(g["spec"], w["spec"]), tag + ": spectrum rows differ"
+        assert np.array_equal(g["wf"], w["wf"]), tag + ": waterfall rows differ"
+        if case.psk:
+            assert np.array_equal(g["psk_bits"], w["psk_bits"]), tag + ": PSK31 bits differ"
+            assert np.array_equal(g["psk_chars"], w["psk_chars"]), tag + ": PSK31 characters differ"
+        for f in cases.DEBUG_INT_FIELDS:
+            assert getattr(g["debug"], f) == getattr(w["debug"], f), "%s: %s" % (tag, f)
+        for f in cases.DEBUG_FLOAT_FIELDS:
+            a, b = getattr(g["debug"], f), getattr(w["debug"], f)
+            assert np.float32(a).view(np.uint32) == np.float32(b).view(np.uint32), "%s: %s %r %r" % (tag, f, a, b)
+        assert g["debug"].dc_state[0] == w["debug"].dc_state[0], tag + ": DC-block state"
+        if check_osc:
+            assert g["debug"].osc_vect_q == w["debug"].osc_vect_q and g["debug"].osc_vect_i == w["debug"].osc_vect_i, \
+                tag + ": oscillator state"
+
+
+def assert_within_tolerance(case, got, want, min_snr_db=90.0):
+    """The north star's stated tolerance for the default (closed-form NCO) path: audio SNR >=
+    90 dB against the oracle per receiver, spectrum rows >= 99.9 % identical and never off by
+    more than 1 LSB, PSK31 bits / characters and every discrete state identical."""
+    stats = []
+    for s, (g, w) in enumerate(zip(got, want)):
+        tag = "%s receiver %d" % (case.name, s)
+        snr = O.snr_db(w["audio"], g["audio"])
+        frac_same = float(np.mean(g["audio"].view(np.uint32) == w["audio"].view(np.uint32)))
+        assert snr >= min_snr_db, "%s: audio SNR %.1f dB < %.0f dB" % (tag, snr, min_snr_db)
+        if w["spec"].size:
+            diff = np.abs(g["spec"].astype(np.int32) - w["spec"].astype(np.int32))
+            assert diff.max() <= 1, tag + ": spectrum row off by more than 1 LSB"
+            assert np.mean(diff == 0) >= 0.999, tag + ": spectrum rows < 99.9 %% identical"
+            assert np.mean(g["wf"] == w["wf"]) >= 0.999, tag + ": waterfall rows < 99.9 %% identical"
+        if case.psk:
+            assert np.array_equal(g["psk_bits"], w["psk_bits"]), tag + ": PSK31 bits differ"
+            assert np.array_equal(g["psk_chars"], w["psk_chars"]), tag + ": PSK31 characters differ"
+        for f in cases.DEBUG_INT_FIELDS:
+            assert getattr(g["debug"], f) == getattr(w["debug"], f), "%s: %s" % (tag, f)
+        stats.append((snr, frac_same))
+    return stats

@@ -1,0 +1,203 @@
+"""GPU tier: the CUDA path, called through the C-ABI (libt41rx.so), against the CPU oracle.
+
+ * exact-oscillator mode (T41RX_FLAG_EXACT_NCO): every output and every piece of debug state
+   is BIT-IDENTICAL to the oracle on all cases (C1-C5 scaled down + edge cases), and the
+   audio digests equal the golden vectors the reference itself produced;
+ * default mode (closed-form FP64 oscillator): audio SNR >= 90 dB (in practice > 120 dB, with
+   > 99.9 % of samples bit-identical), spectrum rows within 1 LSB and >= 99.9 % identical,
+   PSK31 bits / characters and AGC / mode state transitions identical (tolerance stated by the
+   north star; checked in rx_driver.assert_within_tolerance);
+ * at BASELINE.json's full sizes: size-independent properties (call-chunking invariance,
+   receiver permutation invariance, replicated receivers agree) plus oracle spot checks.
+"""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import cases
+import oracle_py as O
+import rx_driver
+from t41_sdr_b200 import rx, synth
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_vectors.npz")
+
+
+def _receiver(n):
+    # fails loudly (T41RxError) if the CUDA library or the device is unusable
+    return rx.Receiver(n)
+
+
+@pytest.mark.parametrize("make", cases.ALL_CASES, ids=lambda m: m.__name__)
+def test_exact_mode_is_bit_identical_to_oracle(make):
+    case = make()
+    want = cases.run_case_on(case, lambda p: O.OracleStream(p))
+    with _receiver(case.n_streams) as eng:
+        got = rx_driver.run_case_batched(case, eng, flags=rx.FLAG_EXACT_NCO)
+        assert eng.kernel_launches() == len(case.segments)
+    rx_driver.assert_identical(case, got, want)
+
+
+@pytest.mark.parametrize("make", cases.ALL_CASES, ids=lambda m: m.__name__)
+def test_exact_mode_matches_reference_golden(make):
+    golden = np.load(GOLDEN)
+    case = make()
+    with _receiver(case.n_streams) as eng:
+        got = rx_driver.run_case_batched(case, eng, flags=rx.FLAG_EXACT_NCO)
+    for s, r in enumerate(got):
+        key = "%s/%d/" % (case.name, s)
+        audio = r["audio"].copy()
+        if np.isnan(audio).any():
+            continue  # NaN payloads are implementation defined; covered by the oracle comparison
+        assert hashlib.sha256(audio.tobytes()).hexdigest() == bytes(golden[key + "audio_sha256"]).hex(), key
+        assert np.array_equal(r["spec"], golden[key + "spec"]), key
+        assert np.array_equal(r["wf"], golden[key + "wf"]), key
+        if case.psk:
+            assert np.array_equal(r["psk_bits"], golden[key + "psk_bits"]), key
+            assert np.array_equal(r["psk_chars"], golden[key + "psk_chars"]), key
+
+
+@pytest.mark.parametrize("make", cases.ALL_CASES, ids=lambda m: m.__name__)
+def test_default_mode_within_stated_tolerance(make):
+    case = make()
+    want = cases.run_case_on(case, lambda p: O.OracleStream(p))
+    with _receiver(case.n_streams) as eng:
+        got = rx_driver.run_case_batched(case, eng, flags=0)
+    if case.name == "edge_silence_fullscale":
+        # NaN audio (0/0 in the NFM discriminator on silence) has no SNR: compare the rest
+        keep = [i for i, w in enumerate(want) if not np.isnan(w["audio"]).any()]
+        got, want = [got[i] for i in keep], [want[i] for i in keep]
+    stats = rx_driver.assert_within_tolerance(case, got, want, min_snr_db=90.0)
+    assert min(snr for snr, _ in stats) >= 120.0
+    assert min(frac for _, frac in stats) >= 0.999
+
+
+def test_psk31_text_is_decoded():
+    case = cases.c5_psk31()
+    with _receiver(case.n_streams) as eng:
+        got = rx_driver.run_case_batched(case, eng, flags=0)
+    for r in got:
+        chars = bytes(r["psk_chars"][r["psk_chars"] > 0])
+        assert cases.PSK_TEXT.encode() in chars
+
+
+def test_error_codes():
+    with _receiver(3) as eng:
+        with pytest.raises(rx.T41RxError):
+            eng.set_params(rx_driver.to_rx_params(cases.P(mode=4)))
+        with pytest.raises(rx.T41RxError):
+            eng.set_params(rx.default_params(), first=2, count=5)
+        with pytest.raises(ValueError):
+            eng.process(np.zeros((2, 1, 2048, 2), np.float32))
+
+
+# ---------------- BASELINE sizes: properties + spot checks ----------------
+def _c2_bank(n_streams, n_blocks, n_distinct=16):
+    """C2-shaped bank: even receivers USB, odd AM, per-receiver NCO; the I/Q of receiver s is
+    distinct signal (s % n_distinct), so a large bank needs little host memory to build."""
+    r = np.random.Generator(np.random.PCG64(2024))
+    base_p, base_iq = [], []
+    for k in range(n_distinct):
+        nco = int(r.integers(-20000, 20001))
+        if k % 2 == 0:
+            base_p.append(cases.P(mode=cases.USB, f_lo_cut=300, f_hi_cut=3000, nco_freq=nco))
+            base_iq.append(synth.tone(900 + k, n_blocks, float(r.uniform(300, 2700)), mode=cases.USB, nco_freq=nco))
+        else:
+            base_p.append(cases.P(mode=cases.AM, nco_freq=nco))
+            base_iq.append(synth.am(900 + k, n_blocks, mode=cases.AM, nco_freq=nco))
+    params = [rx_driver.to_rx_params(base_p[s % n_distinct]) for s in range(n_streams)]
+    iq = np.stack([base_iq[s % n_distinct] for s in range(n_streams)])
+    return base_p, base_iq, params, iq
+
+
+def test_c2_full_size_1024_receivers():
+    S, T, D = 1024, 16, 16
+    base_p, base_iq, params, iq = _c2_bank(S, T, D)
+    with _receiver(S) as eng:
+        eng.set_params_each(params)
+        one = eng.process(iq, row_every=T)
+    audio = one["audio"]
+    # replicated receivers (same params, same input) agree exactly wherever they sit in the grid
+    for k in range(D):
+        grp = audio[k::D]
+        assert np.array_equal(grp.view(np.uint32), np.broadcast_to(grp[0], grp.shape).view(np.uint32))
+        assert np.array_equal(one["spec"][k::D], np.broadcast_to(one["spec"][k], one["spec"][k::D].shape))
+    # spot check against the oracle (default mode tolerance)
+    for k in range(D):
+        w = O.OracleStream(base_p[k]).process(base_iq[k], T)
+        assert O.snr_db(w["audio"], audio[k]) >= 120.0
+        assert np.abs(w["spec"].astype(int) - one["spec"][k].astype(int)).max() <= 1
+    # call-chunking invariance: 16 blocks at once == 5 + 11 blocks (state hand-over through HBM)
+    with _receiver(S) as eng:
+        eng.set_params_each(params)
+        a = eng.process(iq[:, :5])["audio"]
+        b = eng.process(iq[:, 5:])["audio"]
+    assert np.array_equal(np.concatenate([a, b], axis=1).view(np.uint32), audio.view(np.uint32))
+    # receiver permutation invariance: no cross-talk between receivers
+    perm = np.random.Generator(np.random.PCG64(7)).permutation(S)
+    with _receiver(S) as eng:
+        eng.set_params_each([params[i] for i in perm])
+        p = eng.process(iq[perm])["audio"]
+    assert np.array_equal(p.view(np.uint32), audio[perm].view(np.uint32))
+
+
+def test_c4_full_size_16384_spectrum_rows():
+    S, T, D = 16384, 2, 10
+    base_p = [cases.P(spectrum_zoom=k % 5, current_scale=1 + (k // 5)) for k in range(D)]
+    base_iq = [synth.two_tone(400 + k, T, f1=46500.0 - 300 * k, f2=50500.0) for k in range(D)]
+    params = [rx_driver.to_rx_params(base_p[s % D]) for s in range(S)]
+    iq = np.stack([base_iq[s % D] for s in range(S)])
+    with _receiver(S) as eng:
+        eng.set_params_each(params)
+        out = eng.process(iq, row_every=1, flags=rx.FLAG_EXACT_NCO)
+    for k in range(D):
+        w = O.OracleStream(base_p[k]).process(base_iq[k], 1)
+        assert np.array_equal(out["spec"][k::D], np.broadcast_to(w["spec"], out["spec"][k::D].shape))
+        assert np.array_equal(out["wf"][k::D], np.broadcast_to(w["wf"], out["wf"][k::D].shape))
+
+
+def test_c3_full_size_8192_nfm_sam_state_transitions():
+    S, T, D = 8192, 24, 8
+    case = cases.c3_nfm_sam_agc(n=D, T=T)
+    base_p, base_iq = case.segments[0][0], case.iq
+    params = [rx_driver.to_rx_params(base_p[s % D]) for s in range(S)]
+    iq = np.stack([base_iq[s % D] for s in range(S)])
+    with _receiver(S) as eng:
+        eng.set_params_each(params)
+        out = eng.process(iq, flags=0)
+        dbg = [eng.debug(s) for s in (0, 1, 2, 3, 4, 5, 6, 7, S - 8, S - 7, S - 2, S - 1)]
+    want = cases.run_case_on(cases.Case(case.name, case.segments, case.iq), lambda p: O.OracleStream(p))
+    for k in range(D):
+        assert O.snr_db(want[k]["audio"], out["audio"][k]) >= 120.0
+        grp = out["audio"][k::D]
+        assert np.array_equal(grp.view(np.uint32), np.broadcast_to(grp[0], grp.shape).view(np.uint32))
+    for d, s in zip(dbg, (0, 1, 2, 3, 4, 5, 6, 7, S - 8, S - 7, S - 2, S - 1)):
+        w = want[s % D]["debug"]
+        for f in cases.DEBUG_INT_FIELDS:
+            assert getattr(d, f) == getattr(w, f), (s, f)
+
+
+def test_c5_full_size_32768_psk31_bits():
+    """32768 receivers x the full message would need ~1 TB of I/Q; the bank is
+    fed with 4 distinct waveforms and processed in time slices of 6 blocks, bits compared with the
+    oracle's for every distinct waveform and required to agree across all replicas."""
+    S, D, SLICE = 32768, 4, 6
+    case = cases.c5_psk31(n=D)
+    base_p, base_iq = case.segments[0][0], case.iq
+    T = base_iq[0].shape[0]
+    T = min(T, 20 * SLICE)
+    params = [rx_driver.to_rx_params(base_p[s % D]) for s in range(S)]
+    want = [O.OracleStream(base_p[k]).process(base_iq[k][:T], 0, True) for k in range(D)]
+    bits = []
+    with _receiver(S) as eng:
+        eng.set_params_each(params)
+        for b0 in range(0, T, SLICE):
+            iq = np.stack([base_iq[s % D][b0:b0 + SLICE] for s in range(D)])
+            iq = np.ascontiguousarray(np.tile(iq, (S // D, 1, 1, 1)))
+            bits.append(eng.process(iq, want_psk=True)["psk_bits"])
+    bits = np.concatenate(bits, axis=1)
+    for k in range(D):
+        assert np.array_equal(bits[k::D], np.broadcast_to(want[k]["psk_bits"], bits[k::D].shape))
