@@ -25,7 +25,11 @@ namespace t41rx {
 /* ------------------------------------------------------------------ */
 /* the kernel                                                          */
 /* ------------------------------------------------------------------ */
-__global__ void __launch_bounds__(kNT, 2) t41rx_fused_rx_kernel(const LaunchArgs a) {
+#ifdef T41RX_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[128];
+#endif
+
+__global__ void __launch_bounds__(kNT, 8 / kG) t41rx_fused_rx_kernel(const LaunchArgs a) {
   extern __shared__ __align__(16) float smem[];
   Cta c;
   c.a = a;
@@ -42,11 +46,29 @@ __global__ void __launch_bounds__(kNT, 2) t41rx_fused_rx_kernel(const LaunchArgs
     c.t = t;
     c.row = (a.row_every > 0) && (t % a.row_every == 0);
     c.row_idx = c.row ? t / a.row_every : 0;
+#ifdef T41RX_PHASE_TIMING
+    /* developer build only: cycles per phase of CTA 0 (work and the wait at the barrier) */
+    int phase_no = 0;
+#define T41RX_KPHASE(stmt)                                                                   \
+  do {                                                                                       \
+    const long long t0_ = clock64();                                                         \
+    stmt;                                                                                    \
+    const long long t1_ = clock64();                                                         \
+    __syncthreads();                                                                         \
+    const long long t2_ = clock64();                                                         \
+    if (blockIdx.x == 0 && tid == 0) {                                                       \
+      g_phase_cycles[2 * phase_no] += (unsigned long long)(t2_ - t0_);                       \
+      g_phase_cycles[2 * phase_no + 1] += (unsigned long long)(t1_ - t0_);                   \
+    }                                                                                        \
+    ++phase_no;                                                                              \
+  } while (0)
+#else
 #define T41RX_KPHASE(stmt) \
   do {                     \
     stmt;                  \
     __syncthreads();       \
   } while (0)
+#endif
     T41RX_BLOCK_SCHEDULE(T41RX_KPHASE)
 #undef T41RX_KPHASE
   }
@@ -440,6 +462,17 @@ int t41rx_process(t41rx_ctx *ctx, const float *iq, float *audio, int n_blocks, i
   CUDA_TRY(cudaStreamSynchronize(st));
   return T41RX_OK;
 }
+
+#ifdef T41RX_PHASE_TIMING
+int t41rx_debug_phase_cycles(unsigned long long *out128, int reset) {
+  if (cudaMemcpyFromSymbol(out128, g_phase_cycles, sizeof(unsigned long long) * 128) != cudaSuccess) return -1;
+  if (reset) {
+    unsigned long long z[128] = {0};
+    cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
 
 int64_t t41rx_kernel_launches(const t41rx_ctx *ctx) { return ctx ? ctx->launches : 0; }
 

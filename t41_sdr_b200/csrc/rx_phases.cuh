@@ -33,13 +33,26 @@ template <class T> inline T LdgRO(const T *p) { return *p; }
 template <class T> __device__ __forceinline__ T LdgRO(const T *p) { return __ldg(p); }
 #endif
 
+/* hint: pull one 128-byte line towards L2 (next block's I/Q while this block is computed) */
+T41RX_DEV void PrefetchL2(const void *p) {
+#ifndef T41RX_HOST_EMUL
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+
 namespace t41rx {
 
-constexpr int kG = 4;                 /* receivers per CTA */
+#ifndef T41RX_G
+#define T41RX_G 4
+#endif
+constexpr int kG = T41RX_G;           /* receivers per CTA */
 constexpr int kNT = 64 * kG;          /* threads per CTA: 64 per receiver in the FFT phases */
-constexpr int kDcChunks = 8;          /* time-parallel chunks of the 4096-step DC-block chain */
-constexpr int kDcChunkLen = 513;      /* chunk c starts at c*513 (odd: bank-conflict-free lanes) */
+constexpr int kDcChunks = 32;         /* time-parallel chunks of the 4096-step DC-block chain: one warp per receiver */
+constexpr int kDcChunkLen = 129;      /* chunk c starts at c*129 (odd stride: the 32 lanes hit 32 different banks) */
 constexpr int kDcWarm = 256;          /* speculative warm-up length (a1 = 0.854: 0.854^256 ~ 3e-18) */
+static_assert(kDcChunks * kDcChunkLen >= 2 * kBlock && (kDcChunks - 1) * kDcChunkLen < 2 * kBlock, "chunking");
 
 /* ---- shared-memory slot layout, in floats ---- */
 constexpr int kRawLen = 2076;                     /* 27 history + 2048 new (+1 pad) */
@@ -57,7 +70,7 @@ constexpr int oD1H = oNco + 512;                  /* 6836 : dec1 history 2 x 27 
 constexpr int oD2H = oD1H + 56;                   /* 6892 : dec2 history 2 x 45 (-> 92) */
 constexpr int oIntH = oD2H + 92;                  /* 6984 : int1 23 (-> 24) | int2 7 (-> 8) */
 constexpr int oMisc = oIntH + 32;                 /* 7016 : scalars */
-constexpr int kSlotRaw = oMisc + 64;              /* 7080 */
+constexpr int kSlotRaw = oMisc + 160;
 constexpr int kSlot = ((kSlotRaw - 8 + 31) / 32) * 32 + 8;   /* == 8 (mod 32): distinct banks per slot */
 static_assert(kSlot % 32 == 8 && kSlot >= kSlotRaw, "slot stride");
 static_assert((oNco % 4) == 0, "double2 alignment");
@@ -82,7 +95,7 @@ constexpr int vInt2 = 1312;                       /* int2 state: 7 history + 512
 constexpr int vSpecFft = oD1I;                    /* 512 complex = 1024 floats <= 1120 */
 
 /* misc scalar indices */
-enum { mDcD1 = 0, mDcD2 = 1, mDcSpec = 2 /* 8 x 2 */, mDcEnd = 18 /* 8 x 2 */, mNcoMode = 34, mRowFlag = 35 };
+enum { mDcD1 = 0, mDcD2 = 1, mNcoMode = 2, mDcBad = 3, mDcSpec = 4 /* 32 x 2 */, mDcEnd = 68 /* 32 x 2 */ };
 
 struct LaunchArgs {
   const float *iq;
@@ -117,6 +130,20 @@ struct Cta {
 };
 
 T41RX_DEV float *Slot(const Cta &c, int g) { return c.smem + g * kSlot; }
+
+/* which receiver (or -1) thread `tid` serves in a one-lane-per-receiver serial phase:
+ * T41RX_SERIAL_WPS = 1: lane 0 of the receiver's own first warp (no divergence between receivers
+ * in different states, more issue slots); 0: lanes 0..G-1 of warp 0 (fewest issue slots). */
+#ifndef T41RX_SERIAL_WPS
+#define T41RX_SERIAL_WPS 1
+#endif
+T41RX_DEV int SerialStream(const Cta &c, int tid) {
+#if T41RX_SERIAL_WPS
+  return ((tid & 63) == 0 && (tid >> 6) < c.ng) ? (tid >> 6) : -1;
+#else
+  return (tid < c.ng) ? tid : -1;
+#endif
+}
 
 /* ------------------------------------------------------------------ */
 /* scalar helpers (Utility.cpp / Demod.cpp restated for the device)    */
@@ -187,41 +214,48 @@ T41RX_DEV float TableTurns(const float *tab, float in) {
   return wa + wb;
 }
 
-/* Process.cpp:165-174 + Utility.cpp:178-187 on one sample of the conditioned buffers */
-T41RX_DEV void IqCorr(const StreamCfg &cf, float &i, float &q) {
-  if (cf.mirrored) {
-    if (cf.iq_phase < 0.0f) q = q + i * cf.iq_phase;
-    else i = i + q * cf.iq_phase;
+/* Process.cpp:165-174 + Utility.cpp:178-187 on one sample of the conditioned buffers.  The two
+ * per-receiver values are fetched once (registers) so loops over samples do not re-read them. */
+struct IqFix { bool mirrored; float phase; };
+T41RX_DEV IqFix IqFixOf(const StreamCfg &cf) { return IqFix{cf.mirrored != 0, cf.iq_phase}; }
+T41RX_DEV void IqCorr(const IqFix f, float &i, float &q) {
+  if (f.mirrored) {
+    if (f.phase < 0.0f) q = q + i * f.phase;
+    else i = i + q * f.phase;
   }
 }
 
-/* FreqShift1 (Freq_Shift.cpp:42-65): multiply sample n by exp(+j*pi*n/2) */
+/* FreqShift1 (Freq_Shift.cpp:42-65): multiply sample n by exp(+j*pi*n/2); branch-free
+ * (n & 3 differs from lane to lane): 1: (-q, i)  2: (-i, -q)  3: (q, -i) */
 T41RX_DEV void QuarterShift(int n, float &i, float &q) {
-  const float a = i, b = q;
-  switch (n & 3) {
-    case 1: i = -b; q = a; break;
-    case 2: i = -a; q = -b; break;
-    case 3: i = b; q = -a; break;
-    default: break;
-  }
+  const int k = n & 3;
+  const float a = (k & 1) ? q : i;
+  const float b = (k & 1) ? i : q;
+  i = ((k + 1) & 2) ? -a : a;
+  q = (k & 2) ? -b : b;
 }
 
-/* one step of the DC-block biquad (arm_biquad_cascade_df2T_f32, 1 stage; FIR.cpp:87-89) */
-struct DcCoef { float b0, b1, b2, a1, a2; };
-T41RX_DEV float DcStep(const DcCoef &k, float x, float &d1, float &d2) {
+/* The DC-block biquad (arm_biquad_cascade_df2T_f32, 1 stage; coefficients FIR.cpp:87-89):
+ *     y  = (b0*x) + d1;   d1 = ((b1*x) + (a1*y)) + d2;   d2 = (b2*x) + (a2*y)
+ * with b2 = a2 = 0, so d2 is always +-0.  Adding +-0 changes nothing unless the other operand is
+ * -0, and t = (b1*x) + (a1*y) can only be -0 if b1*x = -0 (x = +0, because b1 < 0) AND
+ * a1*y = -0 (y = -0); but x = +0 gives y = (+0) + d1 which is never -0.  Hence d1 = t exactly
+ * for every finite input and d2 is only materialised (from the last x and y) when a state is
+ * stored.  Loop-carried chain per sample: FADD -> FMUL -> FADD. */
+struct DcCoef { float b0, b1, a1; };
+T41RX_DEV DcCoef DcCoefs() {
+  return DcCoef{(float)0.927176191943378969, (float)-0.927176191943378969, (float)0.854352383886757938};
+}
+T41RX_DEV float DcStep(const DcCoef &k, float x, float &d1) {
   const float y = k.b0 * x + d1;
-  const float t = k.b1 * x + k.a1 * y;
-  d1 = t + d2;
-  d2 = k.b2 * x + k.a2 * y;
+  d1 = k.b1 * x + k.a1 * y;
   return y;
 }
-T41RX_DEV DcCoef DcCoefs() {
-  return DcCoef{(float)0.927176191943378969, (float)-0.927176191943378969, (float)0.0,
-                (float)0.854352383886757938, (float)0.0};
-}
+/* d2 = (0*x) + (0*y) of the last processed sample */
+T41RX_DEV float DcD2(float x, float y) { return 0.0f * x + 0.0f * y; }
 
 /* raw sequence index (I block then Q block, B6) -> float offset inside the slot */
-T41RX_DEV int SeqOff(int i) { return i < kBlock ? (oRawI + 27 + i) : (oRawQ + 27 + (i - kBlock)); }
+T41RX_DEV int SeqOff(int i) { return oRawI + 27 + i + ((i >= kBlock) ? (oRawQ - oRawI - kBlock) : 0); }
 
 /* ------------------------------------------------------------------ */
 /* launch prologue / epilogue: state <-> shared memory                 */
@@ -285,22 +319,42 @@ T41RX_DEV void PhStateOut(Cta &c, int tid) {
 /* P0: HBM -> shared, de-interleave; restore dec1 history              */
 /* ------------------------------------------------------------------ */
 T41RX_DEV void PhLoad(Cta &c, int tid) {
+  constexpr int kPer = (kBlock / 2) / kNT;       /* float4 loads per thread per receiver */
+  static_assert(kPer * kNT == kBlock / 2, "load tiling");
+  for (int g0 = 0; g0 < c.ng; g0 += 2) {         /* two receivers' loads in flight at once */
+    float4 v[2][kPer];
+#pragma unroll
+    for (int gg = 0; gg < 2; ++gg) {
+      if (g0 + gg >= c.ng) continue;
+      const float4 *src = reinterpret_cast<const float4 *>(
+          c.a.iq + ((size_t)(c.s0 + g0 + gg) * c.a.n_blocks + c.t) * (2 * kBlock));
+#pragma unroll
+      for (int k = 0; k < kPer; ++k) v[gg][k] = LdgRO(src + tid + kNT * k);
+    }
+#pragma unroll
+    for (int gg = 0; gg < 2; ++gg) {
+      if (g0 + gg >= c.ng) continue;
+      float *s = Slot(c, g0 + gg);
+#pragma unroll
+      for (int k = 0; k < kPer; ++k) {
+        const int j = tid + kNT * k;             /* float4 index: samples 2j, 2j+1 */
+        s[oRawI + 27 + 2 * j] = v[gg][k].x;
+        s[oRawQ + 27 + 2 * j] = v[gg][k].y;
+        s[oRawI + 27 + 2 * j + 1] = v[gg][k].z;
+        s[oRawQ + 27 + 2 * j + 1] = v[gg][k].w;
+      }
+    }
+  }
   for (int g = 0; g < c.ng; ++g) {
     float *s = Slot(c, g);
-    const float4 *src = reinterpret_cast<const float4 *>(
-        c.a.iq + ((size_t)(c.s0 + g) * c.a.n_blocks + c.t) * (2 * kBlock));
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int j = tid + kNT * k;            /* float4 index: samples 2j, 2j+1 */
-      const float4 v = LdgRO(src + j);
-      s[oRawI + 27 + 2 * j] = v.x;
-      s[oRawQ + 27 + 2 * j] = v.y;
-      s[oRawI + 27 + 2 * j + 1] = v.z;
-      s[oRawQ + 27 + 2 * j + 1] = v.w;
+    for (int h = tid; h < 54; h += kNT) {
+      const int ch = h / 27, i = h % 27;
+      s[(ch ? oRawQ : oRawI) + i] = s[oD1H + h];
     }
-    if (tid < 54) {
-      const int ch = tid / 27, i = tid % 27;
-      s[(ch ? oRawQ : oRawI) + i] = s[oD1H + tid];
+    if (c.t + 1 < c.a.n_blocks) {
+      const char *nxt = reinterpret_cast<const char *>(
+          c.a.iq + ((size_t)(c.s0 + g) * c.a.n_blocks + c.t + 1) * (2 * kBlock));
+      for (int line = tid; line < (2 * kBlock * 4) / 128; line += kNT) PrefetchL2(nxt + 128 * line);
     }
   }
 }
@@ -316,42 +370,97 @@ T41RX_DEV void PhLoad(Cta &c, int tid) {
  * chunk's end state bit for bit and recomputes serially from the first mismatch, so the
  * result is always exactly the serial recurrence's.                                       */
 /* ------------------------------------------------------------------ */
+/* Run steps [begin, end) of the conditioning chain from state (d1, d2).  kStore: write the
+ * conditioned samples in place (x RFgain, then for I in mirrored modes x -IQAmp as a second,
+ * separately rounded multiplication: Process.cpp:133,166).  Loads are issued in batches of 4
+ * so that the shared-memory latency is off the recurrence's critical path. */
+struct DcPost { float rfg; float rfgain; float neg_iq_amp; bool mirrored; };
+
+template <bool kStore>
+T41RX_DEV void DcRun(float *s, const DcPost p, int begin, int end, float &d1_io, float &d2_io) {
+  constexpr int kB = 8;
+  const DcCoef k = DcCoefs();
+  float d1 = d1_io;
+  float lx = 0.0f, ly = 0.0f;          /* last (scaled) input and output: define d2 */
+  bool any = false;
+  int i = begin;
+  const int n_batches = (end - begin) / kB;
+  float cur[kB], nxt[kB];
+  if (n_batches > 0) {
+#pragma unroll
+    for (int j = 0; j < kB; ++j) cur[j] = s[SeqOff(i + j)];
+  }
+  for (int bt = 0; bt < n_batches; ++bt) {
+    /* software pipeline: the next batch is in flight while this one runs from registers */
+    if (bt + 1 < n_batches) {
+#pragma unroll
+      for (int j = 0; j < kB; ++j) nxt[j] = s[SeqOff(i + kB + j)];
+    }
+#pragma unroll
+    for (int j = 0; j < kB; ++j) {
+      const float x = cur[j] * p.rfg;
+      float y = DcStep(k, x, d1);
+      lx = x;
+      ly = y;
+      if (kStore) {
+        y = y * p.rfgain;
+        if (p.mirrored && (i + j) < kBlock) y = y * p.neg_iq_amp;
+        s[SeqOff(i + j)] = y;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kB; ++j) cur[j] = nxt[j];
+    i += kB;
+    any = true;
+  }
+  for (; i < end; ++i) {
+    const int off = SeqOff(i);
+    const float x = s[off] * p.rfg;
+    float y = DcStep(k, x, d1);
+    lx = x;
+    ly = y;
+    any = true;
+    if (kStore) {
+      y = y * p.rfgain;
+      if (p.mirrored && i < kBlock) y = y * p.neg_iq_amp;
+      s[off] = y;
+    }
+  }
+  d1_io = d1;
+  if (any) d2_io = DcD2(lx, ly);
+}
+
+T41RX_DEV DcPost DcPostOf(const Cta &c, int g) {
+  const StreamCfg &cf = c.a.cfg[c.s0 + g];
+  return DcPost{cf.rf_gain_value, (float)c.a.st[c.s0 + g].rf_gain, cf.neg_iq_amp, cf.mirrored != 0};
+}
+
 T41RX_DEV void PhDcWarm(Cta &c, int tid) {
   if (tid >= c.ng * kDcChunks) return;
   const int g = tid / kDcChunks, ch = tid % kDcChunks;
-  if (ch == 0) return;
   float *s = Slot(c, g);
-  const StreamCfg &cf = c.a.cfg[c.s0 + g];
-  const DcCoef k = DcCoefs();
-  const float rfg = cf.rf_gain_value;
-  float d1 = 0.0f, d2 = 0.0f;
-  const int start = ch * kDcChunkLen - kDcWarm;
-  for (int i = start; i < start + kDcWarm; ++i) {
-    const float x = s[SeqOff(i)] * rfg;
-    (void)DcStep(k, x, d1, d2);
+  if (ch == 0) {
+    s[oMisc + mDcBad] = 0.0f;
+    return;
   }
+  const DcPost p = DcPostOf(c, g);
+  int start = ch * kDcChunkLen - kDcWarm;
+  float d1 = 0.0f, d2 = 0.0f;
+  if (start <= 0) {            /* the warm-up would reach before the block: start from the carried state instead */
+    start = 0;
+    d1 = s[oMisc + mDcD1];
+    d2 = s[oMisc + mDcD2];
+  }
+  DcRun<false>(s, p, start, ch * kDcChunkLen, d1, d2);
   s[oMisc + mDcSpec + 2 * ch] = d1;
   s[oMisc + mDcSpec + 2 * ch + 1] = d2;
-}
-
-T41RX_DEV void DcRunChunk(float *s, const StreamCfg &cf, float rfgain_f, int begin, int end, float &d1, float &d2) {
-  const DcCoef k = DcCoefs();
-  const float rfg = cf.rf_gain_value;
-  for (int i = begin; i < end; ++i) {
-    const int off = SeqOff(i);
-    const float x = s[off] * rfg;
-    float y = DcStep(k, x, d1, d2) * rfgain_f;
-    if (cf.mirrored && i < kBlock) y = y * cf.neg_iq_amp;
-    s[off] = y;
-  }
 }
 
 T41RX_DEV void PhDcMain(Cta &c, int tid) {
   if (tid >= c.ng * kDcChunks) return;
   const int g = tid / kDcChunks, ch = tid % kDcChunks;
   float *s = Slot(c, g);
-  const StreamCfg &cf = c.a.cfg[c.s0 + g];
-  const float rfgain_f = (float)c.a.st[c.s0 + g].rf_gain;
+  const DcPost p = DcPostOf(c, g);
   float d1, d2;
   if (ch == 0) {
     d1 = s[oMisc + mDcD1];
@@ -362,7 +471,7 @@ T41RX_DEV void PhDcMain(Cta &c, int tid) {
   }
   const int begin = ch * kDcChunkLen;
   const int end = (ch == kDcChunks - 1) ? 2 * kBlock : begin + kDcChunkLen;
-  DcRunChunk(s, cf, rfgain_f, begin, end, d1, d2);
+  DcRun<true>(s, p, begin, end, d1, d2);
   s[oMisc + mDcEnd + 2 * ch] = d1;
   s[oMisc + mDcEnd + 2 * ch + 1] = d2;
 }
@@ -374,34 +483,46 @@ T41RX_DEV bool SameBits(float a, float b) {
   return x.u == y.u;
 }
 
+/* every chunk checks, bit for bit, that the state it started from is the state the previous
+ * chunk ended in; the last chunk's end state becomes the receiver's carried state */
 T41RX_DEV void PhDcVerify(Cta &c, int tid) {
-  if (tid >= c.ng) return;
-  const int g = tid;
+  if (tid >= c.ng * kDcChunks) return;
+  const int g = tid / kDcChunks, ch = tid % kDcChunks;
   float *s = Slot(c, g);
-  const StreamCfg &cf = c.a.cfg[c.s0 + g];
-  const float rfgain_f = (float)c.a.st[c.s0 + g].rf_gain;
-  int bad = -1;
-  for (int ch = 1; ch < kDcChunks; ++ch) {
+  if (ch > 0) {
     if (!SameBits(s[oMisc + mDcSpec + 2 * ch], s[oMisc + mDcEnd + 2 * (ch - 1)]) ||
-        !SameBits(s[oMisc + mDcSpec + 2 * ch + 1], s[oMisc + mDcEnd + 2 * (ch - 1) + 1])) {
-      bad = ch;
+        !SameBits(s[oMisc + mDcSpec + 2 * ch + 1], s[oMisc + mDcEnd + 2 * (ch - 1) + 1]))
+      s[oMisc + mDcBad] = 1.0f;           /* several lanes may store the same value: benign */
+  }
+  if (ch == kDcChunks - 1) {
+    s[oMisc + mDcD1] = s[oMisc + mDcEnd + 2 * ch];
+    s[oMisc + mDcD2] = s[oMisc + mDcEnd + 2 * ch + 1];
+  }
+}
+
+/* speculation missed (vanishingly rare): redo serially from the first bad chunk, re-reading the
+ * raw samples from HBM/L2 because the chunks were filtered in place */
+T41RX_DEV void PhDcFix(Cta &c, int tid) {
+  const int g = SerialStream(c, tid);
+  if (g < 0) return;
+  float *s = Slot(c, g);
+  if (s[oMisc + mDcBad] == 0.0f) return;
+  const DcPost p = DcPostOf(c, g);
+  int bad = 1;
+  for (; bad < kDcChunks; ++bad) {
+    if (!SameBits(s[oMisc + mDcSpec + 2 * bad], s[oMisc + mDcEnd + 2 * (bad - 1)]) ||
+        !SameBits(s[oMisc + mDcSpec + 2 * bad + 1], s[oMisc + mDcEnd + 2 * (bad - 1) + 1]))
       break;
-    }
   }
-  if (bad >= 0) {
-    /* speculation missed (vanishingly rare): redo serially from the first bad chunk,
-       re-reading the raw samples from HBM/L2 because the chunk was filtered in place */
-    const float *src = c.a.iq + ((size_t)(c.s0 + g) * c.a.n_blocks + c.t) * (2 * kBlock);
-    float d1 = s[oMisc + mDcEnd + 2 * (bad - 1)];
-    float d2 = s[oMisc + mDcEnd + 2 * (bad - 1) + 1];
-    for (int i = bad * kDcChunkLen; i < 2 * kBlock; ++i)
-      s[SeqOff(i)] = LdgRO(src + (i < kBlock ? 2 * i : 2 * (i - kBlock) + 1));
-    DcRunChunk(s, cf, rfgain_f, bad * kDcChunkLen, 2 * kBlock, d1, d2);
-    s[oMisc + mDcEnd + 2 * (kDcChunks - 1)] = d1;
-    s[oMisc + mDcEnd + 2 * (kDcChunks - 1) + 1] = d2;
-  }
-  s[oMisc + mDcD1] = s[oMisc + mDcEnd + 2 * (kDcChunks - 1)];
-  s[oMisc + mDcD2] = s[oMisc + mDcEnd + 2 * (kDcChunks - 1) + 1];
+  if (bad >= kDcChunks) return;
+  const float *src = c.a.iq + ((size_t)(c.s0 + g) * c.a.n_blocks + c.t) * (2 * kBlock);
+  float d1 = s[oMisc + mDcEnd + 2 * (bad - 1)];
+  float d2 = s[oMisc + mDcEnd + 2 * (bad - 1) + 1];
+  for (int i = bad * kDcChunkLen; i < 2 * kBlock; ++i)
+    s[SeqOff(i)] = LdgRO(src + (i < kBlock ? 2 * i : 2 * (i - kBlock) + 1));
+  DcRun<true>(s, p, bad * kDcChunkLen, 2 * kBlock, d1, d2);
+  s[oMisc + mDcD1] = d1;
+  s[oMisc + mDcD2] = d2;
 }
 
 /* ------------------------------------------------------------------ */
@@ -411,6 +532,8 @@ T41RX_DEV void PhDcVerify(Cta &c, int tid) {
  * FIR decimation by 2^zoom, first zoom_samples outputs into the 512-deep ring.  One lane
  * per (receiver, channel); the cascade is evaluated sample by sample through all four
  * stages, which yields the same values as the reference's stage-by-stage order.           */
+#ifdef T41RX_HOST_EMUL
+/* host emulation: one lane per (receiver, channel) walks the four stages sample by sample */
 T41RX_DEV void PhZoomIir(Cta &c, int tid) {
   if (!c.row || tid >= c.ng * 2) return;
   const int g = tid >> 1, chn = tid & 1;
@@ -426,9 +549,10 @@ T41RX_DEV void PhZoomIir(Cta &c, int tid) {
   const int M = 1 << cf.zoom;
   int ptr = st.zoom_ptr;
   int produced = 0;
+  const IqFix fix = IqFixOf(cf);
   for (int n = 0; n < kBlock; ++n) {
     float vi = s[oRawI + 27 + n], vq = s[oRawQ + 27 + n];
-    IqCorr(cf, vi, vq);
+    IqCorr(fix, vi, vq);
     QuarterShift(n, vi, vq);
     float x = chn ? vq : vi;
 #pragma unroll
@@ -466,6 +590,94 @@ T41RX_DEV void PhZoomIir(Cta &c, int tid) {
   if (chn == 1) st.zoom_ptr = ptr;   /* both channels advance identically; written after the ring writes */
 }
 
+#else
+/* device: eight lanes per receiver = (channel, biquad stage), software-pipelined with a skew of
+ * two samples per stage; a stage's output travels to the next lane by warp shuffle one step
+ * ahead of its use, so the shuffle latency hides behind the biquad's add chain.  Identical
+ * arithmetic to the sample-by-sample form above. */
+T41RX_DEV void PhZoomIir(Cta &c, int tid) {
+  if (!c.row) return;
+  const int g = tid >> 6, lane = tid & 63;
+  if (g >= c.ng || lane >= 32) return;               /* first warp of the receiver's 64-thread group */
+  const StreamCfg &cf = c.a.cfg[c.s0 + g];
+  if (cf.zoom == 0) return;                          /* warp-uniform */
+  StreamState &st = c.a.st[c.s0 + g];
+  const float *s = Slot(c, g);
+  const bool active = lane < 8;
+  const int chn = (lane >> 2) & 1, sg = lane & 3;
+  float b0 = 0, b1 = 0, b2 = 0, a1 = 0, a2 = 0, x1 = 0, x2 = 0, y1 = 0, y2 = 0;
+  if (active) {
+    const float *kk = c.a.zoom_iir + (cf.zoom - 1) * 20 + 5 * sg;
+    b0 = LdgRO(kk); b1 = LdgRO(kk + 1); b2 = LdgRO(kk + 2); a1 = LdgRO(kk + 3); a2 = LdgRO(kk + 4);
+    x1 = st.zoom_iir[chn][4 * sg]; x2 = st.zoom_iir[chn][4 * sg + 1];
+    y1 = st.zoom_iir[chn][4 * sg + 2]; y2 = st.zoom_iir[chn][4 * sg + 3];
+  }
+  float h0 = 0, h1 = 0, h2 = 0;
+  const bool last = active && sg == 3;
+  if (last) { h0 = st.zoom_fir_hist[chn][0]; h1 = st.zoom_fir_hist[chn][1]; h2 = st.zoom_fir_hist[chn][2]; }
+  const float f0 = cf.zoom_fir[0], f1 = cf.zoom_fir[1], f2 = cf.zoom_fir[2], f3 = cf.zoom_fir[3];
+  const int M = 1 << cf.zoom;
+  const int zs = cf.zoom_samples;
+  int ptr = st.zoom_ptr;
+  int produced = 0;
+  float ylast = 0.0f, xcur = 0.0f;
+  const IqFix fix = IqFixOf(cf);
+  /* every lane runs the same instruction stream (selects instead of branches); the raw sample a
+     stage-0 lane needs is fetched one step ahead */
+  float ri = s[oRawI + 27], rq = s[oRawQ + 27];
+  for (int k = 0; k < kBlock + 6; ++k) {
+    /* my previous output is the next lane's input at step k+1 */
+    const float xfetch = __shfl_up_sync(0xffffffffu, ylast, 1);
+    const int n = k - 2 * sg;
+    const int nn = (k + 1 < kBlock) ? k + 1 : kBlock - 1;
+    const float ri_next = s[oRawI + 27 + nn], rq_next = s[oRawQ + 27 + nn];
+    float vi = ri, vq = rq;                       /* sample k: what a stage-0 lane processes now */
+    IqCorr(fix, vi, vq);
+    QuarterShift(k, vi, vq);
+    const float x0 = chn ? vq : vi;
+    const float x = (sg == 0) ? x0 : xcur;
+    const bool live = active && n >= 0 && n < kBlock;
+    float acc = b0 * x;
+    acc = acc + b1 * x1;
+    acc = acc + b2 * x2;
+    acc = acc + a1 * y1;
+    acc = acc + a2 * y2;
+    if (live) {
+      x2 = x1; x1 = x;
+      y2 = y1; y1 = acc;
+      ylast = acc;
+    }
+    /* 4-tap FIR decimator on the last stage's output (arm_fir_decimate_f32) */
+    float o = 0.0f;
+    o = fmaf(h0, f0, o);
+    o = fmaf(h1, f1, o);
+    o = fmaf(h2, f2, o);
+    o = fmaf(acc, f3, o);
+    if (live && last) {
+      if ((n & (M - 1)) == 0) {
+        if (produced < zs) {
+          st.zoom_ring[chn][ptr] = o;
+          ptr = (ptr + 1 >= kSpecRes) ? 0 : ptr + 1;
+        }
+        ++produced;
+      }
+      h0 = h1; h1 = h2; h2 = acc;
+    }
+    xcur = xfetch;
+    ri = ri_next;
+    rq = rq_next;
+  }
+  if (active) {
+    st.zoom_iir[chn][4 * sg] = x1; st.zoom_iir[chn][4 * sg + 1] = x2;
+    st.zoom_iir[chn][4 * sg + 2] = y1; st.zoom_iir[chn][4 * sg + 3] = y2;
+  }
+  if (last) {
+    st.zoom_fir_hist[chn][0] = h0; st.zoom_fir_hist[chn][1] = h1; st.zoom_fir_hist[chn][2] = h2;
+    if (chn == 1) st.zoom_ptr = ptr;
+  }
+}
+#endif
+
 /* window the 512 samples into the spectrum FFT buffer */
 T41RX_DEV void PhSpecWindow(Cta &c, int tid) {
   if (!c.row) return;
@@ -475,19 +687,22 @@ T41RX_DEV void PhSpecWindow(Cta &c, int tid) {
   const StreamCfg &cf = c.a.cfg[c.s0 + g];
   const StreamState &st = c.a.st[c.s0 + g];
   float2 *buf = reinterpret_cast<float2 *>(s + vSpecFft);
+  const IqFix fix = IqFixOf(cf);
+  const int zoom = cf.zoom, zptr = st.zoom_ptr;
+  const float zmult = cf.zoom_mult;
   for (int j = 0; j < 8; ++j) {
     const int i = u + 64 * j;
     const double w = LdgRO(c.a.hann + i);
     float re, im;
-    if (cf.zoom == 0) {          /* CalcZoom1Magn, FFT.cpp:220-223: raw (pre-shift) samples */
+    if (zoom == 0) {             /* CalcZoom1Magn, FFT.cpp:220-223: raw (pre-shift) samples */
       float vi = s[oRawI + 27 + i], vq = s[oRawQ + 27 + i];
-      IqCorr(cf, vi, vq);
+      IqCorr(fix, vi, vq);
       re = (float)((double)vi * w);
       im = (float)((double)vq * w);
     } else {                     /* ZoomFFTExe, FFT.cpp:109-116: ring, oldest first */
-      const int p = (st.zoom_ptr + i) & (kSpecRes - 1);
-      const float a = cf.zoom_mult * st.zoom_ring[0][p];
-      const float b = cf.zoom_mult * st.zoom_ring[1][p];
+      const int p = (zptr + i) & (kSpecRes - 1);
+      const float a = zmult * st.zoom_ring[0][p];
+      const float b = zmult * st.zoom_ring[1][p];
       re = (float)((double)a * w);
       im = (float)((double)b * w);
     }
@@ -603,6 +818,7 @@ T41RX_DEV void PhMix(Cta &c, int tid) {
         vi = st.osc_i;
       }
       const double oc = cf.osc_cos, os = cf.osc_sin;
+      const IqFix fix = IqFixOf(cf);
       for (int n = 0; n < kBlock; ++n) {
         const double oq = (vq * oc) - (vi * os);
         const double oi = (vi * oc) + (vq * os);
@@ -610,7 +826,7 @@ T41RX_DEV void PhMix(Cta &c, int tid) {
         vq = gain * oq;
         vi = gain * oi;
         float xi = s[oRawI + 27 + n], xq = s[oRawQ + 27 + n];
-        IqCorr(cf, xi, xq);
+        IqCorr(fix, xi, xq);
         QuarterShift(n, xi, xq);
         MixStore(s, n, xi, xq, oq, oi);
       }
@@ -630,16 +846,28 @@ T41RX_DEV void PhMix(Cta &c, int tid) {
     } else {
       const D2 *tab = reinterpret_cast<const D2 *>(s + oNco);
       const D2 w = tab[tid & 63];
+      const IqFix fix = IqFixOf(cf);
+      constexpr int kPer = kBlock / kNT;
+      /* in-place: read this thread's samples first so the compiler may overlap their (long:
+         two conversions each way) dependency chains */
+      for (int k0 = 0; k0 < kPer; k0 += 8) {
+        float xi[8], xq[8];
 #pragma unroll
-      for (int k = 0; k < kBlock / kNT; ++k) {
-        const int n = tid + kNT * k;
-        const D2 cb = tab[96 + (n >> 6)];
-        const double oq = cb.x * w.x - cb.y * w.y;
-        const double oi = cb.x * w.y + cb.y * w.x;
-        float xi = s[oRawI + 27 + n], xq = s[oRawQ + 27 + n];
-        IqCorr(cf, xi, xq);
-        QuarterShift(n, xi, xq);
-        MixStore(s, n, xi, xq, oq, oi);
+        for (int k = 0; k < 8; ++k) {
+          const int n = tid + kNT * (k0 + k);
+          xi[k] = s[oRawI + 27 + n];
+          xq[k] = s[oRawQ + 27 + n];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int n = tid + kNT * (k0 + k);
+          const D2 cb = tab[96 + (n >> 6)];
+          const double oq = cb.x * w.x - cb.y * w.y;
+          const double oi = cb.x * w.y + cb.y * w.x;
+          IqCorr(fix, xi[k], xq[k]);
+          QuarterShift(n, xi[k], xq[k]);
+          MixStore(s, n, xi[k], xq[k], oq, oi);
+        }
       }
     }
   }
@@ -663,75 +891,101 @@ T41RX_DEV void PhNcoAdvance(Cta &c, int tid) {
 /* (Process.cpp:262-267,378-386,474-479)                                */
 /* ------------------------------------------------------------------ */
 T41RX_DEV void PhDec1(Cta &c, int tid) {
-  for (int g = 0; g < c.ng; ++g) {
-    float *s = Slot(c, g);
-    float taps[kDec1Taps];
+  /* 64 threads per receiver; a thread owns outputs u, u+64, ..., u+448 of both channels:
+     16 independent accumulation chains keep the FMA pipe busy despite the in-order tap sums */
+  const int g = tid >> 6, u = tid & 63;
+  if (g >= c.ng) return;
+  float *s = Slot(c, g);
+  float taps[kDec1Taps];
 #pragma unroll
-    for (int i = 0; i < kDec1Taps; ++i) taps[i] = s[oTaps + kTapDec1 + i];
-    if (tid < 90) {               /* dec2 history back in front of the dec1 output */
-      const int ch = tid / 45, i = tid % 45;
-      s[(ch ? oD1Q : oD1I) + i] = s[oD2H + tid];
-    }
+  for (int i = 0; i < kDec1Taps; ++i) taps[i] = s[oTaps + kTapDec1 + i];
+  for (int h = u; h < 90; h += 64) {     /* dec2 history back in front of the dec1 output */
+    const int ch = h / 45, i = h % 45;
+    s[(ch ? oD1Q : oD1I) + i] = s[oD2H + h];
+  }
 #pragma unroll
-    for (int ch = 0; ch < 2; ++ch) {
-      const float *x = s + (ch ? oRawQ : oRawI);
-      float *y = s + (ch ? oD1Q : oD1I) + 45;
+  for (int half = 0; half < 2; ++half) {
+    float acc[2][4];
 #pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const int m = tid + kNT * r;
-        const float4 *w4 = reinterpret_cast<const float4 *>(x + 4 * m);
-        float acc = 0.0f;
+    for (int ch = 0; ch < 2; ++ch)
 #pragma unroll
-        for (int q = 0; q < kDec1Taps / 4; ++q) {
-          const float4 v = w4[q];
-          acc = fmaf(v.x, taps[4 * q + 0], acc);
-          acc = fmaf(v.y, taps[4 * q + 1], acc);
-          acc = fmaf(v.z, taps[4 * q + 2], acc);
-          acc = fmaf(v.w, taps[4 * q + 3], acc);
+      for (int r = 0; r < 4; ++r) acc[ch][r] = 0.0f;
+#pragma unroll
+    for (int q = 0; q < kDec1Taps / 4; ++q) {
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        const float *x = s + (ch ? oRawQ : oRawI);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int m = u + 64 * (4 * half + r);
+          const float4 v = *reinterpret_cast<const float4 *>(x + 4 * m + 4 * q);
+          acc[ch][r] = fmaf(v.x, taps[4 * q + 0], acc[ch][r]);
+          acc[ch][r] = fmaf(v.y, taps[4 * q + 1], acc[ch][r]);
+          acc[ch][r] = fmaf(v.z, taps[4 * q + 2], acc[ch][r]);
+          acc[ch][r] = fmaf(v.w, taps[4 * q + 3], acc[ch][r]);
         }
-        y[m] = acc;
       }
     }
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) s[(ch ? oD1Q : oD1I) + 45 + u + 64 * (4 * half + r)] = acc[ch][r];
   }
 }
 
 /* dec2, level adjust (Process.cpp:482-492), overlap-save assembly (Process.cpp:498-522) */
 T41RX_DEV void PhDec2(Cta &c, int tid) {
-  for (int g = 0; g < c.ng; ++g) {
-    float *s = Slot(c, g);
-    const StreamCfg &cf = c.a.cfg[c.s0 + g];
-    StreamState &st = c.a.st[c.s0 + g];
-    /* dec1's input region is about to be overlaid: keep its last 27 samples */
-    if (tid < 54) {
-      const int ch = tid / 27, i = tid % 27;
-      s[oD1H + tid] = s[(ch ? oRawQ : oRawI) + kBlock + i];
-    }
-    float acc[2];
+  const int g = tid >> 6, u = tid & 63;
+  if (g >= c.ng) return;
+  float *s = Slot(c, g);
+  const StreamCfg &cf = c.a.cfg[c.s0 + g];
+  const int mode = cf.mode;
+  const float vol_scale = cf.vol_scale;
+  const bool first_block = c.a.st[c.s0 + g].first_block != 0;
+  /* dec1's input region is about to be overlaid: keep its last 27 samples */
+  for (int h = u; h < 54; h += 64) {
+    const int ch = h / 27, i = h % 27;
+    s[oD1H + h] = s[(ch ? oRawQ : oRawI) + kBlock + i];
+  }
+  float taps[kDec2Taps];
+#pragma unroll
+  for (int i = 0; i < kDec2Taps; ++i) taps[i] = s[oTaps + kTapDec2 + i];
+  /* outputs u, u+64, u+128, u+192 of both channels: 8 independent chains */
+  float acc[2][4];
+#pragma unroll
+  for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) acc[ch][r] = 0.0f;
+#pragma unroll
+  for (int q = 0; q < kDec2Taps / 2; ++q) {
 #pragma unroll
     for (int ch = 0; ch < 2; ++ch) {
-      const float2 *w2 = reinterpret_cast<const float2 *>(s + (ch ? oD1Q : oD1I) + 2 * tid);
-      float a = 0.0f;
+      const float *x = s + (ch ? oD1Q : oD1I);
 #pragma unroll
-      for (int q = 0; q < kDec2Taps / 2; ++q) {
-        const float2 v = w2[q];
-        a = fmaf(v.x, s[oTaps + kTapDec2 + 2 * q], a);
-        a = fmaf(v.y, s[oTaps + kTapDec2 + 2 * q + 1], a);
+      for (int r = 0; r < 4; ++r) {
+        const int o = u + 64 * r;
+        const float2 v = *reinterpret_cast<const float2 *>(x + 2 * o + 2 * q);
+        acc[ch][r] = fmaf(v.x, taps[2 * q], acc[ch][r]);
+        acc[ch][r] = fmaf(v.y, taps[2 * q + 1], acc[ch][r]);
       }
-      acc[ch] = a;
     }
-    float2 *fa = reinterpret_cast<float2 *>(s + vFftA);
-    if (cf.mode == kModePsk31) {
-      s[vAud + 23 + tid] = acc[0];                 /* Process.cpp:376-387,745: raw decimated I */
-    } else if (cf.mode == kModeNfm) {
-      fa[kDec + tid] = float2{acc[0], acc[1]};     /* Process.cpp:272-275 */
+  }
+  float2 *fa = reinterpret_cast<float2 *>(s + vFftA);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int o = u + 64 * r;
+    if (mode == kModePsk31) {
+      s[vAud + 23 + o] = acc[0][r];                /* Process.cpp:376-387,745: raw decimated I */
+    } else if (mode == kModeNfm) {
+      fa[kDec + o] = float2{acc[0][r], acc[1][r]}; /* Process.cpp:272-275 */
     } else {
-      const float li = acc[0] * cf.vol_scale, lq = acc[1] * cf.vol_scale;
-      float2 prev = float2{s[oOla + tid], s[oOla + 256 + tid]};
-      if (st.first_block) prev = float2{0.0f, 0.0f};
-      fa[tid] = prev;
-      fa[kDec + tid] = float2{li, lq};
-      s[oOla + tid] = li;
-      s[oOla + 256 + tid] = lq;
+      const float li = acc[0][r] * vol_scale, lq = acc[1][r] * vol_scale;
+      float2 prev = float2{s[oOla + o], s[oOla + 256 + o]};
+      if (first_block) prev = float2{0.0f, 0.0f};
+      fa[o] = prev;
+      fa[kDec + o] = float2{li, lq};
+      s[oOla + o] = li;
+      s[oOla + 256 + o] = lq;
     }
   }
 }
@@ -742,30 +996,32 @@ T41RX_DEV void PhPostDec2(Cta &c, int tid) {
     float *s = Slot(c, g);
     const StreamCfg &cf = c.a.cfg[c.s0 + g];
     StreamState &st = c.a.st[c.s0 + g];
-    if (tid < 90) {
-      const int ch = tid / 45, i = tid % 45;
-      s[oD2H + tid] = s[(ch ? oD1Q : oD1I) + kDec1Out + i];
+    for (int h = tid; h < 90; h += kNT) {
+      const int ch = h / 45, i = h % 45;
+      s[oD2H + h] = s[(ch ? oD1Q : oD1I) + kDec1Out + i];
     }
     if (tid == 0 && cf.mode != kModePsk31 && cf.mode != kModeNfm) st.first_block = 0;
     if (cf.mode == kModeNfm) {
       const float2 *fa = reinterpret_cast<const float2 *>(s + vFftA);
       /* fmdemod_quadri_K is a double literal (Demod.h:7): K * num / den runs in double */
       const double kq = 0.340447550238101026565118445432744920253753662109375;
-      const float2 now = fa[kDec + tid];
+      for (int o = tid; o < kDec; o += kNT) {
+      const float2 now = fa[kDec + o];
       const float den = now.x * now.x + now.y * now.y;
       float out;
-      if (tid == 0) {
+      if (o == 0) {
         const float li = st.nfm_last_i, lq = st.nfm_last_q;
         const float num = now.x * (now.y - lq) - now.y * (now.x - li);
         out = (float)(kq * (double)num / (double)den);
       } else {
-        const float2 last = fa[kDec + tid - 1];
+        const float2 last = fa[kDec + o - 1];
         const float num = now.y * last.x - now.x * last.y;
         out = (float)(kq * (double)num / (double)den);
         out = (1.0f < out) ? 1.0f : out;           /* limiter skips index 0 (B5) */
         out = (-1.0f > out) ? -1.0f : out;
       }
-      s[vAmTmp + tid] = out;
+      s[vAmTmp + o] = out;
+      }
     }
   }
 }
@@ -790,10 +1046,12 @@ T41RX_DEV void PhNfmAssemble2(Cta &c, int tid) {
     const StreamCfg &cf = c.a.cfg[c.s0 + g];
     if (cf.mode != kModeNfm) continue;
     float2 *fa = reinterpret_cast<float2 *>(s + vFftA);
-    const float a = s[vAmTmp + tid];
-    fa[tid] = float2{s[oOla + tid], 0.0f};
-    fa[kDec + tid] = float2{a, 0.0f};
-    s[oOla + tid] = a;
+    for (int o = tid; o < kDec; o += kNT) {
+      const float a = s[vAmTmp + o];
+      fa[o] = float2{s[oOla + o], 0.0f};
+      fa[kDec + o] = float2{a, 0.0f};
+      s[oOla + o] = a;
+    }
   }
 }
 
@@ -902,80 +1160,102 @@ T41RX_DEV void PhAgcMaxLevel(Cta &c, int tid, int level) {
   }
 }
 
-/* the serial envelope state machine: one lane per receiver */
+/* the serial envelope state machine (DSP_Fn.cpp:521-626): lane 0 of the receiver's first warp,
+ * so that receivers in different AGC states do not serialise each other through divergence.
+ * All constants and state live in registers; the per-sample inputs (delayed |z| and the
+ * window maximum) are fetched four samples ahead of the recurrence. */
 T41RX_DEV void PhAgcSerial(Cta &c, int tid) {
-  if (tid >= c.ng) return;
-  const int g = tid;
+  const int g = SerialStream(c, tid);
+  if (g < 0) return;
   const StreamCfg &cf = c.a.cfg[c.s0 + g];
   if (!UsesFilter(cf.mode) || cf.agc_mode == 0) return;
   float *s = Slot(c, g);
   StreamState &st = c.a.st[c.s0 + g];
-  const AgcConsts &a = cf.agc;
+  const float k_fbm = cf.agc.fast_backmult, k_omfbm = cf.agc.onemfast_backmult;
+  const float k_hbm = cf.agc.hang_backmult, k_omhbm = cf.agc.onemhang_backmult;
+  const float k_attack = cf.agc.attack_mult, k_decay = cf.agc.decay_mult, k_fdecay = cf.agc.fast_decay_mult;
+  const float k_hdecay = cf.agc.hang_decay_mult, k_pop = cf.agc.pop_ratio, k_hlevel = cf.agc.hang_level;
+  const float k_minv = cf.agc.min_volts;
+  const int k_hload = cf.agc.hang_counter_load, k_henable = cf.agc.hang_enable;
   float fast = st.agc_fast_back, hang = st.agc_hang_back, v = st.agc_volts, save = st.agc_save_volts;
   int hc = st.agc_hang_counter, state = st.agc_state, dtype = st.agc_decay_type, action = st.agc_action;
   float rm = st.agc_ring_max;
-  for (int i = 0; i < kDec; ++i) {
-    const float abs_out = s[vAbs + i];
-    fast = a.fast_backmult * abs_out + a.onemfast_backmult * fast;
-    hang = a.hang_backmult * abs_out + a.onemhang_backmult * hang;
-    rm = s[vRm + i];
-    if (hc > 0) --hc;
-    if (rm >= v) {
-      if (state >= 2) save = v;
-      state = 0;
-      v += (rm - v) * a.attack_mult;
-    } else {
-      switch (state) {
-        case 0:
-          if (v > a.pop_ratio * fast) {
-            state = 1;
-            v += (rm - v) * a.fast_decay_mult;
-          } else if (a.hang_enable && (hang > a.hang_level)) {
-            state = 2;
-            hc = a.hang_counter_load;
-            dtype = 1;
-          } else {
-            state = 3;
-            v += (rm - v) * a.decay_mult;
-            dtype = 0;
-          }
-          break;
-        case 1:
-          if (v > save) {
-            v += (rm - v) * a.fast_decay_mult;
-          } else if (hc > 0) {
-            state = 2;
-          } else if (dtype == 0) {
-            state = 3;
-            v += (rm - v) * a.decay_mult;
-          } else {
-            state = 4;
-            v += (rm - v) * a.hang_decay_mult;
-          }
-          break;
-        case 2:
-          if (hc == 0) {
-            state = 4;
-            v += (rm - v) * a.hang_decay_mult;
-          }
-          break;
-        case 3: {
-          const float step = (rm - v) * a.decay_mult;
-          v = (float)((double)v + (double)step * .05);   /* double product and sum (DSP_Fn.cpp:607) */
-          break;
-        }
-        default:
-          v += (rm - v) * a.hang_decay_mult;
-          break;
+  int i = 0;
+  while (i < kDec) {
+    if (state == 3) {
+      /* run-length fast path for the steady state (slow decay, DSP_Fn.cpp:601-608): one loop-closing
+         branch per sample while the window maximum stays below volts.  Identical arithmetic to the
+         generic step below. */
+      while (i < kDec) {
+        const float r = s[vRm + i];
+        if (r >= v) break;
+        const float abs_out = s[vAbs + i];
+        fast = k_fbm * abs_out + k_omfbm * fast;
+        hang = k_hbm * abs_out + k_omhbm * hang;
+        rm = r;
+        hc = (hc > 0) ? hc - 1 : hc;
+        const float step = (r - v) * k_decay;
+        v = (float)((double)v + (double)step * .05);   /* double product and sum */
+        action = (v < k_minv) ? 0 : 1;
+        v = (v < k_minv) ? k_minv : v;
+        s[vVolt + i] = v;
+        ++i;
       }
+      if (i >= kDec) break;
     }
-    if (v < a.min_volts) {
-      v = a.min_volts;
-      action = 0;
-    } else {
-      action = 1;
+    /* generic step: the 5-state machine of DSP_Fn.cpp:521-626 */
+    {
+      const float abs_out = s[vAbs + i];
+      fast = k_fbm * abs_out + k_omfbm * fast;
+      hang = k_hbm * abs_out + k_omhbm * hang;
+      rm = s[vRm + i];
+      if (hc > 0) --hc;
+      const float d = rm - v;
+      if (rm >= v) {                       /* every state: attack; 2,3,4 remember the level they left */
+        if (state >= 2) save = v;
+        state = 0;
+        v += d * k_attack;
+      } else if (state == 3) {
+        const float step = d * k_decay;
+        v = (float)((double)v + (double)step * .05);
+      } else if (state == 0) {
+        if (v > k_pop * fast) {
+          state = 1;
+          v += d * k_fdecay;
+        } else if (k_henable && (hang > k_hlevel)) {
+          state = 2;
+          hc = k_hload;
+          dtype = 1;
+        } else {
+          state = 3;
+          v += d * k_decay;
+          dtype = 0;
+        }
+      } else if (state == 1) {
+        if (v > save) {
+          v += d * k_fdecay;
+        } else if (hc > 0) {
+          state = 2;
+        } else if (dtype == 0) {
+          state = 3;
+          v += d * k_decay;
+        } else {
+          state = 4;
+          v += d * k_hdecay;
+        }
+      } else if (state == 2) {
+        if (hc == 0) {
+          state = 4;
+          v += d * k_hdecay;
+        }
+      } else {
+        v += d * k_hdecay;
+      }
+      action = (v < k_minv) ? 0 : 1;
+      v = (v < k_minv) ? k_minv : v;
+      s[vVolt + i] = v;
+      ++i;
     }
-    s[vVolt + i] = v;
   }
   st.agc_fast_back = fast;
   st.agc_hang_back = hang;
@@ -1037,8 +1317,8 @@ T41RX_DEV void PhDemodParallel(Cta &c, int tid) {
 }
 
 T41RX_DEV void PhDemodSerial(Cta &c, int tid) {
-  if (tid >= c.ng) return;
-  const int g = tid;
+  const int g = SerialStream(c, tid);
+  if (g < 0) return;
   const StreamCfg &cf = c.a.cfg[c.s0 + g];
   float *s = Slot(c, g);
   StreamState &st = c.a.st[c.s0 + g];
@@ -1048,18 +1328,26 @@ T41RX_DEV void PhDemodSerial(Cta &c, int tid) {
     float wold = st.am_wold;
     float x1 = st.am_lp_state[0], x2 = st.am_lp_state[1], y1 = st.am_lp_state[2], y2 = st.am_lp_state[3];
     const float b0 = cf.am_lp[0], b1 = cf.am_lp[1], b2 = cf.am_lp[2], a1 = cf.am_lp[3], a2 = cf.am_lp[4];
-    for (int i = 0; i < kDec; ++i) {
-      const float w = s[vAmTmp + i] + wold * 0.99f;
-      const float x = w - wold;
-      wold = w;
-      float acc = b0 * x;
-      acc = acc + b1 * x1;
-      acc = acc + b2 * x2;
-      acc = acc + a1 * y1;
-      acc = acc + a2 * y2;
-      x2 = x1; x1 = x;
-      y2 = y1; y1 = acc;
-      s[vAud + 23 + i] = acc;
+    for (int i0 = 0; i0 < kDec; i0 += 4) {
+      float m4[4], o4[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) m4[j] = s[vAmTmp + i0 + j];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float w = m4[j] + wold * 0.99f;
+        const float x = w - wold;
+        wold = w;
+        float acc = b0 * x;
+        acc = acc + b1 * x1;
+        acc = acc + b2 * x2;
+        acc = acc + a1 * y1;
+        acc = acc + a2 * y2;
+        x2 = x1; x1 = x;
+        y2 = y1; y1 = acc;
+        o4[j] = acc;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[vAud + 23 + i0 + j] = o4[j];
     }
     st.am_wold = wold;
     st.am_lp_state[0] = x1; st.am_lp_state[1] = x2; st.am_lp_state[2] = y1; st.am_lp_state[3] = y2;
@@ -1147,44 +1435,69 @@ T41RX_DEV void PhDemodSerial(Cta &c, int tid) {
 T41RX_DEV void PhInterp1(Cta &c, int tid) {
   for (int g = 0; g < c.ng; ++g) {
     float *s = Slot(c, g);
-    if (tid < 23) s[vAud + tid] = s[oIntH + tid];
+    for (int h = tid; h < 23; h += kNT) s[vAud + h] = s[oIntH + h];
   }
 }
 T41RX_DEV void PhInterp1b(Cta &c, int tid) {
-  for (int g = 0; g < c.ng; ++g) {
-    float *s = Slot(c, g);
-    const float *w = s + vAud + tid;          /* oldest-first window of 24 ending at input tid */
-    float a0 = 0.0f, a1 = 0.0f;
+  const int g = tid >> 6, u = tid & 63;
+  if (g >= c.ng) return;
+  float *s = Slot(c, g);
+  float taps[kInt1Taps];
 #pragma unroll
-    for (int k = 0; k < 24; ++k) {
-      const float x = w[k];
-      a0 = fmaf(x, s[oTaps + kTapInt1 + 2 * k + 1], a0);   /* phase 0: c[(L-1) + kL] */
-      a1 = fmaf(x, s[oTaps + kTapInt1 + 2 * k], a1);       /* phase 1: c[0 + kL]     */
+  for (int i = 0; i < kInt1Taps; ++i) taps[i] = s[oTaps + kTapInt1 + i];
+  /* inputs u, u+64, u+128, u+192; two output phases each: 8 independent chains */
+  float a0[4], a1[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) { a0[r] = 0.0f; a1[r] = 0.0f; }
+#pragma unroll
+  for (int k = 0; k < 24; ++k) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float x = s[vAud + u + 64 * r + k];      /* oldest-first window of 24 ending at the input */
+      a0[r] = fmaf(x, taps[2 * k + 1], a0[r]);        /* phase 0: c[(L-1) + kL] */
+      a1[r] = fmaf(x, taps[2 * k], a1[r]);            /* phase 1: c[0 + kL]     */
     }
-    s[vInt2 + 7 + 2 * tid] = a0;
-    s[vInt2 + 7 + 2 * tid + 1] = a1;
-    if (tid < 7) s[vInt2 + tid] = s[oIntH + 24 + tid];
   }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int n = u + 64 * r;
+    s[vInt2 + 7 + 2 * n] = a0[r];
+    s[vInt2 + 7 + 2 * n + 1] = a1[r];
+  }
+  for (int h = u; h < 7; h += 64) s[vInt2 + h] = s[oIntH + 24 + h];
 }
 
 T41RX_DEV void PhInterp2(Cta &c, int tid) {
-  for (int g = 0; g < c.ng; ++g) {
-    float *s = Slot(c, g);
-    const StreamCfg &cf = c.a.cfg[c.s0 + g];
-    float4 *dst = reinterpret_cast<float4 *>(c.a.audio + ((size_t)(c.s0 + g) * c.a.n_blocks + c.t) * kBlock);
-    if (tid < 23) s[oIntH + tid] = s[vAud + kDec + tid];          /* int1 history for the next block */
+  const int g = tid >> 6, u = tid & 63;
+  if (g >= c.ng) return;
+  float *s = Slot(c, g);
+  const float volume = c.a.cfg[c.s0 + g].volume;
+  float4 *dst = reinterpret_cast<float4 *>(c.a.audio + ((size_t)(c.s0 + g) * c.a.n_blocks + c.t) * kBlock);
+  for (int h = u; h < 23; h += 64) s[oIntH + h] = s[vAud + kDec + h];   /* int1 history for the next block */
+  float taps[kInt2Taps];
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int n = tid + kNT * r;
-      const float *w = s + vInt2 + n;
-      float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  for (int i = 0; i < kInt2Taps; ++i) taps[i] = s[oTaps + kTapInt2 + i];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float x = w[k];
+  for (int half = 0; half < 2; ++half) {
+    /* inputs n = u + 64 r: four outputs each (one float4 store), 16 independent chains */
+    float acc[4][4];
 #pragma unroll
-        for (int p = 0; p < 4; ++p) acc[p] = fmaf(x, s[oTaps + kTapInt2 + 4 * k + (3 - p)], acc[p]);
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int p = 0; p < 4; ++p) acc[r][p] = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float x = s[vInt2 + u + 64 * (4 * half + r) + k];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) acc[r][p] = fmaf(x, taps[4 * k + (3 - p)], acc[r][p]);
       }
-      dst[n] = float4{acc[0] * cf.volume, acc[1] * cf.volume, acc[2] * cf.volume, acc[3] * cf.volume};
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int n = u + 64 * (4 * half + r);
+      dst[n] = float4{acc[r][0] * volume, acc[r][1] * volume, acc[r][2] * volume, acc[r][3] * volume};
     }
   }
 }
@@ -1193,8 +1506,8 @@ T41RX_DEV void PhInterp2(Cta &c, int tid) {
 T41RX_DEV void PhBlockEnd(Cta &c, int tid) {
   for (int g = 0; g < c.ng; ++g) {
     float *s = Slot(c, g);
-    if (tid < 7) s[oIntH + 24 + tid] = s[vInt2 + 2 * kDec + tid];
-    if (tid == 32) {
+    for (int h = tid; h < 7; h += kNT) s[oIntH + 24 + h] = s[vInt2 + 2 * kDec + h];
+    if (tid == kNT - 1) {
       StreamState &st = c.a.st[c.s0 + g];
       uint32_t timer = st.codec_timer + 1;
       if (timer > 10000) timer = 10000;
@@ -1217,6 +1530,7 @@ T41RX_DEV void PhBlockEnd(Cta &c, int tid) {
   RX_PHASE(PhDcWarm(c, tid));                                            \
   RX_PHASE(PhDcMain(c, tid));                                            \
   RX_PHASE(PhDcVerify(c, tid));                                          \
+  RX_PHASE(PhDcFix(c, tid));                                             \
   if (c.row) {                                                           \
     RX_PHASE(PhZoomIir(c, tid));                                         \
     RX_PHASE(PhSpecWindow(c, tid));                                      \
