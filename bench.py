@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--streams", type=int, default=1024, help="virtual receivers per GPU")
     ap.add_argument("--blocks", type=int, default=64, help="2048-sample blocks per receiver per step")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget of the cpu_baseline sample")
+    ap.add_argument("--rows-per-step", type=int, default=1, choices=[0, 1],
+                    help="spectrum + waterfall rows per receiver per step (the first block of a step)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -74,7 +76,7 @@ def config_dict(args):
     return {"workload": "C2: %d concurrent virtual receivers per GPU, SSB+AM mixed, 192 kS/s, AGC Long, "
                         "per-receiver NCO, full RX chain fused" % args.streams,
             "receivers_per_gpu": args.streams, "blocks_per_step": args.blocks, "block_samples": 2048,
-            "rows_per_receiver_per_step": 1, "distinct_waveforms": N_DISTINCT,
+            "rows_per_receiver_per_step": args.rows_per_step, "distinct_waveforms": N_DISTINCT,
             "l2_policy": "inputs larger than L2 (%.0f MiB of I/Q per step per GPU)" % (
                 args.streams * args.blocks * 16384 / 2 ** 20),
             "parallelism": "receivers sharded across GPUs, no data-path collective"}
@@ -236,6 +238,7 @@ def ours(args):
     dev = torch.device("cuda", local)
 
     S, T = args.streams, args.blocks
+    row_every = T if args.rows_per_step else 0
     params, sigs = workload(T)
     eng = rx.Receiver(S, device=local)
     eng.set_params_each([rx_driver.to_rx_params(params[s % N_DISTINCT]) for s in range(S)])
@@ -252,7 +255,7 @@ def ours(args):
     torch.cuda.synchronize()
 
     def step():
-        eng.process_device(iq.data_ptr(), audio.data_ptr(), T, T, spec.data_ptr(), wf.data_ptr(),
+        eng.process_device(iq.data_ptr(), audio.data_ptr(), T, row_every, spec.data_ptr(), wf.data_ptr(),
                            None, None, 0, stream.cuda_stream)
 
     def barrier():
@@ -291,7 +294,7 @@ def ours(args):
     value = samples_per_step * args.steps / (total_ms_max * 1e-3) / 1e6
 
     # roofline of the fused kernel (the only kernel of a step)
-    bytes_per_launch = S * T * rx.BYTES_PER_BLOCK + S * rx.BYTES_PER_ROW
+    bytes_per_launch = S * T * rx.BYTES_PER_BLOCK + S * rx.BYTES_PER_ROW * args.rows_per_step
     avg_launch_s = statistics.mean(launch_ms) * 1e-3
     achieved = bytes_per_launch / avg_launch_s / 1e9
     peak, peak_src = measured_peak()
@@ -310,11 +313,11 @@ def ours(args):
                      psk_bits=None, psk_chars=None)
         h_iq_np = h_iq.numpy()
         for _ in range(2):
-            eng.process(h_iq_np, row_every=T, out=h_out)
+            eng.process(h_iq_np, row_every=row_every, out=h_out)
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            eng.process(h_iq_np, row_every=T, out=h_out)
+            eng.process(h_iq_np, row_every=row_every, out=h_out)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
@@ -323,7 +326,7 @@ def ours(args):
         dt = float(tt.item())
         gpu_launches += args.steps
         e2e = {"value": samples_per_step * args.steps / dt / 1e6, "unit": UNIT,
-               "h2d_bytes_per_step": S * T * 16384, "d2h_bytes_per_step": S * T * 8192 + S * rx.BYTES_PER_ROW,
+               "h2d_bytes_per_step": S * T * 16384, "d2h_bytes_per_step": S * T * 8192 + S * rx.BYTES_PER_ROW * args.rows_per_step,
                "timed_with": "host wall clock around t41rx_process (blocking), max over ranks",
                "checksum_audio": float(np.abs(h_out["audio"][::97, -1, ::31]).sum())}
 

@@ -54,8 +54,12 @@ extern "C" {
 #define T41RX_ENODEV -4    /* no usable CUDA device: there is no CPU path */
 
 /* t41rx_process flags */
-#define T41RX_FLAG_EXACT_NCO 1u /* run FreqShift2's FP64 oscillator recurrence step by step (bit-exact
-                                   with the reference, serial); default is the closed-form FP64 phasor */
+#define T41RX_FLAG_EXACT_NCO 1u /* bit-exact kernel, FreqShift2's FP64 oscillator recurrence run step by step:
+                                   every output identical to the reference build, slow */
+#define T41RX_FLAG_PHASED_KERNEL 2u /* bit-exact kernel with the closed-form FP64 oscillator (all other stages
+                                   still rounded operation by operation like the reference) */
+/* flags == 0: the throughput kernel (FP32 with FMA contraction, blocked-scan recurrences): audio within
+   the stated tolerance of the reference (SNR >= 90 dB), discrete state identical */
 
 /* Per-receiver parameters = the globals ProcessIQData() samples at block start. */
 typedef struct t41rx_params {

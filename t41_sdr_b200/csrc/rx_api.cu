@@ -17,6 +17,7 @@
 #include "../../include/t41rx.h"
 #include "rx_design.h"
 #include "rx_host.h"
+#include "rx_launch.h"
 #include "rx_phases.cuh"
 #include "rx_tables_data.h"
 
@@ -103,6 +104,7 @@ static int Fail(int code, const char *fmt, const char *detail = "") {
 struct t41rx_ctx {
   int device = 0;
   int n_streams = 0;
+  int n_sms = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool ev_valid = false;
@@ -238,6 +240,9 @@ int t41rx_create(t41rx_ctx **out, int n_streams, int device) {
   if (cudaFuncSetAttribute(t41rx_fused_rx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)(kSmemFloats * sizeof(float))) != cudaSuccess)
     return bail(Fail(T41RX_ECUDA, "t41rx_create: kernel image for this GPU missing (built for sm_100a)%s"));
+  if (ConfigureStreamKernel() != cudaSuccess ||
+      cudaDeviceGetAttribute(&ctx->n_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || ctx->n_sms <= 0)
+    return bail(Fail(T41RX_ECUDA, "t41rx_create: throughput kernel unavailable on this GPU (built for sm_100a)%s"));
   ctx->host.Init(n_streams);
   if ((rc = UploadConstTables(ctx))) return bail(rc);
   if (cudaMalloc(&ctx->d_cfg, sizeof(StreamCfg) * n_streams) != cudaSuccess ||
@@ -411,10 +416,17 @@ int t41rx_process_device(t41rx_ctx *ctx, const float *iq, float *audio, int n_bl
   a.row_every = row_every;
   a.n_rows = row_every > 0 ? (n_blocks + row_every - 1) / row_every : 0;
   a.flags = flags;
-  const int grid = (ctx->n_streams + kG - 1) / kG;
+  /* kernel choice: the throughput kernel unless the caller asks for the bit-exact oscillator or the
+     phase-structured kernel, or the launch has row-producing blocks (display spectrum: phased kernel) */
+  const bool phased = (flags & (T41RX_FLAG_EXACT_NCO | T41RX_FLAG_PHASED_KERNEL)) != 0 || row_every > 0;
   CUDA_TRY(cudaEventRecord(ctx->ev0, st));
-  t41rx_fused_rx_kernel<<<grid, kNT, kSmemFloats * sizeof(float), st>>>(a);
-  CUDA_TRY(cudaGetLastError());
+  if (phased) {
+    const int grid = (ctx->n_streams + kG - 1) / kG;
+    t41rx_fused_rx_kernel<<<grid, kNT, kSmemFloats * sizeof(float), st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+  } else {
+    CUDA_TRY(LaunchStreamKernel(a, ctx->n_sms, st));
+  }
   CUDA_TRY(cudaEventRecord(ctx->ev1, st));
   ctx->ev_valid = true;
   ctx->launches += 1;

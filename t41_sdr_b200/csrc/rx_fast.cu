@@ -1,0 +1,36 @@
+/*
+ * rx_fast.cu — t41rx_stream_rx_kernel (rx_fast.cuh) and its launcher.  Built WITHOUT --fmad=false:
+ * this kernel trades bit-exactness for throughput (see rx_fast.cuh); the bit-exact kernel lives in
+ * rx_api.cu.
+ */
+#include <cuda_runtime.h>
+
+#include "rx_fast.cuh"
+#include "rx_launch.h"
+
+namespace t41rx {
+
+__global__ void __launch_bounds__(32 * (fast::kFastMaxG + 1), 1) t41rx_stream_rx_kernel(const LaunchArgs a, const int G) {
+  extern __shared__ __align__(16) float smem[];
+  fast::StreamKernelBody(a, G, smem);
+}
+
+int StreamKernelMaxReceiversPerCta() { return fast::kFastMaxG; }
+
+cudaError_t ConfigureStreamKernel() {
+  return cudaFuncSetAttribute(t41rx_stream_rx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)(fast::kFastMaxG * fast::kSlotF * sizeof(float)));
+}
+
+cudaError_t LaunchStreamKernel(const LaunchArgs &a, int n_sms, cudaStream_t st) {
+  /* receivers per CTA: as few as fill every SM once (one CTA per SM: 1024 receivers on 148 SMs -> 7),
+     capped by shared memory; larger banks run in waves */
+  int G = (a.n_streams + n_sms - 1) / n_sms;
+  if (G < 1) G = 1;
+  if (G > fast::kFastMaxG) G = fast::kFastMaxG;
+  const int grid = (a.n_streams + G - 1) / G;
+  t41rx_stream_rx_kernel<<<grid, 32 * (G + 1), (size_t)G * fast::kSlotF * sizeof(float), st>>>(a, G);
+  return cudaGetLastError();
+}
+
+}  // namespace t41rx
