@@ -17,6 +17,17 @@ __global__ void __launch_bounds__(32 * (fast::kFastMaxG + 1), 1) t41rx_stream_rx
 
 int StreamKernelMaxReceiversPerCta() { return fast::kFastMaxG; }
 
+#ifdef T41RX_FAST_TIMING
+extern "C" int t41rx_debug_fast_cycles(unsigned long long *out32, int reset) {
+  if (cudaMemcpyFromSymbol(out32, fast::g_fast_cycles, sizeof(unsigned long long) * 32) != cudaSuccess) return -1;
+  if (reset) {
+    unsigned long long z[32] = {0};
+    cudaMemcpyToSymbol(fast::g_fast_cycles, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
+
 cudaError_t ConfigureStreamKernel() {
   return cudaFuncSetAttribute(t41rx_stream_rx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)(fast::kFastMaxG * fast::kSlotF * sizeof(float)));

@@ -80,6 +80,30 @@ __device__ __forceinline__ float PowA1(int n) {       /* a1^n, n >= 0, by squari
   return r;
 }
 
+#ifdef T41RX_FAST_TIMING
+/* developer build: cycles per section, CTA 0, receiver warp 0 (slots 0..15) and the AGC warp (16..19) */
+__device__ unsigned long long g_fast_cycles[32];
+struct SectionTimer {
+  long long mark;
+  bool on;
+  int base;
+  __device__ __forceinline__ void Start(bool enable, int b) { on = enable; base = b; mark = clock64(); }
+  __device__ __forceinline__ void Lap(int slot) {
+    if (on) {
+      const long long now = clock64();
+      g_fast_cycles[base + slot] += (unsigned long long)(now - mark);
+      mark = now;
+    }
+  }
+};
+#define T41RX_LAP(tm, slot) (tm).Lap(slot)
+#else
+struct SectionTimer {
+  __device__ __forceinline__ void Start(bool, int) {}
+};
+#define T41RX_LAP(tm, slot) ((void)0)
+#endif
+
 struct F2 { float x, y; };
 __device__ __forceinline__ F2 CMul(F2 a, F2 b) { return F2{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
 
@@ -191,6 +215,7 @@ struct RxWarp {
   int sid;           /* receiver index */
   int lane;
   RxRegs r;
+  SectionTimer tm;
   float tap1[kDec1Taps];   /* dec1 taps live in registers for the whole launch */
 
   __device__ __forceinline__ RxWarp(const LaunchArgs &a_, float *s_, int sid_, int lane_) : a(a_), s(s_), sid(sid_), lane(lane_) {}
@@ -463,7 +488,9 @@ struct RxWarp {
       *reinterpret_cast<float4 *>(mix + (4 + p) * kMixPlane + 8 + 4 * lane) = float4{oq[p], oq[4 + p], oq[8 + p], oq[12 + p]};
     }
     __syncwarp();
+    T41RX_LAP(tm, 2);
     Dec1Quarter(q);
+    T41RX_LAP(tm, 3);
   }
 
   /* arm_fir_decimate_f32, M = 4, 28 taps (Process.cpp:474-475): 4 outputs per lane per quarter.
@@ -560,6 +587,7 @@ struct RxWarp {
     for (int i = lane; i < 96; i += 32) s[oD1 + (i / 24) * kD1Plane + (i % 24)] = s[oDH + i];
     /* gains of this block (Process.cpp:117,133): rfGainValue and RFgain are folded into the phasor */
     const float gain = r.in_gain * (float)r.rf_gain;
+    T41RX_LAP(tm, 0);
     const F2 pb = F2{(float)r.ph_re * gain, -(float)r.ph_im * gain};
     float cI = r.dc_w, cQ = tail;
     /* NB: tail misses a1^2048 * (state entering I), which is exactly 0 in float */
@@ -568,6 +596,7 @@ struct RxWarp {
       for (int q = 0; q < 4; ++q) {
         CpAsyncWaitAll();
         __syncwarp();
+        T41RX_LAP(tm, 1);
         if (q < 3) IssueQuarter(t, q + 1);
         else if (t + 1 < a.n_blocks) IssueQuarter(t + 1, 0);
         const F2 qq = F2{s[oNcoW + 32 + 2 * q], s[oNcoW + 32 + 2 * q + 1]};
@@ -629,8 +658,10 @@ struct RxWarp {
     for (int i = lane; i < 64; i += 32) s[oMH + i] = s[oMix + (i >> 3) * kMixPlane + (i & 7)];
     __syncwarp();
     float dq[2][8];
+    T41RX_LAP(tm, 4);
     Dec2(dq);
     __syncwarp();
+    T41RX_LAP(tm, 5);
     /* dec2 history for the next block: entries 232..255 of each plane */
     for (int i = lane; i < 96; i += 32) s[oDH + i] = s[oD1 + (i / 24) * kD1Plane + 24 + 232 + (i % 24)];
     __syncwarp();
@@ -685,6 +716,7 @@ struct RxWarp {
     __syncwarp();
     InvPass<0, true>(fb, tw, lane); InvPass<0, true>(fb, tw, lane + 32);
     __syncwarp();
+    T41RX_LAP(tm, 6);
     /* valid outputs 256..511, scaled by 1/512 */
     float2 z[8];
 #pragma unroll
@@ -751,6 +783,7 @@ struct RxWarp {
     }
     __syncwarp();
     for (int i = lane; i < kAgcDelay; i += 32) s[oAH + i] = E[kDec + i];
+    T41RX_LAP(tm, 7);
   }
 
   /* NFM: discriminator on the decimated samples, then the audio goes through the filter as a real
@@ -839,13 +872,16 @@ struct RxWarp {
     *reinterpret_cast<float4 *>(aud + 24 + o0) = float4{au[0], au[1], au[2], au[3]};
     *reinterpret_cast<float4 *>(aud + 24 + o0 + 4) = float4{au[4], au[5], au[6], au[7]};
     __syncwarp();
+    T41RX_LAP(tm, 8);
     Interp1();
     __syncwarp();
+    T41RX_LAP(tm, 9);
     if (lane < 23) s[oIH + lane] = aud[24 + 233 + lane];
     Interp2(t);
     __syncwarp();
     if (lane < 7) s[oIH + 24 + lane] = s[vI1 + 8 + 505 + lane];
     __syncwarp();
+    T41RX_LAP(tm, 10);
   }
 
   /* arm_fir_interpolate_f32, L = 2, 48 taps (Process.cpp:917): 8 inputs per lane */
@@ -1174,22 +1210,72 @@ struct AgcLane {
   }
 };
 
-/* one block of one receiver per lane.  sta: |z| delayed [256] then window max [256] (overwritten by volts) */
+/* one block of one receiver per lane.  sta: |z| delayed [256] then window max [256] (overwritten by volts).
+ *
+ * Almost every sample leaves the envelope detector in a "quiet" state: slow decay (3), hang decay (4) or
+ * hang (2) with the window maximum below volts, where the update is  v <- max(v + ((r - v) k1) k2, min_volts)
+ * with per-state constants and no branch.  The warp therefore runs 8 samples at a time speculatively on that
+ * branch-free form (all lanes), votes once, and only re-runs the chunk through the exact per-sample state
+ * machine (Step) when some lane saw a transition (attack, end of hang, states 0 / 1). */
 __device__ __forceinline__ void AgcBlock(AgcLane &g, float *sta, bool active) {
+  constexpr int kC = 8;
 #pragma unroll 1
-  for (int i0 = 0; i0 < kDec; i0 += 4) {
-    float4 ab = float4{0, 0, 0, 0}, rm4 = float4{0, 0, 0, 0};
+  for (int i0 = 0; i0 < kDec; i0 += kC) {
+    float ab[kC], rm[kC];
     if (active) {
-      ab = *reinterpret_cast<const float4 *>(sta + i0);
-      rm4 = *reinterpret_cast<const float4 *>(sta + 256 + i0);
+#pragma unroll
+      for (int k = 0; k < kC; k += 4) {
+        const float4 a4 = *reinterpret_cast<const float4 *>(sta + i0 + k);
+        const float4 r4 = *reinterpret_cast<const float4 *>(sta + 256 + i0 + k);
+        ab[k] = a4.x; ab[k + 1] = a4.y; ab[k + 2] = a4.z; ab[k + 3] = a4.w;
+        rm[k] = r4.x; rm[k + 1] = r4.y; rm[k + 2] = r4.z; rm[k + 3] = r4.w;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < kC; ++k) { ab[k] = 0.0f; rm[k] = 0.0f; }
     }
-    float4 vo;
+    /* speculative quiet path */
+    float k1 = 0.0f, k2 = 0.0f;
+    bool ok = true;
+    if (g.state == 3) { k1 = g.decay; k2 = 0.05f; }
+    else if (g.state == 4) { k1 = g.hdecay; k2 = 1.0f; }
+    else if (g.state == 2 && g.hc > kC) { k1 = 0.0f; k2 = 0.0f; }
+    else ok = false;
+    float v = g.v, fast = g.fast, hang = g.hang, last = g.v;
+    float vo[kC];
+#pragma unroll
+    for (int k = 0; k < kC; ++k) {
+      ok = ok && !(rm[k] >= v);
+      fast = g.fbm * ab[k] + g.omfbm * fast;
+      hang = g.hbm * ab[k] + g.omhbm * hang;
+      const float t = (rm[k] - v) * k1;
+      last = fmaf(t, k2, v);
+      v = fmaxf(last, g.minv);
+      vo[k] = v;
+    }
+    if (__all_sync(kFull, ok || !active)) {
+      if (active) {
+        g.v = v; g.fast = fast; g.hang = hang;
+        g.rm = rm[kC - 1];
+        g.hc = max(g.hc - kC, 0);
+        g.action = (last < g.minv) ? 0 : 1;
+      }
+    } else if (active) {
+#pragma unroll 1
+      for (int k = 0; k < kC; ++k) {
+        /* select ab[k], rm[k] without dynamic register indexing */
+        float a_ = ab[0], r_ = rm[0];
+#pragma unroll
+        for (int j = 1; j < kC; ++j) { if (k == j) { a_ = ab[j]; r_ = rm[j]; } }
+        const float vv = g.Step(a_, r_);
+#pragma unroll
+        for (int j = 0; j < kC; ++j) { if (k == j) vo[j] = vv; }
+      }
+    }
     if (active) {
-      vo.x = g.Step(ab.x, rm4.x);
-      vo.y = g.Step(ab.y, rm4.y);
-      vo.z = g.Step(ab.z, rm4.z);
-      vo.w = g.Step(ab.w, rm4.w);
-      *reinterpret_cast<float4 *>(sta + 256 + i0) = vo;
+#pragma unroll
+      for (int k = 0; k < kC; k += 4)
+        *reinterpret_cast<float4 *>(sta + 256 + i0 + k) = float4{vo[k], vo[k + 1], vo[k + 2], vo[k + 3]};
     }
   }
 }
@@ -1210,12 +1296,15 @@ __device__ __forceinline__ void StreamKernelBody(const LaunchArgs &a, int G, flo
       w.LoadState();
       w.IssueQuarter(0, 0);
     }
+    w.tm.Start(blockIdx.x == 0 && warp == 0 && lane == 0, 0);
     for (int k = 0; k < T + 2; ++k) {
       if (live) {
         if (k >= 2) w.BackEnd(k - 2, k & 1);
         if (k < T) w.FrontEnd(k, k & 1);
       }
+      T41RX_LAP(w.tm, 11);
       __syncthreads();
+      T41RX_LAP(w.tm, 12);
     }
     if (live) w.StoreState();
   } else {
@@ -1229,9 +1318,13 @@ __device__ __forceinline__ void StreamKernelBody(const LaunchArgs &a, int G, flo
       active = (cf.mode != kModePsk31) && (cf.agc_mode != 0);
     }
     float *slot = smem + (mine ? lane : 0) * kSlotF;
+    SectionTimer tm;
+    tm.Start(blockIdx.x == 0 && lane == 0, 16);
     for (int k = 0; k < T + 2; ++k) {
       if (k >= 1 && k <= T) AgcBlock(g, slot + oStA + ((k - 1) & 1) * 512, active);
+      T41RX_LAP(tm, 0);
       __syncthreads();
+      T41RX_LAP(tm, 1);
     }
     if (mine && active) g.Store(a.st[s0 + lane]);
   }
