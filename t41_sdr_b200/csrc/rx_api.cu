@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(kNT, 8 / kG) t41rx_fused_rx_kernel(const Launc
   c.t = 0;
   c.row = 0;
   c.row_idx = 0;
+  c.rows_only = 0;
   const int tid = threadIdx.x;
   PhStateIn(c, tid);
   __syncthreads();
@@ -74,6 +75,32 @@ __global__ void __launch_bounds__(kNT, 8 / kG) t41rx_fused_rx_kernel(const Launc
 #undef T41RX_KPHASE
   }
   PhStateOut(c, tid);
+}
+
+/* display spectrum + waterfall rows of the row-producing blocks, for the receivers the throughput kernel
+   serves; launched before it on the same stream (reads the launch-start state, writes only the zoom /
+   spectrum state and the row outputs) */
+__global__ void __launch_bounds__(kNT, 8 / kG) t41rx_rows_kernel(const LaunchArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  Cta c;
+  c.a = a;
+  c.smem = smem;
+  c.s0 = blockIdx.x * kG;
+  c.ng = min(kG, a.n_streams - c.s0);
+  c.row = 1;
+  c.rows_only = 1;
+  const int tid = threadIdx.x;
+  for (int t = 0; t < a.n_blocks; t += a.row_every) {
+    c.t = t;
+    c.row_idx = t / a.row_every;
+#define T41RX_KPHASE(stmt) \
+  do {                     \
+    stmt;                  \
+    __syncthreads();       \
+  } while (0)
+    T41RX_ROWS_SCHEDULE(T41RX_KPHASE)
+#undef T41RX_KPHASE
+  }
 }
 
 }  // namespace t41rx
@@ -124,6 +151,12 @@ struct t41rx_ctx {
   float *d_sam = nullptr;
   uint16_t *d_gradient = nullptr;
   uint32_t *d_varicode = nullptr;
+
+  /* receivers by kernel: the SAM PLL is chaotic while it acquires lock, so SAM receivers stay on the
+     bit-exact kernel; everything else runs on the throughput kernel */
+  std::vector<int32_t> h_fast_ids, h_phased_ids;
+  int32_t *d_fast_ids = nullptr, *d_phased_ids = nullptr;
+  bool ids_dirty = true;
 
   /* device staging for the host-buffer entry point */
   void *d_iq = nullptr, *d_audio = nullptr, *d_spec = nullptr, *d_wf = nullptr, *d_bits = nullptr, *d_chars = nullptr;
@@ -208,7 +241,7 @@ void t41rx_destroy(t41rx_ctx *ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   void *bufs[] = {ctx->d_cfg, ctx->d_state, ctx->d_fsets, ctx->d_nco_tab, ctx->d_twiddle, ctx->d_hann, ctx->d_sin,
                   ctx->d_zoom_iir, ctx->d_sam, ctx->d_gradient, ctx->d_varicode, ctx->d_iq, ctx->d_audio,
-                  ctx->d_spec, ctx->d_wf, ctx->d_bits, ctx->d_chars};
+                  ctx->d_spec, ctx->d_wf, ctx->d_bits, ctx->d_chars, ctx->d_fast_ids, ctx->d_phased_ids};
   for (void *b : bufs)
     if (b) cudaFree(b);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -238,6 +271,8 @@ int t41rx_create(t41rx_ctx **out, int n_streams, int device) {
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess)
     return bail(Fail(T41RX_ECUDA, "t41rx_create: stream/event creation failed%s"));
   if (cudaFuncSetAttribute(t41rx_fused_rx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)(kSmemFloats * sizeof(float))) != cudaSuccess ||
+      cudaFuncSetAttribute(t41rx_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)(kSmemFloats * sizeof(float))) != cudaSuccess)
     return bail(Fail(T41RX_ECUDA, "t41rx_create: kernel image for this GPU missing (built for sm_100a)%s"));
   if (ConfigureStreamKernel() != cudaSuccess ||
@@ -247,7 +282,9 @@ int t41rx_create(t41rx_ctx **out, int n_streams, int device) {
   if ((rc = UploadConstTables(ctx))) return bail(rc);
   if (cudaMalloc(&ctx->d_cfg, sizeof(StreamCfg) * n_streams) != cudaSuccess ||
       cudaMalloc(&ctx->d_state, sizeof(StreamState) * n_streams) != cudaSuccess ||
-      cudaMalloc(&ctx->d_nco_tab, sizeof(double) * 192 * n_streams) != cudaSuccess)
+      cudaMalloc(&ctx->d_nco_tab, sizeof(double) * 192 * n_streams) != cudaSuccess ||
+      cudaMalloc(&ctx->d_fast_ids, sizeof(int32_t) * n_streams) != cudaSuccess ||
+      cudaMalloc(&ctx->d_phased_ids, sizeof(int32_t) * n_streams) != cudaSuccess)
     return bail(Fail(T41RX_ENOMEM, "t41rx_create: device allocation failed%s"));
   {
     std::vector<StreamState> init(n_streams);
@@ -288,7 +325,12 @@ static int SetParamsImpl(t41rx_ctx *ctx, int first, int count, const t41rx_param
       const int32_t z = 0;
       CUDA_TRY(cudaMemcpy(&ctx->d_state[s].zoom_ptr, &z, sizeof(z), cudaMemcpyHostToDevice));
     }
+    if (patch.clear_fast_native) {
+      const int32_t z = 0;
+      CUDA_TRY(cudaMemcpy(&ctx->d_state[s].fast_native, &z, sizeof(z), cudaMemcpyHostToDevice));
+    }
   }
+  ctx->ids_dirty = true;
   CUDA_TRY(cudaMemcpy(ctx->d_cfg + first, ctx->host.cfg.data() + first, sizeof(StreamCfg) * count, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(ctx->d_nco_tab + (size_t)192 * first, ctx->host.nco_tab.data() + (size_t)192 * first,
                       sizeof(double) * 192 * count, cudaMemcpyHostToDevice));
@@ -417,19 +459,50 @@ int t41rx_process_device(t41rx_ctx *ctx, const float *iq, float *audio, int n_bl
   a.n_rows = row_every > 0 ? (n_blocks + row_every - 1) / row_every : 0;
   a.flags = flags;
   /* kernel choice: the throughput kernel unless the caller asks for the bit-exact oscillator or the
-     phase-structured kernel, or the launch has row-producing blocks (display spectrum: phased kernel) */
-  const bool phased = (flags & (T41RX_FLAG_EXACT_NCO | T41RX_FLAG_PHASED_KERNEL)) != 0 || row_every > 0;
+     phase-structured kernel; SAM receivers always take the phase-structured kernel (see t41rx_ctx) */
+  const bool all_phased = (flags & (T41RX_FLAG_EXACT_NCO | T41RX_FLAG_PHASED_KERNEL)) != 0;
+  if (!all_phased && ctx->ids_dirty) {
+    ctx->h_fast_ids.clear();
+    ctx->h_phased_ids.clear();
+    for (int s = 0; s < ctx->n_streams; ++s)
+      (ctx->host.cfg[s].mode == kModeSam ? ctx->h_phased_ids : ctx->h_fast_ids).push_back(s);
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (!ctx->h_fast_ids.empty())
+      CUDA_TRY(cudaMemcpy(ctx->d_fast_ids, ctx->h_fast_ids.data(), sizeof(int32_t) * ctx->h_fast_ids.size(), cudaMemcpyHostToDevice));
+    if (!ctx->h_phased_ids.empty())
+      CUDA_TRY(cudaMemcpy(ctx->d_phased_ids, ctx->h_phased_ids.data(), sizeof(int32_t) * ctx->h_phased_ids.size(), cudaMemcpyHostToDevice));
+    ctx->ids_dirty = false;
+  }
   CUDA_TRY(cudaEventRecord(ctx->ev0, st));
-  if (phased) {
+  if (all_phased) {
     const int grid = (ctx->n_streams + kG - 1) / kG;
     t41rx_fused_rx_kernel<<<grid, kNT, kSmemFloats * sizeof(float), st>>>(a);
     CUDA_TRY(cudaGetLastError());
+    ctx->launches += 1;
   } else {
-    CUDA_TRY(LaunchStreamKernel(a, ctx->n_sms, st));
+    if (!ctx->h_phased_ids.empty()) {
+      LaunchArgs p = a;
+      p.n_streams = (int)ctx->h_phased_ids.size();
+      p.stream_ids = ctx->d_phased_ids;
+      t41rx_fused_rx_kernel<<<(p.n_streams + kG - 1) / kG, kNT, kSmemFloats * sizeof(float), st>>>(p);
+      CUDA_TRY(cudaGetLastError());
+      ctx->launches += 1;
+    }
+    if (!ctx->h_fast_ids.empty()) {
+      LaunchArgs f = a;
+      f.n_streams = (int)ctx->h_fast_ids.size();
+      f.stream_ids = ctx->h_phased_ids.empty() ? nullptr : ctx->d_fast_ids;
+      if (row_every > 0 && (a.spec_rows || a.wf_rows)) {
+        t41rx_rows_kernel<<<(f.n_streams + kG - 1) / kG, kNT, kSmemFloats * sizeof(float), st>>>(f);
+        CUDA_TRY(cudaGetLastError());
+        ctx->launches += 1;
+      }
+      CUDA_TRY(LaunchStreamKernel(f, ctx->n_sms, st));
+      ctx->launches += 1;
+    }
   }
   CUDA_TRY(cudaEventRecord(ctx->ev1, st));
   ctx->ev_valid = true;
-  ctx->launches += 1;
   return T41RX_OK;
 }
 

@@ -10,7 +10,7 @@
 
 namespace t41rx {
 
-__global__ void __launch_bounds__(32 * (fast::kFastMaxG + 1), 1) t41rx_stream_rx_kernel(const LaunchArgs a, const int G) {
+__global__ void __launch_bounds__(64 * fast::kFastMaxG + 32, 1) t41rx_stream_rx_kernel(const LaunchArgs a, const int G) {
   extern __shared__ __align__(16) float smem[];
   fast::StreamKernelBody(a, G, smem);
 }
@@ -40,7 +40,7 @@ cudaError_t LaunchStreamKernel(const LaunchArgs &a, int n_sms, cudaStream_t st) 
   if (G < 1) G = 1;
   if (G > fast::kFastMaxG) G = fast::kFastMaxG;
   const int grid = (a.n_streams + G - 1) / G;
-  t41rx_stream_rx_kernel<<<grid, 32 * (G + 1), (size_t)G * fast::kSlotF * sizeof(float), st>>>(a, G);
+  t41rx_stream_rx_kernel<<<grid, 64 * G + 32, (size_t)G * fast::kSlotF * sizeof(float), st>>>(a, G);
   return cudaGetLastError();
 }
 

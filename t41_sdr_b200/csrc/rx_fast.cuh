@@ -4,10 +4,10 @@
  * Same chain as rx_phases.cuh (ProcessIQData(), reference Process.cpp:70-944), same HBM state
  * (StreamState) and tables, different mapping:
  *   - one CTA owns G <= kFastMaxG receivers for all n_blocks blocks of a launch;
- *   - ONE WARP PER RECEIVER runs every sample-parallel stage (only __syncwarp inside a block);
+ *   - TWO WARPS PER RECEIVER run every sample-parallel stage (64-thread named barriers between stages);
  *   - one extra warp runs the AGC envelope state machine with lane = receiver;
- *   - blocks are software-pipelined with one __syncthreads per block: in superstep k a receiver
- *     warp does back end(k-2) then front end(k), the AGC warp does AGC(k-1).
+ *   - blocks are software-pipelined with one __syncthreads per block: in superstep k a receiver's
+ *     warp pair does back end(k-2) then front end(k), the AGC warp does AGC(k-1).
  * Linear recurrences (DC block, AM detector filters) are blocked scans, the NCO is a closed-form
  * FP32 phasor driven by an FP64 block phasor, the fast-convolution filter fuses the last forward
  * FFT pass, the mask multiply and the first inverse pass in registers.  FP32 with FMA contraction:
@@ -25,12 +25,12 @@
 namespace t41rx {
 namespace fast {
 
-constexpr int kFastMaxG = 7;          /* receivers per CTA (shared memory: 7 x 31.5 KB) */
+constexpr int kFastMaxG = 7;          /* receivers per CTA (shared memory: 7 x 31.7 KB) */
 constexpr unsigned kFull = 0xffffffffu;
 
 /* ---- per-receiver shared-memory slot, in 4-byte words ---- */
-constexpr int kRawChunkWords = 36;                    /* 16 samples (32 words) + 4 pad: conflict-free LDS.128 */
-constexpr int kRawBufWords = 32 * kRawChunkWords;     /* one 512-sample quarter: 1152 */
+constexpr int kRawChunkWords = 20;                    /* 8 samples (16 words) + 4 pad: conflict-free LDS.128 */
+constexpr int kRawBufWords = 64 * kRawChunkWords;     /* one 512-sample quarter: 1280 */
 constexpr int oRaw = 0;                               /* 2 quarter buffers */
 constexpr int oMix = oRaw + 2 * kRawBufWords;         /* 2304: mixed samples, 8 planes (ch, phase) x 136; FFT buffer overlay */
 constexpr int kMixPlane = 136;                        /* 8 history + 128 */
@@ -40,16 +40,19 @@ constexpr int kD1Plane = 280;                         /* 24 history + 256 */
 constexpr int kD1Words = 1152;
 constexpr int oOlaF = oD1 + kD1Words;                 /* 4608: previous 256 complex filter inputs (interleaved) */
 constexpr int oStA = oOlaF + 512;                     /* 5120: 2 x (|z| delayed [256], window max -> volts [256]) */
-constexpr int oStZ = oStA + 1024;                     /* 6144: 2 x 256 complex: delayed filter output */
-constexpr int oZH = oStZ + 1024;                      /* 7168: last 97 complex filter outputs */
-constexpr int oAH = oZH + 196;                        /* 7364: last 97 |z| */
-constexpr int oTapsF = oAH + 100;                     /* 7464: dec1 28 | dec2 46 | int1 48 | int2 32 (+2) */
-constexpr int oNcoW = oTapsF + 156;                   /* 7620: W[16] float2, Q[4] float2 */
+constexpr int kStABuf = 576;                          /* |z| delayed [256] | window max -> volts [256] | (PF, PH)[32] */
+constexpr int oStZ = oStA + 2 * kStABuf;                     /* 6144: 2 x 256 complex: delayed filter output */
+constexpr int kStZBuf = 576;                          /* 256 complex, 2 pad words after every 8 (ZPos) */
+constexpr int oZH = oStZ + 2 * kStZBuf;                      /* 7168: last 97 complex filter outputs */
+constexpr int oTapsF = oZH + 196;                     /* 7464: dec1 28 | dec2 46 | int1 48 | int2 32 (+2) */
+constexpr int oNcoW = oTapsF + 156;                   /* 7620: W[8] float2, Q[4] float2 */
 constexpr int oIH = oNcoW + 40;                       /* 7660: int1 history 23 (24) | int2 history 7 (8) */
 constexpr int oMH = oIH + 32;                         /* 7692: dec1 history, 8 planes x 8 */
 constexpr int oDH = oMH + 64;                         /* 7756: dec2 history, 4 planes x 24 */
 constexpr int oMiscF = oDH + 96;                      /* 7852 */
-constexpr int kSlotF = oMiscF + 16;                   /* 7868 == 4 (mod 8): the AGC warp's LDS.128 hit distinct banks */
+constexpr int kSlotF = oMiscF + 20;                   /* == 4 (mod 8): the AGC warp's LDS.128 hit distinct banks */
+enum { mEndI = 0, mEndQ = 1, mSettled = 2, mPhasor = 4 /* 2 doubles */ };
+static_assert((oMiscF % 2) == 0 && (oTapsF % 4) == 0, "alignment");
 static_assert(kSlotF % 8 == 4, "slot stride");
 static_assert((oStA % 4) == 0 && (oStZ % 4) == 0 && (oRaw % 4) == 0 && (oMix % 4) == 0 && (oD1 % 4) == 0, "16-byte alignment");
 
@@ -57,7 +60,8 @@ static_assert((oStA % 4) == 0 && (oStZ % 4) == 0 && (oRaw % 4) == 0 && (oMix % 4
 constexpr int vE = oD1;                               /* |z| extended: 97 history + 256 new (360) */
 constexpr int vSfx = vE + 360;                        /* suffix maxima inside chunks of 8 */
 constexpr int vPfx = vSfx + 360;                      /* prefix maxima */
-constexpr int vCM = vPfx + 360;                       /* chunk maxima (45 -> 48) then 11-chunk window maxima */
+constexpr int vCM = vPfx + 360;                       /* chunk maxima (45 -> 48) */
+constexpr int vF = vE;                                /* 11-chunk window maxima (36), over |z| once it is consumed */
 static_assert(vCM + 48 <= oD1 + kD1Words, "sliding max scratch");
 /* overlays on the dec1 region in the back end */
 constexpr int vAudF = oD1;                            /* 24 (1 pad + 23 history) + 256 demodulated samples */
@@ -66,6 +70,11 @@ static_assert(vI1 + 520 <= oD1 + kD1Words, "back-end scratch");
 
 /* the 512-point FFT buffer: element i lives at float2 index i + (i >> 3) */
 __device__ __forceinline__ int FPos(int i) { return i + (i >> 3); }
+/* staged filter output: complex sample i lives at float2 index i + (i >> 3) (8 contiguous samples per lane
+   and stride-1 lanes are both conflict-free) */
+__device__ __forceinline__ int ZPos(int i) { return i + (i >> 3); }
+/* overlap-save history of channel ch: sample i at word (i & 7) * 32 + (i >> 3): lane L owns samples 8 L .. 8 L + 7 */
+__device__ __forceinline__ int OlaW(int ch, int i) { return oOlaF + ch * 256 + (i & 7) * 32 + (i >> 3); }
 
 constexpr float kDcA1 = 0.854352383886757938f;        /* FIR.cpp:87-89 */
 constexpr float kDcB0 = 0.927176191943378969f;
@@ -121,7 +130,6 @@ struct RxRegs {
   float in_gain;         /* rfGainValue * b0 * 1.1 (DC-block numerator and freqAdjFactor folded) */
   float neg_iq_amp, iq_phase, vol_scale, volume, fixed_gain;
   /* state */
-  float dc_w;            /* DC-block recurrence value after the last Q sample (B6: feeds the next block's I) */
   int rf_gain;
   unsigned codec_timer;
   int first_block;
@@ -129,13 +137,26 @@ struct RxRegs {
   int nco_closed;
   double osc_q, osc_i;   /* Osc_Vect while the amplitude loop is still settling (lane 0) */
   /* lane constants */
-  F2 lane_rot;           /* nco_amp * exp(-j * delta * (16 * lane + 1)) */
+  F2 lane_rot;           /* nco_amp * exp(-j * delta * (8 * tau + 1)) */
   float tail_w;          /* a1^(4 * lane): weight of this lane's partial sum in the I-tail pre-read */
 };
 
 /* ------------------------------------------------------------------ */
 /* radix-8 passes on the padded buffer                                  */
 /* ------------------------------------------------------------------ */
+/* w[k] = (cos, sin)(2 pi k e / 512), k = 1..7, from one table entry and six complex products (shared
+   memory and L1 bandwidth is the scarce resource of this kernel, FMAs are not) */
+__device__ __forceinline__ void TwiddlePowers(const float2 *tw, int e, F2 (&w)[8]) {
+  const float2 t = __ldg(tw + e);
+  w[1] = F2{t.x, t.y};
+  w[2] = CMul(w[1], w[1]);
+  w[3] = CMul(w[2], w[1]);
+  w[4] = CMul(w[2], w[2]);
+  w[5] = CMul(w[4], w[1]);
+  w[6] = CMul(w[3], w[3]);
+  w[7] = CMul(w[4], w[3]);
+}
+
 template <int PASS>
 __device__ __forceinline__ void FwdPass(float2 *buf, const float2 *tw, int b) {
   int n2, j, i0, stride;
@@ -150,11 +171,11 @@ __device__ __forceinline__ void FwdPass(float2 *buf, const float2 *tw, int b) {
   }
   Dft8(r, im);
   buf[FPos(i0)] = float2{r[0], im[0]};
+  F2 w[8];
+  TwiddlePowers(tw, j * stride, w);
 #pragma unroll
-  for (int k = 1; k < 8; ++k) {
-    const float2 w = __ldg(tw + j * k * stride);
-    buf[FPos(i0 + k * n2)] = float2{r[k] * w.x + im[k] * w.y, im[k] * w.x - r[k] * w.y};
-  }
+  for (int k = 1; k < 8; ++k)
+    buf[FPos(i0 + k * n2)] = float2{r[k] * w[k].x + im[k] * w[k].y, im[k] * w[k].x - r[k] * w[k].y};
 }
 
 /* inverse of FwdPass<PASS> without the 1/8: conjugate twiddles on the inputs, inverse 8-point DFT.
@@ -170,12 +191,13 @@ __device__ __forceinline__ void InvPass(float2 *buf, const float2 *tw, int b) {
     r[0] = x.x;
     im[0] = x.y;
   }
+  F2 w[8];
+  TwiddlePowers(tw, j * stride, w);
 #pragma unroll
   for (int k = 1; k < 8; ++k) {
     const float2 x = buf[FPos(i0 + k * n2)];
-    const float2 w = __ldg(tw + j * k * stride);
-    r[k] = x.x * w.x - x.y * w.y;
-    im[k] = x.y * w.x + x.x * w.y;
+    r[k] = x.x * w[k].x - x.y * w[k].y;
+    im[k] = x.y * w[k].x + x.x * w[k].y;
   }
   Dft8(im, r);   /* swapping the roles of re and im turns the forward DFT into the inverse */
 #pragma unroll
@@ -207,31 +229,40 @@ __device__ __forceinline__ void MidPass(float2 *buf, const float2 *mask, int b) 
 }
 
 /* ------------------------------------------------------------------ */
-/* receiver warp                                                        */
+/* receiver pair: two warps (64 threads) per receiver                   */
 /* ------------------------------------------------------------------ */
-struct RxWarp {
+struct RxPair {
   const LaunchArgs &a;
   float *s;          /* this receiver's slot */
   int sid;           /* receiver index */
-  int lane;
+  int lane;          /* lane in the warp */
+  int w2;            /* warp in the pair: 0 / 1 (also: the channel I / Q it owns in the FIR stages) */
+  int tau;           /* thread in the pair: 0..63 */
+  int bar_id;        /* named barrier of the pair */
   RxRegs r;
   SectionTimer tm;
-  float tap1[kDec1Taps];   /* dec1 taps live in registers for the whole launch */
 
-  __device__ __forceinline__ RxWarp(const LaunchArgs &a_, float *s_, int sid_, int lane_) : a(a_), s(s_), sid(sid_), lane(lane_) {}
+  __device__ __forceinline__ RxPair(const LaunchArgs &a_, float *s_, int sid_, int lane_, int w2_, int bar_)
+      : a(a_), s(s_), sid(sid_), lane(lane_), w2(w2_), tau(32 * w2_ + lane_), bar_id(bar_) {}
+
+  __device__ __forceinline__ void PairSync() const {
+    asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+  }
 
   __device__ __forceinline__ const float *BlockIq(int t) const {
     return a.iq + ((size_t)sid * a.n_blocks + t) * (2 * kBlock);
   }
 
-  /* issue the asynchronous copy of quarter q of block t into raw buffer (q & 1) */
+  /* issue this thread's share of the asynchronous copy of quarter q of block t into raw buffer (q & 1) */
   __device__ __forceinline__ void IssueQuarter(int t, int q) {
     const char *src = reinterpret_cast<const char *>(BlockIq(t)) + q * 4096;
     char *dst = reinterpret_cast<char *>(s + oRaw + (q & 1) * kRawBufWords);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int p = 32 * i + lane;              /* 16-byte piece: coalesced 512 B per instruction */
-      CpAsync16(dst + (p >> 3) * (kRawChunkWords * 4) + (p & 7) * 16, src + 16 * p);
+    for (int i = 0; i < 4; ++i) {
+      /* one warp instruction copies 8 chunks (512 contiguous bytes); the 8 lanes of a quarter-warp write the
+         same 16-byte piece of 8 different chunks: distinct banks (chunk stride 20 words) */
+      const int chunk = 16 * i + 8 * w2 + (lane & 7), piece = lane >> 3;
+      CpAsync16(dst + chunk * (kRawChunkWords * 4) + piece * 16, src + chunk * 64 + piece * 16);
     }
     CpAsyncCommit();
   }
@@ -250,7 +281,6 @@ struct RxWarp {
     r.vol_scale = cf.vol_scale;
     r.volume = cf.volume;
     r.fixed_gain = cf.agc.fixed_gain;
-    r.dc_w = st.dc_d1 / (kDcB0 * (kDcA1 - 1.0f) * cf.rf_gain_value);
     r.rf_gain = st.rf_gain;
     r.codec_timer = st.codec_timer;
     r.first_block = st.first_block;
@@ -258,6 +288,10 @@ struct RxWarp {
     {
       double sn, cs;
       sincos(st.nco_phase, &sn, &cs);
+      if (st.fast_native && r.nco_closed) {
+        cs = st.fast_ph_re;
+        sn = st.fast_ph_im;
+      }
       r.ph_re = cs;
       r.ph_im = sn;
       if (st.nco_closed) {       /* leaving closed form (retune): rebuild the vector at the settled radius */
@@ -271,12 +305,16 @@ struct RxWarp {
     }
     {
       double sn, cs;
-      sincos(-cf.nco_delta * (double)(16 * lane + 1), &sn, &cs);
+      sincos(-cf.nco_delta * (double)(8 * tau + 1), &sn, &cs);
       r.lane_rot = F2{(float)(cf.nco_amp * cs), (float)(cf.nco_amp * sn)};
     }
     r.tail_w = PowA1(4 * lane);
-    /* taps */
-    for (int i = lane; i < 154; i += 32) {
+    /* DC-block recurrence value after the previous block's last Q sample (feeds this block's I chain, B6) */
+    if (tau == 0) {
+      s[oMiscF + mEndQ] = st.fast_native ? st.fast_dc_w : st.dc_d1 / (kDcB0 * (kDcA1 - 1.0f) * cf.rf_gain_value);
+      s[oMiscF + mEndI] = 0.0f;
+    }
+    for (int i = tau; i < 154; i += 64) {
       float v;
       if (i < 28) v = fs.dec1[i];
       else if (i < 74) v = fs.dec2[i - 28];
@@ -284,79 +322,81 @@ struct RxWarp {
       else v = fs.int2[i - 122];
       s[oTapsF + i] = v;
     }
-    /* oscillator tables: W[j] = j^j * exp(-j delta j) (Fs/4 shift folded), Q[q] = exp(-j delta 512 q) */
-    if (lane < 20) {
-      const int n = lane < 16 ? lane : 512 * (lane - 16);
+    /* oscillator tables: W[j] = j^j * exp(-j delta j), j < 8 (Fs/4 shift folded); Q[q] = exp(-j delta 512 q) */
+    if (tau < 12) {
+      const int n = tau < 8 ? tau : 512 * (tau - 8);
       double sn, cs;
       sincos(-cf.nco_delta * (double)n, &sn, &cs);
       float wr = (float)cs, wi = (float)sn;
-      if (lane < 16) {
-        const int k = lane & 3;              /* multiply by j^k */
+      if (tau < 8) {
+        const int k = tau & 3;               /* multiply by j^k */
         const float a0 = wr, b0 = wi;
         if (k == 1) { wr = -b0; wi = a0; }
         else if (k == 2) { wr = -a0; wi = -b0; }
         else if (k == 3) { wr = b0; wi = -a0; }
       }
-      s[oNcoW + 2 * lane] = wr;
-      s[oNcoW + 2 * lane + 1] = wi;
+      s[oNcoW + 2 * tau] = wr;
+      s[oNcoW + 2 * tau + 1] = wi;
     }
     /* histories */
-    for (int i = lane; i < 64; i += 32) {       /* dec1: plane (ch, p) entry e = -8..-1 holds sample 4 e + p */
+    {                                            /* dec1: plane (ch, p) entry e = -8..-1 holds sample 4 e + p */
+      const int i = tau;
       const int pl = i >> 3, e = (i & 7) - 8;
       const int ch = pl >> 2, p = pl & 3;
-      const int n = 4 * e + p;                  /* -32 .. -1 */
+      const int n = 4 * e + p;                   /* -32 .. -1 */
       s[oMH + i] = (n >= -(kDec1Taps - 1)) ? st.dec1_hist[ch][n + (kDec1Taps - 1)] : 0.0f;
     }
-    for (int i = lane; i < 96; i += 32) {       /* dec2: plane (ch, par) entry e = -24..-1 holds sample 2 e + par */
+    for (int i = tau; i < 96; i += 64) {         /* dec2: plane (ch, par) entry e = -24..-1 holds sample 2 e + par */
       const int pl = i / 24, e = (i % 24) - 24;
       const int ch = pl >> 1, par = pl & 1;
       const int n = 2 * e + par;
       s[oDH + i] = (n >= -(kDec2Taps - 1)) ? st.dec2_hist[ch][n + (kDec2Taps - 1)] : 0.0f;
     }
-    for (int i = lane; i < 256; i += 32) {
-      s[oOlaF + 2 * i] = st.ola_prev[0][i];
-      s[oOlaF + 2 * i + 1] = st.ola_prev[1][i];
+    for (int i = tau; i < 256; i += 64) {
+      s[OlaW(0, i)] = st.ola_prev[0][i];
+      s[OlaW(1, i)] = st.ola_prev[1][i];
     }
-    for (int i = lane; i < kAgcDelay; i += 32) {     /* sample -(97 - i) sits at ring index 31 + i */
+    for (int i = tau; i < kAgcDelay; i += 64) {  /* sample -(97 - i) sits at ring index 31 + i */
       s[oZH + 2 * i] = st.agc_re[31 + i];
       s[oZH + 2 * i + 1] = st.agc_im[31 + i];
-      s[oAH + i] = st.agc_abs[31 + i];
     }
-    if (lane < 23) s[oIH + lane] = st.int1_hist[lane];
-    if (lane < 7) s[oIH + 24 + lane] = st.int2_hist[lane];
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < kDec1Taps; ++i) tap1[i] = s[oTapsF + i];
+    if (tau < 23) s[oIH + tau] = st.int1_hist[tau];
+    if (tau < 7) s[oIH + 24 + tau] = st.int2_hist[tau];
+    PairSync();
   }
 
   __device__ void StoreState() {
     StreamState &st = a.st[sid];
     const StreamCfg &cf = a.cfg[sid];
-    __syncwarp();
-    for (int i = lane; i < 2 * (kDec1Taps - 1); i += 32) {
+    PairSync();
+    for (int i = tau; i < 2 * (kDec1Taps - 1); i += 64) {
       const int ch = i / (kDec1Taps - 1), n = (i % (kDec1Taps - 1)) - (kDec1Taps - 1);   /* -27..-1 */
       const int p = n & 3, e = (n - p) / 4;                                              /* e = -7..-1 */
       st.dec1_hist[ch][n + (kDec1Taps - 1)] = s[oMH + (ch * 4 + p) * 8 + (e + 8)];
     }
-    for (int i = lane; i < 2 * (kDec2Taps - 1); i += 32) {
+    for (int i = tau; i < 2 * (kDec2Taps - 1); i += 64) {
       const int ch = i / (kDec2Taps - 1), n = (i % (kDec2Taps - 1)) - (kDec2Taps - 1);   /* -45..-1 */
       const int par = n & 1, e = (n - par) / 2;                                          /* e = -23..-1 */
       st.dec2_hist[ch][n + (kDec2Taps - 1)] = s[oDH + (ch * 2 + par) * 24 + (e + 24)];
     }
-    for (int i = lane; i < 256; i += 32) {
-      st.ola_prev[0][i] = s[oOlaF + 2 * i];
-      st.ola_prev[1][i] = s[oOlaF + 2 * i + 1];
+    for (int i = tau; i < 256; i += 64) {
+      st.ola_prev[0][i] = s[OlaW(0, i)];
+      st.ola_prev[1][i] = s[OlaW(1, i)];
     }
-    for (int i = lane; i < kAgcDelay; i += 32) {
+    for (int i = tau; i < kAgcDelay; i += 64) {
       st.agc_re[31 + i] = s[oZH + 2 * i];
       st.agc_im[31 + i] = s[oZH + 2 * i + 1];
-      st.agc_abs[31 + i] = s[oAH + i];
+      st.agc_abs[31 + i] = __fsqrt_rn(s[oZH + 2 * i] * s[oZH + 2 * i] + s[oZH + 2 * i + 1] * s[oZH + 2 * i + 1]);
     }
-    if (lane < 23) st.int1_hist[lane] = s[oIH + lane];
-    if (lane < 7) st.int2_hist[lane] = s[oIH + 24 + lane];
-    if (lane == 0) {
-      st.dc_d1 = r.dc_w * (kDcB0 * (kDcA1 - 1.0f) * cf.rf_gain_value);
+    if (tau < 23) st.int1_hist[tau] = s[oIH + tau];
+    if (tau < 7) st.int2_hist[tau] = s[oIH + 24 + tau];
+    if (tau == 0) {
+      st.dc_d1 = s[oMiscF + mEndQ] * (kDcB0 * (kDcA1 - 1.0f) * cf.rf_gain_value);
       st.dc_d2 = 0.0f;
+      st.fast_native = 1;
+      st.fast_dc_w = s[oMiscF + mEndQ];
+      st.fast_ph_re = r.ph_re;
+      st.fast_ph_im = r.ph_im;
       st.rf_gain = r.rf_gain;
       st.codec_timer = r.codec_timer;
       st.first_block = r.first_block;
@@ -380,62 +420,88 @@ struct RxWarp {
   }
 
   /* ---------------- front end ---------------- */
-  /* blocked inclusive scan over the lanes of chunk-end values of the recurrence w <- a1 w + x
-     (16 samples per lane): after it, lane L holds the true w at the end of its chunk */
+  /* blocked inclusive scan over the lanes of a warp of chunk-end values of the recurrence w <- a1 w + x
+     (8 samples per lane): after it, lane L holds the true w at the end of its chunk */
   __device__ __forceinline__ float ScanDc(float e) const {
-    const float m1 = PowConst16(), m2 = m1 * m1, m4 = m2 * m2, m8 = m4 * m4;
+    float m = kDcA1;
+    m *= m; m *= m; m *= m;            /* a1^8 */
     float v = e, t;
-    t = __shfl_up_sync(kFull, v, 1); if (lane >= 1) v = fmaf(m1, t, v);
-    t = __shfl_up_sync(kFull, v, 2); if (lane >= 2) v = fmaf(m2, t, v);
-    t = __shfl_up_sync(kFull, v, 4); if (lane >= 4) v = fmaf(m4, t, v);
-    t = __shfl_up_sync(kFull, v, 8); if (lane >= 8) v = fmaf(m8, t, v);
-    /* a1^256 ~ 3e-18: the 16-lane step is below any float's resolution */
+    t = __shfl_up_sync(kFull, v, 1); if (lane >= 1) v = fmaf(m, t, v);
+    m *= m;
+    t = __shfl_up_sync(kFull, v, 2); if (lane >= 2) v = fmaf(m, t, v);
+    m *= m;
+    t = __shfl_up_sync(kFull, v, 4); if (lane >= 4) v = fmaf(m, t, v);
+    m *= m;
+    t = __shfl_up_sync(kFull, v, 8); if (lane >= 8) v = fmaf(m, t, v);
+    /* a1^128 ~ 2e-9: the 16-lane step is below a float's resolution */
     return v;
   }
-  static __device__ __forceinline__ float PowConst16() {
-    float p = kDcA1;        /* a1^16 by four squarings (compile-time folded) */
-    p *= p; p *= p; p *= p; p *= p;
-    return p;
+
+  /* recurrence values (I, Q) at the end of the 128 samples that end just before word offset `end_word`
+     of a padded raw buffer, from zero state (a1^128 ~ 2e-9): 4 samples per lane, weighted reduction */
+  __device__ __forceinline__ void TailFromRaw(const float *rawbuf, int first_chunk, float &ti, float &tq) const {
+    /* lane L covers samples 4 L .. 4 L + 3 of the 128: chunk first_chunk + (L >> 1), half (L & 1) */
+    const float *p = rawbuf + (first_chunk + (lane >> 1)) * kRawChunkWords + (lane & 1) * 8;
+    const float4 u = *reinterpret_cast<const float4 *>(p), v = *reinterpret_cast<const float4 *>(p + 4);
+    float ai = u.x, aq = u.y;
+    ai = fmaf(kDcA1, ai, u.z); aq = fmaf(kDcA1, aq, u.w);
+    ai = fmaf(kDcA1, ai, v.x); aq = fmaf(kDcA1, aq, v.y);
+    ai = fmaf(kDcA1, ai, v.z); aq = fmaf(kDcA1, aq, v.w);
+    const float wgt = __shfl_sync(kFull, r.tail_w, 31 - lane);      /* a1^(4 (31 - L)) */
+    ai *= wgt;
+    aq *= wgt;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+      ai += __shfl_xor_sync(kFull, ai, d);
+      aq += __shfl_xor_sync(kFull, aq, d);
+    }
+    ti = ai;
+    tq = aq;
   }
 
-  /* one 512-sample quarter: DC block + IQ correction + Fs/4 + NCO mix -> phase planes; dec1 -> d1 planes.
-     cI / cQ: recurrence values entering the quarter (updated).  base: conj(block phasor) * Q[q] * gain. */
+  /* one 512-sample quarter, 8 samples per thread: DC block + IQ correction + Fs/4 + NCO mix -> phase planes.
+     cI / cQ: recurrence values entering the quarter (used by warp 0).  base: conj(block phasor) * Q[q] * gain. */
   template <bool kTable>
-  __device__ __forceinline__ void Quarter(int q, float &cI, float &cQ, F2 base, const float2 *osc) {
-    const float *raw = s + oRaw + (q & 1) * kRawBufWords + lane * kRawChunkWords;
-    float xi[16], xq[16];
+  __device__ __forceinline__ void QuarterMix(int q, float cI, float cQ, F2 base, const float2 *osc) {
+    const float *rawbuf = s + oRaw + (q & 1) * kRawBufWords;
+    const float *raw = rawbuf + tau * kRawChunkWords;
+    float xi[8], xq[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < 4; ++k) {
       const float4 v = *reinterpret_cast<const float4 *>(raw + 4 * k);
       xi[2 * k] = v.x; xq[2 * k] = v.y; xi[2 * k + 1] = v.z; xq[2 * k + 1] = v.w;
     }
+    /* warp 1 starts from the recurrence value at the end of warp 0's half: recomputed from its last 128 samples */
+    if (w2 == 1) TailFromRaw(rawbuf, 16, cI, cQ);
     /* zero-state recurrences (two independent chains) */
-    float wi[16], wq[16];
+    float wi[8], wq[8];
     {
       float ai = 0.0f, aq = 0.0f;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
+      for (int j = 0; j < 8; ++j) {
         ai = fmaf(kDcA1, ai, xi[j]);
         aq = fmaf(kDcA1, aq, xq[j]);
         wi[j] = ai;
         wq[j] = aq;
       }
     }
-    /* carries: the value entering the quarter is folded into lane 0's chunk end */
-    const float p16 = PowConst16();
-    float ei = wi[15], eq = wq[15];
-    if (lane == 0) { ei = fmaf(p16, cI, ei); eq = fmaf(p16, cQ, eq); }
+    float p8 = kDcA1;
+    p8 *= p8; p8 *= p8; p8 *= p8;
+    float ei = wi[7], eq = wq[7];
+    if (lane == 0) { ei = fmaf(p8, cI, ei); eq = fmaf(p8, cQ, eq); }
     const float si = ScanDc(ei), sq = ScanDc(eq);
     float ci = __shfl_up_sync(kFull, si, 1), cq = __shfl_up_sync(kFull, sq, 1);
     if (lane == 0) { ci = cI; cq = cQ; }
-    cI = __shfl_sync(kFull, si, 31);
-    cQ = __shfl_sync(kFull, sq, 31);
+    if (tau == 63) {                 /* recurrence values leaving the quarter */
+      s[oMiscF + mEndI] = si;
+      s[oMiscF + mEndQ] = sq;
+    }
     /* true recurrence values, first difference (DC-block numerator 1 - z^-1) */
-    float yi[16], yq[16];
+    float yi[8], yq[8];
     {
       float pw = kDcA1, pi_ = ci, pq_ = cq;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
+      for (int j = 0; j < 8; ++j) {
         const float ti = fmaf(pw, ci, wi[j]);
         const float tq = fmaf(pw, cq, wq[j]);
         yi[j] = ti - pi_;
@@ -448,10 +514,10 @@ struct RxWarp {
     /* I *= -IQAmp, phase correction (Process.cpp:165-174, Utility.cpp:178-187) */
     if (r.mirrored) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) yi[j] *= r.neg_iq_amp;
+      for (int j = 0; j < 8; ++j) yi[j] *= r.neg_iq_amp;
       if (r.iq_phase != 0.0f) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < 8; ++j) {
           if (r.iq_phase < 0.0f) yq[j] = fmaf(yi[j], r.iq_phase, yq[j]);
           else yi[j] = fmaf(yq[j], r.iq_phase, yi[j]);
         }
@@ -460,118 +526,117 @@ struct RxWarp {
     /* mix: multiplier of sample j = base * lane_rot * W[j] */
     const F2 m = CMul(base, r.lane_rot);
     const float4 *wt = reinterpret_cast<const float4 *>(s + oNcoW);
-    float oi[16], oq[16];
+    float oi[8], oq[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < 4; ++k) {
       F2 m0, m1;
       if (kTable) {
         /* settling oscillator: multiplier = gain * conj(osc[n]) * j^n, osc from the step-by-step table */
-        const float4 o2 = *reinterpret_cast<const float4 *>(osc + 16 * lane + 2 * k);
+        const float4 o2 = *reinterpret_cast<const float4 *>(osc + 8 * tau + 2 * k);
         const F2 c0 = F2{o2.x * base.x, -o2.y * base.x}, c1 = F2{o2.z * base.x, -o2.w * base.x};
         m0 = (k & 1) ? F2{-c0.x, -c0.y} : c0;                    /* sample 2k:   j^(2k)   = (-1)^k   */
         m1 = (k & 1) ? F2{c1.y, -c1.x} : F2{-c1.y, c1.x};        /* sample 2k+1: j^(2k+1) = j (-1)^k */
       } else {
-        const float4 w2 = wt[k];
-        m0 = CMul(m, F2{w2.x, w2.y});
-        m1 = CMul(m, F2{w2.z, w2.w});
+        const float4 w2_ = wt[k];
+        m0 = CMul(m, F2{w2_.x, w2_.y});
+        m1 = CMul(m, F2{w2_.z, w2_.w});
       }
       oi[2 * k] = yi[2 * k] * m0.x - yq[2 * k] * m0.y;
       oq[2 * k] = yi[2 * k] * m0.y + yq[2 * k] * m0.x;
       oi[2 * k + 1] = yi[2 * k + 1] * m1.x - yq[2 * k + 1] * m1.y;
       oq[2 * k + 1] = yi[2 * k + 1] * m1.y + yq[2 * k + 1] * m1.x;
     }
-    /* phase planes: sample 16 L + j -> plane (j & 3), entry 4 L + (j >> 2) */
+    /* phase planes: sample 8 tau + j -> plane (j & 3), entry 2 tau + (j >> 2) */
     float *mix = s + oMix;
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
-      *reinterpret_cast<float4 *>(mix + p * kMixPlane + 8 + 4 * lane) = float4{oi[p], oi[4 + p], oi[8 + p], oi[12 + p]};
-      *reinterpret_cast<float4 *>(mix + (4 + p) * kMixPlane + 8 + 4 * lane) = float4{oq[p], oq[4 + p], oq[8 + p], oq[12 + p]};
+      *reinterpret_cast<float2 *>(mix + p * kMixPlane + 8 + 2 * tau) = float2{oi[p], oi[4 + p]};
+      *reinterpret_cast<float2 *>(mix + (4 + p) * kMixPlane + 8 + 2 * tau) = float2{oq[p], oq[4 + p]};
     }
-    __syncwarp();
-    T41RX_LAP(tm, 2);
-    Dec1Quarter(q);
-    T41RX_LAP(tm, 3);
   }
 
-  /* arm_fir_decimate_f32, M = 4, 28 taps (Process.cpp:474-475): 4 outputs per lane per quarter.
-     Output m (quarter-local) = sum_t h[t] x[4 m - 27 + t]; sample 4 m - 27 + t = plane (1 + t) & 3,
-     entry m - 7 + ((1 + t) >> 2). */
+  /* arm_fir_decimate_f32, M = 4, 28 taps (Process.cpp:474-475): warp w2 filters channel w2, 4 outputs per
+     lane per quarter.  Output m (quarter-local) = sum_t h[t] x[4 m - 27 + t]; sample 4 m - 27 + t = plane
+     (1 + t) & 3, entry m - 7 + ((1 + t) >> 2). */
   __device__ __forceinline__ void Dec1Quarter(int q) {
+    const int ch = w2;
     const float *mix = s + oMix;
     float *d1 = s + oD1;
+    float tap[kDec1Taps];
 #pragma unroll
-    for (int ch = 0; ch < 2; ++ch) {
-      float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-      float w[4][12];
-#pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        const float4 *src = reinterpret_cast<const float4 *>(mix + (ch * 4 + p) * kMixPlane + 4 * lane);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const float4 v = src[k];
-          w[p][4 * k] = v.x; w[p][4 * k + 1] = v.y; w[p][4 * k + 2] = v.z; w[p][4 * k + 3] = v.w;
-        }
-      }
-#pragma unroll
-      for (int t = 0; t < kDec1Taps; ++t) {
-        const int p = (1 + t) & 3, off = 1 + ((1 + t) >> 2);
-#pragma unroll
-        for (int o = 0; o < 4; ++o) acc[o] = fmaf(w[p][o + off], tap1[t], acc[o]);
-      }
-      /* d1 sample n = 128 q + 4 L + o -> plane (n & 1), entry n >> 1 */
-      const int e = 64 * q + 2 * lane;
-      *reinterpret_cast<float2 *>(d1 + (ch * 2 + 0) * kD1Plane + 24 + e) = float2{acc[0], acc[2]};
-      *reinterpret_cast<float2 *>(d1 + (ch * 2 + 1) * kD1Plane + 24 + e) = float2{acc[1], acc[3]};
+    for (int k = 0; k < kDec1Taps / 4; ++k) {
+      const float4 v = *reinterpret_cast<const float4 *>(s + oTapsF + 4 * k);
+      tap[4 * k] = v.x; tap[4 * k + 1] = v.y; tap[4 * k + 2] = v.z; tap[4 * k + 3] = v.w;
     }
-    __syncwarp();
-    /* slide the plane histories: entries 120..127 become -8..-1 */
-    for (int i = lane; i < 64; i += 32) {
-      const int pl = i >> 3, e = i & 7;
-      const float v = s[oMix + pl * kMixPlane + 8 + 120 + e];
-      s[oMix + pl * kMixPlane + e] = v;
+    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    float w[4][12];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const float4 *src = reinterpret_cast<const float4 *>(mix + (ch * 4 + p) * kMixPlane + 4 * lane);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float4 v = src[k];
+        w[p][4 * k] = v.x; w[p][4 * k + 1] = v.y; w[p][4 * k + 2] = v.z; w[p][4 * k + 3] = v.w;
+      }
     }
+#pragma unroll
+    for (int t = 0; t < kDec1Taps; ++t) {
+      const int p = (1 + t) & 3, off = 1 + ((1 + t) >> 2);
+#pragma unroll
+      for (int o = 0; o < 4; ++o) acc[o] = fmaf(w[p][o + off], tap[t], acc[o]);
+    }
+    /* d1 sample n = 128 q + 4 L + o -> plane (n & 1), entry n >> 1 */
+    const int e = 64 * q + 2 * lane;
+    *reinterpret_cast<float2 *>(d1 + (ch * 2 + 0) * kD1Plane + 24 + e) = float2{acc[0], acc[2]};
+    *reinterpret_cast<float2 *>(d1 + (ch * 2 + 1) * kD1Plane + 24 + e) = float2{acc[1], acc[3]};
     __syncwarp();
+    /* slide this channel's plane histories: entries 120..127 become -8..-1 (one value per lane) */
+    {
+      const int pl = ch * 4 + (lane >> 3), e8 = lane & 7;
+      const float v = s[oMix + pl * kMixPlane + 8 + 120 + e8];
+      __syncwarp();
+      s[oMix + pl * kMixPlane + e8] = v;
+    }
   }
 
-  /* arm_fir_decimate_f32, M = 2, 46 taps (Process.cpp:478-479): 8 outputs per lane.
+  /* arm_fir_decimate_f32, M = 2, 46 taps (Process.cpp:478-479): warp w2 filters channel w2, 8 outputs per lane.
      Output o = sum_t h[t] d[2 o - 45 + t]; sample 2 o - 45 + t = plane (1 + t) & 1, entry o - 23 + ((1 + t) >> 1). */
-  __device__ __forceinline__ void Dec2(float (&out)[2][8]) {
+  __device__ __forceinline__ void Dec2(float (&out)[8]) {
+    const int ch = w2;
     const float *d1 = s + oD1;
     const float *tp = s + oTapsF + 28;
+    float w[2][32];
 #pragma unroll
-    for (int ch = 0; ch < 2; ++ch) {
-      float w[2][32];
+    for (int par = 0; par < 2; ++par) {
+      const float4 *src = reinterpret_cast<const float4 *>(d1 + (ch * 2 + par) * kD1Plane + 8 * lane);
 #pragma unroll
-      for (int par = 0; par < 2; ++par) {
-        const float4 *src = reinterpret_cast<const float4 *>(d1 + (ch * 2 + par) * kD1Plane + 8 * lane);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float4 v = src[k];
-          w[par][4 * k] = v.x; w[par][4 * k + 1] = v.y; w[par][4 * k + 2] = v.z; w[par][4 * k + 3] = v.w;
-        }
+      for (int k = 0; k < 8; ++k) {
+        const float4 v = src[k];
+        w[par][4 * k] = v.x; w[par][4 * k + 1] = v.y; w[par][4 * k + 2] = v.z; w[par][4 * k + 3] = v.w;
       }
-      float acc[8];
+    }
 #pragma unroll
-      for (int o = 0; o < 8; ++o) acc[o] = 0.0f;
+    for (int o = 0; o < 8; ++o) out[o] = 0.0f;
 #pragma unroll
-      for (int t = 0; t < kDec2Taps; ++t) {
-        const float h = tp[t];
+    for (int t2 = 0; t2 < kDec2Taps; t2 += 2) {
+      const float2 h = *reinterpret_cast<const float2 *>(tp + t2);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int t = t2 + u;
         const int par = (1 + t) & 1, off = 1 + ((1 + t) >> 1);
 #pragma unroll
-        for (int o = 0; o < 8; ++o) acc[o] = fmaf(w[par][o + off], h, acc[o]);
+        for (int o = 0; o < 8; ++o) out[o] = fmaf(w[par][o + off], u ? h.y : h.x, out[o]);
       }
-#pragma unroll
-      for (int o = 0; o < 8; ++o) out[ch][o] = acc[o];
     }
   }
 
-  /* FE for block t.  row blocks and oscillator transients are handled by the caller. */
+  /* FE for block t */
   __device__ void FrontEnd(int t, int buf) {
     const StreamCfg &cf = a.cfg[sid];
     /* the recurrence value entering the Q chain is the one leaving the I chain (B6): pre-read the last
-       128 I samples of the block (a1^128 ~ 2e-9) */
-    float tail;
-    {
+       128 I samples of the block (a1^128 ~ 2e-9); only warp 0's lane 0 consumes it */
+    float tail = 0.0f;
+    if (w2 == 0) {
       const float4 *p = reinterpret_cast<const float4 *>(BlockIq(t) + 2 * (kBlock - 4 * (lane + 1)));
       const float4 u = __ldg(p), v = __ldg(p + 1);    /* samples n0 .. n0+3, n0 = 2044 - 4 lane */
       float acc = u.x;                                 /* oldest first */
@@ -582,42 +647,42 @@ struct RxWarp {
 #pragma unroll
       for (int d = 16; d >= 1; d >>= 1) tail += __shfl_xor_sync(kFull, tail, d);
     }
-    /* restore the decimator histories in front of the planes */
-    for (int i = lane; i < 64; i += 32) s[oMix + (i >> 3) * kMixPlane + (i & 7)] = s[oMH + i];
-    for (int i = lane; i < 96; i += 32) s[oD1 + (i / 24) * kD1Plane + (i % 24)] = s[oDH + i];
+    /* restore the decimator histories in front of the planes (each warp: its own channel) */
+    {
+      const int i = 32 * w2 + lane;                  /* 64 dec1 history values: planes 4 w2 .. 4 w2 + 3 */
+      s[oMix + (i >> 3) * kMixPlane + (i & 7)] = s[oMH + i];
+      for (int j = lane; j < 48; j += 32) {          /* 96 dec2 history values: planes 2 w2, 2 w2 + 1 */
+        const int k = 48 * w2 + j;
+        s[oD1 + (k / 24) * kD1Plane + (k % 24)] = s[oDH + k];
+      }
+    }
     /* gains of this block (Process.cpp:117,133): rfGainValue and RFgain are folded into the phasor */
     const float gain = r.in_gain * (float)r.rf_gain;
-    T41RX_LAP(tm, 0);
     const F2 pb = F2{(float)r.ph_re * gain, -(float)r.ph_im * gain};
-    float cI = r.dc_w, cQ = tail;
-    /* NB: tail misses a1^2048 * (state entering I), which is exactly 0 in float */
-    if (r.nco_closed) {
+    T41RX_LAP(tm, 0);
+    const bool closed = r.nco_closed != 0;
 #pragma unroll 1
-      for (int q = 0; q < 4; ++q) {
-        CpAsyncWaitAll();
-        __syncwarp();
-        T41RX_LAP(tm, 1);
+    for (int q = 0; q < 4; ++q) {
+      /* recurrence values entering the quarter (written by thread 63 before the previous quarter's
+         second barrier; read before this quarter's first barrier: no race with this quarter's writes) */
+      float cI, cQ;
+      if (q == 0) { cI = s[oMiscF + mEndQ]; cQ = tail; }
+      else { cI = s[oMiscF + mEndI]; cQ = s[oMiscF + mEndQ]; }
+      CpAsyncWaitAll();
+      PairSync();                     /* raw quarter visible; planes free (previous dec1 done) */
+      T41RX_LAP(tm, 1);
+      if (closed) {
         if (q < 3) IssueQuarter(t, q + 1);
         else if (t + 1 < a.n_blocks) IssueQuarter(t + 1, 0);
-        const F2 qq = F2{s[oNcoW + 32 + 2 * q], s[oNcoW + 32 + 2 * q + 1]};
-        Quarter<false>(q, cI, cQ, CMul(pb, qq), nullptr);
-      }
-      /* advance the block phasor by 2048 samples */
-      double sn, cs;
-      sincos(cf.nco_block_delta, &sn, &cs);
-      const double nr = r.ph_re * cs - r.ph_im * sn, ni = r.ph_re * sn + r.ph_im * cs;
-      r.ph_re = nr;
-      r.ph_im = ni;
-    } else {
-      /* the oscillator's amplitude loop has not settled (first block of a receiver, block after a
-         retune): FreqShift2's FP64 recurrence step by step (Freq_Shift.cpp:126-140) on lane 0, one
-         quarter at a time into the idle raw buffer (so no copy is in flight during such a block) */
-#pragma unroll 1
-      for (int q = 0; q < 4; ++q) {
-        CpAsyncWaitAll();
+        const F2 qq = F2{s[oNcoW + 16 + 2 * q], s[oNcoW + 16 + 2 * q + 1]};
         __syncwarp();
+        QuarterMix<false>(q, cI, cQ, CMul(pb, qq), nullptr);
+      } else {
+        /* the oscillator's amplitude loop has not settled (first block of a receiver, block after a
+           retune): FreqShift2's FP64 recurrence step by step (Freq_Shift.cpp:126-140) on one thread, one
+           quarter at a time into the idle raw buffer (so no copy is in flight during such a block) */
         float2 *tab = reinterpret_cast<float2 *>(s + oRaw + ((q + 1) & 1) * kRawBufWords);
-        if (lane == 0) {
+        if (tau == 0) {
           double vq = r.osc_q, vi = r.osc_i;
           const double oc = cf.osc_cos, os = cf.osc_sin;
           for (int n = 0; n < 512; ++n) {
@@ -630,41 +695,56 @@ struct RxWarp {
           }
           r.osc_q = vq;
           r.osc_i = vi;
+          if (q == 3) {               /* settled?  then continue in closed form from the vector's angle */
+            const double r2 = vq * vq + vi * vi;
+            const double inv = rsqrt(r2);
+            double *md = reinterpret_cast<double *>(s + oMiscF + mPhasor);
+            md[0] = vq * inv;
+            md[1] = vi * inv;
+            s[oMiscF + mSettled] = (fabs(r2 - cf.nco_r2_fix) < 4.0e-15) ? 1.0f : 0.0f;
+          }
         }
-        __syncwarp();
-        Quarter<true>(q, cI, cQ, F2{gain, 0.0f}, tab);
+        PairSync();
+        QuarterMix<true>(q, cI, cQ, F2{gain, 0.0f}, tab);
+      }
+      PairSync();                     /* planes visible */
+      if (!closed) {
         if (q < 3) IssueQuarter(t, q + 1);
         else if (t + 1 < a.n_blocks) IssueQuarter(t + 1, 0);
       }
-      /* settled?  then continue in closed form from the vector's angle */
-      int settled = 0;
-      double pr = 0.0, pi2 = 0.0;
-      if (lane == 0) {
-        const double r2 = r.osc_q * r.osc_q + r.osc_i * r.osc_i;
-        settled = fabs(r2 - cf.nco_r2_fix) < 4.0e-15;
-        const double inv = rsqrt(r2);
-        pr = r.osc_q * inv;
-        pi2 = r.osc_i * inv;
-      }
-      settled = __shfl_sync(kFull, settled, 0);
-      if (settled) {
-        r.nco_closed = 1;
-        r.ph_re = __shfl_sync(kFull, pr, 0);
-        r.ph_im = __shfl_sync(kFull, pi2, 0);
-      }
+      T41RX_LAP(tm, 2);
+      Dec1Quarter(q);
+      T41RX_LAP(tm, 3);
     }
-    r.dc_w = cQ;
-    /* save the dec1 plane histories (the FFT buffer overlays the planes) */
-    for (int i = lane; i < 64; i += 32) s[oMH + i] = s[oMix + (i >> 3) * kMixPlane + (i & 7)];
+    if (closed) {
+      /* advance the block phasor by 2048 samples */
+      double sn, cs;
+      sincos(cf.nco_block_delta, &sn, &cs);
+      const double nr = r.ph_re * cs - r.ph_im * sn, ni = r.ph_re * sn + r.ph_im * cs;
+      r.ph_re = nr;
+      r.ph_im = ni;
+    } else if (s[oMiscF + mSettled] != 0.0f) {      /* written before the last PairSync of quarter 3 */
+      const double *md = reinterpret_cast<const double *>(s + oMiscF + mPhasor);
+      r.nco_closed = 1;
+      r.ph_re = md[0];
+      r.ph_im = md[1];
+    }
+    /* save this channel's dec1 plane histories (the FFT buffer overlays the planes) */
     __syncwarp();
-    float dq[2][8];
+    {
+      const int i = 32 * w2 + lane;
+      s[oMH + i] = s[oMix + (i >> 3) * kMixPlane + (i & 7)];
+    }
     T41RX_LAP(tm, 4);
+    float dq[8];
     Dec2(dq);
     __syncwarp();
+    /* this channel's dec2 history for the next block: entries 232..255 of each plane */
+    for (int j = lane; j < 48; j += 32) {
+      const int k = 48 * w2 + j;
+      s[oDH + k] = s[oD1 + (k / 24) * kD1Plane + 24 + 232 + (k % 24)];
+    }
     T41RX_LAP(tm, 5);
-    /* dec2 history for the next block: entries 232..255 of each plane */
-    for (int i = lane; i < 96; i += 32) s[oDH + i] = s[oD1 + (i / 24) * kD1Plane + 24 + 232 + (i % 24)];
-    __syncwarp();
     AfterDec2(dq, buf);
     /* Codec_gain (Process.cpp:979-1016 with the clip flags never set) */
     {
@@ -678,76 +758,85 @@ struct RxWarp {
     }
   }
 
-  /* level adjust + overlap-save + fast convolution + |z| + window maximum -> staging */
-  __device__ void AfterDec2(float (&dq)[2][8], int buf) {
+  /* level adjust + overlap-save + fast convolution + |z| + window maximum -> staging.
+     dq: this warp's channel (w2) of the 8 decimated samples 8 lane .. 8 lane + 7 */
+  __device__ void AfterDec2(float (&dq)[8], int buf) {
+    float *fbw = s + oMix;                                   /* FFT buffer as words */
     float2 *fb = reinterpret_cast<float2 *>(s + oMix);
-    float2 *ola = reinterpret_cast<float2 *>(s + oOlaF);
-    float2 *stz = reinterpret_cast<float2 *>(s + oStZ + buf * 512);
+    float2 *stz = reinterpret_cast<float2 *>(s + oStZ + buf * kStZBuf);
     const int o0 = 8 * lane;
     if (r.mode == kModePsk31) {           /* Process.cpp:376-387,745: raw decimated I, no filter, no AGC */
+      if (w2 == 0) {
 #pragma unroll
-      for (int o = 0; o < 8; ++o) stz[o0 + o] = float2{dq[0][o], 0.0f};
+        for (int o = 0; o < 8; ++o) stz[ZPos(o0 + o)] = float2{dq[o], 0.0f};
+      }
       return;
     }
+    PairSync();                           /* both warps are done with the planes the FFT buffer overlays */
     if (r.mode == kModeNfm) {
-      NfmDiscriminator(dq, fb, ola);
+      NfmDiscriminator(dq, fb);
     } else {
+      /* component w2 of: first half = previous block, second half = this block (Process.cpp:498-522) */
 #pragma unroll
       for (int o = 0; o < 8; ++o) {
-        const float2 cur = float2{dq[0][o] * r.vol_scale, dq[1][o] * r.vol_scale};   /* Process.cpp:482-492 */
-        float2 prev = ola[o0 + o];
-        if (r.first_block) prev = float2{0.0f, 0.0f};                                /* Process.cpp:498-504 */
-        fb[FPos(o0 + o)] = prev;
-        fb[FPos(256 + o0 + o)] = cur;
-        ola[o0 + o] = cur;
+        const float cur = dq[o] * r.vol_scale;                                       /* Process.cpp:482-492 */
+        float prev = s[OlaW(w2, o0 + o)];
+        if (r.first_block) prev = 0.0f;                                              /* Process.cpp:498-504 */
+        fbw[2 * FPos(o0 + o) + w2] = prev;
+        fbw[2 * FPos(256 + o0 + o) + w2] = cur;
+        s[OlaW(w2, o0 + o)] = cur;
       }
       r.first_block = 0;
     }
-    __syncwarp();
+    PairSync();
     const float2 *tw = a.twiddle;
     const float2 *mask = reinterpret_cast<const float2 *>(a.fsets[a.cfg[sid].filter_id].mask);
-    FwdPass<0>(fb, tw, lane); FwdPass<0>(fb, tw, lane + 32);
-    __syncwarp();
-    FwdPass<1>(fb, tw, lane); FwdPass<1>(fb, tw, lane + 32);
-    __syncwarp();
-    MidPass(fb, mask, lane); MidPass(fb, mask, lane + 32);
-    __syncwarp();
-    InvPass<1, false>(fb, tw, lane); InvPass<1, false>(fb, tw, lane + 32);
-    __syncwarp();
-    InvPass<0, true>(fb, tw, lane); InvPass<0, true>(fb, tw, lane + 32);
-    __syncwarp();
+    FwdPass<0>(fb, tw, tau);
+    PairSync();
+    FwdPass<1>(fb, tw, tau);
+    PairSync();
+    MidPass(fb, mask, tau);
+    PairSync();
+    InvPass<1, false>(fb, tw, tau);
+    PairSync();
+    InvPass<0, true>(fb, tw, tau);
+    PairSync();
     T41RX_LAP(tm, 6);
-    /* valid outputs 256..511, scaled by 1/512 */
-    float2 z[8];
+    /* valid outputs 256..511, scaled by 1/512: thread tau takes i = tau + 64 o (stride-1 lanes) */
+    float2 z[4];
 #pragma unroll
-    for (int o = 0; o < 8; ++o) {
-      const float2 v = fb[FPos(256 + o0 + o)];
+    for (int o = 0; o < 4; ++o) {
+      const float2 v = fb[FPos(256 + tau + 64 * o)];
       z[o] = float2{v.x * (1.0f / 512.0f), v.y * (1.0f / 512.0f)};
     }
     if (r.agc_mode == 0) {                /* DSP_Fn.cpp:494-502: fixed gain, no delay line */
 #pragma unroll
-      for (int o = 0; o < 8; ++o) stz[o0 + o] = z[o];
+      for (int o = 0; o < 4; ++o) stz[ZPos(tau + 64 * o)] = z[o];
       return;
     }
     /* delayed output: zd[i] = z[i - 97]; keep the last 97 for the next block */
     float2 *zh = reinterpret_cast<float2 *>(s + oZH);
     float *E = s + vE;
-    for (int i = lane; i < kAgcDelay; i += 32) {
-      stz[i] = zh[i];
-      E[i] = s[oAH + i];
+    float *sta = s + oStA + buf * kStABuf;
+    for (int i = tau; i < kAgcDelay; i += 64) {
+      const float2 h = zh[i];
+      stz[ZPos(i)] = h;
+      E[i] = __fsqrt_rn(h.x * h.x + h.y * h.y);
     }
-    __syncwarp();
+    PairSync();
 #pragma unroll
-    for (int o = 0; o < 8; ++o) {
-      const int i = o0 + o;
-      if (i + kAgcDelay < kDec) stz[i + kAgcDelay] = z[o];
+    for (int o = 0; o < 4; ++o) {
+      const int i = tau + 64 * o;
+      if (i + kAgcDelay < kDec) stz[ZPos(i + kAgcDelay)] = z[o];
       else zh[i + kAgcDelay - kDec] = z[o];
       E[kAgcDelay + i] = __fsqrt_rn(z[o].x * z[o].x + z[o].y * z[o].y);
     }
-    if (lane < 7) E[353 + lane] = 0.0f;
-    __syncwarp();
-    /* chunk pass: prefix / suffix maxima inside chunks of 8 (NaN magnitudes count as 0) */
-    for (int c = lane; c < 45; c += 32) {
+    if (tau < 7) E[353 + tau] = 0.0f;
+    PairSync();
+    /* chunk pass: prefix / suffix maxima inside chunks of 8 (NaN magnitudes count as 0); the |z| history
+       moves on and the delayed |z| goes to the AGC staging while E is complete */
+    if (tau < 45) {
+      const int c = tau;
       float v[8];
       const float4 u0 = *reinterpret_cast<const float4 *>(E + 8 * c), u1 = *reinterpret_cast<const float4 *>(E + 8 * c + 4);
       v[0] = u0.x; v[1] = u0.y; v[2] = u0.z; v[3] = u0.w; v[4] = u1.x; v[5] = u1.y; v[6] = u1.z; v[7] = u1.w;
@@ -763,67 +852,85 @@ struct RxWarp {
       *reinterpret_cast<float4 *>(s + vSfx + 8 * c) = float4{sf[0], sf[1], sf[2], sf[3]};
       *reinterpret_cast<float4 *>(s + vSfx + 8 * c + 4) = float4{sf[4], sf[5], sf[6], sf[7]};
       s[vCM + c] = p[7];
-    }
-    __syncwarp();
-    /* F[c] = max(CM[c .. c+10]) for c = 1 .. 33 (kept in registers: lane L needs F[L+1] and F[L+2]) */
-    float f1 = 0.0f, f2 = 0.0f;
+      if (c < 32) {
+        /* zero-state advance of the AGC's two back-averages over this chunk of 8 delayed magnitudes
+           (DSP_Fn.cpp:521-522 are linear recurrences: the AGC warp applies them once per chunk) */
+        const AgcConsts &ag = a.cfg[sid].agc;
+        const float of = ag.onemfast_backmult, oh = ag.onemhang_backmult;
+        float pf = 0.0f, ph = 0.0f;
 #pragma unroll
-    for (int k = 0; k < 11; ++k) {
-      f1 = fmaxf(f1, s[vCM + lane + 1 + k]);
-      f2 = fmaxf(f2, s[vCM + min(lane + 2 + k, 44)]);
+        for (int k = 0; k < 8; ++k) {
+          pf = fmaf(of, pf, v[k]);
+          ph = fmaf(oh, ph, v[k]);
+        }
+        *reinterpret_cast<float2 *>(sta + 512 + 2 * c) = float2{pf * ag.fast_backmult, ph * ag.hang_backmult};
+      }
     }
-    /* rm[i] = max(E[i+1 .. i+97]) = max(Sfx[i+1], F[((i+1) >> 3) + 1], Pfx[i+97]); |z| delayed = E[i] */
-    float *sta = s + oStA + buf * 512;
 #pragma unroll
-    for (int o = 0; o < 8; ++o) {
-      const int i = o0 + o;
-      const float f = (o == 7) ? f2 : f1;
-      sta[256 + i] = fmaxf(fmaxf(s[vSfx + i + 1], f), s[vPfx + i + 97]);
-      sta[i] = E[i];
+    for (int o = 0; o < 4; ++o) sta[tau + 64 * o] = E[tau + 64 * o];
+    PairSync();
+    /* F[c] = max(CM[c .. c+10]), c = 0 .. 34, written over the (consumed) |z| array */
+    if (tau < 35) {
+      float f = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 11; ++k) f = fmaxf(f, s[vCM + min(tau + k, 44)]);
+      s[vF + tau] = f;
     }
-    __syncwarp();
-    for (int i = lane; i < kAgcDelay; i += 32) s[oAH + i] = E[kDec + i];
+    PairSync();
+    /* rm[i] = max(E[i+1 .. i+97]) = max(Sfx[i+1], F[((i+1) >> 3) + 1], Pfx[i+97]) */
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      const int i = tau + 64 * o;
+      sta[256 + i] = fmaxf(fmaxf(s[vSfx + i + 1], s[vF + ((i + 1) >> 3) + 1]), s[vPfx + i + 97]);
+    }
     T41RX_LAP(tm, 7);
   }
 
   /* NFM: discriminator on the decimated samples, then the audio goes through the filter as a real
-     signal (Demod.cpp:220-235, Process.cpp:716-727,765-779) */
-  __device__ __forceinline__ void NfmDiscriminator(float (&dq)[2][8], float2 *fb, float2 *ola) {
+     signal (Demod.cpp:220-235, Process.cpp:716-727,765-779).  The two warps hold I and Q: exchange through
+     the second half of the FFT buffer. */
+  __device__ __forceinline__ void NfmDiscriminator(float (&dq)[8], float2 *fb) {
     StreamState &st = a.st[sid];
+    float *fbw = reinterpret_cast<float *>(fb);
     const float kq = 0.340447550238101026565118445432744920253753662109375f;
     const int o0 = 8 * lane;
-    /* previous sample of the lane's first output comes from the lane below */
-    float pi_ = __shfl_up_sync(kFull, dq[0][7], 1), pq_ = __shfl_up_sync(kFull, dq[1][7], 1);
-    const float li = st.nfm_last_i, lq = st.nfm_last_q;
-    float outv[8];
 #pragma unroll
-    for (int o = 0; o < 8; ++o) {
-      const float I = dq[0][o], Q = dq[1][o];
+    for (int o = 0; o < 8; ++o) fbw[2 * FPos(256 + o0 + o) + w2] = dq[o];
+    PairSync();
+    const int i0 = 4 * tau;
+    float2 cur[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) cur[o] = fb[FPos(256 + i0 + o)];
+    float2 prev = float2{st.nfm_last_i, st.nfm_last_q};
+    if (tau > 0) prev = fb[FPos(256 + i0 - 1)];
+    float outv[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      const float I = cur[o].x, Q = cur[o].y;
       const float den = I * I + Q * Q;
       float out;
-      if (o0 + o == 0) {
-        const float num = I * (Q - lq) - Q * (I - li);
+      if (i0 + o == 0) {
+        const float num = I * (Q - prev.y) - Q * (I - prev.x);
         out = kq * num / den;
       } else {
-        const float num = Q * pi_ - I * pq_;
+        const float num = Q * prev.x - I * prev.y;
         out = kq * num / den;
         out = (1.0f < out) ? 1.0f : out;          /* limiter skips index 0 (B5) */
         out = (-1.0f > out) ? -1.0f : out;
       }
       outv[o] = out;
-      pi_ = I;
-      pq_ = Q;
+      prev = cur[o];
     }
-    __syncwarp();
-    if (lane == 15) {                              /* "last sample" = complex sample 127 (B4) */
-      st.nfm_last_i = dq[0][7];
-      st.nfm_last_q = dq[1][7];
+    PairSync();
+    if (tau == 31) {                               /* "last sample" = complex sample 127 (B4) */
+      st.nfm_last_i = cur[3].x;
+      st.nfm_last_q = cur[3].y;
     }
 #pragma unroll
-    for (int o = 0; o < 8; ++o) {
-      fb[FPos(o0 + o)] = float2{ola[o0 + o].x, 0.0f};
-      fb[FPos(256 + o0 + o)] = float2{outv[o], 0.0f};
-      ola[o0 + o].x = outv[o];
+    for (int o = 0; o < 4; ++o) {
+      fb[FPos(i0 + o)] = float2{s[OlaW(0, i0 + o)], 0.0f};
+      fb[FPos(256 + i0 + o)] = float2{outv[o], 0.0f};
+      s[OlaW(0, i0 + o)] = outv[o];
     }
   }
 
@@ -831,101 +938,113 @@ struct RxWarp {
   __device__ void BackEnd(int t, int buf) {
     const StreamCfg &cf = a.cfg[sid];
     StreamState &st = a.st[sid];
-    const float2 *stz = reinterpret_cast<const float2 *>(s + oStZ + buf * 512);
-    const float *volts = s + oStA + buf * 512 + 256;
+    const float2 *stz = reinterpret_cast<const float2 *>(s + oStZ + buf * kStZBuf);
+    const float *volts = s + oStA + buf * kStABuf + 256;
     float *aud = s + vAudF;
-    const int o0 = 8 * lane;
-    float2 dem[8];
+    /* gain and the sample-parallel part of the demodulators: thread tau takes i = tau + 64 o */
+    {
+      float2 dem[4];
+      GainedSamples(cf, stz, volts, dem);
+      if (a.psk_bits || a.psk_chars || cf.psk31_enable) PskTap(t, dem[0], cf, st);
 #pragma unroll
-    for (int o = 0; o < 8; ++o) dem[o] = stz[o0 + o];
-    if (r.mode != kModePsk31) {
-      if (r.agc_mode == 0) {
-#pragma unroll
-        for (int o = 0; o < 8; ++o) dem[o] = float2{dem[o].x * r.fixed_gain, dem[o].y * r.fixed_gain};
-      } else {
-        const AgcConsts &ag = cf.agc;
-        const float inv_in = ag.inv_max_input, tgt = ag.out_target, slope = ag.slope_constant;
-#pragma unroll
-        for (int o = 0; o < 8; ++o) {
-          const float v = volts[o0 + o];
-          const float lg = Log10Fast(inv_in * v);             /* DSP_Fn.cpp:628 */
-          const float clipped = (0.0f < lg) ? 0.0f : lg;
-          const float mult = (tgt - slope * clipped) / v;
-          dem[o] = float2{dem[o].x * mult, dem[o].y * mult};
-        }
+      for (int o = 0; o < 4; ++o) {
+        /* AM: alpha-beta magnitude (Process.cpp:697-699); USB / LSB / NFM / PSK31: real part (:616-624,688-695) */
+        aud[24 + tau + 64 * o] = (r.mode == kModeAm) ? AlphaBetaMag(dem[o].x, dem[o].y) : dem[o].x;
       }
     }
-    /* demodulators (Process.cpp:615-761) */
-    float au[8];
+    if (tau < 23) aud[1 + tau] = s[oIH + tau];
+    if (tau >= 32 && tau < 39) s[vI1 + 1 + (tau - 32)] = s[oIH + 24 + (tau - 32)];
+    PairSync();
     if (r.mode == kModeAm) {
-      AmDetect(dem, au, st);
-    } else if (r.mode == kModeSam) {
-      SamDetect(dem, au, st);
-    } else {
-#pragma unroll
-      for (int o = 0; o < 8; ++o) au[o] = dem[o].x;           /* USB / LSB / NFM / PSK31: real part */
+      /* the detector's recurrences are blocked scans over one warp (8 samples per lane), in place */
+      if (w2 == 0) {
+        float m[8], au[8];
+        const float4 m0 = *reinterpret_cast<const float4 *>(aud + 24 + 8 * lane), m1 = *reinterpret_cast<const float4 *>(aud + 24 + 8 * lane + 4);
+        m[0] = m0.x; m[1] = m0.y; m[2] = m0.z; m[3] = m0.w; m[4] = m1.x; m[5] = m1.y; m[6] = m1.z; m[7] = m1.w;
+        AmDetect(m, au, st);
+        *reinterpret_cast<float4 *>(aud + 24 + 8 * lane) = float4{au[0], au[1], au[2], au[3]};
+        *reinterpret_cast<float4 *>(aud + 24 + 8 * lane + 4) = float4{au[4], au[5], au[6], au[7]};
+      }
+      PairSync();
     }
-    /* PSK31 tap (psk31.cpp:235-310): first filtered sample of every third block */
-    if (a.psk_bits || a.psk_chars || cf.psk31_enable) PskTap(t, dem[0], cf, st);
-    /* int1 input: 1 pad + 23 history + 256 */
-    if (lane < 23) aud[1 + lane] = s[oIH + lane];
-    *reinterpret_cast<float4 *>(aud + 24 + o0) = float4{au[0], au[1], au[2], au[3]};
-    *reinterpret_cast<float4 *>(aud + 24 + o0 + 4) = float4{au[4], au[5], au[6], au[7]};
-    __syncwarp();
     T41RX_LAP(tm, 8);
     Interp1();
-    __syncwarp();
+    PairSync();
     T41RX_LAP(tm, 9);
-    if (lane < 23) s[oIH + lane] = aud[24 + 233 + lane];
+    if (tau < 23) s[oIH + tau] = aud[24 + 233 + tau];
     Interp2(t);
-    __syncwarp();
-    if (lane < 7) s[oIH + 24 + lane] = s[vI1 + 8 + 505 + lane];
-    __syncwarp();
+    PairSync();
+    if (tau < 7) s[oIH + 24 + tau] = s[vI1 + 8 + 505 + tau];
     T41RX_LAP(tm, 10);
   }
 
-  /* arm_fir_interpolate_f32, L = 2, 48 taps (Process.cpp:917): 8 inputs per lane */
+  /* AGC gain from volts (DSP_Fn.cpp:628) or the fixed gain (DSP_Fn.cpp:494-502) applied to the delayed
+     samples i = tau + 64 o */
+  __device__ __forceinline__ void GainedSamples(const StreamCfg &cf, const float2 *stz, const float *volts,
+                                                float2 (&dem)[4]) const {
+#pragma unroll
+    for (int o = 0; o < 4; ++o) dem[o] = stz[ZPos(tau + 64 * o)];
+    if (r.mode == kModePsk31) return;
+    if (r.agc_mode == 0) {
+#pragma unroll
+      for (int o = 0; o < 4; ++o) dem[o] = float2{dem[o].x * r.fixed_gain, dem[o].y * r.fixed_gain};
+      return;
+    }
+    const AgcConsts &ag = cf.agc;
+    const float inv_in = ag.inv_max_input, tgt = ag.out_target, slope = ag.slope_constant;
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      const float v = volts[tau + 64 * o];
+      const float lg = Log10Fast(inv_in * v);
+      const float clipped = (0.0f < lg) ? 0.0f : lg;
+      const float mult = (tgt - slope * clipped) / v;
+      dem[o] = float2{dem[o].x * mult, dem[o].y * mult};
+    }
+  }
+
+  /* arm_fir_interpolate_f32, L = 2, 48 taps (Process.cpp:917): 4 inputs per thread */
   __device__ __forceinline__ void Interp1() {
     const float *aud = s + vAudF;
     const float *tp = s + oTapsF + 74;
-    float w[32];
-    const float4 *src = reinterpret_cast<const float4 *>(aud + 8 * lane);
+    float w[28];
+    const float4 *src = reinterpret_cast<const float4 *>(aud + 4 * tau);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < 7; ++k) {
       const float4 v = src[k];
       w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
     }
-    float a0[8], a1[8];
+    float a0[4], a1[4];
 #pragma unroll
-    for (int o = 0; o < 8; ++o) { a0[o] = 0.0f; a1[o] = 0.0f; }
+    for (int o = 0; o < 4; ++o) { a0[o] = 0.0f; a1[o] = 0.0f; }
 #pragma unroll
     for (int k = 0; k < 24; ++k) {
-      const float c1 = tp[2 * k + 1], c0 = tp[2 * k];
+      const float2 c = *reinterpret_cast<const float2 *>(tp + 2 * k);
 #pragma unroll
-      for (int o = 0; o < 8; ++o) {
-        const float x = w[o + 1 + k];          /* input n - 23 + k, n = 8 L + o, lives at word 8 L + o + 1 + k */
-        a0[o] = fmaf(x, c1, a0[o]);            /* phase 0: c[(L-1) + k L] */
-        a1[o] = fmaf(x, c0, a1[o]);            /* phase 1: c[0 + k L]     */
+      for (int o = 0; o < 4; ++o) {
+        const float x = w[o + 1 + k];          /* input n - 23 + k, n = 4 tau + o, lives at word 4 tau + o + 1 + k */
+        a0[o] = fmaf(x, c.y, a0[o]);           /* phase 0: c[(L-1) + k L] */
+        a1[o] = fmaf(x, c.x, a1[o]);           /* phase 1: c[0 + k L]     */
       }
     }
-    float *i1 = s + vI1 + 8 + 16 * lane;
-#pragma unroll
-    for (int o = 0; o < 8; o += 2)
-      *reinterpret_cast<float4 *>(i1 + 2 * o) = float4{a0[o], a1[o], a0[o + 1], a1[o + 1]};
-    if (lane < 7) s[vI1 + 1 + lane] = s[oIH + 24 + lane];
+    float *i1 = s + vI1 + 8 + 8 * tau;
+    *reinterpret_cast<float4 *>(i1) = float4{a0[0], a1[0], a0[1], a1[1]};
+    *reinterpret_cast<float4 *>(i1 + 4) = float4{a0[2], a1[2], a0[3], a1[3]};
   }
 
-  /* arm_fir_interpolate_f32, L = 4, 32 taps + volume (Process.cpp:919-931): 4 x 4 inputs per lane */
+  /* arm_fir_interpolate_f32, L = 4, 32 taps + volume (Process.cpp:919-931): 2 x 4 inputs per thread */
   __device__ __forceinline__ void Interp2(int t) {
     const float *tp = s + oTapsF + 122;
     float c[kInt2Taps];
 #pragma unroll
-    for (int i = 0; i < kInt2Taps; ++i) c[i] = tp[i];
+    for (int i = 0; i < kInt2Taps; i += 2) {
+      const float2 v = *reinterpret_cast<const float2 *>(tp + i);
+      c[i] = v.x; c[i + 1] = v.y;
+    }
     float4 *dst = reinterpret_cast<float4 *>(a.audio + ((size_t)sid * a.n_blocks + t) * kBlock);
     const float vol = r.volume;
 #pragma unroll 1
-    for (int rr = 0; rr < 4; ++rr) {
-      const int n0 = 4 * lane + 128 * rr;
+    for (int rr = 0; rr < 2; ++rr) {
+      const int n0 = 4 * tau + 256 * rr;
       float w[12];
       const float4 *src = reinterpret_cast<const float4 *>(s + vI1 + n0);
 #pragma unroll
@@ -949,11 +1068,8 @@ struct RxWarp {
 
   /* AM: alpha-beta magnitude, 1-pole DC removal, 1-stage DF1 low-pass (Process.cpp:697-707) as blocked
      linear scans over the lanes (8 samples per lane) */
-  __device__ __forceinline__ void AmDetect(const float2 (&dem)[8], float (&au)[8], StreamState &st) {
+  __device__ __forceinline__ void AmDetect(const float (&m)[8], float (&au)[8], StreamState &st) {
     const StreamCfg &cf = a.cfg[sid];
-    float m[8];
-#pragma unroll
-    for (int o = 0; o < 8; ++o) m[o] = AlphaBetaMag(dem[o].x, dem[o].y);
     /* w[i] = m[i] + 0.99 w[i-1] */
     const float g = 0.99f;
     float w[8];
@@ -1053,47 +1169,9 @@ struct RxWarp {
     }
   }
 
-  /* SAM PLL (Demod.cpp:40-139): serial, lane 0, through shared memory */
-  __device__ void SamDetect(const float2 (&dem)[8], float (&au)[8], StreamState &st) {
-    float2 *tmp = reinterpret_cast<float2 *>(s + vI1);     /* 256 complex in, audio written over .x */
-#pragma unroll
-    for (int o = 0; o < 8; ++o) tmp[8 * lane + o] = dem[o];
-    __syncwarp();
-    if (lane == 0) {
-      const float tpi = 6.283185307179586476925286766559f;
-      const float omega_min = __ldg(a.sam_consts + 0), omega_max = __ldg(a.sam_consts + 1);
-      const float g1 = __ldg(a.sam_consts + 2), g2 = __ldg(a.sam_consts + 3);
-      float phz = st.sam_phzerror, fil = st.sam_fil_out, om2 = st.sam_omega2;
-      for (int i = 0; i < kDec; ++i) {
-        const float2 z = tmp[i];
-        const float sn = TableTurns(a.sin_table, phz * 0.159154943092f);
-        const float cs = TableTurns(a.sin_table, phz * 0.159154943092f + 0.25f);
-        const float ai = cs * z.x, bi = sn * z.x, aq = cs * z.y, bq = sn * z.y;
-        const float corr0 = +ai + bq;
-        const float corr1 = -bi + aq;
-        tmp[i].x = (ai - bi) + (aq + bq);
-        const float det = Atan2Approx(corr1, corr0);
-        const float del_out = fil;
-        om2 = om2 + g2 * det;
-        if (om2 < omega_min) om2 = omega_min;
-        else if (om2 > omega_max) om2 = omega_max;
-        fil = g1 * det + om2;
-        phz = phz + del_out;
-        while (phz >= tpi) phz -= tpi;
-        while (phz < 0.0f) phz += tpi;
-      }
-      st.sam_phzerror = phz;
-      st.sam_fil_out = fil;
-      st.sam_omega2 = om2;
-    }
-    __syncwarp();
-#pragma unroll
-    for (int o = 0; o < 8; ++o) au[o] = tmp[8 * lane + o].x;
-    __syncwarp();
-  }
 
   __device__ void PskTap(int t, float2 d0, const StreamCfg &cf, StreamState &st) {
-    if (lane != 0) return;
+    if (tau != 0) return;
     int8_t bit_out = -1;
     uint8_t char_out = 0;
     if (cf.psk31_enable && r.mode != kModeNfm && r.mode != kModePsk31) {
@@ -1136,6 +1214,7 @@ struct RxWarp {
 struct AgcLane {
   /* constants */
   float fbm, omfbm, hbm, omhbm, attack, decay, fdecay, hdecay, pop, hlevel, minv;
+  float om8f, om8h;      /* onemfast_backmult^8, onemhang_backmult^8 */
   int hload, henable;
   /* state */
   float fast, hang, v, save, rm;
@@ -1147,6 +1226,8 @@ struct AgcLane {
     attack = cf.agc.attack_mult; decay = cf.agc.decay_mult; fdecay = cf.agc.fast_decay_mult;
     hdecay = cf.agc.hang_decay_mult; pop = cf.agc.pop_ratio; hlevel = cf.agc.hang_level;
     minv = cf.agc.min_volts;
+    om8f = omfbm * omfbm; om8f *= om8f; om8f *= om8f;
+    om8h = omhbm * omhbm; om8h *= om8h; om8h *= om8h;
     hload = cf.agc.hang_counter_load; henable = cf.agc.hang_enable;
     fast = st.agc_fast_back; hang = st.agc_hang_back; v = st.agc_volts; save = st.agc_save_volts;
     rm = st.agc_ring_max;
@@ -1210,57 +1291,68 @@ struct AgcLane {
   }
 };
 
-/* one block of one receiver per lane.  sta: |z| delayed [256] then window max [256] (overwritten by volts).
+/* one block of one receiver per lane.  sta: |z| delayed [256] | window max [256] (overwritten by volts) |
+ * per-chunk zero-state advances (PF, PH)[32] of the two back-averages.
  *
  * Almost every sample leaves the envelope detector in a "quiet" state: slow decay (3), hang decay (4) or
- * hang (2) with the window maximum below volts, where the update is  v <- max(v + ((r - v) k1) k2, min_volts)
- * with per-state constants and no branch.  The warp therefore runs 8 samples at a time speculatively on that
- * branch-free form (all lanes), votes once, and only re-runs the chunk through the exact per-sample state
- * machine (Step) when some lane saw a transition (attack, end of hang, states 0 / 1). */
+ * hang (2) with the window maximum below volts, where the update is v <- max(v + (r - v) c, min_volts) with a
+ * per-state constant and no branch.  The warp runs 8 samples at a time speculatively
+ * on that form (all lanes), votes once, and only re-runs the chunk through the exact per-sample state machine
+ * (Step) when some lane saw a transition (attack, end of hang, states 0 / 1). */
 __device__ __forceinline__ void AgcBlock(AgcLane &g, float *sta, bool active) {
   constexpr int kC = 8;
 #pragma unroll 1
   for (int i0 = 0; i0 < kDec; i0 += kC) {
-    float ab[kC], rm[kC];
+    float rm[kC];
+    float2 pfh = float2{0.0f, 0.0f};
     if (active) {
 #pragma unroll
       for (int k = 0; k < kC; k += 4) {
-        const float4 a4 = *reinterpret_cast<const float4 *>(sta + i0 + k);
         const float4 r4 = *reinterpret_cast<const float4 *>(sta + 256 + i0 + k);
-        ab[k] = a4.x; ab[k + 1] = a4.y; ab[k + 2] = a4.z; ab[k + 3] = a4.w;
         rm[k] = r4.x; rm[k + 1] = r4.y; rm[k + 2] = r4.z; rm[k + 3] = r4.w;
       }
+      pfh = *reinterpret_cast<const float2 *>(sta + 512 + 2 * (i0 / kC));
     } else {
 #pragma unroll
-      for (int k = 0; k < kC; ++k) { ab[k] = 0.0f; rm[k] = 0.0f; }
+      for (int k = 0; k < kC; ++k) rm[k] = 0.0f;
     }
-    /* speculative quiet path */
-    float k1 = 0.0f, k2 = 0.0f;
+    /* speculative quiet path: state 3: v + ((r - v) decay) 0.05 -> one rounded constant (the step is ~1e-6 v,
+       so the difference from the reference's rounding is ~1e-13 v); state 4: v + (r - v) hang_decay; state 2
+       with the hang counter not expiring inside the chunk: v unchanged */
+    float c = 0.0f;
     bool ok = true;
-    if (g.state == 3) { k1 = g.decay; k2 = 0.05f; }
-    else if (g.state == 4) { k1 = g.hdecay; k2 = 1.0f; }
-    else if (g.state == 2 && g.hc > kC) { k1 = 0.0f; k2 = 0.0f; }
+    if (g.state == 3) c = g.decay * 0.05f;
+    else if (g.state == 4) c = g.hdecay;
+    else if (g.state == 2 && g.hc > kC) c = 0.0f;
     else ok = false;
-    float v = g.v, fast = g.fast, hang = g.hang, last = g.v;
+    float v = g.v, last = g.v;
     float vo[kC];
 #pragma unroll
     for (int k = 0; k < kC; ++k) {
       ok = ok && !(rm[k] >= v);
-      fast = g.fbm * ab[k] + g.omfbm * fast;
-      hang = g.hbm * ab[k] + g.omhbm * hang;
-      const float t = (rm[k] - v) * k1;
-      last = fmaf(t, k2, v);
+      last = fmaf(rm[k] - v, c, v);
       v = fmaxf(last, g.minv);
       vo[k] = v;
     }
     if (__all_sync(kFull, ok || !active)) {
       if (active) {
-        g.v = v; g.fast = fast; g.hang = hang;
+        g.v = v;
+        g.fast = fmaf(g.om8f, g.fast, pfh.x);
+        g.hang = fmaf(g.om8h, g.hang, pfh.y);
         g.rm = rm[kC - 1];
         g.hc = max(g.hc - kC, 0);
         g.action = (last < g.minv) ? 0 : 1;
       }
     } else if (active) {
+#ifdef T41RX_FAST_TIMING
+      if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) g_fast_cycles[20] += 1;
+#endif
+      float ab[kC];
+#pragma unroll
+      for (int k = 0; k < kC; k += 4) {
+        const float4 a4 = *reinterpret_cast<const float4 *>(sta + i0 + k);
+        ab[k] = a4.x; ab[k + 1] = a4.y; ab[k + 2] = a4.z; ab[k + 3] = a4.w;
+      }
 #pragma unroll 1
       for (int k = 0; k < kC; ++k) {
         /* select ab[k], rm[k] without dynamic register indexing */
@@ -1288,10 +1380,12 @@ __device__ __forceinline__ void StreamKernelBody(const LaunchArgs &a, int G, flo
   const int s0 = blockIdx.x * G;
   const int ng = min(G, a.n_streams - s0);
   const int T = a.n_blocks;
-  if (warp < G) {
-    /* ---- receiver warp ---- */
-    const bool live = warp < ng;
-    RxWarp w(a, smem + warp * kSlotF, s0 + warp, lane);
+  if (warp < 2 * G) {
+    /* ---- receiver pair ---- */
+    const int pair = warp >> 1;
+    const bool live = pair < ng;
+    const int sid = live ? (a.stream_ids ? __ldg(a.stream_ids + s0 + pair) : s0 + pair) : 0;
+    RxPair w(a, smem + pair * kSlotF, sid, lane, warp & 1, 1 + pair);
     if (live) {
       w.LoadState();
       w.IssueQuarter(0, 0);
@@ -1312,21 +1406,22 @@ __device__ __forceinline__ void StreamKernelBody(const LaunchArgs &a, int G, flo
     AgcLane g;
     const bool mine = lane < ng;
     bool active = false;
+    const int sid = mine ? (a.stream_ids ? __ldg(a.stream_ids + s0 + lane) : s0 + lane) : 0;
     if (mine) {
-      const StreamCfg &cf = a.cfg[s0 + lane];
-      g.Load(cf, a.st[s0 + lane]);
+      const StreamCfg &cf = a.cfg[sid];
+      g.Load(cf, a.st[sid]);
       active = (cf.mode != kModePsk31) && (cf.agc_mode != 0);
     }
     float *slot = smem + (mine ? lane : 0) * kSlotF;
     SectionTimer tm;
     tm.Start(blockIdx.x == 0 && lane == 0, 16);
     for (int k = 0; k < T + 2; ++k) {
-      if (k >= 1 && k <= T) AgcBlock(g, slot + oStA + ((k - 1) & 1) * 512, active);
+      if (k >= 1 && k <= T) AgcBlock(g, slot + oStA + ((k - 1) & 1) * kStABuf, active);
       T41RX_LAP(tm, 0);
       __syncthreads();
       T41RX_LAP(tm, 1);
     }
-    if (mine && active) g.Store(a.st[s0 + lane]);
+    if (mine && active) g.Store(a.st[sid]);
   }
 }
 

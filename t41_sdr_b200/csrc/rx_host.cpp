@@ -147,6 +147,7 @@ int HostModel::Apply(int s, const t41rx_params &p, StatePatch *patch, int *new_f
     patch->rf_gain = p.rf_gain;
   }
   if (p.spectrum_zoom != old.spectrum_zoom) patch->reset_zoom_ptr = true;   /* FFT.cpp:54 */
+  if (p.rf_gain_all_bands != old.rf_gain_all_bands) patch->clear_fast_native = true;
   return 0;
 }
 

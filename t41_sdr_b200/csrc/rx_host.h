@@ -24,6 +24,7 @@ struct StatePatch {
   bool set_rf_gain = false;
   int32_t rf_gain = 0;
   bool reset_zoom_ptr = false;
+  bool clear_fast_native = false;   /* rfGainAllBands changed: the throughput kernel's DC-block form is stale */
 };
 
 struct HostModel {

@@ -115,8 +115,9 @@ struct LaunchArgs {
   const float *sam_consts;    /* omega_min, omega_max, g1, g2 (Demod.cpp:13-18) */
   const uint16_t *gradient;   /* 117 */
   const uint32_t *varicode;   /* 128: code | bits << 16 | ascii << 24 */
-  int n_streams, n_blocks, row_every, n_rows;
+  int n_streams, n_blocks, row_every, n_rows;   /* n_streams: receivers this launch works on */
   uint32_t flags;
+  const int32_t *stream_ids;  /* receiver index of each of them, or NULL for 0 .. n_streams-1 */
 };
 
 struct Cta {
@@ -127,9 +128,12 @@ struct Cta {
   int t;       /* block index within the launch */
   int row;     /* this block produces a spectrum row */
   int row_idx;
+  int rows_only;   /* 1 in t41rx_rows_kernel */
 };
 
 T41RX_DEV float *Slot(const Cta &c, int g) { return c.smem + g * kSlot; }
+/* receiver index of slot g of this CTA */
+T41RX_DEV int Sid(const Cta &c, int g) { return c.a.stream_ids ? LdgRO(c.a.stream_ids + c.s0 + g) : c.s0 + g; }
 
 /* which receiver (or -1) thread `tid` serves in a one-lane-per-receiver serial phase:
  * T41RX_SERIAL_WPS = 1: lane 0 of the receiver's own first warp (no divergence between receivers
@@ -263,8 +267,8 @@ T41RX_DEV int SeqOff(int i) { return oRawI + 27 + i + ((i >= kBlock) ? (oRawQ - 
 T41RX_DEV void PhStateIn(Cta &c, int tid) {
   for (int g = 0; g < c.ng; ++g) {
     float *s = Slot(c, g);
-    const StreamState &st = c.a.st[c.s0 + g];
-    const StreamCfg &cf = c.a.cfg[c.s0 + g];
+    const StreamState &st = c.a.st[Sid(c, g)];
+    const StreamCfg &cf = c.a.cfg[Sid(c, g)];
     const FilterSet &fs = c.a.fsets[cf.filter_id];
     for (int i = tid; i < 512; i += kNT) s[oOla + i] = st.ola_prev[i >> 8][i & 255];
     for (int i = tid; i < 154; i += kNT) {
@@ -281,7 +285,7 @@ T41RX_DEV void PhStateIn(Cta &c, int tid) {
       s[oAgc + 256 + i] = st.agc_abs[i];
     }
     double *nco = reinterpret_cast<double *>(s + oNco);
-    const double *tab = c.a.nco_tab + (size_t)(c.s0 + g) * 192;
+    const double *tab = c.a.nco_tab + (size_t)(Sid(c, g)) * 192;
     for (int i = tid; i < 192; i += kNT) nco[i] = tab[i];
     for (int i = tid; i < 54; i += kNT) s[oD1H + i] = st.dec1_hist[i / 27][i % 27];
     for (int i = tid; i < 90; i += kNT) s[oD2H + i] = st.dec2_hist[i / 45][i % 45];
@@ -297,7 +301,7 @@ T41RX_DEV void PhStateIn(Cta &c, int tid) {
 T41RX_DEV void PhStateOut(Cta &c, int tid) {
   for (int g = 0; g < c.ng; ++g) {
     float *s = Slot(c, g);
-    StreamState &st = c.a.st[c.s0 + g];
+    StreamState &st = c.a.st[Sid(c, g)];
     for (int i = tid; i < 512; i += kNT) st.ola_prev[i >> 8][i & 255] = s[oOla + i];
     for (int i = tid; i < 128; i += kNT) {
       st.agc_re[i] = s[oAgc + i];
@@ -311,6 +315,7 @@ T41RX_DEV void PhStateOut(Cta &c, int tid) {
     if (tid == 0) {
       st.dc_d1 = s[oMisc + mDcD1];
       st.dc_d2 = s[oMisc + mDcD2];
+      st.fast_native = 0;
     }
   }
 }
@@ -327,7 +332,7 @@ T41RX_DEV void PhLoad(Cta &c, int tid) {
     for (int gg = 0; gg < 2; ++gg) {
       if (g0 + gg >= c.ng) continue;
       const float4 *src = reinterpret_cast<const float4 *>(
-          c.a.iq + ((size_t)(c.s0 + g0 + gg) * c.a.n_blocks + c.t) * (2 * kBlock));
+          c.a.iq + ((size_t)(Sid(c, g0 + gg)) * c.a.n_blocks + c.t) * (2 * kBlock));
 #pragma unroll
       for (int k = 0; k < kPer; ++k) v[gg][k] = LdgRO(src + tid + kNT * k);
     }
@@ -353,7 +358,7 @@ T41RX_DEV void PhLoad(Cta &c, int tid) {
     }
     if (c.t + 1 < c.a.n_blocks) {
       const char *nxt = reinterpret_cast<const char *>(
-          c.a.iq + ((size_t)(c.s0 + g) * c.a.n_blocks + c.t + 1) * (2 * kBlock));
+          c.a.iq + ((size_t)(Sid(c, g)) * c.a.n_blocks + c.t + 1) * (2 * kBlock));
       for (int line = tid; line < (2 * kBlock * 4) / 128; line += kNT) PrefetchL2(nxt + 128 * line);
     }
   }
@@ -430,9 +435,19 @@ T41RX_DEV void DcRun(float *s, const DcPost p, int begin, int end, float &d1_io,
   if (any) d2_io = DcD2(lx, ly);
 }
 
+/* RFgain in force while block t of the launch is processed, from the values at launch start: Codec_gain
+   (Process.cpp:979-1016 with the clip flags never set) raises it by one every 50 blocks up to 15 */
+T41RX_DEV int RfGainAtBlock(int rf_gain0, uint32_t timer0, int t) {
+  const int rg = rf_gain0 + (int)((timer0 + (uint32_t)t) / 50u);
+  return rg > 15 ? (rf_gain0 > 15 ? rf_gain0 : 15) : rg;
+}
+
 T41RX_DEV DcPost DcPostOf(const Cta &c, int g) {
-  const StreamCfg &cf = c.a.cfg[c.s0 + g];
-  return DcPost{cf.rf_gain_value, (float)c.a.st[c.s0 + g].rf_gain, cf.neg_iq_amp, cf.mirrored != 0};
+  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+  const StreamState &st = c.a.st[Sid(c, g)];
+  /* rows_only: the state in HBM is the one at launch start (the throughput kernel advances it) */
+  const int rg = c.rows_only ? RfGainAtBlock(st.rf_gain, st.codec_timer, c.t) : st.rf_gain;
+  return DcPost{cf.rf_gain_value, (float)rg, cf.neg_iq_amp, cf.mirrored != 0};
 }
 
 T41RX_DEV void PhDcWarm(Cta &c, int tid) {
@@ -515,7 +530,7 @@ T41RX_DEV void PhDcFix(Cta &c, int tid) {
       break;
   }
   if (bad >= kDcChunks) return;
-  const float *src = c.a.iq + ((size_t)(c.s0 + g) * c.a.n_blocks + c.t) * (2 * kBlock);
+  const float *src = c.a.iq + ((size_t)(Sid(c, g)) * c.a.n_blocks + c.t) * (2 * kBlock);
   float d1 = s[oMisc + mDcEnd + 2 * (bad - 1)];
   float d2 = s[oMisc + mDcEnd + 2 * (bad - 1) + 1];
   for (int i = bad * kDcChunkLen; i < 2 * kBlock; ++i)
@@ -537,9 +552,9 @@ T41RX_DEV void PhDcFix(Cta &c, int tid) {
 T41RX_DEV void PhZoomIir(Cta &c, int tid) {
   if (!c.row || tid >= c.ng * 2) return;
   const int g = tid >> 1, chn = tid & 1;
-  const StreamCfg &cf = c.a.cfg[c.s0 + g];
+  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
   if (cf.zoom == 0) return;
-  StreamState &st = c.a.st[c.s0 + g];
+  StreamState &st = c.a.st[Sid(c, g)];
   const float *s = Slot(c, g);
   float k[20];
   for (int i = 0; i < 20; ++i) k[i] = LdgRO(c.a.zoom_iir + (cf.zoom - 1) * 20 + i);
@@ -599,9 +614,9 @@ T41RX_DEV void PhZoomIir(Cta &c, int tid) {
   if (!c.row) return;
   const int g = tid >> 6, lane = tid & 63;
   if (g >= c.ng || lane >= 32) return;               /* first warp of the receiver's 64-thread group */
-  const StreamCfg &cf = c.a.cfg[c.s0 + g];
+  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
   if (cf.zoom == 0) return;                          /* warp-uniform */
-  StreamState &st = c.a.st[c.s0 + g];
+  StreamState &st = c.a.st[Sid(c, g)];
   const float *s = Slot(c, g);
   const bool active = lane < 8;
   const int chn = (lane >> 2) & 1, sg = lane & 3;
@@ -684,8 +699,8 @@ T41RX_DEV void PhSpecWindow(Cta &c, int tid) {
   const int g = tid >> 6, u = tid & 63;
   if (g >= c.ng) return;
   float *s = Slot(c, g);
-  const StreamCfg &cf = c.a.cfg[c.s0 + g];
-  const StreamState &st = c.a.st[c.s0 + g];
+  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+  const StreamState &st = c.a.st[Sid(c, g)];
   float2 *buf = reinterpret_cast<float2 *>(s + vSpecFft);
   const IqFix fix = IqFixOf(cf);
   const int zoom = cf.zoom, zptr = st.zoom_ptr;
@@ -723,10 +738,10 @@ T41RX_DEV void PhSpecRow(Cta &c, int tid) {
   const int g = tid >> 6, u = tid & 63;
   if (g >= c.ng) return;
   float *s = Slot(c, g);
-  const StreamCfg &cf = c.a.cfg[c.s0 + g];
-  StreamState &st = c.a.st[c.s0 + g];
+  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+  StreamState &st = c.a.st[Sid(c, g)];
   const float2 *buf = reinterpret_cast<const float2 *>(s + vSpecFft);
-  const size_t row_base = ((size_t)(c.s0 + g) * c.a.n_rows + c.row_idx) * kSpecRes;
+  const size_t row_base = ((size_t)(Sid(c, g)) * c.a.n_rows + c.row_idx) * kSpecRes;
   const float lpf = 0.7f;
   for (int j = 0; j < 8; ++j) {
     const int x = u + 64 * j;
@@ -777,8 +792,8 @@ T41RX_DEV void PhNcoPrep(Cta &c, int tid) {
   const int g = tid >> 6, u = tid & 63;
   if (g >= c.ng) return;
   float *s = Slot(c, g);
-  const StreamCfg &cf = c.a.cfg[c.s0 + g];
-  const StreamState &st = c.a.st[c.s0 + g];
+  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+  const StreamState &st = c.a.st[Sid(c, g)];
   const bool exact = (c.a.flags & 1u) || !st.nco_closed || (st.nco_epoch_seen != cf.nco_epoch);
   if (u == 0) s[oMisc + mNcoMode] = exact ? 1.0f : 0.0f;
   if (exact || u >= 32) return;
@@ -800,11 +815,11 @@ T41RX_DEV void MixStore(float *s, int n, float vi, float vq, double oq, double o
 T41RX_DEV void PhMix(Cta &c, int tid) {
   for (int g = 0; g < c.ng; ++g) {
     float *s = Slot(c, g);
-    const StreamCfg &cf = c.a.cfg[c.s0 + g];
+    const StreamCfg &cf = c.a.cfg[Sid(c, g)];
     if (s[oMisc + mNcoMode] != 0.0f) {
       /* exact path: the FP64 oscillator recurrence, one lane per receiver */
       if (tid != g) continue;
-      StreamState &st = c.a.st[c.s0 + g];
+      StreamState &st = c.a.st[Sid(c, g)];
       double vq, vi;
       if (st.nco_closed) {
         /* leaving closed form (retune or forced): rebuild the vector at the settled radius */
@@ -878,8 +893,8 @@ T41RX_DEV void PhNcoAdvance(Cta &c, int tid) {
   if (tid >= c.ng) return;
   float *s = Slot(c, tid);
   if (s[oMisc + mNcoMode] != 0.0f) return;
-  const StreamCfg &cf = c.a.cfg[c.s0 + tid];
-  StreamState &st = c.a.st[c.s0 + tid];
+  const StreamCfg &cf = c.a.cfg[Sid(c, tid)];
+  StreamState &st = c.a.st[Sid(c, tid)];
   double ph = st.nco_phase + cf.nco_block_delta;
   const double two_pi = 6.283185307179586476925286766559;
   if (ph >= two_pi) ph -= two_pi;
@@ -938,10 +953,10 @@ T41RX_DEV void PhDec2(Cta &c, int tid) {
   const int g = tid >> 6, u = tid & 63;
   if (g >= c.ng) return;
   float *s = Slot(c, g);
-  const StreamCfg &cf = c.a.cfg[c.s0 + g];
+  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
   const int mode = cf.mode;
   const float vol_scale = cf.vol_scale;
-  const bool first_block = c.a.st[c.s0 + g].first_block != 0;
+  const bool first_block = c.a.st[Sid(c, g)].first_block != 0;
   /* dec1's input region is about to be overlaid: keep its last 27 samples */
   for (int h = u; h < 54; h += 64) {
     const int ch = h / 27, i = h % 27;
@@ -994,8 +1009,8 @@ T41RX_DEV void PhDec2(Cta &c, int tid) {
 T41RX_DEV void PhPostDec2(Cta &c, int tid) {
   for (int g = 0; g < c.ng; ++g) {
     float *s = Slot(c, g);
-    const StreamCfg &cf = c.a.cfg[c.s0 + g];
-    StreamState &st = c.a.st[c.s0 + g];
+    const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+    StreamState &st = c.a.st[Sid(c, g)];
     for (int h = tid; h < 90; h += kNT) {
       const int ch = h / 45, i = h % 45;
       s[oD2H + h] = s[(ch ? oD1Q : oD1I) + kDec1Out + i];
@@ -1030,9 +1045,9 @@ T41RX_DEV void PhPostDec2(Cta &c, int tid) {
 T41RX_DEV void PhNfmAssemble(Cta &c, int tid) {
   for (int g = 0; g < c.ng; ++g) {
     float *s = Slot(c, g);
-    const StreamCfg &cf = c.a.cfg[c.s0 + g];
+    const StreamCfg &cf = c.a.cfg[Sid(c, g)];
     if (cf.mode != kModeNfm) continue;
-    StreamState &st = c.a.st[c.s0 + g];
+    StreamState &st = c.a.st[Sid(c, g)];
     float2 *fa = reinterpret_cast<float2 *>(s + vFftA);
     if (tid == 0) {                                /* "last sample" = complex sample 127 (B4) */
       st.nfm_last_i = fa[kDec + 127].x;
@@ -1043,7 +1058,7 @@ T41RX_DEV void PhNfmAssemble(Cta &c, int tid) {
 T41RX_DEV void PhNfmAssemble2(Cta &c, int tid) {
   for (int g = 0; g < c.ng; ++g) {
     float *s = Slot(c, g);
-    const StreamCfg &cf = c.a.cfg[c.s0 + g];
+    const StreamCfg &cf = c.a.cfg[Sid(c, g)];
     if (cf.mode != kModeNfm) continue;
     float2 *fa = reinterpret_cast<float2 *>(s + vFftA);
     for (int o = tid; o < kDec; o += kNT) {
@@ -1063,7 +1078,7 @@ T41RX_DEV bool UsesFilter(int mode) { return mode != kModePsk31; }
 T41RX_DEV void PhFftPass(Cta &c, int tid, int which, int pass) {
   const int g = tid >> 6, u = tid & 63;
   if (g >= c.ng) return;
-  if (!UsesFilter(c.a.cfg[c.s0 + g].mode)) return;
+  if (!UsesFilter(c.a.cfg[Sid(c, g)].mode)) return;
   Radix8Butterfly(reinterpret_cast<float2 *>(Slot(c, g) + (which ? vFftB : vFftA)), c.a.twiddle, pass, u);
 }
 
@@ -1071,7 +1086,7 @@ T41RX_DEV void PhFftPass(Cta &c, int tid, int which, int pass) {
 T41RX_DEV void PhMask(Cta &c, int tid) {
   const int g = tid >> 6, u = tid & 63;
   if (g >= c.ng) return;
-  const StreamCfg &cf = c.a.cfg[c.s0 + g];
+  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
   if (!UsesFilter(cf.mode)) return;
   float *s = Slot(c, g);
   const float2 *fa = reinterpret_cast<const float2 *>(s + vFftA);
@@ -1095,7 +1110,7 @@ T41RX_DEV void PhMask(Cta &c, int tid) {
 T41RX_DEV void PhAgcPre(Cta &c, int tid) {
   const int g = tid >> 6, u = tid & 63;
   if (g >= c.ng) return;
-  const StreamCfg &cf = c.a.cfg[c.s0 + g];
+  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
   if (!UsesFilter(cf.mode)) return;
   float *s = Slot(c, g);
   const float2 *fb = reinterpret_cast<const float2 *>(s + vFftB);
@@ -1132,7 +1147,7 @@ T41RX_DEV void PhAgcPre(Cta &c, int tid) {
 T41RX_DEV void PhAgcMaxLevel(Cta &c, int tid, int level) {
   const int g = tid >> 6, u = tid & 63;
   if (g >= c.ng) return;
-  const StreamCfg &cf = c.a.cfg[c.s0 + g];
+  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
   if (!UsesFilter(cf.mode) || cf.agc_mode == 0) return;
   float *s = Slot(c, g);
   const int n = kAgcDelay + kDec;   /* 353 */
@@ -1167,10 +1182,10 @@ T41RX_DEV void PhAgcMaxLevel(Cta &c, int tid, int level) {
 T41RX_DEV void PhAgcSerial(Cta &c, int tid) {
   const int g = SerialStream(c, tid);
   if (g < 0) return;
-  const StreamCfg &cf = c.a.cfg[c.s0 + g];
+  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
   if (!UsesFilter(cf.mode) || cf.agc_mode == 0) return;
   float *s = Slot(c, g);
-  StreamState &st = c.a.st[c.s0 + g];
+  StreamState &st = c.a.st[Sid(c, g)];
   const float k_fbm = cf.agc.fast_backmult, k_omfbm = cf.agc.onemfast_backmult;
   const float k_hbm = cf.agc.hang_backmult, k_omhbm = cf.agc.onemhang_backmult;
   const float k_attack = cf.agc.attack_mult, k_decay = cf.agc.decay_mult, k_fdecay = cf.agc.fast_decay_mult;
@@ -1272,7 +1287,7 @@ T41RX_DEV void PhAgcSerial(Cta &c, int tid) {
 T41RX_DEV void PhAgcPost(Cta &c, int tid) {
   const int g = tid >> 6, u = tid & 63;
   if (g >= c.ng) return;
-  const StreamCfg &cf = c.a.cfg[c.s0 + g];
+  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
   if (!UsesFilter(cf.mode) || cf.agc_mode == 0) return;
   float *s = Slot(c, g);
   const AgcConsts &a = cf.agc;
@@ -1303,7 +1318,7 @@ T41RX_DEV void PhAgcPost(Cta &c, int tid) {
 T41RX_DEV void PhDemodParallel(Cta &c, int tid) {
   const int g = tid >> 6, u = tid & 63;
   if (g >= c.ng) return;
-  const StreamCfg &cf = c.a.cfg[c.s0 + g];
+  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
   if (!UsesFilter(cf.mode)) return;
   float *s = Slot(c, g);
   const float2 *dem = reinterpret_cast<const float2 *>(s + vDem);
@@ -1319,9 +1334,9 @@ T41RX_DEV void PhDemodParallel(Cta &c, int tid) {
 T41RX_DEV void PhDemodSerial(Cta &c, int tid) {
   const int g = SerialStream(c, tid);
   if (g < 0) return;
-  const StreamCfg &cf = c.a.cfg[c.s0 + g];
+  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
   float *s = Slot(c, g);
-  StreamState &st = c.a.st[c.s0 + g];
+  StreamState &st = c.a.st[Sid(c, g)];
   const float2 *dem = reinterpret_cast<const float2 *>(s + vDem);
   if (cf.mode == kModeAm) {
     /* DC removal (Process.cpp:698-704) then 1-stage DF1 low-pass (Process.cpp:705) */
@@ -1418,11 +1433,11 @@ T41RX_DEV void PhDemodSerial(Cta &c, int tid) {
       st.psk_shr = shr;
     }
     st.psk_block_count++;
-    const size_t o = (size_t)(c.s0 + g) * c.a.n_blocks + c.t;
+    const size_t o = (size_t)(Sid(c, g)) * c.a.n_blocks + c.t;
     if (c.a.psk_bits) c.a.psk_bits[o] = bit_out;
     if (c.a.psk_chars) c.a.psk_chars[o] = char_out;
   } else {
-    const size_t o = (size_t)(c.s0 + g) * c.a.n_blocks + c.t;
+    const size_t o = (size_t)(Sid(c, g)) * c.a.n_blocks + c.t;
     if (c.a.psk_bits) c.a.psk_bits[o] = -1;
     if (c.a.psk_chars) c.a.psk_chars[o] = 0;
   }
@@ -1471,8 +1486,8 @@ T41RX_DEV void PhInterp2(Cta &c, int tid) {
   const int g = tid >> 6, u = tid & 63;
   if (g >= c.ng) return;
   float *s = Slot(c, g);
-  const float volume = c.a.cfg[c.s0 + g].volume;
-  float4 *dst = reinterpret_cast<float4 *>(c.a.audio + ((size_t)(c.s0 + g) * c.a.n_blocks + c.t) * kBlock);
+  const float volume = c.a.cfg[Sid(c, g)].volume;
+  float4 *dst = reinterpret_cast<float4 *>(c.a.audio + ((size_t)(Sid(c, g)) * c.a.n_blocks + c.t) * kBlock);
   for (int h = u; h < 23; h += 64) s[oIntH + h] = s[vAud + kDec + h];   /* int1 history for the next block */
   float taps[kInt2Taps];
 #pragma unroll
@@ -1508,7 +1523,7 @@ T41RX_DEV void PhBlockEnd(Cta &c, int tid) {
     float *s = Slot(c, g);
     for (int h = tid; h < 7; h += kNT) s[oIntH + 24 + h] = s[vInt2 + 2 * kDec + h];
     if (tid == kNT - 1) {
-      StreamState &st = c.a.st[c.s0 + g];
+      StreamState &st = c.a.st[Sid(c, g)];
       uint32_t timer = st.codec_timer + 1;
       if (timer > 10000) timer = 10000;
       if (timer >= 50) {
@@ -1521,6 +1536,49 @@ T41RX_DEV void PhBlockEnd(Cta &c, int tid) {
     }
   }
 }
+
+/* ------------------------------------------------------------------ */
+/* rows-only kernel: display spectrum of the row-producing blocks for the receivers the            */
+/* throughput kernel serves (same phase functions as above; runs BEFORE that kernel in the stream)  */
+/* ------------------------------------------------------------------ */
+/* DC-block state at the start of block t: the carried state for t = 0, otherwise the state reached by
+ * filtering the last 256 Q samples of block t-1 from zero (pole 0.854: converged to the last bit, the
+ * same argument as P1's speculative chunks) */
+T41RX_DEV void PhRowDcSeed(Cta &c, int tid) {
+  const int g = SerialStream(c, tid);
+  if (g < 0) return;
+  float *s = Slot(c, g);
+  const StreamState &st = c.a.st[Sid(c, g)];
+  if (c.t == 0) {
+    s[oMisc + mDcD1] = st.dc_d1;
+    s[oMisc + mDcD2] = st.dc_d2;
+    return;
+  }
+  const DcCoef k = DcCoefs();
+  const float rfg = c.a.cfg[Sid(c, g)].rf_gain_value;
+  const float *q = c.a.iq + ((size_t)Sid(c, g) * c.a.n_blocks + (c.t - 1)) * (2 * kBlock) + 2 * (kBlock - kDcWarm) + 1;
+  float d1 = 0.0f, lx = 0.0f, ly = 0.0f;
+  for (int i = 0; i < kDcWarm; ++i) {
+    const float x = LdgRO(q + 2 * i) * rfg;
+    ly = DcStep(k, x, d1);
+    lx = x;
+  }
+  s[oMisc + mDcD1] = d1;
+  s[oMisc + mDcD2] = DcD2(lx, ly);
+}
+
+#define T41RX_ROWS_SCHEDULE(RX_PHASE)                                    \
+  RX_PHASE(PhLoad(c, tid); PhRowDcSeed(c, tid));                         \
+  RX_PHASE(PhDcWarm(c, tid));                                            \
+  RX_PHASE(PhDcMain(c, tid));                                            \
+  RX_PHASE(PhDcVerify(c, tid));                                          \
+  RX_PHASE(PhDcFix(c, tid));                                             \
+  RX_PHASE(PhZoomIir(c, tid));                                           \
+  RX_PHASE(PhSpecWindow(c, tid));                                        \
+  RX_PHASE(PhSpecFftPass(c, tid, 0));                                    \
+  RX_PHASE(PhSpecFftPass(c, tid, 1));                                    \
+  RX_PHASE(PhSpecFftPass(c, tid, 2));                                    \
+  RX_PHASE(PhSpecRow(c, tid));
 
 /* ------------------------------------------------------------------ */
 /* the block schedule; RX_PHASE(stmt) runs stmt for every tid then syncs */

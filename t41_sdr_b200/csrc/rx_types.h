@@ -120,6 +120,12 @@ struct StreamState {
   int32_t pad_;
   float zoom_ring[2][kSpecRes];
   float spec_old[kSpecRes];
+  /* throughput kernel (rx_fast.cuh): its own forms of the DC-block state and of the oscillator angle, kept
+     beside the reference forms above so that a run cut into several calls is bit-identical to one call;
+     valid while fast_native != 0 (the bit-exact kernel clears it) */
+  int32_t fast_native;
+  float fast_dc_w;
+  double fast_ph_re, fast_ph_im;
 };
 
 }  // namespace t41rx

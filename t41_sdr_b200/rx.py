@@ -18,7 +18,9 @@ LIB_PATH = os.environ.get("T41RX_LIB", os.path.join(_HERE, "libt41rx.so"))
 DEMOD_USB, DEMOD_LSB, DEMOD_AM, DEMOD_NFM, DEMOD_PSK31, DEMOD_SAM = 0, 1, 2, 3, 5, 8
 BLOCK = 2048
 SPECTRUM_RES = 512
-FLAG_EXACT_NCO = 1
+FLAG_EXACT_NCO = 1       # bit-exact kernel, step-by-step FP64 oscillator
+FLAG_PHASED_KERNEL = 2   # bit-exact kernel with the closed-form FP64 oscillator
+# flags = 0: the throughput kernel
 
 # algorithmic HBM bytes per stream-block
 BYTES_PER_BLOCK = 2 * BLOCK * 4 + BLOCK * 4        # 16 KiB I/Q in + 8 KiB audio out

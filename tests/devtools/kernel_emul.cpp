@@ -51,6 +51,9 @@ int emul_set_params_each(Emul *e, int first, int count, const t41rx_params *p) {
   return 0;
 }
 
+/* emulation-only flag: produce the spectrum rows with the rows-only schedule (T41RX_ROWS_SCHEDULE) */
+static const uint32_t kEmulSplitRows = 0x100u;
+
 int emul_process(Emul *e, const float *iq, float *audio, int n_blocks, int row_every, int16_t *spec_rows,
                  uint16_t *wf_rows, int8_t *psk_bits, uint8_t *psk_chars, uint32_t flags) {
   HostModel &h = e->host;
@@ -93,16 +96,31 @@ int emul_process(Emul *e, const float *iq, float *audio, int n_blocks, int row_e
     c.t = 0;
     c.row = 0;
     c.row_idx = 0;
+    c.rows_only = 0;
     /* poison: shared memory is uninitialised at CTA start on the GPU */
     for (int i = 0; i < kSmemFloats; ++i) smem[i] = NAN;
 #define EMUL_PHASE(stmt) \
   do {                   \
     for (int tid = 0; tid < kNT; ++tid) { stmt; } \
   } while (0)
+    const bool split_rows = (flags & kEmulSplitRows) != 0 && row_every > 0;
+    if (split_rows) {
+      /* what the product does around the throughput kernel: the rows-only schedule first, on the state
+         of launch start, then the chain itself without rows */
+      c.rows_only = 1;
+      for (int t = 0; t < n_blocks; t += row_every) {
+        c.t = t;
+        c.row = 1;
+        c.row_idx = t / row_every;
+        T41RX_ROWS_SCHEDULE(EMUL_PHASE)
+      }
+      c.rows_only = 0;
+      for (int i = 0; i < kSmemFloats; ++i) smem[i] = NAN;
+    }
     EMUL_PHASE(PhStateIn(c, tid));
     for (int t = 0; t < n_blocks; ++t) {
       c.t = t;
-      c.row = (row_every > 0) && (t % row_every == 0);
+      c.row = !split_rows && (row_every > 0) && (t % row_every == 0);
       c.row_idx = c.row ? t / row_every : 0;
       T41RX_BLOCK_SCHEDULE(EMUL_PHASE)
     }

@@ -1,12 +1,14 @@
 """GPU tier: the CUDA path, called through the C-ABI (libt41rx.so), against the CPU oracle.
 
- * exact-oscillator mode (T41RX_FLAG_EXACT_NCO): every output and every piece of debug state
-   is BIT-IDENTICAL to the oracle on all cases (C1-C5 scaled down + edge cases), and the
-   audio digests equal the golden vectors the reference itself produced;
- * default mode (closed-form FP64 oscillator): audio SNR >= 90 dB (in practice > 120 dB, with
-   > 99.9 % of samples bit-identical), spectrum rows within 1 LSB and >= 99.9 % identical,
-   PSK31 bits / characters and AGC / mode state transitions identical (tolerance stated by the
-   north star; checked in rx_driver.assert_within_tolerance);
+ * bit-exact kernel, exact oscillator (T41RX_FLAG_EXACT_NCO): every output and every piece of
+   debug state is BIT-IDENTICAL to the oracle on all cases (C1-C5 scaled down + edge cases), and
+   the audio digests equal the golden vectors the reference itself produced;
+ * bit-exact kernel, closed-form FP64 oscillator (T41RX_FLAG_PHASED_KERNEL): audio SNR > 120 dB
+   with > 99.9 % of samples bit-identical;
+ * default = throughput kernel (FP32 with FMA contraction, blocked-scan recurrences; SAM receivers
+   stay on the bit-exact kernel): the tolerance the north star states -- audio SNR >= 90 dB
+   (measured: > 100 dB), spectrum rows within 1 LSB and >= 99.9 % identical, PSK31 bits /
+   characters and AGC / mode state transitions identical (rx_driver.assert_within_tolerance);
  * at BASELINE.json's full sizes: size-independent properties (call-chunking invariance,
    receiver permutation invariance, replicated receivers agree) plus oracle spot checks.
 """
@@ -60,19 +62,38 @@ def test_exact_mode_matches_reference_golden(make):
             assert np.array_equal(r["psk_chars"], golden[key + "psk_chars"]), key
 
 
+def _drop_nan_receivers(case, got, want):
+    if case.name == "edge_silence_fullscale":
+        # NaN audio (0/0 in the NFM discriminator on silence) has no SNR: compare the rest
+        keep = [i for i, w in enumerate(want) if not np.isnan(w["audio"]).any()]
+        return [got[i] for i in keep], [want[i] for i in keep]
+    return got, want
+
+
+@pytest.mark.parametrize("make", cases.ALL_CASES, ids=lambda m: m.__name__)
+def test_phased_kernel_closed_form_nco(make):
+    case = make()
+    want = cases.run_case_on(case, lambda p: O.OracleStream(p))
+    with _receiver(case.n_streams) as eng:
+        got = rx_driver.run_case_batched(case, eng, flags=rx.FLAG_PHASED_KERNEL)
+    got, want = _drop_nan_receivers(case, got, want)
+    stats = rx_driver.assert_within_tolerance(case, got, want, min_snr_db=90.0)
+    assert min(snr for snr, _ in stats) >= 120.0
+    assert min(frac for _, frac in stats) >= 0.999
+
+
 @pytest.mark.parametrize("make", cases.ALL_CASES, ids=lambda m: m.__name__)
 def test_default_mode_within_stated_tolerance(make):
+    """flags = 0: the throughput kernel (+ the rows kernel; SAM receivers on the bit-exact kernel).
+    Stated tolerance: audio SNR >= 90 dB per receiver over the run, rows within 1 LSB, discrete
+    state and PSK31 output identical."""
     case = make()
     want = cases.run_case_on(case, lambda p: O.OracleStream(p))
     with _receiver(case.n_streams) as eng:
         got = rx_driver.run_case_batched(case, eng, flags=0)
-    if case.name == "edge_silence_fullscale":
-        # NaN audio (0/0 in the NFM discriminator on silence) has no SNR: compare the rest
-        keep = [i for i, w in enumerate(want) if not np.isnan(w["audio"]).any()]
-        got, want = [got[i] for i in keep], [want[i] for i in keep]
+    got, want = _drop_nan_receivers(case, got, want)
     stats = rx_driver.assert_within_tolerance(case, got, want, min_snr_db=90.0)
-    assert min(snr for snr, _ in stats) >= 120.0
-    assert min(frac for _, frac in stats) >= 0.999
+    assert min(snr for snr, _ in stats) >= 100.0      # measured margin over the stated 90 dB
 
 
 def test_psk31_text_is_decoded():
@@ -128,7 +149,7 @@ def test_c2_full_size_1024_receivers():
     # spot check against the oracle (default mode tolerance)
     for k in range(D):
         w = O.OracleStream(base_p[k]).process(base_iq[k], T)
-        assert O.snr_db(w["audio"], audio[k]) >= 120.0
+        assert O.snr_db(w["audio"], audio[k]) >= 100.0
         assert np.abs(w["spec"].astype(int) - one["spec"][k].astype(int)).max() <= 1
     # call-chunking invariance: 16 blocks at once == 5 + 11 blocks (state hand-over through HBM)
     with _receiver(S) as eng:
@@ -171,7 +192,7 @@ def test_c3_full_size_8192_nfm_sam_state_transitions():
         dbg = [eng.debug(s) for s in (0, 1, 2, 3, 4, 5, 6, 7, S - 8, S - 7, S - 2, S - 1)]
     want = cases.run_case_on(cases.Case(case.name, case.segments, case.iq), lambda p: O.OracleStream(p))
     for k in range(D):
-        assert O.snr_db(want[k]["audio"], out["audio"][k]) >= 120.0
+        assert O.snr_db(want[k]["audio"], out["audio"][k]) >= 100.0
         grp = out["audio"][k::D]
         assert np.array_equal(grp.view(np.uint32), np.broadcast_to(grp[0], grp.shape).view(np.uint32))
     for d, s in zip(dbg, (0, 1, 2, 3, 4, 5, 6, 7, S - 8, S - 7, S - 2, S - 1)):

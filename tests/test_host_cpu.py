@@ -125,3 +125,20 @@ def test_kernel_phases_emulated_closed_form_nco(make):
     eng.close()
     stats = rx_driver.assert_within_tolerance(case, got, want, min_snr_db=120.0)
     assert min(f for _, f in stats) > 0.999      # almost every sample is bit-identical
+
+
+EMUL_SPLIT_ROWS = 0x100   # tests/devtools/kernel_emul.cpp: rows through the rows-only schedule
+
+
+@pytest.mark.parametrize("make", [cases.c1_single_usb, cases.c3_nfm_sam_agc, cases.c4_zoom_rows,
+                                  cases.edge_param_changes], ids=lambda m: m.__name__)
+def test_rows_only_schedule_emulated(make):
+    """The rows-only schedule (what t41rx_rows_kernel runs beside the throughput kernel: DC-block state
+    seeded from the previous block's tail, RFgain extrapolated from the launch-start state) must give
+    the oracle's spectrum and waterfall rows bit for bit, and leave the rest of the chain untouched."""
+    case = make()
+    want = cases.run_case_on(case, lambda p: O.OracleStream(p))
+    eng = rx_driver.EmulReceiver(case.n_streams)
+    got = rx_driver.run_case_batched(case, eng, flags=rx.FLAG_EXACT_NCO | EMUL_SPLIT_ROWS)
+    eng.close()
+    rx_driver.assert_identical(case, got, want)

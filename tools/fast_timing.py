@@ -46,6 +46,7 @@ def main():
     for i, n in enumerate(NAMES):
         if n:
             print("  %-18s %8.0f  %5.1f%%" % (n, v[i], 100 * v[i] / (tot if i < 16 else v[16:18].sum())))
+    print("  agc fallback chunks per block (of 32): %.2f" % v[20])
 
 
 if __name__ == "__main__":
