@@ -69,6 +69,9 @@ def workload(n_blocks):
         else:
             params.append(cases.P(mode=cases.AM, nco_freq=nco, agc_mode=1))
             sigs.append(synth.am(900 + k, n_blocks, mode=cases.AM, nco_freq=nco, depth=0.5, f_mod=400.0))
+    if os.environ.get("T41RX_BENCH_ZOOM"):       # developer knob (rows-kernel experiments)
+        for p in params:
+            p.spectrum_zoom = int(os.environ["T41RX_BENCH_ZOOM"])
     return params, sigs
 
 

@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(kNT, 8 / kG) t41rx_rows_kernel(const LaunchArg
     stmt;                  \
     __syncthreads();       \
   } while (0)
-    T41RX_ROWS_SCHEDULE(T41RX_KPHASE)
+    T41RX_ROWS_SCHEDULE_FAST(T41RX_KPHASE)
 #undef T41RX_KPHASE
   }
 }

@@ -4,6 +4,7 @@
  * rx_api.cu.
  */
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "rx_fast.cuh"
 #include "rx_launch.h"
@@ -30,7 +31,7 @@ extern "C" int t41rx_debug_fast_cycles(unsigned long long *out32, int reset) {
 
 cudaError_t ConfigureStreamKernel() {
   return cudaFuncSetAttribute(t41rx_stream_rx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)(fast::kFastMaxG * fast::kSlotF * sizeof(float)));
+                              (int)(fast::kFastMaxG * fast::kSlotF * sizeof(float) + 64));
 }
 
 cudaError_t LaunchStreamKernel(const LaunchArgs &a, int n_sms, cudaStream_t st) {
@@ -39,8 +40,12 @@ cudaError_t LaunchStreamKernel(const LaunchArgs &a, int n_sms, cudaStream_t st) 
   int G = (a.n_streams + n_sms - 1) / n_sms;
   if (G < 1) G = 1;
   if (G > fast::kFastMaxG) G = fast::kFastMaxG;
+  if (const char *e = getenv("T41RX_FAST_G")) {          /* developer knob: receivers per CTA */
+    const int g = atoi(e);
+    if (g >= 1 && g <= fast::kFastMaxG) G = g;
+  }
   const int grid = (a.n_streams + G - 1) / G;
-  t41rx_stream_rx_kernel<<<grid, 64 * G + 32, (size_t)G * fast::kSlotF * sizeof(float), st>>>(a, G);
+  t41rx_stream_rx_kernel<<<grid, 64 * G + 32, (size_t)G * fast::kSlotF * sizeof(float) + 64, st>>>(a, G);
   return cudaGetLastError();
 }
 

@@ -6,7 +6,7 @@
  *   - one CTA owns G <= kFastMaxG receivers for all n_blocks blocks of a launch;
  *   - TWO WARPS PER RECEIVER run every sample-parallel stage (64-thread named barriers between stages);
  *   - one extra warp runs the AGC envelope state machine with lane = receiver;
- *   - blocks are software-pipelined with one __syncthreads per block: in superstep k a receiver's
+ *   - blocks are software-pipelined through mbarriers (no block-wide barrier in the steady state): in superstep k a receiver's
  *     warp pair does back end(k-2) then front end(k), the AGC warp does AGC(k-1).
  * Linear recurrences (DC block, AM detector filters) are blocked scans, the NCO is a closed-form
  * FP32 phasor driven by an FP64 block phasor, the fast-convolution filter fuses the last forward
@@ -51,7 +51,8 @@ constexpr int oMH = oIH + 32;                         /* 7692: dec1 history, 8 p
 constexpr int oDH = oMH + 64;                         /* 7756: dec2 history, 4 planes x 24 */
 constexpr int oMiscF = oDH + 96;                      /* 7852 */
 constexpr int kSlotF = oMiscF + 20;                   /* == 4 (mod 8): the AGC warp's LDS.128 hit distinct banks */
-enum { mEndI = 0, mEndQ = 1, mSettled = 2, mPhasor = 4 /* 2 doubles */ };
+enum { mEndI = 0, mEndQ = 1, mSettled = 2, mPhasor = 4 /* 2 doubles */, mInvIn = 8, mTarget = 9, mSlope = 10,
+       mOmF = 12, mOmH = 13, mFbm = 14, mHbm = 15 };
 static_assert((oMiscF % 2) == 0 && (oTapsF % 4) == 0, "alignment");
 static_assert(kSlotF % 8 == 4, "slot stride");
 static_assert((oStA % 4) == 0 && (oStZ % 4) == 0 && (oRaw % 4) == 0 && (oMix % 4) == 0 && (oD1 % 4) == 0, "16-byte alignment");
@@ -123,6 +124,24 @@ __device__ __forceinline__ void CpAsync16(void *smem_dst, const void *gsrc) {
 __device__ __forceinline__ void CpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void CpAsyncWaitAll() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+/* ---- mbarriers (shared::cta): the hand-shake between the receiver pairs and the AGC warp ---- */
+__device__ __forceinline__ void MbarInit(uint64_t *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void MbarArrive(uint64_t *bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void MbarWait(uint64_t *bar, unsigned parity) {
+  const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(addr), "r"(parity) : "memory");
+}
+
 /* everything a receiver warp keeps in registers across blocks (uniform over the lanes unless noted) */
 struct RxRegs {
   /* configuration */
@@ -136,6 +155,9 @@ struct RxRegs {
   double ph_re, ph_im;   /* unit block phasor exp(j * phase) of the oscillator */
   int nco_closed;
   double osc_q, osc_i;   /* Osc_Vect while the amplitude loop is still settling (lane 0) */
+  double blk_cos, blk_sin;   /* rotation of the block phasor over 2048 samples */
+  const char *cp_src;    /* this thread's first 16-byte piece of quarter 0 of block 0 */
+  unsigned cp_dst;       /* its shared-memory address in raw buffer 0 */
   /* lane constants */
   F2 lane_rot;           /* nco_amp * exp(-j * delta * (8 * tau + 1)) */
   float tail_w;          /* a1^(4 * lane): weight of this lane's partial sum in the I-tail pre-read */
@@ -255,15 +277,14 @@ struct RxPair {
 
   /* issue this thread's share of the asynchronous copy of quarter q of block t into raw buffer (q & 1) */
   __device__ __forceinline__ void IssueQuarter(int t, int q) {
-    const char *src = reinterpret_cast<const char *>(BlockIq(t)) + q * 4096;
-    char *dst = reinterpret_cast<char *>(s + oRaw + (q & 1) * kRawBufWords);
+    /* one warp instruction copies 8 chunks (512 contiguous bytes); the 8 lanes of a quarter-warp write the
+       same 16-byte piece of 8 different chunks: distinct banks (chunk stride 20 words).  Thread (w2, lane)
+       copies piece (lane >> 3) of chunks 16 i + 8 w2 + (lane & 7), i = 0..3 */
+    const char *src = r.cp_src + ((size_t)t * 4 + q) * 4096;
+    const unsigned dst = r.cp_dst + (q & 1) * (kRawBufWords * 4);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      /* one warp instruction copies 8 chunks (512 contiguous bytes); the 8 lanes of a quarter-warp write the
-         same 16-byte piece of 8 different chunks: distinct banks (chunk stride 20 words) */
-      const int chunk = 16 * i + 8 * w2 + (lane & 7), piece = lane >> 3;
-      CpAsync16(dst + chunk * (kRawChunkWords * 4) + piece * 16, src + chunk * 64 + piece * 16);
-    }
+    for (int i = 0; i < 4; ++i)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 16 * (kRawChunkWords * 4)), "l"(src + i * 1024) : "memory");
     CpAsyncCommit();
   }
 
@@ -309,6 +330,21 @@ struct RxPair {
       r.lane_rot = F2{(float)(cf.nco_amp * cs), (float)(cf.nco_amp * sn)};
     }
     r.tail_w = PowA1(4 * lane);
+    sincos(cf.nco_block_delta, &r.blk_sin, &r.blk_cos);
+    {
+      const int chunk0 = 8 * w2 + (lane & 7), piece = lane >> 3;
+      r.cp_src = reinterpret_cast<const char *>(BlockIq(0)) + chunk0 * 64 + piece * 16;
+      r.cp_dst = (unsigned)__cvta_generic_to_shared(s + oRaw) + chunk0 * (kRawChunkWords * 4) + piece * 16;
+    }
+    if (tau == 1) {
+      s[oMiscF + mInvIn] = cf.agc.inv_max_input;
+      s[oMiscF + mTarget] = cf.agc.out_target;
+      s[oMiscF + mSlope] = cf.agc.slope_constant;
+      s[oMiscF + mOmF] = cf.agc.onemfast_backmult;
+      s[oMiscF + mOmH] = cf.agc.onemhang_backmult;
+      s[oMiscF + mFbm] = cf.agc.fast_backmult;
+      s[oMiscF + mHbm] = cf.agc.hang_backmult;
+    }
     /* DC-block recurrence value after the previous block's last Q sample (feeds this block's I chain, B6) */
     if (tau == 0) {
       s[oMiscF + mEndQ] = st.fast_native ? st.fast_dc_w : st.dc_d1 / (kDcB0 * (kDcA1 - 1.0f) * cf.rf_gain_value);
@@ -513,8 +549,13 @@ struct RxPair {
     }
     /* I *= -IQAmp, phase correction (Process.cpp:165-174, Utility.cpp:178-187) */
     if (r.mirrored) {
+      if (r.neg_iq_amp == -1.0f) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) yi[j] *= r.neg_iq_amp;
+        for (int j = 0; j < 8; ++j) yi[j] = -yi[j];      /* folds into the consumers' operand modifiers */
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) yi[j] *= r.neg_iq_amp;
+      }
       if (r.iq_phase != 0.0f) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -631,14 +672,13 @@ struct RxPair {
   }
 
   /* FE for block t */
-  __device__ void FrontEnd(int t, int buf) {
+  __device__ void FrontEnd(int t, int buf, float4 tail_u, float4 tail_v) {
     const StreamCfg &cf = a.cfg[sid];
     /* the recurrence value entering the Q chain is the one leaving the I chain (B6): pre-read the last
        128 I samples of the block (a1^128 ~ 2e-9); only warp 0's lane 0 consumes it */
     float tail = 0.0f;
     if (w2 == 0) {
-      const float4 *p = reinterpret_cast<const float4 *>(BlockIq(t) + 2 * (kBlock - 4 * (lane + 1)));
-      const float4 u = __ldg(p), v = __ldg(p + 1);    /* samples n0 .. n0+3, n0 = 2044 - 4 lane */
+      const float4 u = tail_u, v = tail_v;            /* samples n0 .. n0+3, n0 = 2044 - 4 lane */
       float acc = u.x;                                 /* oldest first */
       acc = fmaf(kDcA1, acc, u.z);
       acc = fmaf(kDcA1, acc, v.x);
@@ -718,9 +758,7 @@ struct RxPair {
     }
     if (closed) {
       /* advance the block phasor by 2048 samples */
-      double sn, cs;
-      sincos(cf.nco_block_delta, &sn, &cs);
-      const double nr = r.ph_re * cs - r.ph_im * sn, ni = r.ph_re * sn + r.ph_im * cs;
+      const double nr = r.ph_re * r.blk_cos - r.ph_im * r.blk_sin, ni = r.ph_re * r.blk_sin + r.ph_im * r.blk_cos;
       r.ph_re = nr;
       r.ph_im = ni;
     } else if (s[oMiscF + mSettled] != 0.0f) {      /* written before the last PairSync of quarter 3 */
@@ -855,15 +893,14 @@ struct RxPair {
       if (c < 32) {
         /* zero-state advance of the AGC's two back-averages over this chunk of 8 delayed magnitudes
            (DSP_Fn.cpp:521-522 are linear recurrences: the AGC warp applies them once per chunk) */
-        const AgcConsts &ag = a.cfg[sid].agc;
-        const float of = ag.onemfast_backmult, oh = ag.onemhang_backmult;
+        const float of = s[oMiscF + mOmF], oh = s[oMiscF + mOmH];
         float pf = 0.0f, ph = 0.0f;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           pf = fmaf(of, pf, v[k]);
           ph = fmaf(oh, ph, v[k]);
         }
-        *reinterpret_cast<float2 *>(sta + 512 + 2 * c) = float2{pf * ag.fast_backmult, ph * ag.hang_backmult};
+        *reinterpret_cast<float2 *>(sta + 512 + 2 * c) = float2{pf * s[oMiscF + mFbm], ph * s[oMiscF + mHbm]};
       }
     }
 #pragma unroll
@@ -990,8 +1027,7 @@ struct RxPair {
       for (int o = 0; o < 4; ++o) dem[o] = float2{dem[o].x * r.fixed_gain, dem[o].y * r.fixed_gain};
       return;
     }
-    const AgcConsts &ag = cf.agc;
-    const float inv_in = ag.inv_max_input, tgt = ag.out_target, slope = ag.slope_constant;
+    const float inv_in = s[oMiscF + mInvIn], tgt = s[oMiscF + mTarget], slope = s[oMiscF + mSlope];
 #pragma unroll
     for (int o = 0; o < 4; ++o) {
       const float v = volts[tau + 64 * o];
@@ -1380,27 +1416,49 @@ __device__ __forceinline__ void StreamKernelBody(const LaunchArgs &a, int G, flo
   const int s0 = blockIdx.x * G;
   const int ng = min(G, a.n_streams - s0);
   const int T = a.n_blocks;
+  /* block j's front ends -> AGC: full[j & 1] (every thread of every live pair arrives);
+     AGC -> block j's back ends: done[j & 1] (the AGC warp's 32 lanes arrive).  A receiver pair may run up
+     to one block ahead of the others; the double-buffered hand-off areas allow exactly that. */
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + G * kSlotF);
+  uint64_t *done = full + 2;
+  if (threadIdx.x == 0) {
+    MbarInit(full + 0, 64u * ng);
+    MbarInit(full + 1, 64u * ng);
+    MbarInit(done + 0, 32u);
+    MbarInit(done + 1, 32u);
+  }
+  __syncthreads();
   if (warp < 2 * G) {
     /* ---- receiver pair ---- */
     const int pair = warp >> 1;
     const bool live = pair < ng;
-    const int sid = live ? (a.stream_ids ? __ldg(a.stream_ids + s0 + pair) : s0 + pair) : 0;
+    if (!live) return;
+    const int sid = a.stream_ids ? __ldg(a.stream_ids + s0 + pair) : s0 + pair;
     RxPair w(a, smem + pair * kSlotF, sid, lane, warp & 1, 1 + pair);
-    if (live) {
-      w.LoadState();
-      w.IssueQuarter(0, 0);
-    }
+    w.LoadState();
+    w.IssueQuarter(0, 0);
     w.tm.Start(blockIdx.x == 0 && warp == 0 && lane == 0, 0);
     for (int k = 0; k < T + 2; ++k) {
-      if (live) {
-        if (k >= 2) w.BackEnd(k - 2, k & 1);
-        if (k < T) w.FrontEnd(k, k & 1);
+      /* the last 128 I samples of block k (see FrontEnd) are fetched before the back end: their HBM
+         latency hides behind it */
+      float4 tu = float4{0, 0, 0, 0}, tv = tu;
+      if (k < T && (warp & 1) == 0) {
+        const float4 *p = reinterpret_cast<const float4 *>(w.BlockIq(k) + 2 * (kBlock - 4 * (lane + 1)));
+        tu = __ldg(p);
+        tv = __ldg(p + 1);
+      }
+      if (k >= 2) {
+        MbarWait(done + (k & 1), (unsigned)(((k - 2) >> 1) & 1));
+        T41RX_LAP(w.tm, 12);
+        w.BackEnd(k - 2, k & 1);
+      }
+      if (k < T) {
+        w.FrontEnd(k, k & 1, tu, tv);
+        MbarArrive(full + (k & 1));
       }
       T41RX_LAP(w.tm, 11);
-      __syncthreads();
-      T41RX_LAP(w.tm, 12);
     }
-    if (live) w.StoreState();
+    w.StoreState();
   } else {
     /* ---- AGC warp ---- */
     AgcLane g;
@@ -1415,11 +1473,12 @@ __device__ __forceinline__ void StreamKernelBody(const LaunchArgs &a, int G, flo
     float *slot = smem + (mine ? lane : 0) * kSlotF;
     SectionTimer tm;
     tm.Start(blockIdx.x == 0 && lane == 0, 16);
-    for (int k = 0; k < T + 2; ++k) {
-      if (k >= 1 && k <= T) AgcBlock(g, slot + oStA + ((k - 1) & 1) * kStABuf, active);
-      T41RX_LAP(tm, 0);
-      __syncthreads();
+    for (int j = 0; j < T; ++j) {
+      MbarWait(full + (j & 1), (unsigned)((j >> 1) & 1));
       T41RX_LAP(tm, 1);
+      AgcBlock(g, slot + oStA + (j & 1) * kStABuf, active);
+      MbarArrive(done + (j & 1));
+      T41RX_LAP(tm, 0);
     }
     if (mine && active) g.Store(a.st[sid]);
   }

@@ -1567,6 +1567,267 @@ T41RX_DEV void PhRowDcSeed(Cta &c, int tid) {
   s[oMisc + mDcD2] = DcD2(lx, ly);
 }
 
+#ifndef T41RX_HOST_EMUL
+/* ---- device-only throughput forms of the two serial pieces of the rows-only kernel ---- */
+constexpr int vRowTail = oOla;                    /* 256 floats: last Q samples of the previous block */
+
+/* stage the 256 samples PhRowDcSeed filters (coalesced instead of 256 dependent global loads) */
+T41RX_DEV void PhRowTailLoad(Cta &c, int tid) {
+  if (c.t == 0) return;
+  const int g = tid >> 6, u = tid & 63;
+  if (g >= c.ng) return;
+  float *s = Slot(c, g);
+  const float2 *q = reinterpret_cast<const float2 *>(c.a.iq + ((size_t)Sid(c, g) * c.a.n_blocks + (c.t - 1)) * (2 * kBlock)) + (kBlock - kDcWarm);
+  for (int i = u; i < kDcWarm; i += 64) s[vRowTail + i] = LdgRO(q + i).y;
+}
+T41RX_DEV void PhRowDcSeedFast(Cta &c, int tid) {
+  const int g = SerialStream(c, tid);
+  if (g < 0) return;
+  float *s = Slot(c, g);
+  const StreamState &st = c.a.st[Sid(c, g)];
+  if (c.t == 0) {
+    s[oMisc + mDcD1] = st.dc_d1;
+    s[oMisc + mDcD2] = st.dc_d2;
+    return;
+  }
+  const DcCoef k = DcCoefs();
+  const float rfg = c.a.cfg[Sid(c, g)].rf_gain_value;
+  float d1 = 0.0f, lx = 0.0f, ly = 0.0f;
+  for (int i0 = 0; i0 < kDcWarm; i0 += 8) {
+    float x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = s[vRowTail + i0 + j] * rfg;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ly = DcStep(k, x[j], d1); lx = x[j]; }
+  }
+  s[oMisc + mDcD1] = d1;
+  s[oMisc + mDcD2] = DcD2(lx, ly);
+}
+
+/* ZoomFFTExe's input: IQ correction + Fs/4 shift, in place (FFT.cpp:83-84 run on the *_EX buffers) */
+T41RX_DEV void PhZoomShift(Cta &c, int tid) {
+  const int g = tid >> 6, u = tid & 63;
+  if (g >= c.ng) return;
+  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+  if (cf.zoom == 0) return;
+  float *s = Slot(c, g);
+  const IqFix fix = IqFixOf(cf);
+  for (int n = u; n < kBlock; n += 64) {
+    float vi = s[oRawI + 27 + n], vq = s[oRawQ + 27 + n];
+    IqCorr(fix, vi, vq);
+    QuarterShift(n, vi, vq);
+    s[oRawI + 27 + n] = vi;
+    s[oRawQ + 27 + n] = vq;
+  }
+}
+
+/* The 4-stage elliptic DF1 cascade (arm_biquad_cascade_df1_f32, FFT.cpp:83-84) as blocked linear scans:
+ * one warp per channel, lane L owns samples 65 L .. 65 L + 64 (odd stride: conflict-free), every stage =
+ * zero-state pass, 2x2 carry scan over the lanes, correction pass with the two homogeneous responses.
+ * FP32 results differ from the sample-by-sample form in the last bits (rows tolerance: 1 LSB). */
+T41RX_DEV void PhZoomIirScan(Cta &c, int tid) {
+  const int g = tid >> 6, u = tid & 63;
+  if (g >= c.ng) return;
+  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+  if (cf.zoom == 0) return;                          /* warp-uniform */
+  StreamState &st = c.a.st[Sid(c, g)];
+  const int chn = u >> 5, lane = u & 31;
+  float *x = Slot(c, g) + (chn ? oRawQ : oRawI) + 27;
+  constexpr int kLen = 65;
+  const int n0 = kLen * lane;
+  const int n1 = (n0 + kLen < kBlock) ? n0 + kLen : kBlock;
+  const unsigned full = 0xffffffffu;
+  for (int sg = 0; sg < 4; ++sg) {
+    const float *kk = c.a.zoom_iir + (cf.zoom - 1) * 20 + 5 * sg;
+    const float b0 = LdgRO(kk), b1 = LdgRO(kk + 1), b2 = LdgRO(kk + 2), a1 = LdgRO(kk + 3), a2 = LdgRO(kk + 4);
+    /* inputs just before the chunk (previous lane's last two, or the carried state) */
+    float x1 = (lane == 0) ? st.zoom_iir[chn][4 * sg] : x[n0 - 1];
+    float x2 = (lane == 0) ? st.zoom_iir[chn][4 * sg + 1] : ((n0 >= 2) ? x[n0 - 2] : 0.0f);
+    const float sx1 = x[kBlock - 1], sx2 = x[kBlock - 2];       /* this stage's input history for the next block */
+    __syncwarp(full);
+    /* zero-state pass, in place */
+    float y1 = 0.0f, y2 = 0.0f;
+    for (int n = n0; n < n1; ++n) {
+      const float xn = x[n];
+      float f = b0 * xn;
+      f = fmaf(b1, x1, f);
+      f = fmaf(b2, x2, f);
+      const float y = fmaf(a1, y1, fmaf(a2, y2, f));
+      x[n] = y;
+      x2 = x1; x1 = xn;
+      y2 = y1; y1 = y;
+    }
+    /* chunk transfer matrix M = A^65 from the homogeneous responses */
+    float u1 = 1.0f, u2 = 0.0f, v1 = 0.0f, v2 = 1.0f;
+    for (int j = 0; j < kLen; ++j) {
+      const float un = fmaf(a1, u1, a2 * u2), vn = fmaf(a1, v1, a2 * v2);
+      u2 = u1; u1 = un;
+      v2 = v1; v1 = vn;
+    }
+    float m00 = u1, m01 = v1, m10 = u2, m11 = v2;
+    float s1 = y1, s2 = y2;
+    if (lane == 0) {
+      const float c1 = st.zoom_iir[chn][4 * sg + 2], c2 = st.zoom_iir[chn][4 * sg + 3];
+      s1 += m00 * c1 + m01 * c2;
+      s2 += m10 * c1 + m11 * c2;
+    }
+    for (int d = 1; d < 32; d <<= 1) {
+      const float t1 = __shfl_up_sync(full, s1, d), t2 = __shfl_up_sync(full, s2, d);
+      if (lane >= d) {
+        s1 += m00 * t1 + m01 * t2;
+        s2 += m10 * t1 + m11 * t2;
+      }
+      const float q00 = m00 * m00 + m01 * m10, q01 = m00 * m01 + m01 * m11;
+      const float q10 = m10 * m00 + m11 * m10, q11 = m10 * m01 + m11 * m11;
+      m00 = q00; m01 = q01; m10 = q10; m11 = q11;
+    }
+    float c1 = __shfl_up_sync(full, s1, 1), c2 = __shfl_up_sync(full, s2, 1);
+    if (lane == 0) { c1 = st.zoom_iir[chn][4 * sg + 2]; c2 = st.zoom_iir[chn][4 * sg + 3]; }
+    /* correction pass: y[n] += h1[j] c1 + h2[j] c2 */
+    u1 = 1.0f; u2 = 0.0f; v1 = 0.0f; v2 = 1.0f;
+    float yl1 = 0.0f, yl2 = 0.0f;
+    for (int n = n0; n < n1; ++n) {
+      const float un = fmaf(a1, u1, a2 * u2), vn = fmaf(a1, v1, a2 * v2);
+      u2 = u1; u1 = un;
+      v2 = v1; v1 = vn;
+      const float y = x[n] + (un * c1 + vn * c2);
+      x[n] = y;
+      yl2 = yl1; yl1 = y;
+    }
+    if (lane == 31) {
+      st.zoom_iir[chn][4 * sg] = sx1;
+      st.zoom_iir[chn][4 * sg + 1] = sx2;
+      st.zoom_iir[chn][4 * sg + 2] = yl1;
+      st.zoom_iir[chn][4 * sg + 3] = yl2;
+    }
+    __syncwarp(full);
+  }
+}
+
+/* The same cascade, sample by sample and rounded exactly like the reference: eight lanes per receiver =
+ * (channel, biquad stage), software-pipelined with a skew of two samples per stage; a stage's output
+ * travels to the next lane by warp shuffle one step ahead of its use.  Input: the shifted samples
+ * (PhZoomShift); the last stage writes its output in place (it trails the first stage's reads by 6). */
+T41RX_DEV void PhZoomIirPipe(Cta &c, int tid) {
+  const int g = tid >> 6, lane = tid & 63;
+  if (g >= c.ng || lane >= 32) return;               /* first warp of the receiver's 64-thread group */
+  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+  if (cf.zoom == 0) return;                          /* warp-uniform */
+  StreamState &st = c.a.st[Sid(c, g)];
+  const bool active = lane < 8;
+  const int chn = (lane >> 2) & 1, sg = lane & 3;
+  float *x = Slot(c, g) + (chn ? oRawQ : oRawI) + 27;
+  float b0 = 0, b1 = 0, b2 = 0, a1 = 0, a2 = 0, x1 = 0, x2 = 0, y1 = 0, y2 = 0;
+  if (active) {
+    const float *kk = c.a.zoom_iir + (cf.zoom - 1) * 20 + 5 * sg;
+    b0 = LdgRO(kk); b1 = LdgRO(kk + 1); b2 = LdgRO(kk + 2); a1 = LdgRO(kk + 3); a2 = LdgRO(kk + 4);
+    x1 = st.zoom_iir[chn][4 * sg]; x2 = st.zoom_iir[chn][4 * sg + 1];
+    y1 = st.zoom_iir[chn][4 * sg + 2]; y2 = st.zoom_iir[chn][4 * sg + 3];
+  }
+  const bool first = sg == 0, last = active && sg == 3;
+  float ylast = 0.0f, xcur = 0.0f;
+  /* stage 0 reads four samples ahead (up to 4 floats past the block: the next region of the slot, unused) */
+  float xn0 = x[0], xn1 = x[1], xn2 = x[2], xn3 = x[3];
+  float *xw = x - 6;                                  /* the last stage's sample index is k - 6 */
+  /* one pipeline step; kEdge: some lanes are outside their sample range (first 6 / last 6 steps) */
+#define T41RX_ZOOM_STEP(kEdge)                                                     \
+  {                                                                                \
+    const float xfetch = __shfl_up_sync(0xffffffffu, ylast, 1);                    \
+    const float xin = first ? xn0 : xcur;                                          \
+    float acc = b0 * xin;                                                          \
+    acc = acc + b1 * x1;                                                           \
+    acc = acc + b2 * x2;                                                           \
+    acc = acc + a1 * y1;                                                           \
+    acc = acc + a2 * y2;                                                           \
+    bool live = true;                                                              \
+    if (kEdge) {                                                                   \
+      const int n = k - 2 * sg;                                                    \
+      live = n >= 0 && n < kBlock;                                                 \
+    }                                                                              \
+    x2 = live ? x1 : x2;                                                           \
+    x1 = live ? xin : x1;                                                          \
+    y2 = live ? y1 : y2;                                                           \
+    y1 = live ? acc : y1;                                                          \
+    ylast = live ? acc : ylast;                                                    \
+    if (last && live) xw[k] = acc;                                                 \
+    xcur = xfetch;                                                                 \
+    xn0 = xn1; xn1 = xn2; xn2 = xn3;                                               \
+    xn3 = x[k + 4];                                                                \
+  }
+  int k = 0;
+  for (; k < 6; ++k) T41RX_ZOOM_STEP(true)
+#pragma unroll 4
+  for (; k < kBlock; ++k) T41RX_ZOOM_STEP(false)
+  for (; k < kBlock + 6; ++k) T41RX_ZOOM_STEP(true)
+#undef T41RX_ZOOM_STEP
+  if (active) {
+    st.zoom_iir[chn][4 * sg] = x1; st.zoom_iir[chn][4 * sg + 1] = x2;
+    st.zoom_iir[chn][4 * sg + 2] = y1; st.zoom_iir[chn][4 * sg + 3] = y2;
+  }
+}
+
+/* 4-tap FIR decimation by 2^zoom of the cascade's output, first zoom_samples outputs into the 512-deep ring
+ * (arm_fir_decimate_f32, FFT.cpp:86-101) */
+T41RX_DEV void PhZoomDecimate(Cta &c, int tid) {
+  const int g = tid >> 6, u = tid & 63;
+  if (g >= c.ng) return;
+  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+  if (cf.zoom == 0) return;
+  StreamState &st = c.a.st[Sid(c, g)];
+  const float *s = Slot(c, g);
+  const int M = 1 << cf.zoom, zs = cf.zoom_samples, ptr = st.zoom_ptr;
+  const float f0 = cf.zoom_fir[0], f1 = cf.zoom_fir[1], f2 = cf.zoom_fir[2], f3 = cf.zoom_fir[3];
+  for (int e = u; e < 2 * zs; e += 64) {
+    const int chn = e / zs, k = e % zs;
+    const float *y = s + (chn ? oRawQ : oRawI) + 27;
+    const int n = k * M;
+    const float h0 = (n >= 3) ? y[n - 3] : st.zoom_fir_hist[chn][n], h1 = (n >= 2) ? y[n - 2] : st.zoom_fir_hist[chn][n + 1],
+                h2 = (n >= 1) ? y[n - 1] : st.zoom_fir_hist[chn][n + 2];
+    float o = 0.0f;
+    o = fmaf(h0, f0, o);
+    o = fmaf(h1, f1, o);
+    o = fmaf(h2, f2, o);
+    o = fmaf(y[n], f3, o);
+    st.zoom_ring[chn][(ptr + k) & (kSpecRes - 1)] = o;
+  }
+}
+/* history of the decimator and ring pointer (after every lane has read the old values) */
+T41RX_DEV void PhZoomDecimateEnd(Cta &c, int tid) {
+  const int g = tid >> 6, u = tid & 63;
+  if (g >= c.ng) return;
+  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+  if (cf.zoom == 0) return;
+  StreamState &st = c.a.st[Sid(c, g)];
+  const float *s = Slot(c, g);
+  if (u < 6) {
+    const int chn = u / 3, i = u % 3;
+    st.zoom_fir_hist[chn][i] = s[(chn ? oRawQ : oRawI) + 27 + kBlock - 3 + i];
+  }
+  if (u == 63) st.zoom_ptr = (st.zoom_ptr + cf.zoom_samples) & (kSpecRes - 1);
+}
+
+#define T41RX_ROWS_SCHEDULE_FAST(RX_PHASE)                               \
+  RX_PHASE(PhLoad(c, tid); PhRowTailLoad(c, tid));                       \
+  RX_PHASE(PhRowDcSeedFast(c, tid));                                     \
+  RX_PHASE(PhDcWarm(c, tid));                                            \
+  RX_PHASE(PhDcMain(c, tid));                                            \
+  RX_PHASE(PhDcVerify(c, tid));                                          \
+  RX_PHASE(PhDcFix(c, tid));                                             \
+  RX_PHASE(PhZoomShift(c, tid));                                         \
+  if (c.a.flags & 4u) {                                                  \
+    RX_PHASE(PhZoomIirScan(c, tid));                                     \
+  } else {                                                               \
+    RX_PHASE(PhZoomIirPipe(c, tid));                                     \
+  }                                                                      \
+  RX_PHASE(PhZoomDecimate(c, tid));                                      \
+  RX_PHASE(PhZoomDecimateEnd(c, tid));                                   \
+  RX_PHASE(PhSpecWindow(c, tid));                                        \
+  RX_PHASE(PhSpecFftPass(c, tid, 0));                                    \
+  RX_PHASE(PhSpecFftPass(c, tid, 1));                                    \
+  RX_PHASE(PhSpecFftPass(c, tid, 2));                                    \
+  RX_PHASE(PhSpecRow(c, tid));
+#endif
+
 #define T41RX_ROWS_SCHEDULE(RX_PHASE)                                    \
   RX_PHASE(PhLoad(c, tid); PhRowDcSeed(c, tid));                         \
   RX_PHASE(PhDcWarm(c, tid));                                            \

@@ -20,6 +20,7 @@ BLOCK = 2048
 SPECTRUM_RES = 512
 FLAG_EXACT_NCO = 1       # bit-exact kernel, step-by-step FP64 oscillator
 FLAG_PHASED_KERNEL = 2   # bit-exact kernel with the closed-form FP64 oscillator
+FLAG_SCAN_ROWS = 4       # rows kernel: scan form of the ZoomFFT biquads (<= 1 LSB, < 1 % of pixels)
 # flags = 0: the throughput kernel
 
 # algorithmic HBM bytes per stream-block

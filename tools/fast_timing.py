@@ -16,8 +16,8 @@ import rx_driver  # noqa: E402
 from t41_sdr_b200 import rx  # noqa: E402
 
 NAMES = ["fe:setup+tail", "fe:wait cp.async", "fe:dc+mix", "fe:dec1", "fe:save hist", "fe:dec2", "fe:fft filter",
-         "fe:|z|+winmax", "be:gain+demod", "be:interp1", "be:interp2", "codec+loop", "barrier wait", "", "", "",
-         "agc:work", "agc:barrier wait"]
+         "fe:|z|+winmax", "be:gain+demod", "be:interp1", "be:interp2", "codec+arrive", "wait AGC done", "", "", "",
+         "agc:work", "agc:wait FE done"]
 
 
 def main():
