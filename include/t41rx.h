@@ -170,9 +170,12 @@ int t41rx_process_device(t41rx_ctx *ctx, const float *iq, float *audio, int n_bl
 int t41rx_synchronize(t41rx_ctx *ctx);
 
 /* Instrumentation for bench.py: kernels launched by this context so far, and the CUDA-event
- * duration (ms) of the most recent fused RX kernel (valid after t41rx_synchronize). */
+ * duration (ms) of all kernels of the most recent t41rx_process[_device] call (valid after t41rx_synchronize). */
 int64_t t41rx_kernel_launches(const t41rx_ctx *ctx);
 int t41rx_last_kernel_ms(t41rx_ctx *ctx, float *ms);
+/* CUDA-event durations (ms) of the most recent launches (oldest first, at most 32) of the dominant kernel,
+ * t41rx_stream_rx_kernel; returns how many were written, or a negative error code. */
+int t41rx_stream_kernel_times(t41rx_ctx *ctx, float *ms, int max_n);
 
 const char *t41rx_last_error(void);
 const char *t41rx_version(void);

@@ -8,6 +8,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <new>
 #include <string>
@@ -128,13 +129,21 @@ static int Fail(int code, const char *fmt, const char *detail = "") {
 /* ------------------------------------------------------------------ */
 /* context                                                             */
 /* ------------------------------------------------------------------ */
+constexpr int kKernelEventRing = 32;
+constexpr int kProcessChunks = 8;   /* receiver chunks of the host-buffer entry point's copy / compute pipeline */
+
 struct t41rx_ctx {
   int device = 0;
   int n_streams = 0;
   int n_sms = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;   /* t41rx_process: copies overlap the kernels */
+  cudaEvent_t ev_in[kProcessChunks] = {}, ev_done[kProcessChunks] = {};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool ev_valid = false;
+  /* CUDA events around the most recent launches of the dominant kernel (ring), for bench.py's roofline */
+  cudaEvent_t kev[kKernelEventRing][2] = {};
+  int64_t kev_count = 0;
   int64_t launches = 0;
 
   HostModel host;          /* parameter cache + host copies of every table */
@@ -246,6 +255,15 @@ void t41rx_destroy(t41rx_ctx *ctx) {
     if (b) cudaFree(b);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  for (int i = 0; i < kKernelEventRing; ++i)
+    for (int j = 0; j < 2; ++j)
+      if (ctx->kev[i][j]) cudaEventDestroy(ctx->kev[i][j]);
+  for (int i = 0; i < kProcessChunks; ++i) {
+    if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
+    if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
+  }
+  if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+  if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -267,7 +285,16 @@ int t41rx_create(t41rx_ctx **out, int n_streams, int device) {
     t41rx_destroy(ctx);
     return code;
   };
-  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+  for (int i = 0; i < kKernelEventRing; ++i)
+    if (cudaEventCreate(&ctx->kev[i][0]) != cudaSuccess || cudaEventCreate(&ctx->kev[i][1]) != cudaSuccess)
+      return bail(Fail(T41RX_ECUDA, "t41rx_create: event creation failed%s"));
+  for (int i = 0; i < kProcessChunks; ++i)
+    if (cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming) != cudaSuccess)
+      return bail(Fail(T41RX_ECUDA, "t41rx_create: event creation failed%s"));
+  if (cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess)
     return bail(Fail(T41RX_ECUDA, "t41rx_create: stream/event creation failed%s"));
   if (cudaFuncSetAttribute(t41rx_fused_rx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -427,13 +454,10 @@ int t41rx_get_debug(t41rx_ctx *ctx, int stream, t41rx_debug *d) {
   return T41RX_OK;
 }
 
-int t41rx_process_device(t41rx_ctx *ctx, const float *iq, float *audio, int n_blocks, int row_every,
-                         int16_t *spec_rows, uint16_t *wf_rows, int8_t *psk_bits, uint8_t *psk_chars,
-                         uint32_t flags, void *cuda_stream) {
-  if (!ctx || !iq || !audio || n_blocks <= 0 || row_every < 0)
-    return Fail(T41RX_EINVAL, "t41rx_process_device: bad arguments%s");
-  CUDA_TRY(cudaSetDevice(ctx->device));
-  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+/* enqueue the kernels for receivers [first, first + count) of the bank on stream st */
+static int LaunchRange(t41rx_ctx *ctx, const float *iq, float *audio, int n_blocks, int row_every,
+                       int16_t *spec_rows, uint16_t *wf_rows, int8_t *psk_bits, uint8_t *psk_chars,
+                       uint32_t flags, cudaStream_t st, int first, int count) {
   LaunchArgs a;
   memset(&a, 0, sizeof(a));
   a.iq = iq;
@@ -453,7 +477,8 @@ int t41rx_process_device(t41rx_ctx *ctx, const float *iq, float *audio, int n_bl
   a.sam_consts = ctx->d_sam;
   a.gradient = ctx->d_gradient;
   a.varicode = ctx->d_varicode;
-  a.n_streams = ctx->n_streams;
+  a.n_streams = count;
+  a.stream_base = first;
   a.n_blocks = n_blocks;
   a.row_every = row_every;
   a.n_rows = row_every > 0 ? (n_blocks + row_every - 1) / row_every : 0;
@@ -461,46 +486,76 @@ int t41rx_process_device(t41rx_ctx *ctx, const float *iq, float *audio, int n_bl
   /* kernel choice: the throughput kernel unless the caller asks for the bit-exact oscillator or the
      phase-structured kernel; SAM receivers always take the phase-structured kernel (see t41rx_ctx) */
   const bool all_phased = (flags & (T41RX_FLAG_EXACT_NCO | T41RX_FLAG_PHASED_KERNEL)) != 0;
-  if (!all_phased && ctx->ids_dirty) {
-    ctx->h_fast_ids.clear();
-    ctx->h_phased_ids.clear();
-    for (int s = 0; s < ctx->n_streams; ++s)
-      (ctx->host.cfg[s].mode == kModeSam ? ctx->h_phased_ids : ctx->h_fast_ids).push_back(s);
-    CUDA_TRY(cudaStreamSynchronize(st));
-    if (!ctx->h_fast_ids.empty())
-      CUDA_TRY(cudaMemcpy(ctx->d_fast_ids, ctx->h_fast_ids.data(), sizeof(int32_t) * ctx->h_fast_ids.size(), cudaMemcpyHostToDevice));
-    if (!ctx->h_phased_ids.empty())
-      CUDA_TRY(cudaMemcpy(ctx->d_phased_ids, ctx->h_phased_ids.data(), sizeof(int32_t) * ctx->h_phased_ids.size(), cudaMemcpyHostToDevice));
-    ctx->ids_dirty = false;
-  }
-  CUDA_TRY(cudaEventRecord(ctx->ev0, st));
   if (all_phased) {
-    const int grid = (ctx->n_streams + kG - 1) / kG;
-    t41rx_fused_rx_kernel<<<grid, kNT, kSmemFloats * sizeof(float), st>>>(a);
+    t41rx_fused_rx_kernel<<<(count + kG - 1) / kG, kNT, kSmemFloats * sizeof(float), st>>>(a);
     CUDA_TRY(cudaGetLastError());
     ctx->launches += 1;
-  } else {
-    if (!ctx->h_phased_ids.empty()) {
-      LaunchArgs p = a;
-      p.n_streams = (int)ctx->h_phased_ids.size();
-      p.stream_ids = ctx->d_phased_ids;
-      t41rx_fused_rx_kernel<<<(p.n_streams + kG - 1) / kG, kNT, kSmemFloats * sizeof(float), st>>>(p);
+    return T41RX_OK;
+  }
+  /* the slices of the (sorted) per-kernel receiver lists that fall into the range */
+  auto slice = [&](const std::vector<int32_t> &ids, int *off, int *len) {
+    const auto lo = std::lower_bound(ids.begin(), ids.end(), first), hi = std::lower_bound(ids.begin(), ids.end(), first + count);
+    *off = (int)(lo - ids.begin());
+    *len = (int)(hi - lo);
+  };
+  int p_off, p_len, f_off, f_len;
+  slice(ctx->h_phased_ids, &p_off, &p_len);
+  slice(ctx->h_fast_ids, &f_off, &f_len);
+  if (p_len > 0) {
+    LaunchArgs p = a;
+    p.n_streams = p_len;
+    p.stream_ids = ctx->d_phased_ids + p_off;
+    t41rx_fused_rx_kernel<<<(p_len + kG - 1) / kG, kNT, kSmemFloats * sizeof(float), st>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    ctx->launches += 1;
+  }
+  if (f_len > 0) {
+    LaunchArgs f = a;
+    f.n_streams = f_len;
+    f.stream_ids = (p_len > 0) ? ctx->d_fast_ids + f_off : nullptr;     /* no SAM receiver in range: contiguous */
+    if (row_every > 0 && (a.spec_rows || a.wf_rows)) {
+      t41rx_rows_kernel<<<(f_len + kG - 1) / kG, kNT, kSmemFloats * sizeof(float), st>>>(f);
       CUDA_TRY(cudaGetLastError());
       ctx->launches += 1;
     }
-    if (!ctx->h_fast_ids.empty()) {
-      LaunchArgs f = a;
-      f.n_streams = (int)ctx->h_fast_ids.size();
-      f.stream_ids = ctx->h_phased_ids.empty() ? nullptr : ctx->d_fast_ids;
-      if (row_every > 0 && (a.spec_rows || a.wf_rows)) {
-        t41rx_rows_kernel<<<(f.n_streams + kG - 1) / kG, kNT, kSmemFloats * sizeof(float), st>>>(f);
-        CUDA_TRY(cudaGetLastError());
-        ctx->launches += 1;
-      }
-      CUDA_TRY(LaunchStreamKernel(f, ctx->n_sms, st));
-      ctx->launches += 1;
-    }
+    cudaEvent_t *kev = ctx->kev[ctx->kev_count % kKernelEventRing];
+    CUDA_TRY(cudaEventRecord(kev[0], st));
+    CUDA_TRY(LaunchStreamKernel(f, ctx->n_sms, st));
+    CUDA_TRY(cudaEventRecord(kev[1], st));
+    ctx->kev_count += 1;
+    ctx->launches += 1;
   }
+  return T41RX_OK;
+}
+
+/* (re)build the per-kernel receiver lists after a parameter change */
+static int RefreshKernelLists(t41rx_ctx *ctx) {
+  if (!ctx->ids_dirty) return T41RX_OK;
+  ctx->h_fast_ids.clear();
+  ctx->h_phased_ids.clear();
+  for (int s = 0; s < ctx->n_streams; ++s)
+    (ctx->host.cfg[s].mode == kModeSam ? ctx->h_phased_ids : ctx->h_fast_ids).push_back(s);
+  CUDA_TRY(cudaDeviceSynchronize());
+  if (!ctx->h_fast_ids.empty())
+    CUDA_TRY(cudaMemcpy(ctx->d_fast_ids, ctx->h_fast_ids.data(), sizeof(int32_t) * ctx->h_fast_ids.size(), cudaMemcpyHostToDevice));
+  if (!ctx->h_phased_ids.empty())
+    CUDA_TRY(cudaMemcpy(ctx->d_phased_ids, ctx->h_phased_ids.data(), sizeof(int32_t) * ctx->h_phased_ids.size(), cudaMemcpyHostToDevice));
+  ctx->ids_dirty = false;
+  return T41RX_OK;
+}
+
+int t41rx_process_device(t41rx_ctx *ctx, const float *iq, float *audio, int n_blocks, int row_every,
+                         int16_t *spec_rows, uint16_t *wf_rows, int8_t *psk_bits, uint8_t *psk_chars,
+                         uint32_t flags, void *cuda_stream) {
+  if (!ctx || !iq || !audio || n_blocks <= 0 || row_every < 0)
+    return Fail(T41RX_EINVAL, "t41rx_process_device: bad arguments%s");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+  int rc = RefreshKernelLists(ctx);
+  if (rc) return rc;
+  CUDA_TRY(cudaEventRecord(ctx->ev0, st));
+  rc = LaunchRange(ctx, iq, audio, n_blocks, row_every, spec_rows, wf_rows, psk_bits, psk_chars, flags, st, 0, ctx->n_streams);
+  if (rc) return rc;
   CUDA_TRY(cudaEventRecord(ctx->ev1, st));
   ctx->ev_valid = true;
   return T41RX_OK;
@@ -531,20 +586,36 @@ int t41rx_process(t41rx_ctx *ctx, const float *iq, float *audio, int n_blocks, i
   if (n_rows && wf_rows && (rc = Grow(&ctx->d_wf, &ctx->cap_wf, b_wf))) return rc;
   if (psk_bits && (rc = Grow(&ctx->d_bits, &ctx->cap_bits, b_psk))) return rc;
   if (psk_chars && (rc = Grow(&ctx->d_chars, &ctx->cap_chars, b_psk))) return rc;
-  cudaStream_t st = ctx->stream;
-  CUDA_TRY(cudaMemcpyAsync(ctx->d_iq, iq, b_iq, cudaMemcpyHostToDevice, st));
-  rc = t41rx_process_device(ctx, (const float *)ctx->d_iq, (float *)ctx->d_audio, n_blocks, row_every,
-                            (n_rows && spec_rows) ? (int16_t *)ctx->d_spec : nullptr,
-                            (n_rows && wf_rows) ? (uint16_t *)ctx->d_wf : nullptr,
-                            psk_bits ? (int8_t *)ctx->d_bits : nullptr, psk_chars ? (uint8_t *)ctx->d_chars : nullptr,
-                            flags, nullptr);
-  if (rc) return rc;
-  CUDA_TRY(cudaMemcpyAsync(audio, ctx->d_audio, b_audio, cudaMemcpyDeviceToHost, st));
-  if (n_rows && spec_rows) CUDA_TRY(cudaMemcpyAsync(spec_rows, ctx->d_spec, b_spec, cudaMemcpyDeviceToHost, st));
-  if (n_rows && wf_rows) CUDA_TRY(cudaMemcpyAsync(wf_rows, ctx->d_wf, b_wf, cudaMemcpyDeviceToHost, st));
-  if (psk_bits) CUDA_TRY(cudaMemcpyAsync(psk_bits, ctx->d_bits, b_psk, cudaMemcpyDeviceToHost, st));
-  if (psk_chars) CUDA_TRY(cudaMemcpyAsync(psk_chars, ctx->d_chars, b_psk, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaStreamSynchronize(st));
+  if ((rc = RefreshKernelLists(ctx))) return rc;
+  /* receivers are independent: cut the bank into chunks and overlap the copy-in of chunk i+1, the kernels
+     of chunk i and the copy-out of chunk i-1 on three streams (full-duplex host link) */
+  const int n_chunks = (ctx->n_streams >= 8 * kProcessChunks) ? kProcessChunks : 1;
+  int16_t *d_spec = (n_rows && spec_rows) ? (int16_t *)ctx->d_spec : nullptr;
+  uint16_t *d_wf = (n_rows && wf_rows) ? (uint16_t *)ctx->d_wf : nullptr;
+  int8_t *d_bits = psk_bits ? (int8_t *)ctx->d_bits : nullptr;
+  uint8_t *d_chars = psk_chars ? (uint8_t *)ctx->d_chars : nullptr;
+  CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+  for (int ch = 0; ch < n_chunks; ++ch) {
+    const size_t s0 = (size_t)ctx->n_streams * ch / n_chunks, s1 = (size_t)ctx->n_streams * (ch + 1) / n_chunks, n = s1 - s0;
+    const size_t per_iq = T * 2 * kBlock, per_audio = T * kBlock, per_row = n_rows * kSpecRes;
+    CUDA_TRY(cudaMemcpyAsync((float *)ctx->d_iq + s0 * per_iq, iq + s0 * per_iq, n * per_iq * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_in));
+    CUDA_TRY(cudaEventRecord(ctx->ev_in[ch], ctx->copy_in));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[ch], 0));
+    rc = LaunchRange(ctx, (const float *)ctx->d_iq, (float *)ctx->d_audio, n_blocks, row_every, d_spec, d_wf, d_bits, d_chars,
+                     flags, ctx->stream, (int)s0, (int)n);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(ctx->ev_done[ch], ctx->stream));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_done[ch], 0));
+    CUDA_TRY(cudaMemcpyAsync(audio + s0 * per_audio, (float *)ctx->d_audio + s0 * per_audio, n * per_audio * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_out));
+    if (d_spec) CUDA_TRY(cudaMemcpyAsync(spec_rows + s0 * per_row, d_spec + s0 * per_row, n * per_row * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->copy_out));
+    if (d_wf) CUDA_TRY(cudaMemcpyAsync(wf_rows + s0 * per_row, d_wf + s0 * per_row, n * per_row * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->copy_out));
+    if (d_bits) CUDA_TRY(cudaMemcpyAsync(psk_bits + s0 * T, d_bits + s0 * T, n * T, cudaMemcpyDeviceToHost, ctx->copy_out));
+    if (d_chars) CUDA_TRY(cudaMemcpyAsync(psk_chars + s0 * T, d_chars + s0 * T, n * T, cudaMemcpyDeviceToHost, ctx->copy_out));
+  }
+  CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->ev_valid = true;
+  CUDA_TRY(cudaStreamSynchronize(ctx->copy_out));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   return T41RX_OK;
 }
 
@@ -560,6 +631,18 @@ int t41rx_debug_phase_cycles(unsigned long long *out128, int reset) {
 #endif
 
 int64_t t41rx_kernel_launches(const t41rx_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int t41rx_stream_kernel_times(t41rx_ctx *ctx, float *ms, int max_n) {
+  if (!ctx || !ms || max_n <= 0) return Fail(T41RX_EINVAL, "t41rx_stream_kernel_times: bad arguments%s");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  int n = (int)std::min<int64_t>(std::min<int64_t>(ctx->kev_count, kKernelEventRing), max_n);
+  for (int i = 0; i < n; ++i) {
+    cudaEvent_t *kev = ctx->kev[(ctx->kev_count - n + i) % kKernelEventRing];
+    CUDA_TRY(cudaEventSynchronize(kev[1]));
+    CUDA_TRY(cudaEventElapsedTime(ms + i, kev[0], kev[1]));
+  }
+  return n;
+}
 
 int t41rx_last_kernel_ms(t41rx_ctx *ctx, float *ms) {
   if (!ctx || !ms) return Fail(T41RX_EINVAL, "t41rx_last_kernel_ms: bad arguments%s");

@@ -1433,7 +1433,7 @@ __device__ __forceinline__ void StreamKernelBody(const LaunchArgs &a, int G, flo
     const int pair = warp >> 1;
     const bool live = pair < ng;
     if (!live) return;
-    const int sid = a.stream_ids ? __ldg(a.stream_ids + s0 + pair) : s0 + pair;
+    const int sid = a.stream_ids ? __ldg(a.stream_ids + s0 + pair) : a.stream_base + s0 + pair;
     RxPair w(a, smem + pair * kSlotF, sid, lane, warp & 1, 1 + pair);
     w.LoadState();
     w.IssueQuarter(0, 0);
@@ -1464,7 +1464,7 @@ __device__ __forceinline__ void StreamKernelBody(const LaunchArgs &a, int G, flo
     AgcLane g;
     const bool mine = lane < ng;
     bool active = false;
-    const int sid = mine ? (a.stream_ids ? __ldg(a.stream_ids + s0 + lane) : s0 + lane) : 0;
+    const int sid = mine ? (a.stream_ids ? __ldg(a.stream_ids + s0 + lane) : a.stream_base + s0 + lane) : 0;
     if (mine) {
       const StreamCfg &cf = a.cfg[sid];
       g.Load(cf, a.st[sid]);

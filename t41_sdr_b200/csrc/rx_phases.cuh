@@ -117,7 +117,8 @@ struct LaunchArgs {
   const uint32_t *varicode;   /* 128: code | bits << 16 | ascii << 24 */
   int n_streams, n_blocks, row_every, n_rows;   /* n_streams: receivers this launch works on */
   uint32_t flags;
-  const int32_t *stream_ids;  /* receiver index of each of them, or NULL for 0 .. n_streams-1 */
+  const int32_t *stream_ids;  /* receiver index of each of them, or NULL for stream_base .. stream_base + n_streams-1 */
+  int stream_base;
 };
 
 struct Cta {
@@ -133,7 +134,7 @@ struct Cta {
 
 T41RX_DEV float *Slot(const Cta &c, int g) { return c.smem + g * kSlot; }
 /* receiver index of slot g of this CTA */
-T41RX_DEV int Sid(const Cta &c, int g) { return c.a.stream_ids ? LdgRO(c.a.stream_ids + c.s0 + g) : c.s0 + g; }
+T41RX_DEV int Sid(const Cta &c, int g) { return c.a.stream_ids ? LdgRO(c.a.stream_ids + c.s0 + g) : c.a.stream_base + c.s0 + g; }
 
 /* which receiver (or -1) thread `tid` serves in a one-lane-per-receiver serial phase:
  * T41RX_SERIAL_WPS = 1: lane 0 of the receiver's own first warp (no divergence between receivers

@@ -73,6 +73,7 @@ EXPORTS = (
     "t41rx_num_streams", "t41rx_set_params", "t41rx_set_params_each", "t41rx_get_params",
     "t41rx_get_tables", "t41rx_get_debug", "t41rx_design_tables", "t41rx_process",
     "t41rx_process_device", "t41rx_synchronize", "t41rx_kernel_launches", "t41rx_last_kernel_ms",
+    "t41rx_stream_kernel_times",
     "t41rx_last_error", "t41rx_version")
 
 
@@ -108,6 +109,7 @@ def lib():
         L.t41rx_kernel_launches.argtypes = [vp]
         L.t41rx_kernel_launches.restype = C.c_int64
         L.t41rx_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
+        L.t41rx_stream_kernel_times.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
         L.t41rx_last_error.restype = C.c_char_p
         L.t41rx_version.restype = C.c_char_p
         _lib = L
@@ -230,6 +232,14 @@ class Receiver:
 
     def kernel_launches(self):
         return int(lib().t41rx_kernel_launches(self._h))
+
+    def stream_kernel_times(self, max_n=32):
+        """CUDA-event durations (ms) of the most recent t41rx_stream_rx_kernel launches, oldest first."""
+        buf = (C.c_float * max_n)()
+        n = lib().t41rx_stream_kernel_times(self._h, buf, max_n)
+        if n < 0:
+            _check(n, "t41rx_stream_kernel_times")
+        return [float(buf[i]) for i in range(n)]
 
     def last_kernel_ms(self):
         ms = C.c_float()
