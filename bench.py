@@ -54,6 +54,9 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget of the cpu_baseline sample")
     ap.add_argument("--rows-per-step", type=int, default=1, choices=[0, 1],
                     help="spectrum + waterfall rows per receiver per step (the first block of a step)")
+    ap.add_argument("--gather-rows", action="store_true",
+                    help="after the timed region, gather every rank's spectrum rows to rank 0 over NCCL (optional "
+                         "path of SURVEY 8(e); reported as rows_gather_ms)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -232,7 +235,7 @@ def ours(args):
     import torch
     import torch.distributed as dist
     import rx_driver
-    from t41_sdr_b200 import rx
+    from t41_sdr_b200 import rx, sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -293,10 +296,7 @@ def ours(args):
     launch_ms = [a.elapsed_time(b) for a, b in evs]
     gpu_launches = eng.kernel_launches() - launches0
 
-    tm = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    total_ms_max = float(tm.item())
+    total_ms_max = sharding.max_over_ranks(total_ms, dev)
     samples_per_step = world * S * T * 2048
     value = samples_per_step * args.steps / (total_ms_max * 1e-3) / 1e6
 
@@ -332,15 +332,24 @@ def ours(args):
             eng.process(h_iq_np, row_every=row_every, out=h_out)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
+        dt = sharding.max_over_ranks(dt, dev)
         gpu_launches = eng.kernel_launches() - launches0
         e2e = {"value": samples_per_step * args.steps / dt / 1e6, "unit": UNIT,
                "h2d_bytes_per_step": S * T * 16384, "d2h_bytes_per_step": S * T * 8192 + S * rx.BYTES_PER_ROW * args.rows_per_step,
                "timed_with": "host wall clock around t41rx_process (blocking), max over ranks",
                "checksum_audio": float(np.abs(h_out["audio"][::97, -1, ::31]).sum())}
+
+    rows_gather_ms = None
+    if args.gather_rows and row_every:
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        gathered = sharding.gather_rows(spec, world * S, dst=0)
+        g1.record()
+        torch.cuda.synchronize()
+        rows_gather_ms = sharding.max_over_ranks(g0.elapsed_time(g1), dev)
+        if rank == 0:
+            assert tuple(gathered.shape) == (world * S, 1, 512)
 
     clk = clocks.stop()
 
@@ -357,6 +366,8 @@ def ours(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config_dict(args), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": int(gpu_launches), "clocks": clk}
+        if rows_gather_ms is not None:
+            line["rows_gather_ms"] = rows_gather_ms
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:

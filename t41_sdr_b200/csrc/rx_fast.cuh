@@ -69,8 +69,13 @@ constexpr int vAudF = oD1;                            /* 24 (1 pad + 23 history)
 constexpr int vI1 = oD1 + 288;                        /* 8 (1 pad + 7 history) + 512 */
 static_assert(vI1 + 520 <= oD1 + kD1Words, "back-end scratch");
 
-/* the 512-point FFT buffer: element i lives at float2 index i + (i >> 3) */
-__device__ __forceinline__ int FPos(int i) { return i + (i >> 3); }
+/* the 512-point FFT buffer: element i lives at float2 index i ^ ((i >> 3) & 15): an XOR swizzle under which
+   every access pattern of the radix-8 passes (stride 64, stride 8, 8 contiguous) and of the code around them
+   is bank-conflict-free without padding (searched exhaustively, tools/fft_swizzle_search.py) */
+__device__ __forceinline__ int FPos(int i) { return i ^ ((i >> 3) & 15); }
+/* dec1 output planes: word w of a plane lives at D1W(w): adjacent float4 are swapped in every other group of 8,
+   which makes dec2's window loads (8 consecutive float4 per lane, lanes 2 float4 apart) conflict-free */
+__device__ __forceinline__ int D1W(int w) { return (((w >> 2) ^ ((w >> 5) & 1)) << 2) | (w & 3); }
 /* staged filter output: complex sample i lives at float2 index i + (i >> 3) (8 contiguous samples per lane
    and stride-1 lanes are both conflict-free) */
 __device__ __forceinline__ int ZPos(int i) { return i + (i >> 3); }
@@ -230,10 +235,9 @@ __device__ __forceinline__ void InvPass(float2 *buf, const float2 *tw, int b) {
  * octal-digit-reversed positions), inverse pass 2: all in registers */
 __device__ __forceinline__ void MidPass(float2 *buf, const float2 *mask, int b) {
   float r[8], im[8];
-  float2 *p = buf + 9 * b;   /* FPos(8 b) */
 #pragma unroll
   for (int m = 0; m < 8; ++m) {
-    const float2 x = p[m];
+    const float2 x = buf[FPos(8 * b + m)];
     r[m] = x.x;
     im[m] = x.y;
   }
@@ -247,7 +251,7 @@ __device__ __forceinline__ void MidPass(float2 *buf, const float2 *mask, int b) 
   }
   Dft8(im, r);
 #pragma unroll
-  for (int m = 0; m < 8; ++m) p[m] = float2{r[m], im[m]};
+  for (int m = 0; m < 8; ++m) buf[FPos(8 * b + m)] = float2{r[m], im[m]};
 }
 
 /* ------------------------------------------------------------------ */
@@ -628,8 +632,8 @@ struct RxPair {
     }
     /* d1 sample n = 128 q + 4 L + o -> plane (n & 1), entry n >> 1 */
     const int e = 64 * q + 2 * lane;
-    *reinterpret_cast<float2 *>(d1 + (ch * 2 + 0) * kD1Plane + 24 + e) = float2{acc[0], acc[2]};
-    *reinterpret_cast<float2 *>(d1 + (ch * 2 + 1) * kD1Plane + 24 + e) = float2{acc[1], acc[3]};
+    *reinterpret_cast<float2 *>(d1 + (ch * 2 + 0) * kD1Plane + D1W(24 + e)) = float2{acc[0], acc[2]};
+    *reinterpret_cast<float2 *>(d1 + (ch * 2 + 1) * kD1Plane + D1W(24 + e)) = float2{acc[1], acc[3]};
     __syncwarp();
     /* slide this channel's plane histories: entries 120..127 become -8..-1 (one value per lane) */
     {
@@ -649,10 +653,10 @@ struct RxPair {
     float w[2][32];
 #pragma unroll
     for (int par = 0; par < 2; ++par) {
-      const float4 *src = reinterpret_cast<const float4 *>(d1 + (ch * 2 + par) * kD1Plane + 8 * lane);
+      const float *pl = d1 + (ch * 2 + par) * kD1Plane;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const float4 v = src[k];
+        const float4 v = *reinterpret_cast<const float4 *>(pl + D1W(8 * lane + 4 * k));
         w[par][4 * k] = v.x; w[par][4 * k + 1] = v.y; w[par][4 * k + 2] = v.z; w[par][4 * k + 3] = v.w;
       }
     }
@@ -693,7 +697,7 @@ struct RxPair {
       s[oMix + (i >> 3) * kMixPlane + (i & 7)] = s[oMH + i];
       for (int j = lane; j < 48; j += 32) {          /* 96 dec2 history values: planes 2 w2, 2 w2 + 1 */
         const int k = 48 * w2 + j;
-        s[oD1 + (k / 24) * kD1Plane + (k % 24)] = s[oDH + k];
+        s[oD1 + (k / 24) * kD1Plane + (k % 24)] = s[oDH + k];          /* D1W is the identity on words 0..31 */
       }
     }
     /* gains of this block (Process.cpp:117,133): rfGainValue and RFgain are folded into the phasor */
@@ -780,7 +784,7 @@ struct RxPair {
     /* this channel's dec2 history for the next block: entries 232..255 of each plane */
     for (int j = lane; j < 48; j += 32) {
       const int k = 48 * w2 + j;
-      s[oDH + k] = s[oD1 + (k / 24) * kD1Plane + 24 + 232 + (k % 24)];
+      s[oDH + k] = s[oD1 + (k / 24) * kD1Plane + 24 + 232 + (k % 24)];   /* words 256..279: D1W is the identity */
     }
     T41RX_LAP(tm, 5);
     AfterDec2(dq, buf);
