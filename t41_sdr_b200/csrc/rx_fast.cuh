@@ -50,9 +50,10 @@ constexpr int oIH = oNcoW + 40;                       /* 7660: int1 history 23 (
 constexpr int oMH = oIH + 32;                         /* 7692: dec1 history, 8 planes x 8 */
 constexpr int oDH = oMH + 64;                         /* 7756: dec2 history, 4 planes x 24 */
 constexpr int oMiscF = oDH + 96;                      /* 7852 */
-constexpr int kSlotF = oMiscF + 20;                   /* == 4 (mod 8): the AGC warp's LDS.128 hit distinct banks */
+constexpr int kSlotF = oMiscF + 28;                   /* == 4 (mod 8): the AGC warp's LDS.128 hit distinct banks */
 enum { mEndI = 0, mEndQ = 1, mSettled = 2, mPhasor = 4 /* 2 doubles */, mInvIn = 8, mTarget = 9, mSlope = 10,
-       mOmF = 12, mOmH = 13, mFbm = 14, mHbm = 15 };
+       mOmF = 12, mOmH = 13, mFbm = 14, mHbm = 15,
+       mAmWold = 16, mAmX1 = 17, mAmX2 = 18, mAmY1 = 19, mAmY2 = 20, mNfmI = 21, mNfmQ = 22, mAmLp = 23 /* 5 */ };
 static_assert((oMiscF % 2) == 0 && (oTapsF % 4) == 0, "alignment");
 static_assert(kSlotF % 8 == 4, "slot stride");
 static_assert((oStA % 4) == 0 && (oStZ % 4) == 0 && (oRaw % 4) == 0 && (oMix % 4) == 0 && (oD1 % 4) == 0, "16-byte alignment");
@@ -161,6 +162,9 @@ struct RxRegs {
   int nco_closed;
   double osc_q, osc_i;   /* Osc_Vect while the amplitude loop is still settling (lane 0) */
   double blk_cos, blk_sin;   /* rotation of the block phasor over 2048 samples */
+  F2 tw_a, tw_b;         /* this thread's base twiddles of the stride-64 and stride-8 radix-8 passes */
+  const float2 *mask;    /* frequency-domain filter mask of the receiver's filter set */
+  int psk_enable;
   const char *cp_src;    /* this thread's first 16-byte piece of quarter 0 of block 0 */
   unsigned cp_dst;       /* its shared-memory address in raw buffer 0 */
   /* lane constants */
@@ -173,9 +177,8 @@ struct RxRegs {
 /* ------------------------------------------------------------------ */
 /* w[k] = (cos, sin)(2 pi k e / 512), k = 1..7, from one table entry and six complex products (shared
    memory and L1 bandwidth is the scarce resource of this kernel, FMAs are not) */
-__device__ __forceinline__ void TwiddlePowers(const float2 *tw, int e, F2 (&w)[8]) {
-  const float2 t = __ldg(tw + e);
-  w[1] = F2{t.x, t.y};
+__device__ __forceinline__ void TwiddlePowers(F2 t, F2 (&w)[8]) {
+  w[1] = t;
   w[2] = CMul(w[1], w[1]);
   w[3] = CMul(w[2], w[1]);
   w[4] = CMul(w[2], w[2]);
@@ -185,10 +188,10 @@ __device__ __forceinline__ void TwiddlePowers(const float2 *tw, int e, F2 (&w)[8
 }
 
 template <int PASS>
-__device__ __forceinline__ void FwdPass(float2 *buf, const float2 *tw, int b) {
-  int n2, j, i0, stride;
-  if (PASS == 0) { n2 = 64; j = b; i0 = b; stride = 1; }
-  else { n2 = 8; j = b & 7; i0 = (b >> 3) * 64 + j; stride = 8; }
+__device__ __forceinline__ void FwdPass(float2 *buf, F2 tw1, int b) {
+  int n2, i0;
+  if (PASS == 0) { n2 = 64; i0 = b; }
+  else { n2 = 8; i0 = (b >> 3) * 64 + (b & 7); }
   float r[8], im[8];
 #pragma unroll
   for (int m = 0; m < 8; ++m) {
@@ -199,7 +202,7 @@ __device__ __forceinline__ void FwdPass(float2 *buf, const float2 *tw, int b) {
   Dft8(r, im);
   buf[FPos(i0)] = float2{r[0], im[0]};
   F2 w[8];
-  TwiddlePowers(tw, j * stride, w);
+  TwiddlePowers(tw1, w);
 #pragma unroll
   for (int k = 1; k < 8; ++k)
     buf[FPos(i0 + k * n2)] = float2{r[k] * w[k].x + im[k] * w[k].y, im[k] * w[k].x - r[k] * w[k].y};
@@ -208,10 +211,10 @@ __device__ __forceinline__ void FwdPass(float2 *buf, const float2 *tw, int b) {
 /* inverse of FwdPass<PASS> without the 1/8: conjugate twiddles on the inputs, inverse 8-point DFT.
  * kUpperHalf: store only outputs 256..511 (the valid half of the overlap-save result). */
 template <int PASS, bool kUpperHalf>
-__device__ __forceinline__ void InvPass(float2 *buf, const float2 *tw, int b) {
-  int n2, j, i0, stride;
-  if (PASS == 0) { n2 = 64; j = b; i0 = b; stride = 1; }
-  else { n2 = 8; j = b & 7; i0 = (b >> 3) * 64 + j; stride = 8; }
+__device__ __forceinline__ void InvPass(float2 *buf, F2 tw1, int b) {
+  int n2, i0;
+  if (PASS == 0) { n2 = 64; i0 = b; }
+  else { n2 = 8; i0 = (b >> 3) * 64 + (b & 7); }
   float r[8], im[8];
   {
     const float2 x = buf[FPos(i0)];
@@ -219,7 +222,7 @@ __device__ __forceinline__ void InvPass(float2 *buf, const float2 *tw, int b) {
     im[0] = x.y;
   }
   F2 w[8];
-  TwiddlePowers(tw, j * stride, w);
+  TwiddlePowers(tw1, w);
 #pragma unroll
   for (int k = 1; k < 8; ++k) {
     const float2 x = buf[FPos(i0 + k * n2)];
@@ -233,7 +236,7 @@ __device__ __forceinline__ void InvPass(float2 *buf, const float2 *tw, int b) {
 
 /* forward pass 2 (8 contiguous elements, no twiddles), multiply by the filter mask (bins sit in
  * octal-digit-reversed positions), inverse pass 2: all in registers */
-__device__ __forceinline__ void MidPass(float2 *buf, const float2 *mask, int b) {
+__device__ __forceinline__ void MidPass(float2 *buf, const float2 (&hm)[8], int b) {
   float r[8], im[8];
 #pragma unroll
   for (int m = 0; m < 8; ++m) {
@@ -244,7 +247,7 @@ __device__ __forceinline__ void MidPass(float2 *buf, const float2 *mask, int b) 
   Dft8(r, im);
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    const float2 h = __ldg(mask + OctRev3((unsigned)(8 * b + k)));
+    const float2 h = hm[k];
     const float xr = r[k], xi = im[k];
     r[k] = xr * h.x - xi * h.y;
     im[k] = xr * h.y + xi * h.x;
@@ -334,6 +337,23 @@ struct RxPair {
       r.lane_rot = F2{(float)(cf.nco_amp * cs), (float)(cf.nco_amp * sn)};
     }
     r.tail_w = PowA1(4 * lane);
+    {
+      const float2 ta = __ldg(a.twiddle + tau), tb = __ldg(a.twiddle + 8 * (tau & 7));
+      r.tw_a = F2{ta.x, ta.y};
+      r.tw_b = F2{tb.x, tb.y};
+    }
+    r.mask = reinterpret_cast<const float2 *>(fs.mask);
+    r.psk_enable = cf.psk31_enable;
+    if (tau == 2) {
+      s[oMiscF + mAmWold] = st.am_wold;
+      s[oMiscF + mAmX1] = st.am_lp_state[0];
+      s[oMiscF + mAmX2] = st.am_lp_state[1];
+      s[oMiscF + mAmY1] = st.am_lp_state[2];
+      s[oMiscF + mAmY2] = st.am_lp_state[3];
+      s[oMiscF + mNfmI] = st.nfm_last_i;
+      s[oMiscF + mNfmQ] = st.nfm_last_q;
+      for (int i = 0; i < 5; ++i) s[oMiscF + mAmLp + i] = cf.am_lp[i];
+    }
     sincos(cf.nco_block_delta, &r.blk_sin, &r.blk_cos);
     {
       const int chunk0 = 8 * w2 + (lane & 7), piece = lane >> 3;
@@ -430,6 +450,15 @@ struct RxPair {
     }
     if (tau < 23) st.int1_hist[tau] = s[oIH + tau];
     if (tau < 7) st.int2_hist[tau] = s[oIH + 24 + tau];
+    if (tau == 1) {
+      st.am_wold = s[oMiscF + mAmWold];
+      st.am_lp_state[0] = s[oMiscF + mAmX1];
+      st.am_lp_state[1] = s[oMiscF + mAmX2];
+      st.am_lp_state[2] = s[oMiscF + mAmY1];
+      st.am_lp_state[3] = s[oMiscF + mAmY2];
+      st.nfm_last_i = s[oMiscF + mNfmI];
+      st.nfm_last_q = s[oMiscF + mNfmQ];
+    }
     if (tau == 0) {
       st.dc_d1 = s[oMiscF + mEndQ] * (kDcB0 * (kDcA1 - 1.0f) * cf.rf_gain_value);
       st.dc_d2 = 0.0f;
@@ -831,17 +860,21 @@ struct RxPair {
       r.first_block = 0;
     }
     PairSync();
-    const float2 *tw = a.twiddle;
-    const float2 *mask = reinterpret_cast<const float2 *>(a.fsets[a.cfg[sid].filter_id].mask);
-    FwdPass<0>(fb, tw, tau);
+    const float2 *mask = r.mask;
+    /* this thread's 8 mask bins (they sit at octal-digit-reversed positions after the forward passes): fetched
+       now, used two passes later -- there is next to no L1 beside 227 KB of shared memory, so these come from L2 */
+    float2 hm[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) hm[k] = __ldg(mask + OctRev3((unsigned)(8 * tau + k)));
+    FwdPass<0>(fb, r.tw_a, tau);
     PairSync();
-    FwdPass<1>(fb, tw, tau);
+    FwdPass<1>(fb, r.tw_b, tau);
     PairSync();
-    MidPass(fb, mask, tau);
+    MidPass(fb, hm, tau);
     PairSync();
-    InvPass<1, false>(fb, tw, tau);
+    InvPass<1, false>(fb, r.tw_b, tau);
     PairSync();
-    InvPass<0, true>(fb, tw, tau);
+    InvPass<0, true>(fb, r.tw_a, tau);
     PairSync();
     T41RX_LAP(tm, 6);
     /* valid outputs 256..511, scaled by 1/512: thread tau takes i = tau + 64 o (stride-1 lanes) */
@@ -931,7 +964,6 @@ struct RxPair {
      signal (Demod.cpp:220-235, Process.cpp:716-727,765-779).  The two warps hold I and Q: exchange through
      the second half of the FFT buffer. */
   __device__ __forceinline__ void NfmDiscriminator(float (&dq)[8], float2 *fb) {
-    StreamState &st = a.st[sid];
     float *fbw = reinterpret_cast<float *>(fb);
     const float kq = 0.340447550238101026565118445432744920253753662109375f;
     const int o0 = 8 * lane;
@@ -942,7 +974,7 @@ struct RxPair {
     float2 cur[4];
 #pragma unroll
     for (int o = 0; o < 4; ++o) cur[o] = fb[FPos(256 + i0 + o)];
-    float2 prev = float2{st.nfm_last_i, st.nfm_last_q};
+    float2 prev = float2{s[oMiscF + mNfmI], s[oMiscF + mNfmQ]};
     if (tau > 0) prev = fb[FPos(256 + i0 - 1)];
     float outv[4];
 #pragma unroll
@@ -964,8 +996,8 @@ struct RxPair {
     }
     PairSync();
     if (tau == 31) {                               /* "last sample" = complex sample 127 (B4) */
-      st.nfm_last_i = cur[3].x;
-      st.nfm_last_q = cur[3].y;
+      s[oMiscF + mNfmI] = cur[3].x;
+      s[oMiscF + mNfmQ] = cur[3].y;
     }
 #pragma unroll
     for (int o = 0; o < 4; ++o) {
@@ -986,7 +1018,7 @@ struct RxPair {
     {
       float2 dem[4];
       GainedSamples(cf, stz, volts, dem);
-      if (a.psk_bits || a.psk_chars || cf.psk31_enable) PskTap(t, dem[0], cf, st);
+      if (a.psk_bits || a.psk_chars || r.psk_enable) PskTap(t, dem[0], cf, st);
 #pragma unroll
       for (int o = 0; o < 4; ++o) {
         /* AM: alpha-beta magnitude (Process.cpp:697-699); USB / LSB / NFM / PSK31: real part (:616-624,688-695) */
@@ -1109,7 +1141,6 @@ struct RxPair {
   /* AM: alpha-beta magnitude, 1-pole DC removal, 1-stage DF1 low-pass (Process.cpp:697-707) as blocked
      linear scans over the lanes (8 samples per lane) */
   __device__ __forceinline__ void AmDetect(const float (&m)[8], float (&au)[8], StreamState &st) {
-    const StreamCfg &cf = a.cfg[sid];
     /* w[i] = m[i] + 0.99 w[i-1] */
     const float g = 0.99f;
     float w[8];
@@ -1118,7 +1149,7 @@ struct RxPair {
 #pragma unroll
       for (int o = 0; o < 8; ++o) { acc = fmaf(g, acc, m[o]); w[o] = acc; }
     }
-    const float wold = st.am_wold;
+    const float wold = s[oMiscF + mAmWold];
     float g8 = g * g; g8 *= g8; g8 *= g8;       /* 0.99^8 */
     float e = w[7];
     if (lane == 0) e = fmaf(g8, wold, e);
@@ -1147,9 +1178,10 @@ struct RxPair {
       }
     }
     /* biquad: y[i] = b0 x[i] + b1 x[i-1] + b2 x[i-2] + a1 y[i-1] + a2 y[i-2] */
-    const float b0 = cf.am_lp[0], b1 = cf.am_lp[1], b2 = cf.am_lp[2], a1 = cf.am_lp[3], a2 = cf.am_lp[4];
+    const float b0 = s[oMiscF + mAmLp], b1 = s[oMiscF + mAmLp + 1], b2 = s[oMiscF + mAmLp + 2], a1 = s[oMiscF + mAmLp + 3],
+                a2 = s[oMiscF + mAmLp + 4];
     float xm1 = __shfl_up_sync(kFull, x[7], 1), xm2 = __shfl_up_sync(kFull, x[6], 1);
-    if (lane == 0) { xm1 = st.am_lp_state[0]; xm2 = st.am_lp_state[1]; }
+    if (lane == 0) { xm1 = s[oMiscF + mAmX1]; xm2 = s[oMiscF + mAmX2]; }
     float y[8];
     {
       float p1 = 0.0f, p2 = 0.0f, q1 = xm1, q2 = xm2;
@@ -1180,7 +1212,7 @@ struct RxPair {
     float m00 = h1[7], m01 = h2[7], m10 = h1[6], m11 = h2[6];
     float s1 = y[7], s2 = y[6];
     if (lane == 0) {
-      const float y1 = st.am_lp_state[2], y2 = st.am_lp_state[3];
+      const float y1 = s[oMiscF + mAmY1], y2 = s[oMiscF + mAmY2];
       s1 += m00 * y1 + m01 * y2;
       s2 += m10 * y1 + m11 * y2;
     }
@@ -1196,16 +1228,16 @@ struct RxPair {
       m00 = n00; m01 = n01; m10 = n10; m11 = n11;
     }
     float c1 = __shfl_up_sync(kFull, s1, 1), c2 = __shfl_up_sync(kFull, s2, 1);
-    if (lane == 0) { c1 = st.am_lp_state[2]; c2 = st.am_lp_state[3]; }
+    if (lane == 0) { c1 = s[oMiscF + mAmY1]; c2 = s[oMiscF + mAmY2]; }
 #pragma unroll
     for (int o = 0; o < 8; ++o) au[o] = y[o] + h1[o] * c1 + h2[o] * c2;
     __syncwarp();
     if (lane == 31) {
-      st.am_wold = wend;
-      st.am_lp_state[0] = x[7];
-      st.am_lp_state[1] = x[6];
-      st.am_lp_state[2] = au[7];
-      st.am_lp_state[3] = au[6];
+      s[oMiscF + mAmWold] = wend;
+      s[oMiscF + mAmX1] = x[7];
+      s[oMiscF + mAmX2] = x[6];
+      s[oMiscF + mAmY1] = au[7];
+      s[oMiscF + mAmY2] = au[6];
     }
   }
 
