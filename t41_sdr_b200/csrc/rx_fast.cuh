@@ -1373,30 +1373,30 @@ struct AgcLane {
  * (Step) when some lane saw a transition (attack, end of hang, states 0 / 1). */
 __device__ __forceinline__ void AgcBlock(AgcLane &g, float *sta, bool active) {
   constexpr int kC = 8;
+  /* window maxima and back-average advances of the chunk being processed; the next chunk's are fetched
+     while this one runs (the recurrence below is pure latency: nothing else can hide the loads) */
+  float4 r0 = float4{0, 0, 0, 0}, r1 = r0;
+  float2 pfh = float2{0.0f, 0.0f};
+  if (active) {
+    r0 = *reinterpret_cast<const float4 *>(sta + 256);
+    r1 = *reinterpret_cast<const float4 *>(sta + 256 + 4);
+    pfh = *reinterpret_cast<const float2 *>(sta + 512);
+  }
 #pragma unroll 1
   for (int i0 = 0; i0 < kDec; i0 += kC) {
-    float rm[kC];
-    float2 pfh = float2{0.0f, 0.0f};
-    if (active) {
-#pragma unroll
-      for (int k = 0; k < kC; k += 4) {
-        const float4 r4 = *reinterpret_cast<const float4 *>(sta + 256 + i0 + k);
-        rm[k] = r4.x; rm[k + 1] = r4.y; rm[k + 2] = r4.z; rm[k + 3] = r4.w;
-      }
-      pfh = *reinterpret_cast<const float2 *>(sta + 512 + 2 * (i0 / kC));
-    } else {
-#pragma unroll
-      for (int k = 0; k < kC; ++k) rm[k] = 0.0f;
+    const float rm[kC] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+    const float2 pf = pfh;
+    if (active && i0 + kC < kDec) {
+      r0 = *reinterpret_cast<const float4 *>(sta + 256 + i0 + kC);
+      r1 = *reinterpret_cast<const float4 *>(sta + 256 + i0 + kC + 4);
+      pfh = *reinterpret_cast<const float2 *>(sta + 512 + 2 * (i0 / kC + 1));
     }
     /* speculative quiet path: state 3: v + ((r - v) decay) 0.05 -> one rounded constant (the step is ~1e-6 v,
        so the difference from the reference's rounding is ~1e-13 v); state 4: v + (r - v) hang_decay; state 2
        with the hang counter not expiring inside the chunk: v unchanged */
-    float c = 0.0f;
-    bool ok = true;
-    if (g.state == 3) c = g.decay * 0.05f;
-    else if (g.state == 4) c = g.hdecay;
-    else if (g.state == 2 && g.hc > kC) c = 0.0f;
-    else ok = false;
+    const int st = g.state;
+    const float c = (st == 3) ? g.decay * 0.05f : ((st == 4) ? g.hdecay : 0.0f);
+    bool ok = (st == 3) || (st == 4) || (st == 2 && g.hc > kC);
     float v = g.v, last = g.v;
     float vo[kC];
 #pragma unroll
@@ -1407,14 +1407,12 @@ __device__ __forceinline__ void AgcBlock(AgcLane &g, float *sta, bool active) {
       vo[k] = v;
     }
     if (__all_sync(kFull, ok || !active)) {
-      if (active) {
-        g.v = v;
-        g.fast = fmaf(g.om8f, g.fast, pfh.x);
-        g.hang = fmaf(g.om8h, g.hang, pfh.y);
-        g.rm = rm[kC - 1];
-        g.hc = max(g.hc - kC, 0);
-        g.action = (last < g.minv) ? 0 : 1;
-      }
+      g.v = v;
+      g.fast = fmaf(g.om8f, g.fast, pf.x);
+      g.hang = fmaf(g.om8h, g.hang, pf.y);
+      g.rm = rm[kC - 1];
+      g.hc = max(g.hc - kC, 0);
+      g.action = (last < g.minv) ? 0 : 1;
     } else if (active) {
 #ifdef T41RX_FAST_TIMING
       if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) g_fast_cycles[20] += 1;
@@ -1437,9 +1435,8 @@ __device__ __forceinline__ void AgcBlock(AgcLane &g, float *sta, bool active) {
       }
     }
     if (active) {
-#pragma unroll
-      for (int k = 0; k < kC; k += 4)
-        *reinterpret_cast<float4 *>(sta + 256 + i0 + k) = float4{vo[k], vo[k + 1], vo[k + 2], vo[k + 3]};
+      *reinterpret_cast<float4 *>(sta + 256 + i0) = float4{vo[0], vo[1], vo[2], vo[3]};
+      *reinterpret_cast<float4 *>(sta + 256 + i0 + 4) = float4{vo[4], vo[5], vo[6], vo[7]};
     }
   }
 }
