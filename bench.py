@@ -314,30 +314,52 @@ def ours(args):
                 "step_ms_all_kernels": statistics.mean(launch_ms),
                 "share_of_step": statistics.mean(kernel_ms) / statistics.mean(launch_ms)}
 
-    # end to end through the host-buffer C-ABI call: pinned host I/Q in, audio + rows out
+    # end to end through the host-buffer C-ABI calls, pinned host buffers, H2D + kernels + D2H inside the timed
+    # region: `e2e` = t41rx_process_q15, the firmware's own block format (q15 I/Q in, q15 audio out, what the
+    # codec queues of Process.cpp:102-111,936-937 carry); `e2e_float` = t41rx_process on float blocks
     e2e = None
+    e2e_float = None
     if not args.no_e2e:
+        n_rows = 1 if row_every else 0
+        iq_host = iq.cpu()
         h_iq = torch.empty((S, T, 2048, 2), dtype=torch.float32).pin_memory()
-        h_iq.copy_(iq.cpu())
-        h_out = dict(audio=torch.empty((S, T, 2048), dtype=torch.float32).pin_memory().numpy(),
-                     spec=torch.empty((S, 1, 512), dtype=torch.int16).pin_memory().numpy(),
-                     wf=torch.empty((S, 1, 512), dtype=torch.int16).pin_memory().numpy().view(np.uint16),
-                     psk_bits=None, psk_chars=None)
-        h_iq_np = h_iq.numpy()
-        for _ in range(2):
-            eng.process(h_iq_np, row_every=row_every, out=h_out)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            eng.process(h_iq_np, row_every=row_every, out=h_out)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        dt = sharding.max_over_ranks(dt, dev)
-        gpu_launches = eng.kernel_launches() - launches0
+        h_iq.copy_(iq_host)
+        h_iq16 = torch.empty((S, T, 2048, 2), dtype=torch.int16).pin_memory()
+        h_iq16.copy_(torch.round(iq_host * 32768.0).to(torch.int16))       # the synthetic I/Q is q15 / 32768
+        del iq_host
+
+        def host_out(dtype):
+            return dict(audio=torch.empty((S, T, 2048), dtype=dtype).pin_memory().numpy(),
+                        spec=torch.empty((S, max(n_rows, 1), 512), dtype=torch.int16).pin_memory().numpy()[:, :n_rows],
+                        wf=torch.empty((S, max(n_rows, 1), 512), dtype=torch.int16).pin_memory().numpy().view(np.uint16)[:, :n_rows],
+                        psk_bits=None, psk_chars=None)
+
+        def timed(call):
+            for _ in range(2):
+                call()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                call()
+            torch.cuda.synchronize()
+            return sharding.max_over_ranks(time.perf_counter() - t0, dev)
+
+        out16 = host_out(torch.int16)
+        h_iq16_np = h_iq16.numpy()
+        dt = timed(lambda: eng.process_q15(h_iq16_np, row_every=row_every, out=out16))
         e2e = {"value": samples_per_step * args.steps / dt / 1e6, "unit": UNIT,
-               "h2d_bytes_per_step": S * T * 16384, "d2h_bytes_per_step": S * T * 8192 + S * rx.BYTES_PER_ROW * args.rows_per_step,
-               "timed_with": "host wall clock around t41rx_process (blocking), max over ranks",
-               "checksum_audio": float(np.abs(h_out["audio"][::97, -1, ::31]).sum())}
+               "h2d_bytes_per_step": S * T * 8192, "d2h_bytes_per_step": S * T * 4096 + S * rx.BYTES_PER_ROW * args.rows_per_step,
+               "api": "t41rx_process_q15 (q15 I/Q in, q15 audio + rows out; pinned host buffers)",
+               "timed_with": "host wall clock around the blocking call, max over ranks",
+               "checksum_audio": float(np.abs(out16["audio"][::97, -1, ::31].astype(np.float64)).sum() / 32768.0)}
+        outf = host_out(torch.float32)
+        h_iq_np = h_iq.numpy()
+        dt = timed(lambda: eng.process(h_iq_np, row_every=row_every, out=outf))
+        e2e_float = {"value": samples_per_step * args.steps / dt / 1e6, "unit": UNIT,
+                     "h2d_bytes_per_step": S * T * 16384, "d2h_bytes_per_step": S * T * 8192 + S * rx.BYTES_PER_ROW * args.rows_per_step,
+                     "api": "t41rx_process (float blocks; pinned host buffers)",
+                     "checksum_audio": float(np.abs(outf["audio"][::97, -1, ::31]).sum())}
+        gpu_launches = eng.kernel_launches() - launches0
 
     rows_gather_ms = None
     if args.gather_rows and row_every:
@@ -364,7 +386,7 @@ def ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(3, args.warmup), "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": config_dict(args), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                "config": config_dict(args), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_float": e2e_float,
                 "gpu_launches": int(gpu_launches), "clocks": clk}
         if rows_gather_ms is not None:
             line["rows_gather_ms"] = rows_gather_ms

@@ -162,6 +162,15 @@ int t41rx_process(t41rx_ctx *ctx, const float *iq, float *audio, int n_blocks, i
                   int16_t *spec_rows, uint16_t *wf_rows, int8_t *psk_bits, uint8_t *psk_chars,
                   uint32_t flags);
 
+/* The same call on the firmware's own block format: q15 I/Q in (what the codec queues Q_in_R / Q_in_L hold,
+ * interleaved (I,Q): arm_q15_to_float = x / 32768, Process.cpp:107-108) and q15 audio out (what Q_out_L.play
+ * gets: arm_float_to_q15 = saturate(trunc(x * 32768)), Process.cpp:936-937).  HOST buffers; the conversions
+ * run on the device, so half as many bytes cross the host link as with the float entry point.
+ *   iq_q15     int16 [n_streams][n_blocks][2048][2]      audio_q15  int16 [n_streams][n_blocks][2048] */
+int t41rx_process_q15(t41rx_ctx *ctx, const int16_t *iq_q15, int16_t *audio_q15, int n_blocks, int row_every,
+                      int16_t *spec_rows, uint16_t *wf_rows, int8_t *psk_bits, uint8_t *psk_chars,
+                      uint32_t flags);
+
 /* Same, with DEVICE pointers (resident in HBM) and an optional cudaStream_t (NULL = the
  * context's own stream).  Asynchronous: returns after enqueueing. */
 int t41rx_process_device(t41rx_ctx *ctx, const float *iq, float *audio, int n_blocks, int row_every,

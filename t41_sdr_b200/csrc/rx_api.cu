@@ -104,6 +104,32 @@ __global__ void __launch_bounds__(kNT, 8 / kG) t41rx_rows_kernel(const LaunchArg
   }
 }
 
+/* arm_q15_to_float (Process.cpp:107-108): x / 32768, exact in float */
+__global__ void t41rx_q15_to_float_kernel(const short4 *src, float4 *dst, size_t n4) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const short4 v = src[i];
+    dst[i] = float4{(float)v.x / 32768.0f, (float)v.y / 32768.0f, (float)v.z / 32768.0f, (float)v.w / 32768.0f};
+  }
+}
+
+/* arm_float_to_q15 (Process.cpp:936): saturate((q31)(x * 32768)) to 16 bits, truncation toward zero */
+__device__ __forceinline__ short FloatToQ15(float x) {
+  const float v = x * 32768.0f;
+  int q;
+  if (!(v > -2147483648.0f)) q = INT32_MIN;      /* also catches NaN */
+  else if (v >= 2147483648.0f) q = INT32_MAX;
+  else q = (int)v;
+  q = q > 32767 ? 32767 : q;
+  q = q < -32768 ? -32768 : q;
+  return (short)q;
+}
+__global__ void t41rx_float_to_q15_kernel(const float4 *src, short4 *dst, size_t n4) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = src[i];
+    dst[i] = short4{FloatToQ15(v.x), FloatToQ15(v.y), FloatToQ15(v.z), FloatToQ15(v.w)};
+  }
+}
+
 }  // namespace t41rx
 
 using namespace t41rx;
@@ -169,7 +195,8 @@ struct t41rx_ctx {
 
   /* device staging for the host-buffer entry point */
   void *d_iq = nullptr, *d_audio = nullptr, *d_spec = nullptr, *d_wf = nullptr, *d_bits = nullptr, *d_chars = nullptr;
-  size_t cap_iq = 0, cap_audio = 0, cap_spec = 0, cap_wf = 0, cap_bits = 0, cap_chars = 0;
+  void *d_iq16 = nullptr, *d_audio16 = nullptr;   /* q15 staging of t41rx_process_q15 */
+  size_t cap_iq = 0, cap_audio = 0, cap_spec = 0, cap_wf = 0, cap_bits = 0, cap_chars = 0, cap_iq16 = 0, cap_audio16 = 0;
 };
 
 static int EnsureFsetCapacity(t41rx_ctx *ctx, int need) {
@@ -250,7 +277,8 @@ void t41rx_destroy(t41rx_ctx *ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   void *bufs[] = {ctx->d_cfg, ctx->d_state, ctx->d_fsets, ctx->d_nco_tab, ctx->d_twiddle, ctx->d_hann, ctx->d_sin,
                   ctx->d_zoom_iir, ctx->d_sam, ctx->d_gradient, ctx->d_varicode, ctx->d_iq, ctx->d_audio,
-                  ctx->d_spec, ctx->d_wf, ctx->d_bits, ctx->d_chars, ctx->d_fast_ids, ctx->d_phased_ids};
+                  ctx->d_spec, ctx->d_wf, ctx->d_bits, ctx->d_chars, ctx->d_fast_ids, ctx->d_phased_ids,
+                  ctx->d_iq16, ctx->d_audio16};
   for (void *b : bufs)
     if (b) cudaFree(b);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -568,9 +596,12 @@ int t41rx_synchronize(t41rx_ctx *ctx) {
   return T41RX_OK;
 }
 
-int t41rx_process(t41rx_ctx *ctx, const float *iq, float *audio, int n_blocks, int row_every,
-                  int16_t *spec_rows, uint16_t *wf_rows, int8_t *psk_bits, uint8_t *psk_chars, uint32_t flags) {
-  if (!ctx || !iq || !audio || n_blocks <= 0 || row_every < 0)
+/* host-buffer entry points: float (iq / audio) or q15 (iq16 / audio16) blocks */
+static int ProcessHost(t41rx_ctx *ctx, const float *iq, float *audio, const int16_t *iq16, int16_t *audio16,
+                       int n_blocks, int row_every, int16_t *spec_rows, uint16_t *wf_rows, int8_t *psk_bits,
+                       uint8_t *psk_chars, uint32_t flags) {
+  const bool q15 = iq16 != nullptr;
+  if (!ctx || (!q15 && (!iq || !audio)) || (q15 && !audio16) || n_blocks <= 0 || row_every < 0)
     return Fail(T41RX_EINVAL, "t41rx_process: bad arguments%s");
   if (row_every > 0 && !spec_rows && !wf_rows) row_every = 0;
   CUDA_TRY(cudaSetDevice(ctx->device));
@@ -586,6 +617,8 @@ int t41rx_process(t41rx_ctx *ctx, const float *iq, float *audio, int n_blocks, i
   if (n_rows && wf_rows && (rc = Grow(&ctx->d_wf, &ctx->cap_wf, b_wf))) return rc;
   if (psk_bits && (rc = Grow(&ctx->d_bits, &ctx->cap_bits, b_psk))) return rc;
   if (psk_chars && (rc = Grow(&ctx->d_chars, &ctx->cap_chars, b_psk))) return rc;
+  if (q15 && (rc = Grow(&ctx->d_iq16, &ctx->cap_iq16, b_iq / 2))) return rc;
+  if (q15 && (rc = Grow(&ctx->d_audio16, &ctx->cap_audio16, b_audio / 2))) return rc;
   if ((rc = RefreshKernelLists(ctx))) return rc;
   /* receivers are independent: cut the bank into chunks and overlap the copy-in of chunk i+1, the kernels
      of chunk i and the copy-out of chunk i-1 on three streams (full-duplex host link) */
@@ -598,15 +631,33 @@ int t41rx_process(t41rx_ctx *ctx, const float *iq, float *audio, int n_blocks, i
   for (int ch = 0; ch < n_chunks; ++ch) {
     const size_t s0 = (size_t)ctx->n_streams * ch / n_chunks, s1 = (size_t)ctx->n_streams * (ch + 1) / n_chunks, n = s1 - s0;
     const size_t per_iq = T * 2 * kBlock, per_audio = T * kBlock, per_row = n_rows * kSpecRes;
-    CUDA_TRY(cudaMemcpyAsync((float *)ctx->d_iq + s0 * per_iq, iq + s0 * per_iq, n * per_iq * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_in));
+    if (q15)
+      CUDA_TRY(cudaMemcpyAsync((int16_t *)ctx->d_iq16 + s0 * per_iq, iq16 + s0 * per_iq, n * per_iq * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->copy_in));
+    else
+      CUDA_TRY(cudaMemcpyAsync((float *)ctx->d_iq + s0 * per_iq, iq + s0 * per_iq, n * per_iq * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_in));
     CUDA_TRY(cudaEventRecord(ctx->ev_in[ch], ctx->copy_in));
     CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[ch], 0));
+    if (q15) {
+      t41rx_q15_to_float_kernel<<<2 * ctx->n_sms, 256, 0, ctx->stream>>>(
+          reinterpret_cast<const short4 *>((int16_t *)ctx->d_iq16 + s0 * per_iq), reinterpret_cast<float4 *>((float *)ctx->d_iq + s0 * per_iq), n * per_iq / 4);
+      CUDA_TRY(cudaGetLastError());
+      ctx->launches += 1;
+    }
     rc = LaunchRange(ctx, (const float *)ctx->d_iq, (float *)ctx->d_audio, n_blocks, row_every, d_spec, d_wf, d_bits, d_chars,
                      flags, ctx->stream, (int)s0, (int)n);
     if (rc) return rc;
+    if (q15) {
+      t41rx_float_to_q15_kernel<<<2 * ctx->n_sms, 256, 0, ctx->stream>>>(
+          reinterpret_cast<const float4 *>((float *)ctx->d_audio + s0 * per_audio), reinterpret_cast<short4 *>((int16_t *)ctx->d_audio16 + s0 * per_audio), n * per_audio / 4);
+      CUDA_TRY(cudaGetLastError());
+      ctx->launches += 1;
+    }
     CUDA_TRY(cudaEventRecord(ctx->ev_done[ch], ctx->stream));
     CUDA_TRY(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_done[ch], 0));
-    CUDA_TRY(cudaMemcpyAsync(audio + s0 * per_audio, (float *)ctx->d_audio + s0 * per_audio, n * per_audio * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_out));
+    if (q15)
+      CUDA_TRY(cudaMemcpyAsync(audio16 + s0 * per_audio, (int16_t *)ctx->d_audio16 + s0 * per_audio, n * per_audio * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->copy_out));
+    else
+      CUDA_TRY(cudaMemcpyAsync(audio + s0 * per_audio, (float *)ctx->d_audio + s0 * per_audio, n * per_audio * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_out));
     if (d_spec) CUDA_TRY(cudaMemcpyAsync(spec_rows + s0 * per_row, d_spec + s0 * per_row, n * per_row * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->copy_out));
     if (d_wf) CUDA_TRY(cudaMemcpyAsync(wf_rows + s0 * per_row, d_wf + s0 * per_row, n * per_row * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->copy_out));
     if (d_bits) CUDA_TRY(cudaMemcpyAsync(psk_bits + s0 * T, d_bits + s0 * T, n * T, cudaMemcpyDeviceToHost, ctx->copy_out));
@@ -617,6 +668,17 @@ int t41rx_process(t41rx_ctx *ctx, const float *iq, float *audio, int n_blocks, i
   CUDA_TRY(cudaStreamSynchronize(ctx->copy_out));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   return T41RX_OK;
+}
+
+int t41rx_process(t41rx_ctx *ctx, const float *iq, float *audio, int n_blocks, int row_every,
+                  int16_t *spec_rows, uint16_t *wf_rows, int8_t *psk_bits, uint8_t *psk_chars, uint32_t flags) {
+  return ProcessHost(ctx, iq, audio, nullptr, nullptr, n_blocks, row_every, spec_rows, wf_rows, psk_bits, psk_chars, flags);
+}
+
+int t41rx_process_q15(t41rx_ctx *ctx, const int16_t *iq_q15, int16_t *audio_q15, int n_blocks, int row_every,
+                      int16_t *spec_rows, uint16_t *wf_rows, int8_t *psk_bits, uint8_t *psk_chars, uint32_t flags) {
+  if (!iq_q15) return Fail(T41RX_EINVAL, "t41rx_process_q15: bad arguments%s");
+  return ProcessHost(ctx, nullptr, nullptr, iq_q15, audio_q15, n_blocks, row_every, spec_rows, wf_rows, psk_bits, psk_chars, flags);
 }
 
 #ifdef T41RX_PHASE_TIMING

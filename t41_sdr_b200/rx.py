@@ -71,7 +71,7 @@ class Tables(C.Structure):
 EXPORTS = (
     "t41rx_default_params", "t41rx_mode_default_cuts", "t41rx_create", "t41rx_destroy",
     "t41rx_num_streams", "t41rx_set_params", "t41rx_set_params_each", "t41rx_get_params",
-    "t41rx_get_tables", "t41rx_get_debug", "t41rx_design_tables", "t41rx_process",
+    "t41rx_get_tables", "t41rx_get_debug", "t41rx_design_tables", "t41rx_process", "t41rx_process_q15",
     "t41rx_process_device", "t41rx_synchronize", "t41rx_kernel_launches", "t41rx_last_kernel_ms",
     "t41rx_stream_kernel_times",
     "t41rx_last_error", "t41rx_version")
@@ -104,6 +104,7 @@ def lib():
         L.t41rx_get_debug.argtypes = [vp, ip, C.POINTER(Debug)]
         L.t41rx_design_tables.argtypes = [C.POINTER(Params), ip, C.POINTER(Tables)]
         L.t41rx_process.argtypes = [vp, vp, vp, ip, ip, vp, vp, vp, vp, C.c_uint32]
+        L.t41rx_process_q15.argtypes = [vp, vp, vp, ip, ip, vp, vp, vp, vp, C.c_uint32]
         L.t41rx_process_device.argtypes = [vp, vp, vp, ip, ip, vp, vp, vp, vp, C.c_uint32, vp]
         L.t41rx_synchronize.argtypes = [vp]
         L.t41rx_kernel_launches.argtypes = [vp]
@@ -218,6 +219,27 @@ class Receiver:
                                    _np_ptr(out["wf"]) if n_rows else None,
                                    _np_ptr(out.get("psk_bits")), _np_ptr(out.get("psk_chars")), flags),
                "t41rx_process")
+        return out
+
+    def process_q15(self, iq_q15, row_every=0, want_psk=False, flags=0, out=None):
+        """The firmware's own block format: iq_q15 int16 [n_streams, n_blocks, 2048, 2] (host) in, audio int16
+        [n_streams, n_blocks, 2048] out (arm_q15_to_float / arm_float_to_q15 run on the device)."""
+        iq_q15 = np.ascontiguousarray(iq_q15, dtype=np.int16)
+        S, T = self.n_streams, iq_q15.shape[1]
+        if iq_q15.shape != (S, T, BLOCK, 2):
+            raise ValueError("iq_q15 must have shape [n_streams, n_blocks, 2048, 2]")
+        n_rows = 0 if row_every <= 0 else (T + row_every - 1) // row_every
+        if out is None:
+            out = dict(audio=np.empty((S, T, BLOCK), np.int16),
+                       spec=np.zeros((S, n_rows, SPECTRUM_RES), np.int16),
+                       wf=np.zeros((S, n_rows, SPECTRUM_RES), np.uint16),
+                       psk_bits=np.full((S, T), -1, np.int8) if want_psk else None,
+                       psk_chars=np.zeros((S, T), np.uint8) if want_psk else None)
+        _check(lib().t41rx_process_q15(self._h, _np_ptr(iq_q15), _np_ptr(out["audio"]), T, row_every,
+                                       _np_ptr(out["spec"]) if n_rows else None,
+                                       _np_ptr(out["wf"]) if n_rows else None,
+                                       _np_ptr(out.get("psk_bits")), _np_ptr(out.get("psk_chars")), flags),
+               "t41rx_process_q15")
         return out
 
     # ---- ProcessIQData over device buffers (raw pointers, e.g. torch.Tensor.data_ptr()) ----

@@ -105,6 +105,37 @@ def test_psk31_text_is_decoded():
         assert cases.PSK_TEXT.encode() in chars
 
 
+def _float_to_q15(x):
+    """arm_float_to_q15 (oracle/cmsis_port.c): saturate(trunc(x * 32768)); NaN -> INT16_MIN"""
+    v = x.astype(np.float32) * np.float32(32768.0)
+    q = np.where(np.isnan(v), -2147483648.0, np.clip(np.trunc(v.astype(np.float64)), -2147483648.0, 2147483647.0))
+    return np.clip(q, -32768, 32767).astype(np.int16)
+
+
+def test_q15_entry_point_is_the_firmware_block_format():
+    """t41rx_process_q15: q15 I/Q in, q15 audio out (Process.cpp:102-111, 936-937).  The synthetic I/Q of the
+    parity cases IS q15 / 32768, so the oracle on the float input is the reference for the q15 call."""
+    case = cases.c2_ssb_am_mix()
+    want = cases.run_case_on(case, lambda p: O.OracleStream(p))
+    iq = np.stack(case.iq)
+    iq16 = np.round(iq * 32768.0).astype(np.int16)
+    assert np.array_equal(iq16.astype(np.float32) / np.float32(32768.0), iq)
+    params = [rx_driver.to_rx_params(p) for p in case.segments[0][0]]
+    with _receiver(case.n_streams) as eng:
+        eng.set_params_each(params)
+        exact = eng.process_q15(iq16, row_every=case.row_every, flags=rx.FLAG_EXACT_NCO)
+    with _receiver(case.n_streams) as eng:
+        eng.set_params_each(params)
+        fast = eng.process_q15(iq16, row_every=case.row_every, flags=0)
+    for s_, w in enumerate(want):
+        ref16 = _float_to_q15(w["audio"])
+        assert np.array_equal(exact["audio"][s_], ref16), s_                # bit-exact kernel: identical q15 words
+        assert np.array_equal(exact["spec"][s_], w["spec"])
+        d = np.abs(fast["audio"][s_].astype(np.int32) - ref16.astype(np.int32))
+        assert d.max() <= 1 and np.mean(d == 0) >= 0.99, (s_, int(d.max()), float(np.mean(d == 0)))
+        assert np.array_equal(fast["spec"][s_], w["spec"])
+
+
 def test_error_codes():
     with _receiver(3) as eng:
         with pytest.raises(rx.T41RxError):
