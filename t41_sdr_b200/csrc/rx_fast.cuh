@@ -51,7 +51,7 @@ constexpr int oMH = oIH + 32;                         /* 7692: dec1 history, 8 p
 constexpr int oDH = oMH + 64;                         /* 7756: dec2 history, 4 planes x 24 */
 constexpr int oMiscF = oDH + 96;                      /* 7852 */
 constexpr int kSlotF = oMiscF + 28;                   /* == 4 (mod 8): the AGC warp's LDS.128 hit distinct banks */
-enum { mEndI = 0, mEndQ = 1, mSettled = 2, mPhasor = 4 /* 2 doubles */, mInvIn = 8, mTarget = 9, mSlope = 10,
+enum { mEndI = 0, mEndQ = 1, mSettled = 2, mMidI = 3, mMidQ = 11, mPhasor = 4 /* 2 doubles */, mInvIn = 8, mTarget = 9, mSlope = 10,
        mOmF = 12, mOmH = 13, mFbm = 14, mHbm = 15,
        mAmWold = 16, mAmX1 = 17, mAmX2 = 18, mAmY1 = 19, mAmY2 = 20, mNfmI = 21, mNfmQ = 22, mAmLp = 23 /* 5 */ };
 static_assert((oMiscF % 2) == 0 && (oTapsF % 4) == 0, "alignment");
@@ -170,6 +170,7 @@ struct RxRegs {
   /* lane constants */
   F2 lane_rot;           /* nco_amp * exp(-j * delta * (8 * tau + 1)) */
   float tail_w;          /* a1^(4 * lane): weight of this lane's partial sum in the I-tail pre-read */
+  float pow8;            /* a1^(8 * lane): decay of the carry entering the warp's half quarter up to this lane */
 };
 
 /* ------------------------------------------------------------------ */
@@ -337,6 +338,7 @@ struct RxPair {
       r.lane_rot = F2{(float)(cf.nco_amp * cs), (float)(cf.nco_amp * sn)};
     }
     r.tail_w = PowA1(4 * lane);
+    r.pow8 = PowA1(8 * lane);
     {
       const float2 ta = __ldg(a.twiddle + tau), tb = __ldg(a.twiddle + 8 * (tau & 7));
       r.tw_a = F2{ta.x, ta.y};
@@ -506,42 +508,17 @@ struct RxPair {
     return v;
   }
 
-  /* recurrence values (I, Q) at the end of the 128 samples that end just before word offset `end_word`
-     of a padded raw buffer, from zero state (a1^128 ~ 2e-9): 4 samples per lane, weighted reduction */
-  __device__ __forceinline__ void TailFromRaw(const float *rawbuf, int first_chunk, float &ti, float &tq) const {
-    /* lane L covers samples 4 L .. 4 L + 3 of the 128: chunk first_chunk + (L >> 1), half (L & 1) */
-    const float *p = rawbuf + (first_chunk + (lane >> 1)) * kRawChunkWords + (lane & 1) * 8;
-    const float4 u = *reinterpret_cast<const float4 *>(p), v = *reinterpret_cast<const float4 *>(p + 4);
-    float ai = u.x, aq = u.y;
-    ai = fmaf(kDcA1, ai, u.z); aq = fmaf(kDcA1, aq, u.w);
-    ai = fmaf(kDcA1, ai, v.x); aq = fmaf(kDcA1, aq, v.y);
-    ai = fmaf(kDcA1, ai, v.z); aq = fmaf(kDcA1, aq, v.w);
-    const float wgt = __shfl_sync(kFull, r.tail_w, 31 - lane);      /* a1^(4 (31 - L)) */
-    ai *= wgt;
-    aq *= wgt;
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) {
-      ai += __shfl_xor_sync(kFull, ai, d);
-      aq += __shfl_xor_sync(kFull, aq, d);
-    }
-    ti = ai;
-    tq = aq;
-  }
-
   /* one 512-sample quarter, 8 samples per thread: DC block + IQ correction + Fs/4 + NCO mix -> phase planes.
      cI / cQ: recurrence values entering the quarter (used by warp 0).  base: conj(block phasor) * Q[q] * gain. */
   template <bool kTable>
   __device__ __forceinline__ void QuarterMix(int q, float cI, float cQ, F2 base, const float2 *osc) {
-    const float *rawbuf = s + oRaw + (q & 1) * kRawBufWords;
-    const float *raw = rawbuf + tau * kRawChunkWords;
+    const float *raw = s + oRaw + (q & 1) * kRawBufWords + tau * kRawChunkWords;
     float xi[8], xq[8];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const float4 v = *reinterpret_cast<const float4 *>(raw + 4 * k);
       xi[2 * k] = v.x; xq[2 * k] = v.y; xi[2 * k + 1] = v.z; xq[2 * k + 1] = v.w;
     }
-    /* warp 1 starts from the recurrence value at the end of warp 0's half: recomputed from its last 128 samples */
-    if (w2 == 1) TailFromRaw(rawbuf, 16, cI, cQ);
     /* zero-state recurrences (two independent chains) */
     float wi[8], wq[8];
     {
@@ -556,14 +533,27 @@ struct RxPair {
     }
     float p8 = kDcA1;
     p8 *= p8; p8 *= p8; p8 *= p8;
+    /* warp 0 knows the value entering its half (cI, cQ) and folds it into lane 0's chunk end; warp 1 scans from
+       zero and adds the decayed end value of warp 0's half once that is known (the recurrence is linear) */
     float ei = wi[7], eq = wq[7];
-    if (lane == 0) { ei = fmaf(p8, cI, ei); eq = fmaf(p8, cQ, eq); }
-    const float si = ScanDc(ei), sq = ScanDc(eq);
+    if (tau == 0) { ei = fmaf(p8, cI, ei); eq = fmaf(p8, cQ, eq); }
+    float si = ScanDc(ei), sq = ScanDc(eq);
     float ci = __shfl_up_sync(kFull, si, 1), cq = __shfl_up_sync(kFull, sq, 1);
-    if (lane == 0) { ci = cI; cq = cQ; }
-    if (tau == 63) {                 /* recurrence values leaving the quarter */
-      s[oMiscF + mEndI] = si;
-      s[oMiscF + mEndQ] = sq;
+    if (tau == 31) {
+      s[oMiscF + mMidI] = si;
+      s[oMiscF + mMidQ] = sq;
+    }
+    PairSync();
+    if (w2 == 0) {
+      if (lane == 0) { ci = cI; cq = cQ; }
+    } else {
+      const float mI = s[oMiscF + mMidI], mQ = s[oMiscF + mMidQ];
+      if (lane == 0) { ci = mI; cq = mQ; }
+      else { ci = fmaf(r.pow8, mI, ci); cq = fmaf(r.pow8, mQ, cq); }
+      if (lane == 31) {              /* recurrence values leaving the quarter (a1^256 of warp 0's end is below resolution) */
+        s[oMiscF + mEndI] = si;
+        s[oMiscF + mEndQ] = sq;
+      }
     }
     /* true recurrence values, first difference (DC-block numerator 1 - z^-1) */
     float yi[8], yq[8];
