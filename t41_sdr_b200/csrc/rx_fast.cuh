@@ -121,6 +121,23 @@ struct SectionTimer {
 #endif
 
 struct F2 { float x, y; };
+
+/* packed FP32 pairs (sm_100 FFMA2: two FMAs per issue slot) */
+typedef unsigned long long P2;
+__device__ __forceinline__ P2 Pack2(float lo, float hi) {
+  P2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void Unpack2(P2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ float Lo(P2 v) { float a, b; Unpack2(v, a, b); return a; }
+__device__ __forceinline__ float Hi(P2 v) { float a, b; Unpack2(v, a, b); return b; }
+__device__ __forceinline__ P2 Dup(float x) { return Pack2(x, x); }     /* ptxas folds it into FFMA2's scalar operand */
+__device__ __forceinline__ P2 Fma2(P2 a, P2 b, P2 c) {
+  P2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
 __device__ __forceinline__ F2 CMul(F2 a, F2 b) { return F2{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
 
 __device__ __forceinline__ void CpAsync16(void *smem_dst, const void *gsrc) {
@@ -664,34 +681,54 @@ struct RxPair {
   }
 
   /* arm_fir_decimate_f32, M = 2, 46 taps (Process.cpp:478-479): warp w2 filters channel w2, 8 outputs per lane.
-     Output o = sum_t h[t] d[2 o - 45 + t]; sample 2 o - 45 + t = plane (1 + t) & 1, entry o - 23 + ((1 + t) >> 1). */
+     Output o = sum_t h[t] d[2 o - 45 + t]; sample 2 o - 45 + t = plane (1 + t) & 1, entry o - 23 + ((1 + t) >> 1).
+     Packed FP32 (FFMA2, scalar tap x pair of window entries): the window sits in registers as aligned pairs
+     (w[2m], w[2m+1]); a tap whose window offset is even feeds the output pairs (0,1)(2,3)(4,5)(6,7), one whose
+     offset is odd feeds the pairs (1,2)(3,4)(5,6) plus outputs 0 and 7 alone; the two sets are added at the end. */
   __device__ __forceinline__ void Dec2(float (&out)[8]) {
     const int ch = w2;
     const float *d1 = s + oD1;
     const float *tp = s + oTapsF + 28;
-    float w[2][32];
+    P2 w[2][16];
 #pragma unroll
     for (int par = 0; par < 2; ++par) {
       const float *pl = d1 + (ch * 2 + par) * kD1Plane;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const float4 v = *reinterpret_cast<const float4 *>(pl + D1W(8 * lane + 4 * k));
-        w[par][4 * k] = v.x; w[par][4 * k + 1] = v.y; w[par][4 * k + 2] = v.z; w[par][4 * k + 3] = v.w;
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(pl + D1W(8 * lane + 4 * k));
+        w[par][2 * k] = v.x;
+        w[par][2 * k + 1] = v.y;
       }
     }
-#pragma unroll
-    for (int o = 0; o < 8; ++o) out[o] = 0.0f;
+    P2 e[4] = {0ull, 0ull, 0ull, 0ull}, od[3] = {0ull, 0ull, 0ull};
+    float s0 = 0.0f, s7 = 0.0f;
 #pragma unroll
     for (int t2 = 0; t2 < kDec2Taps; t2 += 2) {
-      const float2 h = *reinterpret_cast<const float2 *>(tp + t2);
+      const float2 h2 = *reinterpret_cast<const float2 *>(tp + t2);
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const int t = t2 + u;
-        const int par = (1 + t) & 1, off = 1 + ((1 + t) >> 1);
+        const int par = (1 + t) & 1, off = 1 + ((1 + t) >> 1);     /* output o reads window word o + off */
+        const float h = u ? h2.y : h2.x;
+        if ((off & 1) == 0) {
 #pragma unroll
-        for (int o = 0; o < 8; ++o) out[o] = fmaf(w[par][o + off], u ? h.y : h.x, out[o]);
+          for (int m = 0; m < 4; ++m) e[m] = Fma2(w[par][(2 * m + off) >> 1], Dup(h), e[m]);
+        } else {
+          s0 = fmaf(Hi(w[par][(off - 1) >> 1]), h, s0);                       /* output 0: word off (odd) */
+#pragma unroll
+          for (int m = 0; m < 3; ++m) od[m] = Fma2(w[par][(2 * m + 1 + off) >> 1], Dup(h), od[m]);
+          s7 = fmaf(Lo(w[par][(7 + off) >> 1]), h, s7);                        /* output 7: word 7 + off (even) */
+        }
       }
     }
+    out[0] = Lo(e[0]) + s0;
+    out[1] = Hi(e[0]) + Lo(od[0]);
+    out[2] = Lo(e[1]) + Hi(od[0]);
+    out[3] = Hi(e[1]) + Lo(od[1]);
+    out[4] = Lo(e[2]) + Hi(od[1]);
+    out[5] = Hi(e[2]) + Lo(od[2]);
+    out[6] = Lo(e[3]) + Hi(od[2]);
+    out[7] = Hi(e[3]) + s7;
   }
 
   /* FE for block t */
@@ -1075,55 +1112,57 @@ struct RxPair {
       const float4 v = src[k];
       w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
     }
-    float a0[4], a1[4];
-#pragma unroll
-    for (int o = 0; o < 4; ++o) { a0[o] = 0.0f; a1[o] = 0.0f; }
+    /* packed FP32: (phase 0, phase 1) of an input = x * (c[2k+1], c[2k]) summed over k */
+    P2 acc[4] = {0ull, 0ull, 0ull, 0ull};
 #pragma unroll
     for (int k = 0; k < 24; ++k) {
       const float2 c = *reinterpret_cast<const float2 *>(tp + 2 * k);
+      const P2 cc = Pack2(c.y, c.x);           /* phase 0: c[(L-1) + k L], phase 1: c[0 + k L] */
 #pragma unroll
-      for (int o = 0; o < 4; ++o) {
-        const float x = w[o + 1 + k];          /* input n - 23 + k, n = 4 tau + o, lives at word 4 tau + o + 1 + k */
-        a0[o] = fmaf(x, c.y, a0[o]);           /* phase 0: c[(L-1) + k L] */
-        a1[o] = fmaf(x, c.x, a1[o]);           /* phase 1: c[0 + k L]     */
-      }
+      for (int o = 0; o < 4; ++o)
+        acc[o] = Fma2(Dup(w[o + 1 + k]), cc, acc[o]);   /* input n - 23 + k, n = 4 tau + o, lives at word 4 tau + o + 1 + k */
     }
-    float *i1 = s + vI1 + 8 + 8 * tau;
-    *reinterpret_cast<float4 *>(i1) = float4{a0[0], a1[0], a0[1], a1[1]};
-    *reinterpret_cast<float4 *>(i1 + 4) = float4{a0[2], a1[2], a0[3], a1[3]};
+    ulonglong2 *i1 = reinterpret_cast<ulonglong2 *>(s + vI1 + 8 + 8 * tau);
+    i1[0] = ulonglong2{acc[0], acc[1]};
+    i1[1] = ulonglong2{acc[2], acc[3]};
   }
 
-  /* arm_fir_interpolate_f32, L = 4, 32 taps + volume (Process.cpp:919-931): 2 x 4 inputs per thread */
+  /* arm_fir_interpolate_f32, L = 4, 32 taps + volume (Process.cpp:919-931): 2 x 4 inputs per thread.
+     Packed FP32: the four phases of an input are two (phase 0, phase 1) / (phase 2, phase 3) pairs; out[4 n + p] =
+     sum_k x[n - 7 + k] c[(3 - p) + 4 k], volume folded into the taps. */
   __device__ __forceinline__ void Interp2(int t) {
     const float *tp = s + oTapsF + 122;
-    float c[kInt2Taps];
+    const float vol = r.volume;
+    P2 c01[8], c23[8];
 #pragma unroll
-    for (int i = 0; i < kInt2Taps; i += 2) {
-      const float2 v = *reinterpret_cast<const float2 *>(tp + i);
-      c[i] = v.x; c[i + 1] = v.y;
+    for (int k = 0; k < 8; ++k) {
+      const float2 lo = *reinterpret_cast<const float2 *>(tp + 4 * k), hi = *reinterpret_cast<const float2 *>(tp + 4 * k + 2);
+      c01[k] = Pack2(hi.y * vol, hi.x * vol);                              /* phases 0, 1: c[4k+3], c[4k+2] */
+      c23[k] = Pack2(lo.y * vol, lo.x * vol);                              /* phases 2, 3: c[4k+1], c[4k]   */
     }
     float4 *dst = reinterpret_cast<float4 *>(a.audio + ((size_t)sid * a.n_blocks + t) * kBlock);
-    const float vol = r.volume;
 #pragma unroll 1
     for (int rr = 0; rr < 2; ++rr) {
       const int n0 = 4 * tau + 256 * rr;
-      float w[12];
+      P2 w[12];
       const float4 *src = reinterpret_cast<const float4 *>(s + vI1 + n0);
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         const float4 v = src[k];
-        w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+        w[4 * k] = Pack2(v.x, v.x); w[4 * k + 1] = Pack2(v.y, v.y); w[4 * k + 2] = Pack2(v.z, v.z); w[4 * k + 3] = Pack2(v.w, v.w);
       }
 #pragma unroll
       for (int o = 0; o < 4; ++o) {
-        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        P2 a01 = 0ull, a23 = 0ull;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const float x = w[o + 1 + k];        /* input n - 7 + k at word n + 1 + k */
-#pragma unroll
-          for (int p = 0; p < 4; ++p) acc[p] = fmaf(x, c[4 * k + (3 - p)], acc[p]);
+          a01 = Fma2(w[o + 1 + k], c01[k], a01);     /* input n - 7 + k at word n + 1 + k */
+          a23 = Fma2(w[o + 1 + k], c23[k], a23);
         }
-        dst[n0 + o] = float4{acc[0] * vol, acc[1] * vol, acc[2] * vol, acc[3] * vol};
+        float4 o4;
+        Unpack2(a01, o4.x, o4.y);
+        Unpack2(a23, o4.z, o4.w);
+        dst[n0 + o] = o4;
       }
     }
   }
