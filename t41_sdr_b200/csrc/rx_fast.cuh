@@ -649,23 +649,34 @@ struct RxPair {
       const float4 v = *reinterpret_cast<const float4 *>(s + oTapsF + 4 * k);
       tap[4 * k] = v.x; tap[4 * k + 1] = v.y; tap[4 * k + 2] = v.z; tap[4 * k + 3] = v.w;
     }
-    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-    float w[4][12];
+    /* packed FP32 as in Dec2: even window offsets feed the output pairs (0,1)(2,3), odd ones the pair (1,2) plus
+       outputs 0 and 3 alone */
+    P2 w[4][6];
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
-      const float4 *src = reinterpret_cast<const float4 *>(mix + (ch * 4 + p) * kMixPlane + 4 * lane);
+      const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(mix + (ch * 4 + p) * kMixPlane + 4 * lane);
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        const float4 v = src[k];
-        w[p][4 * k] = v.x; w[p][4 * k + 1] = v.y; w[p][4 * k + 2] = v.z; w[p][4 * k + 3] = v.w;
+        const ulonglong2 v = src[k];
+        w[p][2 * k] = v.x;
+        w[p][2 * k + 1] = v.y;
       }
     }
+    P2 e0 = 0ull, e1 = 0ull, od = 0ull;
+    float s0 = 0.0f, s3 = 0.0f;
 #pragma unroll
     for (int t = 0; t < kDec1Taps; ++t) {
-      const int p = (1 + t) & 3, off = 1 + ((1 + t) >> 2);
-#pragma unroll
-      for (int o = 0; o < 4; ++o) acc[o] = fmaf(w[p][o + off], tap[t], acc[o]);
+      const int p = (1 + t) & 3, off = 1 + ((1 + t) >> 2);        /* output o reads window word o + off */
+      if ((off & 1) == 0) {
+        e0 = Fma2(w[p][off >> 1], Dup(tap[t]), e0);
+        e1 = Fma2(w[p][(off >> 1) + 1], Dup(tap[t]), e1);
+      } else {
+        s0 = fmaf(Hi(w[p][(off - 1) >> 1]), tap[t], s0);
+        od = Fma2(w[p][(off + 1) >> 1], Dup(tap[t]), od);
+        s3 = fmaf(Lo(w[p][(off + 3) >> 1]), tap[t], s3);
+      }
     }
+    const float acc[4] = {Lo(e0) + s0, Hi(e0) + Lo(od), Lo(e1) + Hi(od), Hi(e1) + s3};
     /* d1 sample n = 128 q + 4 L + o -> plane (n & 1), entry n >> 1 */
     const int e = 64 * q + 2 * lane;
     *reinterpret_cast<float2 *>(d1 + (ch * 2 + 0) * kD1Plane + D1W(24 + e)) = float2{acc[0], acc[2]};
