@@ -196,6 +196,24 @@ def test_c2_full_size_1024_receivers():
     assert np.array_equal(p.view(np.uint32), audio[perm].view(np.uint32))
 
 
+def test_receivers_per_cta_invariance(monkeypatch):
+    """The throughput kernel's result for a receiver must not depend on how many receivers share its CTA (which
+    decides which AGC lane and which shared-memory slot it gets, and how the warps interleave): a race between the
+    receiver pairs, the AGC warp and the asynchronous copies would show up here as a difference."""
+    S, T, D = 296, 12, 16
+    base_p, base_iq, params, iq = _c2_bank(S, T, D)
+    outs = []
+    for g in ("1", "2", "5", "7"):
+        monkeypatch.setenv("T41RX_FAST_G", g)        # developer knob of the launcher (receivers per CTA)
+        with _receiver(S) as eng:
+            eng.set_params_each(params)
+            outs.append(eng.process(iq, row_every=4))
+    monkeypatch.delenv("T41RX_FAST_G")
+    for o in outs[1:]:
+        assert np.array_equal(o["audio"].view(np.uint32), outs[0]["audio"].view(np.uint32))
+        assert np.array_equal(o["spec"], outs[0]["spec"])
+
+
 def test_c4_full_size_16384_spectrum_rows():
     S, T, D = 16384, 2, 10
     base_p = [cases.P(spectrum_zoom=k % 5, current_scale=1 + (k // 5)) for k in range(D)]
