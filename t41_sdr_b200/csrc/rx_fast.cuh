@@ -510,6 +510,20 @@ struct RxPair {
   /* ---------------- front end ---------------- */
   /* blocked inclusive scan over the lanes of a warp of chunk-end values of the recurrence w <- a1 w + x
      (8 samples per lane): after it, lane L holds the true w at the end of its chunk */
+  /* the same scan on an (I, Q) pair */
+  __device__ __forceinline__ P2 ScanDc2(P2 e) const {
+    float m = kDcA1;
+    m *= m; m *= m; m *= m;            /* a1^8 */
+    P2 v = e;
+#pragma unroll
+    for (int d = 1; d <= 8; d <<= 1) {
+      const P2 t = Pack2(__shfl_up_sync(kFull, Lo(v), d), __shfl_up_sync(kFull, Hi(v), d));
+      if (lane >= d) v = Fma2(Dup(m), t, v);
+      m *= m;
+    }
+    /* a1^128 ~ 2e-9: the 16-lane step is below a float's resolution */
+    return v;
+  }
   __device__ __forceinline__ float ScanDc(float e) const {
     float m = kDcA1;
     m *= m; m *= m; m *= m;            /* a1^8 */
@@ -530,60 +544,60 @@ struct RxPair {
   template <bool kTable>
   __device__ __forceinline__ void QuarterMix(int q, float cI, float cQ, F2 base, const float2 *osc) {
     const float *raw = s + oRaw + (q & 1) * kRawBufWords + tau * kRawChunkWords;
-    float xi[8], xq[8];
+    /* the I and the Q chain run the same recurrence with the same constants: packed FP32 on (I, Q) pairs, which
+       is how the samples sit in memory */
+    P2 x[8];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const float4 v = *reinterpret_cast<const float4 *>(raw + 4 * k);
-      xi[2 * k] = v.x; xq[2 * k] = v.y; xi[2 * k + 1] = v.z; xq[2 * k + 1] = v.w;
+      const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(raw + 4 * k);
+      x[2 * k] = v.x;
+      x[2 * k + 1] = v.y;
     }
-    /* zero-state recurrences (two independent chains) */
-    float wi[8], wq[8];
+    /* zero-state recurrences */
+    P2 w[8];
     {
-      float ai = 0.0f, aq = 0.0f;
+      P2 acc = 0ull;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        ai = fmaf(kDcA1, ai, xi[j]);
-        aq = fmaf(kDcA1, aq, xq[j]);
-        wi[j] = ai;
-        wq[j] = aq;
+        acc = Fma2(Dup(kDcA1), acc, x[j]);
+        w[j] = acc;
       }
     }
     float p8 = kDcA1;
     p8 *= p8; p8 *= p8; p8 *= p8;
     /* warp 0 knows the value entering its half (cI, cQ) and folds it into lane 0's chunk end; warp 1 scans from
        zero and adds the decayed end value of warp 0's half once that is known (the recurrence is linear) */
-    float ei = wi[7], eq = wq[7];
-    if (tau == 0) { ei = fmaf(p8, cI, ei); eq = fmaf(p8, cQ, eq); }
-    float si = ScanDc(ei), sq = ScanDc(eq);
-    float ci = __shfl_up_sync(kFull, si, 1), cq = __shfl_up_sync(kFull, sq, 1);
+    P2 e = w[7];
+    if (tau == 0) e = Fma2(Dup(p8), Pack2(cI, cQ), e);
+    const P2 sc = ScanDc2(e);
+    P2 c = Pack2(__shfl_up_sync(kFull, Lo(sc), 1), __shfl_up_sync(kFull, Hi(sc), 1));
     if (tau == 31) {
-      s[oMiscF + mMidI] = si;
-      s[oMiscF + mMidQ] = sq;
+      s[oMiscF + mMidI] = Lo(sc);
+      s[oMiscF + mMidQ] = Hi(sc);
     }
     PairSync();
     if (w2 == 0) {
-      if (lane == 0) { ci = cI; cq = cQ; }
+      if (lane == 0) c = Pack2(cI, cQ);
     } else {
-      const float mI = s[oMiscF + mMidI], mQ = s[oMiscF + mMidQ];
-      if (lane == 0) { ci = mI; cq = mQ; }
-      else { ci = fmaf(r.pow8, mI, ci); cq = fmaf(r.pow8, mQ, cq); }
+      const P2 mid = Pack2(s[oMiscF + mMidI], s[oMiscF + mMidQ]);
+      if (lane == 0) c = mid;
+      else c = Fma2(Dup(r.pow8), mid, c);
       if (lane == 31) {              /* recurrence values leaving the quarter (a1^256 of warp 0's end is below resolution) */
-        s[oMiscF + mEndI] = si;
-        s[oMiscF + mEndQ] = sq;
+        s[oMiscF + mEndI] = Lo(sc);
+        s[oMiscF + mEndQ] = Hi(sc);
       }
     }
     /* true recurrence values, first difference (DC-block numerator 1 - z^-1) */
     float yi[8], yq[8];
     {
-      float pw = kDcA1, pi_ = ci, pq_ = cq;
+      float pw = kDcA1;
+      P2 prev = c;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float ti = fmaf(pw, ci, wi[j]);
-        const float tq = fmaf(pw, cq, wq[j]);
-        yi[j] = ti - pi_;
-        yq[j] = tq - pq_;
-        pi_ = ti;
-        pq_ = tq;
+        const P2 t = Fma2(Dup(pw), c, w[j]);
+        const P2 y = Fma2(Dup(-1.0f), prev, t);
+        Unpack2(y, yi[j], yq[j]);
+        prev = t;
         pw *= kDcA1;    /* compile-time constant after unrolling */
       }
     }
