@@ -120,6 +120,13 @@ struct SectionTimer {
 #define T41RX_LAP(tm, slot) ((void)0)
 #endif
 
+/* sqrt.approx.f32: maximum relative error 2^-23 (the envelope detector's input; SNR budget 90 dB) */
+__device__ __forceinline__ float SqrtFast(float x) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 struct F2 { float x, y; };
 
 /* packed FP32 pairs (sm_100 FFMA2: two FMAs per issue slot) */
@@ -948,7 +955,7 @@ struct RxPair {
     for (int i = tau; i < kAgcDelay; i += 64) {
       const float2 h = zh[i];
       stz[ZPos(i)] = h;
-      E[i] = __fsqrt_rn(h.x * h.x + h.y * h.y);
+      E[i] = SqrtFast(h.x * h.x + h.y * h.y);
     }
     PairSync();
 #pragma unroll
@@ -956,7 +963,7 @@ struct RxPair {
       const int i = tau + 64 * o;
       if (i + kAgcDelay < kDec) stz[ZPos(i + kAgcDelay)] = z[o];
       else zh[i + kAgcDelay - kDec] = z[o];
-      E[kAgcDelay + i] = __fsqrt_rn(z[o].x * z[o].x + z[o].y * z[o].y);
+      E[kAgcDelay + i] = SqrtFast(z[o].x * z[o].x + z[o].y * z[o].y);
     }
     if (tau < 7) E[353 + tau] = 0.0f;
     PairSync();
