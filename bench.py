@@ -76,6 +76,14 @@ def workload(n_blocks):
         else:
             params.append(cases.P(mode=cases.AM, nco_freq=nco, agc_mode=1))
             sigs.append(synth.am(900 + k, n_blocks, mode=cases.AM, nco_freq=nco, depth=0.5, f_mod=400.0))
+    if os.environ.get("T41RX_BENCH_MODE"):       # developer knob: every receiver in one mode (0 USB, 2 AM) / AGC off (-1)
+        m = int(os.environ["T41RX_BENCH_MODE"])
+        for p in params:
+            if m < 0:
+                p.agc_mode = 0
+            else:
+                p.mode = m
+                p.f_lo_cut, p.f_hi_cut = (300, 3000) if m == 0 else (-3000, 3000)
     if os.environ.get("T41RX_BENCH_ZOOM"):       # developer knob (rows-kernel experiments)
         for p in params:
             p.spectrum_zoom = int(os.environ["T41RX_BENCH_ZOOM"])

@@ -1427,11 +1427,10 @@ struct AgcLane {
 /* one block of one receiver per lane.  sta: |z| delayed [256] | window max [256] (overwritten by volts) |
  * per-chunk zero-state advances (PF, PH)[32] of the two back-averages.
  *
- * Almost every sample leaves the envelope detector in a "quiet" state: slow decay (3), hang decay (4) or
- * hang (2) with the window maximum below volts, where the update is v <- max(v + (r - v) c, min_volts) with a
- * per-state constant and no branch.  The warp runs 8 samples at a time speculatively
- * on that form (all lanes), votes once, and only re-runs the chunk through the exact per-sample state machine
- * (Step) when some lane saw a transition (attack, end of hang, states 0 / 1). */
+ * Almost every sample CONTINUES the state the envelope detector is in (attack, fast decay, hang, slow decay, hang
+ * decay), where the update is v <- max(v + (r - v) c, min_volts) with a per-state constant and no branch.  The
+ * warp runs 8 samples at a time speculatively on that form (all lanes), votes once, and only re-runs the chunk
+ * through the exact per-sample state machine (Step) when some lane saw a transition between states. */
 __device__ __forceinline__ void AgcBlock(AgcLane &g, float *sta, bool active) {
   constexpr int kC = 8;
   /* window maxima and back-average advances of the chunk being processed; the next chunk's are fetched
@@ -1456,13 +1455,18 @@ __device__ __forceinline__ void AgcBlock(AgcLane &g, float *sta, bool active) {
        so the difference from the reference's rounding is ~1e-13 v); state 4: v + (r - v) hang_decay; state 2
        with the hang counter not expiring inside the chunk: v unchanged */
     const int st = g.state;
-    const float c = (st == 3) ? g.decay * 0.05f : ((st == 4) ? g.hdecay : 0.0f);
-    bool ok = (st == 3) || (st == 4) || (st == 2 && g.hc > kC);
+    /* continuation steps of every state: 0 = attack while the window maximum stays at or above volts; 1 = fast
+       decay while volts stays above the saved level; 2 = hang; 3 / 4 = slow / hang decay; all have the form
+       v <- max(v + (r - v) c, min_volts).  Only the transitions between them need the full state machine. */
+    const bool att = (st == 0);
+    const float c = att ? g.attack : ((st == 1) ? g.fdecay : ((st == 3) ? g.decay * 0.05f : ((st == 4) ? g.hdecay : 0.0f)));
+    const float floor1 = (st == 1) ? g.save : -3.0e38f;       /* state 1 continues only while v > save */
+    bool ok = (st != 2) || (g.hc > kC);
     float v = g.v, last = g.v;
     float vo[kC];
 #pragma unroll
     for (int k = 0; k < kC; ++k) {
-      ok = ok && !(rm[k] >= v);
+      ok = ok && ((rm[k] >= v) == att) && (v > floor1);
       last = fmaf(rm[k] - v, c, v);
       v = fmaxf(last, g.minv);
       vo[k] = v;
