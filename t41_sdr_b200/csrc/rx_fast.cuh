@@ -1526,21 +1526,24 @@ __device__ __forceinline__ void StreamKernelBody(const LaunchArgs &a, int G, flo
     MbarInit(done + 1, 32u);
   }
   __syncthreads();
-  if (warp < 2 * G) {
+  /* warp 0 = the AGC warp (measured: the latency-critical warp does better with the lowest warp id),
+     warps 1 + 2 p, 2 + 2 p = receiver pair p */
+  const int pw = warp - 1;
+  if (warp != 0) {
     /* ---- receiver pair ---- */
-    const int pair = warp >> 1;
+    const int pair = pw >> 1;
     const bool live = pair < ng;
     if (!live) return;
     const int sid = a.stream_ids ? __ldg(a.stream_ids + s0 + pair) : a.stream_base + s0 + pair;
-    RxPair w(a, smem + pair * kSlotF, sid, lane, warp & 1, 1 + pair);
+    RxPair w(a, smem + pair * kSlotF, sid, lane, pw & 1, 1 + pair);
     w.LoadState();
     w.IssueQuarter(0, 0);
-    w.tm.Start(blockIdx.x == 0 && warp == 0 && lane == 0, 0);
+    w.tm.Start(blockIdx.x == 0 && pw == 0 && lane == 0, 0);
     for (int k = 0; k < T + 2; ++k) {
       /* the last 128 I samples of block k (see FrontEnd) are fetched before the back end: their HBM
          latency hides behind it */
       float4 tu = float4{0, 0, 0, 0}, tv = tu;
-      if (k < T && (warp & 1) == 0) {
+      if (k < T && (pw & 1) == 0) {
         const float4 *p = reinterpret_cast<const float4 *>(w.BlockIq(k) + 2 * (kBlock - 4 * (lane + 1)));
         tu = __ldg(p);
         tv = __ldg(p + 1);
