@@ -31,7 +31,7 @@ extern "C" int t41rx_debug_fast_cycles(unsigned long long *out32, int reset) {
 
 cudaError_t ConfigureStreamKernel() {
   return cudaFuncSetAttribute(t41rx_stream_rx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)(fast::kFastMaxG * fast::kSlotF * sizeof(float) + 64));
+                              (int)(fast::kFastMaxG * fast::kSlotF * sizeof(float) + 32));
 }
 
 cudaError_t LaunchStreamKernel(const LaunchArgs &a, int n_sms, cudaStream_t st) {
@@ -45,7 +45,7 @@ cudaError_t LaunchStreamKernel(const LaunchArgs &a, int n_sms, cudaStream_t st) 
     if (g >= 1 && g <= fast::kFastMaxG) G = g;
   }
   const int grid = (a.n_streams + G - 1) / G;
-  t41rx_stream_rx_kernel<<<grid, 64 * G + 32, (size_t)G * fast::kSlotF * sizeof(float) + 64, st>>>(a, G);
+  t41rx_stream_rx_kernel<<<grid, 64 * G + 32, (size_t)G * fast::kSlotF * sizeof(float) + 32, st>>>(a, G);
   return cudaGetLastError();
 }
 

@@ -46,14 +46,19 @@ constexpr int kStZBuf = 576;                          /* 256 complex, 2 pad word
 constexpr int oZH = oStZ + 2 * kStZBuf;                      /* 7168: last 97 complex filter outputs */
 constexpr int oTapsF = oZH + 196;                     /* 7464: dec1 28 | dec2 46 | int1 48 | int2 32 (+2) */
 constexpr int oNcoW = oTapsF + 156;                   /* 7620: W[8] float2, Q[4] float2 */
+constexpr int oXtra = oNcoW + 24;                     /* 7644: 16 words of once-per-block scalars (enum x*) */
 constexpr int oIH = oNcoW + 40;                       /* 7660: int1 history 23 (24) | int2 history 7 (8) */
 constexpr int oMH = oIH + 32;                         /* 7692: dec1 history, 8 planes x 8 */
 constexpr int oDH = oMH + 64;                         /* 7756: dec2 history, 4 planes x 24 */
 constexpr int oMiscF = oDH + 96;                      /* 7852 */
-constexpr int kSlotF = oMiscF + 28;                   /* == 4 (mod 8): the AGC warp's LDS.128 hit distinct banks */
+constexpr int kSlotF = oMiscF + 36;                   /* == 4 (mod 8): the AGC warp's LDS.128 hit distinct banks */
 enum { mEndI = 0, mEndQ = 1, mSettled = 2, mMidI = 3, mMidQ = 11, mPhasor = 4 /* 2 doubles */, mInvIn = 8, mTarget = 9, mSlope = 10,
        mOmF = 12, mOmH = 13, mFbm = 14, mHbm = 15,
-       mAmWold = 16, mAmX1 = 17, mAmX2 = 18, mAmY1 = 19, mAmY2 = 20, mNfmI = 21, mNfmQ = 22, mAmLp = 23 /* 5 */ };
+       mAmWold = 16, mAmX1 = 17, mAmX2 = 18, mAmY1 = 19, mAmY2 = 20, mNfmI = 21, mNfmQ = 22, mAmLp = 23 /* 5 */,
+       mBlkRot = 28 /* 2 doubles: rotation of the block phasor over 2048 samples */, mVolScale = 32, mVolume = 33,
+       mFixedGain = 34, mIqPhase = 35 };
+enum { xInGain = 0 /* rfGainValue * b0 * 1.1 (DC-block numerator and freqAdjFactor folded) */, xRfGain = 1 /* int */,
+       xCodecTimer = 2 /* unsigned */, xNegIqAmp = 3, xFilterId = 4 /* int */ };
 static_assert((oMiscF % 2) == 0 && (oTapsF % 4) == 0, "alignment");
 static_assert(kSlotF % 8 == 4, "slot stride");
 static_assert((oStA % 4) == 0 && (oStZ % 4) == 0 && (oRaw % 4) == 0 && (oMix % 4) == 0 && (oD1 % 4) == 0, "16-byte alignment");
@@ -175,25 +180,13 @@ __device__ __forceinline__ void MbarWait(uint64_t *bar, unsigned parity) {
 /* everything a receiver warp keeps in registers across blocks (uniform over the lanes unless noted) */
 struct RxRegs {
   /* configuration */
-  int mode, agc_mode, mirrored;
-  float in_gain;         /* rfGainValue * b0 * 1.1 (DC-block numerator and freqAdjFactor folded) */
-  float neg_iq_amp, iq_phase, vol_scale, volume, fixed_gain;
-  /* state */
-  int rf_gain;
-  unsigned codec_timer;
-  int first_block;
-  double ph_re, ph_im;   /* unit block phasor exp(j * phase) of the oscillator */
-  int nco_closed;
-  double osc_q, osc_i;   /* Osc_Vect while the amplitude loop is still settling (lane 0) */
-  double blk_cos, blk_sin;   /* rotation of the block phasor over 2048 samples */
+  /* small integers share one register (the kernel sits at its 128-register cap; spills go to L2 here) */
+  unsigned mode : 4, agc_mode : 3, mirrored : 1, first_block : 1, nco_closed : 1, psk_enable : 1;
   F2 tw_a, tw_b;         /* this thread's base twiddles of the stride-64 and stride-8 radix-8 passes */
-  const float2 *mask;    /* frequency-domain filter mask of the receiver's filter set */
-  int psk_enable;
   const char *cp_src;    /* this thread's first 16-byte piece of quarter 0 of block 0 */
   unsigned cp_dst;       /* its shared-memory address in raw buffer 0 */
   /* lane constants */
   F2 lane_rot;           /* nco_amp * exp(-j * delta * (8 * tau + 1)) */
-  float tail_w;          /* a1^(4 * lane): weight of this lane's partial sum in the I-tail pre-read */
   float pow8;            /* a1^(8 * lane): decay of the carry entering the warp's half quarter up to this lane */
 };
 
@@ -299,6 +292,12 @@ struct RxPair {
   __device__ __forceinline__ RxPair(const LaunchArgs &a_, float *s_, int sid_, int lane_, int w2_, int bar_)
       : a(a_), s(s_), sid(sid_), lane(lane_), w2(w2_), tau(32 * w2_ + lane_), bar_id(bar_) {}
 
+  /* Make the thread indices opaque at a stage boundary: address arithmetic derived from them is then
+     recomputed inside the stage instead of being kept live (and spilled) across the whole block loop. */
+  __device__ __forceinline__ void Launder() {
+    asm volatile("" : "+r"(lane), "+r"(tau));
+  }
+
   __device__ __forceinline__ void PairSync() const {
     asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
   }
@@ -327,16 +326,15 @@ struct RxPair {
     const FilterSet &fs = a.fsets[cf.filter_id];
     r.mode = cf.mode;
     r.agc_mode = cf.agc_mode;
-    r.mirrored = cf.mirrored;
-    r.in_gain = cf.rf_gain_value * kDcB0 * 1.1f;
-    r.neg_iq_amp = cf.neg_iq_amp;
-    r.iq_phase = cf.iq_phase;
-    r.vol_scale = cf.vol_scale;
-    r.volume = cf.volume;
-    r.fixed_gain = cf.agc.fixed_gain;
-    r.rf_gain = st.rf_gain;
-    r.codec_timer = st.codec_timer;
-    r.first_block = st.first_block;
+    r.mirrored = cf.mirrored != 0;
+    if (tau == 4) {
+      s[oXtra + xInGain] = cf.rf_gain_value * kDcB0 * 1.1f;
+      s[oXtra + xNegIqAmp] = cf.neg_iq_amp;
+      reinterpret_cast<int *>(s)[oXtra + xRfGain] = st.rf_gain;
+      reinterpret_cast<int *>(s)[oXtra + xFilterId] = cf.filter_id;
+      reinterpret_cast<unsigned *>(s)[oXtra + xCodecTimer] = st.codec_timer;
+    }
+    r.first_block = st.first_block != 0;
     r.nco_closed = (st.nco_closed && st.nco_epoch_seen == cf.nco_epoch) ? 1 : 0;
     {
       double sn, cs;
@@ -345,15 +343,16 @@ struct RxPair {
         cs = st.fast_ph_re;
         sn = st.fast_ph_im;
       }
-      r.ph_re = cs;
-      r.ph_im = sn;
-      if (st.nco_closed) {       /* leaving closed form (retune): rebuild the vector at the settled radius */
+      if (tau == 0) {               /* unit block phasor exp(j * phase) of the oscillator: shared memory, FP64 */
+        double *md = reinterpret_cast<double *>(s + oMiscF + mPhasor);
+        md[0] = cs;
+        md[1] = sn;
+      }
+      /* Osc_Vect of a still-settling oscillator lives in the HBM state (rare path, one thread) */
+      if (st.nco_closed && !r.nco_closed && tau == 0) {   /* leaving closed form (retune): rebuild it at the settled radius */
         const double rr = sqrt(st.osc_q * st.osc_q + st.osc_i * st.osc_i);
-        r.osc_q = rr * cs;
-        r.osc_i = rr * sn;
-      } else {
-        r.osc_q = st.osc_q;
-        r.osc_i = st.osc_i;
+        a.st[sid].osc_q = rr * cs;
+        a.st[sid].osc_i = rr * sn;
       }
     }
     {
@@ -361,15 +360,13 @@ struct RxPair {
       sincos(-cf.nco_delta * (double)(8 * tau + 1), &sn, &cs);
       r.lane_rot = F2{(float)(cf.nco_amp * cs), (float)(cf.nco_amp * sn)};
     }
-    r.tail_w = PowA1(4 * lane);
     r.pow8 = PowA1(8 * lane);
     {
       const float2 ta = __ldg(a.twiddle + tau), tb = __ldg(a.twiddle + 8 * (tau & 7));
       r.tw_a = F2{ta.x, ta.y};
       r.tw_b = F2{tb.x, tb.y};
     }
-    r.mask = reinterpret_cast<const float2 *>(fs.mask);
-    r.psk_enable = cf.psk31_enable;
+    r.psk_enable = cf.psk31_enable != 0;
     if (tau == 2) {
       s[oMiscF + mAmWold] = st.am_wold;
       s[oMiscF + mAmX1] = st.am_lp_state[0];
@@ -380,7 +377,17 @@ struct RxPair {
       s[oMiscF + mNfmQ] = st.nfm_last_q;
       for (int i = 0; i < 5; ++i) s[oMiscF + mAmLp + i] = cf.am_lp[i];
     }
-    sincos(cf.nco_block_delta, &r.blk_sin, &r.blk_cos);
+    if (tau == 3) {
+      double bs, bc;
+      sincos(cf.nco_block_delta, &bs, &bc);
+      double *rot = reinterpret_cast<double *>(s + oMiscF + mBlkRot);
+      rot[0] = bc;
+      rot[1] = bs;
+      s[oMiscF + mVolScale] = cf.vol_scale;
+      s[oMiscF + mVolume] = cf.volume;
+      s[oMiscF + mFixedGain] = cf.agc.fixed_gain;
+      s[oMiscF + mIqPhase] = cf.iq_phase;
+    }
     {
       const int chunk0 = 8 * w2 + (lane & 7), piece = lane >> 3;
       r.cp_src = reinterpret_cast<const char *>(BlockIq(0)) + chunk0 * 64 + piece * 16;
@@ -490,24 +497,24 @@ struct RxPair {
       st.dc_d2 = 0.0f;
       st.fast_native = 1;
       st.fast_dc_w = s[oMiscF + mEndQ];
-      st.fast_ph_re = r.ph_re;
-      st.fast_ph_im = r.ph_im;
-      st.rf_gain = r.rf_gain;
-      st.codec_timer = r.codec_timer;
+      const double *md = reinterpret_cast<const double *>(s + oMiscF + mPhasor);
+      const double ph_re = md[0], ph_im = md[1];
+      st.fast_ph_re = ph_re;
+      st.fast_ph_im = ph_im;
+      st.rf_gain = reinterpret_cast<const int *>(s)[oXtra + xRfGain];
+      st.codec_timer = reinterpret_cast<const unsigned *>(s)[oXtra + xCodecTimer];
       st.first_block = r.first_block;
       if (r.nco_closed) {
-        double ph = atan2(r.ph_im, r.ph_re);
+        double ph = atan2(ph_im, ph_re);
         if (ph < 0) ph += 6.283185307179586476925286766559;
         st.nco_phase = ph;
         st.nco_closed = 1;
         st.nco_epoch_seen = cf.nco_epoch;
         /* keep (osc_q, osc_i) at the settled radius so that a later exact block restarts correctly */
         const double rr = sqrt(cf.nco_r2_fix);
-        st.osc_q = rr * r.ph_re;
-        st.osc_i = rr * r.ph_im;
+        st.osc_q = rr * ph_re;
+        st.osc_i = rr * ph_im;
       } else {
-        st.osc_q = r.osc_q;
-        st.osc_i = r.osc_i;
         st.nco_closed = 0;
         st.nco_epoch_seen = cf.nco_epoch;
       }
@@ -610,18 +617,20 @@ struct RxPair {
     }
     /* I *= -IQAmp, phase correction (Process.cpp:165-174, Utility.cpp:178-187) */
     if (r.mirrored) {
-      if (r.neg_iq_amp == -1.0f) {
+      const float iq_phase_ = s[oMiscF + mIqPhase];
+      const float neg_iq_amp = s[oXtra + xNegIqAmp];
+      if (neg_iq_amp == -1.0f) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) yi[j] = -yi[j];      /* folds into the consumers' operand modifiers */
       } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) yi[j] *= r.neg_iq_amp;
+        for (int j = 0; j < 8; ++j) yi[j] *= neg_iq_amp;
       }
-      if (r.iq_phase != 0.0f) {
+      if (iq_phase_ != 0.0f) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          if (r.iq_phase < 0.0f) yq[j] = fmaf(yi[j], r.iq_phase, yq[j]);
-          else yi[j] = fmaf(yq[j], r.iq_phase, yi[j]);
+          if (iq_phase_ < 0.0f) yq[j] = fmaf(yi[j], iq_phase_, yq[j]);
+          else yi[j] = fmaf(yq[j], iq_phase_, yi[j]);
         }
       }
     }
@@ -775,7 +784,7 @@ struct RxPair {
       acc = fmaf(kDcA1, acc, u.z);
       acc = fmaf(kDcA1, acc, v.x);
       acc = fmaf(kDcA1, acc, v.z);
-      tail = acc * r.tail_w;
+      tail = acc * PowA1(4 * lane);      /* weight of this lane's partial sum */
 #pragma unroll
       for (int d = 16; d >= 1; d >>= 1) tail += __shfl_xor_sync(kFull, tail, d);
     }
@@ -789,8 +798,12 @@ struct RxPair {
       }
     }
     /* gains of this block (Process.cpp:117,133): rfGainValue and RFgain are folded into the phasor */
-    const float gain = r.in_gain * (float)r.rf_gain;
-    const F2 pb = F2{(float)r.ph_re * gain, -(float)r.ph_im * gain};
+    const float gain = s[oXtra + xInGain] * (float)reinterpret_cast<const int *>(s)[oXtra + xRfGain];
+    F2 pb;
+    {
+      const double *md = reinterpret_cast<const double *>(s + oMiscF + mPhasor);
+      pb = F2{(float)md[0] * gain, -(float)md[1] * gain};
+    }
     T41RX_LAP(tm, 0);
     const bool closed = r.nco_closed != 0;
 #pragma unroll 1
@@ -815,7 +828,8 @@ struct RxPair {
            quarter at a time into the idle raw buffer (so no copy is in flight during such a block) */
         float2 *tab = reinterpret_cast<float2 *>(s + oRaw + ((q + 1) & 1) * kRawBufWords);
         if (tau == 0) {
-          double vq = r.osc_q, vi = r.osc_i;
+          StreamState &stt = a.st[sid];
+          double vq = stt.osc_q, vi = stt.osc_i;
           const double oc = cf.osc_cos, os = cf.osc_sin;
           for (int n = 0; n < 512; ++n) {
             const double oq = (vq * oc) - (vi * os);
@@ -825,8 +839,8 @@ struct RxPair {
             vi = gn * oi;
             tab[n] = float2{(float)oq, (float)oi};
           }
-          r.osc_q = vq;
-          r.osc_i = vi;
+          stt.osc_q = vq;
+          stt.osc_i = vi;
           if (q == 3) {               /* settled?  then continue in closed form from the vector's angle */
             const double r2 = vq * vq + vi * vi;
             const double inv = rsqrt(r2);
@@ -850,14 +864,16 @@ struct RxPair {
     }
     if (closed) {
       /* advance the block phasor by 2048 samples */
-      const double nr = r.ph_re * r.blk_cos - r.ph_im * r.blk_sin, ni = r.ph_re * r.blk_sin + r.ph_im * r.blk_cos;
-      r.ph_re = nr;
-      r.ph_im = ni;
-    } else if (s[oMiscF + mSettled] != 0.0f) {      /* written before the last PairSync of quarter 3 */
-      const double *md = reinterpret_cast<const double *>(s + oMiscF + mPhasor);
+      const double *rot = reinterpret_cast<const double *>(s + oMiscF + mBlkRot);
+      const double bc = rot[0], bs = rot[1];
+      if (tau == 0) {               /* every reader is past the quarter loop's barriers; next read is a block away */
+        double *md = reinterpret_cast<double *>(s + oMiscF + mPhasor);
+        const double pr = md[0], pi = md[1];
+        md[0] = pr * bc - pi * bs;
+        md[1] = pr * bs + pi * bc;
+      }
+    } else if (s[oMiscF + mSettled] != 0.0f) {      /* written (with the phasor) before the last PairSync of quarter 3 */
       r.nco_closed = 1;
-      r.ph_re = md[0];
-      r.ph_im = md[1];
     }
     /* save this channel's dec1 plane histories (the FFT buffer overlays the planes) */
     __syncwarp();
@@ -877,20 +893,23 @@ struct RxPair {
     T41RX_LAP(tm, 5);
     AfterDec2(dq, buf);
     /* Codec_gain (Process.cpp:979-1016 with the clip flags never set) */
-    {
-      unsigned timer = r.codec_timer + 1;
+    if (tau == 0) {                   /* the gain was read at the top of this block, behind many barriers */
+      int *rg = reinterpret_cast<int *>(s) + oXtra + xRfGain;
+      unsigned *ct = reinterpret_cast<unsigned *>(s) + oXtra + xCodecTimer;
+      unsigned timer = *ct + 1;
       if (timer > 10000) timer = 10000;
       if (timer >= 50) {
-        r.rf_gain = min(r.rf_gain + 1, 15);
+        *rg = min(*rg + 1, 15);
         timer = 0;
       }
-      r.codec_timer = timer;
+      *ct = timer;
     }
   }
 
   /* level adjust + overlap-save + fast convolution + |z| + window maximum -> staging.
      dq: this warp's channel (w2) of the 8 decimated samples 8 lane .. 8 lane + 7 */
   __device__ void AfterDec2(float (&dq)[8], int buf) {
+    Launder();
     float *fbw = s + oMix;                                   /* FFT buffer as words */
     float2 *fb = reinterpret_cast<float2 *>(s + oMix);
     float2 *stz = reinterpret_cast<float2 *>(s + oStZ + buf * kStZBuf);
@@ -909,7 +928,7 @@ struct RxPair {
       /* component w2 of: first half = previous block, second half = this block (Process.cpp:498-522) */
 #pragma unroll
       for (int o = 0; o < 8; ++o) {
-        const float cur = dq[o] * r.vol_scale;                                       /* Process.cpp:482-492 */
+        const float cur = dq[o] * s[oMiscF + mVolScale];                                       /* Process.cpp:482-492 */
         float prev = s[OlaW(w2, o0 + o)];
         if (r.first_block) prev = 0.0f;                                              /* Process.cpp:498-504 */
         fbw[2 * FPos(o0 + o) + w2] = prev;
@@ -919,7 +938,8 @@ struct RxPair {
       r.first_block = 0;
     }
     PairSync();
-    const float2 *mask = r.mask;
+    /* frequency-domain filter mask of the receiver's filter set */
+    const float2 *mask = reinterpret_cast<const float2 *>(a.fsets[reinterpret_cast<const int *>(s)[oXtra + xFilterId]].mask);
     /* this thread's 8 mask bins (they sit at octal-digit-reversed positions after the forward passes): fetched
        now, used two passes later -- there is next to no L1 beside 227 KB of shared memory, so these come from L2 */
     float2 hm[8];
@@ -1068,6 +1088,7 @@ struct RxPair {
 
   /* ---------------- back end ---------------- */
   __device__ void BackEnd(int t, int buf) {
+    Launder();
     const StreamCfg &cf = a.cfg[sid];
     StreamState &st = a.st[sid];
     const float2 *stz = reinterpret_cast<const float2 *>(s + oStZ + buf * kStZBuf);
@@ -1119,7 +1140,7 @@ struct RxPair {
     if (r.mode == kModePsk31) return;
     if (r.agc_mode == 0) {
 #pragma unroll
-      for (int o = 0; o < 4; ++o) dem[o] = float2{dem[o].x * r.fixed_gain, dem[o].y * r.fixed_gain};
+      for (int o = 0; o < 4; ++o) dem[o] = float2{dem[o].x * s[oMiscF + mFixedGain], dem[o].y * s[oMiscF + mFixedGain]};
       return;
     }
     const float inv_in = s[oMiscF + mInvIn], tgt = s[oMiscF + mTarget], slope = s[oMiscF + mSlope];
@@ -1164,7 +1185,7 @@ struct RxPair {
      sum_k x[n - 7 + k] c[(3 - p) + 4 k], volume folded into the taps. */
   __device__ __forceinline__ void Interp2(int t) {
     const float *tp = s + oTapsF + 122;
-    const float vol = r.volume;
+    const float vol = s[oMiscF + mVolume];
     P2 c01[8], c23[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
