@@ -239,12 +239,17 @@ extern float32_t HP_DC_Butter_state2[2];
 extern int8_t first_block;
 extern int zoom_sample_ptr;
 extern float32_t coefficient_set[];
+/* audio-spectrum by-product of row-producing blocks, Process.cpp:32,34,550-570,791-805 */
+extern int audioYPixel[];
+extern float32_t audioMaxSquaredAve;
 
 static t41o_params g_prm;
 static int g_last_set_rf_gain;
 static int g_inited = 0;
 static unsigned g_psk_block_count = 0;
 static uint16_t g_waterfall[SPECTRUM_RES];
+static int32_t *g_cap_ypixel = 0;   /* [rows][T41O_AUDIO_SPEC_PIXELS], set by t41ref_capture_audio_spectrum */
+static float *g_cap_max_ave = 0;    /* [rows] */
 
 /* RGB565 ramp of Display.cpp:148-161 comes from the generated data header */
 #include "t41_tables_data.h"
@@ -439,9 +444,20 @@ int t41ref_process(const float *iq, float *audio, int n_blocks, int row_every, i
                                   (upd && wf_rows) ? wf_rows + (size_t)rows * 512 : 0,
                                   psk_bits ? psk_bits + b : 0, psk_chars ? psk_chars + b : 0);
     if (rc) return rc;
+    if (upd && g_cap_ypixel) {
+      for (int k = 0; k < T41O_AUDIO_SPEC_PIXELS; k++) g_cap_ypixel[(size_t)rows * T41O_AUDIO_SPEC_PIXELS + k] = audioYPixel[k];
+    }
+    if (upd && g_cap_max_ave) g_cap_max_ave[rows] = audioMaxSquaredAve;
     rows += upd;
   }
   return rows;
+}
+
+/* where the following t41ref_process calls put audioYPixel[0..269] and audioMaxSquaredAve after every
+   row-producing block (NULL = stop capturing) */
+void t41ref_capture_audio_spectrum(int32_t *ypixel_rows, float *max_ave_rows) {
+  g_cap_ypixel = ypixel_rows;
+  g_cap_max_ave = max_ave_rows;
 }
 
 void t41ref_get_params(t41o_params *p) {

@@ -11,6 +11,7 @@
 #ifndef T41_REF_SHIM_H
 #define T41_REF_SHIM_H
 
+#include <type_traits>
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -54,13 +55,21 @@ typedef unsigned int uint;
 #define TWO_PI 6.283185307179586476925286766559
 #define round(x) ((x) >= 0 ? (long)((x) + 0.5) : (long)((x)-0.5))
 
+/* Arduino map() as the Teensyduino core (cores/teensy4/wiring.h; not under /root/reference, no version pinned)
+   overloads it: an integral first argument does 32-bit signed long arithmetic (with the core's range-rounding
+   variant), a floating-point first argument does the plain formula in that argument's own type and returns it.
+   The only use on the receive path is the audio-spectrum by-product (Process.cpp:557,561,799), float argument. */
 template <class T, class A, class B, class C, class D>
-static inline long map(T x, A in_min, B in_max, C out_min, D out_max) {
-  double v = ((double)x - (double)in_min) * ((double)out_max - (double)out_min) /
-                 ((double)in_max - (double)in_min) + (double)out_min;
-  if (!(v > -2.0e9)) return -2000000000L;
-  if (v > 2.0e9) return 2000000000L;
-  return (long)v;
+static inline typename std::enable_if<std::is_integral<T>::value, long>::type map(T _x, A _in_min, B _in_max, C _out_min,
+                                                                                   D _out_max) {
+  long x = _x, in_min = _in_min, in_max = _in_max, out_min = _out_min, out_max = _out_max;
+  if ((in_max - in_min) > (out_max - out_min)) return (x - in_min) * (out_max - out_min + 1) / (in_max - in_min + 1) + out_min;
+  return (x - in_min) * (out_max - out_min) / (in_max - in_min) + out_min;
+}
+template <class T, class A, class B, class C, class D>
+static inline typename std::enable_if<std::is_floating_point<T>::value, T>::type map(T x, A in_min, B in_max, C out_min,
+                                                                                      D out_max) {
+  return (x - (T)in_min) * ((T)out_max - (T)out_min) / ((T)in_max - (T)in_min) + (T)out_min;
 }
 
 static inline void delay(unsigned long) {}

@@ -328,6 +328,11 @@ struct t41o_stream {
   arm_fir_decimate_instance_f32 zoom_fir_i, zoom_fir_q;
   float zoom_ring_x[kSpecRes], zoom_ring_y[kSpecRes];
   int zoom_sample_ptr;
+  /* audio-spectrum by-product, T41/Process.cpp:32-34 */
+  float audio_max_sq_ave;
+  int audio_ypixel[T41O_AUDIO_SPEC_PIXELS];
+  int32_t *cap_ypixel;
+  float *cap_max_ave;
   float spec_buf[2 * kSpecRes];
   float fft_spec[kSpecRes];
   float fft_spec_old[kSpecRes];
@@ -851,6 +856,36 @@ void t41o_get_debug(const t41o_stream *s, t41o_debug *d) {
   d->osc_vect_i = s->osc_vect_i;
 }
 
+/* Arduino map() with a float first argument, as the Teensyduino core overloads it (cores/teensy4/wiring.h; the
+   core is not under /root/reference and no version is pinned): all arithmetic in the argument's type. */
+static inline float MapFloat(float x, int in_min, int in_max, int out_min, int out_max) {
+  return (x - (float)in_min) * ((float)out_max - (float)out_min) / ((float)in_max - (float)in_min) + (float)out_min;
+}
+
+/* T41/Process.cpp:550-570 (offset 50; LSB reads the mirrored side) and :791-805 (NFM, offset 20): squares of the
+   masked spectrum's 1024 floats stored reversed, 3-point average -> 15 log10 -> map() -> int pixel, clamped at 0;
+   the largest square feeds the S-meter's running average.  The float -> int conversion of -inf / NaN (empty
+   spectrum) is undefined in C++ and INT_MIN or 0 on the targets; both end up 0 after the clamp. */
+static void AudioSpectrum(t41o_stream *s, int mode) {
+  float sq[2 * kFFT];
+  for (int k = 0; k < 2 * kFFT; k++) sq[2 * kFFT - 1 - k] = (s->ifft_buf[k] * s->ifft_buf[k]);
+  const int offset = (mode == T41O_DEMOD_NFM) ? 20 : 50;
+  for (int k = 0; k < T41O_AUDIO_SPEC_PIXELS; k++) {
+    float v;
+    if (mode == T41O_DEMOD_USB || mode == T41O_DEMOD_AM || mode == T41O_DEMOD_SAM || mode == T41O_DEMOD_NFM) {
+      v = offset + MapFloat(15 * log10f((sq[1021 - k] + sq[1022 - k] + sq[1023 - k]) / 3), 0, 100, 0, 120);
+    } else if (mode == T41O_DEMOD_LSB) {
+      v = offset + MapFloat(15 * log10f((sq[k] + sq[k + 1] + sq[k + 2]) / 3), 0, 100, 0, 120);
+    } else {
+      continue;
+    }
+    s->audio_ypixel[k] = (v >= 0.0f) ? (int)v : 0;       /* false for NaN too */
+  }
+  float mx = sq[0];
+  for (int k = 1; k < 2 * kFFT; k++) if (sq[k] > mx) mx = sq[k];     /* arm_max_f32 */
+  s->audio_max_sq_ave = .5 * mx + .5 * s->audio_max_sq_ave;
+}
+
 int t41o_process_block(t41o_stream *s, const float *iq, float *audio, int update_display,
                        int16_t *spec_row, uint16_t *wf_row, int8_t *psk_bit, uint8_t *psk_char) {
   if (!s || !iq || !audio) return -1;
@@ -943,6 +978,7 @@ int t41o_process_block(t41o_stream *s, const float *iq, float *audio, int update
     }
     arm_cfft_f32(&arm_cfft_sR_f32_len512, s->fft_buf, 0, 1);
     arm_cmplx_mult_cmplx_f32(s->fft_buf, s->mask, s->ifft_buf, kFFT);
+    if (update_display) AudioSpectrum(s, mode);          /* T41/Process.cpp:550-570 */
     arm_cfft_f32(&arm_cfft_sR_f32_len512, s->ifft_buf, 1, 1);
     AgcBlock(s);
   }
@@ -1008,6 +1044,7 @@ int t41o_process_block(t41o_stream *s, const float *iq, float *audio, int update
     }
     arm_cfft_f32(&arm_cfft_sR_f32_len512, s->fft_buf, 0, 1);
     arm_cmplx_mult_cmplx_f32(s->fft_buf, s->mask, s->ifft_buf, kFFT);
+    if (update_display) AudioSpectrum(s, mode);          /* T41/Process.cpp:791-805 */
     arm_cfft_f32(&arm_cfft_sR_f32_len512, s->ifft_buf, 1, 1);
     AgcBlock(s);
     for (int i = 0; i < kDec; i++) L[i] = io[i * 2];
@@ -1040,9 +1077,28 @@ int t41o_process(t41o_stream *s, const float *iq, float *audio, int n_blocks, in
                                 (upd && wf_rows) ? wf_rows + (size_t)rows * kSpecRes : 0,
                                 psk_bits ? psk_bits + b : 0, psk_chars ? psk_chars + b : 0);
     if (rc) return rc;
+    if (upd && s->cap_ypixel) {
+      for (int k = 0; k < T41O_AUDIO_SPEC_PIXELS; k++) s->cap_ypixel[(size_t)rows * T41O_AUDIO_SPEC_PIXELS + k] = s->audio_ypixel[k];
+    }
+    if (upd && s->cap_max_ave) s->cap_max_ave[rows] = s->audio_max_sq_ave;
     rows += upd;
   }
   return rows;
+}
+
+void t41o_capture_audio_spectrum(t41o_stream *s, int32_t *ypixel_rows, float *max_ave_rows) {
+  s->cap_ypixel = ypixel_rows;
+  s->cap_max_ave = max_ave_rows;
+}
+
+/* T41/Display.cpp:959-981 (TCVSDR_SMETER): dbm_calibration = 22.0, slope = 10.0, cons = -92 are floats, attenuator = 0
+   (Display.cpp:146); the RFgain term's 1.5 is a double literal, so the tail of the sum is FP64 */
+float t41o_smeter_dbm(float audio_max_sq_ave, float gain_correction, int32_t rf_gain, int32_t rf_gain_all_bands) {
+  const float dbm_calibration = 22.0, slope = 10.0, cons = -92;
+  const int attenuator = 0;
+  float dbm = dbm_calibration + gain_correction + (float)attenuator + slope * Log10Fast(audio_max_sq_ave) + cons -
+              (float)rf_gain * 1.5 - rf_gain_all_bands;
+  return dbm;
 }
 
 void t41o_calc_fir_coeffs(float *coeffs, int num_coeffs, float fc, float astop, int type, float dfc, float fs) {

@@ -127,6 +127,16 @@ int t41o_process_block(t41o_stream *s, const float *iq, float *audio, int update
 int t41o_process(t41o_stream *s, const float *iq, float *audio, int n_blocks, int row_every,
                  int16_t *spec_rows, uint16_t *wf_rows, int8_t *psk_bits, uint8_t *psk_chars);
 
+/* Audio-spectrum + S-meter by-product of row-producing blocks (T41/Process.cpp:550-570 and, for NFM, :791-805):
+ * audioYPixel[k], k < AUDIO_SPEC_BOX_W - 2 = 270 (T41/Display.h:6,15,20,42,45), and the running average
+ * audioMaxSquaredAve (T41/Process.cpp:32,569).  Where the following t41o_process calls on this receiver put
+ * them, one row per row-producing block (NULL = stop capturing). */
+#define T41O_AUDIO_SPEC_PIXELS 270
+void t41o_capture_audio_spectrum(t41o_stream *s, int32_t *ypixel_rows, float *max_ave_rows);
+/* S-meter reading the display derives from audioMaxSquaredAve (T41/Display.cpp:976-981, TCVSDR_SMETER build,
+ * MyConfigurationFile.h:34): dBm.  Display.cpp is not part of the Tier-A build; this is a restatement only. */
+float t41o_smeter_dbm(float audio_max_sq_ave, float gain_correction, int32_t rf_gain, int32_t rf_gain_all_bands);
+
 /* ---- control-path functions exposed for unit tests ---- */
 void t41o_calc_fir_coeffs(float *coeffs, int num_coeffs, float fc, float astop, int type, float dfc, float fs);
 void t41o_calc_cplx_fir_coeffs(float *ci, float *cq, int num_coeffs, float f_lo, float f_hi, float fs);

@@ -6,7 +6,8 @@ hot-path translation units compiled in place from /root/reference (oracle/Makefi
 and stores, per receiver:
   * sha256 of the full float32 audio output (the exact check),
   * every 61st audio sample (for a readable SNR when a digest mismatches),
-  * all spectrum / waterfall rows, PSK31 bit decisions and characters,
+  * all spectrum / waterfall rows, audio-spectrum rows (audioYPixel) and audioMaxSquaredAve values, PSK31 bit
+    decisions and characters,
   * the debug scalars the reference exposes with external linkage.
 Inputs are not stored: they are regenerated from the seeded generators in
 t41_sdr_b200/synth.py.  Only runnable where /root/reference is mounted (this container):
@@ -48,6 +49,8 @@ def main():
             out[key + "audio_sub"] = r["audio"].ravel()[::STRIDE].copy()
             out[key + "spec"] = r["spec"]
             out[key + "wf"] = r["wf"]
+            out[key + "audio_ypixel"] = r["audio_ypixel"].astype(np.int16)      # 0..~200
+            out[key + "audio_max_sq_ave"] = r["audio_max_sq_ave"]
             if case.psk:
                 out[key + "psk_bits"] = r["psk_bits"]
                 out[key + "psk_chars"] = r["psk_chars"]

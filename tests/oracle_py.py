@@ -21,6 +21,7 @@ TIER_A_PATH = os.path.join(ORACLE_DIR, "_ref", "libt41ref.so")
 
 DEMOD_USB, DEMOD_LSB, DEMOD_AM, DEMOD_NFM, DEMOD_PSK31, DEMOD_SAM = 0, 1, 2, 3, 5, 8
 BLOCK = 2048
+AUDIO_SPEC_PIXELS = 270   # AUDIO_SPEC_BOX_W - 2 (Display.h:45, Process.cpp:555)
 
 
 class Params(C.Structure):
@@ -84,6 +85,10 @@ def tier_b():
         lib.t41o_get_debug.argtypes = [C.c_void_p, C.POINTER(Debug)]
         lib.t41o_process.argtypes = [C.c_void_p] + [C.c_void_p] * 2 + [C.c_int, C.c_int] + [C.c_void_p] * 4
         lib.t41o_default_params.argtypes = [C.POINTER(Params)]
+        lib.t41o_capture_audio_spectrum.argtypes = [C.c_void_p] * 3
+        lib.t41o_capture_audio_spectrum.restype = None
+        lib.t41o_smeter_dbm.restype = C.c_float
+        lib.t41o_smeter_dbm.argtypes = [C.c_float, C.c_float, C.c_int32, C.c_int32]
         lib.t41o_log10f_fast.restype = C.c_float
         lib.t41o_log10f_fast.argtypes = [C.c_float]
         lib.t41o_approx_atan2.restype = C.c_float
@@ -110,7 +115,8 @@ def _ptr(a):
 
 class _StreamBase:
     def process(self, iq, row_every=0, want_psk=False):
-        """iq: float32 [n_blocks, 2048, 2].  Returns dict(audio, spec, wf, psk_bits, psk_chars)."""
+        """iq: float32 [n_blocks, 2048, 2].  Returns dict(audio, spec, wf, psk_bits, psk_chars, audio_ypixel,
+        audio_max_sq_ave)."""
         iq = np.ascontiguousarray(iq, dtype=np.float32)
         n = iq.shape[0]
         assert iq.shape == (n, BLOCK, 2)
@@ -120,12 +126,19 @@ class _StreamBase:
         wf = np.zeros((n_rows, 512), np.uint16)
         bits = np.full(n, -1, np.int8) if want_psk else None
         chars = np.zeros(n, np.uint8) if want_psk else None
-        rc = self._process(_ptr(iq), _ptr(audio), n, row_every, _ptr(spec) if n_rows else None,
-                           _ptr(wf) if n_rows else None, _ptr(bits), _ptr(chars))
+        ypix = np.zeros((n_rows, AUDIO_SPEC_PIXELS), np.int32)
+        mxave = np.zeros(n_rows, np.float32)
+        self._capture(_ptr(ypix) if n_rows else None, _ptr(mxave) if n_rows else None)
+        try:
+            rc = self._process(_ptr(iq), _ptr(audio), n, row_every, _ptr(spec) if n_rows else None,
+                               _ptr(wf) if n_rows else None, _ptr(bits), _ptr(chars))
+        finally:
+            self._capture(None, None)
         if rc < 0:
             raise RuntimeError("oracle process failed rc=%d" % rc)
         assert rc == n_rows
-        return dict(audio=audio, spec=spec, wf=wf, psk_bits=bits, psk_chars=chars)
+        return dict(audio=audio, spec=spec, wf=wf, psk_bits=bits, psk_chars=chars, audio_ypixel=ypix,
+                    audio_max_sq_ave=mxave)
 
 
 class OracleStream(_StreamBase):
@@ -155,6 +168,9 @@ class OracleStream(_StreamBase):
 
     def _process(self, *a):
         return self.lib.t41o_process(self.h, *a)
+
+    def _capture(self, ypix, mx):
+        self.lib.t41o_capture_audio_spectrum(self.h, ypix, mx)
 
     def tables(self):
         t = Tables()
@@ -188,6 +204,8 @@ class RefStream(_StreamBase):
         lib.t41ref_get_tables.argtypes = [C.POINTER(Tables)]
         lib.t41ref_get_debug.argtypes = [C.POINTER(Debug)]
         lib.t41ref_process.argtypes = [C.c_void_p] * 2 + [C.c_int, C.c_int] + [C.c_void_p] * 4
+        lib.t41ref_capture_audio_spectrum.argtypes = [C.c_void_p] * 2
+        lib.t41ref_capture_audio_spectrum.restype = None
         lib.t41ref_log10f_fast.restype = C.c_float
         lib.t41ref_log10f_fast.argtypes = [C.c_float]
         lib.t41ref_approx_atan2.restype = C.c_float
@@ -205,6 +223,9 @@ class RefStream(_StreamBase):
 
     def _process(self, *a):
         return self.lib.t41ref_process(*a)
+
+    def _capture(self, ypix, mx):
+        self.lib.t41ref_capture_audio_spectrum(ypix, mx)
 
     def tables(self):
         t = Tables()
