@@ -178,6 +178,19 @@ int t41rx_process_device(t41rx_ctx *ctx, const float *iq, float *audio, int n_bl
                          uint32_t flags, void *cuda_stream);
 int t41rx_synchronize(t41rx_ctx *ctx);
 
+/* Audio-spectrum + S-meter by-product of the row-producing blocks (Process.cpp:550-570; NFM: 791-805):
+ *   audio_ypixel      int32 [n_streams][n_rows][270]  audioYPixel[k], k < AUDIO_SPEC_BOX_W - 2 (Process.cpp:34,555)
+ *   audio_max_sq_ave  float [n_streams][n_rows]       audioMaxSquaredAve after the block (Process.cpp:32,569)
+ * Binds where the following t41rx_process / _q15 (HOST pointers) or t41rx_process_device (DEVICE pointers) calls
+ * put them, for row_every > 0; either may be NULL; both NULL unbinds (the default: the by-product is not computed).
+ * Receivers in the raw PSK31 mode do not update either (Process.cpp:376-387): their rows repeat the last values.
+ * While bound the context keeps n_streams * n_rows * 4 KiB of scratch for the masked spectra. */
+#define T41RX_AUDIO_SPEC_PIXELS 270
+int t41rx_bind_audio_spectrum(t41rx_ctx *ctx, int32_t *audio_ypixel, float *audio_max_sq_ave);
+/* The S-meter reading DrawSmeterBar() derives from audioMaxSquaredAve (Display.cpp:959-981, TCVSDR_SMETER build):
+ * dBm, given bands[].gainCorrection, bands[].RFgain (t41rx_debug.rf_gain) and rfGainAllBands.  Host arithmetic. */
+float t41rx_smeter_dbm(float audio_max_sq_ave, float gain_correction, int32_t rf_gain, int32_t rf_gain_all_bands);
+
 /* Instrumentation for bench.py: kernels launched by this context so far, and the CUDA-event
  * duration (ms) of all kernels of the most recent t41rx_process[_device] call (valid after t41rx_synchronize). */
 int64_t t41rx_kernel_launches(const t41rx_ctx *ctx);

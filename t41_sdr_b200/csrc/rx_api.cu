@@ -104,6 +104,32 @@ __global__ void __launch_bounds__(kNT, 8 / kG) t41rx_rows_kernel(const LaunchArg
   }
 }
 
+/* audio-spectrum + S-meter by-product of the row-producing blocks (Process.cpp:550-570,791-805) from the masked
+   spectra the chain kernels left in a.aspec; launched after them on the same stream.  The running average
+   makes the rows of one receiver a serial chain; receivers are independent. */
+__global__ void __launch_bounds__(kNT) t41rx_audio_spectrum_kernel(const LaunchArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  Cta c;
+  c.a = a;
+  c.smem = smem;
+  c.s0 = blockIdx.x * kG;
+  c.ng = min(kG, a.n_streams - c.s0);
+  c.row = 1;
+  c.rows_only = 1;
+  const int tid = threadIdx.x;
+  for (int r = 0; r < a.n_rows; ++r) {
+    c.t = r * a.row_every;
+    c.row_idx = r;
+#define T41RX_KPHASE(stmt) \
+  do {                     \
+    stmt;                  \
+    __syncthreads();       \
+  } while (0)
+    T41RX_AUDIO_SPEC_SCHEDULE(T41RX_KPHASE)
+#undef T41RX_KPHASE
+  }
+}
+
 /* arm_q15_to_float (Process.cpp:107-108): x / 32768, exact in float */
 __global__ void t41rx_q15_to_float_kernel(const short4 *src, float4 *dst, size_t n4) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
@@ -197,6 +223,14 @@ struct t41rx_ctx {
   void *d_iq = nullptr, *d_audio = nullptr, *d_spec = nullptr, *d_wf = nullptr, *d_bits = nullptr, *d_chars = nullptr;
   void *d_iq16 = nullptr, *d_audio16 = nullptr;   /* q15 staging of t41rx_process_q15 */
   size_t cap_iq = 0, cap_audio = 0, cap_spec = 0, cap_wf = 0, cap_bits = 0, cap_chars = 0, cap_iq16 = 0, cap_audio16 = 0;
+
+  /* audio-spectrum by-product: where the caller wants it (t41rx_bind_audio_spectrum; host pointers for the
+     host-buffer entry points, device pointers for t41rx_process_device), the masked-spectrum scratch the
+     chain kernels fill on row-producing blocks, and device staging for the host-buffer entry points */
+  int32_t *bind_ypixel = nullptr;
+  float *bind_max_ave = nullptr;
+  void *d_aspec = nullptr, *d_ypixel = nullptr, *d_max_ave = nullptr;
+  size_t cap_aspec = 0, cap_ypixel = 0, cap_max_ave = 0;
 };
 
 static int EnsureFsetCapacity(t41rx_ctx *ctx, int need) {
@@ -278,7 +312,7 @@ void t41rx_destroy(t41rx_ctx *ctx) {
   void *bufs[] = {ctx->d_cfg, ctx->d_state, ctx->d_fsets, ctx->d_nco_tab, ctx->d_twiddle, ctx->d_hann, ctx->d_sin,
                   ctx->d_zoom_iir, ctx->d_sam, ctx->d_gradient, ctx->d_varicode, ctx->d_iq, ctx->d_audio,
                   ctx->d_spec, ctx->d_wf, ctx->d_bits, ctx->d_chars, ctx->d_fast_ids, ctx->d_phased_ids,
-                  ctx->d_iq16, ctx->d_audio16};
+                  ctx->d_iq16, ctx->d_audio16, ctx->d_aspec, ctx->d_ypixel, ctx->d_max_ave};
   for (void *b : bufs)
     if (b) cudaFree(b);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -328,6 +362,8 @@ int t41rx_create(t41rx_ctx **out, int n_streams, int device) {
   if (cudaFuncSetAttribute(t41rx_fused_rx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)(kSmemFloats * sizeof(float))) != cudaSuccess ||
       cudaFuncSetAttribute(t41rx_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)(kSmemFloats * sizeof(float))) != cudaSuccess ||
+      cudaFuncSetAttribute(t41rx_audio_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)(kSmemFloats * sizeof(float))) != cudaSuccess)
     return bail(Fail(T41RX_ECUDA, "t41rx_create: kernel image for this GPU missing (built for sm_100a)%s"));
   if (ConfigureStreamKernel() != cudaSuccess ||
@@ -485,7 +521,8 @@ int t41rx_get_debug(t41rx_ctx *ctx, int stream, t41rx_debug *d) {
 /* enqueue the kernels for receivers [first, first + count) of the bank on stream st */
 static int LaunchRange(t41rx_ctx *ctx, const float *iq, float *audio, int n_blocks, int row_every,
                        int16_t *spec_rows, uint16_t *wf_rows, int8_t *psk_bits, uint8_t *psk_chars,
-                       uint32_t flags, cudaStream_t st, int first, int count) {
+                       uint32_t flags, cudaStream_t st, int first, int count, int32_t *d_ypixel = nullptr,
+                       float *d_max_ave = nullptr) {
   LaunchArgs a;
   memset(&a, 0, sizeof(a));
   a.iq = iq;
@@ -511,6 +548,19 @@ static int LaunchRange(t41rx_ctx *ctx, const float *iq, float *audio, int n_bloc
   a.row_every = row_every;
   a.n_rows = row_every > 0 ? (n_blocks + row_every - 1) / row_every : 0;
   a.flags = flags;
+  if (a.n_rows > 0 && (d_ypixel || d_max_ave)) {
+    a.aspec = (float2 *)ctx->d_aspec;         /* sized by the caller (EnsureAudioSpecScratch) */
+    a.audio_ypixel = d_ypixel;
+    a.audio_max_ave = d_max_ave;
+  }
+  /* the by-product kernel runs after the chain kernels of the range, on the whole (contiguous) range */
+  auto audio_spectrum = [&]() -> int {
+    if (!a.aspec) return T41RX_OK;
+    t41rx_audio_spectrum_kernel<<<(count + kG - 1) / kG, kNT, kSmemFloats * sizeof(float), st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    ctx->launches += 1;
+    return T41RX_OK;
+  };
   /* kernel choice: the throughput kernel unless the caller asks for the bit-exact oscillator or the
      phase-structured kernel; SAM receivers always take the phase-structured kernel (see t41rx_ctx) */
   const bool all_phased = (flags & (T41RX_FLAG_EXACT_NCO | T41RX_FLAG_PHASED_KERNEL)) != 0;
@@ -518,7 +568,7 @@ static int LaunchRange(t41rx_ctx *ctx, const float *iq, float *audio, int n_bloc
     t41rx_fused_rx_kernel<<<(count + kG - 1) / kG, kNT, kSmemFloats * sizeof(float), st>>>(a);
     CUDA_TRY(cudaGetLastError());
     ctx->launches += 1;
-    return T41RX_OK;
+    return audio_spectrum();
   }
   /* the slices of the (sorted) per-kernel receiver lists that fall into the range */
   auto slice = [&](const std::vector<int32_t> &ids, int *off, int *len) {
@@ -553,7 +603,13 @@ static int LaunchRange(t41rx_ctx *ctx, const float *iq, float *audio, int n_bloc
     ctx->kev_count += 1;
     ctx->launches += 1;
   }
-  return T41RX_OK;
+  return audio_spectrum();
+}
+
+/* scratch for the masked spectra of the row-producing blocks: [n_streams][n_rows][512] float2 */
+static int EnsureAudioSpecScratch(t41rx_ctx *ctx, size_t n_rows) {
+  if (!(ctx->bind_ypixel || ctx->bind_max_ave) || n_rows == 0) return T41RX_OK;
+  return Grow(&ctx->d_aspec, &ctx->cap_aspec, (size_t)ctx->n_streams * n_rows * kFft * sizeof(float2));
 }
 
 /* (re)build the per-kernel receiver lists after a parameter change */
@@ -581,12 +637,45 @@ int t41rx_process_device(t41rx_ctx *ctx, const float *iq, float *audio, int n_bl
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
   int rc = RefreshKernelLists(ctx);
   if (rc) return rc;
+  if ((rc = EnsureAudioSpecScratch(ctx, row_every > 0 ? (size_t)(n_blocks + row_every - 1) / row_every : 0))) return rc;
   CUDA_TRY(cudaEventRecord(ctx->ev0, st));
-  rc = LaunchRange(ctx, iq, audio, n_blocks, row_every, spec_rows, wf_rows, psk_bits, psk_chars, flags, st, 0, ctx->n_streams);
+  rc = LaunchRange(ctx, iq, audio, n_blocks, row_every, spec_rows, wf_rows, psk_bits, psk_chars, flags, st, 0, ctx->n_streams,
+                   ctx->bind_ypixel, ctx->bind_max_ave);
   if (rc) return rc;
   CUDA_TRY(cudaEventRecord(ctx->ev1, st));
   ctx->ev_valid = true;
   return T41RX_OK;
+}
+
+/* log10f_fast (Utility.cpp:245-258) on the host, for the S-meter helper */
+static float HostLog10Fast(float x) {
+  int e;
+  const float f = frexpf(fabsf(x), &e);
+  volatile float y = 1.23149591368684f;     /* volatile: one rounding per operation whatever the host flags */
+  y = y * f;
+  y = y + -4.11852516267426f;
+  y = y * f;
+  y = y + 6.02197014179219f;
+  y = y * f;
+  y = y + -3.13396450166353f;
+  y = y + (float)e;
+  return y * 0.3010299956639812f;
+}
+
+int t41rx_bind_audio_spectrum(t41rx_ctx *ctx, int32_t *audio_ypixel, float *audio_max_sq_ave) {
+  if (!ctx) return Fail(T41RX_EINVAL, "t41rx_bind_audio_spectrum: null context%s");
+  ctx->bind_ypixel = audio_ypixel;
+  ctx->bind_max_ave = audio_max_sq_ave;
+  return T41RX_OK;
+}
+
+/* Display.cpp:959-981 (TCVSDR_SMETER build): float sum up to the constant, then the FP64 tail the double literal
+   1.5 forces; log10f_fast is Utility.cpp:245-258 */
+float t41rx_smeter_dbm(float audio_max_sq_ave, float gain_correction, int32_t rf_gain, int32_t rf_gain_all_bands) {
+  const float dbm_calibration = 22.0f, slope = 10.0f, cons = -92.0f;
+  const int attenuator = 0;                 /* Display.cpp:146 */
+  const float head = dbm_calibration + gain_correction + (float)attenuator + slope * HostLog10Fast(audio_max_sq_ave) + cons;
+  return (float)((double)head - (double)(float)rf_gain * 1.5 - (double)rf_gain_all_bands);
 }
 
 int t41rx_synchronize(t41rx_ctx *ctx) {
@@ -603,7 +692,8 @@ static int ProcessHost(t41rx_ctx *ctx, const float *iq, float *audio, const int1
   const bool q15 = iq16 != nullptr;
   if (!ctx || (!q15 && (!iq || !audio)) || (q15 && !audio16) || n_blocks <= 0 || row_every < 0)
     return Fail(T41RX_EINVAL, "t41rx_process: bad arguments%s");
-  if (row_every > 0 && !spec_rows && !wf_rows) row_every = 0;
+  const bool want_aspec = ctx && (ctx->bind_ypixel || ctx->bind_max_ave);
+  if (row_every > 0 && !spec_rows && !wf_rows && !want_aspec) row_every = 0;
   CUDA_TRY(cudaSetDevice(ctx->device));
   const size_t S = (size_t)ctx->n_streams, T = (size_t)n_blocks;
   const size_t n_rows = row_every > 0 ? (T + row_every - 1) / row_every : 0;
@@ -619,6 +709,12 @@ static int ProcessHost(t41rx_ctx *ctx, const float *iq, float *audio, const int1
   if (psk_chars && (rc = Grow(&ctx->d_chars, &ctx->cap_chars, b_psk))) return rc;
   if (q15 && (rc = Grow(&ctx->d_iq16, &ctx->cap_iq16, b_iq / 2))) return rc;
   if (q15 && (rc = Grow(&ctx->d_audio16, &ctx->cap_audio16, b_audio / 2))) return rc;
+  const size_t b_ypix = S * n_rows * kAudioSpecPixels * sizeof(int32_t), b_max = S * n_rows * sizeof(float);
+  if (n_rows && ctx->bind_ypixel && (rc = Grow(&ctx->d_ypixel, &ctx->cap_ypixel, b_ypix))) return rc;
+  if (n_rows && ctx->bind_max_ave && (rc = Grow(&ctx->d_max_ave, &ctx->cap_max_ave, b_max))) return rc;
+  if ((rc = EnsureAudioSpecScratch(ctx, n_rows))) return rc;
+  int32_t *d_ypix = (n_rows && ctx->bind_ypixel) ? (int32_t *)ctx->d_ypixel : nullptr;
+  float *d_maxave = (n_rows && ctx->bind_max_ave) ? (float *)ctx->d_max_ave : nullptr;
   if ((rc = RefreshKernelLists(ctx))) return rc;
   /* receivers are independent: cut the bank into chunks and overlap the copy-in of chunk i+1, the kernels
      of chunk i and the copy-out of chunk i-1 on three streams (full-duplex host link) */
@@ -644,7 +740,7 @@ static int ProcessHost(t41rx_ctx *ctx, const float *iq, float *audio, const int1
       ctx->launches += 1;
     }
     rc = LaunchRange(ctx, (const float *)ctx->d_iq, (float *)ctx->d_audio, n_blocks, row_every, d_spec, d_wf, d_bits, d_chars,
-                     flags, ctx->stream, (int)s0, (int)n);
+                     flags, ctx->stream, (int)s0, (int)n, d_ypix, d_maxave);
     if (rc) return rc;
     if (q15) {
       t41rx_float_to_q15_kernel<<<2 * ctx->n_sms, 256, 0, ctx->stream>>>(
@@ -660,6 +756,8 @@ static int ProcessHost(t41rx_ctx *ctx, const float *iq, float *audio, const int1
       CUDA_TRY(cudaMemcpyAsync(audio + s0 * per_audio, (float *)ctx->d_audio + s0 * per_audio, n * per_audio * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_out));
     if (d_spec) CUDA_TRY(cudaMemcpyAsync(spec_rows + s0 * per_row, d_spec + s0 * per_row, n * per_row * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->copy_out));
     if (d_wf) CUDA_TRY(cudaMemcpyAsync(wf_rows + s0 * per_row, d_wf + s0 * per_row, n * per_row * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->copy_out));
+    if (d_ypix) CUDA_TRY(cudaMemcpyAsync(ctx->bind_ypixel + s0 * n_rows * kAudioSpecPixels, d_ypix + s0 * n_rows * kAudioSpecPixels, n * n_rows * kAudioSpecPixels * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->copy_out));
+    if (d_maxave) CUDA_TRY(cudaMemcpyAsync(ctx->bind_max_ave + s0 * n_rows, d_maxave + s0 * n_rows, n * n_rows * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_out));
     if (d_bits) CUDA_TRY(cudaMemcpyAsync(psk_bits + s0 * T, d_bits + s0 * T, n * T, cudaMemcpyDeviceToHost, ctx->copy_out));
     if (d_chars) CUDA_TRY(cudaMemcpyAsync(psk_chars + s0 * T, d_chars + s0 * T, n * T, cudaMemcpyDeviceToHost, ctx->copy_out));
   }

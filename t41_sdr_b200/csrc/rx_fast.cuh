@@ -254,7 +254,8 @@ __device__ __forceinline__ void InvPass(float2 *buf, F2 tw1, int b) {
 
 /* forward pass 2 (8 contiguous elements, no twiddles), multiply by the filter mask (bins sit in
  * octal-digit-reversed positions), inverse pass 2: all in registers */
-__device__ __forceinline__ void MidPass(float2 *buf, const float2 (&hm)[8], int b) {
+/* arow: where a row-producing block leaves the masked spectrum for the audio-spectrum by-product, or NULL */
+__device__ __forceinline__ void MidPass(float2 *buf, const float2 (&hm)[8], int b, float2 *arow) {
   float r[8], im[8];
 #pragma unroll
   for (int m = 0; m < 8; ++m) {
@@ -269,6 +270,10 @@ __device__ __forceinline__ void MidPass(float2 *buf, const float2 (&hm)[8], int 
     const float xr = r[k], xi = im[k];
     r[k] = xr * h.x - xi * h.y;
     im[k] = xr * h.y + xi * h.x;
+  }
+  if (arow) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) arow[OctRev3((unsigned)(8 * b + k))] = float2{r[k], im[k]};
   }
   Dft8(im, r);
 #pragma unroll
@@ -891,7 +896,7 @@ struct RxPair {
       s[oDH + k] = s[oD1 + (k / 24) * kD1Plane + 24 + 232 + (k % 24)];   /* words 256..279: D1W is the identity */
     }
     T41RX_LAP(tm, 5);
-    AfterDec2(dq, buf);
+    AfterDec2(dq, buf, t);
     /* Codec_gain (Process.cpp:979-1016 with the clip flags never set) */
     if (tau == 0) {                   /* the gain was read at the top of this block, behind many barriers */
       int *rg = reinterpret_cast<int *>(s) + oXtra + xRfGain;
@@ -908,7 +913,7 @@ struct RxPair {
 
   /* level adjust + overlap-save + fast convolution + |z| + window maximum -> staging.
      dq: this warp's channel (w2) of the 8 decimated samples 8 lane .. 8 lane + 7 */
-  __device__ void AfterDec2(float (&dq)[8], int buf) {
+  __device__ void AfterDec2(float (&dq)[8], int buf, int t) {
     Launder();
     float *fbw = s + oMix;                                   /* FFT buffer as words */
     float2 *fb = reinterpret_cast<float2 *>(s + oMix);
@@ -949,7 +954,10 @@ struct RxPair {
     PairSync();
     FwdPass<1>(fb, r.tw_b, tau);
     PairSync();
-    MidPass(fb, hm, tau);
+    float2 *arow = nullptr;
+    if (a.aspec && a.row_every > 0 && (t % a.row_every) == 0)
+      arow = a.aspec + ((size_t)sid * a.n_rows + t / a.row_every) * kFft;
+    MidPass(fb, hm, tau, arow);
     PairSync();
     InvPass<1, false>(fb, r.tw_b, tau);
     PairSync();

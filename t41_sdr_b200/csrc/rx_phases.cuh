@@ -119,6 +119,10 @@ struct LaunchArgs {
   uint32_t flags;
   const int32_t *stream_ids;  /* receiver index of each of them, or NULL for stream_base .. stream_base + n_streams-1 */
   int stream_base;
+  /* audio-spectrum + S-meter by-product of the row-producing blocks (all NULL when not bound) */
+  float2 *aspec;              /* scratch [receiver][n_rows][512]: the masked spectrum (iFFT_buffer before the inverse FFT) */
+  int32_t *audio_ypixel;      /* [receiver][n_rows][270] */
+  float *audio_max_ave;       /* [receiver][n_rows] */
 };
 
 struct Cta {
@@ -1093,6 +1097,10 @@ T41RX_DEV void PhMask(Cta &c, int tid) {
   const float2 *fa = reinterpret_cast<const float2 *>(s + vFftA);
   float2 *fb = reinterpret_cast<float2 *>(s + vFftB);
   const float2 *mask = reinterpret_cast<const float2 *>(c.a.fsets[cf.filter_id].mask);
+  /* (the display rows of this block may come from the rows-only kernel: c.row is not the test here) */
+  float2 *arow = nullptr;
+  if (c.a.aspec && c.a.row_every > 0 && (c.t % c.a.row_every) == 0)
+    arow = c.a.aspec + ((size_t)Sid(c, g) * c.a.n_rows + c.t / c.a.row_every) * kFft;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int k = u + 64 * j;
@@ -1100,6 +1108,8 @@ T41RX_DEV void PhMask(Cta &c, int tid) {
     const float2 h = LdgRO(mask + k);
     const float rr = x.x * h.x, ii = x.y * h.y, ri = x.x * h.y, ir = x.y * h.x;
     fb[k] = float2{rr - ii, -(ri + ir)};
+    /* row-producing block: keep the masked spectrum for the audio-spectrum by-product (Process.cpp:550-553) */
+    if (arow) arow[k] = float2{rr - ii, ri + ir};
   }
 }
 
@@ -1828,6 +1838,82 @@ T41RX_DEV void PhZoomDecimateEnd(Cta &c, int tid) {
   RX_PHASE(PhSpecFftPass(c, tid, 2));                                    \
   RX_PHASE(PhSpecRow(c, tid));
 #endif
+
+/* ------------------------------------------------------------------ */
+/* audio-spectrum + S-meter by-product (Process.cpp:550-570, NFM :791-805) */
+/* ------------------------------------------------------------------ */
+/* One row of one receiver per 64 threads, from the masked spectrum the chain kernels left in a.aspec:
+ *   audioSpectBuffer[1023 - k] = iFFT_buffer[k]^2 (each float of the 512 complex bins on its own);
+ *   audioYPixel[k] = offset + map(15 log10f(3-point average), 0, 100, 0, 120), offset 50 (20 for NFM), read from
+ *   the top of the reversed array except for LSB; clamped at 0; k < 270;
+ *   audioMaxSquaredAve = .5 max + .5 audioMaxSquaredAve (FP64 sum).
+ * Arduino map() with a float argument computes in float (Teensyduino core, wiring.h).  Modes without the
+ * filter (PSK31 raw mode) leave both untouched: their rows repeat the state.
+ * Shared memory of slot g: words 0..1023 the reversed squares, 1024..1087 partial maxima. */
+T41RX_DEV bool AudioSpecUpdates(int mode) { return UsesFilter(mode); }
+
+T41RX_DEV void PhAudioSquares(Cta &c, int tid) {
+  const int g = tid >> 6, u = tid & 63;
+  if (g >= c.ng) return;
+  const int sid = Sid(c, g);
+  if (!AudioSpecUpdates(c.a.cfg[sid].mode)) return;
+  float *s = Slot(c, g);
+  const float *src = reinterpret_cast<const float *>(c.a.aspec + ((size_t)sid * c.a.n_rows + c.row_idx) * kFft);
+  float m = 0.0f;
+  for (int j = 0; j < 16; ++j) {
+    const int k = u + 64 * j;
+    const float v = src[k];
+    const float q = v * v;
+    s[2 * kFft - 1 - k] = q;
+    m = (q > m) ? q : m;                    /* squares are >= 0: arm_max_f32's result */
+  }
+  s[2 * kFft + u] = m;
+}
+
+T41RX_DEV void PhAudioPixels(Cta &c, int tid) {
+  const int g = tid >> 6, u = tid & 63;
+  if (g >= c.ng) return;
+  const int sid = Sid(c, g);
+  const int mode = c.a.cfg[sid].mode;
+  StreamState &st = c.a.st[sid];
+  const float *sq = Slot(c, g);
+  int32_t *out = c.a.audio_ypixel ? c.a.audio_ypixel + ((size_t)sid * c.a.n_rows + c.row_idx) * kAudioSpecPixels : nullptr;
+  const bool upd = AudioSpecUpdates(mode);
+  const float offset = (mode == kModeNfm) ? 20.0f : 50.0f;
+  for (int k = u; k < kAudioSpecPixels; k += 64) {
+    int pix;
+    if (upd) {
+      float sum;
+      if (mode == kModeLsb) sum = (sq[k] + sq[k + 1]) + sq[k + 2];
+      else sum = (sq[1021 - k] + sq[1022 - k]) + sq[1023 - k];
+      const float x = 15.0f * log10f(sum / 3.0f);
+      const float v = offset + ((x - 0.0f) * (120.0f - 0.0f) / (100.0f - 0.0f) + 0.0f);
+      pix = (v >= 0.0f) ? (int)v : 0;       /* -inf / NaN (empty spectrum) end up 0 like on the targets */
+      st.audio_ypixel[k] = (int16_t)pix;
+    } else {
+      pix = st.audio_ypixel[k];
+    }
+    if (out) out[k] = pix;
+  }
+  if (u == 0) {
+    float ave = st.audio_max_sq_ave;
+    if (upd) {
+      const float *pm = sq + 2 * kFft;
+      float mx = pm[0];
+      for (int i = 1; i < 64; ++i) mx = (pm[i] > mx) ? pm[i] : mx;
+      /* arm_max_f32 starts from element 0 and replaces it only by larger values: a NaN there (NFM discriminator
+         on exact silence) is the result, NaNs elsewhere are skipped like above */
+      if (sq[0] != sq[0]) mx = sq[0];
+      ave = (float)(.5 * (double)mx + .5 * (double)ave);
+      st.audio_max_sq_ave = ave;
+    }
+    if (c.a.audio_max_ave) c.a.audio_max_ave[(size_t)sid * c.a.n_rows + c.row_idx] = ave;
+  }
+}
+
+#define T41RX_AUDIO_SPEC_SCHEDULE(RX_PHASE) \
+  RX_PHASE(PhAudioSquares(c, tid));         \
+  RX_PHASE(PhAudioPixels(c, tid));
 
 #define T41RX_ROWS_SCHEDULE(RX_PHASE)                                    \
   RX_PHASE(PhLoad(c, tid); PhRowDcSeed(c, tid));                         \

@@ -22,6 +22,7 @@ constexpr int kMaskTaps = 257;    /* m_NumTaps, Filter.cpp:18 */
 constexpr int kAgcDelay = 97;     /* attack_buffsize, DSP_Fn.cpp:409 (B11) */
 constexpr int kAgcRing = 128;     /* power-of-two ring >= kAgcDelay + 1 (firmware: 1921, functionally a 97-sample delay) */
 constexpr int kSpecRes = 512;
+constexpr int kAudioSpecPixels = 270;   /* AUDIO_SPEC_BOX_W - 2 = 800 - (0 + 1 + 512 + 15) - 2 (Display.h:6,15,20,42,45; Process.cpp:555) */
 
 /* demodulation modes (SDT.h:57-68), same values as T41RX_DEMOD_* */
 constexpr int kModeUsb = 0, kModeLsb = 1, kModeAm = 2, kModeNfm = 3, kModePsk31 = 5, kModeSam = 8;
@@ -126,6 +127,10 @@ struct StreamState {
   int32_t fast_native;
   float fast_dc_w;
   double fast_ph_re, fast_ph_im;
+  /* audio-spectrum + S-meter by-product (Process.cpp:32,34): audioMaxSquaredAve and audioYPixel[0..269] */
+  float audio_max_sq_ave;
+  int32_t pad2_;
+  int16_t audio_ypixel[kAudioSpecPixels + 2];
 };
 
 }  // namespace t41rx

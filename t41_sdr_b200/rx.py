@@ -18,6 +18,7 @@ LIB_PATH = os.environ.get("T41RX_LIB", os.path.join(_HERE, "libt41rx.so"))
 DEMOD_USB, DEMOD_LSB, DEMOD_AM, DEMOD_NFM, DEMOD_PSK31, DEMOD_SAM = 0, 1, 2, 3, 5, 8
 BLOCK = 2048
 SPECTRUM_RES = 512
+AUDIO_SPEC_PIXELS = 270   # AUDIO_SPEC_BOX_W - 2 (Display.h:45, Process.cpp:555)
 FLAG_EXACT_NCO = 1       # bit-exact kernel, step-by-step FP64 oscillator
 FLAG_PHASED_KERNEL = 2   # bit-exact kernel with the closed-form FP64 oscillator
 FLAG_SCAN_ROWS = 4       # rows kernel: scan form of the ZoomFFT biquads (<= 1 LSB, < 1 % of pixels)
@@ -73,7 +74,7 @@ EXPORTS = (
     "t41rx_num_streams", "t41rx_set_params", "t41rx_set_params_each", "t41rx_get_params",
     "t41rx_get_tables", "t41rx_get_debug", "t41rx_design_tables", "t41rx_process", "t41rx_process_q15",
     "t41rx_process_device", "t41rx_synchronize", "t41rx_kernel_launches", "t41rx_last_kernel_ms",
-    "t41rx_stream_kernel_times",
+    "t41rx_stream_kernel_times", "t41rx_bind_audio_spectrum", "t41rx_smeter_dbm",
     "t41rx_last_error", "t41rx_version")
 
 
@@ -111,6 +112,9 @@ def lib():
         L.t41rx_kernel_launches.restype = C.c_int64
         L.t41rx_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.t41rx_stream_kernel_times.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
+        L.t41rx_bind_audio_spectrum.argtypes = [vp, vp, vp]
+        L.t41rx_smeter_dbm.argtypes = [C.c_float, C.c_float, C.c_int32, C.c_int32]
+        L.t41rx_smeter_dbm.restype = C.c_float
         L.t41rx_last_error.restype = C.c_char_p
         L.t41rx_version.restype = C.c_char_p
         _lib = L
@@ -144,6 +148,11 @@ def design_tables(param_sequence):
     t = Tables()
     _check(lib().t41rx_design_tables(arr, len(param_sequence), C.byref(t)), "t41rx_design_tables")
     return t.as_dict()
+
+
+def smeter_dbm(audio_max_sq_ave, gain_correction=0.0, rf_gain=1, rf_gain_all_bands=1):
+    """DrawSmeterBar()'s dBm reading from audioMaxSquaredAve (Display.cpp:959-981)."""
+    return float(lib().t41rx_smeter_dbm(audio_max_sq_ave, gain_correction, rf_gain, rf_gain_all_bands))
 
 
 def _np_ptr(a):
@@ -201,7 +210,20 @@ class Receiver:
         return d
 
     # ---- ProcessIQData over host buffers ----
-    def process(self, iq, row_every=0, want_psk=False, flags=0, out=None):
+    def bind_audio_spectrum(self, ypixel_ptr, max_ave_ptr):
+        """Raw pointers (host for process/process_q15, device for process_device) of the audio-spectrum by-product
+        outputs: int32 [n_streams, n_rows, 270] and float32 [n_streams, n_rows]; None, None unbinds."""
+        _check(lib().t41rx_bind_audio_spectrum(self._h, ypixel_ptr, max_ave_ptr), "t41rx_bind_audio_spectrum")
+
+    def _audio_spec_arrays(self, out, n_rows, want):
+        if not want or n_rows == 0:
+            return False
+        out.setdefault("audio_ypixel", np.zeros((self.n_streams, n_rows, AUDIO_SPEC_PIXELS), np.int32))
+        out.setdefault("audio_max_sq_ave", np.zeros((self.n_streams, n_rows), np.float32))
+        self.bind_audio_spectrum(_np_ptr(out["audio_ypixel"]), _np_ptr(out["audio_max_sq_ave"]))
+        return True
+
+    def process(self, iq, row_every=0, want_psk=False, flags=0, out=None, want_audio_spec=False):
         """iq: float32 [n_streams, n_blocks, 2048, 2] (host).  Returns dict of host arrays."""
         iq = np.ascontiguousarray(iq, dtype=np.float32)
         S, T = self.n_streams, iq.shape[1]
@@ -214,14 +236,19 @@ class Receiver:
                        wf=np.zeros((S, n_rows, SPECTRUM_RES), np.uint16),
                        psk_bits=np.full((S, T), -1, np.int8) if want_psk else None,
                        psk_chars=np.zeros((S, T), np.uint8) if want_psk else None)
-        _check(lib().t41rx_process(self._h, _np_ptr(iq), _np_ptr(out["audio"]), T, row_every,
-                                   _np_ptr(out["spec"]) if n_rows else None,
-                                   _np_ptr(out["wf"]) if n_rows else None,
-                                   _np_ptr(out.get("psk_bits")), _np_ptr(out.get("psk_chars")), flags),
-               "t41rx_process")
+        bound = self._audio_spec_arrays(out, n_rows, want_audio_spec)
+        try:
+            _check(lib().t41rx_process(self._h, _np_ptr(iq), _np_ptr(out["audio"]), T, row_every,
+                                       _np_ptr(out["spec"]) if n_rows else None,
+                                       _np_ptr(out["wf"]) if n_rows else None,
+                                       _np_ptr(out.get("psk_bits")), _np_ptr(out.get("psk_chars")), flags),
+                   "t41rx_process")
+        finally:
+            if bound:
+                self.bind_audio_spectrum(None, None)
         return out
 
-    def process_q15(self, iq_q15, row_every=0, want_psk=False, flags=0, out=None):
+    def process_q15(self, iq_q15, row_every=0, want_psk=False, flags=0, out=None, want_audio_spec=False):
         """The firmware's own block format: iq_q15 int16 [n_streams, n_blocks, 2048, 2] (host) in, audio int16
         [n_streams, n_blocks, 2048] out (arm_q15_to_float / arm_float_to_q15 run on the device)."""
         iq_q15 = np.ascontiguousarray(iq_q15, dtype=np.int16)
@@ -235,11 +262,16 @@ class Receiver:
                        wf=np.zeros((S, n_rows, SPECTRUM_RES), np.uint16),
                        psk_bits=np.full((S, T), -1, np.int8) if want_psk else None,
                        psk_chars=np.zeros((S, T), np.uint8) if want_psk else None)
-        _check(lib().t41rx_process_q15(self._h, _np_ptr(iq_q15), _np_ptr(out["audio"]), T, row_every,
-                                       _np_ptr(out["spec"]) if n_rows else None,
-                                       _np_ptr(out["wf"]) if n_rows else None,
-                                       _np_ptr(out.get("psk_bits")), _np_ptr(out.get("psk_chars")), flags),
-               "t41rx_process_q15")
+        bound = self._audio_spec_arrays(out, n_rows, want_audio_spec)
+        try:
+            _check(lib().t41rx_process_q15(self._h, _np_ptr(iq_q15), _np_ptr(out["audio"]), T, row_every,
+                                           _np_ptr(out["spec"]) if n_rows else None,
+                                           _np_ptr(out["wf"]) if n_rows else None,
+                                           _np_ptr(out.get("psk_bits")), _np_ptr(out.get("psk_chars")), flags),
+                   "t41rx_process_q15")
+        finally:
+            if bound:
+                self.bind_audio_spectrum(None, None)
         return out
 
     # ---- ProcessIQData over device buffers (raw pointers, e.g. torch.Tensor.data_ptr()) ----

@@ -25,6 +25,10 @@ struct Emul {
   HostModel host;
   std::vector<StreamState> state;
   std::vector<float> smem;
+  /* audio-spectrum by-product: where emul_process puts it (emul_bind_audio_spectrum) and the scratch */
+  int32_t *bind_ypixel = nullptr;
+  float *bind_max_ave = nullptr;
+  std::vector<float2> aspec;
 };
 
 extern "C" {
@@ -81,6 +85,12 @@ int emul_process(Emul *e, const float *iq, float *audio, int n_blocks, int row_e
   a.row_every = row_every;
   a.n_rows = row_every > 0 ? (n_blocks + row_every - 1) / row_every : 0;
   a.flags = flags;
+  if (a.n_rows > 0 && (e->bind_ypixel || e->bind_max_ave)) {
+    e->aspec.assign((size_t)h.n_streams * a.n_rows * kFft, float2{NAN, NAN});
+    a.aspec = e->aspec.data();
+    a.audio_ypixel = e->bind_ypixel;
+    a.audio_max_ave = e->bind_max_ave;
+  }
 
   /* 16-byte aligned shared-memory stand-in */
   float *smem = e->smem.data();
@@ -125,9 +135,25 @@ int emul_process(Emul *e, const float *iq, float *audio, int n_blocks, int row_e
       T41RX_BLOCK_SCHEDULE(EMUL_PHASE)
     }
     EMUL_PHASE(PhStateOut(c, tid));
+    if (a.aspec) {
+      /* t41rx_audio_spectrum_kernel */
+      c.row = 1;
+      c.rows_only = 1;
+      for (int i = 0; i < kSmemFloats; ++i) smem[i] = NAN;
+      for (int r = 0; r < a.n_rows; ++r) {
+        c.t = r * row_every;
+        c.row_idx = r;
+        T41RX_AUDIO_SPEC_SCHEDULE(EMUL_PHASE)
+      }
+    }
 #undef EMUL_PHASE
   }
   return 0;
+}
+
+void emul_bind_audio_spectrum(Emul *e, int32_t *audio_ypixel, float *audio_max_sq_ave) {
+  e->bind_ypixel = audio_ypixel;
+  e->bind_max_ave = audio_max_sq_ave;
 }
 
 int emul_get_debug(Emul *e, int stream, t41rx_debug *d) {

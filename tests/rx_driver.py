@@ -34,6 +34,8 @@ class EmulReceiver:
         L.emul_set_params_each.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(rx.Params)]
         L.emul_process.argtypes = [C.c_void_p] + [C.c_void_p] * 2 + [C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_uint32]
         L.emul_get_debug.argtypes = [C.c_void_p, C.c_int, C.POINTER(rx.Debug)]
+        L.emul_bind_audio_spectrum.argtypes = [C.c_void_p] * 3
+        L.emul_bind_audio_spectrum.restype = None
         self.L = L
         self.n_streams = n_streams
         self.h = L.emul_create(n_streams)
@@ -47,7 +49,7 @@ class EmulReceiver:
         arr = (rx.Params * len(plist))(*plist)
         assert self.L.emul_set_params_each(self.h, first, len(plist), arr) == 0
 
-    def process(self, iq, row_every=0, want_psk=False, flags=0):
+    def process(self, iq, row_every=0, want_psk=False, flags=0, want_audio_spec=False):
         iq = np.ascontiguousarray(iq, np.float32)
         S, T = iq.shape[:2]
         n_rows = 0 if row_every <= 0 else (T + row_every - 1) // row_every
@@ -56,8 +58,13 @@ class EmulReceiver:
                    psk_bits=np.full((S, T), -1, np.int8) if want_psk else None,
                    psk_chars=np.zeros((S, T), np.uint8) if want_psk else None)
         p = lambda a: None if a is None or a.size == 0 else a.ctypes.data
+        if want_audio_spec and n_rows:
+            out["audio_ypixel"] = np.zeros((S, n_rows, rx.AUDIO_SPEC_PIXELS), np.int32)
+            out["audio_max_sq_ave"] = np.zeros((S, n_rows), np.float32)
+            self.L.emul_bind_audio_spectrum(self.h, p(out["audio_ypixel"]), p(out["audio_max_sq_ave"]))
         self.L.emul_process(self.h, iq.ctypes.data, out["audio"].ctypes.data, T, row_every, p(out["spec"]),
                             p(out["wf"]), p(out["psk_bits"]), p(out["psk_chars"]), flags)
+        self.L.emul_bind_audio_spectrum(self.h, None, None)
         return out
 
     def debug(self, stream):
@@ -66,7 +73,7 @@ class EmulReceiver:
         return d
 
 
-def run_case_batched(case, engine, flags=0):
+def run_case_batched(case, engine, flags=0, audio_spec=True):
     """Returns per-receiver dicts shaped like cases.run_case_on()."""
     S = case.n_streams
     iq_all = np.stack(case.iq)            # [S, T, 2048, 2]
@@ -74,7 +81,8 @@ def run_case_batched(case, engine, flags=0):
     b0 = 0
     for plist, n in case.segments:
         engine.set_params_each([to_rx_params(p) for p in plist])
-        parts.append(engine.process(iq_all[:, b0:b0 + n], case.row_every, case.psk, flags))
+        parts.append(engine.process(iq_all[:, b0:b0 + n], case.row_every, case.psk, flags,
+                                    want_audio_spec=audio_spec and case.row_every > 0))
         b0 += n
     out = []
     for s in range(S):
@@ -84,9 +92,29 @@ def run_case_batched(case, engine, flags=0):
         if case.psk:
             r["psk_bits"] = np.concatenate([p["psk_bits"][s] for p in parts])
             r["psk_chars"] = np.concatenate([p["psk_chars"][s] for p in parts])
+        if "audio_ypixel" in parts[0]:
+            r["audio_ypixel"] = np.concatenate([p["audio_ypixel"][s] for p in parts])
+            r["audio_max_sq_ave"] = np.concatenate([p["audio_max_sq_ave"][s] for p in parts])
         r["debug"] = engine.debug(s)
         out.append(r)
     return out
+
+
+def _check_audio_spec(tag, g, w, exact_max):
+    """Audio-spectrum by-product: the pixels pass through log10f and an int truncation, so the device's log10f
+    (2 ulp) may move a value sitting on an integer boundary: >= 99.9 % identical, never off by more than 1 (the
+    rule SURVEY.md section 8(d) states for the display rows).  audioMaxSquaredAve is plain products, maxima and an
+    FP64 average: identical on the bit-exact kernels, 1e-5 relative on the throughput kernel."""
+    d = np.abs(g["audio_ypixel"].astype(np.int64) - w["audio_ypixel"].astype(np.int64))
+    assert d.size == 0 or d.max() <= 1, tag + ": audio-spectrum pixel off by more than 1"
+    assert d.size == 0 or np.mean(d == 0) >= 0.999, tag + ": audio-spectrum rows < 99.9 %% identical (%.5f)" % np.mean(d == 0)
+    if exact_max:
+        # NaN (NFM discriminator on exact silence, like the reference) equals NaN whatever its payload
+        ga, wa = np.asarray(g["audio_max_sq_ave"], np.float32), np.asarray(w["audio_max_sq_ave"], np.float32)
+        same = (ga.view(np.uint32) == wa.view(np.uint32)) | (np.isnan(ga) & np.isnan(wa))
+        assert same.all(), tag + ": audioMaxSquaredAve differs"
+    else:
+        assert np.allclose(g["audio_max_sq_ave"], w["audio_max_sq_ave"], rtol=1e-5, atol=0.0, equal_nan=True), tag + ": audioMaxSquaredAve"
 
 
 def assert_identical(case, got, want, check_osc=True):
@@ -102,6 +130,8 @@ def assert_identical(case, got, want, check_osc=True):
                 tag, len(bad), bad[0], O.snr_db(w["audio"], g["audio"])))
         assert np.array_equal(g["spec"], w["spec"]), tag + ": spectrum rows differ"
         assert np.array_equal(g["wf"], w["wf"]), tag + ": waterfall rows differ"
+        if "audio_ypixel" in g:
+            _check_audio_spec(tag, g, w, exact_max=True)
         if case.psk:
             assert np.array_equal(g["psk_bits"], w["psk_bits"]), tag + ": PSK31 bits differ"
             assert np.array_equal(g["psk_chars"], w["psk_chars"]), tag + ": PSK31 characters differ"
@@ -133,6 +163,8 @@ def assert_within_tolerance(case, got, want, min_snr_db=90.0):
             assert diff.max() <= 1, tag + ": spectrum row off by more than 1 LSB"
             assert np.mean(diff == 0) >= 0.999, tag + ": spectrum rows < 99.9 %% identical"
             assert np.mean(g["wf"] == w["wf"]) >= 0.999, tag + ": waterfall rows < 99.9 %% identical"
+        if "audio_ypixel" in g:
+            _check_audio_spec(tag, g, w, exact_max=False)
         if case.psk:
             assert np.array_equal(g["psk_bits"], w["psk_bits"]), tag + ": PSK31 bits differ"
             assert np.array_equal(g["psk_chars"], w["psk_chars"]), tag + ": PSK31 characters differ"

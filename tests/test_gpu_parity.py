@@ -39,7 +39,8 @@ def test_exact_mode_is_bit_identical_to_oracle(make):
     want = cases.run_case_on(case, lambda p: O.OracleStream(p))
     with _receiver(case.n_streams) as eng:
         got = rx_driver.run_case_batched(case, eng, flags=rx.FLAG_EXACT_NCO)
-        assert eng.kernel_launches() == len(case.segments)
+        # one chain kernel per call, plus the audio-spectrum by-product kernel when the call has row-producing blocks
+        assert eng.kernel_launches() == len(case.segments) * (2 if case.row_every > 0 else 1)
     rx_driver.assert_identical(case, got, want)
 
 
@@ -57,6 +58,9 @@ def test_exact_mode_matches_reference_golden(make):
         assert hashlib.sha256(audio.tobytes()).hexdigest() == bytes(golden[key + "audio_sha256"]).hex(), key
         assert np.array_equal(r["spec"], golden[key + "spec"]), key
         assert np.array_equal(r["wf"], golden[key + "wf"]), key
+        if case.row_every > 0:
+            rx_driver._check_audio_spec(key, r, dict(audio_ypixel=golden[key + "audio_ypixel"],
+                                                     audio_max_sq_ave=golden[key + "audio_max_sq_ave"]), exact_max=True)
         if case.psk:
             assert np.array_equal(r["psk_bits"], golden[key + "psk_bits"]), key
             assert np.array_equal(r["psk_chars"], golden[key + "psk_chars"]), key
@@ -134,6 +138,57 @@ def test_q15_entry_point_is_the_firmware_block_format():
         d = np.abs(fast["audio"][s_].astype(np.int32) - ref16.astype(np.int32))
         assert d.max() <= 1 and np.mean(d == 0) >= 0.99, (s_, int(d.max()), float(np.mean(d == 0)))
         assert np.array_equal(fast["spec"][s_], w["spec"])
+
+
+def test_audio_spectrum_by_product_entry_points():
+    """The audio-spectrum / S-meter by-product (Process.cpp:550-570) through the three entry points: host float,
+    host q15 and device pointers give the same rows; unbinding stops the output; the S-meter helper matches the
+    oracle's restatement of Display.cpp:980."""
+    torch = pytest.importorskip("torch")
+    case = cases.c2_ssb_am_mix()
+    want = cases.run_case_on(case, lambda p: O.OracleStream(p))
+    iq = np.stack(case.iq)
+    S, T = iq.shape[:2]
+    R = (T + case.row_every - 1) // case.row_every
+    params = [rx_driver.to_rx_params(p) for p in case.segments[0][0]]
+    outs = []
+    for flags in (rx.FLAG_EXACT_NCO, 0):
+        with _receiver(S) as eng:
+            eng.set_params_each(params)
+            host = eng.process(iq, row_every=case.row_every, flags=flags, want_audio_spec=True)
+        with _receiver(S) as eng:
+            eng.set_params_each(params)
+            q15 = eng.process_q15(np.round(iq * 32768.0).astype(np.int16), row_every=case.row_every, flags=flags,
+                                  want_audio_spec=True)
+        with _receiver(S) as eng:
+            eng.set_params_each(params)
+            d_iq = torch.from_numpy(iq).cuda()
+            d_audio = torch.empty((S, T, 2048), dtype=torch.float32, device="cuda")
+            d_pix = torch.full((S, R, rx.AUDIO_SPEC_PIXELS), -7, dtype=torch.int32, device="cuda")
+            d_max = torch.full((S, R), -7.0, dtype=torch.float32, device="cuda")
+            eng.bind_audio_spectrum(d_pix.data_ptr(), d_max.data_ptr())
+            eng.process_device(d_iq.data_ptr(), d_audio.data_ptr(), T, row_every=case.row_every, flags=flags)
+            eng.synchronize()
+            eng.bind_audio_spectrum(None, None)
+            dev_pix, dev_max = d_pix.cpu().numpy(), d_max.cpu().numpy()
+            # unbound: a second call leaves the buffers alone
+            d_pix.fill_(-7)
+            eng.process_device(d_iq.data_ptr(), d_audio.data_ptr(), T, row_every=case.row_every, flags=flags)
+            eng.synchronize()
+            assert int(d_pix.max()) == -7
+        for o in (q15,):
+            assert np.array_equal(o["audio_ypixel"], host["audio_ypixel"])
+            assert np.array_equal(o["audio_max_sq_ave"].view(np.uint32), host["audio_max_sq_ave"].view(np.uint32))
+        assert np.array_equal(dev_pix, host["audio_ypixel"])
+        assert np.array_equal(dev_max.view(np.uint32), host["audio_max_sq_ave"].view(np.uint32))
+        for s_, w in enumerate(want):
+            rx_driver._check_audio_spec("receiver %d flags %d" % (s_, flags),
+                                        dict(audio_ypixel=host["audio_ypixel"][s_], audio_max_sq_ave=host["audio_max_sq_ave"][s_]),
+                                        w, exact_max=(flags != 0))
+        outs.append(host)
+    lib = O.tier_b()
+    for v in outs[0]["audio_max_sq_ave"].ravel()[:8]:
+        assert rx.smeter_dbm(float(v), -2.0, 3, 1) == lib.t41o_smeter_dbm(float(v), -2.0, 3, 1)
 
 
 def test_error_codes():

@@ -142,3 +142,15 @@ def test_rows_only_schedule_emulated(make):
     got = rx_driver.run_case_batched(case, eng, flags=rx.FLAG_EXACT_NCO | EMUL_SPLIT_ROWS)
     eng.close()
     rx_driver.assert_identical(case, got, want)
+
+
+def test_smeter_helper_matches_oracle():
+    """t41rx_smeter_dbm is host arithmetic (Display.cpp:959-981): no GPU needed."""
+    lib = O.tier_b()
+    rng = np.random.default_rng(3)
+    for v in np.concatenate([10.0 ** rng.uniform(-6, 6, 200), [0.0, 1.0, 40.0]]).astype(np.float32):
+        for gc, rf, rfall in ((-2.0, 1, 1), (3.5, 15, -10), (0.0, 7, 20)):
+            a, b = rx.smeter_dbm(float(v), gc, rf, rfall), lib.t41o_smeter_dbm(float(v), gc, rf, rfall)
+            assert a == b or (np.isnan(a) and np.isnan(b)) or (np.isinf(a) and a == b), (v, gc, rf, rfall, a, b)
+    # the comment in the reference: audioMaxSquaredAve = 40 is about S9 (-73 dBm) on a calibrated band
+    assert -80.0 < rx.smeter_dbm(40.0, -2.0, 1, 1) < -50.0
