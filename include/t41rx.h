@@ -187,6 +187,16 @@ int t41rx_synchronize(t41rx_ctx *ctx);
  * While bound the context keeps n_streams * n_rows * 4 KiB of scratch for the masked spectra. */
 #define T41RX_AUDIO_SPEC_PIXELS 270
 int t41rx_bind_audio_spectrum(t41rx_ctx *ctx, int32_t *audio_ypixel, float *audio_max_sq_ave);
+/* What the row-producing blocks write to the PC control app's serial port while controlDataFlag is set
+ * (t41Control.cpp:20-48); binding plays the role of the flag:
+ *   spec_frames   uint8 [n_streams][n_rows][518]  "FD" + "%03d" of (255 - max) + 512 data bytes + ';' (FFT.cpp:142-194:
+ *                                                 data = pixelnew + currentNF shifted so that its maximum is 255);
+ *                                                 only ZoomFFTExe sends it: all zeros at spectrum_zoom == 0
+ *   audio_frames  uint8 [n_streams][n_rows][270]  min(audioYPixel, 255), no header (Process.cpp:818-825)
+ * Same pointer rules as t41rx_bind_audio_spectrum.  spec_frames is built from the spectrum rows: with
+ * t41rx_process_device the call's spec_rows must not be NULL. */
+#define T41RX_SPEC_FRAME_BYTES 518
+int t41rx_bind_control_frames(t41rx_ctx *ctx, uint8_t *spec_frames, uint8_t *audio_frames);
 /* The S-meter reading DrawSmeterBar() derives from audioMaxSquaredAve (Display.cpp:959-981, TCVSDR_SMETER build):
  * dBm, given bands[].gainCorrection, bands[].RFgain (t41rx_debug.rf_gain) and rfGainAllBands.  Host arithmetic. */
 float t41rx_smeter_dbm(float audio_max_sq_ave, float gain_correction, int32_t rf_gain, int32_t rf_gain_all_bands);

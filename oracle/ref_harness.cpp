@@ -221,7 +221,12 @@ int ft8_decode(void) { return 0; }
 void DisplayMessages() {}
 void update_synchronization() {}
 void auto_sync_FT8() {}
-void T41ControlSendData(uint8_t *, int) {}
+/* the control serial port: what a block writes to it is captured per block (see t41ref_capture_control_frames) */
+static uint8_t g_sent_spec[T41O_SPEC_FRAME_BYTES], g_sent_audio[T41O_AUDIO_SPEC_PIXELS];
+void T41ControlSendData(uint8_t *data, int len) {
+  if (len == T41O_SPEC_FRAME_BYTES) memcpy(g_sent_spec, data, len);               /* FFT.cpp:193 */
+  else if (len == T41O_AUDIO_SPEC_PIXELS) memcpy(g_sent_audio, data, len);        /* Process.cpp:824 */
+}
 
 /* AGC variables of DSP_Fn.cpp that have external linkage */
 extern uint8_t agc_action;
@@ -250,6 +255,8 @@ static unsigned g_psk_block_count = 0;
 static uint16_t g_waterfall[SPECTRUM_RES];
 static int32_t *g_cap_ypixel = 0;   /* [rows][T41O_AUDIO_SPEC_PIXELS], set by t41ref_capture_audio_spectrum */
 static float *g_cap_max_ave = 0;    /* [rows] */
+static uint8_t *g_cap_frames = 0;   /* [rows][518] */
+static uint8_t *g_cap_audio_frames = 0;   /* [rows][270] */
 
 /* RGB565 ramp of Display.cpp:148-161 comes from the generated data header */
 #include "t41_tables_data.h"
@@ -397,6 +404,8 @@ int t41ref_process_block(const float *iq, float *audio, int update_display, int1
   Q_in_R.push(silence);          /* ProcessIQData wants MORE than N_BLOCKS queued (Process.cpp:93) */
   Q_in_L.push(silence);
   updateDisplayFlag = update_display ? 1 : 0;
+  memset(g_sent_spec, 0, sizeof(g_sent_spec));
+  memset(g_sent_audio, 0, sizeof(g_sent_audio));
   ProcessIQData();
   Q_in_L.clear();
   Q_in_R.clear();
@@ -448,6 +457,8 @@ int t41ref_process(const float *iq, float *audio, int n_blocks, int row_every, i
       for (int k = 0; k < T41O_AUDIO_SPEC_PIXELS; k++) g_cap_ypixel[(size_t)rows * T41O_AUDIO_SPEC_PIXELS + k] = audioYPixel[k];
     }
     if (upd && g_cap_max_ave) g_cap_max_ave[rows] = audioMaxSquaredAve;
+    if (upd && g_cap_frames) memcpy(g_cap_frames + (size_t)rows * T41O_SPEC_FRAME_BYTES, g_sent_spec, T41O_SPEC_FRAME_BYTES);
+    if (upd && g_cap_audio_frames) memcpy(g_cap_audio_frames + (size_t)rows * T41O_AUDIO_SPEC_PIXELS, g_sent_audio, T41O_AUDIO_SPEC_PIXELS);
     rows += upd;
   }
   return rows;
@@ -458,6 +469,14 @@ int t41ref_process(const float *iq, float *audio, int n_blocks, int row_every, i
 void t41ref_capture_audio_spectrum(int32_t *ypixel_rows, float *max_ave_rows) {
   g_cap_ypixel = ypixel_rows;
   g_cap_max_ave = max_ave_rows;
+}
+
+/* capture what every row-producing block sends to the control serial port (all zeros when it sends nothing):
+   the 518-byte spectrum frame and the 270 audio-spectrum bytes; sets controlDataFlag like the control app does */
+void t41ref_capture_control_frames(uint8_t *spec_frame_rows, uint8_t *audio_frame_rows) {
+  g_cap_frames = spec_frame_rows;
+  g_cap_audio_frames = audio_frame_rows;
+  controlDataFlag = (spec_frame_rows != 0) || (audio_frame_rows != 0);
 }
 
 void t41ref_get_params(t41o_params *p) {

@@ -11,6 +11,7 @@
 #include "t41_oracle.h"
 
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -333,6 +334,11 @@ struct t41o_stream {
   int audio_ypixel[T41O_AUDIO_SPEC_PIXELS];
   int32_t *cap_ypixel;
   float *cap_max_ave;
+  /* spectrum serial frame for the PC control app, T41/t41Control.cpp:21-23 */
+  uint8_t spec_data[T41O_SPEC_FRAME_BYTES];
+  int control_data_flag;
+  uint8_t sent_spec[T41O_SPEC_FRAME_BYTES], sent_audio[T41O_AUDIO_SPEC_PIXELS];   /* serial-port writes of this block */
+  uint8_t *cap_frames, *cap_audio_frames;
   float spec_buf[2 * kSpecRes];
   float fft_spec[kSpecRes];
   float fft_spec_old[kSpecRes];
@@ -506,6 +512,31 @@ void SpectrumZoomN(t41o_stream *s) {
     s->fft_spec[i] = LPFcoeff * s->fft_spec[i] + onem_LPFcoeff * s->fft_spec_old[i];
     s->fft_spec_old[i] = s->fft_spec[i];
     s->pixelnew[i] = PixelFromPower(s, s->fft_spec[i]);   /* smoothed value */
+  }
+  /* T41/FFT.cpp:142-194: the "FDxxx<512 bytes>;" frame T41ControlSendData() writes to the control serial port:
+     data = pixelnew + currentNF, shifted so that its maximum (at least 0) becomes 255, negatives clamped to 0;
+     xxx = 255 - max.  sprintf's terminating NUL lands on byte 5 and is overwritten by the first data byte. */
+  int16_t min = 0, max = 0;
+  int16_t data[kSpecRes];
+  for (int i = 0; i < kSpecRes; i++) {
+    if (s->control_data_flag) {
+      data[i] = s->pixelnew[i] + s->prm.current_nf;
+      if (data[i] < min) min = data[i];
+      if (data[i] > max) max = data[i];
+    }
+  }
+  (void)min;
+  char head[16];
+  snprintf(head, sizeof(head), "FD%03d", 255 - max);
+  memcpy(s->spec_data, head, strlen(head) + 1 < 8 ? strlen(head) + 1 : 8);
+  s->spec_data[517] = ';';
+  if (s->control_data_flag) {
+    for (int i = 0; i < kSpecRes; i++) {
+      int tmp = data[i] + 255 - max;
+      if (tmp < 0) tmp = 0;
+      s->spec_data[i + 5] = (uint8_t)tmp;
+    }
+    memcpy(s->sent_spec, s->spec_data, T41O_SPEC_FRAME_BYTES);     /* T41ControlSendData(specData, SPECTRUM_RES + 6) */
   }
 }
 
@@ -889,6 +920,8 @@ static void AudioSpectrum(t41o_stream *s, int mode) {
 int t41o_process_block(t41o_stream *s, const float *iq, float *audio, int update_display,
                        int16_t *spec_row, uint16_t *wf_row, int8_t *psk_bit, uint8_t *psk_char) {
   if (!s || !iq || !audio) return -1;
+  memset(s->sent_spec, 0, sizeof(s->sent_spec));
+  memset(s->sent_audio, 0, sizeof(s->sent_audio));
   const int mode = s->prm.mode;
   float *L = s->bufL, *R = s->bufR;
 
@@ -1050,6 +1083,14 @@ int t41o_process_block(t41o_stream *s, const float *iq, float *audio, int update
     for (int i = 0; i < kDec; i++) L[i] = io[i * 2];
   }
 
+  /* T41/Process.cpp:818-825: the audio-spectrum bytes for the control app (specData is reused as scratch) */
+  if (update_display && s->control_data_flag) {
+    for (int i = 0; i < T41O_AUDIO_SPEC_PIXELS; i++) {
+      s->spec_data[i] = (uint8_t)(s->audio_ypixel[i] > 255 ? 255 : s->audio_ypixel[i]);
+    }
+    memcpy(s->sent_audio, s->spec_data, T41O_AUDIO_SPEC_PIXELS);
+  }
+
   /* T41/Process.cpp:917-920 */
   arm_fir_interpolate_f32(&s->int1, L, s->ifft_buf, kDec);
   arm_fir_interpolate_f32(&s->int2, s->ifft_buf, L, 2 * kDec);
@@ -1081,6 +1122,8 @@ int t41o_process(t41o_stream *s, const float *iq, float *audio, int n_blocks, in
       for (int k = 0; k < T41O_AUDIO_SPEC_PIXELS; k++) s->cap_ypixel[(size_t)rows * T41O_AUDIO_SPEC_PIXELS + k] = s->audio_ypixel[k];
     }
     if (upd && s->cap_max_ave) s->cap_max_ave[rows] = s->audio_max_sq_ave;
+    if (upd && s->cap_frames) memcpy(s->cap_frames + (size_t)rows * T41O_SPEC_FRAME_BYTES, s->sent_spec, T41O_SPEC_FRAME_BYTES);
+    if (upd && s->cap_audio_frames) memcpy(s->cap_audio_frames + (size_t)rows * T41O_AUDIO_SPEC_PIXELS, s->sent_audio, T41O_AUDIO_SPEC_PIXELS);
     rows += upd;
   }
   return rows;
@@ -1089,6 +1132,12 @@ int t41o_process(t41o_stream *s, const float *iq, float *audio, int n_blocks, in
 void t41o_capture_audio_spectrum(t41o_stream *s, int32_t *ypixel_rows, float *max_ave_rows) {
   s->cap_ypixel = ypixel_rows;
   s->cap_max_ave = max_ave_rows;
+}
+
+void t41o_capture_control_frames(t41o_stream *s, uint8_t *spec_frame_rows, uint8_t *audio_frame_rows) {
+  s->cap_frames = spec_frame_rows;
+  s->cap_audio_frames = audio_frame_rows;
+  s->control_data_flag = (spec_frame_rows != 0) || (audio_frame_rows != 0);
 }
 
 /* T41/Display.cpp:959-981 (TCVSDR_SMETER): dbm_calibration = 22.0, slope = 10.0, cons = -92 are floats, attenuator = 0

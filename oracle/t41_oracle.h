@@ -133,6 +133,14 @@ int t41o_process(t41o_stream *s, const float *iq, float *audio, int n_blocks, in
  * them, one row per row-producing block (NULL = stop capturing). */
 #define T41O_AUDIO_SPEC_PIXELS 270
 void t41o_capture_audio_spectrum(t41o_stream *s, int32_t *ypixel_rows, float *max_ave_rows);
+/* What a row-producing block writes to the PC control app's serial port while controlDataFlag is set (capturing
+ * sets it; T41/t41Control.cpp:20-48):
+ *   spectrum frame, 518 bytes (T41/FFT.cpp:142-194): "FD" + "%03d" of (255 - max) + 512 data bytes + ';'.  Only
+ *     ZoomFFTExe (zoom index != 0) sends it; at zoom x1 nothing is sent and the row is all zeros;
+ *   audio-spectrum data, 270 bytes (T41/Process.cpp:819-825): min(audioYPixel[i], 255), no header.
+ * One row of each per row-producing block (NULL, NULL = stop, flag cleared). */
+#define T41O_SPEC_FRAME_BYTES 518
+void t41o_capture_control_frames(t41o_stream *s, uint8_t *spec_frame_rows, uint8_t *audio_frame_rows);
 /* S-meter reading the display derives from audioMaxSquaredAve (T41/Display.cpp:976-981, TCVSDR_SMETER build,
  * MyConfigurationFile.h:34): dBm.  Display.cpp is not part of the Tier-A build; this is a restatement only. */
 float t41o_smeter_dbm(float audio_max_sq_ave, float gain_correction, int32_t rf_gain, int32_t rf_gain_all_bands);

@@ -104,10 +104,12 @@ __global__ void __launch_bounds__(kNT, 8 / kG) t41rx_rows_kernel(const LaunchArg
   }
 }
 
-/* audio-spectrum + S-meter by-product of the row-producing blocks (Process.cpp:550-570,791-805) from the masked
-   spectra the chain kernels left in a.aspec; launched after them on the same stream.  The running average
-   makes the rows of one receiver a serial chain; receivers are independent. */
-__global__ void __launch_bounds__(kNT) t41rx_audio_spectrum_kernel(const LaunchArgs a) {
+/* by-products of the row-producing blocks, launched after the chain (and rows) kernels on the same stream:
+   audio spectrum + S-meter average (Process.cpp:550-570,791-805) from the masked spectra the chain kernels left in
+   a.aspec, and the two frames for the control app's serial port (FFT.cpp:142-194 from the pixelnew rows,
+   Process.cpp:818-825).  The running average makes the rows of one receiver a serial chain; receivers are
+   independent. */
+__global__ void __launch_bounds__(kNT) t41rx_row_byproducts_kernel(const LaunchArgs a) {
   extern __shared__ __align__(16) float smem[];
   Cta c;
   c.a = a;
@@ -125,7 +127,12 @@ __global__ void __launch_bounds__(kNT) t41rx_audio_spectrum_kernel(const LaunchA
     stmt;                  \
     __syncthreads();       \
   } while (0)
-    T41RX_AUDIO_SPEC_SCHEDULE(T41RX_KPHASE)
+    if (a.aspec) {
+      T41RX_AUDIO_SPEC_SCHEDULE(T41RX_KPHASE)
+    }
+    if (a.spec_frames) {
+      T41RX_SPEC_FRAME_SCHEDULE(T41RX_KPHASE)
+    }
 #undef T41RX_KPHASE
   }
 }
@@ -229,8 +236,10 @@ struct t41rx_ctx {
      chain kernels fill on row-producing blocks, and device staging for the host-buffer entry points */
   int32_t *bind_ypixel = nullptr;
   float *bind_max_ave = nullptr;
-  void *d_aspec = nullptr, *d_ypixel = nullptr, *d_max_ave = nullptr;
-  size_t cap_aspec = 0, cap_ypixel = 0, cap_max_ave = 0;
+  uint8_t *bind_spec_frames = nullptr, *bind_audio_frames = nullptr;   /* t41rx_bind_control_frames */
+  void *d_aspec = nullptr, *d_ypixel = nullptr, *d_max_ave = nullptr, *d_sframes = nullptr, *d_aframes = nullptr;
+  size_t cap_aspec = 0, cap_ypixel = 0, cap_max_ave = 0, cap_sframes = 0, cap_aframes = 0;
+  bool WantAudioSpec() const { return bind_ypixel || bind_max_ave || bind_audio_frames; }
 };
 
 static int EnsureFsetCapacity(t41rx_ctx *ctx, int need) {
@@ -312,7 +321,8 @@ void t41rx_destroy(t41rx_ctx *ctx) {
   void *bufs[] = {ctx->d_cfg, ctx->d_state, ctx->d_fsets, ctx->d_nco_tab, ctx->d_twiddle, ctx->d_hann, ctx->d_sin,
                   ctx->d_zoom_iir, ctx->d_sam, ctx->d_gradient, ctx->d_varicode, ctx->d_iq, ctx->d_audio,
                   ctx->d_spec, ctx->d_wf, ctx->d_bits, ctx->d_chars, ctx->d_fast_ids, ctx->d_phased_ids,
-                  ctx->d_iq16, ctx->d_audio16, ctx->d_aspec, ctx->d_ypixel, ctx->d_max_ave};
+                  ctx->d_iq16, ctx->d_audio16, ctx->d_aspec, ctx->d_ypixel, ctx->d_max_ave,
+                  ctx->d_sframes, ctx->d_aframes};
   for (void *b : bufs)
     if (b) cudaFree(b);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -363,7 +373,7 @@ int t41rx_create(t41rx_ctx **out, int n_streams, int device) {
                            (int)(kSmemFloats * sizeof(float))) != cudaSuccess ||
       cudaFuncSetAttribute(t41rx_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)(kSmemFloats * sizeof(float))) != cudaSuccess ||
-      cudaFuncSetAttribute(t41rx_audio_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      cudaFuncSetAttribute(t41rx_row_byproducts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)(kSmemFloats * sizeof(float))) != cudaSuccess)
     return bail(Fail(T41RX_ECUDA, "t41rx_create: kernel image for this GPU missing (built for sm_100a)%s"));
   if (ConfigureStreamKernel() != cudaSuccess ||
@@ -522,7 +532,7 @@ int t41rx_get_debug(t41rx_ctx *ctx, int stream, t41rx_debug *d) {
 static int LaunchRange(t41rx_ctx *ctx, const float *iq, float *audio, int n_blocks, int row_every,
                        int16_t *spec_rows, uint16_t *wf_rows, int8_t *psk_bits, uint8_t *psk_chars,
                        uint32_t flags, cudaStream_t st, int first, int count, int32_t *d_ypixel = nullptr,
-                       float *d_max_ave = nullptr) {
+                       float *d_max_ave = nullptr, uint8_t *d_sframes = nullptr, uint8_t *d_aframes = nullptr) {
   LaunchArgs a;
   memset(&a, 0, sizeof(a));
   a.iq = iq;
@@ -548,15 +558,20 @@ static int LaunchRange(t41rx_ctx *ctx, const float *iq, float *audio, int n_bloc
   a.row_every = row_every;
   a.n_rows = row_every > 0 ? (n_blocks + row_every - 1) / row_every : 0;
   a.flags = flags;
-  if (a.n_rows > 0 && (d_ypixel || d_max_ave)) {
+  if (a.n_rows > 0 && (d_ypixel || d_max_ave || d_aframes)) {
     a.aspec = (float2 *)ctx->d_aspec;         /* sized by the caller (EnsureAudioSpecScratch) */
     a.audio_ypixel = d_ypixel;
     a.audio_max_ave = d_max_ave;
+    a.audio_frames = d_aframes;
+  }
+  if (a.n_rows > 0 && d_sframes) {
+    if (!a.spec_rows) return Fail(T41RX_EINVAL, "t41rx_process: the spectrum frames are built from spec_rows, which is NULL%s");
+    a.spec_frames = d_sframes;
   }
   /* the by-product kernel runs after the chain kernels of the range, on the whole (contiguous) range */
   auto audio_spectrum = [&]() -> int {
-    if (!a.aspec) return T41RX_OK;
-    t41rx_audio_spectrum_kernel<<<(count + kG - 1) / kG, kNT, kSmemFloats * sizeof(float), st>>>(a);
+    if (!a.aspec && !a.spec_frames) return T41RX_OK;
+    t41rx_row_byproducts_kernel<<<(count + kG - 1) / kG, kNT, kSmemFloats * sizeof(float), st>>>(a);
     CUDA_TRY(cudaGetLastError());
     ctx->launches += 1;
     return T41RX_OK;
@@ -608,7 +623,7 @@ static int LaunchRange(t41rx_ctx *ctx, const float *iq, float *audio, int n_bloc
 
 /* scratch for the masked spectra of the row-producing blocks: [n_streams][n_rows][512] float2 */
 static int EnsureAudioSpecScratch(t41rx_ctx *ctx, size_t n_rows) {
-  if (!(ctx->bind_ypixel || ctx->bind_max_ave) || n_rows == 0) return T41RX_OK;
+  if (!ctx->WantAudioSpec() || n_rows == 0) return T41RX_OK;
   return Grow(&ctx->d_aspec, &ctx->cap_aspec, (size_t)ctx->n_streams * n_rows * kFft * sizeof(float2));
 }
 
@@ -640,7 +655,7 @@ int t41rx_process_device(t41rx_ctx *ctx, const float *iq, float *audio, int n_bl
   if ((rc = EnsureAudioSpecScratch(ctx, row_every > 0 ? (size_t)(n_blocks + row_every - 1) / row_every : 0))) return rc;
   CUDA_TRY(cudaEventRecord(ctx->ev0, st));
   rc = LaunchRange(ctx, iq, audio, n_blocks, row_every, spec_rows, wf_rows, psk_bits, psk_chars, flags, st, 0, ctx->n_streams,
-                   ctx->bind_ypixel, ctx->bind_max_ave);
+                   ctx->bind_ypixel, ctx->bind_max_ave, ctx->bind_spec_frames, ctx->bind_audio_frames);
   if (rc) return rc;
   CUDA_TRY(cudaEventRecord(ctx->ev1, st));
   ctx->ev_valid = true;
@@ -669,6 +684,13 @@ int t41rx_bind_audio_spectrum(t41rx_ctx *ctx, int32_t *audio_ypixel, float *audi
   return T41RX_OK;
 }
 
+int t41rx_bind_control_frames(t41rx_ctx *ctx, uint8_t *spec_frames, uint8_t *audio_frames) {
+  if (!ctx) return Fail(T41RX_EINVAL, "t41rx_bind_control_frames: null context%s");
+  ctx->bind_spec_frames = spec_frames;
+  ctx->bind_audio_frames = audio_frames;
+  return T41RX_OK;
+}
+
 /* Display.cpp:959-981 (TCVSDR_SMETER build): float sum up to the constant, then the FP64 tail the double literal
    1.5 forces; log10f_fast is Utility.cpp:245-258 */
 float t41rx_smeter_dbm(float audio_max_sq_ave, float gain_correction, int32_t rf_gain, int32_t rf_gain_all_bands) {
@@ -692,8 +714,8 @@ static int ProcessHost(t41rx_ctx *ctx, const float *iq, float *audio, const int1
   const bool q15 = iq16 != nullptr;
   if (!ctx || (!q15 && (!iq || !audio)) || (q15 && !audio16) || n_blocks <= 0 || row_every < 0)
     return Fail(T41RX_EINVAL, "t41rx_process: bad arguments%s");
-  const bool want_aspec = ctx && (ctx->bind_ypixel || ctx->bind_max_ave);
-  if (row_every > 0 && !spec_rows && !wf_rows && !want_aspec) row_every = 0;
+  const bool want_rows_out = ctx && (ctx->WantAudioSpec() || ctx->bind_spec_frames);
+  if (row_every > 0 && !spec_rows && !wf_rows && !want_rows_out) row_every = 0;
   CUDA_TRY(cudaSetDevice(ctx->device));
   const size_t S = (size_t)ctx->n_streams, T = (size_t)n_blocks;
   const size_t n_rows = row_every > 0 ? (T + row_every - 1) / row_every : 0;
@@ -703,7 +725,8 @@ static int ProcessHost(t41rx_ctx *ctx, const float *iq, float *audio, const int1
   int rc;
   if ((rc = Grow(&ctx->d_iq, &ctx->cap_iq, b_iq))) return rc;
   if ((rc = Grow(&ctx->d_audio, &ctx->cap_audio, b_audio))) return rc;
-  if (n_rows && spec_rows && (rc = Grow(&ctx->d_spec, &ctx->cap_spec, b_spec))) return rc;
+  const bool need_spec = n_rows && (spec_rows || ctx->bind_spec_frames);     /* the frames are built from the rows */
+  if (need_spec && (rc = Grow(&ctx->d_spec, &ctx->cap_spec, b_spec))) return rc;
   if (n_rows && wf_rows && (rc = Grow(&ctx->d_wf, &ctx->cap_wf, b_wf))) return rc;
   if (psk_bits && (rc = Grow(&ctx->d_bits, &ctx->cap_bits, b_psk))) return rc;
   if (psk_chars && (rc = Grow(&ctx->d_chars, &ctx->cap_chars, b_psk))) return rc;
@@ -713,13 +736,17 @@ static int ProcessHost(t41rx_ctx *ctx, const float *iq, float *audio, const int1
   if (n_rows && ctx->bind_ypixel && (rc = Grow(&ctx->d_ypixel, &ctx->cap_ypixel, b_ypix))) return rc;
   if (n_rows && ctx->bind_max_ave && (rc = Grow(&ctx->d_max_ave, &ctx->cap_max_ave, b_max))) return rc;
   if ((rc = EnsureAudioSpecScratch(ctx, n_rows))) return rc;
+  if (n_rows && ctx->bind_spec_frames && (rc = Grow(&ctx->d_sframes, &ctx->cap_sframes, S * n_rows * kSpecFrameBytes))) return rc;
+  if (n_rows && ctx->bind_audio_frames && (rc = Grow(&ctx->d_aframes, &ctx->cap_aframes, S * n_rows * kAudioSpecPixels))) return rc;
+  uint8_t *d_sfr = (n_rows && ctx->bind_spec_frames) ? (uint8_t *)ctx->d_sframes : nullptr;
+  uint8_t *d_afr = (n_rows && ctx->bind_audio_frames) ? (uint8_t *)ctx->d_aframes : nullptr;
   int32_t *d_ypix = (n_rows && ctx->bind_ypixel) ? (int32_t *)ctx->d_ypixel : nullptr;
   float *d_maxave = (n_rows && ctx->bind_max_ave) ? (float *)ctx->d_max_ave : nullptr;
   if ((rc = RefreshKernelLists(ctx))) return rc;
   /* receivers are independent: cut the bank into chunks and overlap the copy-in of chunk i+1, the kernels
      of chunk i and the copy-out of chunk i-1 on three streams (full-duplex host link) */
   const int n_chunks = (ctx->n_streams >= 8 * kProcessChunks) ? kProcessChunks : 1;
-  int16_t *d_spec = (n_rows && spec_rows) ? (int16_t *)ctx->d_spec : nullptr;
+  int16_t *d_spec = need_spec ? (int16_t *)ctx->d_spec : nullptr;
   uint16_t *d_wf = (n_rows && wf_rows) ? (uint16_t *)ctx->d_wf : nullptr;
   int8_t *d_bits = psk_bits ? (int8_t *)ctx->d_bits : nullptr;
   uint8_t *d_chars = psk_chars ? (uint8_t *)ctx->d_chars : nullptr;
@@ -740,7 +767,7 @@ static int ProcessHost(t41rx_ctx *ctx, const float *iq, float *audio, const int1
       ctx->launches += 1;
     }
     rc = LaunchRange(ctx, (const float *)ctx->d_iq, (float *)ctx->d_audio, n_blocks, row_every, d_spec, d_wf, d_bits, d_chars,
-                     flags, ctx->stream, (int)s0, (int)n, d_ypix, d_maxave);
+                     flags, ctx->stream, (int)s0, (int)n, d_ypix, d_maxave, d_sfr, d_afr);
     if (rc) return rc;
     if (q15) {
       t41rx_float_to_q15_kernel<<<2 * ctx->n_sms, 256, 0, ctx->stream>>>(
@@ -754,7 +781,9 @@ static int ProcessHost(t41rx_ctx *ctx, const float *iq, float *audio, const int1
       CUDA_TRY(cudaMemcpyAsync(audio16 + s0 * per_audio, (int16_t *)ctx->d_audio16 + s0 * per_audio, n * per_audio * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->copy_out));
     else
       CUDA_TRY(cudaMemcpyAsync(audio + s0 * per_audio, (float *)ctx->d_audio + s0 * per_audio, n * per_audio * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_out));
-    if (d_spec) CUDA_TRY(cudaMemcpyAsync(spec_rows + s0 * per_row, d_spec + s0 * per_row, n * per_row * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->copy_out));
+    if (d_sfr) CUDA_TRY(cudaMemcpyAsync(ctx->bind_spec_frames + s0 * n_rows * kSpecFrameBytes, d_sfr + s0 * n_rows * kSpecFrameBytes, n * n_rows * kSpecFrameBytes, cudaMemcpyDeviceToHost, ctx->copy_out));
+    if (d_afr) CUDA_TRY(cudaMemcpyAsync(ctx->bind_audio_frames + s0 * n_rows * kAudioSpecPixels, d_afr + s0 * n_rows * kAudioSpecPixels, n * n_rows * kAudioSpecPixels, cudaMemcpyDeviceToHost, ctx->copy_out));
+    if (d_spec && spec_rows) CUDA_TRY(cudaMemcpyAsync(spec_rows + s0 * per_row, d_spec + s0 * per_row, n * per_row * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->copy_out));
     if (d_wf) CUDA_TRY(cudaMemcpyAsync(wf_rows + s0 * per_row, d_wf + s0 * per_row, n * per_row * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->copy_out));
     if (d_ypix) CUDA_TRY(cudaMemcpyAsync(ctx->bind_ypixel + s0 * n_rows * kAudioSpecPixels, d_ypix + s0 * n_rows * kAudioSpecPixels, n * n_rows * kAudioSpecPixels * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->copy_out));
     if (d_maxave) CUDA_TRY(cudaMemcpyAsync(ctx->bind_max_ave + s0 * n_rows, d_maxave + s0 * n_rows, n * n_rows * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_out));

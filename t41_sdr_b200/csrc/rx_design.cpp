@@ -246,6 +246,7 @@ void DesignStreamCfg(const t41rx_params &p, const AgcConsts &agc, int filter_id,
                  p.mode == T41RX_DEMOD_SAM) ? 1 : 0;
   c->pixel_add = t41rx_base_offset[p.current_scale] + (int16_t)p.pixel_offset;
   c->wf_base = p.spectrum_noise_floor - p.current_nf;
+  c->current_nf = p.current_nf;
   int zs = kBlock / (1 << p.spectrum_zoom);
   if (zs > kSpecRes) zs = kSpecRes;
   c->zoom_samples = zs;

@@ -123,6 +123,9 @@ struct LaunchArgs {
   float2 *aspec;              /* scratch [receiver][n_rows][512]: the masked spectrum (iFFT_buffer before the inverse FFT) */
   int32_t *audio_ypixel;      /* [receiver][n_rows][270] */
   float *audio_max_ave;       /* [receiver][n_rows] */
+  /* what the row-producing blocks write to the control app's serial port (NULL when not bound) */
+  uint8_t *spec_frames;       /* [receiver][n_rows][518] */
+  uint8_t *audio_frames;      /* [receiver][n_rows][270] */
 };
 
 struct Cta {
@@ -1894,6 +1897,9 @@ T41RX_DEV void PhAudioPixels(Cta &c, int tid) {
       pix = st.audio_ypixel[k];
     }
     if (out) out[k] = pix;
+    /* Process.cpp:818-825: the same pixels, limited to a byte, go to the control app */
+    if (c.a.audio_frames)
+      c.a.audio_frames[((size_t)sid * c.a.n_rows + c.row_idx) * kAudioSpecPixels + k] = (uint8_t)(pix > 255 ? 255 : pix);
   }
   if (u == 0) {
     float ave = st.audio_max_sq_ave;
@@ -1914,6 +1920,67 @@ T41RX_DEV void PhAudioPixels(Cta &c, int tid) {
 #define T41RX_AUDIO_SPEC_SCHEDULE(RX_PHASE) \
   RX_PHASE(PhAudioSquares(c, tid));         \
   RX_PHASE(PhAudioPixels(c, tid));
+
+/* ------------------------------------------------------------------ */
+/* spectrum frame for the PC control app (FFT.cpp:142-194)              */
+/* ------------------------------------------------------------------ */
+/* "FD" + "%03d" of (255 - max) + 512 bytes + ';' from the pixelnew row the spectrum phases wrote: data = pixelnew +
+ * currentNF (int16), max starts at 0, byte = max(data + 255 - max, 0).  Only ZoomFFTExe (zoom != x1) sends it:
+ * zoom x1 rows are all zeros.  Shared memory of slot g: words 0..63 partial maxima. */
+T41RX_DEV void PhSpecFrameMax(Cta &c, int tid) {
+  const int g = tid >> 6, u = tid & 63;
+  if (g >= c.ng) return;
+  const int sid = Sid(c, g);
+  const StreamCfg &cf = c.a.cfg[sid];
+  if (cf.zoom == 0) return;
+  const int16_t *row = c.a.spec_rows + ((size_t)sid * c.a.n_rows + c.row_idx) * kSpecRes;
+  int m = 0;
+  for (int j = 0; j < 8; ++j) {
+    const int d = (int16_t)((int)row[u + 64 * j] + cf.current_nf);
+    m = d > m ? d : m;
+  }
+  reinterpret_cast<int *>(Slot(c, g))[u] = m;
+}
+
+T41RX_DEV void PhSpecFrameWrite(Cta &c, int tid) {
+  const int g = tid >> 6, u = tid & 63;
+  if (g >= c.ng) return;
+  const int sid = Sid(c, g);
+  const StreamCfg &cf = c.a.cfg[sid];
+  uint8_t *f = c.a.spec_frames + ((size_t)sid * c.a.n_rows + c.row_idx) * kSpecFrameBytes;
+  if (cf.zoom == 0) {                       /* CalcZoom1Magn sends nothing */
+    for (int i = u; i < kSpecFrameBytes; i += 64) f[i] = 0;
+    return;
+  }
+  const int *pm = reinterpret_cast<const int *>(Slot(c, g));
+  int mx = 0;
+  for (int i = 0; i < 64; ++i) mx = pm[i] > mx ? pm[i] : mx;
+  const int16_t *row = c.a.spec_rows + ((size_t)sid * c.a.n_rows + c.row_idx) * kSpecRes;
+  for (int j = 0; j < 8; ++j) {
+    const int x = u + 64 * j;
+    int t = (int16_t)((int)row[x] + cf.current_nf) + 255 - mx;
+    if (t < 0) t = 0;
+    f[5 + x] = (uint8_t)t;
+  }
+  if (u == 0) {
+    /* the first three characters sprintf("%03d") gives for 255 - max (a fourth one would be overwritten) */
+    const int v = 255 - mx;
+    char h0, h1, h2;
+    if (v >= 0) {
+      h0 = (char)('0' + (v / 100) % 10); h1 = (char)('0' + (v / 10) % 10); h2 = (char)('0' + v % 10);
+    } else {
+      int n = -v;
+      while (n >= 100) n /= 10;
+      h0 = '-'; h1 = (char)('0' + n / 10); h2 = (char)('0' + n % 10);
+    }
+    f[0] = 'F'; f[1] = 'D'; f[2] = (uint8_t)h0; f[3] = (uint8_t)h1; f[4] = (uint8_t)h2;
+    f[kSpecFrameBytes - 1] = ';';
+  }
+}
+
+#define T41RX_SPEC_FRAME_SCHEDULE(RX_PHASE) \
+  RX_PHASE(PhSpecFrameMax(c, tid));         \
+  RX_PHASE(PhSpecFrameWrite(c, tid));
 
 #define T41RX_ROWS_SCHEDULE(RX_PHASE)                                    \
   RX_PHASE(PhLoad(c, tid); PhRowDcSeed(c, tid));                         \

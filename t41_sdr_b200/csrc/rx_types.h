@@ -22,6 +22,7 @@ constexpr int kMaskTaps = 257;    /* m_NumTaps, Filter.cpp:18 */
 constexpr int kAgcDelay = 97;     /* attack_buffsize, DSP_Fn.cpp:409 (B11) */
 constexpr int kAgcRing = 128;     /* power-of-two ring >= kAgcDelay + 1 (firmware: 1921, functionally a 97-sample delay) */
 constexpr int kSpecRes = 512;
+constexpr int kSpecFrameBytes = 518;    /* specData[], t41Control.cpp:21 */
 constexpr int kAudioSpecPixels = 270;   /* AUDIO_SPEC_BOX_W - 2 = 800 - (0 + 1 + 512 + 15) - 2 (Display.h:6,15,20,42,45; Process.cpp:555) */
 
 /* demodulation modes (SDT.h:57-68), same values as T41RX_DEMOD_* */
@@ -58,6 +59,7 @@ struct StreamCfg {
   int32_t mirrored;            /* 1 for USB/LSB/AM/SAM: I *= -amp and phase correction (Process.cpp:165-174) */
   int32_t pixel_add;           /* displayScale[].baseOffset + bands[].pixel_offset */
   int32_t wf_base;             /* spectrumNoiseFloor - currentNF */
+  int32_t current_nf;          /* currentNF (FFT.cpp:161: serial frame data = pixelnew + currentNF) */
   int32_t zoom_samples;        /* min(2048 >> zoom, 512), FFT.cpp:78-81 */
   int32_t nco_epoch;           /* bumped when NCOFreq changes: forces one exact block (amplitude transient) */
   float rf_gain_value;         /* pow(10, rfGainAllBands / 20), Process.cpp:117 */

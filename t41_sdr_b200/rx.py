@@ -18,6 +18,7 @@ LIB_PATH = os.environ.get("T41RX_LIB", os.path.join(_HERE, "libt41rx.so"))
 DEMOD_USB, DEMOD_LSB, DEMOD_AM, DEMOD_NFM, DEMOD_PSK31, DEMOD_SAM = 0, 1, 2, 3, 5, 8
 BLOCK = 2048
 SPECTRUM_RES = 512
+SPEC_FRAME_BYTES = 518    # specData[], t41Control.cpp:21
 AUDIO_SPEC_PIXELS = 270   # AUDIO_SPEC_BOX_W - 2 (Display.h:45, Process.cpp:555)
 FLAG_EXACT_NCO = 1       # bit-exact kernel, step-by-step FP64 oscillator
 FLAG_PHASED_KERNEL = 2   # bit-exact kernel with the closed-form FP64 oscillator
@@ -74,7 +75,7 @@ EXPORTS = (
     "t41rx_num_streams", "t41rx_set_params", "t41rx_set_params_each", "t41rx_get_params",
     "t41rx_get_tables", "t41rx_get_debug", "t41rx_design_tables", "t41rx_process", "t41rx_process_q15",
     "t41rx_process_device", "t41rx_synchronize", "t41rx_kernel_launches", "t41rx_last_kernel_ms",
-    "t41rx_stream_kernel_times", "t41rx_bind_audio_spectrum", "t41rx_smeter_dbm",
+    "t41rx_stream_kernel_times", "t41rx_bind_audio_spectrum", "t41rx_bind_control_frames", "t41rx_smeter_dbm",
     "t41rx_last_error", "t41rx_version")
 
 
@@ -113,6 +114,7 @@ def lib():
         L.t41rx_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.t41rx_stream_kernel_times.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
         L.t41rx_bind_audio_spectrum.argtypes = [vp, vp, vp]
+        L.t41rx_bind_control_frames.argtypes = [vp, vp, vp]
         L.t41rx_smeter_dbm.argtypes = [C.c_float, C.c_float, C.c_int32, C.c_int32]
         L.t41rx_smeter_dbm.restype = C.c_float
         L.t41rx_last_error.restype = C.c_char_p
@@ -215,12 +217,21 @@ class Receiver:
         outputs: int32 [n_streams, n_rows, 270] and float32 [n_streams, n_rows]; None, None unbinds."""
         _check(lib().t41rx_bind_audio_spectrum(self._h, ypixel_ptr, max_ave_ptr), "t41rx_bind_audio_spectrum")
 
+    def bind_control_frames(self, spec_frames_ptr, audio_frames_ptr):
+        """Raw pointers of the control-app serial frames of the row-producing blocks: uint8 [n_streams, n_rows, 518]
+        and uint8 [n_streams, n_rows, 270]; None, None unbinds."""
+        _check(lib().t41rx_bind_control_frames(self._h, spec_frames_ptr, audio_frames_ptr), "t41rx_bind_control_frames")
+
     def _audio_spec_arrays(self, out, n_rows, want):
+        """want_audio_spec: bind host arrays for every by-product of the row-producing blocks"""
         if not want or n_rows == 0:
             return False
         out.setdefault("audio_ypixel", np.zeros((self.n_streams, n_rows, AUDIO_SPEC_PIXELS), np.int32))
         out.setdefault("audio_max_sq_ave", np.zeros((self.n_streams, n_rows), np.float32))
+        out.setdefault("spec_frames", np.zeros((self.n_streams, n_rows, SPEC_FRAME_BYTES), np.uint8))
+        out.setdefault("audio_frames", np.zeros((self.n_streams, n_rows, AUDIO_SPEC_PIXELS), np.uint8))
         self.bind_audio_spectrum(_np_ptr(out["audio_ypixel"]), _np_ptr(out["audio_max_sq_ave"]))
+        self.bind_control_frames(_np_ptr(out["spec_frames"]), _np_ptr(out["audio_frames"]))
         return True
 
     def process(self, iq, row_every=0, want_psk=False, flags=0, out=None, want_audio_spec=False):
@@ -246,6 +257,7 @@ class Receiver:
         finally:
             if bound:
                 self.bind_audio_spectrum(None, None)
+                self.bind_control_frames(None, None)
         return out
 
     def process_q15(self, iq_q15, row_every=0, want_psk=False, flags=0, out=None, want_audio_spec=False):
@@ -272,6 +284,7 @@ class Receiver:
         finally:
             if bound:
                 self.bind_audio_spectrum(None, None)
+                self.bind_control_frames(None, None)
         return out
 
     # ---- ProcessIQData over device buffers (raw pointers, e.g. torch.Tensor.data_ptr()) ----

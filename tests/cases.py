@@ -171,7 +171,9 @@ def run_case_on(case, make_stream):
                    spec=np.concatenate([p["spec"] for p in parts]),
                    wf=np.concatenate([p["wf"] for p in parts]),
                    audio_ypixel=np.concatenate([p["audio_ypixel"] for p in parts]),
-                   audio_max_sq_ave=np.concatenate([p["audio_max_sq_ave"] for p in parts]))
+                   audio_max_sq_ave=np.concatenate([p["audio_max_sq_ave"] for p in parts]),
+                   spec_frames=np.concatenate([p["spec_frames"] for p in parts]),
+                   audio_frames=np.concatenate([p["audio_frames"] for p in parts]))
         if case.psk:
             res["psk_bits"] = np.concatenate([p["psk_bits"] for p in parts])
             res["psk_chars"] = np.concatenate([p["psk_chars"] for p in parts])

@@ -28,6 +28,7 @@ struct Emul {
   /* audio-spectrum by-product: where emul_process puts it (emul_bind_audio_spectrum) and the scratch */
   int32_t *bind_ypixel = nullptr;
   float *bind_max_ave = nullptr;
+  uint8_t *bind_spec_frames = nullptr, *bind_audio_frames = nullptr;
   std::vector<float2> aspec;
 };
 
@@ -85,7 +86,9 @@ int emul_process(Emul *e, const float *iq, float *audio, int n_blocks, int row_e
   a.row_every = row_every;
   a.n_rows = row_every > 0 ? (n_blocks + row_every - 1) / row_every : 0;
   a.flags = flags;
-  if (a.n_rows > 0 && (e->bind_ypixel || e->bind_max_ave)) {
+  if (a.n_rows > 0 && e->bind_spec_frames && a.spec_rows) a.spec_frames = e->bind_spec_frames;
+  if (a.n_rows > 0 && (e->bind_ypixel || e->bind_max_ave || e->bind_audio_frames)) {
+    a.audio_frames = e->bind_audio_frames;
     e->aspec.assign((size_t)h.n_streams * a.n_rows * kFft, float2{NAN, NAN});
     a.aspec = e->aspec.data();
     a.audio_ypixel = e->bind_ypixel;
@@ -135,15 +138,20 @@ int emul_process(Emul *e, const float *iq, float *audio, int n_blocks, int row_e
       T41RX_BLOCK_SCHEDULE(EMUL_PHASE)
     }
     EMUL_PHASE(PhStateOut(c, tid));
-    if (a.aspec) {
-      /* t41rx_audio_spectrum_kernel */
+    if (a.aspec || a.spec_frames) {
+      /* t41rx_row_byproducts_kernel */
       c.row = 1;
       c.rows_only = 1;
       for (int i = 0; i < kSmemFloats; ++i) smem[i] = NAN;
       for (int r = 0; r < a.n_rows; ++r) {
         c.t = r * row_every;
         c.row_idx = r;
-        T41RX_AUDIO_SPEC_SCHEDULE(EMUL_PHASE)
+        if (a.aspec) {
+          T41RX_AUDIO_SPEC_SCHEDULE(EMUL_PHASE)
+        }
+        if (a.spec_frames) {
+          T41RX_SPEC_FRAME_SCHEDULE(EMUL_PHASE)
+        }
       }
     }
 #undef EMUL_PHASE
@@ -154,6 +162,11 @@ int emul_process(Emul *e, const float *iq, float *audio, int n_blocks, int row_e
 void emul_bind_audio_spectrum(Emul *e, int32_t *audio_ypixel, float *audio_max_sq_ave) {
   e->bind_ypixel = audio_ypixel;
   e->bind_max_ave = audio_max_sq_ave;
+}
+
+void emul_bind_control_frames(Emul *e, uint8_t *spec_frames, uint8_t *audio_frames) {
+  e->bind_spec_frames = spec_frames;
+  e->bind_audio_frames = audio_frames;
 }
 
 int emul_get_debug(Emul *e, int stream, t41rx_debug *d) {

@@ -51,6 +51,8 @@ def main():
             out[key + "wf"] = r["wf"]
             out[key + "audio_ypixel"] = r["audio_ypixel"].astype(np.int16)      # 0..~200
             out[key + "audio_max_sq_ave"] = r["audio_max_sq_ave"]
+            out[key + "spec_frames"] = r["spec_frames"]                         # control-port writes per row
+            out[key + "audio_frames"] = r["audio_frames"]
             if case.psk:
                 out[key + "psk_bits"] = r["psk_bits"]
                 out[key + "psk_chars"] = r["psk_chars"]

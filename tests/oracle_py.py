@@ -21,6 +21,7 @@ TIER_A_PATH = os.path.join(ORACLE_DIR, "_ref", "libt41ref.so")
 
 DEMOD_USB, DEMOD_LSB, DEMOD_AM, DEMOD_NFM, DEMOD_PSK31, DEMOD_SAM = 0, 1, 2, 3, 5, 8
 BLOCK = 2048
+SPEC_FRAME_BYTES = 518    # specData[], t41Control.cpp:23
 AUDIO_SPEC_PIXELS = 270   # AUDIO_SPEC_BOX_W - 2 (Display.h:45, Process.cpp:555)
 
 
@@ -87,6 +88,8 @@ def tier_b():
         lib.t41o_default_params.argtypes = [C.POINTER(Params)]
         lib.t41o_capture_audio_spectrum.argtypes = [C.c_void_p] * 3
         lib.t41o_capture_audio_spectrum.restype = None
+        lib.t41o_capture_control_frames.argtypes = [C.c_void_p] * 3
+        lib.t41o_capture_control_frames.restype = None
         lib.t41o_smeter_dbm.restype = C.c_float
         lib.t41o_smeter_dbm.argtypes = [C.c_float, C.c_float, C.c_int32, C.c_int32]
         lib.t41o_log10f_fast.restype = C.c_float
@@ -128,17 +131,21 @@ class _StreamBase:
         chars = np.zeros(n, np.uint8) if want_psk else None
         ypix = np.zeros((n_rows, AUDIO_SPEC_PIXELS), np.int32)
         mxave = np.zeros(n_rows, np.float32)
+        frames = np.zeros((n_rows, SPEC_FRAME_BYTES), np.uint8)
+        aframes = np.zeros((n_rows, AUDIO_SPEC_PIXELS), np.uint8)
         self._capture(_ptr(ypix) if n_rows else None, _ptr(mxave) if n_rows else None)
+        self._capture_frames(_ptr(frames) if n_rows else None, _ptr(aframes) if n_rows else None)
         try:
             rc = self._process(_ptr(iq), _ptr(audio), n, row_every, _ptr(spec) if n_rows else None,
                                _ptr(wf) if n_rows else None, _ptr(bits), _ptr(chars))
         finally:
             self._capture(None, None)
+            self._capture_frames(None, None)
         if rc < 0:
             raise RuntimeError("oracle process failed rc=%d" % rc)
         assert rc == n_rows
         return dict(audio=audio, spec=spec, wf=wf, psk_bits=bits, psk_chars=chars, audio_ypixel=ypix,
-                    audio_max_sq_ave=mxave)
+                    audio_max_sq_ave=mxave, spec_frames=frames, audio_frames=aframes)
 
 
 class OracleStream(_StreamBase):
@@ -171,6 +178,9 @@ class OracleStream(_StreamBase):
 
     def _capture(self, ypix, mx):
         self.lib.t41o_capture_audio_spectrum(self.h, ypix, mx)
+
+    def _capture_frames(self, fr, afr):
+        self.lib.t41o_capture_control_frames(self.h, fr, afr)
 
     def tables(self):
         t = Tables()
@@ -206,6 +216,8 @@ class RefStream(_StreamBase):
         lib.t41ref_process.argtypes = [C.c_void_p] * 2 + [C.c_int, C.c_int] + [C.c_void_p] * 4
         lib.t41ref_capture_audio_spectrum.argtypes = [C.c_void_p] * 2
         lib.t41ref_capture_audio_spectrum.restype = None
+        lib.t41ref_capture_control_frames.argtypes = [C.c_void_p] * 2
+        lib.t41ref_capture_control_frames.restype = None
         lib.t41ref_log10f_fast.restype = C.c_float
         lib.t41ref_log10f_fast.argtypes = [C.c_float]
         lib.t41ref_approx_atan2.restype = C.c_float
@@ -226,6 +238,9 @@ class RefStream(_StreamBase):
 
     def _capture(self, ypix, mx):
         self.lib.t41ref_capture_audio_spectrum(ypix, mx)
+
+    def _capture_frames(self, fr, afr):
+        self.lib.t41ref_capture_control_frames(fr, afr)
 
     def tables(self):
         t = Tables()

@@ -36,6 +36,8 @@ class EmulReceiver:
         L.emul_get_debug.argtypes = [C.c_void_p, C.c_int, C.POINTER(rx.Debug)]
         L.emul_bind_audio_spectrum.argtypes = [C.c_void_p] * 3
         L.emul_bind_audio_spectrum.restype = None
+        L.emul_bind_control_frames.argtypes = [C.c_void_p] * 3
+        L.emul_bind_control_frames.restype = None
         self.L = L
         self.n_streams = n_streams
         self.h = L.emul_create(n_streams)
@@ -61,10 +63,14 @@ class EmulReceiver:
         if want_audio_spec and n_rows:
             out["audio_ypixel"] = np.zeros((S, n_rows, rx.AUDIO_SPEC_PIXELS), np.int32)
             out["audio_max_sq_ave"] = np.zeros((S, n_rows), np.float32)
+            out["spec_frames"] = np.zeros((S, n_rows, rx.SPEC_FRAME_BYTES), np.uint8)
+            out["audio_frames"] = np.zeros((S, n_rows, rx.AUDIO_SPEC_PIXELS), np.uint8)
             self.L.emul_bind_audio_spectrum(self.h, p(out["audio_ypixel"]), p(out["audio_max_sq_ave"]))
+            self.L.emul_bind_control_frames(self.h, p(out["spec_frames"]), p(out["audio_frames"]))
         self.L.emul_process(self.h, iq.ctypes.data, out["audio"].ctypes.data, T, row_every, p(out["spec"]),
                             p(out["wf"]), p(out["psk_bits"]), p(out["psk_chars"]), flags)
         self.L.emul_bind_audio_spectrum(self.h, None, None)
+        self.L.emul_bind_control_frames(self.h, None, None)
         return out
 
     def debug(self, stream):
@@ -95,6 +101,8 @@ def run_case_batched(case, engine, flags=0, audio_spec=True):
         if "audio_ypixel" in parts[0]:
             r["audio_ypixel"] = np.concatenate([p["audio_ypixel"][s] for p in parts])
             r["audio_max_sq_ave"] = np.concatenate([p["audio_max_sq_ave"][s] for p in parts])
+            r["spec_frames"] = np.concatenate([p["spec_frames"][s] for p in parts])
+            r["audio_frames"] = np.concatenate([p["audio_frames"][s] for p in parts])
         r["debug"] = engine.debug(s)
         out.append(r)
     return out
@@ -105,6 +113,12 @@ def _check_audio_spec(tag, g, w, exact_max):
     (2 ulp) may move a value sitting on an integer boundary: >= 99.9 % identical, never off by more than 1 (the
     rule SURVEY.md section 8(d) states for the display rows).  audioMaxSquaredAve is plain products, maxima and an
     FP64 average: identical on the bit-exact kernels, 1e-5 relative on the throughput kernel."""
+    if "spec_frames" in g:
+        # the spectrum frame is integer arithmetic on the spectrum row: identical whenever the row is
+        if "spec" not in g or np.array_equal(g["spec"], w["spec"]):
+            assert np.array_equal(g["spec_frames"], w["spec_frames"]), tag + ": spectrum serial frames differ"
+        da = np.abs(g["audio_frames"].astype(np.int64) - w["audio_frames"].astype(np.int64))
+        assert da.size == 0 or (da.max() <= 1 and np.mean(da == 0) >= 0.999), tag + ": audio serial frames differ"
     d = np.abs(g["audio_ypixel"].astype(np.int64) - w["audio_ypixel"].astype(np.int64))
     assert d.size == 0 or d.max() <= 1, tag + ": audio-spectrum pixel off by more than 1"
     assert d.size == 0 or np.mean(d == 0) >= 0.999, tag + ": audio-spectrum rows < 99.9 %% identical (%.5f)" % np.mean(d == 0)

@@ -60,7 +60,10 @@ def test_exact_mode_matches_reference_golden(make):
         assert np.array_equal(r["wf"], golden[key + "wf"]), key
         if case.row_every > 0:
             rx_driver._check_audio_spec(key, r, dict(audio_ypixel=golden[key + "audio_ypixel"],
-                                                     audio_max_sq_ave=golden[key + "audio_max_sq_ave"]), exact_max=True)
+                                                     audio_max_sq_ave=golden[key + "audio_max_sq_ave"],
+                                                     spec_frames=golden[key + "spec_frames"],
+                                                     audio_frames=golden[key + "audio_frames"],
+                                                     spec=golden[key + "spec"]), exact_max=True)
         if case.psk:
             assert np.array_equal(r["psk_bits"], golden[key + "psk_bits"]), key
             assert np.array_equal(r["psk_chars"], golden[key + "psk_chars"]), key
@@ -166,24 +169,37 @@ def test_audio_spectrum_by_product_entry_points():
             d_audio = torch.empty((S, T, 2048), dtype=torch.float32, device="cuda")
             d_pix = torch.full((S, R, rx.AUDIO_SPEC_PIXELS), -7, dtype=torch.int32, device="cuda")
             d_max = torch.full((S, R), -7.0, dtype=torch.float32, device="cuda")
+            d_spec = torch.zeros((S, R, 512), dtype=torch.int16, device="cuda")
+            d_sfr = torch.full((S, R, rx.SPEC_FRAME_BYTES), 9, dtype=torch.uint8, device="cuda")
+            d_afr = torch.full((S, R, rx.AUDIO_SPEC_PIXELS), 9, dtype=torch.uint8, device="cuda")
             eng.bind_audio_spectrum(d_pix.data_ptr(), d_max.data_ptr())
-            eng.process_device(d_iq.data_ptr(), d_audio.data_ptr(), T, row_every=case.row_every, flags=flags)
+            eng.bind_control_frames(d_sfr.data_ptr(), d_afr.data_ptr())
+            with pytest.raises(rx.T41RxError):        # the spectrum frame needs the spectrum rows
+                eng.process_device(d_iq.data_ptr(), d_audio.data_ptr(), T, row_every=case.row_every, flags=flags)
+            eng.process_device(d_iq.data_ptr(), d_audio.data_ptr(), T, row_every=case.row_every,
+                               spec_ptr=d_spec.data_ptr(), flags=flags)
             eng.synchronize()
             eng.bind_audio_spectrum(None, None)
+            eng.bind_control_frames(None, None)
             dev_pix, dev_max = d_pix.cpu().numpy(), d_max.cpu().numpy()
+            assert np.array_equal(d_sfr.cpu().numpy(), host["spec_frames"])
+            assert np.array_equal(d_afr.cpu().numpy(), host["audio_frames"])
             # unbound: a second call leaves the buffers alone
             d_pix.fill_(-7)
             eng.process_device(d_iq.data_ptr(), d_audio.data_ptr(), T, row_every=case.row_every, flags=flags)
             eng.synchronize()
             assert int(d_pix.max()) == -7
         for o in (q15,):
+            assert np.array_equal(o["spec_frames"], host["spec_frames"]) and np.array_equal(o["audio_frames"], host["audio_frames"])
             assert np.array_equal(o["audio_ypixel"], host["audio_ypixel"])
             assert np.array_equal(o["audio_max_sq_ave"].view(np.uint32), host["audio_max_sq_ave"].view(np.uint32))
         assert np.array_equal(dev_pix, host["audio_ypixel"])
         assert np.array_equal(dev_max.view(np.uint32), host["audio_max_sq_ave"].view(np.uint32))
         for s_, w in enumerate(want):
             rx_driver._check_audio_spec("receiver %d flags %d" % (s_, flags),
-                                        dict(audio_ypixel=host["audio_ypixel"][s_], audio_max_sq_ave=host["audio_max_sq_ave"][s_]),
+                                        dict(audio_ypixel=host["audio_ypixel"][s_], audio_max_sq_ave=host["audio_max_sq_ave"][s_],
+                                             spec_frames=host["spec_frames"][s_], audio_frames=host["audio_frames"][s_],
+                                             spec=host["spec"][s_]),
                                         w, exact_max=(flags != 0))
         outs.append(host)
     lib = O.tier_b()

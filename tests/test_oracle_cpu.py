@@ -39,6 +39,8 @@ def test_oracle_matches_reference_golden(make, golden):
         assert np.array_equal(r["wf"], golden[key + "wf"])
         assert np.array_equal(r["audio_ypixel"], golden[key + "audio_ypixel"])
         assert np.array_equal(r["audio_max_sq_ave"].view(np.uint32), golden[key + "audio_max_sq_ave"].view(np.uint32))
+        assert np.array_equal(r["spec_frames"], golden[key + "spec_frames"])
+        assert np.array_equal(r["audio_frames"], golden[key + "audio_frames"])
         if case.psk:
             assert np.array_equal(r["psk_bits"], golden[key + "psk_bits"])
             assert np.array_equal(r["psk_chars"], golden[key + "psk_chars"])
@@ -70,6 +72,8 @@ def test_tier_b_equals_reference_live():
         assert np.array_equal(ra["spec"], rb["spec"]) and np.array_equal(ra["wf"], rb["wf"])
         assert np.array_equal(ra["audio_ypixel"], rb["audio_ypixel"])
         assert np.array_equal(ra["audio_max_sq_ave"].view(np.uint32), rb["audio_max_sq_ave"].view(np.uint32))
+        assert np.array_equal(ra["spec_frames"], rb["spec_frames"])
+        assert np.array_equal(ra["audio_frames"], rb["audio_frames"])
     ta, tb = O.RefStream(case.segments[0][0][0]).tables(), O.OracleStream(case.segments[0][0][0]).tables()
     for k, v in ta.items():
         if isinstance(v, np.ndarray):
