@@ -209,6 +209,18 @@ int t41rx_last_kernel_ms(t41rx_ctx *ctx, float *ms);
  * t41rx_stream_rx_kernel; returns how many were written, or a negative error code. */
 int t41rx_stream_kernel_times(t41rx_ctx *ctx, float *ms, int max_n);
 
+/* The firmware's WAV test-signal reader (Utility.cpp:773-888: load_wav / readWave; 16-bit mono PCM, format chunk of
+ * 16, 18 or 40 bytes), host only.  t41rx_load_wav returns load_wav's own codes: 0, -1 cannot open, -2 format chunk
+ * size, -3 not PCM / mono / 16 bit, -4 more than num_samples samples.  t41rx_read_wave returns 1 with size_buf samples
+ * x / 32768 in buf, or 0 once the reference's end test (byte position + size_buf >= file size) fires; it then closes
+ * the file, like readWave.  Where the reference would convert uninitialised stack (a read running past the end of
+ * the file) the samples are 0. */
+typedef struct t41rx_wav t41rx_wav;
+int t41rx_load_wav(t41rx_wav **out, const char *input_file, uint32_t num_samples);
+int t41rx_read_wave(t41rx_wav *w, float *buf, int size_buf);
+uint32_t t41rx_wav_sample_rate(const t41rx_wav *w);
+void t41rx_wav_close(t41rx_wav *w);
+
 const char *t41rx_last_error(void);
 const char *t41rx_version(void);
 

@@ -479,6 +479,10 @@ void t41ref_capture_control_frames(uint8_t *spec_frame_rows, uint8_t *audio_fram
   controlDataFlag = (spec_frame_rows != 0) || (audio_frame_rows != 0);
 }
 
+/* the reference's WAV reader on a host file (SD.open is backed by stdio in the shim) */
+int t41ref_load_wav(const char *path, uint32_t num_samples) { return load_wav(path, num_samples); }
+int t41ref_read_wave(float *buf, int size_buf) { return readWave(buf, size_buf) ? 1 : 0; }
+
 void t41ref_get_params(t41o_params *p) {
   if (!g_inited) t41ref_init();
   *p = g_prm;

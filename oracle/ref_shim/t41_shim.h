@@ -274,16 +274,28 @@ extern TwoWire Wire1;
 class SPIClass { public: void begin() {} void setMOSI(int) {} void setSCK(int) {} void setMISO(int) {} };
 extern SPIClass SPI;
 
+/* SD-card file: backed by stdio so that the reference's WAV reader (Utility.cpp:773-888) can be run on real files */
 class File : public Print {
  public:
-  operator bool() const { return false; }
+  FILE *fp_ = 0;
+  operator bool() const { return fp_ != 0; }
   int available() { return 0; }
   int read() { return -1; }
-  size_t read(void *, size_t) { return 0; }
-  bool seek(uint32_t) { return false; }
-  uint32_t position() { return 0; }
-  uint32_t size() { return 0; }
-  void close() {}
+  size_t read(void *dst, size_t n) { return fp_ ? fread(dst, 1, n, fp_) : 0; }
+  bool seek(uint32_t pos) { return fp_ && fseek(fp_, (long)pos, SEEK_SET) == 0; }
+  uint32_t position() { return fp_ ? (uint32_t)ftell(fp_) : 0; }
+  uint32_t size() {
+    if (!fp_) return 0;
+    const long here = ftell(fp_);
+    fseek(fp_, 0, SEEK_END);
+    const long n = ftell(fp_);
+    fseek(fp_, here, SEEK_SET);
+    return (uint32_t)n;
+  }
+  void close() {
+    if (fp_) fclose(fp_);
+    fp_ = 0;
+  }
   void flush() {}
   bool isDirectory() { return false; }
   File openNextFile() { return File(); }
@@ -297,7 +309,11 @@ class File : public Print {
 class SDClass {
  public:
   bool begin(int = 0) { return false; }
-  File open(const char *, int = 0) { return File(); }
+  File open(const char *path, int mode = 0) {
+    File f;
+    if (mode == 0 && path) f.fp_ = fopen(path, "rb");      /* FILE_READ only */
+    return f;
+  }
   bool exists(const char *) { return false; }
   bool remove(const char *) { return false; }
   bool mkdir(const char *) { return false; }

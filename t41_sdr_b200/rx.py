@@ -76,6 +76,7 @@ EXPORTS = (
     "t41rx_get_tables", "t41rx_get_debug", "t41rx_design_tables", "t41rx_process", "t41rx_process_q15",
     "t41rx_process_device", "t41rx_synchronize", "t41rx_kernel_launches", "t41rx_last_kernel_ms",
     "t41rx_stream_kernel_times", "t41rx_bind_audio_spectrum", "t41rx_bind_control_frames", "t41rx_smeter_dbm",
+    "t41rx_load_wav", "t41rx_read_wave", "t41rx_wav_sample_rate", "t41rx_wav_close",
     "t41rx_last_error", "t41rx_version")
 
 
@@ -117,6 +118,12 @@ def lib():
         L.t41rx_bind_control_frames.argtypes = [vp, vp, vp]
         L.t41rx_smeter_dbm.argtypes = [C.c_float, C.c_float, C.c_int32, C.c_int32]
         L.t41rx_smeter_dbm.restype = C.c_float
+        L.t41rx_load_wav.argtypes = [C.POINTER(vp), C.c_char_p, C.c_uint32]
+        L.t41rx_read_wave.argtypes = [vp, vp, ip]
+        L.t41rx_wav_sample_rate.argtypes = [vp]
+        L.t41rx_wav_sample_rate.restype = C.c_uint32
+        L.t41rx_wav_close.argtypes = [vp]
+        L.t41rx_wav_close.restype = None
         L.t41rx_last_error.restype = C.c_char_p
         L.t41rx_version.restype = C.c_char_p
         _lib = L
@@ -159,6 +166,28 @@ def smeter_dbm(audio_max_sq_ave, gain_correction=0.0, rf_gain=1, rf_gain_all_ban
 
 def _np_ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class WavReader:
+    """load_wav() / readWave() of the firmware (Utility.cpp:773-888) over t41rx_load_wav / t41rx_read_wave."""
+
+    def __init__(self, path, num_samples):
+        self._h = C.c_void_p()
+        self.rc = lib().t41rx_load_wav(C.byref(self._h), os.fsencode(path), int(num_samples))
+
+    @property
+    def sample_rate(self):
+        return int(lib().t41rx_wav_sample_rate(self._h)) if self._h else 0
+
+    def read(self, size_buf):
+        """float32 [size_buf] or None at the (reference's) end of file"""
+        buf = np.empty(size_buf, np.float32)
+        return buf if self._h and lib().t41rx_read_wave(self._h, _np_ptr(buf), size_buf) else None
+
+    def close(self):
+        if self._h:
+            lib().t41rx_wav_close(self._h)
+            self._h = C.c_void_p()
 
 
 class Receiver:

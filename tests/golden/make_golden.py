@@ -59,6 +59,20 @@ def main():
             d = r["debug"]
             out[key + "debug"] = np.array([float(getattr(d, f)) for f in REF_DEBUG_FIELDS], np.float64)
         print("%-26s receivers=%d blocks=%d" % (case.name, case.n_streams, case.n_blocks))
+    # the firmware's WAV reader (Utility.cpp:773-888) on the files of tests/wav_cases.py
+    import tempfile
+    import wav_cases
+    with tempfile.TemporaryDirectory() as tmp:
+        for name, (data, limit, chunk) in wav_cases.cases().items():
+            p = os.path.join(tmp, name + ".wav")
+            if data is not None:
+                open(p, "wb").write(data)
+            ref = O.RefStream()
+            rc, n, full, tail = wav_cases.run(ref.load_wav, ref.read_wave, p, data, limit, chunk)
+            out["wav/%s/rc_n" % name] = np.array([rc, n], np.int64)
+            out["wav/%s/full" % name] = full
+            out["wav/%s/tail" % name] = tail
+            print("wav %-24s rc=%d reads=%d" % (name, rc, n))
     path = os.path.join(HERE, "ref_vectors.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, "%.1f KiB" % (os.path.getsize(path) / 1024.0))

@@ -218,6 +218,8 @@ class RefStream(_StreamBase):
         lib.t41ref_capture_audio_spectrum.restype = None
         lib.t41ref_capture_control_frames.argtypes = [C.c_void_p] * 2
         lib.t41ref_capture_control_frames.restype = None
+        lib.t41ref_load_wav.argtypes = [C.c_char_p, C.c_uint32]
+        lib.t41ref_read_wave.argtypes = [C.c_void_p, C.c_int]
         lib.t41ref_log10f_fast.restype = C.c_float
         lib.t41ref_log10f_fast.argtypes = [C.c_float]
         lib.t41ref_approx_atan2.restype = C.c_float
@@ -241,6 +243,14 @@ class RefStream(_StreamBase):
 
     def _capture_frames(self, fr, afr):
         self.lib.t41ref_capture_control_frames(fr, afr)
+
+    # the reference's WAV reader (Utility.cpp:773-888) on a host file
+    def load_wav(self, path, num_samples):
+        return self.lib.t41ref_load_wav(os.fsencode(path), int(num_samples))
+
+    def read_wave(self, size_buf):
+        buf = np.empty(size_buf, np.float32)
+        return buf if self.lib.t41ref_read_wave(_ptr(buf), size_buf) else None
 
     def tables(self):
         t = Tables()

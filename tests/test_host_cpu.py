@@ -154,3 +154,49 @@ def test_smeter_helper_matches_oracle():
             assert a == b or (np.isnan(a) and np.isnan(b)) or (np.isinf(a) and a == b), (v, gc, rf, rfall, a, b)
     # the comment in the reference: audioMaxSquaredAve = 40 is about S9 (-73 dBm) on a calibrated band
     assert -80.0 < rx.smeter_dbm(40.0, -2.0, 1, 1) < -50.0
+
+
+def test_wav_reader_matches_reference_golden(tmp_path):
+    """t41rx_load_wav / t41rx_read_wave against what the reference's load_wav / readWave (Utility.cpp:773-888, run
+    from its own translation unit by tests/golden/make_golden.py) returned for the same files: return codes, number
+    of successful reads (the reference's quirky end test included), every sample."""
+    import wav_cases
+    golden = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_vectors.npz"))
+    for name, (data, limit, chunk) in wav_cases.cases().items():
+        p = tmp_path / (name + ".wav")
+        if data is not None:
+            p.write_bytes(data)
+        state = {}
+
+        def load(path, lim):
+            state["w"] = rx.WavReader(path, lim)
+            return state["w"].rc
+
+        rc, n, full, tail = wav_cases.run(load, lambda k: state["w"].read(k), str(p), data, limit, chunk)
+        state["w"].close()
+        assert [rc, n] == list(golden["wav/%s/rc_n" % name]), name
+        assert np.array_equal(full.view(np.uint32), golden["wav/%s/full" % name].view(np.uint32)), name
+        assert np.array_equal(tail.view(np.uint32), golden["wav/%s/tail" % name].view(np.uint32)), name
+    assert list(golden["wav/pcm16_fmt16_chunk128/rc_n"]) == [0, 39]      # 5000 samples = 39 reads of 128 + 8 samples the end test never delivers
+    assert [int(golden["wav/%s/rc_n" % k][0]) for k in ("missing", "fmt20", "stereo", "too_long")] == [-1, -2, -3, -4]
+
+
+@pytest.mark.skipif(not O.tier_a_available(), reason="oracle/_ref/libt41ref.so not built (needs /root/reference)")
+def test_wav_reader_matches_reference_live(tmp_path):
+    import wav_cases
+    for name, (data, limit, chunk) in wav_cases.cases().items():
+        p = tmp_path / (name + ".wav")
+        if data is not None:
+            p.write_bytes(data)
+        ref = O.RefStream()
+        want = wav_cases.run(ref.load_wav, ref.read_wave, str(p), data, limit, chunk)
+        state = {}
+
+        def load(path, lim):
+            state["w"] = rx.WavReader(path, lim)
+            return state["w"].rc
+
+        got = wav_cases.run(load, lambda k: state["w"].read(k), str(p), data, limit, chunk)
+        state["w"].close()
+        assert got[:2] == want[:2], name
+        assert np.array_equal(got[2], want[2]) and np.array_equal(got[3], want[3]), name
