@@ -47,8 +47,8 @@ __global__ void __launch_bounds__(kNT, 8 / kG) t41rx_fused_rx_kernel(const Launc
   __syncthreads();
   for (int t = 0; t < a.n_blocks; ++t) {
     c.t = t;
-    c.row = (a.row_every > 0) && (t % a.row_every == 0);
-    c.row_idx = c.row ? t / a.row_every : 0;
+    c.row = (a.row_every > 0) && ((a.t0 + t) % a.row_every == 0);
+    c.row_idx = c.row ? (a.t0 + t) / a.row_every : 0;
 #ifdef T41RX_PHASE_TIMING
     /* developer build only: cycles per phase of CTA 0 (work and the wait at the barrier) */
     int phase_no = 0;
@@ -91,9 +91,10 @@ __global__ void __launch_bounds__(kNT, 8 / kG) t41rx_rows_kernel(const LaunchArg
   c.row = 1;
   c.rows_only = 1;
   const int tid = threadIdx.x;
-  for (int t = 0; t < a.n_blocks; t += a.row_every) {
+  /* the row-producing blocks of this launch: absolute index a multiple of row_every */
+  for (int t = (a.row_every - a.t0 % a.row_every) % a.row_every; t < a.n_blocks; t += a.row_every) {
     c.t = t;
-    c.row_idx = t / a.row_every;
+    c.row_idx = (a.t0 + t) / a.row_every;
 #define T41RX_KPHASE(stmt) \
   do {                     \
     stmt;                  \
@@ -119,8 +120,9 @@ __global__ void __launch_bounds__(kNT) t41rx_row_byproducts_kernel(const LaunchA
   c.row = 1;
   c.rows_only = 1;
   const int tid = threadIdx.x;
-  for (int r = 0; r < a.n_rows; ++r) {
-    c.t = r * a.row_every;
+  /* the rows of this launch's blocks t0 .. t0 + n_blocks - 1 */
+  for (int r = (a.t0 + a.row_every - 1) / a.row_every; r < a.n_rows && r * a.row_every < a.t0 + a.n_blocks; ++r) {
+    c.t = r * a.row_every - a.t0;
     c.row_idx = r;
 #define T41RX_KPHASE(stmt) \
   do {                     \
@@ -137,11 +139,15 @@ __global__ void __launch_bounds__(kNT) t41rx_row_byproducts_kernel(const LaunchA
   }
 }
 
+/* The two conversions at the edge work on `rows` runs of `width4` 4-element groups, `pitch4` groups apart (a block
+   range of every receiver of a [receiver][block][...] array; pitch4 == width4 for a contiguous range). */
 /* arm_q15_to_float (Process.cpp:107-108): x / 32768, exact in float */
-__global__ void t41rx_q15_to_float_kernel(const short4 *src, float4 *dst, size_t n4) {
+__global__ void t41rx_q15_to_float_kernel(const short4 *src, float4 *dst, size_t rows, size_t width4, size_t pitch4) {
+  const size_t n4 = rows * width4;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-    const short4 v = src[i];
-    dst[i] = float4{(float)v.x / 32768.0f, (float)v.y / 32768.0f, (float)v.z / 32768.0f, (float)v.w / 32768.0f};
+    const size_t o = (i / width4) * pitch4 + (i % width4);
+    const short4 v = src[o];
+    dst[o] = float4{(float)v.x / 32768.0f, (float)v.y / 32768.0f, (float)v.z / 32768.0f, (float)v.w / 32768.0f};
   }
 }
 
@@ -156,10 +162,12 @@ __device__ __forceinline__ short FloatToQ15(float x) {
   q = q < -32768 ? -32768 : q;
   return (short)q;
 }
-__global__ void t41rx_float_to_q15_kernel(const float4 *src, short4 *dst, size_t n4) {
+__global__ void t41rx_float_to_q15_kernel(const float4 *src, short4 *dst, size_t rows, size_t width4, size_t pitch4) {
+  const size_t n4 = rows * width4;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-    const float4 v = src[i];
-    dst[i] = short4{FloatToQ15(v.x), FloatToQ15(v.y), FloatToQ15(v.z), FloatToQ15(v.w)};
+    const size_t o = (i / width4) * pitch4 + (i % width4);
+    const float4 v = src[o];
+    dst[o] = short4{FloatToQ15(v.x), FloatToQ15(v.y), FloatToQ15(v.z), FloatToQ15(v.w)};
   }
 }
 
@@ -189,7 +197,8 @@ static int Fail(int code, const char *fmt, const char *detail = "") {
 /* context                                                             */
 /* ------------------------------------------------------------------ */
 constexpr int kKernelEventRing = 32;
-constexpr int kProcessChunks = 8;   /* receiver chunks of the host-buffer entry point's copy / compute pipeline */
+constexpr int kProcessChunks = 16;  /* most chunks of the host-buffer entry point's copy / compute pipeline (cut over time) */
+constexpr int kReceiverChunks = 8;  /* chunks when a short call is cut over receivers */
 
 struct t41rx_ctx {
   int device = 0;
@@ -528,19 +537,26 @@ int t41rx_get_debug(t41rx_ctx *ctx, int stream, t41rx_debug *d) {
   return T41RX_OK;
 }
 
-/* enqueue the kernels for receivers [first, first + count) of the bank on stream st */
+/* which part of a call a group of launches covers: receivers [first, first + count), blocks [t0, t0 + nt) of the
+   n_blocks the call's buffers hold per receiver */
+struct Span {
+  int first, count, t0, nt;
+};
+
+/* enqueue the kernels for a span of the call on stream st (buffer pointers are those of the whole call) */
 static int LaunchRange(t41rx_ctx *ctx, const float *iq, float *audio, int n_blocks, int row_every,
                        int16_t *spec_rows, uint16_t *wf_rows, int8_t *psk_bits, uint8_t *psk_chars,
-                       uint32_t flags, cudaStream_t st, int first, int count, int32_t *d_ypixel = nullptr,
+                       uint32_t flags, cudaStream_t st, Span sp, int32_t *d_ypixel = nullptr,
                        float *d_max_ave = nullptr, uint8_t *d_sframes = nullptr, uint8_t *d_aframes = nullptr) {
+  const int first = sp.first, count = sp.count;
   LaunchArgs a;
   memset(&a, 0, sizeof(a));
-  a.iq = iq;
-  a.audio = audio;
+  a.iq = iq + (size_t)sp.t0 * 2 * kBlock;
+  a.audio = audio + (size_t)sp.t0 * kBlock;
   a.spec_rows = row_every > 0 ? spec_rows : nullptr;
   a.wf_rows = row_every > 0 ? wf_rows : nullptr;
-  a.psk_bits = psk_bits;
-  a.psk_chars = psk_chars;
+  a.psk_bits = psk_bits ? psk_bits + sp.t0 : nullptr;
+  a.psk_chars = psk_chars ? psk_chars + sp.t0 : nullptr;
   a.cfg = ctx->d_cfg;
   a.st = ctx->d_state;
   a.fsets = ctx->d_fsets;
@@ -554,10 +570,14 @@ static int LaunchRange(t41rx_ctx *ctx, const float *iq, float *audio, int n_bloc
   a.varicode = ctx->d_varicode;
   a.n_streams = count;
   a.stream_base = first;
-  a.n_blocks = n_blocks;
+  a.n_blocks = sp.nt;
+  a.t0 = sp.t0;
+  a.t_stride = n_blocks;
   a.row_every = row_every;
   a.n_rows = row_every > 0 ? (n_blocks + row_every - 1) / row_every : 0;
   a.flags = flags;
+  /* does this block range hold a row-producing block (absolute index a multiple of row_every)? */
+  const bool has_row = row_every > 0 && ((sp.t0 + row_every - 1) / row_every) * row_every < sp.t0 + sp.nt;
   if (a.n_rows > 0 && (d_ypixel || d_max_ave || d_aframes)) {
     a.aspec = (float2 *)ctx->d_aspec;         /* sized by the caller (EnsureAudioSpecScratch) */
     a.audio_ypixel = d_ypixel;
@@ -570,7 +590,7 @@ static int LaunchRange(t41rx_ctx *ctx, const float *iq, float *audio, int n_bloc
   }
   /* the by-product kernel runs after the chain kernels of the range, on the whole (contiguous) range */
   auto audio_spectrum = [&]() -> int {
-    if (!a.aspec && !a.spec_frames) return T41RX_OK;
+    if ((!a.aspec && !a.spec_frames) || !has_row) return T41RX_OK;
     t41rx_row_byproducts_kernel<<<(count + kG - 1) / kG, kNT, kSmemFloats * sizeof(float), st>>>(a);
     CUDA_TRY(cudaGetLastError());
     ctx->launches += 1;
@@ -606,7 +626,7 @@ static int LaunchRange(t41rx_ctx *ctx, const float *iq, float *audio, int n_bloc
     LaunchArgs f = a;
     f.n_streams = f_len;
     f.stream_ids = (p_len > 0) ? ctx->d_fast_ids + f_off : nullptr;     /* no SAM receiver in range: contiguous */
-    if (row_every > 0 && (a.spec_rows || a.wf_rows)) {
+    if (has_row && (a.spec_rows || a.wf_rows)) {
       t41rx_rows_kernel<<<(f_len + kG - 1) / kG, kNT, kSmemFloats * sizeof(float), st>>>(f);
       CUDA_TRY(cudaGetLastError());
       ctx->launches += 1;
@@ -654,8 +674,9 @@ int t41rx_process_device(t41rx_ctx *ctx, const float *iq, float *audio, int n_bl
   if (rc) return rc;
   if ((rc = EnsureAudioSpecScratch(ctx, row_every > 0 ? (size_t)(n_blocks + row_every - 1) / row_every : 0))) return rc;
   CUDA_TRY(cudaEventRecord(ctx->ev0, st));
-  rc = LaunchRange(ctx, iq, audio, n_blocks, row_every, spec_rows, wf_rows, psk_bits, psk_chars, flags, st, 0, ctx->n_streams,
-                   ctx->bind_ypixel, ctx->bind_max_ave, ctx->bind_spec_frames, ctx->bind_audio_frames);
+  rc = LaunchRange(ctx, iq, audio, n_blocks, row_every, spec_rows, wf_rows, psk_bits, psk_chars, flags, st,
+                   Span{0, ctx->n_streams, 0, n_blocks}, ctx->bind_ypixel, ctx->bind_max_ave, ctx->bind_spec_frames,
+                   ctx->bind_audio_frames);
   if (rc) return rc;
   CUDA_TRY(cudaEventRecord(ctx->ev1, st));
   ctx->ev_valid = true;
@@ -743,52 +764,71 @@ static int ProcessHost(t41rx_ctx *ctx, const float *iq, float *audio, const int1
   int32_t *d_ypix = (n_rows && ctx->bind_ypixel) ? (int32_t *)ctx->d_ypixel : nullptr;
   float *d_maxave = (n_rows && ctx->bind_max_ave) ? (float *)ctx->d_max_ave : nullptr;
   if ((rc = RefreshKernelLists(ctx))) return rc;
-  /* receivers are independent: cut the bank into chunks and overlap the copy-in of chunk i+1, the kernels
-     of chunk i and the copy-out of chunk i-1 on three streams (full-duplex host link) */
-  const int n_chunks = (ctx->n_streams >= 8 * kProcessChunks) ? kProcessChunks : 1;
+  /* Cut the call into chunks and overlap the copy-in of chunk i+1, the kernels of chunk i and the copy-out of
+     chunk i-1 on three streams (full-duplex host link).  Long calls are cut over TIME (every receiver, a range of
+     blocks: each launch keeps the whole GPU busy and the last chunk, which nothing overlaps, is short; the state
+     travels between the launches through HBM exactly as between two calls); short calls of a large bank are cut
+     over RECEIVERS (they are independent). */
+  const bool big = S * T >= 2048;                          /* >= 32 MiB of I/Q: below that one chunk, one launch */
+  const bool by_time = big && T >= 16;
+  const int n_chunks = !big ? 1
+                       : by_time ? (int)std::min<size_t>(kProcessChunks, T / 4)
+                                 : ((ctx->n_streams >= 8 * kReceiverChunks) ? kReceiverChunks : 1);
   int16_t *d_spec = need_spec ? (int16_t *)ctx->d_spec : nullptr;
   uint16_t *d_wf = (n_rows && wf_rows) ? (uint16_t *)ctx->d_wf : nullptr;
   int8_t *d_bits = psk_bits ? (int8_t *)ctx->d_bits : nullptr;
   uint8_t *d_chars = psk_chars ? (uint8_t *)ctx->d_chars : nullptr;
   CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+  const size_t blk_iq = 2 * kBlock, blk_audio = kBlock;       /* elements per block */
   for (int ch = 0; ch < n_chunks; ++ch) {
-    const size_t s0 = (size_t)ctx->n_streams * ch / n_chunks, s1 = (size_t)ctx->n_streams * (ch + 1) / n_chunks, n = s1 - s0;
-    const size_t per_iq = T * 2 * kBlock, per_audio = T * kBlock, per_row = n_rows * kSpecRes;
-    if (q15)
-      CUDA_TRY(cudaMemcpyAsync((int16_t *)ctx->d_iq16 + s0 * per_iq, iq16 + s0 * per_iq, n * per_iq * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->copy_in));
-    else
-      CUDA_TRY(cudaMemcpyAsync((float *)ctx->d_iq + s0 * per_iq, iq + s0 * per_iq, n * per_iq * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_in));
+    /* the chunk: receivers [s0, s0 + n) x blocks [t0, t0 + nt) */
+    const size_t s0 = by_time ? 0 : S * ch / n_chunks, n = by_time ? S : S * (ch + 1) / n_chunks - s0;
+    const size_t t0 = by_time ? T * ch / n_chunks : 0, nt = by_time ? T * (ch + 1) / n_chunks - t0 : T;
+    const size_t off_iq = (s0 * T + t0) * blk_iq, off_audio = (s0 * T + t0) * blk_audio;
+    const size_t in_esz = q15 ? sizeof(int16_t) : sizeof(float);
+    const char *h_in = q15 ? (const char *)(iq16 + off_iq) : (const char *)(iq + off_iq);
+    char *d_in = q15 ? (char *)((int16_t *)ctx->d_iq16 + off_iq) : (char *)((float *)ctx->d_iq + off_iq);
+    CUDA_TRY(cudaMemcpy2DAsync(d_in, T * blk_iq * in_esz, h_in, T * blk_iq * in_esz, nt * blk_iq * in_esz, n,
+                               cudaMemcpyHostToDevice, ctx->copy_in));
     CUDA_TRY(cudaEventRecord(ctx->ev_in[ch], ctx->copy_in));
     CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[ch], 0));
     if (q15) {
       t41rx_q15_to_float_kernel<<<2 * ctx->n_sms, 256, 0, ctx->stream>>>(
-          reinterpret_cast<const short4 *>((int16_t *)ctx->d_iq16 + s0 * per_iq), reinterpret_cast<float4 *>((float *)ctx->d_iq + s0 * per_iq), n * per_iq / 4);
+          reinterpret_cast<const short4 *>((int16_t *)ctx->d_iq16 + off_iq), reinterpret_cast<float4 *>((float *)ctx->d_iq + off_iq),
+          n, nt * blk_iq / 4, T * blk_iq / 4);
       CUDA_TRY(cudaGetLastError());
       ctx->launches += 1;
     }
     rc = LaunchRange(ctx, (const float *)ctx->d_iq, (float *)ctx->d_audio, n_blocks, row_every, d_spec, d_wf, d_bits, d_chars,
-                     flags, ctx->stream, (int)s0, (int)n, d_ypix, d_maxave, d_sfr, d_afr);
+                     flags, ctx->stream, Span{(int)s0, (int)n, (int)t0, (int)nt}, d_ypix, d_maxave, d_sfr, d_afr);
     if (rc) return rc;
     if (q15) {
       t41rx_float_to_q15_kernel<<<2 * ctx->n_sms, 256, 0, ctx->stream>>>(
-          reinterpret_cast<const float4 *>((float *)ctx->d_audio + s0 * per_audio), reinterpret_cast<short4 *>((int16_t *)ctx->d_audio16 + s0 * per_audio), n * per_audio / 4);
+          reinterpret_cast<const float4 *>((float *)ctx->d_audio + off_audio), reinterpret_cast<short4 *>((int16_t *)ctx->d_audio16 + off_audio),
+          n, nt * blk_audio / 4, T * blk_audio / 4);
       CUDA_TRY(cudaGetLastError());
       ctx->launches += 1;
     }
     CUDA_TRY(cudaEventRecord(ctx->ev_done[ch], ctx->stream));
     CUDA_TRY(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_done[ch], 0));
-    if (q15)
-      CUDA_TRY(cudaMemcpyAsync(audio16 + s0 * per_audio, (int16_t *)ctx->d_audio16 + s0 * per_audio, n * per_audio * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->copy_out));
-    else
-      CUDA_TRY(cudaMemcpyAsync(audio + s0 * per_audio, (float *)ctx->d_audio + s0 * per_audio, n * per_audio * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_out));
-    if (d_sfr) CUDA_TRY(cudaMemcpyAsync(ctx->bind_spec_frames + s0 * n_rows * kSpecFrameBytes, d_sfr + s0 * n_rows * kSpecFrameBytes, n * n_rows * kSpecFrameBytes, cudaMemcpyDeviceToHost, ctx->copy_out));
-    if (d_afr) CUDA_TRY(cudaMemcpyAsync(ctx->bind_audio_frames + s0 * n_rows * kAudioSpecPixels, d_afr + s0 * n_rows * kAudioSpecPixels, n * n_rows * kAudioSpecPixels, cudaMemcpyDeviceToHost, ctx->copy_out));
-    if (d_spec && spec_rows) CUDA_TRY(cudaMemcpyAsync(spec_rows + s0 * per_row, d_spec + s0 * per_row, n * per_row * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->copy_out));
-    if (d_wf) CUDA_TRY(cudaMemcpyAsync(wf_rows + s0 * per_row, d_wf + s0 * per_row, n * per_row * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->copy_out));
-    if (d_ypix) CUDA_TRY(cudaMemcpyAsync(ctx->bind_ypixel + s0 * n_rows * kAudioSpecPixels, d_ypix + s0 * n_rows * kAudioSpecPixels, n * n_rows * kAudioSpecPixels * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->copy_out));
-    if (d_maxave) CUDA_TRY(cudaMemcpyAsync(ctx->bind_max_ave + s0 * n_rows, d_maxave + s0 * n_rows, n * n_rows * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_out));
-    if (d_bits) CUDA_TRY(cudaMemcpyAsync(psk_bits + s0 * T, d_bits + s0 * T, n * T, cudaMemcpyDeviceToHost, ctx->copy_out));
-    if (d_chars) CUDA_TRY(cudaMemcpyAsync(psk_chars + s0 * T, d_chars + s0 * T, n * T, cudaMemcpyDeviceToHost, ctx->copy_out));
+    const size_t out_esz = q15 ? sizeof(int16_t) : sizeof(float);
+    char *h_out = q15 ? (char *)(audio16 + off_audio) : (char *)(audio + off_audio);
+    const char *d_out = q15 ? (const char *)((int16_t *)ctx->d_audio16 + off_audio) : (const char *)((float *)ctx->d_audio + off_audio);
+    CUDA_TRY(cudaMemcpy2DAsync(h_out, T * blk_audio * out_esz, d_out, T * blk_audio * out_esz, nt * blk_audio * out_esz, n,
+                               cudaMemcpyDeviceToHost, ctx->copy_out));
+    /* the small per-row / per-block outputs of receivers [r0, r0 + rn): with the chunk when cutting over receivers,
+       after the last chunk when cutting over time */
+    if (by_time && ch + 1 < n_chunks) continue;
+    const size_t r0 = by_time ? 0 : s0, rn = by_time ? S : n;
+    const size_t per_row = n_rows * kSpecRes;
+    if (d_sfr) CUDA_TRY(cudaMemcpyAsync(ctx->bind_spec_frames + r0 * n_rows * kSpecFrameBytes, d_sfr + r0 * n_rows * kSpecFrameBytes, rn * n_rows * kSpecFrameBytes, cudaMemcpyDeviceToHost, ctx->copy_out));
+    if (d_afr) CUDA_TRY(cudaMemcpyAsync(ctx->bind_audio_frames + r0 * n_rows * kAudioSpecPixels, d_afr + r0 * n_rows * kAudioSpecPixels, rn * n_rows * kAudioSpecPixels, cudaMemcpyDeviceToHost, ctx->copy_out));
+    if (d_spec && spec_rows) CUDA_TRY(cudaMemcpyAsync(spec_rows + r0 * per_row, d_spec + r0 * per_row, rn * per_row * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->copy_out));
+    if (d_wf) CUDA_TRY(cudaMemcpyAsync(wf_rows + r0 * per_row, d_wf + r0 * per_row, rn * per_row * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->copy_out));
+    if (d_ypix) CUDA_TRY(cudaMemcpyAsync(ctx->bind_ypixel + r0 * n_rows * kAudioSpecPixels, d_ypix + r0 * n_rows * kAudioSpecPixels, rn * n_rows * kAudioSpecPixels * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->copy_out));
+    if (d_maxave) CUDA_TRY(cudaMemcpyAsync(ctx->bind_max_ave + r0 * n_rows, d_maxave + r0 * n_rows, rn * n_rows * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_out));
+    if (d_bits) CUDA_TRY(cudaMemcpyAsync(psk_bits + r0 * T, d_bits + r0 * T, rn * T, cudaMemcpyDeviceToHost, ctx->copy_out));
+    if (d_chars) CUDA_TRY(cudaMemcpyAsync(psk_chars + r0 * T, d_chars + r0 * T, rn * T, cudaMemcpyDeviceToHost, ctx->copy_out));
   }
   CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->ev_valid = true;

@@ -308,7 +308,7 @@ struct RxPair {
   }
 
   __device__ __forceinline__ const float *BlockIq(int t) const {
-    return a.iq + ((size_t)sid * a.n_blocks + t) * (2 * kBlock);
+    return a.iq + ((size_t)sid * a.t_stride + t) * (2 * kBlock);
   }
 
   /* issue this thread's share of the asynchronous copy of quarter q of block t into raw buffer (q & 1) */
@@ -955,8 +955,8 @@ struct RxPair {
     FwdPass<1>(fb, r.tw_b, tau);
     PairSync();
     float2 *arow = nullptr;
-    if (a.aspec && a.row_every > 0 && (t % a.row_every) == 0)
-      arow = a.aspec + ((size_t)sid * a.n_rows + t / a.row_every) * kFft;
+    if (a.aspec && a.row_every > 0 && ((a.t0 + t) % a.row_every) == 0)
+      arow = a.aspec + ((size_t)sid * a.n_rows + (a.t0 + t) / a.row_every) * kFft;
     MidPass(fb, hm, tau, arow);
     PairSync();
     InvPass<1, false>(fb, r.tw_b, tau);
@@ -1201,7 +1201,7 @@ struct RxPair {
       c01[k] = Pack2(hi.y * vol, hi.x * vol);                              /* phases 0, 1: c[4k+3], c[4k+2] */
       c23[k] = Pack2(lo.y * vol, lo.x * vol);                              /* phases 2, 3: c[4k+1], c[4k]   */
     }
-    float4 *dst = reinterpret_cast<float4 *>(a.audio + ((size_t)sid * a.n_blocks + t) * kBlock);
+    float4 *dst = reinterpret_cast<float4 *>(a.audio + ((size_t)sid * a.t_stride + t) * kBlock);
 #pragma unroll 1
     for (int rr = 0; rr < 2; ++rr) {
       const int n0 = 4 * tau + 256 * rr;
@@ -1364,7 +1364,7 @@ struct RxPair {
       }
       st.psk_block_count++;
     }
-    const size_t o = (size_t)sid * a.n_blocks + t;
+    const size_t o = (size_t)sid * a.t_stride + t;
     if (a.psk_bits) a.psk_bits[o] = bit_out;
     if (a.psk_chars) a.psk_chars[o] = char_out;
   }

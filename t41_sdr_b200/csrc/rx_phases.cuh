@@ -116,6 +116,10 @@ struct LaunchArgs {
   const uint16_t *gradient;   /* 117 */
   const uint32_t *varicode;   /* 128: code | bits << 16 | ascii << 24 */
   int n_streams, n_blocks, row_every, n_rows;   /* n_streams: receivers this launch works on */
+  /* a call may be cut into launches over block ranges: this launch covers blocks t0 .. t0 + n_blocks - 1 of a call
+     whose buffers hold t_stride blocks per receiver (iq / audio / psk pointers are already offset by t0; row_every,
+     n_rows and the row outputs refer to the whole call) */
+  int t0, t_stride;
   uint32_t flags;
   const int32_t *stream_ids;  /* receiver index of each of them, or NULL for stream_base .. stream_base + n_streams-1 */
   int stream_base;
@@ -340,7 +344,7 @@ T41RX_DEV void PhLoad(Cta &c, int tid) {
     for (int gg = 0; gg < 2; ++gg) {
       if (g0 + gg >= c.ng) continue;
       const float4 *src = reinterpret_cast<const float4 *>(
-          c.a.iq + ((size_t)(Sid(c, g0 + gg)) * c.a.n_blocks + c.t) * (2 * kBlock));
+          c.a.iq + ((size_t)(Sid(c, g0 + gg)) * c.a.t_stride + c.t) * (2 * kBlock));
 #pragma unroll
       for (int k = 0; k < kPer; ++k) v[gg][k] = LdgRO(src + tid + kNT * k);
     }
@@ -366,7 +370,7 @@ T41RX_DEV void PhLoad(Cta &c, int tid) {
     }
     if (c.t + 1 < c.a.n_blocks) {
       const char *nxt = reinterpret_cast<const char *>(
-          c.a.iq + ((size_t)(Sid(c, g)) * c.a.n_blocks + c.t + 1) * (2 * kBlock));
+          c.a.iq + ((size_t)(Sid(c, g)) * c.a.t_stride + c.t + 1) * (2 * kBlock));
       for (int line = tid; line < (2 * kBlock * 4) / 128; line += kNT) PrefetchL2(nxt + 128 * line);
     }
   }
@@ -538,7 +542,7 @@ T41RX_DEV void PhDcFix(Cta &c, int tid) {
       break;
   }
   if (bad >= kDcChunks) return;
-  const float *src = c.a.iq + ((size_t)(Sid(c, g)) * c.a.n_blocks + c.t) * (2 * kBlock);
+  const float *src = c.a.iq + ((size_t)(Sid(c, g)) * c.a.t_stride + c.t) * (2 * kBlock);
   float d1 = s[oMisc + mDcEnd + 2 * (bad - 1)];
   float d2 = s[oMisc + mDcEnd + 2 * (bad - 1) + 1];
   for (int i = bad * kDcChunkLen; i < 2 * kBlock; ++i)
@@ -1102,8 +1106,8 @@ T41RX_DEV void PhMask(Cta &c, int tid) {
   const float2 *mask = reinterpret_cast<const float2 *>(c.a.fsets[cf.filter_id].mask);
   /* (the display rows of this block may come from the rows-only kernel: c.row is not the test here) */
   float2 *arow = nullptr;
-  if (c.a.aspec && c.a.row_every > 0 && (c.t % c.a.row_every) == 0)
-    arow = c.a.aspec + ((size_t)Sid(c, g) * c.a.n_rows + c.t / c.a.row_every) * kFft;
+  if (c.a.aspec && c.a.row_every > 0 && ((c.a.t0 + c.t) % c.a.row_every) == 0)
+    arow = c.a.aspec + ((size_t)Sid(c, g) * c.a.n_rows + (c.a.t0 + c.t) / c.a.row_every) * kFft;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int k = u + 64 * j;
@@ -1447,11 +1451,11 @@ T41RX_DEV void PhDemodSerial(Cta &c, int tid) {
       st.psk_shr = shr;
     }
     st.psk_block_count++;
-    const size_t o = (size_t)(Sid(c, g)) * c.a.n_blocks + c.t;
+    const size_t o = (size_t)(Sid(c, g)) * c.a.t_stride + c.t;
     if (c.a.psk_bits) c.a.psk_bits[o] = bit_out;
     if (c.a.psk_chars) c.a.psk_chars[o] = char_out;
   } else {
-    const size_t o = (size_t)(Sid(c, g)) * c.a.n_blocks + c.t;
+    const size_t o = (size_t)(Sid(c, g)) * c.a.t_stride + c.t;
     if (c.a.psk_bits) c.a.psk_bits[o] = -1;
     if (c.a.psk_chars) c.a.psk_chars[o] = 0;
   }
@@ -1501,7 +1505,7 @@ T41RX_DEV void PhInterp2(Cta &c, int tid) {
   if (g >= c.ng) return;
   float *s = Slot(c, g);
   const float volume = c.a.cfg[Sid(c, g)].volume;
-  float4 *dst = reinterpret_cast<float4 *>(c.a.audio + ((size_t)(Sid(c, g)) * c.a.n_blocks + c.t) * kBlock);
+  float4 *dst = reinterpret_cast<float4 *>(c.a.audio + ((size_t)(Sid(c, g)) * c.a.t_stride + c.t) * kBlock);
   for (int h = u; h < 23; h += 64) s[oIntH + h] = s[vAud + kDec + h];   /* int1 history for the next block */
   float taps[kInt2Taps];
 #pragma unroll
@@ -1563,14 +1567,14 @@ T41RX_DEV void PhRowDcSeed(Cta &c, int tid) {
   if (g < 0) return;
   float *s = Slot(c, g);
   const StreamState &st = c.a.st[Sid(c, g)];
-  if (c.t == 0) {
+  if (c.a.t0 + c.t == 0) {       /* first block of the call (a later launch of a call cut over time finds block t0 - 1 in the buffer) */
     s[oMisc + mDcD1] = st.dc_d1;
     s[oMisc + mDcD2] = st.dc_d2;
     return;
   }
   const DcCoef k = DcCoefs();
   const float rfg = c.a.cfg[Sid(c, g)].rf_gain_value;
-  const float *q = c.a.iq + ((size_t)Sid(c, g) * c.a.n_blocks + (c.t - 1)) * (2 * kBlock) + 2 * (kBlock - kDcWarm) + 1;
+  const float *q = c.a.iq + ((size_t)Sid(c, g) * c.a.t_stride + (c.t - 1)) * (2 * kBlock) + 2 * (kBlock - kDcWarm) + 1;
   float d1 = 0.0f, lx = 0.0f, ly = 0.0f;
   for (int i = 0; i < kDcWarm; ++i) {
     const float x = LdgRO(q + 2 * i) * rfg;
@@ -1587,11 +1591,11 @@ constexpr int vRowTail = oOla;                    /* 256 floats: last Q samples 
 
 /* stage the 256 samples PhRowDcSeed filters (coalesced instead of 256 dependent global loads) */
 T41RX_DEV void PhRowTailLoad(Cta &c, int tid) {
-  if (c.t == 0) return;
+  if (c.a.t0 + c.t == 0) return;
   const int g = tid >> 6, u = tid & 63;
   if (g >= c.ng) return;
   float *s = Slot(c, g);
-  const float2 *q = reinterpret_cast<const float2 *>(c.a.iq + ((size_t)Sid(c, g) * c.a.n_blocks + (c.t - 1)) * (2 * kBlock)) + (kBlock - kDcWarm);
+  const float2 *q = reinterpret_cast<const float2 *>(c.a.iq + ((size_t)Sid(c, g) * c.a.t_stride + (c.t - 1)) * (2 * kBlock)) + (kBlock - kDcWarm);
   for (int i = u; i < kDcWarm; i += 64) s[vRowTail + i] = LdgRO(q + i).y;
 }
 T41RX_DEV void PhRowDcSeedFast(Cta &c, int tid) {
@@ -1599,7 +1603,7 @@ T41RX_DEV void PhRowDcSeedFast(Cta &c, int tid) {
   if (g < 0) return;
   float *s = Slot(c, g);
   const StreamState &st = c.a.st[Sid(c, g)];
-  if (c.t == 0) {
+  if (c.a.t0 + c.t == 0) {       /* first block of the call (a later launch of a call cut over time finds block t0 - 1 in the buffer) */
     s[oMisc + mDcD1] = st.dc_d1;
     s[oMisc + mDcD2] = st.dc_d2;
     return;

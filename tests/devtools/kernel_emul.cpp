@@ -85,6 +85,8 @@ int emul_process(Emul *e, const float *iq, float *audio, int n_blocks, int row_e
   a.n_blocks = n_blocks;
   a.row_every = row_every;
   a.n_rows = row_every > 0 ? (n_blocks + row_every - 1) / row_every : 0;
+  a.t0 = 0;
+  a.t_stride = n_blocks;
   a.flags = flags;
   if (a.n_rows > 0 && e->bind_spec_frames && a.spec_rows) a.spec_frames = e->bind_spec_frames;
   if (a.n_rows > 0 && (e->bind_ypixel || e->bind_max_ave || e->bind_audio_frames)) {

@@ -267,6 +267,47 @@ def test_c2_full_size_1024_receivers():
     assert np.array_equal(p.view(np.uint32), audio[perm].view(np.uint32))
 
 
+def test_host_pipeline_chunking_is_invisible():
+    """t41rx_process cuts a long call into launches over block ranges (copy / compute / copy-back pipeline); the
+    result must be the one launch of t41rx_process_device, bit for bit: audio, rows whose period (5) does not
+    divide the chunk length (4), by-products, PSK31 bits, end state."""
+    torch = pytest.importorskip("torch")
+    S, T, D, every = 64, 64, 16, 5
+    base_p, base_iq, params, iq = _c2_bank(S, T, D)
+    for p in params:
+        p.psk31_enable = 1
+        p.spectrum_zoom = 2
+    R = (T + every - 1) // every
+    with _receiver(S) as eng:
+        eng.set_params_each(params)
+        n0 = eng.kernel_launches()
+        host = eng.process(iq, row_every=every, want_psk=True, want_audio_spec=True)
+        assert eng.kernel_launches() - n0 >= 16           # really cut into chunks
+        dbg_host = [eng.debug(s) for s in (0, 1, S - 1)]
+    with _receiver(S) as eng:
+        eng.set_params_each(params)
+        d = {k: torch.zeros(shape, dtype=dt, device="cuda") for k, shape, dt in (
+            ("audio", (S, T, 2048), torch.float32), ("spec", (S, R, 512), torch.int16), ("wf", (S, R, 512), torch.int16),
+            ("bits", (S, T), torch.int8), ("chars", (S, T), torch.uint8), ("pix", (S, R, rx.AUDIO_SPEC_PIXELS), torch.int32),
+            ("mx", (S, R), torch.float32), ("sfr", (S, R, rx.SPEC_FRAME_BYTES), torch.uint8),
+            ("afr", (S, R, rx.AUDIO_SPEC_PIXELS), torch.uint8))}
+        d_iq = torch.from_numpy(iq).cuda()
+        eng.bind_audio_spectrum(d["pix"].data_ptr(), d["mx"].data_ptr())
+        eng.bind_control_frames(d["sfr"].data_ptr(), d["afr"].data_ptr())
+        eng.process_device(d_iq.data_ptr(), d["audio"].data_ptr(), T, row_every=every, spec_ptr=d["spec"].data_ptr(),
+                           wf_ptr=d["wf"].data_ptr(), psk_bits_ptr=d["bits"].data_ptr(), psk_chars_ptr=d["chars"].data_ptr())
+        eng.synchronize()
+        dbg_dev = [eng.debug(s) for s in (0, 1, S - 1)]
+    pairs = (("audio", "audio"), ("spec", "spec"), ("wf", "wf"), ("psk_bits", "bits"), ("psk_chars", "chars"),
+             ("audio_ypixel", "pix"), ("audio_max_sq_ave", "mx"), ("spec_frames", "sfr"), ("audio_frames", "afr"))
+    for hk, dk in pairs:
+        dev = d[dk].cpu().numpy()
+        assert np.array_equal(host[hk].view(np.uint8), dev.view(np.uint8)), hk
+    for a_, b_ in zip(dbg_host, dbg_dev):
+        assert bytes(a_) == bytes(b_)
+    assert host["spec_frames"][:, :, 0].min() == ord("F") and np.abs(host["audio"]).max() > 1e-3
+
+
 def test_receivers_per_cta_invariance(monkeypatch):
     """The throughput kernel's result for a receiver must not depend on how many receivers share its CTA (which
     decides which AGC lane and which shared-memory slot it gets, and how the warps interleave): a race between the
