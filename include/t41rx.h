@@ -84,6 +84,8 @@ typedef struct t41rx_params {
   int32_t psk31_enable;         /* DBPSK + varicode tap on the filtered stream (psk31.cpp:235-310)    */
   float iq_amp_correction;      /* IQAmpCorrectionFactor[band]    Process.cpp:166,171                 */
   float iq_phase_correction;    /* IQPhaseCorrectionFactor[band]  Process.cpp:167,172                 */
+  int32_t receive_eq_flag;      /* receiveEQFlag (ON = 1)         Process.cpp:827-831                 */
+  int32_t equalizer_rec[14];    /* EEPROMData.equalizerRec[] 0..100 (default 100)  Filter.cpp:117-165 */
 } t41rx_params;
 
 /* Discrete / scalar DSP state for state-transition parity checks. */

@@ -287,6 +287,11 @@ int t41ref_init(void) {
   g_prm.psk31_enable = 0;
   g_prm.iq_amp_correction = IQAmpCorrectionFactor[currentBand];
   g_prm.iq_phase_correction = IQPhaseCorrectionFactor[currentBand];
+  g_prm.receive_eq_flag = 0;
+  for (int i = 0; i < 14; i++) {
+    EEPROMData.equalizerRec[i] = 100;       /* EEPROM.cpp:59,698 */
+    g_prm.equalizer_rec[i] = 100;
+  }
   g_last_set_rf_gain = g_prm.rf_gain;
 
   CalcCplxFIRCoeffs(FIR_Coef_I, FIR_Coef_Q, m_NumTaps, (float32_t)bands[currentBand].FLoCut,
@@ -371,6 +376,8 @@ int t41ref_set_params(const t41o_params *p) {
   nfmFilterBW = p->nfm_filter_bw;
   IQAmpCorrectionFactor[currentBand] = p->iq_amp_correction;
   IQPhaseCorrectionFactor[currentBand] = p->iq_phase_correction;
+  receiveEQFlag = p->receive_eq_flag;
+  for (int i = 0; i < 14; i++) EEPROMData.equalizerRec[i] = p->equalizer_rec[i];
   if (p->mode != old.mode || p->f_lo_cut != old.f_lo_cut || p->f_hi_cut != old.f_hi_cut) CalcFilters();
   if (p->agc_mode != old.agc_mode || p->agc_thresh != old.agc_thresh) {
     AGCMode = p->agc_mode;

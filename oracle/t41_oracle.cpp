@@ -329,6 +329,9 @@ struct t41o_stream {
   arm_fir_decimate_instance_f32 zoom_fir_i, zoom_fir_q;
   float zoom_ring_x[kSpecRes], zoom_ring_y[kSpecRes];
   int zoom_sample_ptr;
+  /* receive equaliser, T41/Filter.cpp:43-72 */
+  float eq_state[14][8];
+  arm_biquad_cascade_df2T_instance_f32 eq[14];
   /* audio-spectrum by-product, T41/Process.cpp:32-34 */
   float audio_max_sq_ave;
   int audio_ypixel[T41O_AUDIO_SPEC_PIXELS];
@@ -736,6 +739,7 @@ void InitStream(t41o_stream *s) {
   s->last_set_rf_gain = s->prm.rf_gain;
   s->rf_gain = s->prm.rf_gain;
   s->osc_vect_q = 1.0;
+  for (int i = 0; i < 14; i++) arm_biquad_cascade_df2T_init_f32(&s->eq[i], 4, t41o_eq_coeffs[i], s->eq_state[i]);
   s->osc_vect_i = 0.0;
   s->first_block = 1;
   s->agc_out_index = -1;
@@ -804,6 +808,8 @@ void t41o_default_params(t41o_params *p) {
   p->psk31_enable = 0;
   p->iq_amp_correction = 1.0f;    /* T41/gwv.cpp:70-71 */
   p->iq_phase_correction = 0.0f;
+  p->receive_eq_flag = 0;
+  for (int i = 0; i < 14; i++) p->equalizer_rec[i] = 100;   /* T41/EEPROM.cpp:59,698 */
 }
 
 void t41o_mode_default_cuts(int32_t mode, int32_t *f_lo_cut, int32_t *f_hi_cut) {
@@ -885,6 +891,20 @@ void t41o_get_debug(const t41o_stream *s, t41o_debug *d) {
   d->am_wold = s->am_wold;
   d->osc_vect_q = s->osc_vect_q;
   d->osc_vect_i = s->osc_vect_i;
+}
+
+/* T41/Filter.cpp:117-165 DoReceiveEQ: the 256 demodulated samples through 14 third-octave band-pass cascades
+   (4 DF2T biquads each, T41/FIR.cpp:279-371), bands scaled by -/+ equalizerRec / 100 alternately and added in band
+   order */
+static void ReceiveEq(t41o_stream *s) {
+  float *L = s->bufL;
+  float band[14][kDec];
+  float scale[14];
+  for (int i = 0; i < 14; i++) scale[i] = (float)s->prm.equalizer_rec[i] / 100.0;
+  for (int i = 0; i < 14; i++) arm_biquad_cascade_df2T_f32(&s->eq[i], L, band[i], kDec);
+  for (int i = 0; i < 14; i++) arm_scale_f32(band[i], (i & 1) ? scale[i] : -scale[i], band[i], kDec);
+  arm_add_f32(band[0], band[1], L, kDec);
+  for (int i = 2; i < 14; i++) arm_add_f32(L, band[i], L, kDec);
 }
 
 /* Arduino map() with a float first argument, as the Teensyduino core overloads it (cores/teensy4/wiring.h; the
@@ -1090,6 +1110,9 @@ int t41o_process_block(t41o_stream *s, const float *iq, float *audio, int update
     }
     memcpy(s->sent_audio, s->spec_data, T41O_AUDIO_SPEC_PIXELS);
   }
+
+  /* T41/Process.cpp:827-831 */
+  if (s->prm.receive_eq_flag == 1) ReceiveEq(s);
 
   /* T41/Process.cpp:917-920 */
   arm_fir_interpolate_f32(&s->int1, L, s->ifft_buf, kDec);

@@ -52,6 +52,8 @@ typedef struct t41o_params {
   int32_t psk31_enable;         /* harness-defined DBPSK+varicode tap */
   float iq_amp_correction;      /* IQAmpCorrectionFactor[band], default 1         */
   float iq_phase_correction;    /* IQPhaseCorrectionFactor[band], default 0       */
+  int32_t receive_eq_flag;      /* receiveEQFlag, default 0 (OFF)                 */
+  int32_t equalizer_rec[14];    /* EEPROMData.equalizerRec[], default 100 each    */
 } t41o_params;
 
 typedef struct t41o_debug {

@@ -225,12 +225,14 @@ struct t41rx_ctx {
   double *d_hann = nullptr;
   float *d_sin = nullptr;
   float *d_zoom_iir = nullptr;
+  float *d_eq_coeffs = nullptr;
   float *d_sam = nullptr;
   uint16_t *d_gradient = nullptr;
   uint32_t *d_varicode = nullptr;
 
   /* receivers by kernel: the SAM PLL is chaotic while it acquires lock, so SAM receivers stay on the
-     bit-exact kernel; everything else runs on the throughput kernel */
+     bit-exact kernel, and so do receivers with the receive equaliser on (its 56 biquads exist only there so far);
+     everything else runs on the throughput kernel */
   std::vector<int32_t> h_fast_ids, h_phased_ids;
   int32_t *d_fast_ids = nullptr, *d_phased_ids = nullptr;
   bool ids_dirty = true;
@@ -288,6 +290,7 @@ static int UploadConstTables(t41rx_ctx *ctx) {
   if ((rc = UploadConst(&ctx->d_hann, h.hann))) return rc;
   if ((rc = UploadConst(&ctx->d_sin, h.sin_table))) return rc;
   if ((rc = UploadConst(&ctx->d_zoom_iir, h.zoom_iir))) return rc;
+  if ((rc = UploadConst(&ctx->d_eq_coeffs, h.eq_coeffs))) return rc;
   if ((rc = UploadConst(&ctx->d_sam, h.sam_consts))) return rc;
   if ((rc = UploadConst(&ctx->d_gradient, h.gradient))) return rc;
   if ((rc = UploadConst(&ctx->d_varicode, h.varicode))) return rc;
@@ -328,7 +331,7 @@ void t41rx_destroy(t41rx_ctx *ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   void *bufs[] = {ctx->d_cfg, ctx->d_state, ctx->d_fsets, ctx->d_nco_tab, ctx->d_twiddle, ctx->d_hann, ctx->d_sin,
-                  ctx->d_zoom_iir, ctx->d_sam, ctx->d_gradient, ctx->d_varicode, ctx->d_iq, ctx->d_audio,
+                  ctx->d_zoom_iir, ctx->d_eq_coeffs, ctx->d_sam, ctx->d_gradient, ctx->d_varicode, ctx->d_iq, ctx->d_audio,
                   ctx->d_spec, ctx->d_wf, ctx->d_bits, ctx->d_chars, ctx->d_fast_ids, ctx->d_phased_ids,
                   ctx->d_iq16, ctx->d_audio16, ctx->d_aspec, ctx->d_ypixel, ctx->d_max_ave,
                   ctx->d_sframes, ctx->d_aframes};
@@ -565,6 +568,7 @@ static int LaunchRange(t41rx_ctx *ctx, const float *iq, float *audio, int n_bloc
   a.hann = ctx->d_hann;
   a.sin_table = ctx->d_sin;
   a.zoom_iir = ctx->d_zoom_iir;
+  a.eq_coeffs = ctx->d_eq_coeffs;
   a.sam_consts = ctx->d_sam;
   a.gradient = ctx->d_gradient;
   a.varicode = ctx->d_varicode;
@@ -653,7 +657,7 @@ static int RefreshKernelLists(t41rx_ctx *ctx) {
   ctx->h_fast_ids.clear();
   ctx->h_phased_ids.clear();
   for (int s = 0; s < ctx->n_streams; ++s)
-    (ctx->host.cfg[s].mode == kModeSam ? ctx->h_phased_ids : ctx->h_fast_ids).push_back(s);
+    ((ctx->host.cfg[s].mode == kModeSam || ctx->host.cfg[s].eq_on) ? ctx->h_phased_ids : ctx->h_fast_ids).push_back(s);
   CUDA_TRY(cudaDeviceSynchronize());
   if (!ctx->h_fast_ids.empty())
     CUDA_TRY(cudaMemcpy(ctx->d_fast_ids, ctx->h_fast_ids.data(), sizeof(int32_t) * ctx->h_fast_ids.size(), cudaMemcpyHostToDevice));

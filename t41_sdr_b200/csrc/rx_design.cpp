@@ -247,6 +247,11 @@ void DesignStreamCfg(const t41rx_params &p, const AgcConsts &agc, int filter_id,
   c->pixel_add = t41rx_base_offset[p.current_scale] + (int16_t)p.pixel_offset;
   c->wf_base = p.spectrum_noise_floor - p.current_nf;
   c->current_nf = p.current_nf;
+  c->eq_on = (p.receive_eq_flag == 1) ? 1 : 0;                       /* Process.cpp:828 */
+  for (int i = 0; i < 14; ++i) {                                     /* Filter.cpp:118-120,136-149 */
+    const float level = (float)p.equalizer_rec[i] / 100.0;
+    c->eq_scale[i] = (i & 1) ? level : -level;
+  }
   int zs = kBlock / (1 << p.spectrum_zoom);
   if (zs > kSpecRes) zs = kSpecRes;
   c->zoom_samples = zs;

@@ -30,6 +30,8 @@ void DefaultParams(t41rx_params *p) {
   p->psk31_enable = 0;
   p->iq_amp_correction = 1.0f;    /* gwv.cpp:70 */
   p->iq_phase_correction = 0.0f;  /* gwv.cpp:71 */
+  p->receive_eq_flag = 0;         /* OFF */
+  for (int i = 0; i < 14; ++i) p->equalizer_rec[i] = 100;   /* EEPROM.cpp:59,698 */
 }
 
 void HostStateInit(StreamState *st) {
@@ -65,6 +67,7 @@ void HostModel::Init(int n) {
   sin_table[256] = 0.0f;
   sin_table[512] = 0.0f;
   zoom_iir.assign(&t41rx_zoom_iir[0][0], &t41rx_zoom_iir[0][0] + 80);
+  eq_coeffs.assign(&t41rx_eq_coeffs[0][0], &t41rx_eq_coeffs[0][0] + 280);
   {
     /* SAM PLL constants, Demod.cpp:13-18 with omegaN = 200, pll_fmax = 4000 (gwv.cpp:64-65);
        exp() of a float argument is the single-precision overload under ISO C++ */

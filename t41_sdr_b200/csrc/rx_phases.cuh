@@ -91,6 +91,10 @@ constexpr int vDem = 256;                         /* 256 complex AGC output -> 7
 constexpr int vAud = 768;                         /* int1 state: 23 history + 256 -> 1047 */
 constexpr int vAmTmp = 1056;                      /* 256 */
 constexpr int vInt2 = 1312;                       /* int2 state: 7 history + 512 -> 1831 */
+/* receive equaliser, between the demodulator and the interpolators: 14 band outputs of 256 samples; bands 0..11
+   behind the audio buffer (over vAmTmp / vInt2, dead at that point), bands 12 and 13 in the D1 region */
+constexpr int vEqBand = 1056;
+static_assert(vEqBand + 12 * kDec <= 2 * kRawLen, "equaliser bands fit the raw region");
 /* spectrum scratch (row blocks, before dec1): the D1 region */
 constexpr int vSpecFft = oD1I;                    /* 512 complex = 1024 floats <= 1120 */
 
@@ -112,6 +116,7 @@ struct LaunchArgs {
   const double *hann;         /* 512: 0.5 - 0.5*cos(6.28*i/512) */
   const float *sin_table;     /* 513: sin(2*pi*k/512), arm_sin_f32's table */
   const float *zoom_iir;      /* 4 x 20: zoom x2..x16 biquad coefficients (FIR.cpp:582-885) */
+  const float *eq_coeffs;     /* 14 x 20: receive-equaliser band-pass biquads (FIR.cpp:279-371) */
   const float *sam_consts;    /* omega_min, omega_max, g1, g2 (Demod.cpp:13-18) */
   const uint16_t *gradient;   /* 117 */
   const uint32_t *varicode;   /* 128: code | bits << 16 | ascii << 24 */
@@ -1465,6 +1470,63 @@ T41RX_DEV void PhDemodSerial(Cta &c, int tid) {
 /* P14/P15: arm_fir_interpolate_f32 x2 (48 taps) and x4 (32 taps), volume */
 /* (Process.cpp:917-931)                                                 */
 /* ------------------------------------------------------------------ */
+/* ------------------------------------------------------------------ */
+/* receive equaliser (Filter.cpp:117-165, hook Process.cpp:827-831)      */
+/* ------------------------------------------------------------------ */
+T41RX_DEV float *EqBand(float *s, int band) { return s + (band < 12 ? vEqBand + kDec * band : oD1I + kDec * (band - 12)); }
+
+/* one lane per (receiver, band): the band's 4-stage transposed-direct-form-II cascade over the 256 demodulated
+   samples, arm_biquad_cascade_df2T_f32's operation order (y = b0 x + d1; d1 = (b1 x + a1 y) + d2; d2 = b2 x + a2 y),
+   all four stages per sample in registers (each stage sees the same input sequence as stage-by-stage order) */
+T41RX_DEV void PhEqBands(Cta &c, int tid) {
+  const int g = tid >> 6, u = tid & 63;
+  if (g >= c.ng || u >= 14) return;
+  const int sid = Sid(c, g);
+  if (!c.a.cfg[sid].eq_on) return;
+  float *s = Slot(c, g);
+  StreamState &st = c.a.st[sid];
+  const float *k = c.a.eq_coeffs + 20 * u;
+  float b0[4], b1[4], b2[4], a1[4], a2[4], d1[4], d2[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    b0[j] = LdgRO(k + 5 * j); b1[j] = LdgRO(k + 5 * j + 1); b2[j] = LdgRO(k + 5 * j + 2);
+    a1[j] = LdgRO(k + 5 * j + 3); a2[j] = LdgRO(k + 5 * j + 4);
+    d1[j] = st.eq_state[u][2 * j]; d2[j] = st.eq_state[u][2 * j + 1];
+  }
+  const float *x = s + vAud + 23;
+  float *out = EqBand(s, u);
+  for (int n = 0; n < kDec; ++n) {
+    float v = x[n];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float y = b0[j] * v + d1[j];
+      const float t = b1[j] * v + a1[j] * y;
+      d1[j] = t + d2[j];
+      d2[j] = b2[j] * v + a2[j] * y;
+      v = y;
+    }
+    out[n] = v;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { st.eq_state[u][2 * j] = d1[j]; st.eq_state[u][2 * j + 1] = d2[j]; }
+}
+
+/* bands scaled by -/+ level (arm_scale_f32) and added in band order (arm_add_f32 chain, Filter.cpp:151-164) */
+T41RX_DEV void PhEqSum(Cta &c, int tid) {
+  const int g = tid >> 6, u = tid & 63;
+  if (g >= c.ng) return;
+  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+  if (!cf.eq_on) return;
+  float *s = Slot(c, g);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int n = u + 64 * r;
+    float acc = EqBand(s, 0)[n] * cf.eq_scale[0] + EqBand(s, 1)[n] * cf.eq_scale[1];
+    for (int b = 2; b < 14; ++b) acc = acc + EqBand(s, b)[n] * cf.eq_scale[b];
+    s[vAud + 23 + n] = acc;
+  }
+}
+
 T41RX_DEV void PhInterp1(Cta &c, int tid) {
   for (int g = 0; g < c.ng; ++g) {
     float *s = Slot(c, g);
@@ -2042,6 +2104,8 @@ T41RX_DEV void PhSpecFrameWrite(Cta &c, int tid) {
   RX_PHASE(PhAgcPost(c, tid));                                           \
   RX_PHASE(PhDemodParallel(c, tid); PhInterp1(c, tid));                  \
   RX_PHASE(PhDemodSerial(c, tid));                                       \
+  RX_PHASE(PhEqBands(c, tid));                                           \
+  RX_PHASE(PhEqSum(c, tid));                                             \
   RX_PHASE(PhInterp1b(c, tid));                                          \
   RX_PHASE(PhInterp2(c, tid));                                           \
   RX_PHASE(PhBlockEnd(c, tid));

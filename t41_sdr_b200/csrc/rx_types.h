@@ -60,6 +60,8 @@ struct StreamCfg {
   int32_t pixel_add;           /* displayScale[].baseOffset + bands[].pixel_offset */
   int32_t wf_base;             /* spectrumNoiseFloor - currentNF */
   int32_t current_nf;          /* currentNF (FFT.cpp:161: serial frame data = pixelnew + currentNF) */
+  int32_t eq_on;               /* receiveEQFlag == ON (Process.cpp:828) */
+  float eq_scale[14];          /* -/+ recEQ_LevelScale[i] = (float)equalizerRec[i] / 100.0, sign as Filter.cpp:136-149 */
   int32_t zoom_samples;        /* min(2048 >> zoom, 512), FFT.cpp:78-81 */
   int32_t nco_epoch;           /* bumped when NCOFreq changes: forces one exact block (amplitude transient) */
   float rf_gain_value;         /* pow(10, rfGainAllBands / 20), Process.cpp:117 */
@@ -132,6 +134,8 @@ struct StreamState {
   /* audio-spectrum + S-meter by-product (Process.cpp:32,34): audioMaxSquaredAve and audioYPixel[0..269] */
   float audio_max_sq_ave;
   int32_t pad2_;
+  /* receive equaliser: rec_EQ_Band1..14_state (Filter.cpp:43-56), 4 stages x (d1, d2) per band */
+  float eq_state[14][8];
   int16_t audio_ypixel[kAudioSpecPixels + 2];
 };
 

@@ -150,8 +150,35 @@ def edge_rf_gain_ramp():
     return Case("edge_rf_gain_ramp", [([P(mode=USB)], T)], [synth.tone(800, T, 1200.0, amp=0.02)], row_every=0)
 
 
+def _eq(p, levels):
+    p.receive_eq_flag = 1
+    for i, v in enumerate(levels):
+        p.equalizer_rec[i] = v
+    return p
+
+
+def c6_receive_eq():
+    """Receive equaliser (Filter.cpp:117-165) in every mode, levels from flat to a deep notch,
+    switched and re-levelled between the segments (the band states carry over, also while it is off)."""
+    T1, T2, T3 = 7, 6, 5
+    T = T1 + T2 + T3
+    flat = [100] * 14
+    tilt = [100, 80, 0, 120, 55, 100, 30, 90, 100, 10, 70, 100, 45, 100]
+    bass = [0, 0, 0, 10, 20, 40, 60, 80, 100, 100, 100, 100, 100, 100]
+    iqs = [synth.tone(900, T, 1000.0, amp=0.1), synth.tone(901, T, -1200.0, mode=LSB), synth.am(902, T),
+           synth.nfm(903, T), synth.am(904, T, mode=SAM, carrier_offset=50.0), synth.tone(905, T, 500.0),
+           synth.two_tone(906, T, 46500.0, 47900.0), synth.tone(907, T, 700.0)]
+    seg1 = [_eq(P(mode=USB), tilt), _eq(P(mode=LSB), bass), _eq(P(mode=AM), tilt), _eq(P(mode=NFM, agc_mode=3), bass),
+            _eq(P(mode=SAM, agc_mode=4), flat), _eq(P(mode=PSK31), tilt), _eq(P(mode=USB, agc_mode=0), flat), P(mode=USB)]
+    seg2 = [P(mode=USB), _eq(P(mode=LSB), tilt), _eq(P(mode=AM), bass), _eq(P(mode=NFM, agc_mode=3), bass),
+            P(mode=SAM, agc_mode=4), _eq(P(mode=PSK31), flat), _eq(P(mode=USB, agc_mode=0), bass), _eq(P(mode=USB), tilt)]
+    seg3 = [_eq(P(mode=USB), bass), P(mode=LSB), _eq(P(mode=AM), bass), _eq(P(mode=USB, agc_mode=3), tilt),
+            _eq(P(mode=SAM, agc_mode=4), tilt), P(mode=PSK31), _eq(P(mode=USB, agc_mode=0), bass), _eq(P(mode=USB), tilt)]
+    return Case("c6_receive_eq", [(seg1, T1), (seg2, T2), (seg3, T3)], iqs, row_every=4)
+
+
 ALL_CASES = [c1_single_usb, c1_single_usb_agc_off, c2_ssb_am_mix, c3_nfm_sam_agc, c4_zoom_rows, c5_psk31,
-             edge_silence_fullscale, edge_param_changes, edge_rf_gain_ramp]
+             edge_silence_fullscale, edge_param_changes, edge_rf_gain_ramp, c6_receive_eq]
 
 
 def run_case_on(case, make_stream):

@@ -30,7 +30,8 @@ class Params(C.Structure):
         "mode", "f_lo_cut", "f_hi_cut", "nco_freq", "agc_mode", "agc_thresh", "audio_volume",
         "rf_gain_all_bands", "rf_gain", "spectrum_zoom", "current_scale", "pixel_offset",
         "current_nf", "spectrum_noise_floor", "nfm_filter_bw", "psk31_enable")] + [
-        ("iq_amp_correction", C.c_float), ("iq_phase_correction", C.c_float)]
+        ("iq_amp_correction", C.c_float), ("iq_phase_correction", C.c_float),
+        ("receive_eq_flag", C.c_int32), ("equalizer_rec", C.c_int32 * 14)]
 
     def copy(self):
         p = Params()
