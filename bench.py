@@ -39,6 +39,10 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 # receivers x 64 blocks; the algorithmic figure is 1610.6 MB, part of the last audio blocks is still in L2 at
 # kernel end); only meaningful for the default workload, None otherwise
 TRAFFIC_BYTES_PER_LAUNCH = 1079477000 + 500310784
+# smsp__inst_executed.sum / stream-blocks of the same capture: warp-instructions the stream kernel executes per
+# 2048-sample block of one receiver (the chain is bound by FP32 issue slots, not by HBM: DESIGN.md section 3.5)
+WARP_INSTR_PER_STREAM_BLOCK = 7853
+N_SMS, ISSUE_SLOTS_PER_SM = 148, 4
 
 METRIC = "aggregate IQ Msamples/s (full RX chain)"
 UNIT = "Msamples/s"
@@ -86,6 +90,11 @@ def workload(n_blocks):
             else:
                 p.mode = m
                 p.f_lo_cut, p.f_hi_cut = (300, 3000) if m == 0 else (-3000, 3000)
+    if os.environ.get("T41RX_BENCH_EQ"):         # developer knob: receive equaliser on for every receiver (not the C2 metric)
+        for p in params:
+            p.receive_eq_flag = 1
+            for i, v in enumerate([100, 80, 0, 120, 55, 100, 30, 90, 100, 10, 70, 100, 45, 100]):
+                p.equalizer_rec[i] = v
     if os.environ.get("T41RX_BENCH_ZOOM"):       # developer knob (rows-kernel experiments)
         for p in params:
             p.spectrum_zoom = int(os.environ["T41RX_BENCH_ZOOM"])
@@ -384,6 +393,14 @@ def ours(args):
             assert tuple(gathered.shape) == (world * S, 1, 512)
 
     clk = clocks.stop()
+    # explanatory second roofline: share of the SMs' issue slots the stream kernel used (instruction count of the
+    # committed ncu capture, this run's kernel time and SM clock)
+    if clk.get("sm_mhz"):
+        issued = WARP_INSTR_PER_STREAM_BLOCK * S * T / (statistics.mean(kernel_ms) * 1e-3)
+        slots = N_SMS * ISSUE_SLOTS_PER_SM * clk["sm_mhz"] * 1e6
+        roofline["issue_slots"] = {"bound": "fp32 issue", "achieved": issued / 1e12, "peak": slots / 1e12,
+                                   "unit": "T warp-instr/s", "frac": issued / slots,
+                                   "warp_instr_per_stream_block": WARP_INSTR_PER_STREAM_BLOCK}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -181,7 +181,7 @@ __device__ __forceinline__ void MbarWait(uint64_t *bar, unsigned parity) {
 struct RxRegs {
   /* configuration */
   /* small integers share one register (the kernel sits at its 128-register cap; spills go to L2 here) */
-  unsigned mode : 4, agc_mode : 3, mirrored : 1, first_block : 1, nco_closed : 1, psk_enable : 1;
+  unsigned mode : 4, agc_mode : 3, mirrored : 1, first_block : 1, nco_closed : 1, psk_enable : 1, eq_on : 1;
   F2 tw_a, tw_b;         /* this thread's base twiddles of the stride-64 and stride-8 radix-8 passes */
   const char *cp_src;    /* this thread's first 16-byte piece of quarter 0 of block 0 */
   unsigned cp_dst;       /* its shared-memory address in raw buffer 0 */
@@ -372,6 +372,7 @@ struct RxPair {
       r.tw_b = F2{tb.x, tb.y};
     }
     r.psk_enable = cf.psk31_enable != 0;
+    r.eq_on = cf.eq_on != 0;
     if (tau == 2) {
       s[oMiscF + mAmWold] = st.am_wold;
       s[oMiscF + mAmX1] = st.am_lp_state[0];
@@ -1128,6 +1129,7 @@ struct RxPair {
       }
       PairSync();
     }
+    if (r.eq_on) ReceiveEq(cf, st, aud);
     T41RX_LAP(tm, 8);
     Interp1();
     PairSync();
@@ -1137,6 +1139,78 @@ struct RxPair {
     PairSync();
     if (tau < 7) s[oIH + 24 + tau] = s[vI1 + 8 + 505 + tau];
     T41RX_LAP(tm, 10);
+  }
+
+  /* Receive equaliser (DoReceiveEQ, Filter.cpp:117-165; hook Process.cpp:827-831) on the 256 demodulated samples,
+     in place: 14 band-passes of 4 transposed-direct-form-II biquads (FIR.cpp:279-371), scaled by -/+ level and added
+     in band order.  Thread (band, stage) = (tau >> 2, tau & 3): the 56 biquads run as a software pipeline over the
+     samples, stage j one sample behind stage j - 1, whose output it receives by shuffle (the four stages of a band
+     are four adjacent lanes); the last stages write their scaled outputs for 64 samples, which the pair then adds
+     up.  Band states live in StreamState in the layout the bit-exact kernel uses (they cross to and from HBM once
+     per block: only receivers with the equaliser on pay for it). */
+  __device__ void ReceiveEq(const StreamCfg &cf, StreamState &st, float *aud) {
+    constexpr int kEqStride = 65;                    /* band stride of the chunk buffer: the writers hit 8 banks */
+    const int band = tau >> 2, j = tau & 3;
+    const bool live = band < 14;
+    float b0 = 0.0f, b1 = 0.0f, b2 = 0.0f, a1 = 0.0f, a2 = 0.0f, d1 = 0.0f, d2 = 0.0f, scale = 0.0f;
+    if (live) {
+      const float *k = a.eq_coeffs + 20 * band + 5 * j;
+      b0 = __ldg(k); b1 = __ldg(k + 1); b2 = __ldg(k + 2); a1 = __ldg(k + 3); a2 = __ldg(k + 4);
+      d1 = st.eq_state[band][2 * j];
+      d2 = st.eq_state[band][2 * j + 1];
+      scale = cf.eq_scale[band];
+    }
+    float *E = s + oMix;                             /* [14][65]: free between two front ends */
+    const float *x = aud + 24;
+    float ylast = 0.0f, xnext = x[0];
+    float *eout = E + (live ? band : 0) * kEqStride;
+    const bool writer = live && j == 3;
+    /* one pipeline step; kEdge: some stages are outside the block (the first and the last three steps) */
+#define T41RX_EQ_STEP(kEdge, k_, slot_)                                    \
+  {                                                                        \
+    const float up = __shfl_up_sync(kFull, ylast, 1);                      \
+    const float xin = (j == 0) ? xnext : up;                               \
+    xnext = x[(k_) + 1];                 /* x[256] at the end: in the scratch, unused */ \
+    const float y = fmaf(b0, xin, d1);                                     \
+    const float nd1 = fmaf(a1, y, fmaf(b1, xin, d2));                      \
+    const float nd2 = fmaf(a2, y, b2 * xin);                               \
+    bool valid = true;                                                     \
+    if (kEdge) {                                                           \
+      const int n = (k_) - j;                                              \
+      valid = n >= 0 && n < kDec;                                          \
+    }                                                                      \
+    if (valid) {                                                           \
+      d1 = nd1;                                                            \
+      d2 = nd2;                                                            \
+      ylast = y;                                                           \
+      if (writer) eout[slot_] = y * scale;                                 \
+    }                                                                      \
+  }
+    for (int k = 0; k < 3; ++k) T41RX_EQ_STEP(true, k, 0)            /* no writer is valid yet */
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      const int k0 = 64 * c + 3;                     /* the steps whose outputs are samples 64 c .. 64 c + 63 */
+      if (c < 3) {
+#pragma unroll 4
+        for (int i = 0; i < 64; ++i) T41RX_EQ_STEP(false, k0 + i, i)
+      } else {
+#pragma unroll 1
+        for (int i = 0; i < 61; ++i) T41RX_EQ_STEP(false, k0 + i, i)
+        for (int i = 61; i < 64; ++i) T41RX_EQ_STEP(true, k0 + i, i)
+      }
+      PairSync();
+      float acc = E[tau] + E[kEqStride + tau];
+#pragma unroll
+      for (int b = 2; b < 14; ++b) acc += E[b * kEqStride + tau];
+      aud[24 + 64 * c + tau] = acc;                  /* stage 0 is past these inputs */
+      PairSync();
+    }
+#undef T41RX_EQ_STEP
+    if (live) {
+      st.eq_state[band][2 * j] = d1;
+      st.eq_state[band][2 * j + 1] = d2;
+    }
+    PairSync();
   }
 
   /* AGC gain from volts (DSP_Fn.cpp:628) or the fixed gain (DSP_Fn.cpp:494-502) applied to the delayed
