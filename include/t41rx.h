@@ -86,6 +86,9 @@ typedef struct t41rx_params {
   float iq_phase_correction;    /* IQPhaseCorrectionFactor[band]  Process.cpp:167,172                 */
   int32_t receive_eq_flag;      /* receiveEQFlag (ON = 1)         Process.cpp:827-831                 */
   int32_t equalizer_rec[14];    /* EEPROMData.equalizerRec[] 0..100 (default 100)  Filter.cpp:117-165 */
+  int32_t nr_option;            /* nrOptionSelect: 0 off, 3 LMS (Xanr); 1 (Kim) and 2 (spectral) are not built:
+                                   T41RX_EINVAL                   Process.cpp:841-857                 */
+  int32_t anr_notch_on;         /* ANR_notchOn: automatic notch (Xanr)  Process.cpp:860-865           */
 } t41rx_params;
 
 /* Discrete / scalar DSP state for state-transition parity checks. */

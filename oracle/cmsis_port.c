@@ -92,6 +92,21 @@ void arm_var_f32(const float32_t *pSrc, uint32_t n, float32_t *result) {
 }
 
 /* T41/Process.cpp:568,803 — maximum and the index of its first occurrence */
+void arm_fill_f32(float32_t value, float32_t *pDst, uint32_t blockSize) {
+  for (uint32_t i = 0; i < blockSize; ++i) pDst[i] = value;
+}
+
+void arm_lms_norm_init_f32(arm_lms_norm_instance_f32 *S, uint16_t numTaps, float32_t *pCoeffs, float32_t *pState,
+                           float32_t mu, uint32_t blockSize) {
+  S->numTaps = numTaps;
+  S->pCoeffs = pCoeffs;
+  memset(pState, 0, ((size_t)numTaps + (blockSize - 1u)) * sizeof(float32_t));
+  S->pState = pState;
+  S->mu = mu;
+  S->energy = 0.0f;
+  S->x0 = 0.0f;
+}
+
 void arm_max_f32(const float32_t *pSrc, uint32_t n, float32_t *pResult, uint32_t *pIndex) {
   float32_t best = pSrc[0];
   uint32_t where = 0;

@@ -99,6 +99,11 @@ typedef struct {
   float32_t x0;
 } arm_lms_norm_instance_f32;
 
+/* only so that the reference's Noise.cpp links (its LMS-norm set-up is not on the receive path) */
+void arm_fill_f32(float32_t value, float32_t *pDst, uint32_t blockSize);
+void arm_lms_norm_init_f32(arm_lms_norm_instance_f32 *S, uint16_t numTaps, float32_t *pCoeffs, float32_t *pState,
+                           float32_t mu, uint32_t blockSize);
+
 extern const arm_cfft_instance_f32 arm_cfft_sR_f32_len256;
 extern const arm_cfft_instance_f32 arm_cfft_sR_f32_len512;
 extern const arm_cfft_instance_f32 arm_cfft_sR_f32_len1024;

@@ -162,6 +162,7 @@ int rfGainAllBands = 1;
 int spectrumNoiseFloor = 247;
 int xmtMode = SSB_MODE;
 int nrOptionSelect = 0;
+float NR_PSI = 0.0, NR_alpha = 0.95, NR_beta = 0.85;   /* gwv.cpp:61-63 (Noise.cpp's spectral NR, not driven here) */
 int currentScale = 1;
 long spectrumZoom = 1;
 int CWFilterIndex = 5;
@@ -212,9 +213,6 @@ void ShowBandwidthBarValues() {}
 void MyDrawFloat(float, int, int, int, char *) {}
 void UpdateInfoBoxItem(uint8_t) {}
 void CalibrateOptions() {}
-void Kim1_NR() {}
-void Xanr() {}
-void SpectralNoiseReduction() {}
 void SetFreq() {}
 void process_FT8_FFT() {}
 int ft8_decode(void) { return 0; }
@@ -288,6 +286,8 @@ int t41ref_init(void) {
   g_prm.iq_amp_correction = IQAmpCorrectionFactor[currentBand];
   g_prm.iq_phase_correction = IQPhaseCorrectionFactor[currentBand];
   g_prm.receive_eq_flag = 0;
+  g_prm.nr_option = 0;
+  g_prm.anr_notch_on = 0;
   for (int i = 0; i < 14; i++) {
     EEPROMData.equalizerRec[i] = 100;       /* EEPROM.cpp:59,698 */
     g_prm.equalizer_rec[i] = 100;
@@ -377,6 +377,9 @@ int t41ref_set_params(const t41o_params *p) {
   IQAmpCorrectionFactor[currentBand] = p->iq_amp_correction;
   IQPhaseCorrectionFactor[currentBand] = p->iq_phase_correction;
   receiveEQFlag = p->receive_eq_flag;
+  if (p->nr_option != 0 && p->nr_option != 3) return -1;
+  nrOptionSelect = p->nr_option;
+  ANR_notchOn = (uint8_t)p->anr_notch_on;
   for (int i = 0; i < 14; i++) EEPROMData.equalizerRec[i] = p->equalizer_rec[i];
   if (p->mode != old.mode || p->f_lo_cut != old.f_lo_cut || p->f_hi_cut != old.f_hi_cut) CalcFilters();
   if (p->agc_mode != old.agc_mode || p->agc_thresh != old.agc_thresh) {

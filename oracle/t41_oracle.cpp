@@ -329,6 +329,10 @@ struct t41o_stream {
   arm_fir_decimate_instance_f32 zoom_fir_i, zoom_fir_q;
   float zoom_ring_x[kSpecRes], zoom_ring_y[kSpecRes];
   int zoom_sample_ptr;
+  /* variable-leak LMS of the automatic notch / LMS noise reduction, T41/Noise.cpp:33-53 */
+  float anr_d[512], anr_w[512];
+  int anr_in_idx;
+  float anr_lidx, anr_ngamma;
   /* receive equaliser, T41/Filter.cpp:43-72 */
   float eq_state[14][8];
   arm_biquad_cascade_df2T_instance_f32 eq[14];
@@ -416,6 +420,7 @@ int ValidParams(const t41o_params *p) {
   if (p->current_scale < 0 || p->current_scale > 4) return 0;
   if (p->f_hi_cut <= p->f_lo_cut) return 0;
   if (p->audio_volume < 0 || p->audio_volume > 100) return 0;
+  if (p->nr_option != 0 && p->nr_option != 3) return 0;      /* Kim (1) and spectral (2) NR are not restated */
   return 1;
 }
 
@@ -739,6 +744,8 @@ void InitStream(t41o_stream *s) {
   s->last_set_rf_gain = s->prm.rf_gain;
   s->rf_gain = s->prm.rf_gain;
   s->osc_vect_q = 1.0;
+  s->anr_lidx = 120.0;       /* T41/Noise.cpp:47,52 */
+  s->anr_ngamma = 0.001;
   for (int i = 0; i < 14; i++) arm_biquad_cascade_df2T_init_f32(&s->eq[i], 4, t41o_eq_coeffs[i], s->eq_state[i]);
   s->osc_vect_i = 0.0;
   s->first_block = 1;
@@ -810,6 +817,8 @@ void t41o_default_params(t41o_params *p) {
   p->iq_phase_correction = 0.0f;
   p->receive_eq_flag = 0;
   for (int i = 0; i < 14; i++) p->equalizer_rec[i] = 100;   /* T41/EEPROM.cpp:59,698 */
+  p->nr_option = 0;
+  p->anr_notch_on = 0;
 }
 
 void t41o_mode_default_cuts(int32_t mode, int32_t *f_lo_cut, int32_t *f_hi_cut) {
@@ -905,6 +914,47 @@ static void ReceiveEq(t41o_stream *s) {
   for (int i = 0; i < 14; i++) arm_scale_f32(band[i], (i & 1) ? scale[i] : -scale[i], band[i], kDec);
   arm_add_f32(band[0], band[1], L, kDec);
   for (int i = 2; i < 14; i++) arm_add_f32(L, band[i], L, kDec);
+}
+
+/* T41/Noise.cpp:322-369 Xanr: variable-leak LMS (wdsp), 64 taps, delay 16, 512-deep delay line; constants
+   T41/Noise.cpp:39-53.  Unsuffixed literals make several expressions FP64, as written there. */
+static void Xanr(t41o_stream *s, int notch, const float *in, float *out) {
+  const int ANR_delay = 16, ANR_mask = 511, ANR_taps = 64;
+  const float ANR_den_mult = 6.25e-10, ANR_gamma = 0.1, ANR_lidx_min = 120.0, ANR_lidx_max = 200.0, ANR_lincr = 1.0,
+              ANR_ldecr = 3.0, ANR_two_mu = 0.0001;
+  int idx;
+  float c0, c1;
+  float y, error, sigma, inv_sigp;
+  float nel, nev;
+  for (int i = 0; i < kDec; i++) {
+    s->anr_d[s->anr_in_idx] = in[i];
+    y = 0;
+    sigma = 0;
+    for (int j = 0; j < ANR_taps; j++) {
+      idx = (s->anr_in_idx + j + ANR_delay) & ANR_mask;
+      y += s->anr_w[j] * s->anr_d[idx];
+      sigma += s->anr_d[idx] * s->anr_d[idx];
+    }
+    inv_sigp = 1.0 / (sigma + 1e-10);
+    error = s->anr_d[s->anr_in_idx] - y;
+    if (notch) out[i] = error;
+    else out[i] = y;
+    if ((nel = error * (1.0 - ANR_two_mu * sigma * inv_sigp)) < 0.0) nel = -nel;
+    if ((nev = s->anr_d[s->anr_in_idx] - (1.0 - ANR_two_mu * s->anr_ngamma) * y - ANR_two_mu * error * sigma * inv_sigp) < 0.0)
+      nev = -nev;
+    if (nev < nel) {
+      if ((s->anr_lidx += ANR_lincr) > ANR_lidx_max) s->anr_lidx = ANR_lidx_max;
+      else if ((s->anr_lidx -= ANR_ldecr) < ANR_lidx_min) s->anr_lidx = ANR_lidx_min;
+    }
+    s->anr_ngamma = ANR_gamma * (s->anr_lidx * s->anr_lidx) * (s->anr_lidx * s->anr_lidx) * ANR_den_mult;
+    c0 = 1.0 - ANR_two_mu * s->anr_ngamma;
+    c1 = ANR_two_mu * error * inv_sigp;
+    for (int j = 0; j < ANR_taps; j++) {
+      idx = (s->anr_in_idx + j + ANR_delay) & ANR_mask;
+      s->anr_w[j] = c0 * s->anr_w[j] + c1 * s->anr_d[idx];
+    }
+    s->anr_in_idx = (s->anr_in_idx + ANR_mask) & ANR_mask;
+  }
 }
 
 /* Arduino map() with a float first argument, as the Teensyduino core overloads it (cores/teensy4/wiring.h; the
@@ -1113,6 +1163,18 @@ int t41o_process_block(t41o_stream *s, const float *iq, float *audio, int update
 
   /* T41/Process.cpp:827-831 */
   if (s->prm.receive_eq_flag == 1) ReceiveEq(s);
+
+  /* T41/Process.cpp:841-865.  LMS noise reduction (option 3): Xanr leaves its output in float_buffer_R, which
+     nothing reads afterwards - what reaches the audio is float_buffer_L x 1.5, and the adaptive filter's state
+     (shared with the notch) still advances.  Automatic notch: Xanr's error signal replaces float_buffer_L. */
+  if (s->prm.nr_option == 3) {
+    Xanr(s, 0, L, R);
+    arm_scale_f32(L, 1.5, L, kDec);
+  }
+  if (s->prm.anr_notch_on == 1) {
+    Xanr(s, 1, L, R);
+    arm_copy_f32(R, L, kDec);
+  }
 
   /* T41/Process.cpp:917-920 */
   arm_fir_interpolate_f32(&s->int1, L, s->ifft_buf, kDec);

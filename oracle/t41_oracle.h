@@ -54,6 +54,8 @@ typedef struct t41o_params {
   float iq_phase_correction;    /* IQPhaseCorrectionFactor[band], default 0       */
   int32_t receive_eq_flag;      /* receiveEQFlag, default 0 (OFF)                 */
   int32_t equalizer_rec[14];    /* EEPROMData.equalizerRec[], default 100 each    */
+  int32_t nr_option;            /* nrOptionSelect: 0 off, 3 LMS; 1 / 2 rejected   */
+  int32_t anr_notch_on;         /* ANR_notchOn, default 0                         */
 } t41o_params;
 
 typedef struct t41o_debug {

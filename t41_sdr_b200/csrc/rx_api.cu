@@ -231,7 +231,8 @@ struct t41rx_ctx {
   uint32_t *d_varicode = nullptr;
 
   /* receivers by kernel: the SAM PLL is chaotic while it acquires lock, so SAM receivers stay on the
-     bit-exact kernel; everything else runs on the throughput kernel */
+     bit-exact kernel, and so do receivers with the LMS noise reduction / automatic notch on (only built there so
+     far); everything else runs on the throughput kernel */
   std::vector<int32_t> h_fast_ids, h_phased_ids;
   int32_t *d_fast_ids = nullptr, *d_phased_ids = nullptr;
   bool ids_dirty = true;
@@ -656,7 +657,9 @@ static int RefreshKernelLists(t41rx_ctx *ctx) {
   ctx->h_fast_ids.clear();
   ctx->h_phased_ids.clear();
   for (int s = 0; s < ctx->n_streams; ++s)
-    (ctx->host.cfg[s].mode == kModeSam ? ctx->h_phased_ids : ctx->h_fast_ids).push_back(s);
+    ((ctx->host.cfg[s].mode == kModeSam || ctx->host.cfg[s].nr_lms || ctx->host.cfg[s].anr_notch) ? ctx->h_phased_ids
+                                                                                                      : ctx->h_fast_ids)
+        .push_back(s);
   CUDA_TRY(cudaDeviceSynchronize());
   if (!ctx->h_fast_ids.empty())
     CUDA_TRY(cudaMemcpy(ctx->d_fast_ids, ctx->h_fast_ids.data(), sizeof(int32_t) * ctx->h_fast_ids.size(), cudaMemcpyHostToDevice));

@@ -32,6 +32,8 @@ void DefaultParams(t41rx_params *p) {
   p->iq_phase_correction = 0.0f;  /* gwv.cpp:71 */
   p->receive_eq_flag = 0;         /* OFF */
   for (int i = 0; i < 14; ++i) p->equalizer_rec[i] = 100;   /* EEPROM.cpp:59,698 */
+  p->nr_option = 0;               /* nrOptionSelect */
+  p->anr_notch_on = 0;            /* ANR_notchOn */
 }
 
 void HostStateInit(StreamState *st) {
@@ -41,6 +43,8 @@ void HostStateInit(StreamState *st) {
   st->first_block = 1;       /* Process.cpp:47 */
   st->rf_gain = 1;           /* bands[].RFgain, T41_SDR.ino:149-167 */
   st->agc_pos = kAgcRing - 1;
+  st->anr_lidx = 120.0f;     /* Noise.cpp:47 */
+  st->anr_ngamma = 0.001f;   /* Noise.cpp:52 */
 }
 
 static void BuildNcoTable(const StreamCfg &c, double *tab /*192*/) {

@@ -1527,6 +1527,84 @@ T41RX_DEV void PhEqSum(Cta &c, int tid) {
   }
 }
 
+/* ------------------------------------------------------------------ */
+/* LMS noise reduction / automatic notch (Xanr, Noise.cpp:322-369; hooks Process.cpp:841-865) */
+/* ------------------------------------------------------------------ */
+/* One pass of the variable-leak LMS over the 256 samples at vAud + 23, one lane per receiver, every operation in the
+   reference's order and precision (its unsuffixed literals make part of the arithmetic FP64).  notch: the output
+   is the error signal, written back in place; otherwise the reference leaves the filter output in float_buffer_R,
+   which nothing reads: only the state advances.  The 64-term sums are the serial bottleneck of this exactness
+   path (the throughput kernel has its own form). */
+constexpr int vAnrD = vEqBand;                    /* 512: the delay line, staged in shared memory for the block */
+constexpr int vAnrW = vEqBand + 512;              /* 64: the taps */
+
+T41RX_DEV void XanrPass(float *aud, float *d, float *w, StreamState &st, bool notch) {
+  const int kDelay = 16, kMask = 511, kTaps = 64;
+  const float den_mult = 6.25e-10, gamma = 0.1, lidx_min = 120.0, lidx_max = 200.0, lincr = 1.0, ldecr = 3.0,
+              two_mu = 0.0001;
+  int in_idx = st.anr_in_idx;
+  float lidx = st.anr_lidx, ngamma = st.anr_ngamma;
+  for (int i = 0; i < kDec; ++i) {
+    d[in_idx] = aud[i];
+    float y = 0, sigma = 0;
+    for (int j = 0; j < kTaps; ++j) {
+      const float dv = d[(in_idx + j + kDelay) & kMask];
+      y += w[j] * dv;
+      sigma += dv * dv;
+    }
+    const float inv_sigp = 1.0 / (sigma + 1e-10);
+    const float error = d[in_idx] - y;
+    if (notch) aud[i] = error;
+    float nel = error * (1.0 - two_mu * sigma * inv_sigp);
+    if (nel < 0.0) nel = -nel;
+    float nev = d[in_idx] - (1.0 - two_mu * ngamma) * y - two_mu * error * sigma * inv_sigp;
+    if (nev < 0.0) nev = -nev;
+    if (nev < nel) {
+      if ((lidx += lincr) > lidx_max) lidx = lidx_max;
+      else if ((lidx -= ldecr) < lidx_min) lidx = lidx_min;
+    }
+    ngamma = gamma * (lidx * lidx) * (lidx * lidx) * den_mult;
+    const float c0 = 1.0 - two_mu * ngamma;
+    const float c1 = two_mu * error * inv_sigp;
+    for (int j = 0; j < kTaps; ++j) w[j] = c0 * w[j] + c1 * d[(in_idx + j + kDelay) & kMask];
+    in_idx = (in_idx + kMask) & kMask;
+  }
+  st.anr_in_idx = in_idx;
+  st.anr_lidx = lidx;
+  st.anr_ngamma = ngamma;
+}
+
+/* delay line and taps between HBM and shared memory (dir 0: in, 1: out), 64 threads per receiver */
+T41RX_DEV void PhNrStage(Cta &c, int tid, int dir) {
+  const int g = tid >> 6, u = tid & 63;
+  if (g >= c.ng) return;
+  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+  if (!cf.nr_lms && !cf.anr_notch) return;
+  float *s = Slot(c, g);
+  StreamState &st = c.a.st[Sid(c, g)];
+  for (int i = u; i < 512; i += 64) {
+    if (dir == 0) s[vAnrD + i] = st.anr_d[i];
+    else st.anr_d[i] = s[vAnrD + i];
+  }
+  if (dir == 0) s[vAnrW + u] = st.anr_w[u];
+  else st.anr_w[u] = s[vAnrW + u];
+}
+
+T41RX_DEV void PhNrNotch(Cta &c, int tid) {
+  const int g = SerialStream(c, tid);
+  if (g < 0) return;
+  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+  if (!cf.nr_lms && !cf.anr_notch) return;
+  float *s = Slot(c, g);
+  float *aud = s + vAud + 23;
+  StreamState &st = c.a.st[Sid(c, g)];
+  if (cf.nr_lms) {                         /* Process.cpp:852-856: Xanr's output is dropped, float_buffer_L x 1.5 */
+    XanrPass(aud, s + vAnrD, s + vAnrW, st, false);
+    for (int i = 0; i < kDec; ++i) aud[i] = aud[i] * 1.5f;
+  }
+  if (cf.anr_notch) XanrPass(aud, s + vAnrD, s + vAnrW, st, true);   /* Process.cpp:860-865 */
+}
+
 T41RX_DEV void PhInterp1(Cta &c, int tid) {
   for (int g = 0; g < c.ng; ++g) {
     float *s = Slot(c, g);
@@ -2106,6 +2184,9 @@ T41RX_DEV void PhSpecFrameWrite(Cta &c, int tid) {
   RX_PHASE(PhDemodSerial(c, tid));                                       \
   RX_PHASE(PhEqBands(c, tid));                                           \
   RX_PHASE(PhEqSum(c, tid));                                             \
+  RX_PHASE(PhNrStage(c, tid, 0));                                        \
+  RX_PHASE(PhNrNotch(c, tid));                                           \
+  RX_PHASE(PhNrStage(c, tid, 1));                                        \
   RX_PHASE(PhInterp1b(c, tid));                                          \
   RX_PHASE(PhInterp2(c, tid));                                           \
   RX_PHASE(PhBlockEnd(c, tid));

@@ -61,6 +61,8 @@ struct StreamCfg {
   int32_t wf_base;             /* spectrumNoiseFloor - currentNF */
   int32_t current_nf;          /* currentNF (FFT.cpp:161: serial frame data = pixelnew + currentNF) */
   int32_t eq_on;               /* receiveEQFlag == ON (Process.cpp:828) */
+  int32_t nr_lms;              /* nrOptionSelect == 3 (Process.cpp:852-856) */
+  int32_t anr_notch;           /* ANR_notchOn == 1 (Process.cpp:860-865) */
   float eq_scale[14];          /* -/+ recEQ_LevelScale[i] = (float)equalizerRec[i] / 100.0, sign as Filter.cpp:136-149 */
   int32_t zoom_samples;        /* min(2048 >> zoom, 512), FFT.cpp:78-81 */
   int32_t nco_epoch;           /* bumped when NCOFreq changes: forces one exact block (amplitude transient) */
@@ -136,6 +138,11 @@ struct StreamState {
   int32_t pad2_;
   /* receive equaliser: rec_EQ_Band1..14_state (Filter.cpp:43-56), 4 stages x (d1, d2) per band */
   float eq_state[14][8];
+  /* variable-leak LMS of the automatic notch / LMS noise reduction (Noise.cpp:33-53): delay line, taps, state */
+  float anr_d[512], anr_w[64];
+  int32_t anr_in_idx;
+  float anr_lidx, anr_ngamma;
+  int32_t pad3_;
   int16_t audio_ypixel[kAudioSpecPixels + 2];
 };
 

@@ -177,8 +177,25 @@ def c6_receive_eq():
     return Case("c6_receive_eq", [(seg1, T1), (seg2, T2), (seg3, T3)], iqs, row_every=4)
 
 
+def c7_lms_notch():
+    """Automatic notch and LMS noise reduction (Xanr, Noise.cpp:322-369): each alone, both (two
+    passes over one shared state), with the equaliser in front, switched between the segments."""
+    T1, T2 = 8, 6
+    T = T1 + T2
+    tilt = [100, 80, 0, 120, 55, 100, 30, 90, 100, 10, 70, 100, 45, 100]
+    iqs = [synth.two_tone(910, T, 46500.0, 47900.0), synth.tone(911, T, -1200.0, mode=LSB), synth.am(912, T),
+           synth.nfm(913, T), synth.am(914, T, mode=SAM, carrier_offset=50.0), synth.tone(915, T, 500.0),
+           synth.two_tone(916, T, 46800.0, 48100.0)]
+    seg1 = [P(mode=USB, anr_notch_on=1), P(mode=LSB, nr_option=3), P(mode=AM, nr_option=3, anr_notch_on=1),
+            P(mode=NFM, agc_mode=3, anr_notch_on=1), P(mode=SAM, agc_mode=4, anr_notch_on=1), P(mode=PSK31, anr_notch_on=1),
+            _eq(P(mode=USB, nr_option=3, anr_notch_on=1), tilt)]
+    seg2 = [P(mode=USB, nr_option=3), P(mode=LSB, anr_notch_on=1), P(mode=AM), P(mode=NFM, agc_mode=3, nr_option=3, anr_notch_on=1),
+            P(mode=SAM, agc_mode=4), P(mode=PSK31, nr_option=3), P(mode=USB, anr_notch_on=1)]
+    return Case("c7_lms_notch", [(seg1, T1), (seg2, T2)], iqs, row_every=4)
+
+
 ALL_CASES = [c1_single_usb, c1_single_usb_agc_off, c2_ssb_am_mix, c3_nfm_sam_agc, c4_zoom_rows, c5_psk31,
-             edge_silence_fullscale, edge_param_changes, edge_rf_gain_ramp, c6_receive_eq]
+             edge_silence_fullscale, edge_param_changes, edge_rf_gain_ramp, c6_receive_eq, c7_lms_notch]
 
 
 def run_case_on(case, make_stream):
