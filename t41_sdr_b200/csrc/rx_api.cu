@@ -230,11 +230,12 @@ struct t41rx_ctx {
   uint16_t *d_gradient = nullptr;
   uint32_t *d_varicode = nullptr;
 
-  /* receivers by kernel: the SAM PLL is chaotic while it acquires lock, so SAM receivers stay on the
-     bit-exact kernel, and so do receivers with the LMS noise reduction / automatic notch on (only built there so
-     far); everything else runs on the throughput kernel */
-  std::vector<int32_t> h_fast_ids, h_phased_ids;
-  int32_t *d_fast_ids = nullptr, *d_phased_ids = nullptr;
+  /* receivers by kernel: the SAM PLL is chaotic while it acquires lock, and the LMS notch cancels most of its
+     input, which amplifies any FP32 re-ordering beyond the stated tolerance: those receivers stay on the bit-exact
+     kernel; everything else runs on the throughput kernel.  Variant [1] of the lists is the split under
+     T41RX_FLAG_FAST_LMS (LMS / notch receivers on the throughput kernel too). */
+  std::vector<int32_t> h_fast_ids[2], h_phased_ids[2];
+  int32_t *d_fast_ids[2] = {nullptr, nullptr}, *d_phased_ids[2] = {nullptr, nullptr};
   bool ids_dirty = true;
 
   /* device staging for the host-buffer entry point */
@@ -332,7 +333,8 @@ void t41rx_destroy(t41rx_ctx *ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   void *bufs[] = {ctx->d_cfg, ctx->d_state, ctx->d_fsets, ctx->d_nco_tab, ctx->d_twiddle, ctx->d_hann, ctx->d_sin,
                   ctx->d_zoom_iir, ctx->d_eq_coeffs, ctx->d_sam, ctx->d_gradient, ctx->d_varicode, ctx->d_iq, ctx->d_audio,
-                  ctx->d_spec, ctx->d_wf, ctx->d_bits, ctx->d_chars, ctx->d_fast_ids, ctx->d_phased_ids,
+                  ctx->d_spec, ctx->d_wf, ctx->d_bits, ctx->d_chars, ctx->d_fast_ids[0], ctx->d_phased_ids[0], ctx->d_fast_ids[1],
+                  ctx->d_phased_ids[1],
                   ctx->d_iq16, ctx->d_audio16, ctx->d_aspec, ctx->d_ypixel, ctx->d_max_ave,
                   ctx->d_sframes, ctx->d_aframes};
   for (void *b : bufs)
@@ -396,8 +398,10 @@ int t41rx_create(t41rx_ctx **out, int n_streams, int device) {
   if (cudaMalloc(&ctx->d_cfg, sizeof(StreamCfg) * n_streams) != cudaSuccess ||
       cudaMalloc(&ctx->d_state, sizeof(StreamState) * n_streams) != cudaSuccess ||
       cudaMalloc(&ctx->d_nco_tab, sizeof(double) * 192 * n_streams) != cudaSuccess ||
-      cudaMalloc(&ctx->d_fast_ids, sizeof(int32_t) * n_streams) != cudaSuccess ||
-      cudaMalloc(&ctx->d_phased_ids, sizeof(int32_t) * n_streams) != cudaSuccess)
+      cudaMalloc(&ctx->d_fast_ids[0], sizeof(int32_t) * n_streams) != cudaSuccess ||
+      cudaMalloc(&ctx->d_phased_ids[0], sizeof(int32_t) * n_streams) != cudaSuccess ||
+      cudaMalloc(&ctx->d_fast_ids[1], sizeof(int32_t) * n_streams) != cudaSuccess ||
+      cudaMalloc(&ctx->d_phased_ids[1], sizeof(int32_t) * n_streams) != cudaSuccess)
     return bail(Fail(T41RX_ENOMEM, "t41rx_create: device allocation failed%s"));
   {
     std::vector<StreamState> init(n_streams);
@@ -616,12 +620,13 @@ static int LaunchRange(t41rx_ctx *ctx, const float *iq, float *audio, int n_bloc
     *len = (int)(hi - lo);
   };
   int p_off, p_len, f_off, f_len;
-  slice(ctx->h_phased_ids, &p_off, &p_len);
-  slice(ctx->h_fast_ids, &f_off, &f_len);
+  const int v = (flags & T41RX_FLAG_FAST_LMS) ? 1 : 0;
+  slice(ctx->h_phased_ids[v], &p_off, &p_len);
+  slice(ctx->h_fast_ids[v], &f_off, &f_len);
   if (p_len > 0) {
     LaunchArgs p = a;
     p.n_streams = p_len;
-    p.stream_ids = ctx->d_phased_ids + p_off;
+    p.stream_ids = ctx->d_phased_ids[v] + p_off;
     t41rx_fused_rx_kernel<<<(p_len + kG - 1) / kG, kNT, kSmemFloats * sizeof(float), st>>>(p);
     CUDA_TRY(cudaGetLastError());
     ctx->launches += 1;
@@ -629,7 +634,7 @@ static int LaunchRange(t41rx_ctx *ctx, const float *iq, float *audio, int n_bloc
   if (f_len > 0) {
     LaunchArgs f = a;
     f.n_streams = f_len;
-    f.stream_ids = (p_len > 0) ? ctx->d_fast_ids + f_off : nullptr;     /* no SAM receiver in range: contiguous */
+    f.stream_ids = (p_len > 0) ? ctx->d_fast_ids[v] + f_off : nullptr;     /* nothing for the other kernel in range: contiguous */
     if (has_row && (a.spec_rows || a.wf_rows)) {
       t41rx_rows_kernel<<<(f_len + kG - 1) / kG, kNT, kSmemFloats * sizeof(float), st>>>(f);
       CUDA_TRY(cudaGetLastError());
@@ -654,17 +659,20 @@ static int EnsureAudioSpecScratch(t41rx_ctx *ctx, size_t n_rows) {
 /* (re)build the per-kernel receiver lists after a parameter change */
 static int RefreshKernelLists(t41rx_ctx *ctx) {
   if (!ctx->ids_dirty) return T41RX_OK;
-  ctx->h_fast_ids.clear();
-  ctx->h_phased_ids.clear();
-  for (int s = 0; s < ctx->n_streams; ++s)
-    ((ctx->host.cfg[s].mode == kModeSam || ctx->host.cfg[s].nr_lms || ctx->host.cfg[s].anr_notch) ? ctx->h_phased_ids
-                                                                                                      : ctx->h_fast_ids)
-        .push_back(s);
   CUDA_TRY(cudaDeviceSynchronize());
-  if (!ctx->h_fast_ids.empty())
-    CUDA_TRY(cudaMemcpy(ctx->d_fast_ids, ctx->h_fast_ids.data(), sizeof(int32_t) * ctx->h_fast_ids.size(), cudaMemcpyHostToDevice));
-  if (!ctx->h_phased_ids.empty())
-    CUDA_TRY(cudaMemcpy(ctx->d_phased_ids, ctx->h_phased_ids.data(), sizeof(int32_t) * ctx->h_phased_ids.size(), cudaMemcpyHostToDevice));
+  for (int v = 0; v < 2; ++v) {
+    ctx->h_fast_ids[v].clear();
+    ctx->h_phased_ids[v].clear();
+    for (int s = 0; s < ctx->n_streams; ++s) {
+      const StreamCfg &cf = ctx->host.cfg[s];
+      const bool phased = cf.mode == kModeSam || (v == 0 && (cf.nr_lms || cf.anr_notch));
+      (phased ? ctx->h_phased_ids[v] : ctx->h_fast_ids[v]).push_back(s);
+    }
+    if (!ctx->h_fast_ids[v].empty())
+      CUDA_TRY(cudaMemcpy(ctx->d_fast_ids[v], ctx->h_fast_ids[v].data(), sizeof(int32_t) * ctx->h_fast_ids[v].size(), cudaMemcpyHostToDevice));
+    if (!ctx->h_phased_ids[v].empty())
+      CUDA_TRY(cudaMemcpy(ctx->d_phased_ids[v], ctx->h_phased_ids[v].data(), sizeof(int32_t) * ctx->h_phased_ids[v].size(), cudaMemcpyHostToDevice));
+  }
   ctx->ids_dirty = false;
   return T41RX_OK;
 }

@@ -181,7 +181,8 @@ __device__ __forceinline__ void MbarWait(uint64_t *bar, unsigned parity) {
 struct RxRegs {
   /* configuration */
   /* small integers share one register (the kernel sits at its 128-register cap; spills go to L2 here) */
-  unsigned mode : 4, agc_mode : 3, mirrored : 1, first_block : 1, nco_closed : 1, psk_enable : 1, eq_on : 1;
+  unsigned mode : 4, agc_mode : 3, mirrored : 1, first_block : 1, nco_closed : 1, psk_enable : 1, eq_on : 1, nr_lms : 1,
+      anr_notch : 1;
   F2 tw_a, tw_b;         /* this thread's base twiddles of the stride-64 and stride-8 radix-8 passes */
   const char *cp_src;    /* this thread's first 16-byte piece of quarter 0 of block 0 */
   unsigned cp_dst;       /* its shared-memory address in raw buffer 0 */
@@ -373,6 +374,8 @@ struct RxPair {
     }
     r.psk_enable = cf.psk31_enable != 0;
     r.eq_on = cf.eq_on != 0;
+    r.nr_lms = cf.nr_lms != 0;
+    r.anr_notch = cf.anr_notch != 0;
     if (tau == 2) {
       s[oMiscF + mAmWold] = st.am_wold;
       s[oMiscF + mAmX1] = st.am_lp_state[0];
@@ -1130,6 +1133,19 @@ struct RxPair {
       PairSync();
     }
     if (r.eq_on) ReceiveEq(cf, st, aud);
+    if (r.nr_lms || r.anr_notch) {
+      /* Process.cpp:841-865: LMS noise reduction (Xanr's output is dropped: the audio is float_buffer_L x 1.5, the
+         adaptive state still advances), then the automatic notch (the error signal replaces the audio) */
+      if (w2 == 0) {
+        if (r.nr_lms) {
+          Xanr(st, aud + 24, false);
+          for (int i = lane; i < kDec; i += 32) aud[24 + i] *= 1.5f;
+          __syncwarp();
+        }
+        if (r.anr_notch) Xanr(st, aud + 24, true);
+      }
+      PairSync();
+    }
     T41RX_LAP(tm, 8);
     Interp1();
     PairSync();
@@ -1139,6 +1155,62 @@ struct RxPair {
     PairSync();
     if (tau < 7) s[oIH + 24 + tau] = s[vI1 + 8 + 505 + tau];
     T41RX_LAP(tm, 10);
+  }
+
+  /* Xanr (Noise.cpp:322-369): variable-leak LMS, 64 taps behind a delay of 16, one pass over the 256 samples at x,
+     run by ONE warp (the adaptation is a serial chain over the samples; two taps per lane, j = lane and lane + 32,
+     keep both dot products inside the warp: butterfly shuffles, no barrier).  The samples sit in a linear window
+     (79 of history + 256) so that tap j of sample i is a plain offset.  State in StreamState in the reference's
+     layout (delay line as a 512-deep ring with the write index running down), crossing to and from HBM once per
+     pass.  FP32 throughout (the reference's FP64 sub-expressions included): its branch on two nearly equal error
+     estimates can fall the other way once in a while, which moves the leak by one step of ~1e-6. */
+  __device__ void Xanr(StreamState &st, float *x, bool notch) {
+    constexpr int kHist = 79, kMask = 511;
+    constexpr float den_mult = 6.25e-10f, gamma = 0.1f, lidx_min = 120.0f, lidx_max = 200.0f, lincr = 1.0f, ldecr = 3.0f,
+                    two_mu = 0.0001f;
+    float *W = s + oMix;                            /* [79 + 256]: free between two front ends */
+    const int i0 = st.anr_in_idx;
+    float lidx = st.anr_lidx, ngamma = st.anr_ngamma;
+    float w0 = st.anr_w[lane], w1 = st.anr_w[lane + 32];
+    for (int k = lane + 1; k <= kHist; k += 32) W[kHist - k] = st.anr_d[(i0 + k) & kMask];
+    for (int i = lane; i < kDec; i += 32) W[kHist + i] = x[i];
+    __syncwarp();
+    float mine = 0.0f;
+#pragma unroll 1
+    for (int i = 0; i < kDec; ++i) {
+      const float a = W[kHist - 16 + i - lane], b = W[kHist - 48 + i - lane], xi = W[kHist + i];
+      float y = fmaf(w0, a, w1 * b), sigma = fmaf(a, a, b * b);
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) {
+        y += __shfl_xor_sync(kFull, y, d);
+        sigma += __shfl_xor_sync(kFull, sigma, d);
+      }
+      const float inv_sigp = 1.0f / (sigma + 1e-10f);
+      const float error = xi - y;
+      if ((i & 31) == lane) mine = error;
+      const float se = two_mu * sigma * inv_sigp;
+      const float nel = fabsf(error * (1.0f - se));
+      const float nev = fabsf(xi - (1.0f - two_mu * ngamma) * y - error * se);
+      if (nev < nel) {
+        if ((lidx += lincr) > lidx_max) lidx = lidx_max;
+        else if ((lidx -= ldecr) < lidx_min) lidx = lidx_min;
+      }
+      ngamma = gamma * (lidx * lidx) * (lidx * lidx) * den_mult;
+      const float c0 = 1.0f - two_mu * ngamma;
+      const float c1 = two_mu * error * inv_sigp;
+      w0 = fmaf(c0, w0, c1 * a);
+      w1 = fmaf(c0, w1, c1 * b);
+      if (notch && (i & 31) == 31) x[i - 31 + lane] = mine;      /* the window, not x, feeds the taps */
+    }
+    st.anr_w[lane] = w0;
+    st.anr_w[lane + 32] = w1;
+    for (int i = lane; i < kDec; i += 32) st.anr_d[(i0 - i) & kMask] = W[kHist + i];
+    if (lane == 0) {
+      st.anr_in_idx = (i0 - kDec) & kMask;
+      st.anr_lidx = lidx;
+      st.anr_ngamma = ngamma;
+    }
+    __syncwarp();
   }
 
   /* Receive equaliser (DoReceiveEQ, Filter.cpp:117-165; hook Process.cpp:827-831) on the 256 demodulated samples,
