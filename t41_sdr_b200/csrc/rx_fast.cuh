@@ -282,6 +282,141 @@ __device__ __forceinline__ void MidPass(float2 *buf, const float2 (&hm)[8], int 
 }
 
 /* ------------------------------------------------------------------ */
+/* optional audio stages between the demodulator and the interpolators */
+/* (free functions, not inlined: the default path's code and register  */
+/* allocation stay what they are without them)                         */
+/* ------------------------------------------------------------------ */
+/* Xanr (Noise.cpp:322-369): variable-leak LMS, 64 taps behind a delay of 16, one pass over the 256 samples at x,
+   run by ONE warp (the adaptation is a serial chain over the samples; two taps per lane, j = lane and lane + 32,
+   keep both dot products inside the warp: butterfly shuffles, no barrier).  The samples sit in a linear window
+   (79 of history + 256) so that tap j of sample i is a plain offset.  State in StreamState in the reference's
+   layout (delay line as a 512-deep ring with the write index running down), crossing to and from HBM once per
+   pass.  FP32 throughout (the reference's FP64 sub-expressions included): its branch on two nearly equal error
+   estimates can fall the other way once in a while, which moves the leak by one step of ~1e-6. */
+__device__ __noinline__ void XanrWarp(float *s, StreamState &st, float *x, int lane, bool notch) {
+  constexpr int kHist = 79, kMask = 511;
+  constexpr float den_mult = 6.25e-10f, gamma = 0.1f, lidx_min = 120.0f, lidx_max = 200.0f, lincr = 1.0f, ldecr = 3.0f,
+                  two_mu = 0.0001f;
+  float *W = s + oMix;                            /* [79 + 256]: free between two front ends */
+  const int i0 = st.anr_in_idx;
+  float lidx = st.anr_lidx, ngamma = st.anr_ngamma;
+  float w0 = st.anr_w[lane], w1 = st.anr_w[lane + 32];
+  for (int k = lane + 1; k <= kHist; k += 32) W[kHist - k] = st.anr_d[(i0 + k) & kMask];
+  for (int i = lane; i < kDec; i += 32) W[kHist + i] = x[i];
+  __syncwarp();
+  float mine = 0.0f;
+#pragma unroll 1
+  for (int i = 0; i < kDec; ++i) {
+    const float a = W[kHist - 16 + i - lane], b = W[kHist - 48 + i - lane], xi = W[kHist + i];
+    float y = fmaf(w0, a, w1 * b), sigma = fmaf(a, a, b * b);
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+      y += __shfl_xor_sync(kFull, y, d);
+      sigma += __shfl_xor_sync(kFull, sigma, d);
+    }
+    const float inv_sigp = 1.0f / (sigma + 1e-10f);
+    const float error = xi - y;
+    if ((i & 31) == lane) mine = error;
+    const float se = two_mu * sigma * inv_sigp;
+    const float nel = fabsf(error * (1.0f - se));
+    const float nev = fabsf(xi - (1.0f - two_mu * ngamma) * y - error * se);
+    if (nev < nel) {
+      if ((lidx += lincr) > lidx_max) lidx = lidx_max;
+      else if ((lidx -= ldecr) < lidx_min) lidx = lidx_min;
+    }
+    ngamma = gamma * (lidx * lidx) * (lidx * lidx) * den_mult;
+    const float c0 = 1.0f - two_mu * ngamma;
+    const float c1 = two_mu * error * inv_sigp;
+    w0 = fmaf(c0, w0, c1 * a);
+    w1 = fmaf(c0, w1, c1 * b);
+    if (notch && (i & 31) == 31) x[i - 31 + lane] = mine;      /* the window, not x, feeds the taps */
+  }
+  st.anr_w[lane] = w0;
+  st.anr_w[lane + 32] = w1;
+  for (int i = lane; i < kDec; i += 32) st.anr_d[(i0 - i) & kMask] = W[kHist + i];
+  if (lane == 0) {
+    st.anr_in_idx = (i0 - kDec) & kMask;
+    st.anr_lidx = lidx;
+    st.anr_ngamma = ngamma;
+  }
+  __syncwarp();
+}
+
+/* Receive equaliser (DoReceiveEQ, Filter.cpp:117-165; hook Process.cpp:827-831) on the 256 demodulated samples,
+   in place: 14 band-passes of 4 transposed-direct-form-II biquads (FIR.cpp:279-371), scaled by -/+ level and added
+   in band order.  Thread (band, stage) = (tau >> 2, tau & 3): the 56 biquads run as a software pipeline over the
+   samples, stage j one sample behind stage j - 1, whose output it receives by shuffle (the four stages of a band
+   are four adjacent lanes); the last stages write their scaled outputs for 64 samples, which the pair then adds
+   up.  Band states live in StreamState in the layout the bit-exact kernel uses (they cross to and from HBM once
+   per block: only receivers with the equaliser on pay for it). */
+__device__ __noinline__ void ReceiveEqPair(float *s, const float *eq_coeffs, const StreamCfg &cf, StreamState &st, float *aud,
+                                         int tau, int bar_id) {
+  constexpr int kEqStride = 65;                    /* band stride of the chunk buffer: the writers hit 8 banks */
+  const int band = tau >> 2, j = tau & 3;
+  const bool live = band < 14;
+  float b0 = 0.0f, b1 = 0.0f, b2 = 0.0f, a1 = 0.0f, a2 = 0.0f, d1 = 0.0f, d2 = 0.0f, scale = 0.0f;
+  if (live) {
+    const float *k = eq_coeffs + 20 * band + 5 * j;
+    b0 = __ldg(k); b1 = __ldg(k + 1); b2 = __ldg(k + 2); a1 = __ldg(k + 3); a2 = __ldg(k + 4);
+    d1 = st.eq_state[band][2 * j];
+    d2 = st.eq_state[band][2 * j + 1];
+    scale = cf.eq_scale[band];
+  }
+  float *E = s + oMix;                             /* [14][65]: free between two front ends */
+  const float *x = aud + 24;
+  float ylast = 0.0f, xnext = x[0];
+  float *eout = E + (live ? band : 0) * kEqStride;
+  const bool writer = live && j == 3;
+  /* one pipeline step; kEdge: some stages are outside the block (the first and the last three steps) */
+#define T41RX_EQ_STEP(kEdge, k_, slot_)                                    \
+{                                                                        \
+  const float up = __shfl_up_sync(kFull, ylast, 1);                      \
+  const float xin = (j == 0) ? xnext : up;                               \
+  xnext = x[(k_) + 1];                 /* x[256] at the end: in the scratch, unused */ \
+  const float y = fmaf(b0, xin, d1);                                     \
+  const float nd1 = fmaf(a1, y, fmaf(b1, xin, d2));                      \
+  const float nd2 = fmaf(a2, y, b2 * xin);                               \
+  bool valid = true;                                                     \
+  if (kEdge) {                                                           \
+    const int n = (k_) - j;                                              \
+    valid = n >= 0 && n < kDec;                                          \
+  }                                                                      \
+  if (valid) {                                                           \
+    d1 = nd1;                                                            \
+    d2 = nd2;                                                            \
+    ylast = y;                                                           \
+    if (writer) eout[slot_] = y * scale;                                 \
+  }                                                                      \
+}
+  for (int k = 0; k < 3; ++k) T41RX_EQ_STEP(true, k, 0)            /* no writer is valid yet */
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    const int k0 = 64 * c + 3;                     /* the steps whose outputs are samples 64 c .. 64 c + 63 */
+    if (c < 3) {
+#pragma unroll 4
+      for (int i = 0; i < 64; ++i) T41RX_EQ_STEP(false, k0 + i, i)
+    } else {
+#pragma unroll 1
+      for (int i = 0; i < 61; ++i) T41RX_EQ_STEP(false, k0 + i, i)
+      for (int i = 61; i < 64; ++i) T41RX_EQ_STEP(true, k0 + i, i)
+    }
+    asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+    float acc = E[tau] + E[kEqStride + tau];
+#pragma unroll
+    for (int b = 2; b < 14; ++b) acc += E[b * kEqStride + tau];
+    aud[24 + 64 * c + tau] = acc;                  /* stage 0 is past these inputs */
+    asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+  }
+#undef T41RX_EQ_STEP
+  if (live) {
+    st.eq_state[band][2 * j] = d1;
+    st.eq_state[band][2 * j + 1] = d2;
+  }
+  asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+}
+
+
+/* ------------------------------------------------------------------ */
 /* receiver pair: two warps (64 threads) per receiver                   */
 /* ------------------------------------------------------------------ */
 struct RxPair {
@@ -1132,17 +1267,17 @@ struct RxPair {
       }
       PairSync();
     }
-    if (r.eq_on) ReceiveEq(cf, st, aud);
+    if (r.eq_on) ReceiveEqPair(s, a.eq_coeffs, cf, st, aud, tau, bar_id);
     if (r.nr_lms || r.anr_notch) {
       /* Process.cpp:841-865: LMS noise reduction (Xanr's output is dropped: the audio is float_buffer_L x 1.5, the
          adaptive state still advances), then the automatic notch (the error signal replaces the audio) */
       if (w2 == 0) {
         if (r.nr_lms) {
-          Xanr(st, aud + 24, false);
+          XanrWarp(s, st, aud + 24, lane, false);
           for (int i = lane; i < kDec; i += 32) aud[24 + i] *= 1.5f;
           __syncwarp();
         }
-        if (r.anr_notch) Xanr(st, aud + 24, true);
+        if (r.anr_notch) XanrWarp(s, st, aud + 24, lane, true);
       }
       PairSync();
     }
@@ -1155,134 +1290,6 @@ struct RxPair {
     PairSync();
     if (tau < 7) s[oIH + 24 + tau] = s[vI1 + 8 + 505 + tau];
     T41RX_LAP(tm, 10);
-  }
-
-  /* Xanr (Noise.cpp:322-369): variable-leak LMS, 64 taps behind a delay of 16, one pass over the 256 samples at x,
-     run by ONE warp (the adaptation is a serial chain over the samples; two taps per lane, j = lane and lane + 32,
-     keep both dot products inside the warp: butterfly shuffles, no barrier).  The samples sit in a linear window
-     (79 of history + 256) so that tap j of sample i is a plain offset.  State in StreamState in the reference's
-     layout (delay line as a 512-deep ring with the write index running down), crossing to and from HBM once per
-     pass.  FP32 throughout (the reference's FP64 sub-expressions included): its branch on two nearly equal error
-     estimates can fall the other way once in a while, which moves the leak by one step of ~1e-6. */
-  __device__ void Xanr(StreamState &st, float *x, bool notch) {
-    constexpr int kHist = 79, kMask = 511;
-    constexpr float den_mult = 6.25e-10f, gamma = 0.1f, lidx_min = 120.0f, lidx_max = 200.0f, lincr = 1.0f, ldecr = 3.0f,
-                    two_mu = 0.0001f;
-    float *W = s + oMix;                            /* [79 + 256]: free between two front ends */
-    const int i0 = st.anr_in_idx;
-    float lidx = st.anr_lidx, ngamma = st.anr_ngamma;
-    float w0 = st.anr_w[lane], w1 = st.anr_w[lane + 32];
-    for (int k = lane + 1; k <= kHist; k += 32) W[kHist - k] = st.anr_d[(i0 + k) & kMask];
-    for (int i = lane; i < kDec; i += 32) W[kHist + i] = x[i];
-    __syncwarp();
-    float mine = 0.0f;
-#pragma unroll 1
-    for (int i = 0; i < kDec; ++i) {
-      const float a = W[kHist - 16 + i - lane], b = W[kHist - 48 + i - lane], xi = W[kHist + i];
-      float y = fmaf(w0, a, w1 * b), sigma = fmaf(a, a, b * b);
-#pragma unroll
-      for (int d = 16; d >= 1; d >>= 1) {
-        y += __shfl_xor_sync(kFull, y, d);
-        sigma += __shfl_xor_sync(kFull, sigma, d);
-      }
-      const float inv_sigp = 1.0f / (sigma + 1e-10f);
-      const float error = xi - y;
-      if ((i & 31) == lane) mine = error;
-      const float se = two_mu * sigma * inv_sigp;
-      const float nel = fabsf(error * (1.0f - se));
-      const float nev = fabsf(xi - (1.0f - two_mu * ngamma) * y - error * se);
-      if (nev < nel) {
-        if ((lidx += lincr) > lidx_max) lidx = lidx_max;
-        else if ((lidx -= ldecr) < lidx_min) lidx = lidx_min;
-      }
-      ngamma = gamma * (lidx * lidx) * (lidx * lidx) * den_mult;
-      const float c0 = 1.0f - two_mu * ngamma;
-      const float c1 = two_mu * error * inv_sigp;
-      w0 = fmaf(c0, w0, c1 * a);
-      w1 = fmaf(c0, w1, c1 * b);
-      if (notch && (i & 31) == 31) x[i - 31 + lane] = mine;      /* the window, not x, feeds the taps */
-    }
-    st.anr_w[lane] = w0;
-    st.anr_w[lane + 32] = w1;
-    for (int i = lane; i < kDec; i += 32) st.anr_d[(i0 - i) & kMask] = W[kHist + i];
-    if (lane == 0) {
-      st.anr_in_idx = (i0 - kDec) & kMask;
-      st.anr_lidx = lidx;
-      st.anr_ngamma = ngamma;
-    }
-    __syncwarp();
-  }
-
-  /* Receive equaliser (DoReceiveEQ, Filter.cpp:117-165; hook Process.cpp:827-831) on the 256 demodulated samples,
-     in place: 14 band-passes of 4 transposed-direct-form-II biquads (FIR.cpp:279-371), scaled by -/+ level and added
-     in band order.  Thread (band, stage) = (tau >> 2, tau & 3): the 56 biquads run as a software pipeline over the
-     samples, stage j one sample behind stage j - 1, whose output it receives by shuffle (the four stages of a band
-     are four adjacent lanes); the last stages write their scaled outputs for 64 samples, which the pair then adds
-     up.  Band states live in StreamState in the layout the bit-exact kernel uses (they cross to and from HBM once
-     per block: only receivers with the equaliser on pay for it). */
-  __device__ void ReceiveEq(const StreamCfg &cf, StreamState &st, float *aud) {
-    constexpr int kEqStride = 65;                    /* band stride of the chunk buffer: the writers hit 8 banks */
-    const int band = tau >> 2, j = tau & 3;
-    const bool live = band < 14;
-    float b0 = 0.0f, b1 = 0.0f, b2 = 0.0f, a1 = 0.0f, a2 = 0.0f, d1 = 0.0f, d2 = 0.0f, scale = 0.0f;
-    if (live) {
-      const float *k = a.eq_coeffs + 20 * band + 5 * j;
-      b0 = __ldg(k); b1 = __ldg(k + 1); b2 = __ldg(k + 2); a1 = __ldg(k + 3); a2 = __ldg(k + 4);
-      d1 = st.eq_state[band][2 * j];
-      d2 = st.eq_state[band][2 * j + 1];
-      scale = cf.eq_scale[band];
-    }
-    float *E = s + oMix;                             /* [14][65]: free between two front ends */
-    const float *x = aud + 24;
-    float ylast = 0.0f, xnext = x[0];
-    float *eout = E + (live ? band : 0) * kEqStride;
-    const bool writer = live && j == 3;
-    /* one pipeline step; kEdge: some stages are outside the block (the first and the last three steps) */
-#define T41RX_EQ_STEP(kEdge, k_, slot_)                                    \
-  {                                                                        \
-    const float up = __shfl_up_sync(kFull, ylast, 1);                      \
-    const float xin = (j == 0) ? xnext : up;                               \
-    xnext = x[(k_) + 1];                 /* x[256] at the end: in the scratch, unused */ \
-    const float y = fmaf(b0, xin, d1);                                     \
-    const float nd1 = fmaf(a1, y, fmaf(b1, xin, d2));                      \
-    const float nd2 = fmaf(a2, y, b2 * xin);                               \
-    bool valid = true;                                                     \
-    if (kEdge) {                                                           \
-      const int n = (k_) - j;                                              \
-      valid = n >= 0 && n < kDec;                                          \
-    }                                                                      \
-    if (valid) {                                                           \
-      d1 = nd1;                                                            \
-      d2 = nd2;                                                            \
-      ylast = y;                                                           \
-      if (writer) eout[slot_] = y * scale;                                 \
-    }                                                                      \
-  }
-    for (int k = 0; k < 3; ++k) T41RX_EQ_STEP(true, k, 0)            /* no writer is valid yet */
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      const int k0 = 64 * c + 3;                     /* the steps whose outputs are samples 64 c .. 64 c + 63 */
-      if (c < 3) {
-#pragma unroll 4
-        for (int i = 0; i < 64; ++i) T41RX_EQ_STEP(false, k0 + i, i)
-      } else {
-#pragma unroll 1
-        for (int i = 0; i < 61; ++i) T41RX_EQ_STEP(false, k0 + i, i)
-        for (int i = 61; i < 64; ++i) T41RX_EQ_STEP(true, k0 + i, i)
-      }
-      PairSync();
-      float acc = E[tau] + E[kEqStride + tau];
-#pragma unroll
-      for (int b = 2; b < 14; ++b) acc += E[b * kEqStride + tau];
-      aud[24 + 64 * c + tau] = acc;                  /* stage 0 is past these inputs */
-      PairSync();
-    }
-#undef T41RX_EQ_STEP
-    if (live) {
-      st.eq_state[band][2 * j] = d1;
-      st.eq_state[band][2 * j + 1] = d2;
-    }
-    PairSync();
   }
 
   /* AGC gain from volts (DSP_Fn.cpp:628) or the fixed gain (DSP_Fn.cpp:494-502) applied to the delayed
