@@ -91,6 +91,9 @@ constexpr int vDem = 256;                         /* 256 complex AGC output -> 7
 constexpr int vAud = 768;                         /* int1 state: 23 history + 256 -> 1047 */
 constexpr int vAmTmp = 1056;                      /* 256 */
 constexpr int vInt2 = 1312;                       /* int2 state: 7 history + 512 -> 1831 */
+constexpr int vSamSin = 1056;                     /* SAM: arm_sin_f32's 513-entry table, staged for the serial PLL (the
+                                                     kernel has next to no L1: a table read from L2 costs ~300 clk, and
+                                                     the PLL makes 4 dependent ones per sample) -> 1569 */
 /* receive equaliser, between the demodulator and the interpolators: 14 band outputs of 256 samples; bands 0..11
    behind the audio buffer (over vAmTmp / vInt2, dead at that point), bands 12 and 13 in the D1 region */
 constexpr int vEqBand = 1056;
@@ -228,8 +231,8 @@ T41RX_DEV float TableTurns(const float *tab, float in) {
     findex -= 512.0f;
   }
   const float fract = findex - (float)index;
-  const float a = LdgRO(tab + index);
-  const float b = LdgRO(tab + index + 1);
+  const float a = tab[index];                     /* the table sits in shared memory (vSamSin) */
+  const float b = tab[index + 1];
   const float wa = (1.0f - fract) * a;
   const float wb = fract * b;
   return wa + wb;
@@ -1352,6 +1355,9 @@ T41RX_DEV void PhDemodParallel(Cta &c, int tid) {
     if (cf.mode == kModeAm) s[vAmTmp + i] = AlphaBetaMag(z.x, z.y);
     else if (cf.mode != kModeSam) s[vAud + 23 + i] = z.x;   /* USB / LSB / NFM: real part */
   }
+  if (cf.mode == kModeSam) {
+    for (int i = u; i < 513; i += 64) s[vSamSin + i] = LdgRO(c.a.sin_table + i);
+  }
 }
 
 T41RX_DEV void PhDemodSerial(Cta &c, int tid) {
@@ -1399,8 +1405,8 @@ T41RX_DEV void PhDemodSerial(Cta &c, int tid) {
     float phz = st.sam_phzerror, fil = st.sam_fil_out, om2 = st.sam_omega2;
     for (int i = 0; i < kDec; ++i) {
       const float2 z = dem[i];
-      const float sn = TableTurns(c.a.sin_table, phz * 0.159154943092f);
-      const float cs = TableTurns(c.a.sin_table, phz * 0.159154943092f + 0.25f);
+      const float sn = TableTurns(s + vSamSin, phz * 0.159154943092f);
+      const float cs = TableTurns(s + vSamSin, phz * 0.159154943092f + 0.25f);
       const float ai = cs * z.x, bi = sn * z.x, aq = cs * z.y, bq = sn * z.y;
       const float corr0 = +ai + bq;
       const float corr1 = -bi + aq;
