@@ -283,9 +283,11 @@ def ours(args):
     stream = torch.cuda.Stream(device=dev)     # a real (non-default) stream: the kernel is launched on it
     torch.cuda.synchronize()
 
+    dev_flags = int(os.environ.get("T41RX_BENCH_FLAGS", "0"))     # developer knob (t41rx_process flags; 0 = the metric)
+
     def step():
         eng.process_device(iq.data_ptr(), audio.data_ptr(), T, row_every, spec.data_ptr(), wf.data_ptr(),
-                           None, None, 0, stream.cuda_stream)
+                           None, None, dev_flags, stream.cuda_stream)
 
     def barrier():
         if world > 1:

@@ -64,6 +64,10 @@ extern "C" {
 #define T41RX_FLAG_FAST_LMS 8u /* receivers with the LMS noise reduction / automatic notch on also run on the throughput
                                    kernel (by default they stay on the bit-exact one): the notch cancels most of its input,
                                    so FP32 re-ordering shows 20-30 dB stronger in what is left: audio SNR >= 70 dB */
+#define T41RX_FLAG_FAST_SAM 16u /* SAM receivers also run on the throughput kernel (by default they stay on the bit-exact
+                                   one, ~9x slower): identical to the reference only in the statistical sense while
+                                   the PLL pulls in (its acquisition is chaotic: ApproxAtan2's 2 pi quirk), within the
+                                   stated tolerance once it is locked */
 /* flags == 0: the throughput kernel (FP32 with FMA contraction, blocked-scan recurrences): audio within
    the stated tolerance of the reference (SNR >= 90 dB), discrete state identical */
 

@@ -232,10 +232,11 @@ struct t41rx_ctx {
 
   /* receivers by kernel: the SAM PLL is chaotic while it acquires lock, and the LMS notch cancels most of its
      input, which amplifies any FP32 re-ordering beyond the stated tolerance: those receivers stay on the bit-exact
-     kernel; everything else runs on the throughput kernel.  Variant [1] of the lists is the split under
-     T41RX_FLAG_FAST_LMS (LMS / notch receivers on the throughput kernel too). */
-  std::vector<int32_t> h_fast_ids[2], h_phased_ids[2];
-  int32_t *d_fast_ids[2] = {nullptr, nullptr}, *d_phased_ids[2] = {nullptr, nullptr};
+     kernel; everything else runs on the throughput kernel.  The variants of the lists are the splits under
+     T41RX_FLAG_FAST_LMS (bit 0 of the index: LMS / notch receivers on the throughput kernel too) and
+     T41RX_FLAG_FAST_SAM (bit 1: SAM receivers too). */
+  std::vector<int32_t> h_fast_ids[4], h_phased_ids[4];
+  int32_t *d_fast_ids[4] = {nullptr, nullptr, nullptr, nullptr}, *d_phased_ids[4] = {nullptr, nullptr, nullptr, nullptr};
   bool ids_dirty = true;
 
   /* device staging for the host-buffer entry point */
@@ -334,7 +335,7 @@ void t41rx_destroy(t41rx_ctx *ctx) {
   void *bufs[] = {ctx->d_cfg, ctx->d_state, ctx->d_fsets, ctx->d_nco_tab, ctx->d_twiddle, ctx->d_hann, ctx->d_sin,
                   ctx->d_zoom_iir, ctx->d_eq_coeffs, ctx->d_sam, ctx->d_gradient, ctx->d_varicode, ctx->d_iq, ctx->d_audio,
                   ctx->d_spec, ctx->d_wf, ctx->d_bits, ctx->d_chars, ctx->d_fast_ids[0], ctx->d_phased_ids[0], ctx->d_fast_ids[1],
-                  ctx->d_phased_ids[1],
+                  ctx->d_phased_ids[1], ctx->d_fast_ids[2], ctx->d_phased_ids[2], ctx->d_fast_ids[3], ctx->d_phased_ids[3],
                   ctx->d_iq16, ctx->d_audio16, ctx->d_aspec, ctx->d_ypixel, ctx->d_max_ave,
                   ctx->d_sframes, ctx->d_aframes};
   for (void *b : bufs)
@@ -401,7 +402,11 @@ int t41rx_create(t41rx_ctx **out, int n_streams, int device) {
       cudaMalloc(&ctx->d_fast_ids[0], sizeof(int32_t) * n_streams) != cudaSuccess ||
       cudaMalloc(&ctx->d_phased_ids[0], sizeof(int32_t) * n_streams) != cudaSuccess ||
       cudaMalloc(&ctx->d_fast_ids[1], sizeof(int32_t) * n_streams) != cudaSuccess ||
-      cudaMalloc(&ctx->d_phased_ids[1], sizeof(int32_t) * n_streams) != cudaSuccess)
+      cudaMalloc(&ctx->d_phased_ids[1], sizeof(int32_t) * n_streams) != cudaSuccess ||
+      cudaMalloc(&ctx->d_fast_ids[2], sizeof(int32_t) * n_streams) != cudaSuccess ||
+      cudaMalloc(&ctx->d_phased_ids[2], sizeof(int32_t) * n_streams) != cudaSuccess ||
+      cudaMalloc(&ctx->d_fast_ids[3], sizeof(int32_t) * n_streams) != cudaSuccess ||
+      cudaMalloc(&ctx->d_phased_ids[3], sizeof(int32_t) * n_streams) != cudaSuccess)
     return bail(Fail(T41RX_ENOMEM, "t41rx_create: device allocation failed%s"));
   {
     std::vector<StreamState> init(n_streams);
@@ -620,7 +625,7 @@ static int LaunchRange(t41rx_ctx *ctx, const float *iq, float *audio, int n_bloc
     *len = (int)(hi - lo);
   };
   int p_off, p_len, f_off, f_len;
-  const int v = (flags & T41RX_FLAG_FAST_LMS) ? 1 : 0;
+  const int v = ((flags & T41RX_FLAG_FAST_LMS) ? 1 : 0) | ((flags & T41RX_FLAG_FAST_SAM) ? 2 : 0);
   slice(ctx->h_phased_ids[v], &p_off, &p_len);
   slice(ctx->h_fast_ids[v], &f_off, &f_len);
   if (p_len > 0) {
@@ -660,12 +665,12 @@ static int EnsureAudioSpecScratch(t41rx_ctx *ctx, size_t n_rows) {
 static int RefreshKernelLists(t41rx_ctx *ctx) {
   if (!ctx->ids_dirty) return T41RX_OK;
   CUDA_TRY(cudaDeviceSynchronize());
-  for (int v = 0; v < 2; ++v) {
+  for (int v = 0; v < 4; ++v) {
     ctx->h_fast_ids[v].clear();
     ctx->h_phased_ids[v].clear();
     for (int s = 0; s < ctx->n_streams; ++s) {
       const StreamCfg &cf = ctx->host.cfg[s];
-      const bool phased = cf.mode == kModeSam || (v == 0 && (cf.nr_lms || cf.anr_notch));
+      const bool phased = (cf.mode == kModeSam && !(v & 2)) || (!(v & 1) && (cf.nr_lms || cf.anr_notch));
       (phased ? ctx->h_phased_ids[v] : ctx->h_fast_ids[v]).push_back(s);
     }
     if (!ctx->h_fast_ids[v].empty())

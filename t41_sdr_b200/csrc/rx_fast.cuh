@@ -282,6 +282,65 @@ __device__ __forceinline__ void MidPass(float2 *buf, const float2 (&hm)[8], int 
 }
 
 /* ------------------------------------------------------------------ */
+/* SAM (AMDecodeSAM, Demod.cpp:40-139) on ONE lane: the PLL is a serial  */
+/* chain over the 256 samples.  Only under T41RX_FLAG_FAST_SAM: the loop */
+/* is chaotic while it pulls in (ApproxAtan2's 2 pi quirk), so a 1e-7    */
+/* difference at its input gives a different acquisition transient; once */
+/* locked, the two trajectories agree again.                             */
+/* ------------------------------------------------------------------ */
+/* Atan2Approx (rx_phases.cuh, Demod.cpp:148-197, 2 pi quirk included) with the approximate division: the PLL lane is
+   one long dependent chain and an IEEE division is a third of it */
+__device__ __forceinline__ float Atan2Quick(float y, float x) {
+  const float pi = 3.1415926535897932384626433832795f;
+  const float tpi = 6.283185307179586476925286766559f;
+  if (x != 0.0f) {
+    if (fabsf(x) > fabsf(y)) {
+      const float a = AtanPoly(__fdividef(y, x));
+      return (x > 0.0f) ? a : ((y >= 0.0f) ? a + pi : a - pi);
+    }
+    const float a = AtanPoly(__fdividef(x, y));
+    return (y > 0.0f) ? tpi - a : -a - tpi;
+  }
+  return (y > 0.0f) ? tpi : ((y < 0.0f) ? -tpi : 0.0f);
+}
+
+__device__ __noinline__ void SamPllLane(const float *tab, const float *sam_consts, StreamState &st, const float2 *z,
+                                        float *audio) {
+  const float tpi = 6.283185307179586476925286766559f;
+  const float omega_min = __ldg(sam_consts + 0), omega_max = __ldg(sam_consts + 1);
+  const float g1 = __ldg(sam_consts + 2), g2 = __ldg(sam_consts + 3);
+  float phz = st.sam_phzerror, fil = st.sam_fil_out, om2 = st.sam_omega2;
+  float2 v = z[0];
+#pragma unroll 1
+  for (int i = 0; i < kDec; ++i) {
+    const float2 vn = z[min(i + 1, kDec - 1)];     /* off the chain */
+    /* arm_sin_f32 / arm_cos_f32 (table + linear interpolation) with one index computation: phz is in [0, 2 pi),
+       the cosine reads a quarter of the table further on */
+    const float fidx = phz * (512.0f * 0.159154943092f);
+    const int idx = (int)fidx;
+    const float fr = fidx - (float)idx;
+    const int is = idx & 511, ic = (idx + 128) & 511;
+    const float s0 = tab[is], s1 = tab[is + 1], c0 = tab[ic], c1 = tab[ic + 1];
+    const float sn = fmaf(fr, s1 - s0, s0), cs = fmaf(fr, c1 - c0, c0);
+    const float ai = cs * v.x, bi = sn * v.x, aq = cs * v.y, bq = sn * v.y;
+    const float corr0 = ai + bq;
+    const float corr1 = aq - bi;
+    audio[i] = (ai - bi) + (aq + bq);              /* the fade leveller is a no-op */
+    const float det = Atan2Quick(corr1, corr0);
+    const float del_out = fil;
+    om2 = fminf(fmaxf(fmaf(g2, det, om2), omega_min), omega_max);
+    fil = fmaf(g1, det, om2);
+    phz = phz + del_out;
+    phz = (phz >= tpi) ? phz - tpi : phz;          /* |fil_out| is far below 2 pi: one wrap at most */
+    phz = (phz < 0.0f) ? phz + tpi : phz;
+    v = vn;
+  }
+  st.sam_phzerror = phz;
+  st.sam_fil_out = fil;
+  st.sam_omega2 = om2;
+}
+
+/* ------------------------------------------------------------------ */
 /* optional audio stages between the demodulator and the interpolators */
 /* (free functions, not inlined: the default path's code and register  */
 /* allocation stay what they are without them)                         */
@@ -1251,10 +1310,21 @@ struct RxPair {
         /* AM: alpha-beta magnitude (Process.cpp:697-699); USB / LSB / NFM / PSK31: real part (:616-624,688-695) */
         aud[24 + tau + 64 * o] = (r.mode == kModeAm) ? AlphaBetaMag(dem[o].x, dem[o].y) : dem[o].x;
       }
+      if (r.mode == kModeSam) {
+        /* the PLL lane needs the 256 gained samples in order, and arm_sin_f32's table within reach */
+        float2 *zs = reinterpret_cast<float2 *>(s + oMix);
+#pragma unroll
+        for (int o = 0; o < 4; ++o) zs[tau + 64 * o] = dem[o];
+        for (int i = tau; i < 513; i += 64) s[oMix + 2 * kDec + i] = __ldg(a.sin_table + i);
+      }
     }
     if (tau < 23) aud[1 + tau] = s[oIH + tau];
     if (tau >= 32 && tau < 39) s[vI1 + 1 + (tau - 32)] = s[oIH + 24 + (tau - 32)];
     PairSync();
+    if (r.mode == kModeSam) {
+      if (tau == 0) SamPllLane(s + oMix + 2 * kDec, a.sam_consts, st, reinterpret_cast<const float2 *>(s + oMix), aud + 24);
+      PairSync();
+    }
     if (r.mode == kModeAm) {
       /* the detector's recurrences are blocked scans over one warp (8 samples per lane), in place */
       if (w2 == 0) {

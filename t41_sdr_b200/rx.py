@@ -23,6 +23,7 @@ AUDIO_SPEC_PIXELS = 270   # AUDIO_SPEC_BOX_W - 2 (Display.h:45, Process.cpp:555)
 FLAG_EXACT_NCO = 1       # bit-exact kernel, step-by-step FP64 oscillator
 FLAG_PHASED_KERNEL = 2   # bit-exact kernel with the closed-form FP64 oscillator
 FLAG_FAST_LMS = 8        # LMS / notch receivers on the throughput kernel too (audio SNR >= 70 dB instead of 90)
+FLAG_FAST_SAM = 16       # SAM receivers on the throughput kernel too (acquisition transient differs, locked: >= 90 dB)
 FLAG_SCAN_ROWS = 4       # rows kernel: scan form of the ZoomFFT biquads (<= 1 LSB, < 1 % of pixels)
 # flags = 0: the throughput kernel
 

@@ -20,6 +20,9 @@ def main():
     names = [a for a in sys.argv[1:] if not a.startswith("--")]
     norows = "--norows" in sys.argv
     flags = 2 if "--phased" in sys.argv else 0
+    for a_ in sys.argv[1:]:
+        if a_.startswith("--flags="):
+            flags = int(a_.split("=")[1])
     for make in cases.ALL_CASES:
         if names and make.__name__ not in names:
             continue
@@ -38,7 +41,7 @@ def main():
             worst = int(np.argmin(blk))
             msg = "  rx %2d mode %d agc %d: SNR %6.1f dB, worst block %d (%.1f dB), first blocks %s" % (
                 s, case.segments[0][0][s].mode, case.segments[0][0][s].agc_mode, snr, worst, blk[worst],
-                " ".join("%.0f" % b for b in blk[:6]))
+                " ".join("%.0f" % b for b in blk[:40]))
             if w["spec"].size:
                 d = np.abs(g["spec"].astype(int) - w["spec"].astype(int))
                 msg += " | spec maxdiff %d same %.4f" % (d.max(), np.mean(d == 0))
