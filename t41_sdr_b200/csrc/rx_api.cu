@@ -95,11 +95,29 @@ __global__ void __launch_bounds__(kNT, 8 / kG) t41rx_rows_kernel(const LaunchArg
   for (int t = (a.row_every - a.t0 % a.row_every) % a.row_every; t < a.n_blocks; t += a.row_every) {
     c.t = t;
     c.row_idx = (a.t0 + t) / a.row_every;
+#ifdef T41RX_PHASE_TIMING
+    /* developer build only: cycles per phase of CTA 0, slots 64.. of g_phase_cycles */
+    int phase_no = 32;
+#define T41RX_KPHASE(stmt)                                                                   \
+  do {                                                                                       \
+    const long long t0_ = clock64();                                                         \
+    stmt;                                                                                    \
+    const long long t1_ = clock64();                                                         \
+    __syncthreads();                                                                         \
+    const long long t2_ = clock64();                                                         \
+    if (blockIdx.x == 0 && tid == 0) {                                                       \
+      g_phase_cycles[2 * phase_no] += (unsigned long long)(t2_ - t0_);                       \
+      g_phase_cycles[2 * phase_no + 1] += (unsigned long long)(t1_ - t0_);                   \
+    }                                                                                        \
+    ++phase_no;                                                                              \
+  } while (0)
+#else
 #define T41RX_KPHASE(stmt) \
   do {                     \
     stmt;                  \
     __syncthreads();       \
   } while (0)
+#endif
     T41RX_ROWS_SCHEDULE_FAST(T41RX_KPHASE)
 #undef T41RX_KPHASE
   }

@@ -1873,14 +1873,19 @@ T41RX_DEV void PhZoomIirScan(Cta &c, int tid) {
  * travels to the next lane by warp shuffle one step ahead of its use.  Input: the shifted samples
  * (PhZoomShift); the last stage writes its output in place (it trails the first stage's reads by 6). */
 T41RX_DEV void PhZoomIirPipe(Cta &c, int tid) {
-  const int g = tid >> 6, lane = tid & 63;
-  if (g >= c.ng || lane >= 32) return;               /* first warp of the receiver's 64-thread group */
-  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
-  if (cf.zoom == 0) return;                          /* warp-uniform */
-  StreamState &st = c.a.st[Sid(c, g)];
-  const bool active = lane < 8;
+  /* ONE warp serves the CTA's receivers, eight lanes each: the pipeline is a serial chain of ~20 instructions per
+     sample step, and one instruction stream for four receivers instead of four keeps the schedulers of the SM free
+     for it (slots sit 8 banks apart, the two channels 28: the lanes' loads and stores do not collide) */
+  static_assert(kG * 8 <= 32, "eight lanes per receiver in one warp");
+  if (tid >= 32) return;
+  const int lane = tid, g = lane >> 3;
+  const bool have = g < c.ng;
+  const int gg = have ? g : 0;
+  const StreamCfg &cf = c.a.cfg[Sid(c, gg)];
+  StreamState &st = c.a.st[Sid(c, gg)];
+  const bool active = have && cf.zoom != 0;
   const int chn = (lane >> 2) & 1, sg = lane & 3;
-  float *x = Slot(c, g) + (chn ? oRawQ : oRawI) + 27;
+  float *x = Slot(c, gg) + (chn ? oRawQ : oRawI) + 27;
   float b0 = 0, b1 = 0, b2 = 0, a1 = 0, a2 = 0, x1 = 0, x2 = 0, y1 = 0, y2 = 0;
   if (active) {
     const float *kk = c.a.zoom_iir + (cf.zoom - 1) * 20 + 5 * sg;
