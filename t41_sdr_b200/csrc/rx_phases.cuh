@@ -1869,14 +1869,17 @@ T41RX_DEV void PhZoomIirScan(Cta &c, int tid) {
 }
 
 /* The same cascade, sample by sample and rounded exactly like the reference: eight lanes per receiver =
- * (channel, biquad stage), software-pipelined with a skew of two samples per stage; a stage's output
- * travels to the next lane by warp shuffle one step ahead of its use.  Input: the shifted samples
- * (PhZoomShift); the last stage writes its output in place (it trails the first stage's reads by 6). */
+ * (channel, biquad stage), the four stages of a channel working IN PLACE on the same array (as CMSIS cascades do),
+ * stage s a fixed kSkew samples behind stage s - 1.  Nothing crosses lanes inside a step (a stage finds its input in
+ * shared memory, written kSkew steps earlier by its predecessor and fetched four steps ahead of use), so a step is
+ * as long as one biquad's own recurrence: acc3 = acc2 + a1 y1, acc = acc3 + a2 y2.  Input: the shifted samples
+ * (PhZoomShift); output: the last stage's, in place. */
 T41RX_DEV void PhZoomIirPipe(Cta &c, int tid) {
-  /* ONE warp serves the CTA's receivers, eight lanes each: the pipeline is a serial chain of ~20 instructions per
-     sample step, and one instruction stream for four receivers instead of four keeps the schedulers of the SM free
-     for it (slots sit 8 banks apart, the two channels 28: the lanes' loads and stores do not collide) */
+  /* ONE warp serves the CTA's receivers, eight lanes each (slots sit 8 banks apart, the two channels 28: the lanes'
+     loads and stores do not collide) */
   static_assert(kG * 8 <= 32, "eight lanes per receiver in one warp");
+  constexpr int kSkew = 12, kAhead = 4, kGroup = 8;
+  static_assert(kGroup <= kSkew - kAhead, "a stage never fetches what its predecessor has not written yet");
   if (tid >= 32) return;
   const int lane = tid, g = lane >> 3;
   const bool have = g < c.ng;
@@ -1893,41 +1896,57 @@ T41RX_DEV void PhZoomIirPipe(Cta &c, int tid) {
     x1 = st.zoom_iir[chn][4 * sg]; x2 = st.zoom_iir[chn][4 * sg + 1];
     y1 = st.zoom_iir[chn][4 * sg + 2]; y2 = st.zoom_iir[chn][4 * sg + 3];
   }
-  const bool first = sg == 0, last = active && sg == 3;
-  float ylast = 0.0f, xcur = 0.0f;
-  /* stage 0 reads four samples ahead (up to 4 floats past the block: the next region of the slot, unused) */
-  float xn0 = x[0], xn1 = x[1], xn2 = x[2], xn3 = x[3];
-  float *xw = x - 6;                                  /* the last stage's sample index is k - 6 */
-  /* one pipeline step; kEdge: some lanes are outside their sample range (first 6 / last 6 steps) */
+  float *xm = x - kSkew * sg;                         /* this stage's sample at step k is xm[k] */
+  const int lo = kSkew * sg - 27;                     /* xm[lo] is the first float of the raw region: early fetches stop there */
+  float xn0 = xm[max(0, lo)], xn1 = xm[max(1, lo)], xn2 = xm[max(2, lo)], xn3 = xm[max(3, lo)];
+  /* one step; kEdge: some stages are outside the block (the first and the last 3 kSkew steps) */
+  /* the sum is ((((b0 x + b1 x1) + b2 x2) + a1 y1) + a2 y2) in this order (arm_biquad_cascade_df1_f32); its first
+     three terms do not involve the recurrence and are formed one step ahead (pre), beside the previous step's
+     y-chain */
 #define T41RX_ZOOM_STEP(kEdge)                                                     \
   {                                                                                \
-    const float xfetch = __shfl_up_sync(0xffffffffu, ylast, 1);                    \
-    const float xin = first ? xn0 : xcur;                                          \
-    float acc = b0 * xin;                                                          \
-    acc = acc + b1 * x1;                                                           \
-    acc = acc + b2 * x2;                                                           \
-    acc = acc + a1 * y1;                                                           \
+    const float xin = xn0;                                                         \
+    float acc = pre + a1 * y1;                                                     \
     acc = acc + a2 * y2;                                                           \
-    bool live = true;                                                              \
+    bool live = active;                                                            \
     if (kEdge) {                                                                   \
-      const int n = k - 2 * sg;                                                    \
-      live = n >= 0 && n < kBlock;                                                 \
+      const int n = k - kSkew * sg;                                                \
+      live = live && n >= 0 && n < kBlock;                                         \
     }                                                                              \
-    x2 = live ? x1 : x2;                                                           \
-    x1 = live ? xin : x1;                                                          \
-    y2 = live ? y1 : y2;                                                           \
-    y1 = live ? acc : y1;                                                          \
-    ylast = live ? acc : ylast;                                                    \
-    if (last && live) xw[k] = acc;                                                 \
-    xcur = xfetch;                                                                 \
+    if (live) {                                                                    \
+      x2 = x1;                                                                     \
+      x1 = xin;                                                                    \
+      y2 = y1;                                                                     \
+      y1 = acc;                                                                    \
+      xm[k] = acc;                                                                 \
+    }                                                                              \
+    pre = b0 * xn1;                                                                \
+    pre = pre + b1 * x1;                                                           \
+    pre = pre + b2 * x2;                                                           \
     xn0 = xn1; xn1 = xn2; xn2 = xn3;                                               \
-    xn3 = x[k + 4];                                                                \
+    xn3 = xm[kEdge ? max(k + kAhead, lo) : k + kAhead];                            \
   }
+  float pre = b0 * xn0;
+  pre = pre + b1 * x1;
+  pre = pre + b2 * x2;
+  /* a warp-level barrier every kGroup steps keeps the compiler from moving a fetch above the predecessor's store it
+     has to see (that store is kSkew - kAhead steps older than the fetch); inside such a group any order is fine */
+  static_assert((3 * kSkew) % kGroup == 4 && kBlock % kGroup == 0, "groups");
   int k = 0;
-  for (; k < 6; ++k) T41RX_ZOOM_STEP(true)
-#pragma unroll 4
-  for (; k < kBlock; ++k) T41RX_ZOOM_STEP(false)
-  for (; k < kBlock + 6; ++k) T41RX_ZOOM_STEP(true)
+  for (; k < 40;) {                                   /* 3 kSkew = 36 edge steps, rounded up to whole groups of the main loop */
+    for (int u_ = 0; u_ < 4; ++u_, ++k) T41RX_ZOOM_STEP(true)
+    __syncwarp();
+  }
+#pragma unroll 1
+  for (; k < kBlock;) {
+#pragma unroll
+    for (int u_ = 0; u_ < kGroup; ++u_, ++k) T41RX_ZOOM_STEP(false)
+    __syncwarp();
+  }
+  for (; k < kBlock + 3 * kSkew;) {
+    for (int u_ = 0; u_ < 4; ++u_, ++k) T41RX_ZOOM_STEP(true)
+    __syncwarp();
+  }
 #undef T41RX_ZOOM_STEP
   if (active) {
     st.zoom_iir[chn][4 * sg] = x1; st.zoom_iir[chn][4 * sg + 1] = x2;
