@@ -1908,17 +1908,19 @@ T41RX_DEV void PhZoomIirPipe(Cta &c, int tid) {
     const float xin = xn0;                                                         \
     float acc = pre + a1 * y1;                                                     \
     acc = acc + a2 * y2;                                                           \
-    bool live = active;                                                            \
+    /* away from the edges every stage is inside the block: the state moves are plain register renames; lanes     \
+       without a receiver (or at zoom x1) compute on whatever they read and never store */                       \
+    bool live = true;                                                              \
     if (kEdge) {                                                                   \
       const int n = k - kSkew * sg;                                                \
-      live = live && n >= 0 && n < kBlock;                                         \
+      live = n >= 0 && n < kBlock;                                                 \
     }                                                                              \
     if (live) {                                                                    \
       x2 = x1;                                                                     \
       x1 = xin;                                                                    \
       y2 = y1;                                                                     \
       y1 = acc;                                                                    \
-      xm[k] = acc;                                                                 \
+      if (active) xm[k] = acc;                                                     \
     }                                                                              \
     pre = b0 * xn1;                                                                \
     pre = pre + b1 * x1;                                                           \
