@@ -348,6 +348,31 @@ def test_host_pipeline_chunking_is_invisible():
     assert host["spec_frames"][:, :, 0].min() == ord("F") and np.abs(host["audio"]).max() > 1e-3
 
 
+@pytest.mark.parametrize("S,T", [(1, 1), (149, 3), (1037, 2), (5, 17)])
+def test_ragged_bank_sizes(S, T):
+    """Bank sizes that do not divide into CTAs (one receiver more than there are SMs, a prime count, a single receiver
+    and a single block): every receiver's output equals what the same receiver gives in a bank of its own distinct
+    signals, and the oracle's within the default tolerance."""
+    D = 16
+    base_p, base_iq, params, iq = _c2_bank(S, T, D)
+    with _receiver(S) as eng:
+        eng.set_params_each(params)
+        big = eng.process(iq, row_every=1)
+    n = min(S, D)
+    with _receiver(n) as eng:
+        eng.set_params_each(params[:n])
+        small = eng.process(iq[:n], row_every=1)
+    for s_ in range(S):
+        k = s_ % D
+        if k < n:
+            assert np.array_equal(big["audio"][s_].view(np.uint32), small["audio"][k].view(np.uint32)), s_
+            assert np.array_equal(big["spec"][s_], small["spec"][k]) and np.array_equal(big["wf"][s_], small["wf"][k]), s_
+    for k in range(n):
+        w = O.OracleStream(base_p[k]).process(base_iq[k], 1)
+        assert O.snr_db(w["audio"], small["audio"][k]) >= 90.0
+        assert np.array_equal(w["spec"], small["spec"][k])
+
+
 def test_receivers_per_cta_invariance(monkeypatch):
     """The throughput kernel's result for a receiver must not depend on how many receivers share its CTA (which
     decides which AGC lane and which shared-memory slot it gets, and how the warps interleave): a race between the
