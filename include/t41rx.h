@@ -96,6 +96,9 @@ typedef struct t41rx_params {
   int32_t nr_option;            /* nrOptionSelect: 0 off, 3 LMS (Xanr); 1 (Kim) and 2 (spectral) are not built:
                                    T41RX_EINVAL                   Process.cpp:841-857                 */
   int32_t anr_notch_on;         /* ANR_notchOn: automatic notch (Xanr)  Process.cpp:860-865           */
+  int32_t cw_receive;           /* T41State == CW_RECEIVE: the CW audio low-pass below is in the chain (the CW decoder
+                                   of that state, DoCWReceiveProcessing, is out of scope)  Process.cpp:878 */
+  int32_t cw_filter_index;      /* CWFilterIndex 0..4 = 0.8 / 1.0 / 1.3 / 1.8 / 2.0 kHz, 5 = off (default)  Process.cpp:882-912 */
 } t41rx_params;
 
 /* Discrete / scalar DSP state for state-transition parity checks. */

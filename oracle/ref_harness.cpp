@@ -111,8 +111,17 @@ arm_fir_interpolate_instance_f32 FIR_int1_I, FIR_int1_Q, FIR_int2_I, FIR_int2_Q;
 arm_lms_norm_instance_f32 LMS_Norm_instance;
 arm_lms_instance_f32 LMS_instance;
 arm_fir_instance_f32 FIR_Hilbert_L, FIR_Hilbert_R;
-arm_biquad_cascade_df2T_instance_f32 S1_CW_AudioFilter1, S1_CW_AudioFilter2, S1_CW_AudioFilter3,
-    S1_CW_AudioFilter4, S1_CW_AudioFilter5;
+/* CWProcessing.cpp:38-49 (that translation unit is the CW decoder and is not built): states and instances of the CW
+   audio low-passes ProcessIQData() applies in the CW receive state; coefficients from the reference's FIR.cpp */
+extern float32_t CW_AudioFilterCoeffs1[30], CW_AudioFilterCoeffs2[30], CW_AudioFilterCoeffs3[30], CW_AudioFilterCoeffs4[30],
+    CW_AudioFilterCoeffs5[30];
+float32_t CW_AudioFilter1_state[12], CW_AudioFilter2_state[12], CW_AudioFilter3_state[12], CW_AudioFilter4_state[12],
+    CW_AudioFilter5_state[12];
+arm_biquad_cascade_df2T_instance_f32 S1_CW_AudioFilter1 = {6, CW_AudioFilter1_state, CW_AudioFilterCoeffs1};
+arm_biquad_cascade_df2T_instance_f32 S1_CW_AudioFilter2 = {6, CW_AudioFilter2_state, CW_AudioFilterCoeffs2};
+arm_biquad_cascade_df2T_instance_f32 S1_CW_AudioFilter3 = {6, CW_AudioFilter3_state, CW_AudioFilterCoeffs3};
+arm_biquad_cascade_df2T_instance_f32 S1_CW_AudioFilter4 = {6, CW_AudioFilter4_state, CW_AudioFilterCoeffs4};
+arm_biquad_cascade_df2T_instance_f32 S1_CW_AudioFilter5 = {6, CW_AudioFilter5_state, CW_AudioFilterCoeffs5};
 
 /* T41_SDR.ino:333-345 — same expressions, evaluated once here */
 const float32_t DF1 = 4.0;
@@ -288,6 +297,8 @@ int t41ref_init(void) {
   g_prm.receive_eq_flag = 0;
   g_prm.nr_option = 0;
   g_prm.anr_notch_on = 0;
+  g_prm.cw_receive = 0;
+  g_prm.cw_filter_index = 5;
   for (int i = 0; i < 14; i++) {
     EEPROMData.equalizerRec[i] = 100;       /* EEPROM.cpp:59,698 */
     g_prm.equalizer_rec[i] = 100;
@@ -380,6 +391,9 @@ int t41ref_set_params(const t41o_params *p) {
   if (p->nr_option != 0 && p->nr_option != 3) return -1;
   nrOptionSelect = p->nr_option;
   ANR_notchOn = (uint8_t)p->anr_notch_on;
+  if (p->cw_filter_index < 0 || p->cw_filter_index > 5) return -1;
+  T41State = p->cw_receive == 1 ? CW_RECEIVE : 1;      /* 1: the state the harness otherwise sits in */
+  CWFilterIndex = p->cw_filter_index;
   for (int i = 0; i < 14; i++) EEPROMData.equalizerRec[i] = p->equalizer_rec[i];
   if (p->mode != old.mode || p->f_lo_cut != old.f_lo_cut || p->f_hi_cut != old.f_hi_cut) CalcFilters();
   if (p->agc_mode != old.agc_mode || p->agc_thresh != old.agc_thresh) {

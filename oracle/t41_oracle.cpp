@@ -333,6 +333,9 @@ struct t41o_stream {
   float anr_d[512], anr_w[512];
   int anr_in_idx;
   float anr_lidx, anr_ngamma;
+  /* CW audio low-passes, T41/CWProcessing.cpp:38-49 */
+  float cw_state[5][12];
+  arm_biquad_cascade_df2T_instance_f32 cw[5];
   /* receive equaliser, T41/Filter.cpp:43-72 */
   float eq_state[14][8];
   arm_biquad_cascade_df2T_instance_f32 eq[14];
@@ -421,6 +424,7 @@ int ValidParams(const t41o_params *p) {
   if (p->f_hi_cut <= p->f_lo_cut) return 0;
   if (p->audio_volume < 0 || p->audio_volume > 100) return 0;
   if (p->nr_option != 0 && p->nr_option != 3) return 0;      /* Kim (1) and spectral (2) NR are not restated */
+  if (p->cw_filter_index < 0 || p->cw_filter_index > 5) return 0;
   return 1;
 }
 
@@ -744,6 +748,7 @@ void InitStream(t41o_stream *s) {
   s->last_set_rf_gain = s->prm.rf_gain;
   s->rf_gain = s->prm.rf_gain;
   s->osc_vect_q = 1.0;
+  for (int i = 0; i < 5; i++) arm_biquad_cascade_df2T_init_f32(&s->cw[i], 6, t41o_cw_coeffs[i], s->cw_state[i]);
   s->anr_lidx = 120.0;       /* T41/Noise.cpp:47,52 */
   s->anr_ngamma = 0.001;
   for (int i = 0; i < 14; i++) arm_biquad_cascade_df2T_init_f32(&s->eq[i], 4, t41o_eq_coeffs[i], s->eq_state[i]);
@@ -819,6 +824,8 @@ void t41o_default_params(t41o_params *p) {
   for (int i = 0; i < 14; i++) p->equalizer_rec[i] = 100;   /* T41/EEPROM.cpp:59,698 */
   p->nr_option = 0;
   p->anr_notch_on = 0;
+  p->cw_receive = 0;
+  p->cw_filter_index = 5;
 }
 
 void t41o_mode_default_cuts(int32_t mode, int32_t *f_lo_cut, int32_t *f_hi_cut) {
@@ -1173,6 +1180,13 @@ int t41o_process_block(t41o_stream *s, const float *iq, float *audio, int update
   }
   if (s->prm.anr_notch_on == 1) {
     Xanr(s, 1, L, R);
+    arm_copy_f32(R, L, kDec);
+  }
+
+  /* T41/Process.cpp:878-914: in the CW receive state (the decoder itself, DoCWReceiveProcessing, is not part of
+     this chain) the selected 12-pole low-pass, each filter with its own state */
+  if (s->prm.cw_receive == 1 && s->prm.cw_filter_index != 5) {
+    arm_biquad_cascade_df2T_f32(&s->cw[s->prm.cw_filter_index], L, R, kDec);
     arm_copy_f32(R, L, kDec);
   }
 

@@ -244,6 +244,7 @@ struct t41rx_ctx {
   float *d_sin = nullptr;
   float *d_zoom_iir = nullptr;
   float *d_eq_coeffs = nullptr;
+  float *d_cw_coeffs = nullptr;
   float *d_sam = nullptr;
   uint16_t *d_gradient = nullptr;
   uint32_t *d_varicode = nullptr;
@@ -311,6 +312,7 @@ static int UploadConstTables(t41rx_ctx *ctx) {
   if ((rc = UploadConst(&ctx->d_sin, h.sin_table))) return rc;
   if ((rc = UploadConst(&ctx->d_zoom_iir, h.zoom_iir))) return rc;
   if ((rc = UploadConst(&ctx->d_eq_coeffs, h.eq_coeffs))) return rc;
+  if ((rc = UploadConst(&ctx->d_cw_coeffs, h.cw_coeffs))) return rc;
   if ((rc = UploadConst(&ctx->d_sam, h.sam_consts))) return rc;
   if ((rc = UploadConst(&ctx->d_gradient, h.gradient))) return rc;
   if ((rc = UploadConst(&ctx->d_varicode, h.varicode))) return rc;
@@ -351,7 +353,7 @@ void t41rx_destroy(t41rx_ctx *ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   void *bufs[] = {ctx->d_cfg, ctx->d_state, ctx->d_fsets, ctx->d_nco_tab, ctx->d_twiddle, ctx->d_hann, ctx->d_sin,
-                  ctx->d_zoom_iir, ctx->d_eq_coeffs, ctx->d_sam, ctx->d_gradient, ctx->d_varicode, ctx->d_iq, ctx->d_audio,
+                  ctx->d_zoom_iir, ctx->d_eq_coeffs, ctx->d_cw_coeffs, ctx->d_sam, ctx->d_gradient, ctx->d_varicode, ctx->d_iq, ctx->d_audio,
                   ctx->d_spec, ctx->d_wf, ctx->d_bits, ctx->d_chars, ctx->d_fast_ids[0], ctx->d_phased_ids[0], ctx->d_fast_ids[1],
                   ctx->d_phased_ids[1], ctx->d_fast_ids[2], ctx->d_phased_ids[2], ctx->d_fast_ids[3], ctx->d_phased_ids[3],
                   ctx->d_iq16, ctx->d_audio16, ctx->d_aspec, ctx->d_ypixel, ctx->d_max_ave,
@@ -596,6 +598,7 @@ static int LaunchRange(t41rx_ctx *ctx, const float *iq, float *audio, int n_bloc
   a.sin_table = ctx->d_sin;
   a.zoom_iir = ctx->d_zoom_iir;
   a.eq_coeffs = ctx->d_eq_coeffs;
+  a.cw_coeffs = ctx->d_cw_coeffs;
   a.sam_consts = ctx->d_sam;
   a.gradient = ctx->d_gradient;
   a.varicode = ctx->d_varicode;

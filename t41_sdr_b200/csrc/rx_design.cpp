@@ -250,6 +250,7 @@ void DesignStreamCfg(const t41rx_params &p, const AgcConsts &agc, int filter_id,
   c->eq_on = (p.receive_eq_flag == 1) ? 1 : 0;                       /* Process.cpp:828 */
   c->nr_lms = (p.nr_option == 3) ? 1 : 0;                            /* Process.cpp:852 */
   c->anr_notch = (p.anr_notch_on == 1) ? 1 : 0;                      /* Process.cpp:860 */
+  c->cw_filter = (p.cw_receive == 1 && p.cw_filter_index != 5) ? p.cw_filter_index : -1;   /* Process.cpp:878-912 */
   for (int i = 0; i < 14; ++i) {                                     /* Filter.cpp:118-120,136-149 */
     const float level = (float)p.equalizer_rec[i] / 100.0;
     c->eq_scale[i] = (i & 1) ? level : -level;
@@ -317,6 +318,7 @@ int ValidateParams(const t41rx_params &p) {
   if (p.f_hi_cut <= p.f_lo_cut) return 0;
   if (p.audio_volume < 0 || p.audio_volume > 100) return 0;
   if (p.nr_option != 0 && p.nr_option != 3) return 0;         /* Kim (1) and spectral (2) noise reduction are not built */
+  if (p.cw_filter_index < 0 || p.cw_filter_index > 5) return 0;
   return 1;
 }
 

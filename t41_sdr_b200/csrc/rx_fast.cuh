@@ -182,7 +182,7 @@ struct RxRegs {
   /* configuration */
   /* small integers share one register (the kernel sits at its 128-register cap; spills go to L2 here) */
   unsigned mode : 4, agc_mode : 3, mirrored : 1, first_block : 1, nco_closed : 1, psk_enable : 1, eq_on : 1, nr_lms : 1,
-      anr_notch : 1;
+      anr_notch : 1, cw_filter : 1;
   F2 tw_a, tw_b;         /* this thread's base twiddles of the stride-64 and stride-8 radix-8 passes */
   const char *cp_src;    /* this thread's first 16-byte piece of quarter 0 of block 0 */
   unsigned cp_dst;       /* its shared-memory address in raw buffer 0 */
@@ -338,6 +338,34 @@ __device__ __noinline__ void SamPllLane(const float *tab, const float *sam_const
   st.sam_phzerror = phz;
   st.sam_fil_out = fil;
   st.sam_omega2 = om2;
+}
+
+/* CW audio low-pass, 6 transposed-direct-form-II biquads over 256 samples in place (CwFilterLane of rx_phases.cuh with
+   FMA contraction) */
+__device__ __noinline__ void CwFilterFast(float *aud, const float *coef, float *st) {
+  float b0[6], b1[6], b2[6], a1[6], a2[6], d1[6], d2[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    b0[j] = __ldg(coef + 5 * j); b1[j] = __ldg(coef + 5 * j + 1); b2[j] = __ldg(coef + 5 * j + 2);
+    a1[j] = __ldg(coef + 5 * j + 3); a2[j] = __ldg(coef + 5 * j + 4);
+    d1[j] = st[2 * j]; d2[j] = st[2 * j + 1];
+  }
+  float v = aud[0];
+#pragma unroll 2
+  for (int n = 0; n < kDec; ++n) {
+    const float vn = aud[min(n + 1, kDec - 1)];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      const float y = fmaf(b0[j], v, d1[j]);
+      d1[j] = fmaf(a1[j], y, fmaf(b1[j], v, d2[j]));
+      d2[j] = fmaf(a2[j], y, b2[j] * v);
+      v = y;
+    }
+    aud[n] = v;
+    v = vn;
+  }
+#pragma unroll
+  for (int j = 0; j < 6; ++j) { st[2 * j] = d1[j]; st[2 * j + 1] = d2[j]; }
 }
 
 /* ------------------------------------------------------------------ */
@@ -570,6 +598,7 @@ struct RxPair {
     r.eq_on = cf.eq_on != 0;
     r.nr_lms = cf.nr_lms != 0;
     r.anr_notch = cf.anr_notch != 0;
+    r.cw_filter = cf.cw_filter >= 0;
     if (tau == 2) {
       s[oMiscF + mAmWold] = st.am_wold;
       s[oMiscF + mAmX1] = st.am_lp_state[0];
@@ -1349,6 +1378,11 @@ struct RxPair {
         }
         if (r.anr_notch) XanrWarp(s, st, aud + 24, lane, true);
       }
+      PairSync();
+    }
+    if (r.cw_filter) {
+      /* Process.cpp:878-914: the CW receive state's audio low-pass; one lane (6 chained biquads per sample) */
+      if (tau == 0) CwFilterFast(aud + 24, a.cw_coeffs + 30 * cf.cw_filter, st.cw_state[cf.cw_filter]);
       PairSync();
     }
     T41RX_LAP(tm, 8);

@@ -34,6 +34,8 @@ void DefaultParams(t41rx_params *p) {
   for (int i = 0; i < 14; ++i) p->equalizer_rec[i] = 100;   /* EEPROM.cpp:59,698 */
   p->nr_option = 0;               /* nrOptionSelect */
   p->anr_notch_on = 0;            /* ANR_notchOn */
+  p->cw_receive = 0;              /* T41State = SSB_RECEIVE */
+  p->cw_filter_index = 5;         /* CWFilterIndex: off (gwv.cpp) */
 }
 
 void HostStateInit(StreamState *st) {
@@ -72,6 +74,7 @@ void HostModel::Init(int n) {
   sin_table[512] = 0.0f;
   zoom_iir.assign(&t41rx_zoom_iir[0][0], &t41rx_zoom_iir[0][0] + 80);
   eq_coeffs.assign(&t41rx_eq_coeffs[0][0], &t41rx_eq_coeffs[0][0] + 280);
+  cw_coeffs.assign(&t41rx_cw_coeffs[0][0], &t41rx_cw_coeffs[0][0] + 150);
   {
     /* SAM PLL constants, Demod.cpp:13-18 with omegaN = 200, pll_fmax = 4000 (gwv.cpp:64-65);
        exp() of a float argument is the single-precision overload under ISO C++ */

@@ -45,6 +45,7 @@ struct HostModel {
   std::vector<float> sin_table;         /* 513 */
   std::vector<float> zoom_iir;          /* 80 */
   std::vector<float> eq_coeffs;         /* 14 x 20 */
+  std::vector<float> cw_coeffs;         /* 5 x 30 */
   std::vector<float> sam_consts;        /* 4 */
   std::vector<uint16_t> gradient;       /* 117 */
   std::vector<uint32_t> varicode;       /* 128 */

@@ -120,6 +120,7 @@ struct LaunchArgs {
   const float *sin_table;     /* 513: sin(2*pi*k/512), arm_sin_f32's table */
   const float *zoom_iir;      /* 4 x 20: zoom x2..x16 biquad coefficients (FIR.cpp:582-885) */
   const float *eq_coeffs;     /* 14 x 20: receive-equaliser band-pass biquads (FIR.cpp:279-371) */
+  const float *cw_coeffs;     /* 5 x 30: CW audio low-passes (FIR.cpp:15-65) */
   const float *sam_consts;    /* omega_min, omega_max, g1, g2 (Demod.cpp:13-18) */
   const uint16_t *gradient;   /* 117 */
   const uint32_t *varicode;   /* 128: code | bits << 16 | ascii << 24 */
@@ -1611,6 +1612,40 @@ T41RX_DEV void PhNrNotch(Cta &c, int tid) {
   if (cf.anr_notch) XanrPass(aud, s + vAnrD, s + vAnrW, st, true);   /* Process.cpp:860-865 */
 }
 
+/* CW audio low-pass (Process.cpp:878-914: CW receive state, CWFilterIndex 0..4): 6 transposed-direct-form-II
+   biquads over the 256 samples at aud, arm_biquad_cascade_df2T_f32's operation order, all stages per sample in
+   registers; st: the selected filter's 12 state values.  One lane. */
+T41RX_DEV void CwFilterLane(float *aud, const float *coef, float *st) {
+  float b0[6], b1[6], b2[6], a1[6], a2[6], d1[6], d2[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    b0[j] = coef[5 * j]; b1[j] = coef[5 * j + 1]; b2[j] = coef[5 * j + 2]; a1[j] = coef[5 * j + 3]; a2[j] = coef[5 * j + 4];
+    d1[j] = st[2 * j]; d2[j] = st[2 * j + 1];
+  }
+  for (int n = 0; n < kDec; ++n) {
+    float v = aud[n];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      const float y = b0[j] * v + d1[j];
+      const float t = b1[j] * v + a1[j] * y;
+      d1[j] = t + d2[j];
+      d2[j] = b2[j] * v + a2[j] * y;
+      v = y;
+    }
+    aud[n] = v;
+  }
+#pragma unroll
+  for (int j = 0; j < 6; ++j) { st[2 * j] = d1[j]; st[2 * j + 1] = d2[j]; }
+}
+
+T41RX_DEV void PhCwFilter(Cta &c, int tid) {
+  const int g = SerialStream(c, tid);
+  if (g < 0) return;
+  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+  if (cf.cw_filter < 0) return;
+  CwFilterLane(Slot(c, g) + vAud + 23, c.a.cw_coeffs + 30 * cf.cw_filter, c.a.st[Sid(c, g)].cw_state[cf.cw_filter]);
+}
+
 T41RX_DEV void PhInterp1(Cta &c, int tid) {
   for (int g = 0; g < c.ng; ++g) {
     float *s = Slot(c, g);
@@ -2219,6 +2254,7 @@ T41RX_DEV void PhSpecFrameWrite(Cta &c, int tid) {
   RX_PHASE(PhNrStage(c, tid, 0));                                        \
   RX_PHASE(PhNrNotch(c, tid));                                           \
   RX_PHASE(PhNrStage(c, tid, 1));                                        \
+  RX_PHASE(PhCwFilter(c, tid));                                          \
   RX_PHASE(PhInterp1b(c, tid));                                          \
   RX_PHASE(PhInterp2(c, tid));                                           \
   RX_PHASE(PhBlockEnd(c, tid));

@@ -63,6 +63,7 @@ struct StreamCfg {
   int32_t eq_on;               /* receiveEQFlag == ON (Process.cpp:828) */
   int32_t nr_lms;              /* nrOptionSelect == 3 (Process.cpp:852-856) */
   int32_t anr_notch;           /* ANR_notchOn == 1 (Process.cpp:860-865) */
+  int32_t cw_filter;           /* CW audio low-pass 0..4 in the chain (T41State == CW_RECEIVE, CWFilterIndex != 5), else -1 */
   float eq_scale[14];          /* -/+ recEQ_LevelScale[i] = (float)equalizerRec[i] / 100.0, sign as Filter.cpp:136-149 */
   int32_t zoom_samples;        /* min(2048 >> zoom, 512), FFT.cpp:78-81 */
   int32_t nco_epoch;           /* bumped when NCOFreq changes: forces one exact block (amplitude transient) */
@@ -143,6 +144,8 @@ struct StreamState {
   int32_t anr_in_idx;
   float anr_lidx, anr_ngamma;
   int32_t pad3_;
+  /* CW audio low-passes: CW_AudioFilter1..5_state (CWProcessing.cpp:38-42), each filter keeps its own */
+  float cw_state[5][12];
   int16_t audio_ypixel[kAudioSpecPixels + 2];
 };
 

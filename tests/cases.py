@@ -194,8 +194,22 @@ def c7_lms_notch():
     return Case("c7_lms_notch", [(seg1, T1), (seg2, T2)], iqs, row_every=4)
 
 
+def c8_cw_filters():
+    """The CW receive state's audio low-passes (Process.cpp:878-914): every filter index, off,
+    outside the CW state, switched between the segments (each filter keeps its own state), behind equaliser + notch."""
+    T1, T2 = 7, 6
+    T = T1 + T2
+    tilt = [100, 80, 0, 120, 55, 100, 30, 90, 100, 10, 70, 100, 45, 100]
+    iqs = [synth.two_tone(920 + k, T, 46300.0 + 150.0 * k, 48200.0 - 90.0 * k) for k in range(8)]
+    cw = lambda i, **kw: P(mode=kw.pop("mode", USB), cw_receive=1, cw_filter_index=i, **kw)
+    seg1 = [cw(0), cw(1, mode=LSB), cw(2), cw(3, agc_mode=0), cw(4), cw(5), P(mode=USB, cw_filter_index=2),
+            _eq(cw(1, anr_notch_on=1), tilt)]
+    seg2 = [cw(3), cw(1, mode=LSB), P(mode=USB), cw(0, agc_mode=0), cw(5), cw(2), cw(2), _eq(cw(4, anr_notch_on=1), tilt)]
+    return Case("c8_cw_filters", [(seg1, T1), (seg2, T2)], iqs, row_every=5)
+
+
 ALL_CASES = [c1_single_usb, c1_single_usb_agc_off, c2_ssb_am_mix, c3_nfm_sam_agc, c4_zoom_rows, c5_psk31,
-             edge_silence_fullscale, edge_param_changes, edge_rf_gain_ramp, c6_receive_eq, c7_lms_notch]
+             edge_silence_fullscale, edge_param_changes, edge_rf_gain_ramp, c6_receive_eq, c7_lms_notch, c8_cw_filters]
 
 
 def run_case_on(case, make_stream):

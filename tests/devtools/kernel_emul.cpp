@@ -79,6 +79,7 @@ int emul_process(Emul *e, const float *iq, float *audio, int n_blocks, int row_e
   a.sin_table = h.sin_table.data();
   a.zoom_iir = h.zoom_iir.data();
   a.eq_coeffs = h.eq_coeffs.data();
+  a.cw_coeffs = h.cw_coeffs.data();
   a.sam_consts = h.sam_consts.data();
   a.gradient = h.gradient.data();
   a.varicode = h.varicode.data();
