@@ -82,6 +82,17 @@ def workload(n_blocks):
         else:
             params.append(cases.P(mode=cases.AM, nco_freq=nco, agc_mode=1))
             sigs.append(synth.am(900 + k, n_blocks, mode=cases.AM, nco_freq=nco, depth=0.5, f_mod=400.0))
+    if os.environ.get("T41RX_BENCH_WORKLOAD") == "c3":   # developer knob: BASELINE.json configs[2] (NFM + SAM with AGC), not the metric
+        params, sigs = [], []
+        for k in range(N_DISTINCT):
+            agc = 1 + (k % 4)
+            if k % 2 == 0:
+                params.append(cases.P(mode=cases.NFM, agc_mode=agc, nfm_filter_bw=12000))
+                sigs.append(synth.nfm(300 + k, n_blocks, level_step_block=n_blocks // 2, level_step_db=-20.0))
+            else:
+                params.append(cases.P(mode=cases.SAM, agc_mode=agc))
+                sigs.append(synth.am(300 + k, n_blocks, mode=cases.SAM, carrier_offset=float(r.uniform(-200, 200)), depth=0.5,
+                                     level_step_block=n_blocks // 2, level_step_db=-20.0))
     if os.environ.get("T41RX_BENCH_MODE"):       # developer knob: every receiver in one mode (0 USB, 2 AM) / AGC off (-1)
         m = int(os.environ["T41RX_BENCH_MODE"])
         for p in params:

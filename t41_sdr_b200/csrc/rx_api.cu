@@ -256,6 +256,11 @@ struct t41rx_ctx {
      T41RX_FLAG_FAST_SAM (bit 1: SAM receivers too). */
   std::vector<int32_t> h_fast_ids[4], h_phased_ids[4];
   int32_t *d_fast_ids[4] = {nullptr, nullptr, nullptr, nullptr}, *d_phased_ids[4] = {nullptr, nullptr, nullptr, nullptr};
+  /* the throughput kernel's receivers once more, those with a slow serial stage (SAM PLL, equaliser, LMS, CW filter)
+     first: the pairs of a CTA advance in lock-step, so slow receivers share CTAs among themselves when a launch
+     covers the whole bank; empty when there is nothing to group */
+  std::vector<int32_t> h_fast_grouped[4];
+  int32_t *d_fast_grouped[4] = {nullptr, nullptr, nullptr, nullptr};
   bool ids_dirty = true;
 
   /* device staging for the host-buffer entry point */
@@ -356,6 +361,7 @@ void t41rx_destroy(t41rx_ctx *ctx) {
                   ctx->d_zoom_iir, ctx->d_eq_coeffs, ctx->d_cw_coeffs, ctx->d_sam, ctx->d_gradient, ctx->d_varicode, ctx->d_iq, ctx->d_audio,
                   ctx->d_spec, ctx->d_wf, ctx->d_bits, ctx->d_chars, ctx->d_fast_ids[0], ctx->d_phased_ids[0], ctx->d_fast_ids[1],
                   ctx->d_phased_ids[1], ctx->d_fast_ids[2], ctx->d_phased_ids[2], ctx->d_fast_ids[3], ctx->d_phased_ids[3],
+                  ctx->d_fast_grouped[0], ctx->d_fast_grouped[1], ctx->d_fast_grouped[2], ctx->d_fast_grouped[3],
                   ctx->d_iq16, ctx->d_audio16, ctx->d_aspec, ctx->d_ypixel, ctx->d_max_ave,
                   ctx->d_sframes, ctx->d_aframes};
   for (void *b : bufs)
@@ -419,6 +425,10 @@ int t41rx_create(t41rx_ctx **out, int n_streams, int device) {
   if (cudaMalloc(&ctx->d_cfg, sizeof(StreamCfg) * n_streams) != cudaSuccess ||
       cudaMalloc(&ctx->d_state, sizeof(StreamState) * n_streams) != cudaSuccess ||
       cudaMalloc(&ctx->d_nco_tab, sizeof(double) * 192 * n_streams) != cudaSuccess ||
+      cudaMalloc(&ctx->d_fast_grouped[0], sizeof(int32_t) * n_streams) != cudaSuccess ||
+      cudaMalloc(&ctx->d_fast_grouped[1], sizeof(int32_t) * n_streams) != cudaSuccess ||
+      cudaMalloc(&ctx->d_fast_grouped[2], sizeof(int32_t) * n_streams) != cudaSuccess ||
+      cudaMalloc(&ctx->d_fast_grouped[3], sizeof(int32_t) * n_streams) != cudaSuccess ||
       cudaMalloc(&ctx->d_fast_ids[0], sizeof(int32_t) * n_streams) != cudaSuccess ||
       cudaMalloc(&ctx->d_phased_ids[0], sizeof(int32_t) * n_streams) != cudaSuccess ||
       cudaMalloc(&ctx->d_fast_ids[1], sizeof(int32_t) * n_streams) != cudaSuccess ||
@@ -661,6 +671,7 @@ static int LaunchRange(t41rx_ctx *ctx, const float *iq, float *audio, int n_bloc
     LaunchArgs f = a;
     f.n_streams = f_len;
     f.stream_ids = (p_len > 0) ? ctx->d_fast_ids[v] + f_off : nullptr;     /* nothing for the other kernel in range: contiguous */
+    if (first == 0 && count == ctx->n_streams && !ctx->h_fast_grouped[v].empty()) f.stream_ids = ctx->d_fast_grouped[v];
     if (has_row && (a.spec_rows || a.wf_rows)) {
       t41rx_rows_kernel<<<(f_len + kG - 1) / kG, kNT, kSmemFloats * sizeof(float), st>>>(f);
       CUDA_TRY(cudaGetLastError());
@@ -696,6 +707,17 @@ static int RefreshKernelLists(t41rx_ctx *ctx) {
     }
     if (!ctx->h_fast_ids[v].empty())
       CUDA_TRY(cudaMemcpy(ctx->d_fast_ids[v], ctx->h_fast_ids[v].data(), sizeof(int32_t) * ctx->h_fast_ids[v].size(), cudaMemcpyHostToDevice));
+    {
+      auto slow = [&](int32_t s) {
+        const StreamCfg &cf = ctx->host.cfg[s];
+        return cf.mode == kModeSam || cf.eq_on || cf.nr_lms || cf.anr_notch || cf.cw_filter >= 0;
+      };
+      std::vector<int32_t> &g = ctx->h_fast_grouped[v];
+      g = ctx->h_fast_ids[v];
+      const auto mid = std::stable_partition(g.begin(), g.end(), slow);
+      if (mid == g.begin() || mid == g.end()) g.clear();         /* all alike: the plain list (or no list) does */
+      else CUDA_TRY(cudaMemcpy(ctx->d_fast_grouped[v], g.data(), sizeof(int32_t) * g.size(), cudaMemcpyHostToDevice));
+    }
     if (!ctx->h_phased_ids[v].empty())
       CUDA_TRY(cudaMemcpy(ctx->d_phased_ids[v], ctx->h_phased_ids[v].data(), sizeof(int32_t) * ctx->h_phased_ids[v].size(), cudaMemcpyHostToDevice));
   }
