@@ -35,13 +35,13 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one t41rx_stream_rx_kernel launch of this workload from the
-# committed `ncu --set full` capture (profiles/summary_r01_final.md: 1078.9 MB read + 502.4 MB written at 1024
+# committed `ncu --set full` capture (profiles/summary_r01_final.md: 1078.9 MB read + 501.2 MB written at 1024
 # receivers x 64 blocks; the algorithmic figure is 1610.6 MB, part of the last audio blocks is still in L2 at
 # kernel end); only meaningful for the default workload, None otherwise
-TRAFFIC_BYTES_PER_LAUNCH = 1078935000 + 502429440
+TRAFFIC_BYTES_PER_LAUNCH = 1078915000 + 501194752
 # smsp__inst_executed.sum / stream-blocks of the same capture: warp-instructions the stream kernel executes per
 # 2048-sample block of one receiver (the chain is bound by FP32 issue slots, not by HBM: DESIGN.md section 3.5)
-WARP_INSTR_PER_STREAM_BLOCK = 7921
+WARP_INSTR_PER_STREAM_BLOCK = 7975
 N_SMS, ISSUE_SLOTS_PER_SM = 148, 4
 
 METRIC = "aggregate IQ Msamples/s (full RX chain)"
