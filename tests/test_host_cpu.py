@@ -200,3 +200,18 @@ def test_wav_reader_matches_reference_live(tmp_path):
         state["w"].close()
         assert got[:2] == want[:2], name
         assert np.array_equal(got[2], want[2]) and np.array_equal(got[3], want[3]), name
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the CPU chain on the host cores: oracle/_ref when built, else the oracle port) must
+    run without a GPU and print the contract's JSON line."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                          "--cpu-seconds", "1", "--blocks", "8"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["unit"] == "Msamples/s"
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
