@@ -215,6 +215,9 @@ int t41rx_bind_control_frames(t41rx_ctx *ctx, uint8_t *spec_frames, uint8_t *aud
 /* The S-meter reading DrawSmeterBar() derives from audioMaxSquaredAve (Display.cpp:959-981, TCVSDR_SMETER build):
  * dBm, given bands[].gainCorrection, bands[].RFgain (t41rx_debug.rf_gain) and rfGainAllBands.  Host arithmetic. */
 float t41rx_smeter_dbm(float audio_max_sq_ave, float gain_correction, int32_t rf_gain, int32_t rf_gain_all_bands);
+/* Length of the S-meter bar in pixels for that reading (Display.cpp:995-998): map(dbm, S1 = -127, S9 = -73, 0, 9 * 12)
+ * in float (Teensy core map()), truncated to int16, limited to 0 .. SMETER_BAR_LENGTH = 180 (Display.h:69). */
+int32_t t41rx_smeter_bar(float dbm);
 
 /* Instrumentation for bench.py: kernels launched by this context so far, and the CUDA-event
  * duration (ms) of all kernels of the most recent t41rx_process[_device] call (valid after t41rx_synchronize). */

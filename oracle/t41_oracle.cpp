@@ -1239,6 +1239,18 @@ void t41o_capture_control_frames(t41o_stream *s, uint8_t *spec_frame_rows, uint8
   s->control_data_flag = (spec_frame_rows != 0) || (audio_frame_rows != 0);
 }
 
+/* T41/Display.cpp:942,958,995-998: smeterPad = map(dbm, -73.0-9*6.0, -73.0, 0, 9*pixels_per_s) with the float overload
+   of map(), into an int16_t, then max(0, .) and min(SMETER_BAR_LENGTH = 180, .) */
+int32_t t41o_smeter_bar(float dbm) {
+  const float pixels_per_s = 12;
+  const float v = (dbm - (float)(-73.0 - 9 * 6.0)) * ((float)(9 * pixels_per_s) - (float)0) / ((float)-73.0 - (float)(-73.0 - 9 * 6.0)) + (float)0;
+  int16_t pad = (v < -32768.0f || v != v) ? (int16_t)-32768 : (v > 32767.0f ? (int16_t)32767 : (int16_t)v);
+  int r = pad;
+  r = r > 0 ? r : 0;
+  r = r < 180 ? r : 180;
+  return r;
+}
+
 /* T41/Display.cpp:959-981 (TCVSDR_SMETER): dbm_calibration = 22.0, slope = 10.0, cons = -92 are floats, attenuator = 0
    (Display.cpp:146); the RFgain term's 1.5 is a double literal, so the tail of the sum is FP64 */
 float t41o_smeter_dbm(float audio_max_sq_ave, float gain_correction, int32_t rf_gain, int32_t rf_gain_all_bands) {

@@ -150,6 +150,8 @@ void t41o_capture_control_frames(t41o_stream *s, uint8_t *spec_frame_rows, uint8
 /* S-meter reading the display derives from audioMaxSquaredAve (T41/Display.cpp:976-981, TCVSDR_SMETER build,
  * MyConfigurationFile.h:34): dBm.  Display.cpp is not part of the Tier-A build; this is a restatement only. */
 float t41o_smeter_dbm(float audio_max_sq_ave, float gain_correction, int32_t rf_gain, int32_t rf_gain_all_bands);
+/* T41/Display.cpp:995-998: length of the S-meter bar (restatement, like t41o_smeter_dbm) */
+int32_t t41o_smeter_bar(float dbm);
 
 /* ---- control-path functions exposed for unit tests ---- */
 void t41o_calc_fir_coeffs(float *coeffs, int num_coeffs, float fc, float astop, int type, float dfc, float fs);

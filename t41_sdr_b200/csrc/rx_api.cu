@@ -783,6 +783,21 @@ float t41rx_smeter_dbm(float audio_max_sq_ave, float gain_correction, int32_t rf
   return (float)((double)head - (double)(float)rf_gain * 1.5 - (double)rf_gain_all_bands);
 }
 
+/* Display.cpp:942,995-998 (TCVSDR_SMETER: pixels_per_s = 12) */
+int32_t t41rx_smeter_bar(float dbm) {
+  const float pixels_per_s = 12;
+  const float in_min = (float)(-73.0 - 9 * 6.0), in_max = (float)-73.0, out_min = (float)0, out_max = (float)(9 * pixels_per_s);
+  const volatile float num = (dbm - in_min) * (out_max - out_min);
+  const float v = num / (in_max - in_min) + out_min;
+  int pad;
+  if (!(v > -32769.0f)) pad = -32768;        /* the int16 conversion of what does not fit saturates on the target */
+  else if (v > 32767.0f) pad = 32767;
+  else pad = (int16_t)v;
+  pad = pad < 0 ? 0 : pad;
+  pad = pad > 180 ? 180 : pad;
+  return pad;
+}
+
 int t41rx_synchronize(t41rx_ctx *ctx) {
   if (!ctx) return Fail(T41RX_EINVAL, "t41rx_synchronize: null context%s");
   CUDA_TRY(cudaSetDevice(ctx->device));

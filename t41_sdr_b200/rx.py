@@ -80,7 +80,7 @@ EXPORTS = (
     "t41rx_num_streams", "t41rx_set_params", "t41rx_set_params_each", "t41rx_get_params",
     "t41rx_get_tables", "t41rx_get_debug", "t41rx_design_tables", "t41rx_process", "t41rx_process_q15",
     "t41rx_process_device", "t41rx_synchronize", "t41rx_kernel_launches", "t41rx_last_kernel_ms",
-    "t41rx_stream_kernel_times", "t41rx_bind_audio_spectrum", "t41rx_bind_control_frames", "t41rx_smeter_dbm",
+    "t41rx_stream_kernel_times", "t41rx_bind_audio_spectrum", "t41rx_bind_control_frames", "t41rx_smeter_dbm", "t41rx_smeter_bar",
     "t41rx_load_wav", "t41rx_read_wave", "t41rx_wav_sample_rate", "t41rx_wav_close",
     "t41rx_last_error", "t41rx_version")
 
@@ -123,6 +123,8 @@ def lib():
         L.t41rx_bind_control_frames.argtypes = [vp, vp, vp]
         L.t41rx_smeter_dbm.argtypes = [C.c_float, C.c_float, C.c_int32, C.c_int32]
         L.t41rx_smeter_dbm.restype = C.c_float
+        L.t41rx_smeter_bar.argtypes = [C.c_float]
+        L.t41rx_smeter_bar.restype = C.c_int32
         L.t41rx_load_wav.argtypes = [C.POINTER(vp), C.c_char_p, C.c_uint32]
         L.t41rx_read_wave.argtypes = [vp, vp, ip]
         L.t41rx_wav_sample_rate.argtypes = [vp]
@@ -167,6 +169,11 @@ def design_tables(param_sequence):
 def smeter_dbm(audio_max_sq_ave, gain_correction=0.0, rf_gain=1, rf_gain_all_bands=1):
     """DrawSmeterBar()'s dBm reading from audioMaxSquaredAve (Display.cpp:959-981)."""
     return float(lib().t41rx_smeter_dbm(audio_max_sq_ave, gain_correction, rf_gain, rf_gain_all_bands))
+
+
+def smeter_bar(dbm):
+    """Pixels of the S-meter bar for a dBm reading (Display.cpp:995-998)."""
+    return int(lib().t41rx_smeter_bar(dbm))
 
 
 def _np_ptr(a):

@@ -95,6 +95,8 @@ def tier_b():
         lib.t41o_capture_control_frames.restype = None
         lib.t41o_smeter_dbm.restype = C.c_float
         lib.t41o_smeter_dbm.argtypes = [C.c_float, C.c_float, C.c_int32, C.c_int32]
+        lib.t41o_smeter_bar.argtypes = [C.c_float]
+        lib.t41o_smeter_bar.restype = C.c_int32
         lib.t41o_log10f_fast.restype = C.c_float
         lib.t41o_log10f_fast.argtypes = [C.c_float]
         lib.t41o_approx_atan2.restype = C.c_float

@@ -152,6 +152,9 @@ def test_smeter_helper_matches_oracle():
         for gc, rf, rfall in ((-2.0, 1, 1), (3.5, 15, -10), (0.0, 7, 20)):
             a, b = rx.smeter_dbm(float(v), gc, rf, rfall), lib.t41o_smeter_dbm(float(v), gc, rf, rfall)
             assert a == b or (np.isnan(a) and np.isnan(b)) or (np.isinf(a) and a == b), (v, gc, rf, rfall, a, b)
+    for dbm in np.concatenate([rng.uniform(-160, 0, 300), [-127.0, -73.0, -73.0 + 1e-4, -200.0, 50.0]]).astype(np.float32):
+        assert rx.smeter_bar(float(dbm)) == lib.t41o_smeter_bar(float(dbm)), dbm
+    assert rx.smeter_bar(-127.0) == 0 and rx.smeter_bar(-73.0) == 108 and rx.smeter_bar(0.0) == 180
     # the comment in the reference: audioMaxSquaredAve = 40 is about S9 (-73 dBm) on a calibrated band
     assert -80.0 < rx.smeter_dbm(40.0, -2.0, 1, 1) < -50.0
 
