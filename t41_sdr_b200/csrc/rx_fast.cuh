@@ -293,15 +293,12 @@ __device__ __forceinline__ void MidPass(float2 *buf, const float2 (&hm)[8], int 
 __device__ __forceinline__ float Atan2Quick(float y, float x) {
   const float pi = 3.1415926535897932384626433832795f;
   const float tpi = 6.283185307179586476925286766559f;
-  if (x != 0.0f) {
-    if (fabsf(x) > fabsf(y)) {
-      const float a = AtanPoly(__fdividef(y, x));
-      return (x > 0.0f) ? a : ((y >= 0.0f) ? a + pi : a - pi);
-    }
-    const float a = AtanPoly(__fdividef(x, y));
-    return (y > 0.0f) ? tpi - a : -a - tpi;
-  }
-  return (y > 0.0f) ? tpi : ((y < 0.0f) ? -tpi : 0.0f);
+  const bool wide = fabsf(x) > fabsf(y);
+  const float p = AtanPoly(__fdividef(wide ? y : x, wide ? x : y));
+  const float r_wide = (x > 0.0f) ? p : ((y >= 0.0f) ? p + pi : p - pi);
+  const float r_tall = (y > 0.0f) ? tpi - p : -p - tpi;
+  const float r_axis = (y > 0.0f) ? tpi : ((y < 0.0f) ? -tpi : 0.0f);
+  return (x != 0.0f) ? (wide ? r_wide : r_tall) : r_axis;
 }
 
 __device__ __noinline__ void SamPllLane(const float *tab, const float *sam_consts, StreamState &st, const float2 *z,
@@ -310,29 +307,40 @@ __device__ __noinline__ void SamPllLane(const float *tab, const float *sam_const
   const float omega_min = __ldg(sam_consts + 0), omega_max = __ldg(sam_consts + 1);
   const float g1 = __ldg(sam_consts + 2), g2 = __ldg(sam_consts + 3);
   float phz = st.sam_phzerror, fil = st.sam_fil_out, om2 = st.sam_omega2;
-  float2 v = z[0];
-#pragma unroll 1
-  for (int i = 0; i < kDec; ++i) {
-    const float2 vn = z[min(i + 1, kDec - 1)];     /* off the chain */
-    /* arm_sin_f32 / arm_cos_f32 (table + linear interpolation) with one index computation: phz is in [0, 2 pi),
-       the cosine reads a quarter of the table further on */
-    const float fidx = phz * (512.0f * 0.159154943092f);
+  /* arm_sin_f32 / arm_cos_f32 (table + linear interpolation) with one index computation: phz is in [0, 2 pi), the
+     cosine reads a quarter of the table further on */
+  auto sincos_tab = [&](float ph, float &sn_, float &cs_) {
+    const float fidx = ph * (512.0f * 0.159154943092f);
     const int idx = (int)fidx;
     const float fr = fidx - (float)idx;
     const int is = idx & 511, ic = (idx + 128) & 511;
     const float s0 = tab[is], s1 = tab[is + 1], c0 = tab[ic], c1 = tab[ic + 1];
-    const float sn = fmaf(fr, s1 - s0, s0), cs = fmaf(fr, c1 - c0, c0);
+    sn_ = fmaf(fr, s1 - s0, s0);
+    cs_ = fmaf(fr, c1 - c0, c0);
+  };
+  /* the phase of sample i + 1 is phz + the loop filter's output of sample i - 1: its sine / cosine are formed beside
+     sample i's arctangent, two dependent chains side by side */
+  float sn, cs;
+  sincos_tab(phz, sn, cs);
+  float2 v = z[0];
+#pragma unroll 1
+  for (int i = 0; i < kDec; ++i) {
+    const float2 vn = z[min(i + 1, kDec - 1)];     /* off the chain */
+    float phz_n = phz + fil;
+    phz_n = (phz_n >= tpi) ? phz_n - tpi : phz_n;  /* |fil_out| is far below 2 pi: one wrap at most */
+    phz_n = (phz_n < 0.0f) ? phz_n + tpi : phz_n;
+    float sn_n, cs_n;
+    sincos_tab(phz_n, sn_n, cs_n);
     const float ai = cs * v.x, bi = sn * v.x, aq = cs * v.y, bq = sn * v.y;
     const float corr0 = ai + bq;
     const float corr1 = aq - bi;
     audio[i] = (ai - bi) + (aq + bq);              /* the fade leveller is a no-op */
     const float det = Atan2Quick(corr1, corr0);
-    const float del_out = fil;
     om2 = fminf(fmaxf(fmaf(g2, det, om2), omega_min), omega_max);
     fil = fmaf(g1, det, om2);
-    phz = phz + del_out;
-    phz = (phz >= tpi) ? phz - tpi : phz;          /* |fil_out| is far below 2 pi: one wrap at most */
-    phz = (phz < 0.0f) ? phz + tpi : phz;
+    phz = phz_n;
+    sn = sn_n;
+    cs = cs_n;
     v = vn;
   }
   st.sam_phzerror = phz;

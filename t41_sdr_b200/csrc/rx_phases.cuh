@@ -202,22 +202,18 @@ T41RX_DEV float AtanPoly(float z) {               /* Utility.cpp:298-302 */
 }
 
 T41RX_DEV float Atan2Approx(float y, float x) {   /* Demod.cpp:148-197 (TPI quirk kept) */
+  /* the reference's branches as selects around ONE division (the operands it would divide on the branch taken): the
+     callers run this inside long serial chains, where a branch per sample keeps the compiler from overlapping the
+     chain with anything else */
   const float pi = 3.1415926535897932384626433832795f;
   const float tpi = 6.283185307179586476925286766559f;
-  if (x != 0.0f) {
-    if (fabsf(x) > fabsf(y)) {
-      const float z = y / x;
-      if (x > 0.0f) return AtanPoly(z);
-      if (y >= 0.0f) return AtanPoly(z) + pi;
-      return AtanPoly(z) - pi;
-    }
-    const float z = x / y;
-    if (y > 0.0f) return -AtanPoly(z) + tpi;
-    return -AtanPoly(z) - tpi;
-  }
-  if (y > 0.0f) return tpi;
-  if (y < 0.0f) return -tpi;
-  return 0.0f;
+  const bool wide = fabsf(x) > fabsf(y);
+  const float z = (wide ? y : x) / (wide ? x : y);        /* x != 0 and not wide: |y| >= |x| > 0 */
+  const float p = AtanPoly(z);
+  const float r_wide = (x > 0.0f) ? p : ((y >= 0.0f) ? p + pi : p - pi);
+  const float r_tall = (y > 0.0f) ? -p + tpi : -p - tpi;
+  const float r_axis = (y > 0.0f) ? tpi : ((y < 0.0f) ? -tpi : 0.0f);
+  return (x != 0.0f) ? (wide ? r_wide : r_tall) : r_axis;
 }
 
 /* arm_sin_f32 / arm_cos_f32 tail: linear interpolation in the 513-entry table */
@@ -1404,10 +1400,20 @@ T41RX_DEV void PhDemodSerial(Cta &c, int tid) {
     const float g1 = LdgRO(c.a.sam_consts + 2);
     const float g2 = LdgRO(c.a.sam_consts + 3);
     float phz = st.sam_phzerror, fil = st.sam_fil_out, om2 = st.sam_omega2;
+    /* The phase of sample i + 1 is phz + the loop filter's output of sample i - 1 (del_out): it does not wait for
+       sample i's detector.  Its sine / cosine are therefore formed beside sample i's arctangent - the same
+       operations on the same values as the reference's loop, two dependent chains side by side instead of one. */
+    float sn = TableTurns(s + vSamSin, phz * 0.159154943092f);
+    float cs = TableTurns(s + vSamSin, phz * 0.159154943092f + 0.25f);
     for (int i = 0; i < kDec; ++i) {
       const float2 z = dem[i];
-      const float sn = TableTurns(s + vSamSin, phz * 0.159154943092f);
-      const float cs = TableTurns(s + vSamSin, phz * 0.159154943092f + 0.25f);
+      float phz_n = phz + fil;                       /* del_out = fil_out before this sample's update */
+      /* the reference's two while loops: phz is in [0, 2 pi) and |fil_out| <= g1 * 2 pi + omega_max < 1.2, so each
+         runs at most once */
+      phz_n = (phz_n >= tpi) ? phz_n - tpi : phz_n;
+      phz_n = (phz_n < 0.0f) ? phz_n + tpi : phz_n;
+      const float sn_n = TableTurns(s + vSamSin, phz_n * 0.159154943092f);
+      const float cs_n = TableTurns(s + vSamSin, phz_n * 0.159154943092f + 0.25f);
       const float ai = cs * z.x, bi = sn * z.x, aq = cs * z.y, bq = sn * z.y;
       const float corr0 = +ai + bq;
       const float corr1 = -bi + aq;
@@ -1419,14 +1425,13 @@ T41RX_DEV void PhDemodSerial(Cta &c, int tid) {
       audio = (audio + 0.0f) - 0.0f;
       s[vAud + 23 + i] = audio;
       const float det = Atan2Approx(corr1, corr0);
-      const float del_out = fil;
       om2 = om2 + g2 * det;
       if (om2 < omega_min) om2 = omega_min;
       else if (om2 > omega_max) om2 = omega_max;
       fil = g1 * det + om2;
-      phz = phz + del_out;
-      while (phz >= tpi) phz -= tpi;
-      while (phz < 0.0f) phz += tpi;
+      phz = phz_n;
+      sn = sn_n;
+      cs = cs_n;
     }
     st.sam_phzerror = phz;
     st.sam_fil_out = fil;

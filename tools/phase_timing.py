@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Developer tool: per-phase cycle breakdown of the fused RX kernel (CTA 0, thread 0).
-Needs a library built with -DT41RX_PHASE_TIMING (tools/build_variants.sh) selected via T41RX_LIB."""
+Needs a library built with -DT41RX_PHASE_TIMING (tools/build_phase_timing.sh) selected via T41RX_LIB;\nenv: ROWS (row period, 0 = none), FLAGS (t41rx_process flags, default 2), bench.py's T41RX_BENCH_* workload knobs."""
 import ctypes as C
 import os
 import sys
@@ -17,7 +17,8 @@ from t41_sdr_b200 import rx  # noqa: E402
 
 NAMES = ["Load", "DcWarm", "DcMain", "DcVerify", "DcFix", "NcoPrep", "Mix", "Dec1", "Dec2", "PostDec2", "NfmAsm", "NfmAsm2",
          "FftA0", "FftA1", "FftA2", "Mask", "FftB0", "FftB1", "FftB2", "AgcPre", "Max1", "Max2", "Max3", "Max4", "Max5",
-         "Max6", "Max7", "AgcSerial", "AgcPost", "DemodPar", "DemodSer", "Interp1b", "Interp2", "BlockEnd"]
+         "Max6", "Max7", "AgcSerial", "AgcPost", "DemodPar", "DemodSer", "EqBands", "EqSum", "NrStageIn", "NrNotch", "NrStageOut",
+         "CwFilter", "Interp1b", "Interp2", "BlockEnd"]
 ROW_NAMES = ["ZoomIir", "SpecWin", "SpecFft0", "SpecFft1", "SpecFft2", "SpecRow"]
 
 
@@ -36,7 +37,8 @@ def main():
     L = rx.lib()
     buf = (C.c_ulonglong * 128)()
     for it in range(3):
-        eng.process_device(iq.data_ptr(), audio.data_ptr(), T, rows, spec.data_ptr(), wf.data_ptr())
+        eng.process_device(iq.data_ptr(), audio.data_ptr(), T, rows, spec.data_ptr(), wf.data_ptr(), None, None,
+                           int(os.environ.get("FLAGS", "2")))      # 2: the bit-exact kernel with the closed-form oscillator
         eng.synchronize()
         L.t41rx_debug_phase_cycles(buf, 1)
     v = np.array(buf[:], dtype=np.float64).reshape(64, 2) / T
