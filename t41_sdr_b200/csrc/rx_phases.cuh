@@ -1224,10 +1224,14 @@ T41RX_DEV void PhAgcSerial(Cta &c, int tid) {
       /* run-length fast path for the steady state (slow decay, DSP_Fn.cpp:601-608): one loop-closing
          branch per sample while the window maximum stays below volts.  Identical arithmetic to the
          generic step below. */
+      /* the next sample's window maximum and magnitude are fetched before this sample's branch: the branch waits
+         for volts anyway, the loads need not wait for the branch (index kDec of either array is readable scratch) */
+      float r_nx = s[vRm + i], a_nx = s[vAbs + i];
       while (i < kDec) {
-        const float r = s[vRm + i];
+        const float r = r_nx, abs_out = a_nx;
+        r_nx = s[vRm + i + 1];
+        a_nx = s[vAbs + i + 1];
         if (r >= v) break;
-        const float abs_out = s[vAbs + i];
         fast = k_fbm * abs_out + k_omfbm * fast;
         hang = k_hbm * abs_out + k_omhbm * hang;
         rm = r;
