@@ -187,7 +187,12 @@ int t41rx_process_q15(t41rx_ctx *ctx, const int16_t *iq_q15, int16_t *audio_q15,
                       uint32_t flags);
 
 /* Same, with DEVICE pointers (resident in HBM) and an optional cudaStream_t (NULL = the
- * context's own stream).  Asynchronous: returns after enqueueing. */
+ * context's own stream).  Asynchronous: returns after enqueueing.
+ * Ordering contract: the context records the end of the call on the stream it was given.  t41rx_set_params*,
+ * t41rx_get_debug, t41rx_synchronize, t41rx_destroy and the host-buffer entry points wait for that point (and for
+ * the context's own streams) before they touch device tables or state, so they are safe after a call on ANY stream.
+ * Two t41rx_process_device calls on DIFFERENT streams are not ordered against each other by the library: the
+ * receivers' state lives in the context, so the caller must order them (one stream, or an event between them). */
 int t41rx_process_device(t41rx_ctx *ctx, const float *iq, float *audio, int n_blocks, int row_every,
                          int16_t *spec_rows, uint16_t *wf_rows, int8_t *psk_bits, uint8_t *psk_chars,
                          uint32_t flags, void *cuda_stream);

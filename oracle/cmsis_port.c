@@ -26,7 +26,8 @@ void arm_float_to_q15(const float32_t *pSrc, q15_t *pDst, uint32_t n) {
   for (uint32_t i = 0; i < n; ++i) {
     float32_t v = pSrc[i] * 32768.0f;
     int32_t q;
-    if (!(v > -2147483648.0f)) q = INT32_MIN;      /* also catches NaN */
+    if (v != v) q = 0;                             /* NaN: Cortex-M7 VCVT.S32.F32 converts NaN to 0 (not the x86 INT32_MIN) */
+    else if (!(v > -2147483648.0f)) q = INT32_MIN;
     else if (v >= 2147483648.0f) q = INT32_MAX;
     else q = (int32_t)v;
     if (q > 32767) q = 32767;

@@ -173,7 +173,8 @@ __global__ void t41rx_q15_to_float_kernel(const short4 *src, float4 *dst, size_t
 __device__ __forceinline__ short FloatToQ15(float x) {
   const float v = x * 32768.0f;
   int q;
-  if (!(v > -2147483648.0f)) q = INT32_MIN;      /* also catches NaN */
+  if (v != v) q = 0;                             /* NaN: the target's VCVT.S32.F32 gives 0 (x86 cvttss2si would give INT32_MIN) */
+  else if (!(v > -2147483648.0f)) q = INT32_MIN;
   else if (v >= 2147483648.0f) q = INT32_MAX;
   else q = (int)v;
   q = q > 32767 ? 32767 : q;
@@ -227,6 +228,10 @@ struct t41rx_ctx {
   cudaEvent_t ev_in[kProcessChunks] = {}, ev_done[kProcessChunks] = {};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool ev_valid = false;
+  /* t41rx_process_device may enqueue on a caller-supplied stream: the end of its work is recorded here and every
+     entry point that touches the context's device tables, state or scratch waits for it first */
+  cudaEvent_t ev_ext = nullptr;
+  bool ext_pending = false;
   /* CUDA events around the most recent launches of the dominant kernel (ring), for bench.py's roofline */
   cudaEvent_t kev[kKernelEventRing][2] = {};
   int64_t kev_count = 0;
@@ -278,6 +283,18 @@ struct t41rx_ctx {
   size_t cap_aspec = 0, cap_ypixel = 0, cap_max_ave = 0, cap_sframes = 0, cap_aframes = 0;
   bool WantAudioSpec() const { return bind_ypixel || bind_max_ave || bind_audio_frames; }
 };
+
+/* wait for everything the context has enqueued: its own streams and the last caller-supplied stream */
+static int Quiesce(t41rx_ctx *ctx) {
+  if (ctx->ext_pending) {
+    CUDA_TRY(cudaEventSynchronize(ctx->ev_ext));
+    ctx->ext_pending = false;
+  }
+  CUDA_TRY(cudaStreamSynchronize(ctx->copy_in));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->copy_out));
+  return 0;
+}
 
 static int EnsureFsetCapacity(t41rx_ctx *ctx, int need) {
   if (need <= ctx->fset_capacity) return 0;
@@ -356,7 +373,10 @@ void t41rx_mode_default_cuts(int32_t mode, int32_t *f_lo_cut, int32_t *f_hi_cut)
 void t41rx_destroy(t41rx_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  if (ctx->ext_pending && ctx->ev_ext) cudaEventSynchronize(ctx->ev_ext);
+  if (ctx->copy_in) cudaStreamSynchronize(ctx->copy_in);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->copy_out) cudaStreamSynchronize(ctx->copy_out);
   void *bufs[] = {ctx->d_cfg, ctx->d_state, ctx->d_fsets, ctx->d_nco_tab, ctx->d_twiddle, ctx->d_hann, ctx->d_sin,
                   ctx->d_zoom_iir, ctx->d_eq_coeffs, ctx->d_cw_coeffs, ctx->d_sam, ctx->d_gradient, ctx->d_varicode, ctx->d_iq, ctx->d_audio,
                   ctx->d_spec, ctx->d_wf, ctx->d_bits, ctx->d_chars, ctx->d_fast_ids[0], ctx->d_phased_ids[0], ctx->d_fast_ids[1],
@@ -368,6 +388,7 @@ void t41rx_destroy(t41rx_ctx *ctx) {
     if (b) cudaFree(b);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->ev_ext) cudaEventDestroy(ctx->ev_ext);
   for (int i = 0; i < kKernelEventRing; ++i)
     for (int j = 0; j < 2; ++j)
       if (ctx->kev[i][j]) cudaEventDestroy(ctx->kev[i][j]);
@@ -408,7 +429,8 @@ int t41rx_create(t41rx_ctx **out, int n_streams, int device) {
   if (cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess)
+      cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_ext, cudaEventDisableTiming) != cudaSuccess)
     return bail(Fail(T41RX_ECUDA, "t41rx_create: stream/event creation failed%s"));
   if (cudaFuncSetAttribute(t41rx_fused_rx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)(kSmemFloats * sizeof(float))) != cudaSuccess ||
@@ -461,7 +483,16 @@ static int SetParamsImpl(t41rx_ctx *ctx, int first, int count, const t41rx_param
   for (int i = 0; i < count; ++i)
     if (!ValidateParams(each ? p[i] : p[0])) return Fail(T41RX_EINVAL, "t41rx_set_params: parameter out of range%s");
   CUDA_TRY(cudaSetDevice(ctx->device));
-  CUDA_TRY(cudaStreamSynchronize(ctx->stream));   /* changes apply at a block boundary */
+  {                                               /* changes apply at a block boundary: nothing may be in flight */
+    const int rc = Quiesce(ctx);
+    if (rc) return rc;
+  }
+  /* room for every filter set this call can add BEFORE the host model changes: the device allocation is the step that
+     can fail, and a failure after HostModel::Apply would leave host and device out of step */
+  {
+    const int rc = EnsureFsetCapacity(ctx, (int)ctx->host.fsets.size() + count);
+    if (rc) return rc;
+  }
   for (int i = 0; i < count; ++i) {
     const int s = first + i;
     StatePatch patch;
@@ -545,7 +576,10 @@ int t41rx_design_tables(const t41rx_params *seq, int n_seq, t41rx_tables *t) {
 int t41rx_get_debug(t41rx_ctx *ctx, int stream, t41rx_debug *d) {
   if (!ctx || !d || stream < 0 || stream >= ctx->n_streams) return Fail(T41RX_EINVAL, "t41rx_get_debug: bad arguments%s");
   CUDA_TRY(cudaSetDevice(ctx->device));
-  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  {
+    const int rc = Quiesce(ctx);
+    if (rc) return rc;
+  }
   StreamState st;
   CUDA_TRY(cudaMemcpy(&st, ctx->d_state + stream, sizeof(st), cudaMemcpyDeviceToHost));
   memset(d, 0, sizeof(*d));
@@ -739,6 +773,10 @@ int t41rx_process_device(t41rx_ctx *ctx, const float *iq, float *audio, int n_bl
   rc = LaunchRange(ctx, iq, audio, n_blocks, row_every, spec_rows, wf_rows, psk_bits, psk_chars, flags, st,
                    Span{0, ctx->n_streams, 0, n_blocks}, ctx->bind_ypixel, ctx->bind_max_ave, ctx->bind_spec_frames,
                    ctx->bind_audio_frames);
+  if (st != ctx->stream) {                        /* ordering contract (t41rx.h): remember the caller's stream */
+    cudaEventRecord(ctx->ev_ext, st);
+    ctx->ext_pending = true;
+  }
   if (rc) return rc;
   CUDA_TRY(cudaEventRecord(ctx->ev1, st));
   ctx->ev_valid = true;
@@ -801,8 +839,7 @@ int32_t t41rx_smeter_bar(float dbm) {
 int t41rx_synchronize(t41rx_ctx *ctx) {
   if (!ctx) return Fail(T41RX_EINVAL, "t41rx_synchronize: null context%s");
   CUDA_TRY(cudaSetDevice(ctx->device));
-  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  return T41RX_OK;
+  return Quiesce(ctx) ? T41RX_ECUDA : T41RX_OK;
 }
 
 /* host-buffer entry points: float (iq / audio) or q15 (iq16 / audio16) blocks */
@@ -855,6 +892,9 @@ static int ProcessHost(t41rx_ctx *ctx, const float *iq, float *audio, const int1
   uint16_t *d_wf = (n_rows && wf_rows) ? (uint16_t *)ctx->d_wf : nullptr;
   int8_t *d_bits = psk_bits ? (int8_t *)ctx->d_bits : nullptr;
   uint8_t *d_chars = psk_chars ? (uint8_t *)ctx->d_chars : nullptr;
+  /* everything enqueued below reads or writes the caller's host buffers asynchronously: whatever fails, no copy may
+     still be in flight when the call returns */
+  auto enqueue = [&]() -> int {
   CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
   const size_t blk_iq = 2 * kBlock, blk_audio = kBlock;       /* elements per block */
   for (int ch = 0; ch < n_chunks; ++ch) {
@@ -912,6 +952,14 @@ static int ProcessHost(t41rx_ctx *ctx, const float *iq, float *audio, const int1
   CUDA_TRY(cudaStreamSynchronize(ctx->copy_out));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   return T41RX_OK;
+  };
+  rc = enqueue();
+  if (rc) {                                        /* keep the first error's text */
+    cudaStreamSynchronize(ctx->copy_in);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->copy_out);
+  }
+  return rc;
 }
 
 int t41rx_process(t41rx_ctx *ctx, const float *iq, float *audio, int n_blocks, int row_every,

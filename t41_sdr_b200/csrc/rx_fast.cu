@@ -40,10 +40,12 @@ cudaError_t LaunchStreamKernel(const LaunchArgs &a, int n_sms, cudaStream_t st) 
   int G = (a.n_streams + n_sms - 1) / n_sms;
   if (G < 1) G = 1;
   if (G > fast::kFastMaxG) G = fast::kFastMaxG;
-  if (const char *e = getenv("T41RX_FAST_G")) {          /* developer knob: receivers per CTA */
+#ifdef T41RX_DEV_KNOBS
+  if (const char *e = getenv("T41RX_FAST_G")) {          /* developer builds only: receivers per CTA */
     const int g = atoi(e);
     if (g >= 1 && g <= fast::kFastMaxG) G = g;
   }
+#endif
   const int grid = (a.n_streams + G - 1) / G;
   t41rx_stream_rx_kernel<<<grid, 64 * G + 32, (size_t)G * fast::kSlotF * sizeof(float) + 32, st>>>(a, G);
   return cudaGetLastError();

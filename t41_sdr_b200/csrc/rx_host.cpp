@@ -114,6 +114,7 @@ void HostModel::Init(int n) {
   fsets.emplace_back();
   DesignFilterSet(def, &fsets[0]);
   fset_ids[std::make_tuple(0, 0, def.f_lo_cut, def.f_hi_cut)] = 0;
+  fset_refs.assign(1, n);
   DesignStreamCfg(def, agc[0], 0, &cfg[0]);
   BuildNcoTable(cfg[0], &nco_tab[0]);
   for (int s = 0; s < n; ++s) {
@@ -136,16 +137,30 @@ int HostModel::Apply(int s, const t41rx_params &p, StatePatch *patch, int *new_f
   const bool nfm = p.mode == T41RX_DEMOD_NFM;
   const auto key = std::make_tuple(nfm ? 1 : 0, nfm ? p.nfm_filter_bw : 0, p.f_lo_cut, p.f_hi_cut);
   int fid;
+  const int old_fid = cfg[s].filter_id;
   auto it = fset_ids.find(key);
   if (it != fset_ids.end()) {
     fid = it->second;
   } else {
-    fid = (int)fsets.size();
-    fsets.emplace_back();
-    DesignFilterSet(p, &fsets.back());
+    /* a slot no receiver references any more is re-used (a tuning sweep on a long-lived context would otherwise grow
+       the table without bound); this receiver's own old slot counts once it is the only one on it */
+    fid = -1;
+    for (int i = 0; i < (int)fsets.size() && fid < 0; ++i)
+      if (fset_refs[i] == 0 || (i == old_fid && fset_refs[i] == 1)) fid = i;
+    if (fid >= 0) {
+      for (auto e = fset_ids.begin(); e != fset_ids.end(); ++e)
+        if (e->second == fid) { fset_ids.erase(e); break; }
+    } else {
+      fid = (int)fsets.size();
+      fsets.emplace_back();
+      fset_refs.push_back(0);
+    }
+    DesignFilterSet(p, &fsets[fid]);
     fset_ids[key] = fid;
     *new_fset = fid;
   }
+  fset_refs[old_fid] -= 1;
+  fset_refs[fid] += 1;
   DesignStreamCfg(p, agc[s], fid, &cfg[s]);
   if (p.nco_freq != old.nco_freq) {
     cfg[s].nco_epoch += 1;

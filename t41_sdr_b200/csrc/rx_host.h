@@ -38,6 +38,7 @@ struct HostModel {
   std::vector<double> nco_tab;          /* 192 per receiver: W[64], C[32] as (cos, sin) */
   std::vector<FilterSet> fsets;
   std::map<std::tuple<int, int, int, int>, int> fset_ids;
+  std::vector<int> fset_refs;           /* receivers on each filter set: unreferenced slots are re-used */
 
   /* constant tables */
   std::vector<float> twiddle;           /* 512 (cos, sin) */

@@ -455,8 +455,10 @@ T41RX_DEV void DcRun(float *s, const DcPost p, int begin, int end, float &d1_io,
 /* RFgain in force while block t of the launch is processed, from the values at launch start: Codec_gain
    (Process.cpp:979-1016 with the clip flags never set) raises it by one every 50 blocks up to 15 */
 T41RX_DEV int RfGainAtBlock(int rf_gain0, uint32_t timer0, int t) {
-  const int rg = rf_gain0 + (int)((timer0 + (uint32_t)t) / 50u);
-  return rg > 15 ? (rf_gain0 > 15 ? rf_gain0 : 15) : rg;
+  const int k = (int)((timer0 + (uint32_t)t) / 50u);          /* ticks of the 50-block timer so far */
+  if (k == 0) return rf_gain0;
+  const int rg = rf_gain0 + k;                                /* each tick: min(RFgain + 1, 15), also from above 15 */
+  return rg > 15 ? 15 : rg;
 }
 
 T41RX_DEV DcPost DcPostOf(const Cta &c, int g) {

@@ -155,9 +155,9 @@ def test_psk31_text_is_decoded():
 
 
 def _float_to_q15(x):
-    """arm_float_to_q15 (oracle/cmsis_port.c): saturate(trunc(x * 32768)); NaN -> INT16_MIN"""
+    """arm_float_to_q15 (oracle/cmsis_port.c): saturate(trunc(x * 32768)); NaN -> 0 (the target's VCVT)"""
     v = x.astype(np.float32) * np.float32(32768.0)
-    q = np.where(np.isnan(v), -2147483648.0, np.clip(np.trunc(v.astype(np.float64)), -2147483648.0, 2147483647.0))
+    q = np.where(np.isnan(v), 0.0, np.clip(np.trunc(v.astype(np.float64)), -2147483648.0, 2147483647.0))
     return np.clip(q, -32768, 32767).astype(np.int16)
 
 
