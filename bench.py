@@ -15,6 +15,10 @@ Prints ONE JSON line (rank 0).  `value`  : complex Msamples/s, inputs resident i
                                             buffers (H2D + kernel + D2H inside the timed region).
                                  `roofline`: algorithmic bytes / measured kernel time vs measured HBM peak.
                                  `cpu_baseline`: the CPU oracle on the host cores, bounded sample.
+`configs` : BASELINE.json configs[2..4] on the same GPUs, device-resident, each with its own roofline:
+            c3 = 8192 receivers NFM + SAM with AGC 1-4 (8192 / N per GPU), c4 = 16384 receivers, zoom x1..x16,
+            every block a spectrum + waterfall row (16384 / N per GPU), c5 = 32768 receivers PSK31 front end
+            with the DBPSK + varicode tap (32768 / N per GPU).  `value` stays C2.
 `--impl reference` times the reference's own CPU implementation of the path (oracle/_ref, the
 reference translation units compiled in place; falls back to the oracle port) on all host cores.
 """
@@ -65,34 +69,57 @@ def parse_args():
                          "path of SURVEY 8(e); reported as rows_gather_ms)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip BASELINE.json configs[2..4] (c3 / c4 / c5)")
     return ap.parse_args()
 
 
-def workload(n_blocks):
-    """C2: even receivers USB (+300..+3000), odd AM (+-3000), per-receiver tone / NCO."""
-    import cases
-    from t41_sdr_b200 import synth
+USB, LSB, AM, NFM, PSK31, SAM = 0, 1, 2, 3, 5, 8     # SDT.h:57-68 (t41rx.h T41RX_DEMOD_*)
+
+
+def workload(n_blocks, name="c2"):
+    """(params, signals) of a bank's N_DISTINCT-or-fewer distinct receivers; receiver s of a bank runs number
+    s % len(params).  Parameters are built through the product's own C-ABI (rx.make_params): nothing under oracle/
+    is touched here.
+    c2: even receivers USB (+300..+3000), odd AM (+-3000), per-receiver tone / NCO (BASELINE.json configs[1]).
+    c3: even NFM (+-2.5 kHz deviation), odd SAM (carrier offset U[-200, 200] Hz), AGC mode cycling 1..4, a -20 dB level
+        step in the middle of the step (configs[2]).
+    c4: zoom index = receiver % 5 (x1 .. x16), two tones + noise, every block a row (configs[3]).
+    c5: PSK31 front end: +-100 Hz mask, AGC off, DBPSK + varicode tap on a carrier tuned to DC (configs[4])."""
+    from t41_sdr_b200 import rx, synth
+    P = rx.make_params
     r = np.random.Generator(np.random.PCG64(2024))
     params, sigs = [], []
-    for k in range(N_DISTINCT):
-        nco = int(r.integers(-20000, 20001))
-        if k % 2 == 0:
-            params.append(cases.P(mode=cases.USB, f_lo_cut=300, f_hi_cut=3000, nco_freq=nco, agc_mode=1))
-            sigs.append(synth.tone(900 + k, n_blocks, float(r.uniform(300, 2700)), mode=cases.USB, nco_freq=nco))
-        else:
-            params.append(cases.P(mode=cases.AM, nco_freq=nco, agc_mode=1))
-            sigs.append(synth.am(900 + k, n_blocks, mode=cases.AM, nco_freq=nco, depth=0.5, f_mod=400.0))
-    if os.environ.get("T41RX_BENCH_WORKLOAD") == "c3":   # developer knob: BASELINE.json configs[2] (NFM + SAM with AGC), not the metric
-        params, sigs = [], []
+    if name == "c2":
+        for k in range(N_DISTINCT):
+            nco = int(r.integers(-20000, 20001))
+            if k % 2 == 0:
+                params.append(P(mode=USB, f_lo_cut=300, f_hi_cut=3000, nco_freq=nco, agc_mode=1))
+                sigs.append(synth.tone(900 + k, n_blocks, float(r.uniform(300, 2700)), mode=USB, nco_freq=nco))
+            else:
+                params.append(P(mode=AM, nco_freq=nco, agc_mode=1))
+                sigs.append(synth.am(900 + k, n_blocks, mode=AM, nco_freq=nco, depth=0.5, f_mod=400.0))
+    elif name == "c3":
         for k in range(N_DISTINCT):
             agc = 1 + (k % 4)
             if k % 2 == 0:
-                params.append(cases.P(mode=cases.NFM, agc_mode=agc, nfm_filter_bw=12000))
+                params.append(P(mode=NFM, agc_mode=agc, nfm_filter_bw=12000))
                 sigs.append(synth.nfm(300 + k, n_blocks, level_step_block=n_blocks // 2, level_step_db=-20.0))
             else:
-                params.append(cases.P(mode=cases.SAM, agc_mode=agc))
-                sigs.append(synth.am(300 + k, n_blocks, mode=cases.SAM, carrier_offset=float(r.uniform(-200, 200)), depth=0.5,
+                params.append(P(mode=SAM, agc_mode=agc))
+                sigs.append(synth.am(300 + k, n_blocks, mode=SAM, carrier_offset=float(r.uniform(-200, 200)), depth=0.5,
                                      level_step_block=n_blocks // 2, level_step_db=-20.0))
+    elif name == "c4":
+        for z in range(5):
+            params.append(P(mode=USB, spectrum_zoom=z, current_scale=1))
+            sigs.append(synth.two_tone(40 + z, n_blocks, 46500.0, 50500.0))
+    elif name == "c5":
+        for k in range(4):
+            params.append(P(mode=USB, f_lo_cut=-100, f_hi_cut=100, agc_mode=0, psk31_enable=1))
+            sigs.append(synth.tone(50 + k, n_blocks, 0.0))
+    else:
+        raise ValueError(name)
+    if name == "c2" and os.environ.get("T41RX_BENCH_WORKLOAD") == "c3":   # developer knob: C3 as the main line
+        return workload(n_blocks, "c3")
     if os.environ.get("T41RX_BENCH_MODE"):       # developer knob: every receiver in one mode (0 USB, 2 AM) / AGC off (-1)
         m = int(os.environ["T41RX_BENCH_MODE"])
         for p in params:
@@ -131,7 +158,14 @@ def cpu_run(kind, params, sigs, n_blocks, seconds, cores):
     use_ref = (kind == "reference") and O.tier_a_available()
     if not use_ref and not os.path.exists(O.TIER_B_PATH):
         O.build_oracle()
-    mk = (lambda p: O.RefStream(p)) if use_ref else (lambda p: O.OracleStream(p))
+    import ctypes as C
+
+    def conv(p):                             # same field layout on both sides of the C-ABI (tests/rx_driver.py)
+        q = O.Params()
+        assert C.sizeof(q) == C.sizeof(p)
+        C.memmove(C.byref(q), C.byref(p), C.sizeof(q))
+        return q
+    mk = (lambda p: O.RefStream(conv(p))) if use_ref else (lambda p: O.OracleStream(conv(p)))
     streams = [mk(params[i % len(params)]) for i in range(cores)]
     # calibrate on one thread
     t0 = time.perf_counter()
@@ -250,6 +284,28 @@ class ClockSampler:
         return out
 
 
+def bind_to_gpu_numa_node(local):
+    """Best effort: run this rank (and first-touch its pinned host buffers) on the NUMA node the GPU hangs off, so
+    that N ranks do not all stage through node 0's memory.  Returns a short description for the JSON line."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip())
+        if node < 0:
+            return {"numa_node": None, "note": "the platform reports no NUMA node for %s" % bdf}
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0) or cpus
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus": len(cpus), "pci": bdf}
+    except Exception as e:     # noqa: BLE001 - diagnostic only
+        return {"numa_node": None, "note": "%s: %s" % (type(e).__name__, e)}
+
+
 def measured_peak():
     try:
         pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -261,10 +317,77 @@ def measured_peak():
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
+EXTRA_CONFIGS = {
+    # name: (receivers over all GPUs, blocks per step, row_every, psk tap, algorithmic bytes per stream-block, text)
+    "c3": (8192, 64, 0, False, 24576, "C3: 8192 receivers, even NFM / odd SAM, AGC modes 1-4, -20 dB level step mid-step"),
+    "c4": (16384, 32, 1, False, 16384 + 2048, "C4: 16384 receivers, zoom x1..x16 by receiver, every block a spectrum + "
+                                              "waterfall row (the audio chain runs beside it)"),
+    "c5": (32768, 24, 0, True, 24576, "C5: 32768 receivers, PSK31 front end (+-100 Hz mask, AGC off) + DBPSK + varicode tap"),
+}
+
+
+def run_extra_config(name, world, local, dev, steps, peak):
+    """One of BASELINE.json configs[2..4], device-resident, sharded over the ranks (strong scaling: the config
+    fixes the receiver count).  Returns this rank's numbers; the caller reduces the time over ranks."""
+    import torch
+    from t41_sdr_b200 import rx
+    S_all, T, row_every, psk, bytes_per_block, text = EXTRA_CONFIGS[name]
+    S = S_all // world
+    params, sigs = workload(T, name)
+    D = len(params)
+    base = torch.from_numpy(np.stack(sigs)).to(dev)
+    iq = base.index_select(0, torch.arange(S, device=dev) % D).contiguous()
+    del base
+    R = (T + row_every - 1) // row_every if row_every else 0
+    audio = torch.empty((S, T, 2048), dtype=torch.float32, device=dev)
+    spec = torch.empty((S, max(R, 1), 512), dtype=torch.int16, device=dev)
+    wf = torch.empty((S, max(R, 1), 512), dtype=torch.int16, device=dev)
+    bits = torch.empty((S, T), dtype=torch.int8, device=dev) if psk else None
+    chars = torch.empty((S, T), dtype=torch.uint8, device=dev) if psk else None
+    stream = torch.cuda.Stream(device=dev)
+    with rx.Receiver(S, device=local) as eng:
+        eng.set_params_each([params[s % D] for s in range(S)])
+
+        def step():
+            eng.process_device(iq.data_ptr(), audio.data_ptr(), T, row_every, spec.data_ptr() if R else None,
+                               wf.data_ptr() if R else None, bits.data_ptr() if psk else None,
+                               chars.data_ptr() if psk else None, 0, stream.cuda_stream)
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        l0 = eng.kernel_launches()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            step()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        launches = (eng.kernel_launches() - l0) // steps
+        check = float(audio[::max(1, S // 7), -1, ::257].abs().double().sum().item())
+    del iq, audio, spec, wf
+    torch.cuda.empty_cache()
+    return dict(name=name, text=text, S=S, S_all=S_all, T=T, R=R, ms=ms, bytes_per_block=bytes_per_block, launches=launches,
+                check=check)
+
+
+def extra_config_entry(r, ms_max, world, peak):
+    blocks = r["S_all"] * r["T"]
+    achieved = (r["S"] * r["T"] * r["bytes_per_block"]) / (ms_max * 1e-3) / 1e9      # per GPU
+    e = {"workload": r["text"], "receivers": r["S_all"], "receivers_per_gpu": r["S"], "blocks_per_step": r["T"],
+         "value": blocks * 2048 / (ms_max * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_max, "scaling": "strong",
+         "kernel_launches_per_step": r["launches"],
+         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                      "algorithmic_bytes_per_stream_block": r["bytes_per_block"], "per": "GPU, all kernels of the step"},
+         "checksum_audio": r["check"]}
+    if r["R"]:
+        e["rows_per_s"] = r["S_all"] * r["R"] / (ms_max * 1e-3)
+    return e
+
+
 def ours(args):
     import torch
     import torch.distributed as dist
-    import rx_driver
     from t41_sdr_b200 import rx, sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -281,11 +404,11 @@ def ours(args):
     row_every = T if args.rows_per_step else 0
     params, sigs = workload(T)
     eng = rx.Receiver(S, device=local)
-    eng.set_params_each([rx_driver.to_rx_params(params[s % N_DISTINCT]) for s in range(S)])
+    eng.set_params_each([params[s % len(params)] for s in range(S)])
 
     # synthetic input resident in HBM: receiver s gets waveform s % N_DISTINCT
     base = torch.from_numpy(np.stack(sigs)).to(dev)                       # [D, T, 2048, 2]
-    idx = torch.arange(S, device=dev) % N_DISTINCT
+    idx = torch.arange(S, device=dev) % len(sigs)
     iq = base.index_select(0, idx).contiguous()                            # [S, T, 2048, 2]
     del base
     audio = torch.empty((S, T, 2048), dtype=torch.float32, device=dev)
@@ -356,6 +479,7 @@ def ours(args):
     e2e_float = None
     if not args.no_e2e:
         n_rows = 1 if row_every else 0
+        numa = bind_to_gpu_numa_node(local)
         iq_host = iq.cpu()
         h_iq = torch.empty((S, T, 2048, 2), dtype=torch.float32).pin_memory()
         h_iq.copy_(iq_host)
@@ -386,6 +510,11 @@ def ours(args):
                "h2d_bytes_per_step": S * T * 8192, "d2h_bytes_per_step": S * T * 4096 + S * rx.BYTES_PER_ROW * args.rows_per_step,
                "api": "t41rx_process_q15 (q15 I/Q in, q15 audio + rows out; pinned host buffers)",
                "timed_with": "host wall clock around the blocking call, max over ranks",
+               "host_link_per_rank": {"h2d_gbs": S * T * 8192 * args.steps / dt / 1e9,
+                                      "d2h_gbs": (S * T * 4096 + S * rx.BYTES_PER_ROW * args.rows_per_step) * args.steps / dt / 1e9,
+                                      "pinned_buffers": numa,
+                                      "note": "the ranks of one box share the host's memory and PCIe / C2C links: this, "
+                                              "not the GPUs, bounds e2e at N > 1"},
                "checksum_audio": float(np.abs(out16["audio"][::97, -1, ::31].astype(np.float64)).sum() / 32768.0)}
         outf = host_out(torch.float32)
         h_iq_np = h_iq.numpy()
@@ -408,6 +537,19 @@ def ours(args):
         if rank == 0:
             assert tuple(gathered.shape) == (world * S, 1, 512)
 
+    # BASELINE.json configs[2..4] on the same GPUs (device-resident; C2 above stays `value`)
+    extra = {}
+    if not args.no_extra_configs:
+        del iq, audio, spec, wf
+        torch.cuda.empty_cache()
+        peak_gbs, _ = measured_peak()
+        for name in ("c3", "c4", "c5"):
+            barrier()
+            r = run_extra_config(name, world, local, dev, max(2, min(args.steps, 5)), peak_gbs)
+            ms_max = sharding.max_over_ranks(r["ms"], dev)
+            extra[name] = extra_config_entry(r, ms_max, world, peak_gbs)
+            gpu_launches += r["launches"] * max(2, min(args.steps, 5))
+
     clk = clocks.stop()
     # explanatory second roofline: share of the SMs' issue slots the stream kernel used (instruction count of the
     # committed ncu capture, this run's kernel time and SM clock)
@@ -424,6 +566,10 @@ def ours(args):
         v, kind, blocks, dt = cpu_run("port", params, sigs, T, args.cpu_seconds, cores)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
                "sample": "%d stream-blocks of the same C2 mix on %d threads in %.1f s" % (blocks, cores, dt)}
+        # BASELINE.json configs[0]: one receiver on ONE host core (USB, 2.7 kHz filter: the first C2 receiver)
+        v1, kind1, blocks1, dt1 = cpu_run("port", params[:1], sigs[:1], T, min(4.0, args.cpu_seconds / 3), 1)
+        cpu["single_core"] = {"value": v1, "unit": UNIT, "cores": 1, "kind": kind1,
+                              "sample": "C1: one USB receiver, %d stream-blocks on one thread in %.1f s" % (blocks1, dt1)}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -431,6 +577,8 @@ def ours(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config_dict(args), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_float": e2e_float,
                 "gpu_launches": int(gpu_launches), "clocks": clk}
+        if extra:
+            line["configs"] = extra
         if rows_gather_ms is not None:
             line["rows_gather_ms"] = rows_gather_ms
         print(json.dumps(line), flush=True)

@@ -158,6 +158,19 @@ def mode_default_cuts(mode):
     return lo.value, hi.value
 
 
+def make_params(**kw):
+    """Reference defaults with the given fields replaced; a mode without explicit cut-offs takes the mode's preset
+    (SetupMode, Filter.cpp:341-385)."""
+    p = default_params()
+    if "mode" in kw and "f_lo_cut" not in kw and "f_hi_cut" not in kw:
+        kw["f_lo_cut"], kw["f_hi_cut"] = mode_default_cuts(kw["mode"])
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise AttributeError(k)
+        setattr(p, k, v)
+    return p
+
+
 def design_tables(param_sequence):
     """Control path only (no GPU): tables of a fresh receiver after the given set_params calls."""
     arr = (Params * max(1, len(param_sequence)))(*param_sequence)
