@@ -69,6 +69,7 @@ def parse_args():
                          "path of SURVEY 8(e); reported as rows_gather_ms)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-q15", action="store_true", help="skip the device-resident q15 leg (value_q15)")
     ap.add_argument("--no-extra-configs", action="store_true", help="skip BASELINE.json configs[2..4] (c3 / c4 / c5)")
     return ap.parse_args()
 
@@ -472,6 +473,39 @@ def ours(args):
                 "step_ms_all_kernels": statistics.mean(launch_ms),
                 "share_of_step": statistics.mean(kernel_ms) / statistics.mean(launch_ms)}
 
+    # the same steps on the firmware's own q15 block format, device-resident (t41rx_process_device_q15: the chain
+    # kernels convert at their loads and stores; 6 B of HBM traffic per complex sample instead of 12)
+    value_q15 = None
+    if not args.no_q15:
+        iq16 = torch.round(iq * 32768.0).to(torch.int16)                  # the synthetic I/Q is q15 / 32768
+        audio16 = torch.empty((S, T, 2048), dtype=torch.int16, device=dev)
+
+        def step16():
+            eng.process_device_q15(iq16.data_ptr(), audio16.data_ptr(), T, row_every, spec.data_ptr(), wf.data_ptr(),
+                                   None, None, dev_flags, stream.cuda_stream)
+        for _ in range(3):
+            step16()
+        barrier()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record(stream)
+        for _ in range(args.steps):
+            step16()
+        q1.record(stream)
+        barrier()
+        q_ms = sharding.max_over_ranks(q0.elapsed_time(q1), dev) / args.steps
+        gpu_launches = eng.kernel_launches() - launches0
+        kq = eng.stream_kernel_times(min(args.steps, 32))
+        pk, _ = measured_peak()
+        kq_ms = statistics.mean(kq) if kq else q_ms
+        ach = S * T * rx.BYTES_PER_BLOCK_Q15 / (kq_ms * 1e-3) / 1e9
+        value_q15 = {"value": samples_per_step / (q_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": q_ms,
+                     "api": "t41rx_process_device_q15 (q15 I/Q in, q15 audio out, resident in HBM)",
+                     "roofline": {"bound": "hbm", "achieved": ach, "peak": pk, "unit": "GB/s", "frac": ach / pk,
+                                  "algorithmic_bytes_per_stream_block": rx.BYTES_PER_BLOCK_Q15,
+                                  "kernel": "t41rx_stream_rx_q15_kernel", "avg_launch_ms": kq_ms},
+                     "checksum_audio": float(audio16[::97, -1, ::31].abs().double().sum().item() / 32768.0)}
+        del iq16, audio16
+
     # end to end through the host-buffer C-ABI calls, pinned host buffers, H2D + kernels + D2H inside the timed
     # region: `e2e` = t41rx_process_q15, the firmware's own block format (q15 I/Q in, q15 audio out, what the
     # codec queues of Process.cpp:102-111,936-937 carry); `e2e_float` = t41rx_process on float blocks
@@ -577,6 +611,8 @@ def ours(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config_dict(args), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_float": e2e_float,
                 "gpu_launches": int(gpu_launches), "clocks": clk}
+        if value_q15 is not None:
+            line["value_q15"] = value_q15
         if extra:
             line["configs"] = extra
         if rows_gather_ms is not None:

@@ -68,6 +68,9 @@ extern "C" {
                                    one, ~9x slower): identical to the reference only in the statistical sense while
                                    the PLL pulls in (its acquisition is chaotic: ApproxAtan2's 2 pi quirk), within the
                                    stated tolerance once it is locked */
+#define T41RX_FLAG_FUSED_EXACT 32u /* developer / comparison switch: run the bit-exact chain as the single fused kernel
+                                   (serial stages on one lane per receiver) instead of its front | serial | back
+                                   kernels (serial stages with thread = receiver); same results bit for bit, ~3x slower */
 /* flags == 0: the throughput kernel (FP32 with FMA contraction, blocked-scan recurrences): audio within
    the stated tolerance of the reference (SNR >= 90 dB), discrete state identical */
 
@@ -180,7 +183,8 @@ int t41rx_process(t41rx_ctx *ctx, const float *iq, float *audio, int n_blocks, i
 /* The same call on the firmware's own block format: q15 I/Q in (what the codec queues Q_in_R / Q_in_L hold,
  * interleaved (I,Q): arm_q15_to_float = x / 32768, Process.cpp:107-108) and q15 audio out (what Q_out_L.play
  * gets: arm_float_to_q15 = saturate(trunc(x * 32768)), Process.cpp:936-937).  HOST buffers; the conversions
- * run on the device, so half as many bytes cross the host link as with the float entry point.
+ * run inside the chain kernels (at their loads and stores), so half as many bytes cross the host link and HBM as
+ * with the float entry point.
  *   iq_q15     int16 [n_streams][n_blocks][2048][2]      audio_q15  int16 [n_streams][n_blocks][2048] */
 int t41rx_process_q15(t41rx_ctx *ctx, const int16_t *iq_q15, int16_t *audio_q15, int n_blocks, int row_every,
                       int16_t *spec_rows, uint16_t *wf_rows, int8_t *psk_bits, uint8_t *psk_chars,
@@ -196,6 +200,11 @@ int t41rx_process_q15(t41rx_ctx *ctx, const int16_t *iq_q15, int16_t *audio_q15,
 int t41rx_process_device(t41rx_ctx *ctx, const float *iq, float *audio, int n_blocks, int row_every,
                          int16_t *spec_rows, uint16_t *wf_rows, int8_t *psk_bits, uint8_t *psk_chars,
                          uint32_t flags, void *cuda_stream);
+/* t41rx_process_device on q15 blocks resident in HBM (layouts of t41rx_process_q15): the firmware's own block format
+ * end to end, 12 KiB of HBM traffic per stream-block instead of 24. */
+int t41rx_process_device_q15(t41rx_ctx *ctx, const int16_t *iq_q15, int16_t *audio_q15, int n_blocks, int row_every,
+                             int16_t *spec_rows, uint16_t *wf_rows, int8_t *psk_bits, uint8_t *psk_chars,
+                             uint32_t flags, void *cuda_stream);
 int t41rx_synchronize(t41rx_ctx *ctx);
 
 /* Audio-spectrum + S-meter by-product of the row-producing blocks (Process.cpp:550-570; NFM: 791-805):

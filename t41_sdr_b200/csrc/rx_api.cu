@@ -78,6 +78,68 @@ __global__ void __launch_bounds__(kNT, 8 / kG) t41rx_fused_rx_kernel(const Launc
   PhStateOut(c, tid);
 }
 
+/* The same chain as three kernels (rx_phases.cuh, "Split form of the chain"): the sample-parallel phases up to the AGC
+   look-ahead, the serial stages with THREAD = RECEIVER, the sample-parallel phases behind the demodulator.  Bit-identical
+   to t41rx_fused_rx_kernel; the default route of every receiver that needs the bit-exact chain. */
+#define T41RX_KPHASE(stmt) \
+  do {                     \
+    stmt;                  \
+    __syncthreads();       \
+  } while (0)
+__global__ void __launch_bounds__(kNT, 8 / kG) t41rx_exact_front_kernel(const LaunchArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  Cta c;
+  c.a = a;
+  c.smem = smem;
+  c.s0 = blockIdx.x * kG;
+  c.ng = min(kG, a.n_streams - c.s0);
+  c.t = 0;
+  c.row = 0;
+  c.row_idx = 0;
+  c.rows_only = 0;
+  const int tid = threadIdx.x;
+  PhStateIn(c, tid);
+  __syncthreads();
+  for (int t = 0; t < a.n_blocks; ++t) {
+    c.t = t;
+    c.row = (a.row_every > 0) && ((a.t0 + t) % a.row_every == 0);
+    c.row_idx = c.row ? (a.t0 + t) / a.row_every : 0;
+    T41RX_FRONT_SCHEDULE(T41RX_KPHASE)
+  }
+  PhFrontStateOut(c, tid);
+}
+
+constexpr int kSerialThreads = 32;     /* one warp per CTA: the kernel is a bundle of serial chains, spread over every SM */
+__global__ void __launch_bounds__(kSerialThreads) t41rx_exact_serial_kernel(const LaunchArgs a) {
+  __shared__ float sin_tab[513];
+  for (int i = threadIdx.x; i < 513; i += kSerialThreads) sin_tab[i] = __ldg(a.sin_table + i);
+  __syncthreads();
+  const int r = blockIdx.x * kSerialThreads + threadIdx.x;
+  if (r < a.n_streams) SerialReceiver(a, r, sin_tab);
+}
+
+__global__ void __launch_bounds__(kNT, 8 / kG) t41rx_exact_back_kernel(const LaunchArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  Cta c;
+  c.a = a;
+  c.smem = smem;
+  c.s0 = blockIdx.x * kG;
+  c.ng = min(kG, a.n_streams - c.s0);
+  c.t = 0;
+  c.row = 0;
+  c.row_idx = 0;
+  c.rows_only = 0;
+  const int tid = threadIdx.x;
+  PhBackStateIn(c, tid);
+  __syncthreads();
+  for (int t = 0; t < a.n_blocks; ++t) {
+    c.t = t;
+    T41RX_BACK_SCHEDULE(T41RX_KPHASE)
+  }
+  PhBackStateOut(c, tid);
+}
+#undef T41RX_KPHASE
+
 /* display spectrum + waterfall rows of the row-producing blocks, for the receivers the throughput kernel
    serves; launched before it on the same stream (reads the launch-start state, writes only the zoom /
    spectrum state and the row outputs) */
@@ -157,39 +219,6 @@ __global__ void __launch_bounds__(kNT) t41rx_row_byproducts_kernel(const LaunchA
   }
 }
 
-/* The two conversions at the edge work on `rows` runs of `width4` 4-element groups, `pitch4` groups apart (a block
-   range of every receiver of a [receiver][block][...] array; pitch4 == width4 for a contiguous range). */
-/* arm_q15_to_float (Process.cpp:107-108): x / 32768, exact in float */
-__global__ void t41rx_q15_to_float_kernel(const short4 *src, float4 *dst, size_t rows, size_t width4, size_t pitch4) {
-  const size_t n4 = rows * width4;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t o = (i / width4) * pitch4 + (i % width4);
-    const short4 v = src[o];
-    dst[o] = float4{(float)v.x / 32768.0f, (float)v.y / 32768.0f, (float)v.z / 32768.0f, (float)v.w / 32768.0f};
-  }
-}
-
-/* arm_float_to_q15 (Process.cpp:936): saturate((q31)(x * 32768)) to 16 bits, truncation toward zero */
-__device__ __forceinline__ short FloatToQ15(float x) {
-  const float v = x * 32768.0f;
-  int q;
-  if (v != v) q = 0;                             /* NaN: the target's VCVT.S32.F32 gives 0 (x86 cvttss2si would give INT32_MIN) */
-  else if (!(v > -2147483648.0f)) q = INT32_MIN;
-  else if (v >= 2147483648.0f) q = INT32_MAX;
-  else q = (int)v;
-  q = q > 32767 ? 32767 : q;
-  q = q < -32768 ? -32768 : q;
-  return (short)q;
-}
-__global__ void t41rx_float_to_q15_kernel(const float4 *src, short4 *dst, size_t rows, size_t width4, size_t pitch4) {
-  const size_t n4 = rows * width4;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t o = (i / width4) * pitch4 + (i % width4);
-    const float4 v = src[o];
-    dst[o] = short4{FloatToQ15(v.x), FloatToQ15(v.y), FloatToQ15(v.z), FloatToQ15(v.w)};
-  }
-}
-
 }  // namespace t41rx
 
 using namespace t41rx;
@@ -218,6 +247,7 @@ static int Fail(int code, const char *fmt, const char *detail = "") {
 constexpr int kKernelEventRing = 32;
 constexpr int kProcessChunks = 16;  /* most chunks of the host-buffer entry point's copy / compute pipeline (cut over time) */
 constexpr int kReceiverChunks = 8;  /* chunks when a short call is cut over receivers */
+constexpr size_t kSerialScratchBytes = (size_t)768 << 20;   /* most hand-over scratch of the split bit-exact chain */
 
 struct t41rx_ctx {
   int device = 0;
@@ -267,6 +297,11 @@ struct t41rx_ctx {
   std::vector<int32_t> h_fast_grouped[4];
   int32_t *d_fast_grouped[4] = {nullptr, nullptr, nullptr, nullptr};
   bool ids_dirty = true;
+
+  /* hand-over buffers of the split bit-exact chain (front | serial | back kernels): 5 KiB per stream-block; calls
+     whose exact receivers need more than kSerialScratchBytes are cut over time */
+  void *d_ser_in = nullptr, *d_ser_out = nullptr;
+  size_t cap_ser_in = 0, cap_ser_out = 0;
 
   /* device staging for the host-buffer entry point */
   void *d_iq = nullptr, *d_audio = nullptr, *d_spec = nullptr, *d_wf = nullptr, *d_bits = nullptr, *d_chars = nullptr;
@@ -382,7 +417,7 @@ void t41rx_destroy(t41rx_ctx *ctx) {
                   ctx->d_spec, ctx->d_wf, ctx->d_bits, ctx->d_chars, ctx->d_fast_ids[0], ctx->d_phased_ids[0], ctx->d_fast_ids[1],
                   ctx->d_phased_ids[1], ctx->d_fast_ids[2], ctx->d_phased_ids[2], ctx->d_fast_ids[3], ctx->d_phased_ids[3],
                   ctx->d_fast_grouped[0], ctx->d_fast_grouped[1], ctx->d_fast_grouped[2], ctx->d_fast_grouped[3],
-                  ctx->d_iq16, ctx->d_audio16, ctx->d_aspec, ctx->d_ypixel, ctx->d_max_ave,
+                  ctx->d_iq16, ctx->d_audio16, ctx->d_ser_in, ctx->d_ser_out, ctx->d_aspec, ctx->d_ypixel, ctx->d_max_ave,
                   ctx->d_sframes, ctx->d_aframes};
   for (void *b : bufs)
     if (b) cudaFree(b);
@@ -433,6 +468,10 @@ int t41rx_create(t41rx_ctx **out, int n_streams, int device) {
       cudaEventCreateWithFlags(&ctx->ev_ext, cudaEventDisableTiming) != cudaSuccess)
     return bail(Fail(T41RX_ECUDA, "t41rx_create: stream/event creation failed%s"));
   if (cudaFuncSetAttribute(t41rx_fused_rx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)(kSmemFloats * sizeof(float))) != cudaSuccess ||
+      cudaFuncSetAttribute(t41rx_exact_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)(kSmemFloats * sizeof(float))) != cudaSuccess ||
+      cudaFuncSetAttribute(t41rx_exact_back_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)(kSmemFloats * sizeof(float))) != cudaSuccess ||
       cudaFuncSetAttribute(t41rx_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)(kSmemFloats * sizeof(float))) != cudaSuccess ||
@@ -619,16 +658,61 @@ struct Span {
   int first, count, t0, nt;
 };
 
+/* the bit-exact chain for the receivers of `p` (p.n_streams of them, p.stream_ids / p.stream_base) on stream st:
+   front | serial | back kernels with the hand-over in HBM, cut over time so that the scratch stays bounded;
+   T41RX_FLAG_FUSED_EXACT: the single fused kernel (one lane per receiver in the serial phases) instead */
+static int LaunchExact(t41rx_ctx *ctx, const LaunchArgs &p, cudaStream_t st) {
+  const int n = p.n_streams;
+  const int grid = (n + kG - 1) / kG;
+  if (p.flags & T41RX_FLAG_FUSED_EXACT) {
+    t41rx_fused_rx_kernel<<<grid, kNT, kSmemFloats * sizeof(float), st>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    ctx->launches += 1;
+    return T41RX_OK;
+  }
+  const size_t per_block = (size_t)n * kDec * (sizeof(float4) + sizeof(float));
+  int chunk = (int)std::min<size_t>((size_t)p.n_blocks, std::max<size_t>(1, kSerialScratchBytes / per_block));
+  int rc;
+  if ((rc = Grow(&ctx->d_ser_in, &ctx->cap_ser_in, (size_t)n * chunk * kDec * sizeof(float4)))) return rc;
+  if ((rc = Grow(&ctx->d_ser_out, &ctx->cap_ser_out, (size_t)n * chunk * kDec * sizeof(float)))) return rc;
+  for (int c0 = 0; c0 < p.n_blocks; c0 += chunk) {
+    LaunchArgs q = p;
+    q.iq = p.iq ? p.iq + (size_t)c0 * 2 * kBlock : nullptr;
+    q.audio = p.audio ? p.audio + (size_t)c0 * kBlock : nullptr;
+    q.iq16 = p.iq16 ? p.iq16 + (size_t)c0 * 2 * kBlock : nullptr;
+    q.audio16 = p.audio16 ? p.audio16 + (size_t)c0 * kBlock : nullptr;
+    q.psk_bits = p.psk_bits ? p.psk_bits + c0 : nullptr;
+    q.psk_chars = p.psk_chars ? p.psk_chars + c0 : nullptr;
+    q.t0 = p.t0 + c0;
+    q.n_blocks = std::min(chunk, p.n_blocks - c0);
+    q.ser_in = (float4 *)ctx->d_ser_in;
+    q.ser_out = (float *)ctx->d_ser_out;
+    t41rx_exact_front_kernel<<<grid, kNT, kSmemFloats * sizeof(float), st>>>(q);
+    CUDA_TRY(cudaGetLastError());
+    t41rx_exact_serial_kernel<<<(n + kSerialThreads - 1) / kSerialThreads, kSerialThreads, 0, st>>>(q);
+    CUDA_TRY(cudaGetLastError());
+    t41rx_exact_back_kernel<<<grid, kNT, kSmemFloats * sizeof(float), st>>>(q);
+    CUDA_TRY(cudaGetLastError());
+    ctx->launches += 3;
+  }
+  return T41RX_OK;
+}
+
 /* enqueue the kernels for a span of the call on stream st (buffer pointers are those of the whole call) */
-static int LaunchRange(t41rx_ctx *ctx, const float *iq, float *audio, int n_blocks, int row_every,
+static int LaunchRange(t41rx_ctx *ctx, const void *iq_any, void *audio_any, bool q15, int n_blocks, int row_every,
                        int16_t *spec_rows, uint16_t *wf_rows, int8_t *psk_bits, uint8_t *psk_chars,
                        uint32_t flags, cudaStream_t st, Span sp, int32_t *d_ypixel = nullptr,
                        float *d_max_ave = nullptr, uint8_t *d_sframes = nullptr, uint8_t *d_aframes = nullptr) {
   const int first = sp.first, count = sp.count;
   LaunchArgs a;
   memset(&a, 0, sizeof(a));
-  a.iq = iq + (size_t)sp.t0 * 2 * kBlock;
-  a.audio = audio + (size_t)sp.t0 * kBlock;
+  if (q15) {
+    a.iq16 = (const int16_t *)iq_any + (size_t)sp.t0 * 2 * kBlock;
+    a.audio16 = (int16_t *)audio_any + (size_t)sp.t0 * kBlock;
+  } else {
+    a.iq = (const float *)iq_any + (size_t)sp.t0 * 2 * kBlock;
+    a.audio = (float *)audio_any + (size_t)sp.t0 * kBlock;
+  }
   a.spec_rows = row_every > 0 ? spec_rows : nullptr;
   a.wf_rows = row_every > 0 ? wf_rows : nullptr;
   a.psk_bits = psk_bits ? psk_bits + sp.t0 : nullptr;
@@ -678,9 +762,8 @@ static int LaunchRange(t41rx_ctx *ctx, const float *iq, float *audio, int n_bloc
      phase-structured kernel; SAM receivers always take the phase-structured kernel (see t41rx_ctx) */
   const bool all_phased = (flags & (T41RX_FLAG_EXACT_NCO | T41RX_FLAG_PHASED_KERNEL)) != 0;
   if (all_phased) {
-    t41rx_fused_rx_kernel<<<(count + kG - 1) / kG, kNT, kSmemFloats * sizeof(float), st>>>(a);
-    CUDA_TRY(cudaGetLastError());
-    ctx->launches += 1;
+    const int rc = LaunchExact(ctx, a, st);
+    if (rc) return rc;
     return audio_spectrum();
   }
   /* the slices of the (sorted) per-kernel receiver lists that fall into the range */
@@ -697,9 +780,8 @@ static int LaunchRange(t41rx_ctx *ctx, const float *iq, float *audio, int n_bloc
     LaunchArgs p = a;
     p.n_streams = p_len;
     p.stream_ids = ctx->d_phased_ids[v] + p_off;
-    t41rx_fused_rx_kernel<<<(p_len + kG - 1) / kG, kNT, kSmemFloats * sizeof(float), st>>>(p);
-    CUDA_TRY(cudaGetLastError());
-    ctx->launches += 1;
+    const int rc = LaunchExact(ctx, p, st);
+    if (rc) return rc;
   }
   if (f_len > 0) {
     LaunchArgs f = a;
@@ -759,7 +841,7 @@ static int RefreshKernelLists(t41rx_ctx *ctx) {
   return T41RX_OK;
 }
 
-int t41rx_process_device(t41rx_ctx *ctx, const float *iq, float *audio, int n_blocks, int row_every,
+static int ProcessDevice(t41rx_ctx *ctx, const void *iq, void *audio, bool q15, int n_blocks, int row_every,
                          int16_t *spec_rows, uint16_t *wf_rows, int8_t *psk_bits, uint8_t *psk_chars,
                          uint32_t flags, void *cuda_stream) {
   if (!ctx || !iq || !audio || n_blocks <= 0 || row_every < 0)
@@ -770,7 +852,7 @@ int t41rx_process_device(t41rx_ctx *ctx, const float *iq, float *audio, int n_bl
   if (rc) return rc;
   if ((rc = EnsureAudioSpecScratch(ctx, row_every > 0 ? (size_t)(n_blocks + row_every - 1) / row_every : 0))) return rc;
   CUDA_TRY(cudaEventRecord(ctx->ev0, st));
-  rc = LaunchRange(ctx, iq, audio, n_blocks, row_every, spec_rows, wf_rows, psk_bits, psk_chars, flags, st,
+  rc = LaunchRange(ctx, iq, audio, q15, n_blocks, row_every, spec_rows, wf_rows, psk_bits, psk_chars, flags, st,
                    Span{0, ctx->n_streams, 0, n_blocks}, ctx->bind_ypixel, ctx->bind_max_ave, ctx->bind_spec_frames,
                    ctx->bind_audio_frames);
   if (st != ctx->stream) {                        /* ordering contract (t41rx.h): remember the caller's stream */
@@ -781,6 +863,18 @@ int t41rx_process_device(t41rx_ctx *ctx, const float *iq, float *audio, int n_bl
   CUDA_TRY(cudaEventRecord(ctx->ev1, st));
   ctx->ev_valid = true;
   return T41RX_OK;
+}
+
+int t41rx_process_device(t41rx_ctx *ctx, const float *iq, float *audio, int n_blocks, int row_every,
+                         int16_t *spec_rows, uint16_t *wf_rows, int8_t *psk_bits, uint8_t *psk_chars,
+                         uint32_t flags, void *cuda_stream) {
+  return ProcessDevice(ctx, iq, audio, false, n_blocks, row_every, spec_rows, wf_rows, psk_bits, psk_chars, flags, cuda_stream);
+}
+
+int t41rx_process_device_q15(t41rx_ctx *ctx, const int16_t *iq_q15, int16_t *audio_q15, int n_blocks, int row_every,
+                             int16_t *spec_rows, uint16_t *wf_rows, int8_t *psk_bits, uint8_t *psk_chars,
+                             uint32_t flags, void *cuda_stream) {
+  return ProcessDevice(ctx, iq_q15, audio_q15, true, n_blocks, row_every, spec_rows, wf_rows, psk_bits, psk_chars, flags, cuda_stream);
 }
 
 /* log10f_fast (Utility.cpp:245-258) on the host, for the S-meter helper */
@@ -858,8 +952,8 @@ static int ProcessHost(t41rx_ctx *ctx, const float *iq, float *audio, const int1
   const size_t b_spec = S * n_rows * kSpecRes * sizeof(int16_t), b_wf = S * n_rows * kSpecRes * sizeof(uint16_t);
   const size_t b_psk = S * T;
   int rc;
-  if ((rc = Grow(&ctx->d_iq, &ctx->cap_iq, b_iq))) return rc;
-  if ((rc = Grow(&ctx->d_audio, &ctx->cap_audio, b_audio))) return rc;
+  if (!q15 && (rc = Grow(&ctx->d_iq, &ctx->cap_iq, b_iq))) return rc;
+  if (!q15 && (rc = Grow(&ctx->d_audio, &ctx->cap_audio, b_audio))) return rc;
   const bool need_spec = n_rows && (spec_rows || ctx->bind_spec_frames);     /* the frames are built from the rows */
   if (need_spec && (rc = Grow(&ctx->d_spec, &ctx->cap_spec, b_spec))) return rc;
   if (n_rows && wf_rows && (rc = Grow(&ctx->d_wf, &ctx->cap_wf, b_wf))) return rc;
@@ -909,23 +1003,11 @@ static int ProcessHost(t41rx_ctx *ctx, const float *iq, float *audio, const int1
                                cudaMemcpyHostToDevice, ctx->copy_in));
     CUDA_TRY(cudaEventRecord(ctx->ev_in[ch], ctx->copy_in));
     CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[ch], 0));
-    if (q15) {
-      t41rx_q15_to_float_kernel<<<2 * ctx->n_sms, 256, 0, ctx->stream>>>(
-          reinterpret_cast<const short4 *>((int16_t *)ctx->d_iq16 + off_iq), reinterpret_cast<float4 *>((float *)ctx->d_iq + off_iq),
-          n, nt * blk_iq / 4, T * blk_iq / 4);
-      CUDA_TRY(cudaGetLastError());
-      ctx->launches += 1;
-    }
-    rc = LaunchRange(ctx, (const float *)ctx->d_iq, (float *)ctx->d_audio, n_blocks, row_every, d_spec, d_wf, d_bits, d_chars,
-                     flags, ctx->stream, Span{(int)s0, (int)n, (int)t0, (int)nt}, d_ypix, d_maxave, d_sfr, d_afr);
+    /* q15 blocks go through the kernels as they are: each converts at its own load / store */
+    rc = LaunchRange(ctx, q15 ? ctx->d_iq16 : ctx->d_iq, q15 ? ctx->d_audio16 : ctx->d_audio, q15, n_blocks, row_every, d_spec,
+                     d_wf, d_bits, d_chars, flags, ctx->stream, Span{(int)s0, (int)n, (int)t0, (int)nt}, d_ypix, d_maxave,
+                     d_sfr, d_afr);
     if (rc) return rc;
-    if (q15) {
-      t41rx_float_to_q15_kernel<<<2 * ctx->n_sms, 256, 0, ctx->stream>>>(
-          reinterpret_cast<const float4 *>((float *)ctx->d_audio + off_audio), reinterpret_cast<short4 *>((int16_t *)ctx->d_audio16 + off_audio),
-          n, nt * blk_audio / 4, T * blk_audio / 4);
-      CUDA_TRY(cudaGetLastError());
-      ctx->launches += 1;
-    }
     CUDA_TRY(cudaEventRecord(ctx->ev_done[ch], ctx->stream));
     CUDA_TRY(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_done[ch], 0));
     const size_t out_esz = q15 ? sizeof(int16_t) : sizeof(float);

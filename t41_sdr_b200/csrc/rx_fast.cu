@@ -13,7 +13,12 @@ namespace t41rx {
 
 __global__ void __launch_bounds__(64 * fast::kFastMaxG + 32, 1) t41rx_stream_rx_kernel(const LaunchArgs a, const int G) {
   extern __shared__ __align__(16) float smem[];
-  fast::StreamKernelBody(a, G, smem);
+  fast::StreamKernelBody<false>(a, G, smem);
+}
+/* the same kernel on the firmware's q15 block format (a.iq16 in, a.audio16 out) */
+__global__ void __launch_bounds__(64 * fast::kFastMaxG + 32, 1) t41rx_stream_rx_q15_kernel(const LaunchArgs a, const int G) {
+  extern __shared__ __align__(16) float smem[];
+  fast::StreamKernelBody<true>(a, G, smem);
 }
 
 int StreamKernelMaxReceiversPerCta() { return fast::kFastMaxG; }
@@ -30,7 +35,10 @@ extern "C" int t41rx_debug_fast_cycles(unsigned long long *out32, int reset) {
 #endif
 
 cudaError_t ConfigureStreamKernel() {
-  return cudaFuncSetAttribute(t41rx_stream_rx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  const cudaError_t e = cudaFuncSetAttribute(t41rx_stream_rx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(fast::kFastMaxG * fast::kSlotF * sizeof(float) + 32));
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(t41rx_stream_rx_q15_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)(fast::kFastMaxG * fast::kSlotF * sizeof(float) + 32));
 }
 
@@ -47,7 +55,8 @@ cudaError_t LaunchStreamKernel(const LaunchArgs &a, int n_sms, cudaStream_t st) 
   }
 #endif
   const int grid = (a.n_streams + G - 1) / G;
-  t41rx_stream_rx_kernel<<<grid, 64 * G + 32, (size_t)G * fast::kSlotF * sizeof(float) + 32, st>>>(a, G);
+  if (a.iq16) t41rx_stream_rx_q15_kernel<<<grid, 64 * G + 32, (size_t)G * fast::kSlotF * sizeof(float) + 32, st>>>(a, G);
+  else t41rx_stream_rx_kernel<<<grid, 64 * G + 32, (size_t)G * fast::kSlotF * sizeof(float) + 32, st>>>(a, G);
   return cudaGetLastError();
 }
 

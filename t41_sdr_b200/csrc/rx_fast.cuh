@@ -132,6 +132,15 @@ __device__ __forceinline__ float SqrtFast(float x) {
   return r;
 }
 
+/* arm_float_to_q15 (Process.cpp:936): saturate(trunc(x * 32768)) to 16 bits; cvt.rzi.s16.f32 truncates toward zero,
+   saturates, and converts NaN to 0 like the target's VCVT */
+__device__ __forceinline__ unsigned PackQ15(float lo, float hi) {
+  short a, b;
+  asm("cvt.rzi.s16.f32 %0, %1;" : "=h"(a) : "f"(lo * 32768.0f));
+  asm("cvt.rzi.s16.f32 %0, %1;" : "=h"(b) : "f"(hi * 32768.0f));
+  return (unsigned)(unsigned short)a | ((unsigned)(unsigned short)b << 16);
+}
+
 struct F2 { float x, y; };
 
 /* packed FP32 pairs (sm_100 FFMA2: two FMAs per issue slot) */
@@ -514,6 +523,10 @@ __device__ __noinline__ void ReceiveEqPair(float *s, const float *eq_coeffs, con
 /* ------------------------------------------------------------------ */
 /* receiver pair: two warps (64 threads) per receiver                   */
 /* ------------------------------------------------------------------ */
+/* kQ15: the call's blocks are the firmware's q15 format (a.iq16 / a.audio16: arm_q15_to_float on the way in,
+   Process.cpp:107-108, arm_float_to_q15 on the way out, :936): 8 KiB in + 4 KiB out per stream-block instead of 16 + 8 */
+constexpr int kRawChunkWordsQ = 12;                   /* q15: 8 samples (8 words) + 4 pad: conflict-free LDS.128 */
+template <bool kQ15>
 struct RxPair {
   const LaunchArgs &a;
   float *s;          /* this receiver's slot */
@@ -541,17 +554,29 @@ struct RxPair {
   __device__ __forceinline__ const float *BlockIq(int t) const {
     return a.iq + ((size_t)sid * a.t_stride + t) * (2 * kBlock);
   }
+  __device__ __forceinline__ const int16_t *BlockIq16(int t) const {
+    return a.iq16 + ((size_t)sid * a.t_stride + t) * (2 * kBlock);
+  }
 
   /* issue this thread's share of the asynchronous copy of quarter q of block t into raw buffer (q & 1) */
   __device__ __forceinline__ void IssueQuarter(int t, int q) {
     /* one warp instruction copies 8 chunks (512 contiguous bytes); the 8 lanes of a quarter-warp write the
        same 16-byte piece of 8 different chunks: distinct banks (chunk stride 20 words).  Thread (w2, lane)
        copies piece (lane >> 3) of chunks 16 i + 8 w2 + (lane & 7), i = 0..3 */
-    const char *src = r.cp_src + ((size_t)t * 4 + q) * 4096;
     const unsigned dst = r.cp_dst + (q & 1) * (kRawBufWords * 4);
+    if (kQ15) {
+      /* q15: a chunk is 32 bytes = 2 pieces; thread (w2, lane) copies piece (lane >> 4) of chunks 32 i + 16 w2 + (lane & 15),
+         i = 0, 1: one warp instruction reads 512 contiguous bytes, 8 lanes write 8 different chunks (stride 12 words) */
+      const char *src = r.cp_src + ((size_t)t * 4 + q) * 2048;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 16 * (kRawChunkWords * 4)), "l"(src + i * 1024) : "memory");
+      for (int i = 0; i < 2; ++i)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 32 * (kRawChunkWordsQ * 4)), "l"(src + i * 1024) : "memory");
+    } else {
+      const char *src = r.cp_src + ((size_t)t * 4 + q) * 4096;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 16 * (kRawChunkWords * 4)), "l"(src + i * 1024) : "memory");
+    }
     CpAsyncCommit();
   }
 
@@ -628,7 +653,11 @@ struct RxPair {
       s[oMiscF + mFixedGain] = cf.agc.fixed_gain;
       s[oMiscF + mIqPhase] = cf.iq_phase;
     }
-    {
+    if (kQ15) {
+      const int chunk0 = 16 * w2 + (lane & 15), piece = lane >> 4;
+      r.cp_src = reinterpret_cast<const char *>(BlockIq16(0)) + chunk0 * 32 + piece * 16;
+      r.cp_dst = (unsigned)__cvta_generic_to_shared(s + oRaw) + chunk0 * (kRawChunkWordsQ * 4) + piece * 16;
+    } else {
       const int chunk0 = 8 * w2 + (lane & 7), piece = lane >> 3;
       r.cp_src = reinterpret_cast<const char *>(BlockIq(0)) + chunk0 * 64 + piece * 16;
       r.cp_dst = (unsigned)__cvta_generic_to_shared(s + oRaw) + chunk0 * (kRawChunkWords * 4) + piece * 16;
@@ -797,15 +826,32 @@ struct RxPair {
      cI / cQ: recurrence values entering the quarter (used by warp 0).  base: conj(block phasor) * Q[q] * gain. */
   template <bool kTable>
   __device__ __forceinline__ void QuarterMix(int q, float cI, float cQ, F2 base, const float2 *osc) {
-    const float *raw = s + oRaw + (q & 1) * kRawBufWords + tau * kRawChunkWords;
     /* the I and the Q chain run the same recurrence with the same constants: packed FP32 on (I, Q) pairs, which
        is how the samples sit in memory */
     P2 x[8];
+    if (kQ15) {
+      /* arm_q15_to_float: x / 32768, exact.  A word holds (I, Q) as two int16: flip the sign bits (offset binary), drop
+         each half into the mantissa of 256.0f (whose last place weighs 2^-15) and take 257 away again */
+      const float *raw = s + oRaw + (q & 1) * kRawBufWords + tau * kRawChunkWordsQ;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(raw + 4 * k);
-      x[2 * k] = v.x;
-      x[2 * k + 1] = v.y;
+      for (int k = 0; k < 2; ++k) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(raw + 4 * k);
+        const unsigned w[4] = {v.x ^ 0x80008000u, v.y ^ 0x80008000u, v.z ^ 0x80008000u, v.w ^ 0x80008000u};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float fi = __uint_as_float(__byte_perm(w[j], 0x43800000u, 0x7610));
+          const float fq = __uint_as_float(__byte_perm(w[j], 0x43800000u, 0x7632));
+          x[4 * k + j] = Fma2(Pack2(fi, fq), Dup(1.0f), Dup(-257.0f));
+        }
+      }
+    } else {
+      const float *raw = s + oRaw + (q & 1) * kRawBufWords + tau * kRawChunkWords;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(raw + 4 * k);
+        x[2 * k] = v.x;
+        x[2 * k + 1] = v.y;
+      }
     }
     /* zero-state recurrences */
     P2 w[8];
@@ -1467,6 +1513,7 @@ struct RxPair {
       c23[k] = Pack2(lo.y * vol, lo.x * vol);                              /* phases 2, 3: c[4k+1], c[4k]   */
     }
     float4 *dst = reinterpret_cast<float4 *>(a.audio + ((size_t)sid * a.t_stride + t) * kBlock);
+    uint2 *dst16 = reinterpret_cast<uint2 *>(a.audio16 + ((size_t)sid * a.t_stride + t) * kBlock);
 #pragma unroll 1
     for (int rr = 0; rr < 2; ++rr) {
       const int n0 = 4 * tau + 256 * rr;
@@ -1488,7 +1535,8 @@ struct RxPair {
         float4 o4;
         Unpack2(a01, o4.x, o4.y);
         Unpack2(a23, o4.z, o4.w);
-        dst[n0 + o] = o4;
+        if (kQ15) dst16[n0 + o] = uint2{PackQ15(o4.x, o4.y), PackQ15(o4.z, o4.w)};
+        else dst[n0 + o] = o4;
       }
     }
   }
@@ -1803,6 +1851,7 @@ __device__ __forceinline__ void AgcBlock(AgcLane &g, float *sta, bool active) {
 /* ------------------------------------------------------------------ */
 /* kernel body                                                          */
 /* ------------------------------------------------------------------ */
+template <bool kQ15>
 __device__ __forceinline__ void StreamKernelBody(const LaunchArgs &a, int G, float *smem) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s0 = blockIdx.x * G;
@@ -1829,7 +1878,7 @@ __device__ __forceinline__ void StreamKernelBody(const LaunchArgs &a, int G, flo
     const bool live = pair < ng;
     if (!live) return;
     const int sid = a.stream_ids ? __ldg(a.stream_ids + s0 + pair) : a.stream_base + s0 + pair;
-    RxPair w(a, smem + pair * kSlotF, sid, lane, pw & 1, 1 + pair);
+    RxPair<kQ15> w(a, smem + pair * kSlotF, sid, lane, pw & 1, 1 + pair);
     w.LoadState();
     w.IssueQuarter(0, 0);
     w.tm.Start(blockIdx.x == 0 && pw == 0 && lane == 0, 0);
@@ -1838,9 +1887,15 @@ __device__ __forceinline__ void StreamKernelBody(const LaunchArgs &a, int G, flo
          latency hides behind it */
       float4 tu = float4{0, 0, 0, 0}, tv = tu;
       if (k < T && (pw & 1) == 0) {
-        const float4 *p = reinterpret_cast<const float4 *>(w.BlockIq(k) + 2 * (kBlock - 4 * (lane + 1)));
-        tu = __ldg(p);
-        tv = __ldg(p + 1);
+        if (kQ15) {                    /* only the I components (.x, .z) are used */
+          const uint4 v = __ldg(reinterpret_cast<const uint4 *>(w.BlockIq16(k) + 2 * (kBlock - 4 * (lane + 1))));
+          tu = float4{(float)(short)(v.x & 0xffffu) * (1.0f / 32768.0f), 0.0f, (float)(short)(v.y & 0xffffu) * (1.0f / 32768.0f), 0.0f};
+          tv = float4{(float)(short)(v.z & 0xffffu) * (1.0f / 32768.0f), 0.0f, (float)(short)(v.w & 0xffffu) * (1.0f / 32768.0f), 0.0f};
+        } else {
+          const float4 *p = reinterpret_cast<const float4 *>(w.BlockIq(k) + 2 * (kBlock - 4 * (lane + 1)));
+          tu = __ldg(p);
+          tv = __ldg(p + 1);
+        }
       }
       if (k >= 2) {
         MbarWait(done + (k & 1), (unsigned)(((k - 2) >> 1) & 1));

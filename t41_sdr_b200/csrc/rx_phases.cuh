@@ -107,6 +107,11 @@ enum { mDcD1 = 0, mDcD2 = 1, mNcoMode = 2, mDcBad = 3, mDcSpec = 4 /* 32 x 2 */,
 struct LaunchArgs {
   const float *iq;
   float *audio;
+  /* the firmware's q15 block format instead (both set, iq / audio NULL): int16 [receiver][block][2048][2] in,
+     int16 [receiver][block][2048] out; every kernel converts at its own load / store (arm_q15_to_float = x / 32768,
+     arm_float_to_q15 = saturate(trunc(x * 32768)); Process.cpp:107-108,936) */
+  const int16_t *iq16;
+  int16_t *audio16;
   int16_t *spec_rows;
   uint16_t *wf_rows;
   int8_t *psk_bits;
@@ -139,6 +144,12 @@ struct LaunchArgs {
   /* what the row-producing blocks write to the control app's serial port (NULL when not bound) */
   uint8_t *spec_frames;       /* [receiver][n_rows][518] */
   uint8_t *audio_frames;      /* [receiver][n_rows][270] */
+  /* split form of the bit-exact chain (front kernel | serial kernel, thread = receiver | back kernel): hand-over
+     through HBM, receiver-minor so that the serial kernel's lanes read and write consecutive words:
+       ser_in  [n_blocks][256][n_streams]  (delayed z.re, delayed z.im, delayed |z|, window maximum)
+       ser_out [n_blocks][256][n_streams]  demodulated audio sample */
+  float4 *ser_in;
+  float *ser_out;
 };
 
 struct Cta {
@@ -155,6 +166,25 @@ struct Cta {
 T41RX_DEV float *Slot(const Cta &c, int g) { return c.smem + g * kSlot; }
 /* receiver index of slot g of this CTA */
 T41RX_DEV int Sid(const Cta &c, int g) { return c.a.stream_ids ? LdgRO(c.a.stream_ids + c.s0 + g) : c.a.stream_base + c.s0 + g; }
+
+/* one word of a receiver's I/Q (float index `w` inside the [receiver][block][2048][2] array, block-relative base
+   already applied): the float buffer, or arm_q15_to_float of the q15 one (x / 32768, exact) */
+T41RX_DEV float IqWord(const LaunchArgs &a, size_t w) {
+  return a.iq16 ? (float)LdgRO(a.iq16 + w) / 32768.0f : LdgRO(a.iq + w);
+}
+/* arm_float_to_q15 (Process.cpp:936): saturate((q31)(x * 32768)) to 16 bits, truncation toward zero; NaN -> 0 (the
+   target's VCVT.S32.F32) */
+T41RX_DEV int16_t FloatToQ15Word(float x) {
+  const float v = x * 32768.0f;
+  int q;
+  if (v != v) q = 0;
+  else if (!(v > -2147483648.0f)) q = INT32_MIN;
+  else if (v >= 2147483648.0f) q = INT32_MAX;
+  else q = (int)v;
+  q = q > 32767 ? 32767 : q;
+  q = q < -32768 ? -32768 : q;
+  return (int16_t)q;
+}
 
 /* which receiver (or -1) thread `tid` serves in a one-lane-per-receiver serial phase:
  * T41RX_SERIAL_WPS = 1: lane 0 of the receiver's own first warp (no divergence between receivers
@@ -348,10 +378,19 @@ T41RX_DEV void PhLoad(Cta &c, int tid) {
 #pragma unroll
     for (int gg = 0; gg < 2; ++gg) {
       if (g0 + gg >= c.ng) continue;
-      const float4 *src = reinterpret_cast<const float4 *>(
-          c.a.iq + ((size_t)(Sid(c, g0 + gg)) * c.a.t_stride + c.t) * (2 * kBlock));
+      const size_t blk = ((size_t)(Sid(c, g0 + gg)) * c.a.t_stride + c.t) * (2 * kBlock);
+      if (c.a.iq16) {
+        const short4 *src = reinterpret_cast<const short4 *>(c.a.iq16 + blk);
 #pragma unroll
-      for (int k = 0; k < kPer; ++k) v[gg][k] = LdgRO(src + tid + kNT * k);
+        for (int k = 0; k < kPer; ++k) {
+          const short4 q = LdgRO(src + tid + kNT * k);
+          v[gg][k] = float4{(float)q.x / 32768.0f, (float)q.y / 32768.0f, (float)q.z / 32768.0f, (float)q.w / 32768.0f};
+        }
+      } else {
+        const float4 *src = reinterpret_cast<const float4 *>(c.a.iq + blk);
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) v[gg][k] = LdgRO(src + tid + kNT * k);
+      }
     }
 #pragma unroll
     for (int gg = 0; gg < 2; ++gg) {
@@ -374,9 +413,10 @@ T41RX_DEV void PhLoad(Cta &c, int tid) {
       s[(ch ? oRawQ : oRawI) + i] = s[oD1H + h];
     }
     if (c.t + 1 < c.a.n_blocks) {
-      const char *nxt = reinterpret_cast<const char *>(
-          c.a.iq + ((size_t)(Sid(c, g)) * c.a.t_stride + c.t + 1) * (2 * kBlock));
-      for (int line = tid; line < (2 * kBlock * 4) / 128; line += kNT) PrefetchL2(nxt + 128 * line);
+      const size_t blk = ((size_t)(Sid(c, g)) * c.a.t_stride + c.t + 1) * (2 * kBlock);
+      const char *nxt = c.a.iq16 ? reinterpret_cast<const char *>(c.a.iq16 + blk) : reinterpret_cast<const char *>(c.a.iq + blk);
+      const int bytes = c.a.iq16 ? 2 * kBlock * 2 : 2 * kBlock * 4;
+      for (int line = tid; line < bytes / 128; line += kNT) PrefetchL2(nxt + 128 * line);
     }
   }
 }
@@ -549,11 +589,11 @@ T41RX_DEV void PhDcFix(Cta &c, int tid) {
       break;
   }
   if (bad >= kDcChunks) return;
-  const float *src = c.a.iq + ((size_t)(Sid(c, g)) * c.a.t_stride + c.t) * (2 * kBlock);
+  const size_t src = ((size_t)(Sid(c, g)) * c.a.t_stride + c.t) * (2 * kBlock);
   float d1 = s[oMisc + mDcEnd + 2 * (bad - 1)];
   float d2 = s[oMisc + mDcEnd + 2 * (bad - 1) + 1];
   for (int i = bad * kDcChunkLen; i < 2 * kBlock; ++i)
-    s[SeqOff(i)] = LdgRO(src + (i < kBlock ? 2 * i : 2 * (i - kBlock) + 1));
+    s[SeqOff(i)] = IqWord(c.a, src + (i < kBlock ? 2 * i : 2 * (i - kBlock) + 1));
   DcRun<true>(s, p, bad * kDcChunkLen, 2 * kBlock, d1, d2);
   s[oMisc + mDcD1] = d1;
   s[oMisc + mDcD2] = d2;
@@ -1485,6 +1525,380 @@ T41RX_DEV void PhDemodSerial(Cta &c, int tid) {
 }
 
 /* ------------------------------------------------------------------ */
+/* Split form of the chain: what PhAgcSerial / PhAgcPost / PhDemod* do   */
+/* on ONE LANE PER RECEIVER (the envelope detector, the SAM PLL and the  */
+/* AM detector are serial chains over the 256 samples of a block) runs   */
+/* in a kernel of its own with THREAD = RECEIVER, 32 receivers per warp, */
+/* over all blocks of the launch; the sample-parallel phases before and  */
+/* after it keep their 64 threads per receiver in a front and a back     */
+/* kernel.  Every float operation is the one the fused schedule does, in */
+/* the same order: the three kernels are bit-identical to it.            */
+/* ------------------------------------------------------------------ */
+/* front kernel, after the AGC look-ahead: hand the block to the serial kernel and refresh the delay line
+   (PhAgcPost's second half).  Thread (i, g) = (tid >> 2, tid & 3): four adjacent lanes write 64 contiguous bytes. */
+T41RX_DEV void PhSerialStore(Cta &c, int tid) {
+  const int g = tid % kG, u = tid / kG;           /* u: 0..63 */
+  if (g < c.ng) {
+    const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+    const float *s = Slot(c, g);
+    const size_t n = (size_t)c.a.n_streams;
+    float4 *dst = c.a.ser_in + ((size_t)c.t * kDec) * n + (size_t)(c.s0 + g);
+    const bool filt = UsesFilter(cf.mode);
+    const bool agc = filt && cf.agc_mode != 0;
+    const float2 *zext = reinterpret_cast<const float2 *>(s + vZext);
+    const float2 *dem = reinterpret_cast<const float2 *>(s + vDem);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = u + 64 * j;
+      float4 v;
+      if (agc) {
+        const float2 z = zext[i];
+        v = float4{z.x, z.y, s[vAbs + i], s[vRm + i]};
+      } else if (filt) {
+        const float2 z = dem[i];                  /* AGC off: PhAgcPre applied the fixed gain */
+        v = float4{z.x, z.y, 0.0f, 0.0f};
+      } else {
+        v = float4{s[vAud + 23 + i], 0.0f, 0.0f, 0.0f};   /* raw PSK31 mode: the decimated I channel is the audio */
+      }
+      dst[(size_t)i * n] = v;
+    }
+  }
+}
+T41RX_DEV void PhSerialRing(Cta &c, int tid) {
+  const int g = tid >> 6, u = tid & 63;
+  if (g >= c.ng) return;
+  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+  if (!UsesFilter(cf.mode) || cf.agc_mode == 0) return;
+  float *s = Slot(c, g);
+  const float2 *zext = reinterpret_cast<const float2 *>(s + vZext);
+  /* ring index r holds new sample 128 + r of this block = zext[97 + 128 + r] */
+  for (int r = u; r < kAgcRing; r += 64) {
+    const float2 z = zext[kAgcDelay + 128 + r];
+    s[oAgc + r] = z.x;
+    s[oAgc + 128 + r] = z.y;
+    s[oAgc + 256 + r] = s[vAbs + kAgcDelay + 128 + r];
+  }
+}
+
+/* Codec_gain alone (the front kernel's share of PhBlockEnd) */
+T41RX_DEV void PhCodecGain(Cta &c, int tid) {
+  if (tid != kNT - 1) return;
+  for (int g = 0; g < c.ng; ++g) {
+    StreamState &st = c.a.st[Sid(c, g)];
+    uint32_t timer = st.codec_timer + 1;
+    if (timer > 10000) timer = 10000;
+    if (timer >= 50) {
+      int rg = st.rf_gain + 1;
+      if (rg > 15) rg = 15;
+      st.rf_gain = rg;
+      timer = 0;
+    }
+    st.codec_timer = timer;
+  }
+}
+
+/* the serial kernel's work for receiver number r of the launch: AGC envelope (DSP_Fn.cpp:504-631), gain
+   (DSP_Fn.cpp:628), demodulator (Process.cpp:615-761, Demod.cpp:40-139) and the PSK31 tap, for every block.
+   sin_tab: arm_sin_f32's table (shared memory on the device). */
+T41RX_DEV void SerialReceiver(const LaunchArgs &a, int r, const float *sin_tab) {
+  const int sid = a.stream_ids ? LdgRO(a.stream_ids + r) : a.stream_base + r;
+  const StreamCfg &cf = a.cfg[sid];
+  StreamState &st = a.st[sid];
+  const size_t n = (size_t)a.n_streams;
+  const int mode = cf.mode;
+  const bool filt = UsesFilter(mode);
+  const bool agc_on = filt && cf.agc_mode != 0;
+  /* AGC constants and state */
+  const float k_fbm = cf.agc.fast_backmult, k_omfbm = cf.agc.onemfast_backmult;
+  const float k_hbm = cf.agc.hang_backmult, k_omhbm = cf.agc.onemhang_backmult;
+  const float k_attack = cf.agc.attack_mult, k_decay = cf.agc.decay_mult, k_fdecay = cf.agc.fast_decay_mult;
+  const float k_hdecay = cf.agc.hang_decay_mult, k_pop = cf.agc.pop_ratio, k_hlevel = cf.agc.hang_level;
+  const float k_minv = cf.agc.min_volts;
+  const float k_inv_in = cf.agc.inv_max_input, k_target = cf.agc.out_target, k_slope = cf.agc.slope_constant;
+  const int k_hload = cf.agc.hang_counter_load, k_henable = cf.agc.hang_enable;
+  float fast = st.agc_fast_back, hang = st.agc_hang_back, v = st.agc_volts, save = st.agc_save_volts;
+  int hc = st.agc_hang_counter, state = st.agc_state, dtype = st.agc_decay_type, action = st.agc_action;
+  float rm = st.agc_ring_max;
+  /* AM detector */
+  float wold = st.am_wold;
+  float x1 = st.am_lp_state[0], x2 = st.am_lp_state[1], y1 = st.am_lp_state[2], y2 = st.am_lp_state[3];
+  const float b0 = cf.am_lp[0], b1 = cf.am_lp[1], b2 = cf.am_lp[2], a1 = cf.am_lp[3], a2 = cf.am_lp[4];
+  /* SAM PLL */
+  const float tpi = 6.283185307179586476925286766559f;
+  const float omega_min = LdgRO(a.sam_consts + 0), omega_max = LdgRO(a.sam_consts + 1);
+  const float g1 = LdgRO(a.sam_consts + 2), g2 = LdgRO(a.sam_consts + 3);
+  float phz = st.sam_phzerror, fil = st.sam_fil_out, om2 = st.sam_omega2;
+  constexpr int kU = 8;                            /* samples per step of the software pipeline */
+  const float4 *src = a.ser_in + r;
+  float *dst = a.ser_out + r;
+  float4 nx[kU];
+#pragma unroll
+  for (int k = 0; k < kU; ++k) nx[k] = LdgRO(src + (size_t)k * n);
+  for (int t = 0; t < a.n_blocks; ++t) {
+    float2 dem0 = float2{0.0f, 0.0f};
+    /* the phase of sample i + 1 is phz + the loop filter's output of sample i - 1: its sine / cosine are formed
+       beside sample i's arctangent (same operations on the same values as the reference's loop) */
+    float sn = 0.0f, cs = 0.0f;
+    if (mode == kModeSam) {
+      sn = TableTurns(sin_tab, phz * 0.159154943092f);
+      cs = TableTurns(sin_tab, phz * 0.159154943092f + 0.25f);
+    }
+    for (int i0 = 0; i0 < kDec; i0 += kU) {
+      float4 cur[kU];
+#pragma unroll
+      for (int k = 0; k < kU; ++k) cur[k] = nx[k];
+      {                                            /* next step's inputs: in flight while this one is computed */
+        const size_t e = (size_t)t * kDec + i0 + kU;
+        if (e < (size_t)a.n_blocks * kDec) {
+#pragma unroll
+          for (int k = 0; k < kU; ++k) nx[k] = LdgRO(src + (e + k) * n);
+        }
+      }
+      float vv[kU];
+      if (agc_on) {
+        /* the envelope state machine, sample by sample (PhAgcSerial's generic step) */
+#pragma unroll
+        for (int k = 0; k < kU; ++k) {
+          const float abs_out = cur[k].z;
+          fast = k_fbm * abs_out + k_omfbm * fast;
+          hang = k_hbm * abs_out + k_omhbm * hang;
+          rm = cur[k].w;
+          if (hc > 0) --hc;
+          const float d = rm - v;
+          if (rm >= v) {
+            if (state >= 2) save = v;
+            state = 0;
+            v += d * k_attack;
+          } else if (state == 3) {
+            const float step = d * k_decay;
+            v = (float)((double)v + (double)step * .05);
+          } else if (state == 0) {
+            if (v > k_pop * fast) {
+              state = 1;
+              v += d * k_fdecay;
+            } else if (k_henable && (hang > k_hlevel)) {
+              state = 2;
+              hc = k_hload;
+              dtype = 1;
+            } else {
+              state = 3;
+              v += d * k_decay;
+              dtype = 0;
+            }
+          } else if (state == 1) {
+            if (v > save) {
+              v += d * k_fdecay;
+            } else if (hc > 0) {
+              state = 2;
+            } else if (dtype == 0) {
+              state = 3;
+              v += d * k_decay;
+            } else {
+              state = 4;
+              v += d * k_hdecay;
+            }
+          } else if (state == 2) {
+            if (hc == 0) {
+              state = 4;
+              v += d * k_hdecay;
+            }
+          } else {
+            v += d * k_hdecay;
+          }
+          action = (v < k_minv) ? 0 : 1;
+          v = (v < k_minv) ? k_minv : v;
+          vv[k] = v;
+        }
+        /* gain from volts (PhAgcPost), independent from sample to sample */
+#pragma unroll
+        for (int k = 0; k < kU; ++k) {
+          const double lg = (double)Log10Fast(k_inv_in * vv[k]);
+          const double clipped = (0.0 < lg) ? 0.0 : lg;
+          const float mult = (float)(((double)k_target - (double)k_slope * clipped) / (double)vv[k]);
+          cur[k].x = cur[k].x * mult;
+          cur[k].y = cur[k].y * mult;
+        }
+      }
+      if (i0 == 0) dem0 = float2{cur[0].x, cur[0].y};
+      float au[kU];
+      if (mode == kModeSam) {
+#pragma unroll
+        for (int k = 0; k < kU; ++k) {
+          const float zx = cur[k].x, zy = cur[k].y;
+          float phz_n = phz + fil;
+          phz_n = (phz_n >= tpi) ? phz_n - tpi : phz_n;
+          phz_n = (phz_n < 0.0f) ? phz_n + tpi : phz_n;
+          const float sn_n = TableTurns(sin_tab, phz_n * 0.159154943092f);
+          const float cs_n = TableTurns(sin_tab, phz_n * 0.159154943092f + 0.25f);
+          const float ai = cs * zx, bi = sn * zx, aq = cs * zy, bq = sn * zy;
+          const float corr0 = +ai + bq;
+          const float corr1 = -bi + aq;
+          float audio = (ai - bi) + (aq + bq);
+          audio = (audio + 0.0f) - 0.0f;           /* the fade leveller's identity (see PhDemodSerial) */
+          au[k] = audio;
+          const float det = Atan2Approx(corr1, corr0);
+          om2 = om2 + g2 * det;
+          if (om2 < omega_min) om2 = omega_min;
+          else if (om2 > omega_max) om2 = omega_max;
+          fil = g1 * det + om2;
+          phz = phz_n;
+          sn = sn_n;
+          cs = cs_n;
+        }
+      } else if (mode == kModeAm) {
+#pragma unroll
+        for (int k = 0; k < kU; ++k) {
+          const float m = AlphaBetaMag(cur[k].x, cur[k].y);
+          const float w = m + wold * 0.99f;
+          const float x = w - wold;
+          wold = w;
+          float acc = b0 * x;
+          acc = acc + b1 * x1;
+          acc = acc + b2 * x2;
+          acc = acc + a1 * y1;
+          acc = acc + a2 * y2;
+          x2 = x1; x1 = x;
+          y2 = y1; y1 = acc;
+          au[k] = acc;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < kU; ++k) au[k] = cur[k].x;   /* USB / LSB / NFM: real part; raw PSK31 mode: the sample itself */
+      }
+      {
+        const size_t e = (size_t)t * kDec + i0;
+#pragma unroll
+        for (int k = 0; k < kU; ++k) dst[(e + k) * n] = au[k];
+      }
+    }
+    /* PSK31 tap (psk31.cpp:235-310): first filtered sample of every third block */
+    int8_t bit_out = -1;
+    uint8_t char_out = 0;
+    if (cf.psk31_enable && mode != kModeNfm && mode != kModePsk31) {
+      if (st.psk_block_count % 3u == 0u) {
+        const double pi_d = 3.1415926535897932384626433832795;
+        const float phase = Atan2Approx(dem0.y, dem0.x);
+        float dphase = phase - st.psk_last_phase;
+        while ((double)dphase < -pi_d) dphase = (float)((double)dphase + 2 * pi_d);
+        while ((double)dphase >= pi_d) dphase = (float)((double)dphase - 2 * pi_d);
+        const uint8_t bit = (((double)dphase > (pi_d / 2)) || ((double)dphase < (-pi_d / 2))) ? 0 : 1;
+        st.psk_last_phase = phase;
+        bit_out = (int8_t)bit;
+        unsigned long long shr = (st.psk_shr << 1) | (unsigned long long)bit;
+        if ((shr & 0xFFFull) != 0) {
+          for (int i = 0; i < 128; ++i) {
+            const uint32_t e = LdgRO(a.varicode + i);
+            const unsigned long long want = ((unsigned long long)(e & 0xFFFFu)) << 2;
+            const unsigned nbits = (((e >> 16) & 0xFFu) + 4u) & 63u;
+            const unsigned long long keep = (nbits == 0) ? 0ull : (~0ull >> (64u - nbits));
+            if (want == (shr & keep)) {
+              shr = 0;
+              char_out = (uint8_t)(e >> 24);
+              break;
+            }
+          }
+        }
+        st.psk_shr = shr;
+      }
+      st.psk_block_count++;
+    }
+    const size_t o = (size_t)sid * a.t_stride + t;
+    if (a.psk_bits) a.psk_bits[o] = bit_out;
+    if (a.psk_chars) a.psk_chars[o] = char_out;
+  }
+  if (agc_on) {
+    st.agc_fast_back = fast;
+    st.agc_hang_back = hang;
+    st.agc_volts = v;
+    st.agc_save_volts = save;
+    st.agc_ring_max = rm;
+    st.agc_hang_counter = hc;
+    st.agc_state = state;
+    st.agc_decay_type = dtype;
+    st.agc_action = action;
+  }
+  if (mode == kModeAm) {
+    st.am_wold = wold;
+    st.am_lp_state[0] = x1; st.am_lp_state[1] = x2; st.am_lp_state[2] = y1; st.am_lp_state[3] = y2;
+  } else if (mode == kModeSam) {
+    st.sam_phzerror = phz;
+    st.sam_fil_out = fil;
+    st.sam_omega2 = om2;
+  }
+}
+
+/* back kernel: the demodulated block from the serial kernel into the audio buffer (+ PhInterp1's history restore) */
+T41RX_DEV void PhBackLoad(Cta &c, int tid) {
+  const int g = tid % kG, u = tid / kG;
+  if (g < c.ng) {
+    float *s = Slot(c, g);
+    const size_t n = (size_t)c.a.n_streams;
+    const float *src = c.a.ser_out + ((size_t)c.t * kDec) * n + (size_t)(c.s0 + g);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = u + 64 * j;
+      s[vAud + 23 + i] = src[(size_t)i * n];
+    }
+  }
+  for (int gg = 0; gg < c.ng; ++gg) {
+    float *s = Slot(c, gg);
+    for (int h = tid; h < 23; h += kNT) s[vAud + h] = s[oIntH + h];
+  }
+}
+T41RX_DEV void PhBackStateIn(Cta &c, int tid) {
+  for (int g = 0; g < c.ng; ++g) {
+    float *s = Slot(c, g);
+    const StreamState &st = c.a.st[Sid(c, g)];
+    const FilterSet &fs = c.a.fsets[c.a.cfg[Sid(c, g)].filter_id];
+    for (int i = tid; i < 154; i += kNT) {
+      float v;
+      if (i < kTapDec2) v = fs.dec1[i];
+      else if (i < kTapInt1) v = fs.dec2[i - kTapDec2];
+      else if (i < kTapInt2) v = fs.int1[i - kTapInt1];
+      else v = fs.int2[i - kTapInt2];
+      s[oTaps + i] = v;
+    }
+    for (int i = tid; i < 23; i += kNT) s[oIntH + i] = st.int1_hist[i];
+    for (int i = tid; i < 7; i += kNT) s[oIntH + 24 + i] = st.int2_hist[i];
+  }
+}
+T41RX_DEV void PhBackStateOut(Cta &c, int tid) {
+  for (int g = 0; g < c.ng; ++g) {
+    float *s = Slot(c, g);
+    StreamState &st = c.a.st[Sid(c, g)];
+    for (int i = tid; i < 23; i += kNT) st.int1_hist[i] = s[oIntH + i];
+    for (int i = tid; i < 7; i += kNT) st.int2_hist[i] = s[oIntH + 24 + i];
+  }
+}
+/* the front kernel's state: everything PhStateOut stores except the interpolator histories (the back kernel's) */
+T41RX_DEV void PhFrontStateOut(Cta &c, int tid) {
+  for (int g = 0; g < c.ng; ++g) {
+    float *s = Slot(c, g);
+    StreamState &st = c.a.st[Sid(c, g)];
+    for (int i = tid; i < 512; i += kNT) st.ola_prev[i >> 8][i & 255] = s[oOla + i];
+    for (int i = tid; i < 128; i += kNT) {
+      st.agc_re[i] = s[oAgc + i];
+      st.agc_im[i] = s[oAgc + 128 + i];
+      st.agc_abs[i] = s[oAgc + 256 + i];
+    }
+    for (int i = tid; i < 54; i += kNT) st.dec1_hist[i / 27][i % 27] = s[oD1H + i];
+    for (int i = tid; i < 90; i += kNT) st.dec2_hist[i / 45][i % 45] = s[oD2H + i];
+    if (tid == 0) {
+      st.dc_d1 = s[oMisc + mDcD1];
+      st.dc_d2 = s[oMisc + mDcD2];
+      st.fast_native = 0;
+    }
+  }
+}
+/* int2 history alone (the back kernel's share of PhBlockEnd) */
+T41RX_DEV void PhBackBlockEnd(Cta &c, int tid) {
+  for (int g = 0; g < c.ng; ++g) {
+    float *s = Slot(c, g);
+    for (int h = tid; h < 7; h += kNT) s[oIntH + 24 + h] = s[vInt2 + 2 * kDec + h];
+  }
+}
+
+/* ------------------------------------------------------------------ */
 /* P14/P15: arm_fir_interpolate_f32 x2 (48 taps) and x4 (32 taps), volume */
 /* (Process.cpp:917-931)                                                 */
 /* ------------------------------------------------------------------ */
@@ -1698,6 +2112,7 @@ T41RX_DEV void PhInterp2(Cta &c, int tid) {
   float *s = Slot(c, g);
   const float volume = c.a.cfg[Sid(c, g)].volume;
   float4 *dst = reinterpret_cast<float4 *>(c.a.audio + ((size_t)(Sid(c, g)) * c.a.t_stride + c.t) * kBlock);
+  int16_t *dst16 = c.a.audio16 ? c.a.audio16 + ((size_t)(Sid(c, g)) * c.a.t_stride + c.t) * kBlock : nullptr;
   for (int h = u; h < 23; h += 64) s[oIntH + h] = s[vAud + kDec + h];   /* int1 history for the next block */
   float taps[kInt2Taps];
 #pragma unroll
@@ -1722,7 +2137,13 @@ T41RX_DEV void PhInterp2(Cta &c, int tid) {
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const int n = u + 64 * (4 * half + r);
-      dst[n] = float4{acc[r][0] * volume, acc[r][1] * volume, acc[r][2] * volume, acc[r][3] * volume};
+      const float4 o4 = float4{acc[r][0] * volume, acc[r][1] * volume, acc[r][2] * volume, acc[r][3] * volume};
+      if (dst16) {
+        dst16[4 * n] = FloatToQ15Word(o4.x); dst16[4 * n + 1] = FloatToQ15Word(o4.y);
+        dst16[4 * n + 2] = FloatToQ15Word(o4.z); dst16[4 * n + 3] = FloatToQ15Word(o4.w);
+      } else {
+        dst[n] = o4;
+      }
     }
   }
 }
@@ -1766,10 +2187,10 @@ T41RX_DEV void PhRowDcSeed(Cta &c, int tid) {
   }
   const DcCoef k = DcCoefs();
   const float rfg = c.a.cfg[Sid(c, g)].rf_gain_value;
-  const float *q = c.a.iq + ((size_t)Sid(c, g) * c.a.t_stride + (c.t - 1)) * (2 * kBlock) + 2 * (kBlock - kDcWarm) + 1;
+  const size_t q = ((size_t)Sid(c, g) * c.a.t_stride + (c.t - 1)) * (2 * kBlock) + 2 * (kBlock - kDcWarm) + 1;
   float d1 = 0.0f, lx = 0.0f, ly = 0.0f;
   for (int i = 0; i < kDcWarm; ++i) {
-    const float x = LdgRO(q + 2 * i) * rfg;
+    const float x = IqWord(c.a, q + 2 * i) * rfg;
     ly = DcStep(k, x, d1);
     lx = x;
   }
@@ -1787,8 +2208,8 @@ T41RX_DEV void PhRowTailLoad(Cta &c, int tid) {
   const int g = tid >> 6, u = tid & 63;
   if (g >= c.ng) return;
   float *s = Slot(c, g);
-  const float2 *q = reinterpret_cast<const float2 *>(c.a.iq + ((size_t)Sid(c, g) * c.a.t_stride + (c.t - 1)) * (2 * kBlock)) + (kBlock - kDcWarm);
-  for (int i = u; i < kDcWarm; i += 64) s[vRowTail + i] = LdgRO(q + i).y;
+  const size_t q = ((size_t)Sid(c, g) * c.a.t_stride + (c.t - 1)) * (2 * kBlock) + 2 * (kBlock - kDcWarm);
+  for (int i = u; i < kDcWarm; i += 64) s[vRowTail + i] = IqWord(c.a, q + 2 * i + 1);
 }
 T41RX_DEV void PhRowDcSeedFast(Cta &c, int tid) {
   const int g = SerialStream(c, tid);
@@ -2269,6 +2690,58 @@ T41RX_DEV void PhSpecFrameWrite(Cta &c, int tid) {
   RX_PHASE(PhInterp1b(c, tid));                                          \
   RX_PHASE(PhInterp2(c, tid));                                           \
   RX_PHASE(PhBlockEnd(c, tid));
+
+/* the same block as three kernels (see "Split form of the chain") */
+#define T41RX_FRONT_SCHEDULE(RX_PHASE)                                   \
+  RX_PHASE(PhLoad(c, tid));                                              \
+  RX_PHASE(PhDcWarm(c, tid));                                            \
+  RX_PHASE(PhDcMain(c, tid));                                            \
+  RX_PHASE(PhDcVerify(c, tid));                                          \
+  RX_PHASE(PhDcFix(c, tid));                                             \
+  if (c.row) {                                                           \
+    RX_PHASE(PhZoomIir(c, tid));                                         \
+    RX_PHASE(PhSpecWindow(c, tid));                                      \
+    RX_PHASE(PhSpecFftPass(c, tid, 0));                                  \
+    RX_PHASE(PhSpecFftPass(c, tid, 1));                                  \
+    RX_PHASE(PhSpecFftPass(c, tid, 2));                                  \
+    RX_PHASE(PhSpecRow(c, tid));                                         \
+  }                                                                      \
+  RX_PHASE(PhNcoPrep(c, tid));                                           \
+  RX_PHASE(PhMix(c, tid));                                               \
+  RX_PHASE(PhNcoAdvance(c, tid); PhDec1(c, tid));                        \
+  RX_PHASE(PhDec2(c, tid));                                              \
+  RX_PHASE(PhPostDec2(c, tid));                                          \
+  RX_PHASE(PhNfmAssemble(c, tid));                                       \
+  RX_PHASE(PhNfmAssemble2(c, tid));                                      \
+  RX_PHASE(PhFftPass(c, tid, 0, 0));                                     \
+  RX_PHASE(PhFftPass(c, tid, 0, 1));                                     \
+  RX_PHASE(PhFftPass(c, tid, 0, 2));                                     \
+  RX_PHASE(PhMask(c, tid));                                              \
+  RX_PHASE(PhFftPass(c, tid, 1, 0));                                     \
+  RX_PHASE(PhFftPass(c, tid, 1, 1));                                     \
+  RX_PHASE(PhFftPass(c, tid, 1, 2));                                     \
+  RX_PHASE(PhAgcPre(c, tid));                                            \
+  RX_PHASE(PhAgcMaxLevel(c, tid, 1));                                    \
+  RX_PHASE(PhAgcMaxLevel(c, tid, 2));                                    \
+  RX_PHASE(PhAgcMaxLevel(c, tid, 3));                                    \
+  RX_PHASE(PhAgcMaxLevel(c, tid, 4));                                    \
+  RX_PHASE(PhAgcMaxLevel(c, tid, 5));                                    \
+  RX_PHASE(PhAgcMaxLevel(c, tid, 6));                                    \
+  RX_PHASE(PhAgcMaxLevel(c, tid, 7));                                    \
+  RX_PHASE(PhSerialStore(c, tid));                                       \
+  RX_PHASE(PhSerialRing(c, tid); PhCodecGain(c, tid));
+
+#define T41RX_BACK_SCHEDULE(RX_PHASE)                                    \
+  RX_PHASE(PhBackLoad(c, tid));                                          \
+  RX_PHASE(PhEqBands(c, tid));                                           \
+  RX_PHASE(PhEqSum(c, tid));                                             \
+  RX_PHASE(PhNrStage(c, tid, 0));                                        \
+  RX_PHASE(PhNrNotch(c, tid));                                           \
+  RX_PHASE(PhNrStage(c, tid, 1));                                        \
+  RX_PHASE(PhCwFilter(c, tid));                                          \
+  RX_PHASE(PhInterp1b(c, tid));                                          \
+  RX_PHASE(PhInterp2(c, tid));                                           \
+  RX_PHASE(PhBackBlockEnd(c, tid));
 
 }  // namespace t41rx
 #endif

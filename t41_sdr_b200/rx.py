@@ -24,11 +24,13 @@ FLAG_EXACT_NCO = 1       # bit-exact kernel, step-by-step FP64 oscillator
 FLAG_PHASED_KERNEL = 2   # bit-exact kernel with the closed-form FP64 oscillator
 FLAG_FAST_LMS = 8        # LMS / notch receivers on the throughput kernel too (audio SNR >= 70 dB instead of 90)
 FLAG_FAST_SAM = 16       # SAM receivers on the throughput kernel too (acquisition transient differs, locked: >= 90 dB)
+FLAG_FUSED_EXACT = 32    # bit-exact chain as the single fused kernel instead of front | serial | back kernels
 FLAG_SCAN_ROWS = 4       # rows kernel: scan form of the ZoomFFT biquads (<= 1 LSB, < 1 % of pixels)
 # flags = 0: the throughput kernel
 
 # algorithmic HBM bytes per stream-block
 BYTES_PER_BLOCK = 2 * BLOCK * 4 + BLOCK * 4        # 16 KiB I/Q in + 8 KiB audio out
+BYTES_PER_BLOCK_Q15 = 2 * BLOCK * 2 + BLOCK * 2    # the firmware's q15 blocks: 8 KiB I/Q in + 4 KiB audio out
 BYTES_PER_ROW = SPECTRUM_RES * 2 + SPECTRUM_RES * 2  # int16 spectrum row + RGB565 waterfall row
 
 
@@ -79,7 +81,7 @@ EXPORTS = (
     "t41rx_default_params", "t41rx_mode_default_cuts", "t41rx_create", "t41rx_destroy",
     "t41rx_num_streams", "t41rx_set_params", "t41rx_set_params_each", "t41rx_get_params",
     "t41rx_get_tables", "t41rx_get_debug", "t41rx_design_tables", "t41rx_process", "t41rx_process_q15",
-    "t41rx_process_device", "t41rx_synchronize", "t41rx_kernel_launches", "t41rx_last_kernel_ms",
+    "t41rx_process_device", "t41rx_process_device_q15", "t41rx_synchronize", "t41rx_kernel_launches", "t41rx_last_kernel_ms",
     "t41rx_stream_kernel_times", "t41rx_bind_audio_spectrum", "t41rx_bind_control_frames", "t41rx_smeter_dbm", "t41rx_smeter_bar",
     "t41rx_load_wav", "t41rx_read_wave", "t41rx_wav_sample_rate", "t41rx_wav_close",
     "t41rx_last_error", "t41rx_version")
@@ -114,6 +116,7 @@ def lib():
         L.t41rx_process.argtypes = [vp, vp, vp, ip, ip, vp, vp, vp, vp, C.c_uint32]
         L.t41rx_process_q15.argtypes = [vp, vp, vp, ip, ip, vp, vp, vp, vp, C.c_uint32]
         L.t41rx_process_device.argtypes = [vp, vp, vp, ip, ip, vp, vp, vp, vp, C.c_uint32, vp]
+        L.t41rx_process_device_q15.argtypes = [vp, vp, vp, ip, ip, vp, vp, vp, vp, C.c_uint32, vp]
         L.t41rx_synchronize.argtypes = [vp]
         L.t41rx_kernel_launches.argtypes = [vp]
         L.t41rx_kernel_launches.restype = C.c_int64
@@ -347,6 +350,13 @@ class Receiver:
         _check(lib().t41rx_process_device(self._h, iq_ptr, audio_ptr, n_blocks, row_every, spec_ptr, wf_ptr,
                                           psk_bits_ptr, psk_chars_ptr, flags, cuda_stream),
                "t41rx_process_device")
+
+    def process_device_q15(self, iq16_ptr, audio16_ptr, n_blocks, row_every=0, spec_ptr=None, wf_ptr=None,
+                           psk_bits_ptr=None, psk_chars_ptr=None, flags=0, cuda_stream=None):
+        """process_device on q15 blocks resident in HBM (int16 [S, T, 2048, 2] in, int16 [S, T, 2048] out)"""
+        _check(lib().t41rx_process_device_q15(self._h, iq16_ptr, audio16_ptr, n_blocks, row_every, spec_ptr, wf_ptr,
+                                              psk_bits_ptr, psk_chars_ptr, flags, cuda_stream),
+               "t41rx_process_device_q15")
 
     def synchronize(self):
         _check(lib().t41rx_synchronize(self._h), "t41rx_synchronize")

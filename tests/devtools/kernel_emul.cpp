@@ -58,6 +58,9 @@ int emul_set_params_each(Emul *e, int first, int count, const t41rx_params *p) {
 
 /* emulation-only flag: produce the spectrum rows with the rows-only schedule (T41RX_ROWS_SCHEDULE) */
 static const uint32_t kEmulSplitRows = 0x100u;
+/* emulation-only flag: the chain as the product's front | serial | back kernels (T41RX_FRONT_SCHEDULE over every CTA,
+   SerialReceiver for every receiver, T41RX_BACK_SCHEDULE over every CTA) instead of the fused schedule */
+static const uint32_t kEmulSplitExact = 0x200u;
 
 int emul_process(Emul *e, const float *iq, float *audio, int n_blocks, int row_every, int16_t *spec_rows,
                  uint16_t *wf_rows, int8_t *psk_bits, uint8_t *psk_chars, uint32_t flags) {
@@ -104,6 +107,54 @@ int emul_process(Emul *e, const float *iq, float *audio, int n_blocks, int row_e
   while ((reinterpret_cast<uintptr_t>(smem) & 15u) != 0) ++smem;
 
   const int grid = (h.n_streams + kG - 1) / kG;
+  const bool split_exact = (flags & kEmulSplitExact) != 0;
+  std::vector<float4> ser_in;
+  std::vector<float> ser_out;
+  if (split_exact) {
+    ser_in.assign((size_t)h.n_streams * n_blocks * kDec, float4{NAN, NAN, NAN, NAN});
+    ser_out.assign((size_t)h.n_streams * n_blocks * kDec, NAN);
+    a.ser_in = ser_in.data();
+    a.ser_out = ser_out.data();
+#define EMUL_PHASE(stmt) \
+  do {                   \
+    for (int tid = 0; tid < kNT; ++tid) { stmt; } \
+  } while (0)
+    auto cta_of = [&](int cta) {
+      Cta c;
+      c.a = a;
+      c.smem = smem;
+      c.s0 = cta * kG;
+      c.ng = (h.n_streams - c.s0 < kG) ? (h.n_streams - c.s0) : kG;
+      c.t = 0;
+      c.row = 0;
+      c.row_idx = 0;
+      c.rows_only = 0;
+      for (int i = 0; i < kSmemFloats; ++i) smem[i] = NAN;
+      return c;
+    };
+    for (int cta = 0; cta < grid; ++cta) {          /* t41rx_exact_front_kernel */
+      Cta c = cta_of(cta);
+      EMUL_PHASE(PhStateIn(c, tid));
+      for (int t = 0; t < n_blocks; ++t) {
+        c.t = t;
+        c.row = (row_every > 0) && (t % row_every == 0);
+        c.row_idx = c.row ? t / row_every : 0;
+        T41RX_FRONT_SCHEDULE(EMUL_PHASE)
+      }
+      EMUL_PHASE(PhFrontStateOut(c, tid));
+    }
+    for (int r = 0; r < h.n_streams; ++r) SerialReceiver(a, r, h.sin_table.data());   /* t41rx_exact_serial_kernel */
+    for (int cta = 0; cta < grid; ++cta) {          /* t41rx_exact_back_kernel */
+      Cta c = cta_of(cta);
+      EMUL_PHASE(PhBackStateIn(c, tid));
+      for (int t = 0; t < n_blocks; ++t) {
+        c.t = t;
+        T41RX_BACK_SCHEDULE(EMUL_PHASE)
+      }
+      EMUL_PHASE(PhBackStateOut(c, tid));
+    }
+#undef EMUL_PHASE
+  }
   for (int cta = 0; cta < grid; ++cta) {
     Cta c;
     c.a = a;
@@ -134,14 +185,16 @@ int emul_process(Emul *e, const float *iq, float *audio, int n_blocks, int row_e
       c.rows_only = 0;
       for (int i = 0; i < kSmemFloats; ++i) smem[i] = NAN;
     }
-    EMUL_PHASE(PhStateIn(c, tid));
-    for (int t = 0; t < n_blocks; ++t) {
-      c.t = t;
-      c.row = !split_rows && (row_every > 0) && (t % row_every == 0);
-      c.row_idx = c.row ? t / row_every : 0;
-      T41RX_BLOCK_SCHEDULE(EMUL_PHASE)
+    if (!split_exact) {
+      EMUL_PHASE(PhStateIn(c, tid));
+      for (int t = 0; t < n_blocks; ++t) {
+        c.t = t;
+        c.row = !split_rows && (row_every > 0) && (t % row_every == 0);
+        c.row_idx = c.row ? t / row_every : 0;
+        T41RX_BLOCK_SCHEDULE(EMUL_PHASE)
+      }
+      EMUL_PHASE(PhStateOut(c, tid));
     }
-    EMUL_PHASE(PhStateOut(c, tid));
     if (a.aspec || a.spec_frames) {
       /* t41rx_row_byproducts_kernel */
       c.row = 1;

@@ -39,7 +39,19 @@ def test_exact_mode_is_bit_identical_to_oracle(make):
     want = cases.run_case_on(case, lambda p: O.OracleStream(p))
     with _receiver(case.n_streams) as eng:
         got = rx_driver.run_case_batched(case, eng, flags=rx.FLAG_EXACT_NCO)
-        # one chain kernel per call, plus the audio-spectrum by-product kernel when the call has row-producing blocks
+        # the chain as front | serial | back kernels per call, plus the audio-spectrum by-product kernel when the call
+        # has row-producing blocks
+        assert eng.kernel_launches() == len(case.segments) * (4 if case.row_every > 0 else 3)
+    rx_driver.assert_identical(case, got, want)
+
+
+@pytest.mark.parametrize("make", cases.ALL_CASES, ids=lambda m: m.__name__)
+def test_exact_mode_fused_kernel_is_bit_identical_too(make):
+    """T41RX_FLAG_FUSED_EXACT: the same chain as ONE kernel (serial stages on one lane per receiver)."""
+    case = make()
+    want = cases.run_case_on(case, lambda p: O.OracleStream(p))
+    with _receiver(case.n_streams) as eng:
+        got = rx_driver.run_case_batched(case, eng, flags=rx.FLAG_EXACT_NCO | rx.FLAG_FUSED_EXACT)
         assert eng.kernel_launches() == len(case.segments) * (2 if case.row_every > 0 else 1)
     rx_driver.assert_identical(case, got, want)
 

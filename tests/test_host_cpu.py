@@ -144,6 +144,23 @@ def test_rows_only_schedule_emulated(make):
     rx_driver.assert_identical(case, got, want)
 
 
+EMUL_SPLIT_EXACT = 0x200  # tests/devtools/kernel_emul.cpp: the chain as the front | serial | back kernels
+
+
+@pytest.mark.parametrize("make", EMUL_CASES + [cases.c5_psk31, cases.c1_single_usb], ids=lambda m: m.__name__)
+def test_split_exact_kernels_emulated(make):
+    """The bit-exact chain as the product runs it by default (t41rx_exact_front_kernel, t41rx_exact_serial_kernel with
+    thread = receiver, t41rx_exact_back_kernel; hand-over through receiver-minor scratch) must equal the oracle bit for
+    bit on every output and every piece of state, like the fused schedule: every mode, AGC on / off, equaliser, LMS /
+    notch, CW filters, parameter changes between calls, silence and full scale."""
+    case = make()
+    want = cases.run_case_on(case, lambda p: O.OracleStream(p))
+    eng = rx_driver.EmulReceiver(case.n_streams)
+    got = rx_driver.run_case_batched(case, eng, flags=rx.FLAG_EXACT_NCO | EMUL_SPLIT_EXACT)
+    eng.close()
+    rx_driver.assert_identical(case, got, want)
+
+
 def test_smeter_helper_matches_oracle():
     """t41rx_smeter_dbm is host arithmetic (Display.cpp:959-981): no GPU needed."""
     lib = O.tier_b()
