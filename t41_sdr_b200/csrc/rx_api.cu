@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <functional>
 #include <map>
 #include <new>
 #include <string>
@@ -109,13 +110,135 @@ __global__ void __launch_bounds__(kNT, 8 / kG) t41rx_exact_front_kernel(const La
   PhFrontStateOut(c, tid);
 }
 
-constexpr int kSerialThreads = 32;     /* one warp per CTA: the kernel is a bundle of serial chains, spread over every SM */
+/* The serial stages as a pipeline of three warps over chunks of kSerU samples, LANE = RECEIVER (32 receivers per CTA):
+   warp 0 the AGC envelope state machine, warp 1 the gain from volts (its FP64 division and logarithm are off every
+   recurrence), warp 2 the demodulator (SAM PLL / AM detector) and the PSK31 tap.  Each stage is one long dependent
+   chain per receiver, so a warp issues an instruction every few clocks at best: three warps on three schedulers run
+   the chains side by side.  Hand-over through double-buffered shared memory with named barriers (producer arrives on
+   "full", consumer arrives on "empty").  The arithmetic is SerAgc / SerGain / SerDemod of rx_phases.cuh, the same
+   objects the host emulation steps sample by sample. */
+constexpr int kSerialThreads = 96;
+constexpr int kSerialLanes = 32;
+constexpr int kSerU = 8;
+__device__ __forceinline__ void NamedSync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void NamedArrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+
+#ifndef T41RX_SER_UNROLL
+#define T41RX_SER_UNROLL 4
+#endif
+#define T41RX_SER_PRAGMA_(x) _Pragma(#x)
+#define T41RX_SER_PRAGMA(x) T41RX_SER_PRAGMA_(x)
+#define T41RX_SER_LOOP T41RX_SER_PRAGMA(unroll T41RX_SER_UNROLL)
 __global__ void __launch_bounds__(kSerialThreads) t41rx_exact_serial_kernel(const LaunchArgs a) {
   __shared__ float sin_tab[513];
+  __shared__ float2 inbuf[2][kSerU][kSerialLanes];     /* each loading stage's own staging of its global inputs */
+  __shared__ float vbuf[2][kSerU][kSerialLanes];
+  __shared__ float2 dbuf[2][kSerU][kSerialLanes];
   for (int i = threadIdx.x; i < 513; i += kSerialThreads) sin_tab[i] = __ldg(a.sin_table + i);
   __syncthreads();
-  const int r = blockIdx.x * kSerialThreads + threadIdx.x;
-  if (r < a.n_streams) SerialReceiver(a, r, sin_tab);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * kSerialLanes + lane;
+  const bool live = r < a.n_streams;
+  const int sid = live ? (a.stream_ids ? __ldg(a.stream_ids + r) : a.stream_base + r) : 0;
+  const StreamCfg &cf = a.cfg[sid];
+  StreamState &st = a.st[sid];
+  const bool agc_on = live && UsesFilter(cf.mode) && cf.agc_mode != 0;
+  const size_t n = (size_t)a.n_streams;
+  const int n_chunks = a.n_blocks * (kDec / kSerU);
+  /* named barriers 1..8: full_v[b] = 1 + b, empty_v[b] = 3 + b, full_d[b] = 5 + b, empty_d[b] = 7 + b.
+     The per-sample loops stay rolled (T41RX_SER_UNROLL): with one warp per stage nothing hides an instruction-cache
+     miss, and the unrolled bodies of the three stages do not fit the cache together. */
+  const float2 *in2 = reinterpret_cast<const float2 *>(a.ser_in) + 2 * (size_t)(live ? r : 0);   /* + 2 n per sample */
+  if (warp == 0) {
+    SerAgc agc;
+    agc.Load(cf, st);
+    float2 nx[kSerU];
+#pragma unroll
+    for (int k = 0; k < kSerU; ++k) nx[k] = agc_on ? __ldg(in2 + 2 * n * k + 1) : float2{0.0f, 0.0f};
+    for (int c = 0; c < n_chunks; ++c) {
+      const int b = c & 1;
+#pragma unroll
+      for (int k = 0; k < kSerU; ++k) inbuf[0][k][lane] = nx[k];
+      if (agc_on && c + 1 < n_chunks) {
+#pragma unroll
+        for (int k = 0; k < kSerU; ++k) nx[k] = __ldg(in2 + 2 * n * ((size_t)(c + 1) * kSerU + k) + 1);
+      }
+      if (c >= 2) NamedSync(3 + b);
+      __syncwarp();
+      T41RX_SER_LOOP
+      for (int k = 0; k < kSerU; ++k) {
+        const float2 x = inbuf[0][k][lane];
+#ifdef T41RX_SER_NO_AGC
+        vbuf[b][k][lane] = x.y + 1.0f;
+#else
+        vbuf[b][k][lane] = agc_on ? agc.Step(x.x, x.y) : 0.0f;
+#endif
+      }
+      NamedArrive(1 + b);
+    }
+    if (agc_on) agc.Store(st);
+  } else if (warp == 1) {
+    SerGain gain;
+    gain.Load(cf);
+    float2 nx[kSerU];
+#pragma unroll
+    for (int k = 0; k < kSerU; ++k) nx[k] = live ? __ldg(in2 + 2 * n * k) : float2{0.0f, 0.0f};
+    for (int c = 0; c < n_chunks; ++c) {
+      const int b = c & 1;
+#pragma unroll
+      for (int k = 0; k < kSerU; ++k) inbuf[1][k][lane] = nx[k];
+      if (live && c + 1 < n_chunks) {
+#pragma unroll
+        for (int k = 0; k < kSerU; ++k) nx[k] = __ldg(in2 + 2 * n * ((size_t)(c + 1) * kSerU + k));
+      }
+      NamedSync(1 + b);
+      if (c >= 2) NamedSync(7 + b);
+      __syncwarp();
+      T41RX_SER_LOOP
+      for (int k = 0; k < kSerU; ++k) {
+        float2 z = inbuf[1][k][lane];
+        if (agc_on) {
+#ifdef T41RX_SER_NO_GAIN
+          const float m = vbuf[b][k][lane];
+#else
+          const float m = gain.Mult(vbuf[b][k][lane]);
+#endif
+          z.x = z.x * m;
+          z.y = z.y * m;
+        }
+        dbuf[b][k][lane] = z;
+      }
+      if (c + 2 < n_chunks) NamedArrive(3 + b);
+      NamedArrive(5 + b);
+    }
+  } else {
+    SerDemod dem;
+    dem.Load(a, cf, st, sin_tab);
+    float *dst = a.ser_out + (live ? r : 0);
+    float2 dem0 = float2{0.0f, 0.0f};
+    for (int c = 0; c < n_chunks; ++c) {
+      const int b = c & 1;
+      NamedSync(5 + b);
+      const int i0 = (c % (kDec / kSerU)) * kSerU;
+      if (i0 == 0) {
+        dem.BlockStart();
+        dem0 = dbuf[b][0][lane];
+      }
+      T41RX_SER_LOOP
+      for (int k = 0; k < kSerU; ++k) {
+        const float2 z = dbuf[b][k][lane];
+#ifdef T41RX_SER_NO_DEMOD
+        const float au = z.x;
+#else
+        const float au = dem.Step(z.x, z.y);
+#endif
+        if (live) dst[((size_t)c * kSerU + k) * n] = au;
+      }
+      if (c + 2 < n_chunks) NamedArrive(7 + b);
+      if (live && i0 == kDec - kSerU) SerPskTap(a, cf, st, sid, c / (kDec / kSerU), dem0);
+    }
+    if (live) dem.Store(st);
+  }
 }
 
 __global__ void __launch_bounds__(kNT, 8 / kG) t41rx_exact_back_kernel(const LaunchArgs a) {
@@ -247,7 +370,7 @@ static int Fail(int code, const char *fmt, const char *detail = "") {
 constexpr int kKernelEventRing = 32;
 constexpr int kProcessChunks = 16;  /* most chunks of the host-buffer entry point's copy / compute pipeline (cut over time) */
 constexpr int kReceiverChunks = 8;  /* chunks when a short call is cut over receivers */
-constexpr size_t kSerialScratchBytes = (size_t)768 << 20;   /* most hand-over scratch of the split bit-exact chain */
+constexpr size_t kSerialScratchBytes = (size_t)2048 << 20;  /* most hand-over scratch of the split bit-exact chain */
 
 struct t41rx_ctx {
   int device = 0;
@@ -255,6 +378,10 @@ struct t41rx_ctx {
   int n_sms = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_in = nullptr, copy_out = nullptr;   /* t41rx_process: copies overlap the kernels */
+  /* the serial kernel of the split bit-exact chain is a bundle of latency-bound chains (one warp trio per 32
+     receivers): in a mixed bank it runs on this stream beside the throughput kernel of the other receivers */
+  cudaStream_t aux = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev_in[kProcessChunks] = {}, ev_done[kProcessChunks] = {};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool ev_valid = false;
@@ -327,6 +454,7 @@ static int Quiesce(t41rx_ctx *ctx) {
   }
   CUDA_TRY(cudaStreamSynchronize(ctx->copy_in));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->aux));
   CUDA_TRY(cudaStreamSynchronize(ctx->copy_out));
   return 0;
 }
@@ -431,6 +559,9 @@ void t41rx_destroy(t41rx_ctx *ctx) {
     if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
     if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
   }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->aux) cudaStreamDestroy(ctx->aux);
   if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
   if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -464,6 +595,9 @@ int t41rx_create(t41rx_ctx **out, int n_streams, int device) {
   if (cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_ext, cudaEventDisableTiming) != cudaSuccess)
     return bail(Fail(T41RX_ECUDA, "t41rx_create: stream/event creation failed%s"));
@@ -661,14 +795,14 @@ struct Span {
 /* the bit-exact chain for the receivers of `p` (p.n_streams of them, p.stream_ids / p.stream_base) on stream st:
    front | serial | back kernels with the hand-over in HBM, cut over time so that the scratch stays bounded;
    T41RX_FLAG_FUSED_EXACT: the single fused kernel (one lane per receiver in the serial phases) instead */
-static int LaunchExact(t41rx_ctx *ctx, const LaunchArgs &p, cudaStream_t st) {
+static int LaunchExact(t41rx_ctx *ctx, const LaunchArgs &p, cudaStream_t st, const std::function<int()> &overlap) {
   const int n = p.n_streams;
   const int grid = (n + kG - 1) / kG;
   if (p.flags & T41RX_FLAG_FUSED_EXACT) {
     t41rx_fused_rx_kernel<<<grid, kNT, kSmemFloats * sizeof(float), st>>>(p);
     CUDA_TRY(cudaGetLastError());
     ctx->launches += 1;
-    return T41RX_OK;
+    return overlap();
   }
   const size_t per_block = (size_t)n * kDec * (sizeof(float4) + sizeof(float));
   int chunk = (int)std::min<size_t>((size_t)p.n_blocks, std::max<size_t>(1, kSerialScratchBytes / per_block));
@@ -689,8 +823,19 @@ static int LaunchExact(t41rx_ctx *ctx, const LaunchArgs &p, cudaStream_t st) {
     q.ser_out = (float *)ctx->d_ser_out;
     t41rx_exact_front_kernel<<<grid, kNT, kSmemFloats * sizeof(float), st>>>(q);
     CUDA_TRY(cudaGetLastError());
-    t41rx_exact_serial_kernel<<<(n + kSerialThreads - 1) / kSerialThreads, kSerialThreads, 0, st>>>(q);
-    CUDA_TRY(cudaGetLastError());
+    if (c0 == 0) {
+      /* first chunk: the serial kernel on the side stream, the other receivers' kernels (overlap) on st beside it */
+      CUDA_TRY(cudaEventRecord(ctx->ev_fork, st));
+      CUDA_TRY(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
+      t41rx_exact_serial_kernel<<<(n + kSerialLanes - 1) / kSerialLanes, kSerialThreads, 0, ctx->aux>>>(q);
+      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaEventRecord(ctx->ev_join, ctx->aux));
+      if ((rc = overlap())) return rc;
+      CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    } else {
+      t41rx_exact_serial_kernel<<<(n + kSerialLanes - 1) / kSerialLanes, kSerialThreads, 0, st>>>(q);
+      CUDA_TRY(cudaGetLastError());
+    }
     t41rx_exact_back_kernel<<<grid, kNT, kSmemFloats * sizeof(float), st>>>(q);
     CUDA_TRY(cudaGetLastError());
     ctx->launches += 3;
@@ -762,7 +907,7 @@ static int LaunchRange(t41rx_ctx *ctx, const void *iq_any, void *audio_any, bool
      phase-structured kernel; SAM receivers always take the phase-structured kernel (see t41rx_ctx) */
   const bool all_phased = (flags & (T41RX_FLAG_EXACT_NCO | T41RX_FLAG_PHASED_KERNEL)) != 0;
   if (all_phased) {
-    const int rc = LaunchExact(ctx, a, st);
+    const int rc = LaunchExact(ctx, a, st, []() { return (int)T41RX_OK; });
     if (rc) return rc;
     return audio_spectrum();
   }
@@ -776,14 +921,9 @@ static int LaunchRange(t41rx_ctx *ctx, const void *iq_any, void *audio_any, bool
   const int v = ((flags & T41RX_FLAG_FAST_LMS) ? 1 : 0) | ((flags & T41RX_FLAG_FAST_SAM) ? 2 : 0);
   slice(ctx->h_phased_ids[v], &p_off, &p_len);
   slice(ctx->h_fast_ids[v], &f_off, &f_len);
-  if (p_len > 0) {
-    LaunchArgs p = a;
-    p.n_streams = p_len;
-    p.stream_ids = ctx->d_phased_ids[v] + p_off;
-    const int rc = LaunchExact(ctx, p, st);
-    if (rc) return rc;
-  }
-  if (f_len > 0) {
+  /* the throughput kernel's receivers (rows kernel first: it reads the launch-start state) */
+  auto fast_kernels = [&]() -> int {
+    if (f_len <= 0) return T41RX_OK;
     LaunchArgs f = a;
     f.n_streams = f_len;
     f.stream_ids = (p_len > 0) ? ctx->d_fast_ids[v] + f_off : nullptr;     /* nothing for the other kernel in range: contiguous */
@@ -799,6 +939,18 @@ static int LaunchRange(t41rx_ctx *ctx, const void *iq_any, void *audio_any, bool
     CUDA_TRY(cudaEventRecord(kev[1], st));
     ctx->kev_count += 1;
     ctx->launches += 1;
+    return T41RX_OK;
+  };
+  if (p_len > 0) {
+    /* the bit-exact chain's receivers; the throughput kernel of the others runs beside its serial kernel */
+    LaunchArgs p = a;
+    p.n_streams = p_len;
+    p.stream_ids = ctx->d_phased_ids[v] + p_off;
+    const int rc = LaunchExact(ctx, p, st, fast_kernels);
+    if (rc) return rc;
+  } else {
+    const int rc = fast_kernels();
+    if (rc) return rc;
   }
   return audio_spectrum();
 }

@@ -1597,234 +1597,245 @@ T41RX_DEV void PhCodecGain(Cta &c, int tid) {
   }
 }
 
-/* the serial kernel's work for receiver number r of the launch: AGC envelope (DSP_Fn.cpp:504-631), gain
-   (DSP_Fn.cpp:628), demodulator (Process.cpp:615-761, Demod.cpp:40-139) and the PSK31 tap, for every block.
-   sin_tab: arm_sin_f32's table (shared memory on the device). */
+/* ---- the serial stages as three small state machines (shared by the host emulation, which runs them one after the
+   other per sample, and the device kernel, which runs them on three warps as a pipeline over chunks of samples) ---- */
+/* AGC envelope (DSP_Fn.cpp:504-626; PhAgcSerial's generic step) */
+struct SerAgc {
+  float k_fbm, k_omfbm, k_hbm, k_omhbm, k_attack, k_decay, k_fdecay, k_hdecay, k_pop, k_hlevel, k_minv;
+  int k_hload, k_henable;
+  float fast, hang, v, save, rm;
+  int hc, state, dtype, action;
+  T41RX_DEV void Load(const StreamCfg &cf, const StreamState &st) {
+    k_fbm = cf.agc.fast_backmult; k_omfbm = cf.agc.onemfast_backmult;
+    k_hbm = cf.agc.hang_backmult; k_omhbm = cf.agc.onemhang_backmult;
+    k_attack = cf.agc.attack_mult; k_decay = cf.agc.decay_mult; k_fdecay = cf.agc.fast_decay_mult;
+    k_hdecay = cf.agc.hang_decay_mult; k_pop = cf.agc.pop_ratio; k_hlevel = cf.agc.hang_level;
+    k_minv = cf.agc.min_volts;
+    k_hload = cf.agc.hang_counter_load; k_henable = cf.agc.hang_enable;
+    fast = st.agc_fast_back; hang = st.agc_hang_back; v = st.agc_volts; save = st.agc_save_volts;
+    rm = st.agc_ring_max;
+    hc = st.agc_hang_counter; state = st.agc_state; dtype = st.agc_decay_type; action = st.agc_action;
+  }
+  T41RX_DEV void Store(StreamState &st) const {
+    st.agc_fast_back = fast; st.agc_hang_back = hang; st.agc_volts = v; st.agc_save_volts = save;
+    st.agc_ring_max = rm;
+    st.agc_hang_counter = hc; st.agc_state = state; st.agc_decay_type = dtype; st.agc_action = action;
+  }
+  /* one sample: delayed |z| and the window maximum in, volts out */
+  T41RX_DEV float Step(float abs_out, float r) {
+    fast = k_fbm * abs_out + k_omfbm * fast;
+    hang = k_hbm * abs_out + k_omhbm * hang;
+    rm = r;
+    if (hc > 0) --hc;
+    const float d = rm - v;
+    if (rm >= v) {                       /* every state: attack; 2,3,4 remember the level they left */
+      if (state >= 2) save = v;
+      state = 0;
+      v += d * k_attack;
+    } else if (state == 3) {
+      const float step = d * k_decay;
+      v = (float)((double)v + (double)step * .05);   /* double product and sum */
+    } else if (state == 0) {
+      if (v > k_pop * fast) {
+        state = 1;
+        v += d * k_fdecay;
+      } else if (k_henable && (hang > k_hlevel)) {
+        state = 2;
+        hc = k_hload;
+        dtype = 1;
+      } else {
+        state = 3;
+        v += d * k_decay;
+        dtype = 0;
+      }
+    } else if (state == 1) {
+      if (v > save) {
+        v += d * k_fdecay;
+      } else if (hc > 0) {
+        state = 2;
+      } else if (dtype == 0) {
+        state = 3;
+        v += d * k_decay;
+      } else {
+        state = 4;
+        v += d * k_hdecay;
+      }
+    } else if (state == 2) {
+      if (hc == 0) {
+        state = 4;
+        v += d * k_hdecay;
+      }
+    } else {
+      v += d * k_hdecay;
+    }
+    action = (v < k_minv) ? 0 : 1;
+    v = (v < k_minv) ? k_minv : v;
+    return v;
+  }
+};
+
+/* gain from volts (DSP_Fn.cpp:628; PhAgcPost) */
+struct SerGain {
+  float k_inv_in, k_target, k_slope;
+  T41RX_DEV void Load(const StreamCfg &cf) {
+    k_inv_in = cf.agc.inv_max_input; k_target = cf.agc.out_target; k_slope = cf.agc.slope_constant;
+  }
+  T41RX_DEV float Mult(float v) const {
+    const double lg = (double)Log10Fast(k_inv_in * v);
+    const double clipped = (0.0 < lg) ? 0.0 : lg;
+    return (float)(((double)k_target - (double)k_slope * clipped) / (double)v);
+  }
+};
+
+/* demodulators with a serial chain (Process.cpp:697-707 AM, Demod.cpp:40-139 SAM) and the pass-through modes */
+struct SerDemod {
+  int mode;
+  /* AM */
+  float wold, x1, x2, y1, y2, b0, b1, b2, a1, a2;
+  /* SAM */
+  float omega_min, omega_max, g1, g2, phz, fil, om2, sn, cs;
+  const float *tab;
+  T41RX_DEV void Load(const LaunchArgs &a, const StreamCfg &cf, const StreamState &st, const float *sin_tab) {
+    mode = cf.mode;
+    wold = st.am_wold;
+    x1 = st.am_lp_state[0]; x2 = st.am_lp_state[1]; y1 = st.am_lp_state[2]; y2 = st.am_lp_state[3];
+    b0 = cf.am_lp[0]; b1 = cf.am_lp[1]; b2 = cf.am_lp[2]; a1 = cf.am_lp[3]; a2 = cf.am_lp[4];
+    omega_min = LdgRO(a.sam_consts + 0); omega_max = LdgRO(a.sam_consts + 1);
+    g1 = LdgRO(a.sam_consts + 2); g2 = LdgRO(a.sam_consts + 3);
+    phz = st.sam_phzerror; fil = st.sam_fil_out; om2 = st.sam_omega2;
+    sn = 0.0f; cs = 0.0f;
+    tab = sin_tab;
+  }
+  T41RX_DEV void Store(StreamState &st) const {
+    if (mode == kModeAm) {
+      st.am_wold = wold;
+      st.am_lp_state[0] = x1; st.am_lp_state[1] = x2; st.am_lp_state[2] = y1; st.am_lp_state[3] = y2;
+    } else if (mode == kModeSam) {
+      st.sam_phzerror = phz;
+      st.sam_fil_out = fil;
+      st.sam_omega2 = om2;
+    }
+  }
+  /* at the start of every block: the reference's loop takes the sine / cosine of the carried phase first */
+  T41RX_DEV void BlockStart() {
+    if (mode == kModeSam) {
+      sn = TableTurns(tab, phz * 0.159154943092f);
+      cs = TableTurns(tab, phz * 0.159154943092f + 0.25f);
+    }
+  }
+  /* one gained sample in, one audio sample out */
+  T41RX_DEV float Step(float zx, float zy) {
+    if (mode == kModeSam) {
+      const float tpi = 6.283185307179586476925286766559f;
+      /* the phase of sample i + 1 is phz + the loop filter's output of sample i - 1: its sine / cosine are formed
+         beside sample i's arctangent (same operations on the same values as the reference's loop) */
+      float phz_n = phz + fil;
+      phz_n = (phz_n >= tpi) ? phz_n - tpi : phz_n;
+      phz_n = (phz_n < 0.0f) ? phz_n + tpi : phz_n;
+      const float sn_n = TableTurns(tab, phz_n * 0.159154943092f);
+      const float cs_n = TableTurns(tab, phz_n * 0.159154943092f + 0.25f);
+      const float ai = cs * zx, bi = sn * zx, aq = cs * zy, bq = sn * zy;
+      const float corr0 = +ai + bq;
+      const float corr1 = -bi + aq;
+      float audio = (ai - bi) + (aq + bq);
+      audio = (audio + 0.0f) - 0.0f;             /* the fade leveller's identity (see PhDemodSerial) */
+      const float det = Atan2Approx(corr1, corr0);
+      om2 = om2 + g2 * det;
+      if (om2 < omega_min) om2 = omega_min;
+      else if (om2 > omega_max) om2 = omega_max;
+      fil = g1 * det + om2;
+      phz = phz_n;
+      sn = sn_n;
+      cs = cs_n;
+      return audio;
+    }
+    if (mode == kModeAm) {
+      const float m = AlphaBetaMag(zx, zy);
+      const float w = m + wold * 0.99f;
+      const float x = w - wold;
+      wold = w;
+      float acc = b0 * x;
+      acc = acc + b1 * x1;
+      acc = acc + b2 * x2;
+      acc = acc + a1 * y1;
+      acc = acc + a2 * y2;
+      x2 = x1; x1 = x;
+      y2 = y1; y1 = acc;
+      return acc;
+    }
+    return zx;                                   /* USB / LSB / NFM: real part; raw PSK31 mode: the sample itself */
+  }
+};
+
+/* PSK31 tap (psk31.cpp:235-310) on the first gained sample of a block; writes the block's bit / character outputs */
+T41RX_DEV void SerPskTap(const LaunchArgs &a, const StreamCfg &cf, StreamState &st, int sid, int t, float2 dem0) {
+  int8_t bit_out = -1;
+  uint8_t char_out = 0;
+  if (cf.psk31_enable && cf.mode != kModeNfm && cf.mode != kModePsk31) {
+    if (st.psk_block_count % 3u == 0u) {
+      const double pi_d = 3.1415926535897932384626433832795;
+      const float phase = Atan2Approx(dem0.y, dem0.x);
+      float dphase = phase - st.psk_last_phase;
+      while ((double)dphase < -pi_d) dphase = (float)((double)dphase + 2 * pi_d);
+      while ((double)dphase >= pi_d) dphase = (float)((double)dphase - 2 * pi_d);
+      const uint8_t bit = (((double)dphase > (pi_d / 2)) || ((double)dphase < (-pi_d / 2))) ? 0 : 1;
+      st.psk_last_phase = phase;
+      bit_out = (int8_t)bit;
+      unsigned long long shr = (st.psk_shr << 1) | (unsigned long long)bit;
+      if ((shr & 0xFFFull) != 0) {
+        for (int i = 0; i < 128; ++i) {
+          const uint32_t e = LdgRO(a.varicode + i);
+          const unsigned long long want = ((unsigned long long)(e & 0xFFFFu)) << 2;
+          const unsigned nbits = (((e >> 16) & 0xFFu) + 4u) & 63u;
+          const unsigned long long keep = (nbits == 0) ? 0ull : (~0ull >> (64u - nbits));
+          if (want == (shr & keep)) {
+            shr = 0;
+            char_out = (uint8_t)(e >> 24);
+            break;
+          }
+        }
+      }
+      st.psk_shr = shr;
+    }
+    st.psk_block_count++;
+  }
+  const size_t o = (size_t)sid * a.t_stride + t;
+  if (a.psk_bits) a.psk_bits[o] = bit_out;
+  if (a.psk_chars) a.psk_chars[o] = char_out;
+}
+
+/* the serial kernel's work for receiver number r of the launch, one stage after the other per sample (the host
+   emulation's form; the device kernel runs the same three state machines as a warp pipeline, rx_api.cu) */
 T41RX_DEV void SerialReceiver(const LaunchArgs &a, int r, const float *sin_tab) {
   const int sid = a.stream_ids ? LdgRO(a.stream_ids + r) : a.stream_base + r;
   const StreamCfg &cf = a.cfg[sid];
   StreamState &st = a.st[sid];
   const size_t n = (size_t)a.n_streams;
-  const int mode = cf.mode;
-  const bool filt = UsesFilter(mode);
-  const bool agc_on = filt && cf.agc_mode != 0;
-  /* AGC constants and state */
-  const float k_fbm = cf.agc.fast_backmult, k_omfbm = cf.agc.onemfast_backmult;
-  const float k_hbm = cf.agc.hang_backmult, k_omhbm = cf.agc.onemhang_backmult;
-  const float k_attack = cf.agc.attack_mult, k_decay = cf.agc.decay_mult, k_fdecay = cf.agc.fast_decay_mult;
-  const float k_hdecay = cf.agc.hang_decay_mult, k_pop = cf.agc.pop_ratio, k_hlevel = cf.agc.hang_level;
-  const float k_minv = cf.agc.min_volts;
-  const float k_inv_in = cf.agc.inv_max_input, k_target = cf.agc.out_target, k_slope = cf.agc.slope_constant;
-  const int k_hload = cf.agc.hang_counter_load, k_henable = cf.agc.hang_enable;
-  float fast = st.agc_fast_back, hang = st.agc_hang_back, v = st.agc_volts, save = st.agc_save_volts;
-  int hc = st.agc_hang_counter, state = st.agc_state, dtype = st.agc_decay_type, action = st.agc_action;
-  float rm = st.agc_ring_max;
-  /* AM detector */
-  float wold = st.am_wold;
-  float x1 = st.am_lp_state[0], x2 = st.am_lp_state[1], y1 = st.am_lp_state[2], y2 = st.am_lp_state[3];
-  const float b0 = cf.am_lp[0], b1 = cf.am_lp[1], b2 = cf.am_lp[2], a1 = cf.am_lp[3], a2 = cf.am_lp[4];
-  /* SAM PLL */
-  const float tpi = 6.283185307179586476925286766559f;
-  const float omega_min = LdgRO(a.sam_consts + 0), omega_max = LdgRO(a.sam_consts + 1);
-  const float g1 = LdgRO(a.sam_consts + 2), g2 = LdgRO(a.sam_consts + 3);
-  float phz = st.sam_phzerror, fil = st.sam_fil_out, om2 = st.sam_omega2;
-  constexpr int kU = 8;                            /* samples per step of the software pipeline */
-  const float4 *src = a.ser_in + r;
-  float *dst = a.ser_out + r;
-  float4 nx[kU];
-#pragma unroll
-  for (int k = 0; k < kU; ++k) nx[k] = LdgRO(src + (size_t)k * n);
+  const bool agc_on = UsesFilter(cf.mode) && cf.agc_mode != 0;
+  SerAgc agc;
+  SerGain gain;
+  SerDemod dem;
+  agc.Load(cf, st);
+  gain.Load(cf);
+  dem.Load(a, cf, st, sin_tab);
   for (int t = 0; t < a.n_blocks; ++t) {
     float2 dem0 = float2{0.0f, 0.0f};
-    /* the phase of sample i + 1 is phz + the loop filter's output of sample i - 1: its sine / cosine are formed
-       beside sample i's arctangent (same operations on the same values as the reference's loop) */
-    float sn = 0.0f, cs = 0.0f;
-    if (mode == kModeSam) {
-      sn = TableTurns(sin_tab, phz * 0.159154943092f);
-      cs = TableTurns(sin_tab, phz * 0.159154943092f + 0.25f);
-    }
-    for (int i0 = 0; i0 < kDec; i0 += kU) {
-      float4 cur[kU];
-#pragma unroll
-      for (int k = 0; k < kU; ++k) cur[k] = nx[k];
-      {                                            /* next step's inputs: in flight while this one is computed */
-        const size_t e = (size_t)t * kDec + i0 + kU;
-        if (e < (size_t)a.n_blocks * kDec) {
-#pragma unroll
-          for (int k = 0; k < kU; ++k) nx[k] = LdgRO(src + (e + k) * n);
-        }
-      }
-      float vv[kU];
+    dem.BlockStart();
+    for (int i = 0; i < kDec; ++i) {
+      const size_t e = ((size_t)t * kDec + i) * n + r;
+      float4 x = LdgRO(a.ser_in + e);
       if (agc_on) {
-        /* the envelope state machine, sample by sample (PhAgcSerial's generic step) */
-#pragma unroll
-        for (int k = 0; k < kU; ++k) {
-          const float abs_out = cur[k].z;
-          fast = k_fbm * abs_out + k_omfbm * fast;
-          hang = k_hbm * abs_out + k_omhbm * hang;
-          rm = cur[k].w;
-          if (hc > 0) --hc;
-          const float d = rm - v;
-          if (rm >= v) {
-            if (state >= 2) save = v;
-            state = 0;
-            v += d * k_attack;
-          } else if (state == 3) {
-            const float step = d * k_decay;
-            v = (float)((double)v + (double)step * .05);
-          } else if (state == 0) {
-            if (v > k_pop * fast) {
-              state = 1;
-              v += d * k_fdecay;
-            } else if (k_henable && (hang > k_hlevel)) {
-              state = 2;
-              hc = k_hload;
-              dtype = 1;
-            } else {
-              state = 3;
-              v += d * k_decay;
-              dtype = 0;
-            }
-          } else if (state == 1) {
-            if (v > save) {
-              v += d * k_fdecay;
-            } else if (hc > 0) {
-              state = 2;
-            } else if (dtype == 0) {
-              state = 3;
-              v += d * k_decay;
-            } else {
-              state = 4;
-              v += d * k_hdecay;
-            }
-          } else if (state == 2) {
-            if (hc == 0) {
-              state = 4;
-              v += d * k_hdecay;
-            }
-          } else {
-            v += d * k_hdecay;
-          }
-          action = (v < k_minv) ? 0 : 1;
-          v = (v < k_minv) ? k_minv : v;
-          vv[k] = v;
-        }
-        /* gain from volts (PhAgcPost), independent from sample to sample */
-#pragma unroll
-        for (int k = 0; k < kU; ++k) {
-          const double lg = (double)Log10Fast(k_inv_in * vv[k]);
-          const double clipped = (0.0 < lg) ? 0.0 : lg;
-          const float mult = (float)(((double)k_target - (double)k_slope * clipped) / (double)vv[k]);
-          cur[k].x = cur[k].x * mult;
-          cur[k].y = cur[k].y * mult;
-        }
+        const float m = gain.Mult(agc.Step(x.z, x.w));
+        x.x = x.x * m;
+        x.y = x.y * m;
       }
-      if (i0 == 0) dem0 = float2{cur[0].x, cur[0].y};
-      float au[kU];
-      if (mode == kModeSam) {
-#pragma unroll
-        for (int k = 0; k < kU; ++k) {
-          const float zx = cur[k].x, zy = cur[k].y;
-          float phz_n = phz + fil;
-          phz_n = (phz_n >= tpi) ? phz_n - tpi : phz_n;
-          phz_n = (phz_n < 0.0f) ? phz_n + tpi : phz_n;
-          const float sn_n = TableTurns(sin_tab, phz_n * 0.159154943092f);
-          const float cs_n = TableTurns(sin_tab, phz_n * 0.159154943092f + 0.25f);
-          const float ai = cs * zx, bi = sn * zx, aq = cs * zy, bq = sn * zy;
-          const float corr0 = +ai + bq;
-          const float corr1 = -bi + aq;
-          float audio = (ai - bi) + (aq + bq);
-          audio = (audio + 0.0f) - 0.0f;           /* the fade leveller's identity (see PhDemodSerial) */
-          au[k] = audio;
-          const float det = Atan2Approx(corr1, corr0);
-          om2 = om2 + g2 * det;
-          if (om2 < omega_min) om2 = omega_min;
-          else if (om2 > omega_max) om2 = omega_max;
-          fil = g1 * det + om2;
-          phz = phz_n;
-          sn = sn_n;
-          cs = cs_n;
-        }
-      } else if (mode == kModeAm) {
-#pragma unroll
-        for (int k = 0; k < kU; ++k) {
-          const float m = AlphaBetaMag(cur[k].x, cur[k].y);
-          const float w = m + wold * 0.99f;
-          const float x = w - wold;
-          wold = w;
-          float acc = b0 * x;
-          acc = acc + b1 * x1;
-          acc = acc + b2 * x2;
-          acc = acc + a1 * y1;
-          acc = acc + a2 * y2;
-          x2 = x1; x1 = x;
-          y2 = y1; y1 = acc;
-          au[k] = acc;
-        }
-      } else {
-#pragma unroll
-        for (int k = 0; k < kU; ++k) au[k] = cur[k].x;   /* USB / LSB / NFM: real part; raw PSK31 mode: the sample itself */
-      }
-      {
-        const size_t e = (size_t)t * kDec + i0;
-#pragma unroll
-        for (int k = 0; k < kU; ++k) dst[(e + k) * n] = au[k];
-      }
+      if (i == 0) dem0 = float2{x.x, x.y};
+      a.ser_out[e] = dem.Step(x.x, x.y);
     }
-    /* PSK31 tap (psk31.cpp:235-310): first filtered sample of every third block */
-    int8_t bit_out = -1;
-    uint8_t char_out = 0;
-    if (cf.psk31_enable && mode != kModeNfm && mode != kModePsk31) {
-      if (st.psk_block_count % 3u == 0u) {
-        const double pi_d = 3.1415926535897932384626433832795;
-        const float phase = Atan2Approx(dem0.y, dem0.x);
-        float dphase = phase - st.psk_last_phase;
-        while ((double)dphase < -pi_d) dphase = (float)((double)dphase + 2 * pi_d);
-        while ((double)dphase >= pi_d) dphase = (float)((double)dphase - 2 * pi_d);
-        const uint8_t bit = (((double)dphase > (pi_d / 2)) || ((double)dphase < (-pi_d / 2))) ? 0 : 1;
-        st.psk_last_phase = phase;
-        bit_out = (int8_t)bit;
-        unsigned long long shr = (st.psk_shr << 1) | (unsigned long long)bit;
-        if ((shr & 0xFFFull) != 0) {
-          for (int i = 0; i < 128; ++i) {
-            const uint32_t e = LdgRO(a.varicode + i);
-            const unsigned long long want = ((unsigned long long)(e & 0xFFFFu)) << 2;
-            const unsigned nbits = (((e >> 16) & 0xFFu) + 4u) & 63u;
-            const unsigned long long keep = (nbits == 0) ? 0ull : (~0ull >> (64u - nbits));
-            if (want == (shr & keep)) {
-              shr = 0;
-              char_out = (uint8_t)(e >> 24);
-              break;
-            }
-          }
-        }
-        st.psk_shr = shr;
-      }
-      st.psk_block_count++;
-    }
-    const size_t o = (size_t)sid * a.t_stride + t;
-    if (a.psk_bits) a.psk_bits[o] = bit_out;
-    if (a.psk_chars) a.psk_chars[o] = char_out;
+    SerPskTap(a, cf, st, sid, t, dem0);
   }
-  if (agc_on) {
-    st.agc_fast_back = fast;
-    st.agc_hang_back = hang;
-    st.agc_volts = v;
-    st.agc_save_volts = save;
-    st.agc_ring_max = rm;
-    st.agc_hang_counter = hc;
-    st.agc_state = state;
-    st.agc_decay_type = dtype;
-    st.agc_action = action;
-  }
-  if (mode == kModeAm) {
-    st.am_wold = wold;
-    st.am_lp_state[0] = x1; st.am_lp_state[1] = x2; st.am_lp_state[2] = y1; st.am_lp_state[3] = y2;
-  } else if (mode == kModeSam) {
-    st.sam_phzerror = phz;
-    st.sam_fil_out = fil;
-    st.sam_omega2 = om2;
-  }
+  if (agc_on) agc.Store(st);
+  dem.Store(st);
 }
 
 /* back kernel: the demodulated block from the serial kernel into the audio buffer (+ PhInterp1's history restore) */
