@@ -153,8 +153,8 @@ void t41rx_default_params(t41rx_params *p);
 /* FLoCut/FHiCut presets a mode change applies (SetupMode, Filter.cpp:341-385). */
 void t41rx_mode_default_cuts(int32_t mode, int32_t *f_lo_cut, int32_t *f_hi_cut);
 
-/* A context owns n_streams receivers on ONE CUDA device (one process per GPU shards
- * contiguous stream ranges across contexts).  Every receiver starts in the state
+/* A context owns n_streams receivers on ONE CUDA device (t41rx_create_multi below shards a bank over several
+ * devices in one process; one process per GPU with a context each works too).  Every receiver starts in the state
  * InitializeDataArrays() + SoftReset() leave the firmware in (T41_SDR.ino:473-667,753-795). */
 int t41rx_create(t41rx_ctx **out, int n_streams, int device);
 void t41rx_destroy(t41rx_ctx *ctx);
@@ -206,6 +206,38 @@ int t41rx_process_device_q15(t41rx_ctx *ctx, const int16_t *iq_q15, int16_t *aud
                              int16_t *spec_rows, uint16_t *wf_rows, int8_t *psk_bits, uint8_t *psk_chars,
                              uint32_t flags, void *cuda_stream);
 int t41rx_synchronize(t41rx_ctx *ctx);
+
+/* ---- a bank over several CUDA devices ----
+ * n_streams receivers sharded over n_dev devices: device_ids[g] owns the contiguous range [g n / N, (g + 1) n / N) in a
+ * single-device context of its own; every call fans out to one host thread per device.  No inter-GPU traffic on the
+ * hot path; the optional gather of rows is the only collective.  A device id may be listed more than once (several
+ * shards on one GPU).  Failures: negative T41RX_E* code, text in t41rx_multi_last_error() (it names the shard). */
+typedef struct t41rx_multi t41rx_multi;
+int t41rx_create_multi(t41rx_multi **out, int n_streams, const int *device_ids, int n_dev);
+void t41rx_destroy_multi(t41rx_multi *m);
+int t41rx_multi_num_devices(const t41rx_multi *m);
+int t41rx_multi_num_streams(const t41rx_multi *m);
+/* shard g: its device, receiver range and single-device context (for the per-context calls above); any may be NULL */
+int t41rx_multi_shard(const t41rx_multi *m, int shard, int *device, int *first, int *count, t41rx_ctx **ctx);
+/* receiver indices are those of the whole bank */
+int t41rx_multi_set_params(t41rx_multi *m, int first, int count, const t41rx_params *p);
+int t41rx_multi_set_params_each(t41rx_multi *m, int first, int count, const t41rx_params *p);
+int t41rx_multi_get_debug(t41rx_multi *m, int stream, t41rx_debug *d);
+/* t41rx_process / t41rx_process_q15 on HOST buffers of the whole bank: every device works on its slice concurrently */
+int t41rx_multi_process(t41rx_multi *m, const float *iq, float *audio, int n_blocks, int row_every, int16_t *spec_rows,
+                        uint16_t *wf_rows, int8_t *psk_bits, uint8_t *psk_chars, uint32_t flags);
+int t41rx_multi_process_q15(t41rx_multi *m, const int16_t *iq_q15, int16_t *audio_q15, int n_blocks, int row_every,
+                            int16_t *spec_rows, uint16_t *wf_rows, int8_t *psk_bits, uint8_t *psk_chars, uint32_t flags);
+/* device-resident: arrays of n_dev DEVICE pointers, entry g on shard g's device with that shard's receivers
+ * ([count][n_blocks][...]); asynchronous on every context's own stream; spec_rows / wf_rows may be NULL */
+int t41rx_multi_process_device(t41rx_multi *m, const float *const *iq, float *const *audio, int n_blocks, int row_every,
+                               int16_t *const *spec_rows, uint16_t *const *wf_rows, uint32_t flags);
+int t41rx_multi_synchronize(t41rx_multi *m);
+/* optional collective: the shards' row buffers (rows[g] on shard g's device, bytes_per_receiver bytes per receiver, e.g.
+ * n_rows * 512 * 2) gathered into dst on device_ids[0] in receiver order; NCCL send / recv over NVLink / NVSwitch when
+ * libnccl can be loaded and the devices are distinct, else peer copies; blocking; *used_nccl (may be NULL) reports it */
+int t41rx_multi_gather_rows(t41rx_multi *m, const void *const *rows, size_t bytes_per_receiver, void *dst, int *used_nccl);
+const char *t41rx_multi_last_error(void);
 
 /* Audio-spectrum + S-meter by-product of the row-producing blocks (Process.cpp:550-570; NFM: 791-805):
  *   audio_ypixel      int32 [n_streams][n_rows][270]  audioYPixel[k], k < AUDIO_SPEC_BOX_W - 2 (Process.cpp:34,555)

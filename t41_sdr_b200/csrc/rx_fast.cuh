@@ -175,15 +175,22 @@ __device__ __forceinline__ void MbarInit(uint64_t *bar, unsigned count) {
 __device__ __forceinline__ void MbarArrive(uint64_t *bar) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
+/* upper bound of the time a waiting thread may stay suspended before try_wait returns false and the loop retries: the
+   hardware wakes the thread when the phase completes, so a long hint costs nothing, while the default (short) one makes
+   the waiting warp spin through issue slots its scheduler's other warps could use */
+#ifndef T41RX_MBAR_HINT
+#define T41RX_MBAR_HINT 0x989680u
+#endif
+constexpr unsigned kMbarSuspendHint = T41RX_MBAR_HINT;
 __device__ __forceinline__ void MbarWait(uint64_t *bar, unsigned parity) {
   const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"(addr), "r"(parity) : "memory");
+      "DONE_%=:\n\t}" ::"r"(addr), "r"(parity), "r"(kMbarSuspendHint) : "memory");
 }
 
 /* everything a receiver warp keeps in registers across blocks (uniform over the lanes unless noted) */

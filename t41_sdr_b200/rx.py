@@ -84,7 +84,11 @@ EXPORTS = (
     "t41rx_process_device", "t41rx_process_device_q15", "t41rx_synchronize", "t41rx_kernel_launches", "t41rx_last_kernel_ms",
     "t41rx_stream_kernel_times", "t41rx_bind_audio_spectrum", "t41rx_bind_control_frames", "t41rx_smeter_dbm", "t41rx_smeter_bar",
     "t41rx_load_wav", "t41rx_read_wave", "t41rx_wav_sample_rate", "t41rx_wav_close",
-    "t41rx_last_error", "t41rx_version")
+    "t41rx_last_error", "t41rx_version",
+    "t41rx_create_multi", "t41rx_destroy_multi", "t41rx_multi_num_devices", "t41rx_multi_num_streams", "t41rx_multi_shard",
+    "t41rx_multi_set_params", "t41rx_multi_set_params_each", "t41rx_multi_get_debug", "t41rx_multi_process",
+    "t41rx_multi_process_q15", "t41rx_multi_process_device", "t41rx_multi_synchronize", "t41rx_multi_gather_rows",
+    "t41rx_multi_last_error")
 
 
 def build_library():
@@ -136,6 +140,21 @@ def lib():
         L.t41rx_wav_close.restype = None
         L.t41rx_last_error.restype = C.c_char_p
         L.t41rx_version.restype = C.c_char_p
+        L.t41rx_create_multi.argtypes = [C.POINTER(vp), ip, C.POINTER(ip), ip]
+        L.t41rx_destroy_multi.argtypes = [vp]
+        L.t41rx_destroy_multi.restype = None
+        L.t41rx_multi_num_devices.argtypes = [vp]
+        L.t41rx_multi_num_streams.argtypes = [vp]
+        L.t41rx_multi_shard.argtypes = [vp, ip, C.POINTER(ip), C.POINTER(ip), C.POINTER(ip), C.POINTER(vp)]
+        L.t41rx_multi_set_params.argtypes = [vp, ip, ip, C.POINTER(Params)]
+        L.t41rx_multi_set_params_each.argtypes = [vp, ip, ip, C.POINTER(Params)]
+        L.t41rx_multi_get_debug.argtypes = [vp, ip, C.POINTER(Debug)]
+        L.t41rx_multi_process.argtypes = [vp, vp, vp, ip, ip, vp, vp, vp, vp, C.c_uint32]
+        L.t41rx_multi_process_q15.argtypes = [vp, vp, vp, ip, ip, vp, vp, vp, vp, C.c_uint32]
+        L.t41rx_multi_process_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), ip, ip, C.POINTER(vp), C.POINTER(vp), C.c_uint32]
+        L.t41rx_multi_synchronize.argtypes = [vp]
+        L.t41rx_multi_gather_rows.argtypes = [vp, C.POINTER(vp), C.c_size_t, vp, C.POINTER(ip)]
+        L.t41rx_multi_last_error.restype = C.c_char_p
         _lib = L
     return _lib
 
@@ -376,3 +395,104 @@ class Receiver:
         ms = C.c_float()
         _check(lib().t41rx_last_kernel_ms(self._h, C.byref(ms)), "t41rx_last_kernel_ms")
         return float(ms.value)
+
+
+def _check_multi(rc, what):
+    if rc != 0:
+        raise T41RxError("%s failed (%d): %s" % (what, rc, lib().t41rx_multi_last_error().decode()))
+
+
+class MultiReceiver:
+    """A bank of n_streams receivers sharded over several CUDA devices in ONE process (t41rx_create_multi): contiguous
+    receiver ranges, one host thread per device inside every call, no inter-GPU traffic on the hot path."""
+
+    def __init__(self, n_streams, devices):
+        self._h = C.c_void_p()
+        self.n_streams = int(n_streams)
+        self.devices = [int(d) for d in devices]
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        _check_multi(lib().t41rx_create_multi(C.byref(self._h), self.n_streams, arr, len(self.devices)), "t41rx_create_multi")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().t41rx_destroy_multi(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def shards(self):
+        """[(device, first, count)] of every shard"""
+        out = []
+        for g in range(lib().t41rx_multi_num_devices(self._h)):
+            d, f, c = C.c_int(), C.c_int(), C.c_int()
+            _check_multi(lib().t41rx_multi_shard(self._h, g, C.byref(d), C.byref(f), C.byref(c), None), "t41rx_multi_shard")
+            out.append((d.value, f.value, c.value))
+        return out
+
+    def set_params_each(self, plist, first=0):
+        arr = (Params * len(plist))(*plist)
+        _check_multi(lib().t41rx_multi_set_params_each(self._h, first, len(plist), arr), "t41rx_multi_set_params_each")
+
+    def set_params(self, p, first=0, count=None):
+        count = self.n_streams - first if count is None else count
+        _check_multi(lib().t41rx_multi_set_params(self._h, first, count, C.byref(p)), "t41rx_multi_set_params")
+
+    def debug(self, stream):
+        d = Debug()
+        _check_multi(lib().t41rx_multi_get_debug(self._h, stream, C.byref(d)), "t41rx_multi_get_debug")
+        return d
+
+    def _out(self, T, row_every, want_psk, dtype):
+        S = self.n_streams
+        n_rows = 0 if row_every <= 0 else (T + row_every - 1) // row_every
+        return n_rows, dict(audio=np.empty((S, T, BLOCK), dtype),
+                            spec=np.zeros((S, n_rows, SPECTRUM_RES), np.int16),
+                            wf=np.zeros((S, n_rows, SPECTRUM_RES), np.uint16),
+                            psk_bits=np.full((S, T), -1, np.int8) if want_psk else None,
+                            psk_chars=np.zeros((S, T), np.uint8) if want_psk else None)
+
+    def process(self, iq, row_every=0, want_psk=False, flags=0):
+        iq = np.ascontiguousarray(iq, dtype=np.float32)
+        T = iq.shape[1]
+        n_rows, out = self._out(T, row_every, want_psk, np.float32)
+        _check_multi(lib().t41rx_multi_process(self._h, _np_ptr(iq), _np_ptr(out["audio"]), T, row_every,
+                                               _np_ptr(out["spec"]) if n_rows else None, _np_ptr(out["wf"]) if n_rows else None,
+                                               _np_ptr(out["psk_bits"]), _np_ptr(out["psk_chars"]), flags), "t41rx_multi_process")
+        return out
+
+    def process_q15(self, iq16, row_every=0, want_psk=False, flags=0):
+        iq16 = np.ascontiguousarray(iq16, dtype=np.int16)
+        T = iq16.shape[1]
+        n_rows, out = self._out(T, row_every, want_psk, np.int16)
+        _check_multi(lib().t41rx_multi_process_q15(self._h, _np_ptr(iq16), _np_ptr(out["audio"]), T, row_every,
+                                                   _np_ptr(out["spec"]) if n_rows else None, _np_ptr(out["wf"]) if n_rows else None,
+                                                   _np_ptr(out["psk_bits"]), _np_ptr(out["psk_chars"]), flags),
+                     "t41rx_multi_process_q15")
+        return out
+
+    def process_device(self, iq_ptrs, audio_ptrs, n_blocks, row_every=0, spec_ptrs=None, wf_ptrs=None, flags=0):
+        n = len(self.devices)
+        arr = lambda ps: (C.c_void_p * n)(*ps) if ps is not None else None      # noqa: E731
+        _check_multi(lib().t41rx_multi_process_device(self._h, arr(iq_ptrs), arr(audio_ptrs), n_blocks, row_every,
+                                                      arr(spec_ptrs), arr(wf_ptrs), flags), "t41rx_multi_process_device")
+
+    def synchronize(self):
+        _check_multi(lib().t41rx_multi_synchronize(self._h), "t41rx_multi_synchronize")
+
+    def gather_rows(self, row_ptrs, bytes_per_receiver, dst_ptr):
+        """row buffers of the shards (device pointers) -> dst on the first device; returns True when NCCL carried it"""
+        n = len(self.devices)
+        used = C.c_int(0)
+        _check_multi(lib().t41rx_multi_gather_rows(self._h, (C.c_void_p * n)(*row_ptrs), bytes_per_receiver, dst_ptr,
+                                                   C.byref(used)), "t41rx_multi_gather_rows")
+        return bool(used.value)

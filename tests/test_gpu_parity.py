@@ -462,3 +462,91 @@ def test_c5_full_size_32768_psk31_bits():
     bits = np.concatenate(bits, axis=1)
     for k in range(D):
         assert np.array_equal(bits[k::D], np.broadcast_to(want[k]["psk_bits"], bits[k::D].shape))
+
+
+# ---- a bank over several devices behind the C-ABI (t41rx_create_multi) ----
+def _n_gpus():
+    torch = pytest.importorskip("torch")
+    return torch.cuda.device_count()
+
+
+def test_multi_device_bank_equals_one_context():
+    """t41rx_create_multi shards a bank into contiguous receiver ranges, one single-device context and one host thread
+    each.  Receivers are independent, so the sharded bank must give exactly the single context's results - audio, rows,
+    PSK31 output, state - whatever the shard boundaries (here 3 shards of a ragged 13-receiver bank; all on the GPUs this
+    box has, several shards per GPU when it has fewer)."""
+    S, T, D = 13, 12, 16
+    base_p, base_iq, params, iq = _c2_bank(S, T, D)
+    for p in params:
+        p.psk31_enable = 1
+    with _receiver(S) as eng:
+        eng.set_params_each(params)
+        one = eng.process(iq, row_every=4, want_psk=True)
+        dbg_one = [eng.debug(s) for s in range(S)]
+    devs = [g % _n_gpus() for g in range(3)]
+    with rx.MultiReceiver(S, devs) as m:
+        assert [(f, c) for _, f, c in m.shards()] == [(0, 4), (4, 4), (8, 5)]
+        m.set_params_each(params)
+        many = m.process(iq, row_every=4, want_psk=True)
+        dbg_many = [m.debug(s) for s in range(S)]
+        iq16 = np.round(iq * 32768.0).astype(np.int16)
+    for k in ("audio", "spec", "wf", "psk_bits", "psk_chars"):
+        a, b = one[k], many[k]
+        assert np.array_equal(a.view(np.uint32) if a.dtype == np.float32 else a, b.view(np.uint32) if b.dtype == np.float32 else b), k
+    for a, b in zip(dbg_one, dbg_many):
+        for f in cases.DEBUG_INT_FIELDS:
+            assert getattr(a, f) == getattr(b, f), f
+    # the q15 entry point through the same fan-out
+    with _receiver(S) as eng:
+        eng.set_params_each(params)
+        one16 = eng.process_q15(iq16, row_every=4)
+    with rx.MultiReceiver(S, devs) as m:
+        m.set_params_each(params)
+        many16 = m.process_q15(iq16, row_every=4)
+    assert np.array_equal(one16["audio"], many16["audio"]) and np.array_equal(one16["spec"], many16["spec"])
+
+
+def test_multi_device_errors_name_the_shard():
+    with pytest.raises(rx.T41RxError) as e:
+        rx.MultiReceiver(8, [0, 99])
+    assert "shard 1" in str(e.value) and "device" in str(e.value)
+    with rx.MultiReceiver(8, [0, 0]) as m:
+        p = rx.default_params()
+        p.agc_mode = 77
+        with pytest.raises(rx.T41RxError):
+            m.set_params(p, first=3, count=3)
+
+
+def test_multi_device_resident_and_row_gather():
+    """Device-resident fan-out (per-shard device pointers) and the optional gather of spectrum rows to the first device:
+    NCCL send / recv when the shards sit on distinct GPUs, peer / device copies otherwise.  The gathered rows must be the
+    single context's rows in receiver order."""
+    torch = pytest.importorskip("torch")
+    S, T, D = 16, 8, 16
+    base_p, base_iq, params, iq = _c2_bank(S, T, D)
+    with _receiver(S) as eng:
+        eng.set_params_each(params)
+        one = eng.process(iq, row_every=4)
+    n_gpu = _n_gpus()
+    devs = [0, 1] if n_gpu >= 2 else [0, 0]
+    R = 2
+    with rx.MultiReceiver(S, devs) as m:
+        m.set_params_each(params)
+        bufs = []
+        for dev, first, count in m.shards():
+            d = torch.device("cuda", dev)
+            bufs.append(dict(iq=torch.from_numpy(iq[first:first + count]).to(d),
+                             audio=torch.zeros((count, T, 2048), dtype=torch.float32, device=d),
+                             spec=torch.zeros((count, R, 512), dtype=torch.int16, device=d),
+                             wf=torch.zeros((count, R, 512), dtype=torch.int16, device=d)))
+        for dev in set(devs):
+            torch.cuda.synchronize(dev)
+        m.process_device([b["iq"].data_ptr() for b in bufs], [b["audio"].data_ptr() for b in bufs], T, 4,
+                         [b["spec"].data_ptr() for b in bufs], [b["wf"].data_ptr() for b in bufs])
+        m.synchronize()
+        audio = np.concatenate([b["audio"].cpu().numpy() for b in bufs])
+        assert np.array_equal(audio.view(np.uint32), one["audio"].view(np.uint32))
+        dst = torch.zeros((S, R, 512), dtype=torch.int16, device=torch.device("cuda", devs[0]))
+        used_nccl = m.gather_rows([b["spec"].data_ptr() for b in bufs], R * 512 * 2, dst.data_ptr())
+        assert np.array_equal(dst.cpu().numpy(), one["spec"])
+        assert used_nccl == (n_gpu >= 2)
