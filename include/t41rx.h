@@ -96,12 +96,14 @@ typedef struct t41rx_params {
   float iq_phase_correction;    /* IQPhaseCorrectionFactor[band]  Process.cpp:167,172                 */
   int32_t receive_eq_flag;      /* receiveEQFlag (ON = 1)         Process.cpp:827-831                 */
   int32_t equalizer_rec[14];    /* EEPROMData.equalizerRec[] 0..100 (default 100)  Filter.cpp:117-165 */
-  int32_t nr_option;            /* nrOptionSelect: 0 off, 3 LMS (Xanr); 1 (Kim) and 2 (spectral) are not built:
-                                   T41RX_EINVAL                   Process.cpp:841-857                 */
+  int32_t nr_option;            /* nrOptionSelect: 0 off, 1 Kim (Kim1_NR, then x 30), 2 spectral
+                                   (SpectralNoiseReduction), 3 LMS (Xanr)   Process.cpp:841-857, Noise.cpp:108-655 */
   int32_t anr_notch_on;         /* ANR_notchOn: automatic notch (Xanr)  Process.cpp:860-865           */
   int32_t cw_receive;           /* T41State == CW_RECEIVE: the CW audio low-pass below is in the chain (the CW decoder
                                    of that state, DoCWReceiveProcessing, is out of scope)  Process.cpp:878 */
   int32_t cw_filter_index;      /* CWFilterIndex 0..4 = 0.8 / 1.0 / 1.3 / 1.8 / 2.0 kHz, 5 = off (default)  Process.cpp:882-912 */
+  int32_t nb_on;                /* NB_on: the LPC impulse blanker (NoiseBlanker / AltNoiseBlanking) behind the notch; default 0
+                                   Process.cpp:39,873-876, DSP_Fn.cpp:105-362 */
 } t41rx_params;
 
 /* Discrete / scalar DSP state for state-transition parity checks. */

@@ -467,8 +467,133 @@ static uint32_t octal_reverse3(uint32_t p) {
   return ((p & 7u) << 6) | (p & 0x38u) | ((p >> 6) & 7u);
 }
 
+/* ------------------------------------------------------------------ */
+/* complex FFT, N = 256 = 4 * 8 * 8 (the noise-reduction stages,        */
+/* T41/Noise.cpp:206,279,454,636): one radix-4 decimation-in-frequency  */
+/* stage over the four quarters, then two radix-8 stages inside each    */
+/* 64-point quarter (CMSIS: arm_cfft_radix8by4_f32), then the mixed     */
+/* digit reversal.  The operation order below IS the definition the     */
+/* CUDA side replicates.                                                */
+/* ------------------------------------------------------------------ */
+#define T41_FFT_N256 256
+static float32_t g_twiddle256[2 * T41_FFT_N256]; /* cos(2*pi*i/256), sin(2*pi*i/256) */
+static int g_twiddle256_ready = 0;
+
+static const float32_t *twiddle256(void) {
+  if (!g_twiddle256_ready) {
+    for (int i = 0; i < T41_FFT_N256; ++i) {
+      double a = 2.0 * 3.14159265358979323846 * (double)i / (double)T41_FFT_N256;
+      g_twiddle256[2 * i] = (float32_t)cos(a);
+      g_twiddle256[2 * i + 1] = (float32_t)sin(a);
+    }
+    g_twiddle256[2 * 0] = 1.0f;    g_twiddle256[2 * 0 + 1] = 0.0f;
+    g_twiddle256[2 * 64] = 0.0f;   g_twiddle256[2 * 64 + 1] = 1.0f;
+    g_twiddle256[2 * 128] = -1.0f; g_twiddle256[2 * 128 + 1] = 0.0f;
+    g_twiddle256[2 * 192] = 0.0f;  g_twiddle256[2 * 192 + 1] = -1.0f;
+    g_twiddle256_ready = 1;
+  }
+  return g_twiddle256;
+}
+
+/* (re, im) * exp(-j*2*pi*t/256): the same four products and two sums as the 512-point stages */
+static void twiddle_mul256(const float32_t *tw, uint32_t t, float32_t *re, float32_t *im) {
+  const float32_t co = tw[2u * t], si = tw[2u * t + 1u];
+  const float32_t rc = *re * co, is = *im * si;
+  const float32_t ic = *im * co, rs = *re * si;
+  *re = rc + is;
+  *im = ic - rs;
+}
+
+static void dif_256(float32_t *buf) {
+  const float32_t *tw = twiddle256();
+  /* radix-4 stage: quarter q of the result holds the inputs of the 64-point transform of bins 4 k + q */
+  for (uint32_t j = 0; j < 64u; ++j) {
+    const float32_t ar = buf[2u * j], ai = buf[2u * j + 1u];
+    const float32_t br = buf[2u * (j + 64u)], bi = buf[2u * (j + 64u) + 1u];
+    const float32_t cr = buf[2u * (j + 128u)], ci = buf[2u * (j + 128u) + 1u];
+    const float32_t dr = buf[2u * (j + 192u)], di = buf[2u * (j + 192u) + 1u];
+    const float32_t s0r = ar + cr, s0i = ai + ci;      /* a + c */
+    const float32_t d0r = ar - cr, d0i = ai - ci;      /* a - c */
+    const float32_t s1r = br + dr, s1i = bi + di;      /* b + d */
+    const float32_t d1r = br - dr, d1i = bi - di;      /* b - d */
+    float32_t y0r = s0r + s1r, y0i = s0i + s1i;
+    float32_t y2r = s0r - s1r, y2i = s0i - s1i;
+    float32_t y1r = d0r + d1i, y1i = d0i - d1r;        /* (a - c) - j (b - d) */
+    float32_t y3r = d0r - d1i, y3i = d0i + d1r;        /* (a - c) + j (b - d) */
+    if (j != 0u) {
+      twiddle_mul256(tw, j, &y1r, &y1i);
+      twiddle_mul256(tw, 2u * j, &y2r, &y2i);
+      twiddle_mul256(tw, 3u * j, &y3r, &y3i);
+    }
+    buf[2u * j] = y0r;            buf[2u * j + 1u] = y0i;
+    buf[2u * (j + 64u)] = y1r;    buf[2u * (j + 64u) + 1u] = y1i;
+    buf[2u * (j + 128u)] = y2r;   buf[2u * (j + 128u) + 1u] = y2i;
+    buf[2u * (j + 192u)] = y3r;   buf[2u * (j + 192u) + 1u] = y3i;
+  }
+  /* two radix-8 stages inside each quarter: n1 = 64 (twiddle step 4 of the 256-table), then n1 = 8 (no twiddles) */
+  for (uint32_t q = 0; q < 4u; ++q) {
+    float32_t *b = buf + 2u * 64u * q;
+    uint32_t n2 = 64u, stride = 4u;
+    while (n2 > 1u) {
+      const uint32_t n1 = n2;
+      n2 >>= 3;
+      for (uint32_t j = 0; j < n2; ++j) {
+        for (uint32_t i0 = j; i0 < 64u; i0 += n1) {
+          float32_t xr[8], xi[8], yr[8], yi[8];
+          for (uint32_t m = 0; m < 8u; ++m) {
+            xr[m] = b[2u * (i0 + m * n2)];
+            xi[m] = b[2u * (i0 + m * n2) + 1u];
+          }
+          dft8(xr, xi, yr, yi);
+          b[2u * i0] = yr[0];
+          b[2u * i0 + 1u] = yi[0];
+          for (uint32_t k = 1; k < 8u; ++k) {
+            float32_t re = yr[k], im = yi[k];
+            if (j != 0u) twiddle_mul256(tw, j * k * stride, &re, &im);
+            b[2u * (i0 + k * n2)] = re;
+            b[2u * (i0 + k * n2) + 1u] = im;
+          }
+        }
+      }
+      stride <<= 3;
+    }
+  }
+}
+
+/* position p = 64 q + 8 d1 + d0 holds bin 4 (8 d0 + d1) + q */
+static uint32_t digit_reverse_256(uint32_t p) {
+  return 4u * (8u * (p & 7u) + ((p >> 3) & 7u)) + (p >> 6);
+}
+
+static void cfft256(float32_t *p1, uint8_t ifftFlag, uint8_t bitReverseFlag) {
+  if (ifftFlag) {
+    for (uint32_t i = 0; i < T41_FFT_N256; ++i) p1[2u * i + 1u] = -p1[2u * i + 1u];
+  }
+  dif_256(p1);
+  if (bitReverseFlag) {
+    float32_t tmp[2 * T41_FFT_N256];
+    memcpy(tmp, p1, sizeof(tmp));
+    for (uint32_t p = 0; p < T41_FFT_N256; ++p) {
+      const uint32_t k = digit_reverse_256(p);
+      p1[2u * k] = tmp[2u * p];
+      p1[2u * k + 1u] = tmp[2u * p + 1u];
+    }
+  }
+  if (ifftFlag) {
+    const float32_t invL = 1.0f / (float32_t)T41_FFT_N256;
+    for (uint32_t i = 0; i < T41_FFT_N256; ++i) {
+      p1[2u * i] = p1[2u * i] * invL;
+      p1[2u * i + 1u] = -p1[2u * i + 1u] * invL;
+    }
+  }
+}
+
 void arm_cfft_f32(const arm_cfft_instance_f32 *S, float32_t *p1, uint8_t ifftFlag, uint8_t bitReverseFlag) {
-  if (S->fftLen != T41_FFT_N) abort(); /* only the 512-point transform is on the RX path */
+  if (S->fftLen == T41_FFT_N256) {
+    cfft256(p1, ifftFlag, bitReverseFlag);
+    return;
+  }
+  if (S->fftLen != T41_FFT_N) abort(); /* only the 512- and 256-point transforms are on the RX path */
   if (ifftFlag) {
     for (uint32_t i = 0; i < T41_FFT_N; ++i) p1[2u * i + 1u] = -p1[2u * i + 1u];
   }

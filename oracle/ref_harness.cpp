@@ -237,6 +237,7 @@ void T41ControlSendData(uint8_t *data, int len) {
 
 /* AGC variables of DSP_Fn.cpp that have external linkage */
 extern uint8_t agc_action;
+extern uint8_t NB_on;                                   /* Process.cpp:39 */
 extern int attack_buffsize;
 extern int hang_counter;
 extern int out_index;
@@ -299,6 +300,7 @@ int t41ref_init(void) {
   g_prm.anr_notch_on = 0;
   g_prm.cw_receive = 0;
   g_prm.cw_filter_index = 5;
+  g_prm.nb_on = 0;
   for (int i = 0; i < 14; i++) {
     EEPROMData.equalizerRec[i] = 100;       /* EEPROM.cpp:59,698 */
     g_prm.equalizer_rec[i] = 100;
@@ -388,9 +390,10 @@ int t41ref_set_params(const t41o_params *p) {
   IQAmpCorrectionFactor[currentBand] = p->iq_amp_correction;
   IQPhaseCorrectionFactor[currentBand] = p->iq_phase_correction;
   receiveEQFlag = p->receive_eq_flag;
-  if (p->nr_option != 0 && p->nr_option != 3) return -1;
+  if (p->nr_option < 0 || p->nr_option > 3) return -1;
   nrOptionSelect = p->nr_option;
   ANR_notchOn = (uint8_t)p->anr_notch_on;
+  NB_on = (uint8_t)(p->nb_on != 0);                    /* Process.cpp:39 */
   if (p->cw_filter_index < 0 || p->cw_filter_index > 5) return -1;
   T41State = p->cw_receive == 1 ? CW_RECEIVE : 1;      /* 1: the state the harness otherwise sits in */
   CWFilterIndex = p->cw_filter_index;

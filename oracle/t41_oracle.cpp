@@ -333,6 +333,19 @@ struct t41o_stream {
   float anr_d[512], anr_w[512];
   int anr_in_idx;
   float anr_lidx, anr_ngamma;
+  /* spectral noise reduction stages, T41/Noise.cpp:17-37: Kim1_NR and SpectralNoiseReduction work on the SAME arrays
+     (they are globals there); zero at start like every static of the host build */
+  float nr_last_sample[128], nr_last_ifft[128];
+  float nr_X[128][3], nr_E[128][15], nr_M[128], nr_Nest[128][2], nr_lambda[128], nr_Gts[128][2], nr_G[128];
+  float nr_SNR_prio[128], nr_SNR_post[128], nr_Hk_old[128], nr_long_tone_gain[128];
+  uint32_t nr_X_pointer, nr_E_pointer;               /* Kim1_NR's statics, Noise.cpp:109-110 */
+  uint8_t nr_init_counter;                           /* SpectralNoiseReduction's statics, Noise.cpp:389-427 */
+  int nr_first_time_2;
+  float nr_pslp[128], nr_xt[128];
+  int nr_consts_ready;
+  float nr_xih1r, nr_pfac;
+  /* noise blanker, T41/DSP_Fn.cpp:143 */
+  float nb_last_frame_end[80];
   /* CW audio low-passes, T41/CWProcessing.cpp:38-49 */
   float cw_state[5][12];
   arm_biquad_cascade_df2T_instance_f32 cw[5];
@@ -423,7 +436,7 @@ int ValidParams(const t41o_params *p) {
   if (p->current_scale < 0 || p->current_scale > 4) return 0;
   if (p->f_hi_cut <= p->f_lo_cut) return 0;
   if (p->audio_volume < 0 || p->audio_volume > 100) return 0;
-  if (p->nr_option != 0 && p->nr_option != 3) return 0;      /* Kim (1) and spectral (2) NR are not restated */
+  if (p->nr_option < 0 || p->nr_option > 3) return 0;
   if (p->cw_filter_index < 0 || p->cw_filter_index > 5) return 0;
   return 1;
 }
@@ -750,6 +763,7 @@ void InitStream(t41o_stream *s) {
   s->osc_vect_q = 1.0;
   for (int i = 0; i < 5; i++) arm_biquad_cascade_df2T_init_f32(&s->cw[i], 6, t41o_cw_coeffs[i], s->cw_state[i]);
   s->anr_lidx = 120.0;       /* T41/Noise.cpp:47,52 */
+  s->nr_first_time_2 = 1;    /* T41/Noise.cpp:427 */
   s->anr_ngamma = 0.001;
   for (int i = 0; i < 14; i++) arm_biquad_cascade_df2T_init_f32(&s->eq[i], 4, t41o_eq_coeffs[i], s->eq_state[i]);
   s->osc_vect_i = 0.0;
@@ -826,6 +840,7 @@ void t41o_default_params(t41o_params *p) {
   p->anr_notch_on = 0;
   p->cw_receive = 0;
   p->cw_filter_index = 5;
+  p->nb_on = 0;
 }
 
 void t41o_mode_default_cuts(int32_t mode, int32_t *f_lo_cut, int32_t *f_hi_cut) {
@@ -962,6 +977,294 @@ static void Xanr(t41o_stream *s, int notch, const float *in, float *out) {
     }
     s->anr_in_idx = (s->anr_in_idx + ANR_mask) & ANR_mask;
   }
+}
+
+/* ---- spectral noise-reduction stages (T41/Noise.cpp:108-311, 379-655), 256-point frames with 128 new samples each ---- */
+static const float kNrPsi = 0.0, kNrAlpha = 0.95, kNrBeta = 0.85;     /* EEPROM.cpp:71-73 (gwv.cpp defaults) */
+enum { kNrL = 256, kNrHalf = 128, kNrLFrames = 3, kNrNFrames = 15 };
+
+/* the voice-activity bin range both stages derive from the filter cut-offs (Noise.cpp:141-172, 429-443, 515-529) */
+static void NrVadRange(const t41o_stream *s, uint8_t *lo, uint8_t *hi) {
+  float lf_freq, uf_freq;
+  const int flo = s->prm.f_lo_cut, fhi = s->prm.f_hi_cut;
+  if (flo <= 0 && fhi >= 0) {
+    lf_freq = 0.0;
+    uf_freq = fmax(-(float)flo, (float)fhi);
+  } else if (flo > 0) {
+    lf_freq = (float)flo;
+    uf_freq = (float)fhi;
+  } else {
+    uf_freq = -(float)flo;
+    lf_freq = -(float)fhi;
+  }
+  lf_freq /= (((float)kSampleRate / kDF) / kNrL);
+  uf_freq /= (((float)kSampleRate / kDF) / kNrL);
+  uint8_t VAD_low = (int)lf_freq, VAD_high = (int)uf_freq;
+  if (VAD_low == VAD_high) VAD_high++;
+  if (VAD_low < 1) VAD_low = 1;
+  else if (VAD_low > kNrL / 2 - 2) VAD_low = kNrL / 2 - 2;
+  if (VAD_high < 1) VAD_high = 1;
+  else if (VAD_high > kNrL / 2) VAD_high = kNrL / 2;
+  *lo = VAD_low;
+  *hi = VAD_high;
+}
+
+/* frame k of a block: previous 128 samples | the block's samples 128 k .. 128 k + 127, imaginary parts zero */
+static void NrLoadFrame(t41o_stream *s, const float *L, int k, float *buf) {
+  for (int i = 0; i < kNrHalf; i++) {
+    buf[i * 2] = s->nr_last_sample[i];
+    buf[i * 2 + 1] = 0.0;
+  }
+  for (int i = 0; i < kNrHalf; i++) s->nr_last_sample[i] = L[i + k * kNrHalf];
+  for (int i = 0; i < kNrHalf; i++) {
+    buf[kNrL + i * 2] = L[i + k * kNrHalf];
+    buf[kNrL + i * 2 + 1] = 0.0;
+  }
+}
+
+/* Kim & Ruwisch 2002 as the reference runs it (power instead of magnitude, gains clamped at 0), T41/Noise.cpp:108-311 */
+static void Kim1Nr(t41o_stream *s, float *L, float *R) {
+  float buf[2 * kNrL], out[kNrL];
+  const float NR_KIM_K = 1.0;
+  const float NR_onemalpha = (1.0 - kNrAlpha);
+  const float NR_onemtwobeta = (1.0 - (2.0 * kNrBeta));
+  uint8_t VAD_low, VAD_high;
+  NrVadRange(s, &VAD_low, &VAD_high);
+  for (int k = 0; k < 2; k++) {
+    NrLoadFrame(s, L, k, buf);
+    for (int idx = 0; idx < kNrL; idx++) {          /* Hann window, evaluated like the reference's expression */
+      const float w = 0.5 * (float)(1.0 - (cosf(3.1415926535897932384626433832795 * 2.0 * (float)idx / (float)(kNrL - 1))));
+      buf[idx * 2] *= w;
+    }
+    arm_cfft_f32(&arm_cfft_sR_f32_len256, buf, 0, 1);
+    for (int i = 0; i < kNrHalf; i++) s->nr_X[i][s->nr_X_pointer] = (buf[i * 2] * buf[i * 2] + buf[i * 2 + 1] * buf[i * 2 + 1]);
+    for (int i = VAD_low; i < VAD_high; i++) {
+      float sum = 0.0;
+      for (int j = 0; j < kNrLFrames; j++) sum = sum + s->nr_X[i][j];
+      s->nr_E[i][s->nr_E_pointer] = sum / (float)kNrLFrames;
+    }
+    for (int i = VAD_low; i < VAD_high; i++) {
+      s->nr_M[i] = s->nr_E[i][0];
+      for (int j = 1; j < kNrNFrames; j++)
+        if (s->nr_E[i][j] < s->nr_M[i]) s->nr_M[i] = s->nr_E[i][j];
+    }
+    for (int i = VAD_low; i < VAD_high; i++) {
+      const float T = s->nr_X[i][s->nr_X_pointer] / s->nr_M[i];
+      s->nr_lambda[i] = (T > kNrPsi) ? s->nr_M[i] : s->nr_E[i][s->nr_E_pointer];
+    }
+    for (int i = VAD_low; i < VAD_high; i++) {      /* NR_use_X == 0 */
+      s->nr_G[i] = 1.0 - (s->nr_lambda[i] * NR_KIM_K / s->nr_E[i][s->nr_E_pointer]);
+      if (s->nr_G[i] < 0.0) s->nr_G[i] = 0.0;
+      s->nr_Gts[i][0] = kNrAlpha * s->nr_Gts[i][1] + (NR_onemalpha) * s->nr_G[i];
+      s->nr_Gts[i][1] = s->nr_Gts[i][0];
+    }
+    for (int i = 1; i < (kNrHalf - 1); i++)
+      s->nr_G[i] = kNrBeta * s->nr_Gts[i - 1][0] + NR_onemtwobeta * s->nr_Gts[i][0] + kNrBeta * s->nr_Gts[i + 1][0];
+    s->nr_G[0] = (NR_onemtwobeta + kNrBeta) * s->nr_Gts[0][0] + kNrBeta * s->nr_Gts[1][0];
+    s->nr_G[kNrHalf - 1] = kNrBeta * s->nr_Gts[kNrHalf - 2][0] + (NR_onemtwobeta + kNrBeta) * s->nr_Gts[kNrHalf - 1][0];
+    for (int i = 0; i < kNrHalf; i++) {             /* the "conjugate symmetric" side pairs bin i with bin 255 - i, as written */
+      buf[i * 2] = buf[i * 2] * s->nr_G[i];
+      buf[i * 2 + 1] = buf[i * 2 + 1] * s->nr_G[i];
+      buf[kNrL * 2 - i * 2 - 2] = buf[kNrL * 2 - i * 2 - 2] * s->nr_G[i];
+      buf[kNrL * 2 - i * 2 - 1] = buf[kNrL * 2 - i * 2 - 1] * s->nr_G[i];
+    }
+    if (++s->nr_X_pointer >= kNrLFrames) s->nr_X_pointer = 0;
+    if (++s->nr_E_pointer >= kNrNFrames) s->nr_E_pointer = 0;
+    arm_cfft_f32(&arm_cfft_sR_f32_len256, buf, 1, 1);
+    for (int i = 0; i < kNrHalf; i++) out[i + k * kNrHalf] = buf[i * 2] + s->nr_last_ifft[i];
+    for (int i = 0; i < kNrHalf; i++) s->nr_last_ifft[i] = buf[kNrL + i * 2];
+  }
+  for (int i = 0; i < kNrL; i++) {
+    L[i] = out[i];
+    R[i] = L[i];
+  }
+}
+
+/* T41/Noise.cpp:379-655.  Quirks kept: everything from the final weighting to the overlap-add sits inside the
+   `first_time == 3` branch (the first 20 frames pass the audio through untouched); the musical-noise smoothing runs once
+   per bin of the gain loop; NR_long_tone_gain is never written anywhere in the reference (all zeros in the host
+   build), so once the stage has initialised its output is (signed) zero. */
+static void SpectralNr(t41o_stream *s, float *L, float *R) {
+  float buf[2 * kNrL];
+  const float tinc = 0.00533333, tax = 0.0239, tap = 0.05062, psthr = 0.99, pnsaf = 0.01, asnr = 20, psini = 0.5, pspri = 0.5;
+  const float ax = expf(-tinc / tax), ap = expf(-tinc / tap);
+  const float xih1 = powf(10, (float)asnr / 10.0);
+  if (!s->nr_consts_ready) {                 /* function statics: initialised on the first call */
+    s->nr_xih1r = 1.0 / (1.0 + xih1) - 1.0;
+    s->nr_pfac = (1.0 / pspri - 1.0) * (1.0 + xih1);
+    s->nr_consts_ready = 1;
+  }
+  const float xih1r = s->nr_xih1r, pfac = s->nr_pfac;
+  const float snr_prio_min = powf(10, -(float)20 / 20.0);
+  const int16_t NR_width = 4;
+  const float power_threshold = 0.4;
+  float ph1y[kNrHalf];
+  float xtr, pre_power, post_power, power_ratio;
+  int16_t NN;
+  uint8_t VAD_low, VAD_high;
+  if (s->nr_first_time_2 == 1) {
+    for (int i = 0; i < kNrHalf; i++) {
+      s->nr_last_sample[i] = 0.0;
+      s->nr_G[i] = 1.0;
+      s->nr_Hk_old[i] = 1.0;
+      s->nr_Nest[i][0] = 0.0;
+      s->nr_Nest[i][1] = 1.0;
+      s->nr_pslp[i] = 0.5;
+    }
+    s->nr_first_time_2 = 2;
+  }
+  for (int k = 0; k < 2; k++) {
+    NrLoadFrame(s, L, k, buf);
+    for (int idx = 0; idx < kNrL; idx++) buf[idx * 2] *= t41o_sqrt_hann[idx];
+    arm_cfft_f32(&arm_cfft_sR_f32_len256, buf, 0, 1);
+    for (int i = 0; i < kNrHalf; i++) s->nr_X[i][0] = (buf[i * 2] * buf[i * 2] + buf[i * 2 + 1] * buf[i * 2 + 1]);
+    if (s->nr_first_time_2 == 2) {
+      for (int i = 0; i < kNrHalf; i++) {
+        s->nr_Nest[i][0] = s->nr_Nest[i][0] + 0.05 * s->nr_X[i][0];
+        s->nr_xt[i] = psini * s->nr_Nest[i][0];
+      }
+      s->nr_init_counter++;
+      if (s->nr_init_counter > 19) {
+        s->nr_init_counter = 0;
+        s->nr_first_time_2 = 3;
+      }
+    }
+    if (s->nr_first_time_2 == 3) {
+      for (int i = 0; i < kNrHalf; i++) {
+        ph1y[i] = 1.0 / (1.0 + pfac * expf(xih1r * s->nr_X[i][0] / s->nr_xt[i]));
+        s->nr_pslp[i] = ap * s->nr_pslp[i] + (1.0 - ap) * ph1y[i];
+        if (s->nr_pslp[i] > psthr) ph1y[i] = 1.0 - pnsaf;
+        else ph1y[i] = fmin(ph1y[i], 1.0);
+        xtr = (1.0 - ph1y[i]) * s->nr_X[i][0] + ph1y[i] * s->nr_xt[i];
+        s->nr_xt[i] = ax * s->nr_xt[i] + (1.0 - ax) * xtr;
+      }
+      for (int i = 0; i < kNrHalf; i++) {
+        s->nr_SNR_post[i] = fmax(fmin(s->nr_X[i][0] / s->nr_xt[i], 1000.0), snr_prio_min);
+        s->nr_SNR_prio[i] = fmax(kNrAlpha * s->nr_Hk_old[i] + (1.0 - kNrAlpha) * fmax(s->nr_SNR_post[i] - 1.0, 0.0), 0.0);
+      }
+      NrVadRange(s, &VAD_low, &VAD_high);
+      float v;
+      for (int i = VAD_low; i < VAD_high; i++) {
+        v = s->nr_SNR_prio[i] * s->nr_SNR_post[i] / (1.0 + s->nr_SNR_prio[i]);
+        s->nr_G[i] = 1.0 / s->nr_SNR_post[i] * sqrtf((0.7212 * v + v * v));
+        s->nr_Hk_old[i] = s->nr_SNR_post[i] * s->nr_G[i] * s->nr_G[i];
+        /* musical-noise treatment: inside the gain loop, as written */
+        pre_power = 0.0;
+        post_power = 0.0;
+        for (int m = VAD_low; m < VAD_high; m++) {
+          pre_power += s->nr_X[m][0];
+          post_power += s->nr_G[m] * s->nr_G[m] * s->nr_X[m][0];
+        }
+        power_ratio = post_power / pre_power;
+        if (power_ratio > power_threshold) {
+          power_ratio = 1.0;
+          NN = 1;
+        } else {
+          NN = 1 + 2 * (int)(0.5 + NR_width * (1.0 - power_ratio / power_threshold));
+        }
+        for (int b = VAD_low + NN / 2; b < VAD_high - NN / 2; b++) {
+          s->nr_Nest[b][0] = 0.0;
+          for (int m = b - NN / 2; m <= b + NN / 2; m++) s->nr_Nest[b][0] += s->nr_G[m];
+          s->nr_Nest[b][0] /= (float)NN;
+        }
+        for (int b = VAD_low; b < VAD_low + NN / 2; b++) {
+          s->nr_Nest[b][0] = 0.0;
+          for (int m = b; m < (b + NN); m++) s->nr_Nest[b][0] += s->nr_G[m];
+          s->nr_Nest[b][0] /= (float)NN;
+        }
+        for (int b = VAD_high - NN; b < VAD_high; b++) {
+          s->nr_Nest[b][0] = 0.0;
+          for (int m = b; m > (b - NN); m--) s->nr_Nest[b][0] += s->nr_G[m];
+          s->nr_Nest[b][0] /= (float)NN;
+        }
+        for (int b = VAD_low + NN / 2; b < VAD_high - NN / 2; b++) s->nr_G[b] = s->nr_Nest[b][0];
+      }
+      for (int i = 0; i < kNrHalf; i++) {
+        buf[i * 2] = buf[i * 2] * s->nr_G[i] * s->nr_long_tone_gain[i];
+        buf[i * 2 + 1] = buf[i * 2 + 1] * s->nr_G[i] * s->nr_long_tone_gain[i];
+        buf[kNrL * 2 - i * 2 - 2] = buf[kNrL * 2 - i * 2 - 2] * s->nr_G[i] * s->nr_long_tone_gain[i];
+        buf[kNrL * 2 - i * 2 - 1] = buf[kNrL * 2 - i * 2 - 1] * s->nr_G[i] * s->nr_long_tone_gain[i];
+      }
+      arm_cfft_f32(&arm_cfft_sR_f32_len256, buf, 1, 1);
+      for (int idx = 0; idx < kNrL; idx++) buf[idx * 2] *= t41o_sqrt_hann[idx];
+      for (int i = 0; i < kNrHalf; i++) {
+        L[i + k * kNrHalf] = buf[i * 2] + s->nr_last_ifft[i];
+        R[i + k * kNrHalf] = L[i + k * kNrHalf];
+      }
+      for (int i = 0; i < kNrHalf; i++) s->nr_last_ifft[i] = buf[kNrL + i * 2];
+    }
+  }
+}
+
+/* T41/DSP_Fn.cpp:105-362 NoiseBlanker / AltNoiseBlanking: LPC (order 10, Levinson-Durbin on the block's
+   autocorrelation), inverse + matched filtering to expose impulses, threshold 2.5 sigma, and 7 samples around each
+   impulse replaced by the windowed sum of a forward and a backward linear prediction */
+static void NoiseBlank(t41o_stream *s, float *insamp, float *outsamp) {
+  enum { Nsam = 256, order = 10, impulse_length = 7, PL = 3, boundary_blank = 14 };
+  const float NB_thresh = 2.5;
+  int impulse_positions[20];
+  int search_pos = 0, impulse_count = 0;
+  arm_fir_instance_f32 LPC;
+  float lpcs[order + 1], reverse_lpcs[order + 1], firState[Nsam + order], tempsamp[Nsam];
+  float sigma2, lpc_power, impulse_threshold;
+  float R[11], k, alfa, any[order + 1];
+  float Rfw[impulse_length + order], Rbw[impulse_length + order], Wfw[impulse_length], Wbw[impulse_length];
+  float sacc;
+  memset(R, 0, sizeof(R));
+  for (int i = 0; i < impulse_length; i++) {
+    Wbw[i] = 1.0 * i / (impulse_length - 1);
+    Wfw[impulse_length - i - 1] = Wbw[i];
+  }
+  for (int i = 0; i < (order + 1); i++) arm_dot_prod_f32(&insamp[0], &insamp[i], Nsam - i, &R[i]);
+  R[0] = R[0] * (1.0 + 1.0e-9);
+  lpcs[0] = 1;
+  for (int i = 1; i < order + 1; i++) lpcs[i] = 0;
+  alfa = R[0];
+  for (int m = 1; m <= order; m++) {
+    sacc = 0.0;
+    for (int u = 1; u < m; u++) sacc = sacc + lpcs[u] * R[m - u];
+    k = -(R[m] + sacc) / alfa;
+    for (int v = 1; v < m; v++) any[v] = lpcs[v] + k * lpcs[m - v];
+    for (int w = 1; w < m; w++) lpcs[w] = any[w];
+    lpcs[m] = k;
+    alfa = alfa * (1 - k * k);
+  }
+  for (int o = 0; o < order + 1; o++) reverse_lpcs[order - o] = lpcs[o];
+  arm_fir_init_f32(&LPC, order + 1, &reverse_lpcs[0], &firState[0], Nsam);
+  arm_fir_f32(&LPC, insamp, tempsamp, Nsam);
+  arm_fir_init_f32(&LPC, order + 1, &lpcs[0], &firState[0], Nsam);
+  arm_fir_f32(&LPC, tempsamp, tempsamp, Nsam);
+  arm_var_f32(tempsamp, Nsam, &sigma2);
+  arm_power_f32(lpcs, order, &lpc_power);
+  impulse_threshold = NB_thresh * sqrtf(sigma2 * lpc_power);
+  search_pos = order + PL;
+  impulse_count = 0;
+  do {
+    if ((tempsamp[search_pos] > impulse_threshold) || (tempsamp[search_pos] < (-impulse_threshold))) {
+      impulse_positions[impulse_count] = search_pos - order;
+      impulse_count++;
+      search_pos += PL;
+    }
+    search_pos++;
+  } while (((unsigned int)search_pos < Nsam - (unsigned int)boundary_blank) && ((unsigned int)impulse_count < 20U));
+  arm_negate_f32(&lpcs[1], &lpcs[1], order);
+  arm_negate_f32(&reverse_lpcs[0], &reverse_lpcs[0], order);
+  for (int j = 0; j < impulse_count; j++) {
+    for (int q = 0; q < order; q++) {
+      if ((impulse_positions[j] - PL - order + q) < 0) Rfw[q] = s->nb_last_frame_end[impulse_positions[j] + q];
+      else Rfw[q] = insamp[impulse_positions[j] - PL - order + q];
+      Rbw[impulse_length + q] = insamp[impulse_positions[j] + PL + q + 1];
+    }
+    for (int i = 0; i < impulse_length; i++) {
+      arm_dot_prod_f32(&reverse_lpcs[0], &Rfw[i], order, &Rfw[i + order]);
+      arm_dot_prod_f32(&lpcs[1], &Rbw[impulse_length - i], order, &Rbw[impulse_length - i - 1]);
+    }
+    arm_mult_f32(&Wfw[0], &Rfw[order], &Rfw[order], impulse_length);
+    arm_mult_f32(&Wbw[0], &Rbw[0], &Rbw[0], impulse_length);
+    arm_add_f32(&Rfw[order], &Rbw[0], &insamp[impulse_positions[j] - PL], impulse_length);
+  }
+  for (int p = 0; p < (order + PL); p++) s->nb_last_frame_end[p] = insamp[Nsam - 1 - order - PL + p];
+  for (int q = 0; q < Nsam; q++) outsamp[q] = insamp[q];
 }
 
 /* Arduino map() with a float first argument, as the Teensyduino core overloads it (cores/teensy4/wiring.h; the
@@ -1174,12 +1477,21 @@ int t41o_process_block(t41o_stream *s, const float *iq, float *audio, int update
   /* T41/Process.cpp:841-865.  LMS noise reduction (option 3): Xanr leaves its output in float_buffer_R, which
      nothing reads afterwards - what reaches the audio is float_buffer_L x 1.5, and the adaptive filter's state
      (shared with the notch) still advances.  Automatic notch: Xanr's error signal replaces float_buffer_L. */
-  if (s->prm.nr_option == 3) {
+  if (s->prm.nr_option == 1) {                 /* Process.cpp:845-849 */
+    Kim1Nr(s, L, R);
+    arm_scale_f32(L, 30, L, kDec);
+  } else if (s->prm.nr_option == 2) {          /* Process.cpp:850-852 */
+    SpectralNr(s, L, R);
+  } else if (s->prm.nr_option == 3) {
     Xanr(s, 0, L, R);
     arm_scale_f32(L, 1.5, L, kDec);
   }
   if (s->prm.anr_notch_on == 1) {
     Xanr(s, 1, L, R);
+    arm_copy_f32(R, L, kDec);
+  }
+  if (s->prm.nb_on != 0) {                     /* Process.cpp:873-876 */
+    NoiseBlank(s, L, R);
     arm_copy_f32(R, L, kDec);
   }
 

@@ -54,10 +54,11 @@ typedef struct t41o_params {
   float iq_phase_correction;    /* IQPhaseCorrectionFactor[band], default 0       */
   int32_t receive_eq_flag;      /* receiveEQFlag, default 0 (OFF)                 */
   int32_t equalizer_rec[14];    /* EEPROMData.equalizerRec[], default 100 each    */
-  int32_t nr_option;            /* nrOptionSelect: 0 off, 3 LMS; 1 / 2 rejected   */
+  int32_t nr_option;            /* nrOptionSelect: 0 off, 1 Kim, 2 spectral, 3 LMS */
   int32_t anr_notch_on;         /* ANR_notchOn, default 0                         */
   int32_t cw_receive;           /* T41State == CW_RECEIVE, default 0              */
   int32_t cw_filter_index;      /* CWFilterIndex 0..5, default 5 (off)            */
+  int32_t nb_on;                /* NB_on, default 0                               */
 } t41o_params;
 
 typedef struct t41o_debug {

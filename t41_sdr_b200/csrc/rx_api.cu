@@ -408,6 +408,8 @@ struct t41rx_ctx {
   float *d_eq_coeffs = nullptr;
   float *d_cw_coeffs = nullptr;
   float *d_sam = nullptr;
+  float *d_nr_tab = nullptr;
+  NrState *d_nr = nullptr;      /* allocated (zeroed) when the first receiver switches a spectral NR stage / the blanker on */
   uint16_t *d_gradient = nullptr;
   uint32_t *d_varicode = nullptr;
 
@@ -499,6 +501,7 @@ static int UploadConstTables(t41rx_ctx *ctx) {
   if ((rc = UploadConst(&ctx->d_eq_coeffs, h.eq_coeffs))) return rc;
   if ((rc = UploadConst(&ctx->d_cw_coeffs, h.cw_coeffs))) return rc;
   if ((rc = UploadConst(&ctx->d_sam, h.sam_consts))) return rc;
+  if ((rc = UploadConst(&ctx->d_nr_tab, h.nr_tab))) return rc;
   if ((rc = UploadConst(&ctx->d_gradient, h.gradient))) return rc;
   if ((rc = UploadConst(&ctx->d_varicode, h.varicode))) return rc;
   return 0;
@@ -541,7 +544,7 @@ void t41rx_destroy(t41rx_ctx *ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->copy_out) cudaStreamSynchronize(ctx->copy_out);
   void *bufs[] = {ctx->d_cfg, ctx->d_state, ctx->d_fsets, ctx->d_nco_tab, ctx->d_twiddle, ctx->d_hann, ctx->d_sin,
-                  ctx->d_zoom_iir, ctx->d_eq_coeffs, ctx->d_cw_coeffs, ctx->d_sam, ctx->d_gradient, ctx->d_varicode, ctx->d_iq, ctx->d_audio,
+                  ctx->d_zoom_iir, ctx->d_eq_coeffs, ctx->d_cw_coeffs, ctx->d_sam, ctx->d_nr_tab, ctx->d_nr, ctx->d_gradient, ctx->d_varicode, ctx->d_iq, ctx->d_audio,
                   ctx->d_spec, ctx->d_wf, ctx->d_bits, ctx->d_chars, ctx->d_fast_ids[0], ctx->d_phased_ids[0], ctx->d_fast_ids[1],
                   ctx->d_phased_ids[1], ctx->d_fast_ids[2], ctx->d_phased_ids[2], ctx->d_fast_ids[3], ctx->d_phased_ids[3],
                   ctx->d_fast_grouped[0], ctx->d_fast_grouped[1], ctx->d_fast_grouped[2], ctx->d_fast_grouped[3],
@@ -674,6 +677,11 @@ static int SetParamsImpl(t41rx_ctx *ctx, int first, int count, const t41rx_param
     if (new_fset >= 0) {
       int rc = UploadFset(ctx, new_fset);
       if (rc) return rc;
+    }
+    const StreamCfg &ncf = ctx->host.cfg[s];
+    if ((ncf.nr_kim || ncf.nr_spectral || ncf.nb_on) && !ctx->d_nr) {
+      CUDA_TRY(cudaMalloc(&ctx->d_nr, sizeof(NrState) * (size_t)ctx->n_streams));
+      CUDA_TRY(cudaMemset(ctx->d_nr, 0, sizeof(NrState) * (size_t)ctx->n_streams));
     }
     if (patch.set_rf_gain)
       CUDA_TRY(cudaMemcpy(&ctx->d_state[s].rf_gain, &patch.rf_gain, sizeof(int32_t), cudaMemcpyHostToDevice));
@@ -873,6 +881,8 @@ static int LaunchRange(t41rx_ctx *ctx, const void *iq_any, void *audio_any, bool
   a.eq_coeffs = ctx->d_eq_coeffs;
   a.cw_coeffs = ctx->d_cw_coeffs;
   a.sam_consts = ctx->d_sam;
+  a.nr = ctx->d_nr;
+  a.nr_tab = ctx->d_nr_tab;
   a.gradient = ctx->d_gradient;
   a.varicode = ctx->d_varicode;
   a.n_streams = count;
@@ -970,7 +980,9 @@ static int RefreshKernelLists(t41rx_ctx *ctx) {
     ctx->h_phased_ids[v].clear();
     for (int s = 0; s < ctx->n_streams; ++s) {
       const StreamCfg &cf = ctx->host.cfg[s];
-      const bool phased = (cf.mode == kModeSam && !(v & 2)) || (!(v & 1) && (cf.nr_lms || cf.anr_notch));
+      /* the 256-point spectral NR stages and the noise blanker only exist on the bit-exact chain */
+      const bool phased = (cf.mode == kModeSam && !(v & 2)) || (!(v & 1) && (cf.nr_lms || cf.anr_notch)) || cf.nr_kim ||
+                          cf.nr_spectral || cf.nb_on;
       (phased ? ctx->h_phased_ids[v] : ctx->h_fast_ids[v]).push_back(s);
     }
     if (!ctx->h_fast_ids[v].empty())

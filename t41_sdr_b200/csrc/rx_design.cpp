@@ -251,6 +251,34 @@ void DesignStreamCfg(const t41rx_params &p, const AgcConsts &agc, int filter_id,
   c->nr_lms = (p.nr_option == 3) ? 1 : 0;                            /* Process.cpp:852 */
   c->anr_notch = (p.anr_notch_on == 1) ? 1 : 0;                      /* Process.cpp:860 */
   c->cw_filter = (p.cw_receive == 1 && p.cw_filter_index != 5) ? p.cw_filter_index : -1;   /* Process.cpp:878-912 */
+  c->nr_kim = (p.nr_option == 1) ? 1 : 0;                            /* Process.cpp:845 */
+  c->nr_spectral = (p.nr_option == 2) ? 1 : 0;                       /* Process.cpp:850 */
+  c->nb_on = (p.nb_on != 0) ? 1 : 0;                                 /* Process.cpp:873 */
+  {
+    /* VAD_low / VAD_high (Noise.cpp:141-172 = :429-443,515-529): the bins between the filter cut-offs, bin width
+       (SampleRate / DF) / NR_FFT_L = 93.75 Hz; the reference keeps them in uint8_t */
+    float lf_freq, uf_freq;
+    if (p.f_lo_cut <= 0 && p.f_hi_cut >= 0) {
+      lf_freq = 0.0;
+      uf_freq = fmax(-(float)p.f_lo_cut, (float)p.f_hi_cut);
+    } else if (p.f_lo_cut > 0) {
+      lf_freq = (float)p.f_lo_cut;
+      uf_freq = (float)p.f_hi_cut;
+    } else {
+      uf_freq = -(float)p.f_lo_cut;
+      lf_freq = -(float)p.f_hi_cut;
+    }
+    lf_freq /= (((float)kFs / kDf) / 256);
+    uf_freq /= (((float)kFs / kDf) / 256);
+    uint8_t lo = (uint8_t)(int)lf_freq, hi = (uint8_t)(int)uf_freq;
+    if (lo == hi) hi++;
+    if (lo < 1) lo = 1;
+    else if (lo > 256 / 2 - 2) lo = 256 / 2 - 2;
+    if (hi < 1) hi = 1;
+    else if (hi > 256 / 2) hi = 256 / 2;
+    c->nr_vad_lo = lo;
+    c->nr_vad_hi = hi;
+  }
   for (int i = 0; i < 14; ++i) {                                     /* Filter.cpp:118-120,136-149 */
     const float level = (float)p.equalizer_rec[i] / 100.0;
     c->eq_scale[i] = (i & 1) ? level : -level;
@@ -317,7 +345,7 @@ int ValidateParams(const t41rx_params &p) {
   if (p.current_scale < 0 || p.current_scale > 4) return 0;
   if (p.f_hi_cut <= p.f_lo_cut) return 0;
   if (p.audio_volume < 0 || p.audio_volume > 100) return 0;
-  if (p.nr_option != 0 && p.nr_option != 3) return 0;         /* Kim (1) and spectral (2) noise reduction are not built */
+  if (p.nr_option < 0 || p.nr_option > 3) return 0;
   if (p.cw_filter_index < 0 || p.cw_filter_index > 5) return 0;
   return 1;
 }

@@ -36,6 +36,7 @@ void DefaultParams(t41rx_params *p) {
   p->anr_notch_on = 0;            /* ANR_notchOn */
   p->cw_receive = 0;              /* T41State = SSB_RECEIVE */
   p->cw_filter_index = 5;         /* CWFilterIndex: off (gwv.cpp) */
+  p->nb_on = 0;                   /* NB_on (Process.cpp:39) */
 }
 
 void HostStateInit(StreamState *st) {
@@ -89,6 +90,21 @@ void HostModel::Init(int n) {
     sam_consts[2] = 1.0 - exp(-2.0 * omegaN * zeta * 1 / 24000);
     sam_consts[3] = -sam_consts[2] +
                     2.0 * (1 - expf(-omegaN * zeta * 1 / 24000) * cosf(omegaN * 1 / 24000 * sqrtf(1.0 - zeta * zeta)));
+  }
+  {
+    /* tables of the spectral noise-reduction stages (rx_nr.cuh): the reference's own expressions, evaluated once with
+       the host's libm like the reference build evaluates them on every call */
+    nr_tab.assign(520, 0.0f);
+    const float tinc = 0.00533333, tax = 0.0239, tap = 0.05062, asnr = 20, pspri = 0.5;      /* Noise.cpp:396-403 */
+    const float xih1 = powf(10, (float)asnr / 10.0);
+    nr_tab[0] = expf(-tinc / tax);                                   /* ax */
+    nr_tab[1] = expf(-tinc / tap);                                   /* ap */
+    nr_tab[2] = 1.0 / (1.0 + xih1) - 1.0;                            /* xih1r */
+    nr_tab[3] = (1.0 / pspri - 1.0) * (1.0 + xih1);                  /* pfac */
+    nr_tab[4] = powf(10, -(float)20 / 20.0);                         /* snr_prio_min */
+    for (int idx = 0; idx < 256; ++idx)                              /* Noise.cpp:198-201 (PI is Arduino's double there) */
+      nr_tab[8 + idx] = 0.5 * (float)(1.0 - (cosf(3.1415926535897932384626433832795 * 2.0 * (float)idx / (float)((256) - 1))));
+    for (int idx = 0; idx < 256; ++idx) nr_tab[264 + idx] = t41rx_sqrt_hann[idx];
   }
   gradient.assign(t41rx_gradient, t41rx_gradient + 117);
   varicode.resize(128);

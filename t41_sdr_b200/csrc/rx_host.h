@@ -48,6 +48,7 @@ struct HostModel {
   std::vector<float> eq_coeffs;         /* 14 x 20 */
   std::vector<float> cw_coeffs;         /* 5 x 30 */
   std::vector<float> sam_consts;        /* 4 */
+  std::vector<float> nr_tab;            /* 520: constants, Kim's Hann window, sqrtHann (rx_nr.cuh) */
   std::vector<uint16_t> gradient;       /* 117 */
   std::vector<uint32_t> varicode;       /* 128 */
 

@@ -27,9 +27,11 @@
 
 #ifdef T41RX_HOST_EMUL
 #define T41RX_DEV inline
+#define T41RX_DEV_NOINLINE inline
 template <class T> inline T LdgRO(const T *p) { return *p; }
 #else
 #define T41RX_DEV __device__ __forceinline__
+#define T41RX_DEV_NOINLINE static __device__ __noinline__
 template <class T> __device__ __forceinline__ T LdgRO(const T *p) { return __ldg(p); }
 #endif
 
@@ -150,6 +152,10 @@ struct LaunchArgs {
        ser_out [n_blocks][256][n_streams]  demodulated audio sample */
   float4 *ser_in;
   float *ser_out;
+  /* spectral noise reduction / noise blanker (rx_nr.cuh): per-receiver state (NULL until a receiver uses a stage) and
+     the host-computed tables */
+  NrState *nr;
+  const float *nr_tab;
 };
 
 struct Cta {
@@ -2048,6 +2054,34 @@ T41RX_DEV void PhNrNotch(Cta &c, int tid) {
   if (cf.anr_notch) XanrPass(aud, s + vAnrD, s + vAnrW, st, true);   /* Process.cpp:860-865 */
 }
 
+}  // namespace t41rx
+#include "rx_nr.cuh"
+namespace t41rx {
+
+/* Kim / spectral noise reduction (Process.cpp:845-852), one lane per receiver; scratch over the equaliser's band
+   buffers (consumed by then; the LMS stage that follows re-stages its own data there) */
+constexpr int vNrBuf = vEqBand, vNrTmp = vNrBuf + 512, vNrOut = vNrTmp + 512, vNrPh = vNrOut + 256;
+static_assert(vNrPh + 128 <= 2 * kRawLen, "noise-reduction scratch fits the raw region");
+T41RX_DEV void PhNrSpectral(Cta &c, int tid) {
+  const int g = SerialStream(c, tid);
+  if (g < 0) return;
+  const int sid = Sid(c, g);
+  const StreamCfg &cf = c.a.cfg[sid];
+  if ((!cf.nr_kim && !cf.nr_spectral) || !c.a.nr) return;
+  float *s = Slot(c, g);
+  if (cf.nr_kim) KimNrLane(c.a.nr[sid], cf, c.a.nr_tab, c.a.twiddle, s + vAud + 23, s + vNrBuf, s + vNrTmp, s + vNrOut);
+  else SpectralNrLane(c.a.nr[sid], cf, c.a.nr_tab, c.a.twiddle, s + vAud + 23, s + vNrBuf, s + vNrTmp, s + vNrPh);
+}
+/* noise blanker (Process.cpp:873-876), behind the notch */
+T41RX_DEV void PhNoiseBlank(Cta &c, int tid) {
+  const int g = SerialStream(c, tid);
+  if (g < 0) return;
+  const int sid = Sid(c, g);
+  if (!c.a.cfg[sid].nb_on || !c.a.nr) return;
+  float *s = Slot(c, g);
+  NoiseBlankLane(c.a.nr[sid], s + vAud + 23, s + vNrBuf, s + vNrTmp);
+}
+
 /* CW audio low-pass (Process.cpp:878-914: CW receive state, CWFilterIndex 0..4): 6 transposed-direct-form-II
    biquads over the 256 samples at aud, arm_biquad_cascade_df2T_f32's operation order, all stages per sample in
    registers; st: the selected filter's 12 state values.  One lane. */
@@ -2694,9 +2728,11 @@ T41RX_DEV void PhSpecFrameWrite(Cta &c, int tid) {
   RX_PHASE(PhDemodSerial(c, tid));                                       \
   RX_PHASE(PhEqBands(c, tid));                                           \
   RX_PHASE(PhEqSum(c, tid));                                             \
+  RX_PHASE(PhNrSpectral(c, tid));                                        \
   RX_PHASE(PhNrStage(c, tid, 0));                                        \
   RX_PHASE(PhNrNotch(c, tid));                                           \
   RX_PHASE(PhNrStage(c, tid, 1));                                        \
+  RX_PHASE(PhNoiseBlank(c, tid));                                        \
   RX_PHASE(PhCwFilter(c, tid));                                          \
   RX_PHASE(PhInterp1b(c, tid));                                          \
   RX_PHASE(PhInterp2(c, tid));                                           \
@@ -2746,9 +2782,11 @@ T41RX_DEV void PhSpecFrameWrite(Cta &c, int tid) {
   RX_PHASE(PhBackLoad(c, tid));                                          \
   RX_PHASE(PhEqBands(c, tid));                                           \
   RX_PHASE(PhEqSum(c, tid));                                             \
+  RX_PHASE(PhNrSpectral(c, tid));                                        \
   RX_PHASE(PhNrStage(c, tid, 0));                                        \
   RX_PHASE(PhNrNotch(c, tid));                                           \
   RX_PHASE(PhNrStage(c, tid, 1));                                        \
+  RX_PHASE(PhNoiseBlank(c, tid));                                        \
   RX_PHASE(PhCwFilter(c, tid));                                          \
   RX_PHASE(PhInterp1b(c, tid));                                          \
   RX_PHASE(PhInterp2(c, tid));                                           \

@@ -64,6 +64,11 @@ struct StreamCfg {
   int32_t nr_lms;              /* nrOptionSelect == 3 (Process.cpp:852-856) */
   int32_t anr_notch;           /* ANR_notchOn == 1 (Process.cpp:860-865) */
   int32_t cw_filter;           /* CW audio low-pass 0..4 in the chain (T41State == CW_RECEIVE, CWFilterIndex != 5), else -1 */
+  int32_t nr_kim;              /* nrOptionSelect == 1: Kim1_NR, then x 30 (Process.cpp:845-849) */
+  int32_t nr_spectral;         /* nrOptionSelect == 2: SpectralNoiseReduction (Process.cpp:850-852) */
+  int32_t nb_on;               /* NB_on != 0: NoiseBlanker behind the notch (Process.cpp:873-876) */
+  int32_t nr_vad_lo, nr_vad_hi;/* VAD_low / VAD_high: the bins the spectral stages work on (Noise.cpp:141-172) */
+  int32_t pad_nr_;
   float eq_scale[14];          /* -/+ recEQ_LevelScale[i] = (float)equalizerRec[i] / 100.0, sign as Filter.cpp:136-149 */
   int32_t zoom_samples;        /* min(2048 >> zoom, 512), FFT.cpp:78-81 */
   int32_t nco_epoch;           /* bumped when NCOFreq changes: forces one exact block (amplitude transient) */
@@ -147,6 +152,20 @@ struct StreamState {
   /* CW audio low-passes: CW_AudioFilter1..5_state (CWProcessing.cpp:38-42), each filter keeps its own */
   float cw_state[5][12];
   int16_t audio_ypixel[kAudioSpecPixels + 2];
+};
+
+/* State of the 256-point spectral noise-reduction stages and the noise blanker (Noise.cpp:17-37,109-110,389-427,
+   DSP_Fn.cpp:143): one per receiver, in an array of its own that only exists once a receiver switches one of these
+   stages on.  All zero at start, like the reference's statics in the host build (spectral_stage = NR_first_time_2 - 1).
+   Kim1_NR and SpectralNoiseReduction share the first group of arrays, as they do in the reference. */
+struct NrState {
+  float last_sample[128], last_ifft[128];
+  float X[128][3], E[128][15], M[128], Nest[128][2], lambda[128], Gts[128][2], G[128];
+  float SNR_prio[128], SNR_post[128], Hk_old[128], long_tone_gain[128];
+  float pslp[128], xt[128];
+  uint32_t x_ptr, e_ptr;
+  int32_t spectral_stage, init_counter;
+  float nb_last_frame_end[80];
 };
 
 }  // namespace t41rx

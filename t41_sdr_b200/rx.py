@@ -43,7 +43,7 @@ class Params(C.Structure):
         ("iq_amp_correction", C.c_float), ("iq_phase_correction", C.c_float),
         ("receive_eq_flag", C.c_int32), ("equalizer_rec", C.c_int32 * 14),
         ("nr_option", C.c_int32), ("anr_notch_on", C.c_int32), ("cw_receive", C.c_int32),
-        ("cw_filter_index", C.c_int32)]
+        ("cw_filter_index", C.c_int32), ("nb_on", C.c_int32)]
 
     def copy(self):
         p = Params()

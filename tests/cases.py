@@ -208,8 +208,40 @@ def c8_cw_filters():
     return Case("c8_cw_filters", [(seg1, T1), (seg2, T2)], iqs, row_every=5)
 
 
+def _with_clicks(iq, every=4, first=3, amp=0.5):
+    """add a three-sample impulse to every `every`-th block (something for the noise blanker to find)"""
+    iq = iq.copy()
+    for t in range(first, iq.shape[0], every):
+        iq[t, 700:703, 0] += amp
+    return synth.to_q15_grid(iq)
+
+
+def c9_kim_spectral_nb():
+    """The 256-point spectral noise-reduction stages and the noise blanker (rest of SURVEY 8(f) rank 2): Kim1_NR
+    (Noise.cpp:108-311, then x 30), SpectralNoiseReduction (Noise.cpp:379-655: 10 blocks of training that pass the audio
+    through, then - the reference never sets its long-tone gain - signed zeros), NoiseBlanker (DSP_Fn.cpp:105-362) on
+    clicks; every mode, narrow and wide filters (the stages' bin ranges follow the cut-offs), combined with the notch,
+    the equaliser and each other, switched between the segments (Kim and spectral NR share their arrays)."""
+    T1, T2 = 14, 8
+    T = T1 + T2
+    tilt = [100, 80, 0, 120, 55, 100, 30, 90, 100, 10, 70, 100, 45, 100]
+    iqs = [synth.tone(930, T, 1000.0), synth.tone(931, T, -1200.0, mode=LSB), _with_clicks(synth.am(932, T)),
+           synth.nfm(933, T), _with_clicks(synth.am(934, T, mode=SAM, carrier_offset=50.0)), synth.tone(935, T, 500.0),
+           _with_clicks(synth.two_tone(936, T, 46800.0, 48100.0)), synth.tone(937, T, 700.0),
+           _with_clicks(synth.tone(938, T, 900.0), every=1, first=0)]
+    seg1 = [P(mode=USB, nr_option=1), P(mode=LSB, nr_option=2), P(mode=AM, nb_on=1), P(mode=NFM, agc_mode=3, nr_option=1),
+            P(mode=SAM, agc_mode=4, nr_option=1, nb_on=1), P(mode=PSK31, nr_option=1, nb_on=1),
+            _eq(P(mode=USB, nr_option=2, anr_notch_on=1, nb_on=1), tilt), P(mode=USB, f_lo_cut=-100, f_hi_cut=100, nr_option=1),
+            P(mode=USB, nb_on=1, agc_mode=0)]
+    seg2 = [P(mode=USB, nr_option=2), P(mode=LSB, nr_option=1), P(mode=AM, nr_option=1, nb_on=1), P(mode=NFM, agc_mode=3),
+            P(mode=SAM, agc_mode=4, nr_option=2), P(mode=PSK31), P(mode=USB, nr_option=1, anr_notch_on=1),
+            P(mode=USB, f_lo_cut=300, f_hi_cut=3000, nr_option=1), P(mode=USB, nb_on=1, nr_option=3)]
+    return Case("c9_kim_spectral_nb", [(seg1, T1), (seg2, T2)], iqs, row_every=5)
+
+
 ALL_CASES = [c1_single_usb, c1_single_usb_agc_off, c2_ssb_am_mix, c3_nfm_sam_agc, c4_zoom_rows, c5_psk31,
-             edge_silence_fullscale, edge_param_changes, edge_rf_gain_ramp, c6_receive_eq, c7_lms_notch, c8_cw_filters]
+             edge_silence_fullscale, edge_param_changes, edge_rf_gain_ramp, c6_receive_eq, c7_lms_notch, c8_cw_filters,
+             c9_kim_spectral_nb]
 
 
 def run_case_on(case, make_stream):

@@ -30,6 +30,7 @@ struct Emul {
   float *bind_max_ave = nullptr;
   uint8_t *bind_spec_frames = nullptr, *bind_audio_frames = nullptr;
   std::vector<float2> aspec;
+  std::vector<NrState> nr;
 };
 
 extern "C" {
@@ -40,6 +41,8 @@ Emul *emul_create(int n_streams) {
   e->state.resize(n_streams);
   for (int s = 0; s < n_streams; ++s) HostStateInit(&e->state[s]);
   e->smem.assign(kSmemFloats + 64, 0.0f);
+  e->nr.resize(n_streams);
+  memset(e->nr.data(), 0, sizeof(NrState) * n_streams);
   return e;
 }
 
@@ -84,6 +87,8 @@ int emul_process(Emul *e, const float *iq, float *audio, int n_blocks, int row_e
   a.eq_coeffs = h.eq_coeffs.data();
   a.cw_coeffs = h.cw_coeffs.data();
   a.sam_consts = h.sam_consts.data();
+  a.nr = e->nr.data();
+  a.nr_tab = h.nr_tab.data();
   a.gradient = h.gradient.data();
   a.varicode = h.varicode.data();
   a.n_streams = h.n_streams;

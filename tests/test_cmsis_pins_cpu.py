@@ -216,3 +216,23 @@ def test_elementwise_and_reductions(lib):
     idx = C.c_uint32()
     lib.arm_max_f32(_p(a), 256, C.byref(r), C.byref(idx))
     assert r.value == a.max() and idx.value == int(np.argmax(a))
+
+
+def test_cfft256_matches_numpy(lib):
+    """the 256-point instance the noise-reduction stages use (Noise.cpp:206,279,454,636); the 512-point one is pinned in
+    test_oracle_cpu.py"""
+    class CfftInst(C.Structure):
+        _fields_ = [("fftLen", C.c_uint16), ("pTwiddle", F32P), ("pBitRevTable", C.POINTER(C.c_uint16)),
+                    ("bitRevLength", C.c_uint16)]
+    inst = CfftInst.in_dll(lib, "arm_cfft_sR_f32_len256")
+    assert inst.fftLen == 256
+    rng = np.random.default_rng(12)
+    x = rng.standard_normal(256) + 1j * rng.standard_normal(256)
+    buf = np.empty(512, np.float32)
+    buf[0::2], buf[1::2] = x.real, x.imag
+    orig = buf.copy()
+    lib.arm_cfft_f32(C.byref(inst), _p(buf), 0, 1)
+    want = np.fft.fft(orig[0::2].astype(np.float64) + 1j * orig[1::2].astype(np.float64))
+    assert np.abs((buf[0::2] + 1j * buf[1::2]) - want).max() / np.abs(want).max() < 1e-6
+    lib.arm_cfft_f32(C.byref(inst), _p(buf), 1, 1)
+    assert np.abs(buf - orig).max() < 2e-6

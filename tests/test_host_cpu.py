@@ -43,7 +43,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_params_struct_layout_is_shared():
-    assert C.sizeof(rx.Params) == C.sizeof(O.Params) == (18 + 1 + 14 + 2 + 2) * 4
+    assert C.sizeof(rx.Params) == C.sizeof(O.Params) == (18 + 1 + 14 + 2 + 2 + 1) * 4
     assert [f[0] for f in rx.Params._fields_] == [f[0] for f in O.Params._fields_]
     a, b = rx.default_params(), O.default_params()
     assert bytes(a) == bytes(b)
@@ -101,7 +101,7 @@ def test_no_gpu_means_failure_not_fallback():
 
 
 # ---- kernel phase logic on the host (development aid, see tests/devtools/kernel_emul.cpp) ----
-EMUL_CASES = [cases.c1_single_usb_agc_off, cases.c2_ssb_am_mix, cases.c3_nfm_sam_agc, cases.c4_zoom_rows, cases.c6_receive_eq, cases.c7_lms_notch, cases.c8_cw_filters,
+EMUL_CASES = [cases.c1_single_usb_agc_off, cases.c2_ssb_am_mix, cases.c3_nfm_sam_agc, cases.c4_zoom_rows, cases.c6_receive_eq, cases.c7_lms_notch, cases.c8_cw_filters, cases.c9_kim_spectral_nb,
               cases.edge_silence_fullscale, cases.edge_param_changes]
 
 
