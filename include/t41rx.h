@@ -270,6 +270,10 @@ int32_t t41rx_smeter_bar(float dbm);
 /* Instrumentation for bench.py: kernels launched by this context so far, and the CUDA-event
  * duration (ms) of all kernels of the most recent t41rx_process[_device] call (valid after t41rx_synchronize). */
 int64_t t41rx_kernel_launches(const t41rx_ctx *ctx);
+/* Bit-exact chain and rows kernel, current device: how many blocks had to re-run their input conditioning serially
+ * because a time-parallel chunk's speculative start state differed from the true one in the last bit (the result is
+ * exact either way; this only costs time).  -1 on a CUDA error. */
+int64_t t41rx_dc_refilter_count(void);
 int t41rx_last_kernel_ms(t41rx_ctx *ctx, float *ms);
 /* CUDA-event durations (ms) of the most recent launches (oldest first, at most 32) of the dominant kernel,
  * t41rx_stream_rx_kernel; returns how many were written, or a negative error code. */

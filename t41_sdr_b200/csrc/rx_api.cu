@@ -44,6 +44,8 @@ __global__ void __launch_bounds__(kNT, 8 / kG) t41rx_fused_rx_kernel(const Launc
   c.row_idx = 0;
   c.rows_only = 0;
   const int tid = threadIdx.x;
+  PhCtaInit(c, tid);
+  __syncthreads();
   PhStateIn(c, tid);
   __syncthreads();
   for (int t = 0; t < a.n_blocks; ++t) {
@@ -99,6 +101,8 @@ __global__ void __launch_bounds__(kNT, 8 / kG) t41rx_exact_front_kernel(const La
   c.row_idx = 0;
   c.rows_only = 0;
   const int tid = threadIdx.x;
+  PhCtaInit(c, tid);
+  __syncthreads();
   PhStateIn(c, tid);
   __syncthreads();
   for (int t = 0; t < a.n_blocks; ++t) {
@@ -253,6 +257,8 @@ __global__ void __launch_bounds__(kNT, 8 / kG) t41rx_exact_back_kernel(const Lau
   c.row_idx = 0;
   c.rows_only = 0;
   const int tid = threadIdx.x;
+  PhCtaInit(c, tid);
+  __syncthreads();
   PhBackStateIn(c, tid);
   __syncthreads();
   for (int t = 0; t < a.n_blocks; ++t) {
@@ -276,6 +282,8 @@ __global__ void __launch_bounds__(kNT, 8 / kG) t41rx_rows_kernel(const LaunchArg
   c.row = 1;
   c.rows_only = 1;
   const int tid = threadIdx.x;
+  PhCtaInit(c, tid);
+  __syncthreads();
   /* the row-producing blocks of this launch: absolute index a multiple of row_every */
   for (int t = (a.row_every - a.t0 % a.row_every) % a.row_every; t < a.n_blocks; t += a.row_every) {
     c.t = t;
@@ -323,6 +331,8 @@ __global__ void __launch_bounds__(kNT) t41rx_row_byproducts_kernel(const LaunchA
   c.row = 1;
   c.rows_only = 1;
   const int tid = threadIdx.x;
+  PhCtaInit(c, tid);
+  __syncthreads();
   /* the rows of this launch's blocks t0 .. t0 + n_blocks - 1 */
   for (int r = (a.t0 + a.row_every - 1) / a.row_every; r < a.n_rows && r * a.row_every < a.t0 + a.n_blocks; ++r) {
     c.t = r * a.row_every - a.t0;
@@ -1231,6 +1241,12 @@ int t41rx_debug_phase_cycles(unsigned long long *out128, int reset) {
 #endif
 
 int64_t t41rx_kernel_launches(const t41rx_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int64_t t41rx_dc_refilter_count(void) {
+  unsigned long long v = 0;
+  if (cudaMemcpyFromSymbol(&v, g_dc_refilter_count, sizeof(v)) != cudaSuccess) return -1;
+  return (int64_t)v;
+}
 
 int t41rx_stream_kernel_times(t41rx_ctx *ctx, float *ms, int max_n) {
   if (!ctx || !ms || max_n <= 0) return Fail(T41RX_EINVAL, "t41rx_stream_kernel_times: bad arguments%s");

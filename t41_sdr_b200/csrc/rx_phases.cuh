@@ -51,9 +51,16 @@ namespace t41rx {
 #endif
 constexpr int kG = T41RX_G;           /* receivers per CTA */
 constexpr int kNT = 64 * kG;          /* threads per CTA: 64 per receiver in the FFT phases */
-constexpr int kDcChunks = 32;         /* time-parallel chunks of the 4096-step DC-block chain: one warp per receiver */
-constexpr int kDcChunkLen = 129;      /* chunk c starts at c*129 (odd stride: the 32 lanes hit 32 different banks) */
-constexpr int kDcWarm = 256;          /* speculative warm-up length (a1 = 0.854: 0.854^256 ~ 3e-18) */
+constexpr int kDcChunks = 64;         /* time-parallel chunks of the 4096-step DC-block chain: both warps of a receiver */
+constexpr int kDcChunkLen = 65;       /* chunk c starts at c*65 (odd stride: the lanes of a warp hit 32 different banks) */
+#ifndef T41RX_DC_SPEC_WARM
+#define T41RX_DC_SPEC_WARM 192
+#endif
+constexpr int kDcSpecWarm = T41RX_DC_SPEC_WARM;      /* warm-up of a chunk's speculative start state (a1 = 0.854: 0.854^192 ~ 7e-14, a
+                                         millionth of a float's last place; every start state is VERIFIED bit for bit
+                                         against the previous chunk's end state and redone serially on a mismatch) */
+constexpr int kDcWarm = 256;          /* warm-up where nothing can verify it (the rows-only kernel's block-start state):
+                                         0.854^256 ~ 3e-18 */
 static_assert(kDcChunks * kDcChunkLen >= 2 * kBlock && (kDcChunks - 1) * kDcChunkLen < 2 * kBlock, "chunking");
 
 /* ---- shared-memory slot layout, in floats ---- */
@@ -104,7 +111,11 @@ static_assert(vEqBand + 12 * kDec <= 2 * kRawLen, "equaliser bands fit the raw r
 constexpr int vSpecFft = oD1I;                    /* 512 complex = 1024 floats <= 1120 */
 
 /* misc scalar indices */
-enum { mDcD1 = 0, mDcD2 = 1, mNcoMode = 2, mDcBad = 3, mDcSpec = 4 /* 32 x 2 */, mDcEnd = 68 /* 32 x 2 */ };
+enum { mDcD1 = 0, mDcD2 = 1, mNcoMode = 2, mDcBad = 3, mSid = 4 /* int: the receiver this slot serves */ };
+/* the chunks' speculative start states and end states, 64 x 2 each, during the DC phases only: the dec1 output region
+   (its history is restored by PhDec1, the spectrum scratch of a row block is written after PhDcFix) */
+constexpr int vDcSpec = oD1I, vDcEnd = oD1I + 2 * kDcChunks;
+static_assert(4 * kDcChunks <= kD1Len, "DC chunk states fit the dec1 region");
 
 struct LaunchArgs {
   const float *iq;
@@ -171,7 +182,17 @@ struct Cta {
 
 T41RX_DEV float *Slot(const Cta &c, int g) { return c.smem + g * kSlot; }
 /* receiver index of slot g of this CTA */
-T41RX_DEV int Sid(const Cta &c, int g) { return c.a.stream_ids ? LdgRO(c.a.stream_ids + c.s0 + g) : c.a.stream_base + c.s0 + g; }
+/* (a launch over an id list keeps the ids in the slots, PhCtaInit: with next to no L1 beside the shared memory a look-up
+   in the list is a trip to L2, and the phases ask thousands of times per block; a contiguous range is plain arithmetic) */
+T41RX_DEV int Sid(const Cta &c, int g) {
+  return c.a.stream_ids ? reinterpret_cast<const int *>(c.smem + g * kSlot)[oMisc + mSid] : c.a.stream_base + c.s0 + g;
+}
+/* first thing every kernel of this file does, followed by a barrier */
+T41RX_DEV void PhCtaInit(Cta &c, int tid) {
+  if (tid < c.ng)
+    reinterpret_cast<int *>(c.smem + tid * kSlot)[oMisc + mSid] =
+        c.a.stream_ids ? LdgRO(c.a.stream_ids + c.s0 + tid) : c.a.stream_base + c.s0 + tid;
+}
 
 /* one word of a receiver's I/Q (float index `w` inside the [receiver][block][2048][2] array, block-relative base
    already applied): the float buffer, or arm_q15_to_float of the q15 one (x / 32768, exact) */
@@ -444,58 +465,70 @@ T41RX_DEV void PhLoad(Cta &c, int tid) {
  * so that the shared-memory latency is off the recurrence's critical path. */
 struct DcPost { float rfg; float rfgain; float neg_iq_amp; bool mirrored; };
 
+/* n consecutive samples at x (one channel's part of the sequence: no address arithmetic per sample).  second: the
+   I channel's extra factor -IQAmp in the mirrored modes */
 template <bool kStore>
-T41RX_DEV void DcRun(float *s, const DcPost p, int begin, int end, float &d1_io, float &d2_io) {
+T41RX_DEV void DcSegment(float *x, int n, const DcCoef &k, const DcPost &p, bool second, float &d1, float &lx, float &ly) {
   constexpr int kB = 8;
-  const DcCoef k = DcCoefs();
-  float d1 = d1_io;
-  float lx = 0.0f, ly = 0.0f;          /* last (scaled) input and output: define d2 */
-  bool any = false;
-  int i = begin;
-  const int n_batches = (end - begin) / kB;
+  const int n_batches = n / kB;
   float cur[kB], nxt[kB];
   if (n_batches > 0) {
 #pragma unroll
-    for (int j = 0; j < kB; ++j) cur[j] = s[SeqOff(i + j)];
+    for (int j = 0; j < kB; ++j) cur[j] = x[j];
   }
+  int i = 0;
   for (int bt = 0; bt < n_batches; ++bt) {
     /* software pipeline: the next batch is in flight while this one runs from registers */
     if (bt + 1 < n_batches) {
 #pragma unroll
-      for (int j = 0; j < kB; ++j) nxt[j] = s[SeqOff(i + kB + j)];
+      for (int j = 0; j < kB; ++j) nxt[j] = x[i + kB + j];
     }
 #pragma unroll
     for (int j = 0; j < kB; ++j) {
-      const float x = cur[j] * p.rfg;
-      float y = DcStep(k, x, d1);
-      lx = x;
+      const float v = cur[j] * p.rfg;
+      float y = DcStep(k, v, d1);
+      lx = v;
       ly = y;
       if (kStore) {
         y = y * p.rfgain;
-        if (p.mirrored && (i + j) < kBlock) y = y * p.neg_iq_amp;
-        s[SeqOff(i + j)] = y;
+        if (second) y = y * p.neg_iq_amp;
+        x[i + j] = y;
       }
     }
 #pragma unroll
     for (int j = 0; j < kB; ++j) cur[j] = nxt[j];
     i += kB;
-    any = true;
   }
-  for (; i < end; ++i) {
-    const int off = SeqOff(i);
-    const float x = s[off] * p.rfg;
-    float y = DcStep(k, x, d1);
-    lx = x;
+  for (; i < n; ++i) {
+    const float v = x[i] * p.rfg;
+    float y = DcStep(k, v, d1);
+    lx = v;
     ly = y;
-    any = true;
     if (kStore) {
       y = y * p.rfgain;
-      if (p.mirrored && i < kBlock) y = y * p.neg_iq_amp;
-      s[off] = y;
+      if (second) y = y * p.neg_iq_amp;
+      x[i] = y;
     }
   }
+}
+
+template <bool kStore>
+T41RX_DEV void DcRun(float *s, const DcPost p, int begin, int end, float &d1_io, float &d2_io) {
+  const DcCoef k = DcCoefs();
+  float d1 = d1_io;
+  float lx = 0.0f, ly = 0.0f;          /* last (scaled) input and output: define d2 */
+  /* the sequence is the I block, then the Q block (B6): at most one piece of each */
+  const int i_end = end < kBlock ? end : kBlock, q_begin = begin > kBlock ? begin : kBlock;
+#ifndef T41RX_HOST_EMUL
+#pragma unroll 1                          /* one copy of the loop body: two would spill (and a spill is an L2 access here) */
+#endif
+  for (int seg = 0; seg < 2; ++seg) {
+    float *x = seg ? s + oRawQ + 27 + (q_begin - kBlock) : s + oRawI + 27 + begin;
+    const int n = seg ? end - q_begin : i_end - begin;
+    if (n > 0) DcSegment<kStore>(x, n, k, p, seg == 0 && p.mirrored, d1, lx, ly);
+  }
   d1_io = d1;
-  if (any) d2_io = DcD2(lx, ly);
+  if (end > begin) d2_io = DcD2(lx, ly);
 }
 
 /* RFgain in force while block t of the launch is processed, from the values at launch start: Codec_gain
@@ -524,7 +557,7 @@ T41RX_DEV void PhDcWarm(Cta &c, int tid) {
     return;
   }
   const DcPost p = DcPostOf(c, g);
-  int start = ch * kDcChunkLen - kDcWarm;
+  int start = ch * kDcChunkLen - kDcSpecWarm;
   float d1 = 0.0f, d2 = 0.0f;
   if (start <= 0) {            /* the warm-up would reach before the block: start from the carried state instead */
     start = 0;
@@ -532,8 +565,8 @@ T41RX_DEV void PhDcWarm(Cta &c, int tid) {
     d2 = s[oMisc + mDcD2];
   }
   DcRun<false>(s, p, start, ch * kDcChunkLen, d1, d2);
-  s[oMisc + mDcSpec + 2 * ch] = d1;
-  s[oMisc + mDcSpec + 2 * ch + 1] = d2;
+  s[vDcSpec + 2 * ch] = d1;
+  s[vDcSpec + 2 * ch + 1] = d2;
 }
 
 T41RX_DEV void PhDcMain(Cta &c, int tid) {
@@ -546,16 +579,20 @@ T41RX_DEV void PhDcMain(Cta &c, int tid) {
     d1 = s[oMisc + mDcD1];
     d2 = s[oMisc + mDcD2];
   } else {
-    d1 = s[oMisc + mDcSpec + 2 * ch];
-    d2 = s[oMisc + mDcSpec + 2 * ch + 1];
+    d1 = s[vDcSpec + 2 * ch];
+    d2 = s[vDcSpec + 2 * ch + 1];
   }
   const int begin = ch * kDcChunkLen;
   const int end = (ch == kDcChunks - 1) ? 2 * kBlock : begin + kDcChunkLen;
   DcRun<true>(s, p, begin, end, d1, d2);
-  s[oMisc + mDcEnd + 2 * ch] = d1;
-  s[oMisc + mDcEnd + 2 * ch + 1] = d2;
+  s[vDcEnd + 2 * ch] = d1;
+  s[vDcEnd + 2 * ch + 1] = d2;
 }
 
+#ifndef T41RX_HOST_EMUL
+/* how often a chunk's speculative start state missed (instrumentation: t41rx_dc_refilter_count) */
+static __device__ unsigned long long g_dc_refilter_count;
+#endif
 T41RX_DEV bool SameBits(float a, float b) {
   union { float f; uint32_t u; } x, y;
   x.f = a;
@@ -570,13 +607,13 @@ T41RX_DEV void PhDcVerify(Cta &c, int tid) {
   const int g = tid / kDcChunks, ch = tid % kDcChunks;
   float *s = Slot(c, g);
   if (ch > 0) {
-    if (!SameBits(s[oMisc + mDcSpec + 2 * ch], s[oMisc + mDcEnd + 2 * (ch - 1)]) ||
-        !SameBits(s[oMisc + mDcSpec + 2 * ch + 1], s[oMisc + mDcEnd + 2 * (ch - 1) + 1]))
+    if (!SameBits(s[vDcSpec + 2 * ch], s[vDcEnd + 2 * (ch - 1)]) ||
+        !SameBits(s[vDcSpec + 2 * ch + 1], s[vDcEnd + 2 * (ch - 1) + 1]))
       s[oMisc + mDcBad] = 1.0f;           /* several lanes may store the same value: benign */
   }
   if (ch == kDcChunks - 1) {
-    s[oMisc + mDcD1] = s[oMisc + mDcEnd + 2 * ch];
-    s[oMisc + mDcD2] = s[oMisc + mDcEnd + 2 * ch + 1];
+    s[oMisc + mDcD1] = s[vDcEnd + 2 * ch];
+    s[oMisc + mDcD2] = s[vDcEnd + 2 * ch + 1];
   }
 }
 
@@ -590,14 +627,17 @@ T41RX_DEV void PhDcFix(Cta &c, int tid) {
   const DcPost p = DcPostOf(c, g);
   int bad = 1;
   for (; bad < kDcChunks; ++bad) {
-    if (!SameBits(s[oMisc + mDcSpec + 2 * bad], s[oMisc + mDcEnd + 2 * (bad - 1)]) ||
-        !SameBits(s[oMisc + mDcSpec + 2 * bad + 1], s[oMisc + mDcEnd + 2 * (bad - 1) + 1]))
+    if (!SameBits(s[vDcSpec + 2 * bad], s[vDcEnd + 2 * (bad - 1)]) ||
+        !SameBits(s[vDcSpec + 2 * bad + 1], s[vDcEnd + 2 * (bad - 1) + 1]))
       break;
   }
   if (bad >= kDcChunks) return;
+#ifndef T41RX_HOST_EMUL
+  atomicAdd(&g_dc_refilter_count, 1ull);
+#endif
   const size_t src = ((size_t)(Sid(c, g)) * c.a.t_stride + c.t) * (2 * kBlock);
-  float d1 = s[oMisc + mDcEnd + 2 * (bad - 1)];
-  float d2 = s[oMisc + mDcEnd + 2 * (bad - 1) + 1];
+  float d1 = s[vDcEnd + 2 * (bad - 1)];
+  float d2 = s[vDcEnd + 2 * (bad - 1) + 1];
   for (int i = bad * kDcChunkLen; i < 2 * kBlock; ++i)
     s[SeqOff(i)] = IqWord(c.a, src + (i < kBlock ? 2 * i : 2 * (i - kBlock) + 1));
   DcRun<true>(s, p, bad * kDcChunkLen, 2 * kBlock, d1, d2);

@@ -88,7 +88,7 @@ EXPORTS = (
     "t41rx_create_multi", "t41rx_destroy_multi", "t41rx_multi_num_devices", "t41rx_multi_num_streams", "t41rx_multi_shard",
     "t41rx_multi_set_params", "t41rx_multi_set_params_each", "t41rx_multi_get_debug", "t41rx_multi_process",
     "t41rx_multi_process_q15", "t41rx_multi_process_device", "t41rx_multi_synchronize", "t41rx_multi_gather_rows",
-    "t41rx_multi_last_error")
+    "t41rx_multi_last_error", "t41rx_dc_refilter_count")
 
 
 def build_library():
@@ -155,6 +155,7 @@ def lib():
         L.t41rx_multi_synchronize.argtypes = [vp]
         L.t41rx_multi_gather_rows.argtypes = [vp, C.POINTER(vp), C.c_size_t, vp, C.POINTER(ip)]
         L.t41rx_multi_last_error.restype = C.c_char_p
+        L.t41rx_dc_refilter_count.restype = C.c_int64
         _lib = L
     return _lib
 

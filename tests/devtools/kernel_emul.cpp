@@ -135,6 +135,7 @@ int emul_process(Emul *e, const float *iq, float *audio, int n_blocks, int row_e
       c.row_idx = 0;
       c.rows_only = 0;
       for (int i = 0; i < kSmemFloats; ++i) smem[i] = NAN;
+      for (int tid = 0; tid < kNT; ++tid) PhCtaInit(c, tid);
       return c;
     };
     for (int cta = 0; cta < grid; ++cta) {          /* t41rx_exact_front_kernel */
@@ -172,6 +173,7 @@ int emul_process(Emul *e, const float *iq, float *audio, int n_blocks, int row_e
     c.rows_only = 0;
     /* poison: shared memory is uninitialised at CTA start on the GPU */
     for (int i = 0; i < kSmemFloats; ++i) smem[i] = NAN;
+    for (int tid = 0; tid < kNT; ++tid) PhCtaInit(c, tid);
 #define EMUL_PHASE(stmt) \
   do {                   \
     for (int tid = 0; tid < kNT; ++tid) { stmt; } \
@@ -189,6 +191,7 @@ int emul_process(Emul *e, const float *iq, float *audio, int n_blocks, int row_e
       }
       c.rows_only = 0;
       for (int i = 0; i < kSmemFloats; ++i) smem[i] = NAN;
+      for (int tid = 0; tid < kNT; ++tid) PhCtaInit(c, tid);
     }
     if (!split_exact) {
       EMUL_PHASE(PhStateIn(c, tid));
@@ -205,6 +208,7 @@ int emul_process(Emul *e, const float *iq, float *audio, int n_blocks, int row_e
       c.row = 1;
       c.rows_only = 1;
       for (int i = 0; i < kSmemFloats; ++i) smem[i] = NAN;
+      for (int tid = 0; tid < kNT; ++tid) PhCtaInit(c, tid);
       for (int r = 0; r < a.n_rows; ++r) {
         c.t = r * row_every;
         c.row_idx = r;
