@@ -2439,6 +2439,7 @@ T41RX_DEV void PhZoomIirPipe(Cta &c, int tid) {
   const StreamCfg &cf = c.a.cfg[Sid(c, gg)];
   StreamState &st = c.a.st[Sid(c, gg)];
   const bool active = have && cf.zoom != 0;
+  if (!__any_sync(0xffffffffu, active)) return;       /* every receiver of the CTA at zoom x1: no cascade (CalcZoom1Magn) */
   const int chn = (lane >> 2) & 1, sg = lane & 3;
   float *x = Slot(c, gg) + (chn ? oRawQ : oRawI) + 27;
   float b0 = 0, b1 = 0, b2 = 0, a1 = 0, a2 = 0, x1 = 0, x2 = 0, y1 = 0, y2 = 0;
