@@ -39,13 +39,13 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one t41rx_stream_rx_kernel launch of this workload from the
-# committed `ncu --set full` capture (profiles/summary_r01_final.md: 1078.9 MB read + 501.2 MB written at 1024
+# committed `ncu --set full` capture (profiles/summary_r02.md: 1078.8 MB read + 500.8 MB written at 1024
 # receivers x 64 blocks; the algorithmic figure is 1610.6 MB, part of the last audio blocks is still in L2 at
 # kernel end); only meaningful for the default workload, None otherwise
-TRAFFIC_BYTES_PER_LAUNCH = 1078915000 + 501194752
+TRAFFIC_BYTES_PER_LAUNCH = 1078842000 + 500761344
 # smsp__inst_executed.sum / stream-blocks of the same capture: warp-instructions the stream kernel executes per
-# 2048-sample block of one receiver (the chain is bound by FP32 issue slots, not by HBM: DESIGN.md section 3.5)
-WARP_INSTR_PER_STREAM_BLOCK = 7975
+# 2048-sample block of one receiver (profiles/summary_r02.md section 3)
+WARP_INSTR_PER_STREAM_BLOCK = 7931
 N_SMS, ISSUE_SLOTS_PER_SM = 148, 4
 
 METRIC = "aggregate IQ Msamples/s (full RX chain)"
@@ -294,7 +294,21 @@ def bind_to_gpu_numa_node(local):
         bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
         node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip())
         if node < 0:
-            return {"numa_node": None, "note": "the platform reports no NUMA node for %s" % bdf}
+            # no NUMA node in sysfs (a VM / container often hides it): ask NVML which CPUs are close to the GPU
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                h = pynvml.nvmlDeviceGetHandleByPciBusId(bdf.encode())
+                words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+                ideal = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+                allowed = os.sched_getaffinity(0)
+                use = ideal & allowed
+                if use and use != allowed:
+                    os.sched_setaffinity(0, use)
+                return {"numa_node": None, "source": "nvml", "gpu_local_cpus": len(ideal), "allowed_cpus": len(allowed),
+                        "bound_to": len(use) if use else 0, "pci": bdf}
+            except Exception as e:     # noqa: BLE001 - diagnostic only
+                return {"numa_node": None, "note": "no NUMA node for %s in sysfs; NVML: %s: %s" % (bdf, type(e).__name__, e)}
         cpus = set()
         for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
             lo, _, hi = part.partition("-")
