@@ -552,6 +552,7 @@ void t41rx_destroy(t41rx_ctx *ctx) {
   if (ctx->ext_pending && ctx->ev_ext) cudaEventSynchronize(ctx->ev_ext);
   if (ctx->copy_in) cudaStreamSynchronize(ctx->copy_in);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->aux) cudaStreamSynchronize(ctx->aux);
   if (ctx->copy_out) cudaStreamSynchronize(ctx->copy_out);
   void *bufs[] = {ctx->d_cfg, ctx->d_state, ctx->d_fsets, ctx->d_nco_tab, ctx->d_twiddle, ctx->d_hann, ctx->d_sin,
                   ctx->d_zoom_iir, ctx->d_eq_coeffs, ctx->d_cw_coeffs, ctx->d_sam, ctx->d_nr_tab, ctx->d_nr, ctx->d_gradient, ctx->d_varicode, ctx->d_iq, ctx->d_audio,
@@ -1213,6 +1214,7 @@ static int ProcessHost(t41rx_ctx *ctx, const float *iq, float *audio, const int1
   if (rc) {                                        /* keep the first error's text */
     cudaStreamSynchronize(ctx->copy_in);
     cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->aux);
     cudaStreamSynchronize(ctx->copy_out);
   }
   return rc;
