@@ -235,3 +235,34 @@ def test_bench_reference_arm_prints_one_json_line():
     assert line["impl"] == "reference" and line["value"] > 0 and line["unit"] == "Msamples/s"
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_filter_set_slots_are_reused_in_a_tuning_sweep():
+    """A long sweep of filter cut-offs on one receiver (HostModel::Apply re-uses the slot nobody references any more instead
+    of growing the table, rx_host.cpp) must leave exactly the tables a fresh design of the last setting has (the AGC
+    block keeps the sticky hang_thresh of its own history, B12: compared separately on equal AGC sequences)."""
+    seq = [cases.P(mode=cases.USB, f_lo_cut=200 + 10 * k, f_hi_cut=2400 + 25 * k) for k in range(40)]
+    seq += [cases.P(mode=cases.NFM, nfm_filter_bw=9000 + 500 * k) for k in range(6)]
+    seq += [cases.P(mode=cases.LSB, f_lo_cut=-2900, f_hi_cut=-150)]
+    swept = rx.design_tables([rx_driver.to_rx_params(p) for p in seq])
+    fresh = rx.design_tables([rx_driver.to_rx_params(seq[-1])])
+    for k in ("dec1", "dec2", "int1", "int2", "mask", "am_lp", "zoom_fir"):
+        assert np.array_equal(np.asarray(swept[k]).view(np.uint32), np.asarray(fresh[k]).view(np.uint32)), k
+    # NFM re-designs the decimators with its own cut-off (B15): the sweep went through NFM, the fresh receiver did not,
+    # and both end on the LSB design: equal above means the re-used slots really were re-designed
+
+
+def test_bench_workloads_are_valid_product_parameters():
+    """bench.py builds C2 - C5 through the product's own C-ABI (no oracle library in the GPU arm): every parameter set must
+    pass the library's validation, and the receiver counts / shapes are BASELINE.json's."""
+    import bench
+    for name, n in (("c2", 16), ("c3", 16), ("c4", 5), ("c5", 4)):
+        params, sigs = bench.workload(2, name)
+        assert len(params) == len(sigs) == n
+        for p, s in zip(params, sigs):
+            assert isinstance(p, rx.Params)
+            rx.design_tables([p])                         # raises on an invalid parameter set
+            assert s.shape == (2, 2048, 2) and s.dtype == np.float32
+    assert bench.EXTRA_CONFIGS["c3"][0] == 8192 and bench.EXTRA_CONFIGS["c4"][0] == 16384 and bench.EXTRA_CONFIGS["c5"][0] == 32768
+    assert {p.mode for p in bench.workload(2, "c3")[0]} == {3, 8}           # NFM + SAM
+    assert sorted({p.spectrum_zoom for p in bench.workload(2, "c4")[0]}) == [0, 1, 2, 3, 4]
