@@ -465,11 +465,14 @@ T41RX_DEV void PhLoad(Cta &c, int tid) {
  * so that the shared-memory latency is off the recurrence's critical path. */
 struct DcPost { float rfg; float rfgain; float neg_iq_amp; bool mirrored; };
 
+#ifndef T41RX_DC_BATCH
+#define T41RX_DC_BATCH 4   /* register batch of the chain: 4 keeps the front kernel (128-register cap) almost spill-free; a spill is an L2 access here */
+#endif
 /* n consecutive samples at x (one channel's part of the sequence: no address arithmetic per sample).  second: the
    I channel's extra factor -IQAmp in the mirrored modes */
 template <bool kStore>
 T41RX_DEV void DcSegment(float *x, int n, const DcCoef &k, const DcPost &p, bool second, float &d1, float &lx, float &ly) {
-  constexpr int kB = 8;
+  constexpr int kB = T41RX_DC_BATCH;
   const int n_batches = n / kB;
   float cur[kB], nxt[kB];
   if (n_batches > 0) {
