@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(kNT, 8 / kG) t41rx_fused_rx_kernel(const Launc
   c.row = 0;
   c.row_idx = 0;
   c.rows_only = 0;
+  c.casc_warp = 0;
   const int tid = threadIdx.x;
   PhCtaInit(c, tid);
   __syncthreads();
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(kNT, 8 / kG) t41rx_exact_front_kernel(const La
   c.row = 0;
   c.row_idx = 0;
   c.rows_only = 0;
+  c.casc_warp = 0;
   const int tid = threadIdx.x;
   PhCtaInit(c, tid);
   __syncthreads();
@@ -109,7 +111,27 @@ __global__ void __launch_bounds__(kNT, 8 / kG) t41rx_exact_front_kernel(const La
     c.t = t;
     c.row = (a.row_every > 0) && ((a.t0 + t) % a.row_every == 0);
     c.row_idx = c.row ? (a.t0 + t) / a.row_every : 0;
+#ifdef T41RX_PHASE_TIMING
+    /* developer build only: cycles per phase of CTA 0, the slots the fused kernel uses (it does not run beside this one) */
+    int phase_no = 0;
+#define T41RX_KPHASE_T(stmt)                                                                 \
+  do {                                                                                       \
+    const long long t0_ = clock64();                                                         \
+    stmt;                                                                                    \
+    const long long t1_ = clock64();                                                         \
+    __syncthreads();                                                                         \
+    const long long t2_ = clock64();                                                         \
+    if (blockIdx.x == 0 && tid == 0) {                                                       \
+      g_phase_cycles[2 * phase_no] += (unsigned long long)(t2_ - t0_);                       \
+      g_phase_cycles[2 * phase_no + 1] += (unsigned long long)(t1_ - t0_);                   \
+    }                                                                                        \
+    ++phase_no;                                                                              \
+  } while (0)
+    T41RX_FRONT_SCHEDULE(T41RX_KPHASE_T)
+#undef T41RX_KPHASE_T
+#else
     T41RX_FRONT_SCHEDULE(T41RX_KPHASE)
+#endif
   }
   PhFrontStateOut(c, tid);
 }
@@ -256,6 +278,7 @@ __global__ void __launch_bounds__(kNT, 8 / kG) t41rx_exact_back_kernel(const Lau
   c.row = 0;
   c.row_idx = 0;
   c.rows_only = 0;
+  c.casc_warp = 0;
   const int tid = threadIdx.x;
   PhCtaInit(c, tid);
   __syncthreads();
@@ -282,8 +305,14 @@ __global__ void __launch_bounds__(kNT, 8 / kG) t41rx_rows_kernel(const LaunchArg
   c.row = 1;
   c.rows_only = 1;
   const int tid = threadIdx.x;
+  /* The cascade is one warp's 2084-step recurrence (12 instructions on a 12-clock chain per step) while the CTA's other
+     warps wait.  Two CTAs share an SM; were both cascades on the same warp scheduler (warp slot mod 4), they would
+     alternate and take twice as long: the CTA in the upper warp slots gives the cascade to its second warp. */
+  __shared__ unsigned first_warp_slot;
+  if (tid == 0) asm("mov.u32 %0, %%warpid;" : "=r"(first_warp_slot));
   PhCtaInit(c, tid);
   __syncthreads();
+  c.casc_warp = (int)((first_warp_slot / (kNT / 32)) & 3u);
   /* the row-producing blocks of this launch: absolute index a multiple of row_every */
   for (int t = (a.row_every - a.t0 % a.row_every) % a.row_every; t < a.n_blocks; t += a.row_every) {
     c.t = t;
@@ -330,6 +359,7 @@ __global__ void __launch_bounds__(kNT) t41rx_row_byproducts_kernel(const LaunchA
   c.ng = min(kG, a.n_streams - c.s0);
   c.row = 1;
   c.rows_only = 1;
+  c.casc_warp = 0;
   const int tid = threadIdx.x;
   PhCtaInit(c, tid);
   __syncthreads();
@@ -840,8 +870,16 @@ static int LaunchExact(t41rx_ctx *ctx, const LaunchArgs &p, cudaStream_t st, con
     q.n_blocks = std::min(chunk, p.n_blocks - c0);
     q.ser_in = (float4 *)ctx->d_ser_in;
     q.ser_out = (float *)ctx->d_ser_out;
+#ifdef T41RX_DEV_KNOBS
+    static cudaEvent_t dev_ev[6];
+    if (!dev_ev[0]) for (auto &e : dev_ev) cudaEventCreate(&e);
+    cudaEventRecord(dev_ev[0], st);
+#endif
     t41rx_exact_front_kernel<<<grid, kNT, kSmemFloats * sizeof(float), st>>>(q);
     CUDA_TRY(cudaGetLastError());
+#ifdef T41RX_DEV_KNOBS
+    cudaEventRecord(dev_ev[1], st);
+#endif
     if (c0 == 0) {
       /* first chunk: the serial kernel on the side stream, the other receivers' kernels (overlap) on st beside it */
       CUDA_TRY(cudaEventRecord(ctx->ev_fork, st));
@@ -849,14 +887,36 @@ static int LaunchExact(t41rx_ctx *ctx, const LaunchArgs &p, cudaStream_t st, con
       t41rx_exact_serial_kernel<<<(n + kSerialLanes - 1) / kSerialLanes, kSerialThreads, 0, ctx->aux>>>(q);
       CUDA_TRY(cudaGetLastError());
       CUDA_TRY(cudaEventRecord(ctx->ev_join, ctx->aux));
+#ifdef T41RX_DEV_KNOBS
+      cudaEventRecord(dev_ev[5], ctx->aux);
+#endif
       if ((rc = overlap())) return rc;
+#ifdef T41RX_DEV_KNOBS
+      cudaEventRecord(dev_ev[2], st);
+#endif
       CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+#ifdef T41RX_DEV_KNOBS
+      cudaEventRecord(dev_ev[3], st);
+#endif
     } else {
       t41rx_exact_serial_kernel<<<(n + kSerialLanes - 1) / kSerialLanes, kSerialThreads, 0, st>>>(q);
       CUDA_TRY(cudaGetLastError());
     }
     t41rx_exact_back_kernel<<<grid, kNT, kSmemFloats * sizeof(float), st>>>(q);
     CUDA_TRY(cudaGetLastError());
+#ifdef T41RX_DEV_KNOBS
+    if (c0 == 0 && getenv("T41RX_DEV_TIMELINE")) {          /* developer builds only: where the step's time goes */
+      cudaEventRecord(dev_ev[4], st);
+      cudaEventSynchronize(dev_ev[4]);
+      float f, o, j, b, js;
+      cudaEventElapsedTime(&f, dev_ev[0], dev_ev[1]);
+      cudaEventElapsedTime(&o, dev_ev[1], dev_ev[2]);
+      cudaEventElapsedTime(&j, dev_ev[2], dev_ev[3]);
+      cudaEventElapsedTime(&b, dev_ev[3], dev_ev[4]);
+      cudaEventElapsedTime(&js, dev_ev[1], dev_ev[5]);
+      fprintf(stderr, "[exact timeline] front %.3f ms | other kernels on st %.3f | wait for serial %.3f (serial done at +%.3f) | back %.3f\n", f, o, j, js, b);
+    }
+#endif
     ctx->launches += 3;
   }
   return T41RX_OK;

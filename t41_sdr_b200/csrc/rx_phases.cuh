@@ -178,6 +178,7 @@ struct Cta {
   int row;     /* this block produces a spectrum row */
   int row_idx;
   int rows_only;   /* 1 in t41rx_rows_kernel */
+  int casc_warp;   /* rows kernel: the warp of the CTA that runs the ZoomFFT cascade */
 };
 
 T41RX_DEV float *Slot(const Cta &c, int g) { return c.smem + g * kSlot; }
@@ -2430,13 +2431,24 @@ T41RX_DEV void PhZoomIirScan(Cta &c, int tid) {
  * as long as one biquad's own recurrence: acc3 = acc2 + a1 y1, acc = acc3 + a2 y2.  Input: the shifted samples
  * (PhZoomShift); output: the last stage's, in place. */
 T41RX_DEV void PhZoomIirPipe(Cta &c, int tid) {
-  /* ONE warp serves the CTA's receivers, eight lanes each (slots sit 8 banks apart, the two channels 28: the lanes'
-     loads and stores do not collide) */
+  /* ONE warp serves the CTA's receivers, eight lanes each.  Lane (receiver g, channel c, stage s) touches bank
+     8 g + 28 c - kSkew s (mod 32) at every step: with an ODD skew these are 32 different banks (an even one leaves
+     only the multiples of 4: a 4-way conflict on every load and store of the loop).
+     Where the time of a step goes (tools/ubench/casc_loop.cu, one warp, clocks per step): the y-chain alone 12.2, with
+     the three input terms 14.4, with the fetch 14.5, with the store of the step's own result 18.0, and 20.8 if that
+     store is predicated (the form of the first two rounds).  The result of a step is the last link of the chain: a
+     store of it sits in the issue order right where the next step's multiply wants to go.  So the main loop stores
+     the result of two steps ago (a register that has been ready for 24 clocks) and never predicates: lanes without a
+     receiver, or at zoom x1, run on a dead stretch of their slot instead.  15.5 clocks per step. */
   static_assert(kG * 8 <= 32, "eight lanes per receiver in one warp");
-  constexpr int kSkew = 12, kAhead = 4, kGroup = 8;
-  static_assert(kGroup <= kSkew - kAhead, "a stage never fetches what its predecessor has not written yet");
-  if (tid >= 32) return;
-  const int lane = tid, g = lane >> 3;
+  constexpr int kSkew = 15, kAhead = 4, kGroup = 8, kLate = 2, kEdgeSteps = 48;
+  static_assert(kGroup <= kSkew - kAhead - kLate, "a stage never fetches what its predecessor has not written yet");
+  static_assert(kSlot % 32 == 8 && (oRawQ - oRawI) % 32 == 28 && kSkew % 2 == 1, "bank map of the cascade lanes");
+  /* the stretch inactive lanes work on: dead in the rows kernel between PhDcFix and PhSpecWindow */
+  constexpr int kDummy = oD1I + 80;
+  static_assert(kDummy - 27 - 3 * kSkew >= oD1I && kDummy + kBlock + 3 * kSkew + kAhead + 4 <= oD1H, "dummy stretch inside the slot");
+  if ((tid >> 5) != c.casc_warp) return;
+  const int lane = tid & 31, g = lane >> 3;
   const bool have = g < c.ng;
   const int gg = have ? g : 0;
   const StreamCfg &cf = c.a.cfg[Sid(c, gg)];
@@ -2444,7 +2456,7 @@ T41RX_DEV void PhZoomIirPipe(Cta &c, int tid) {
   const bool active = have && cf.zoom != 0;
   if (!__any_sync(0xffffffffu, active)) return;       /* every receiver of the CTA at zoom x1: no cascade (CalcZoom1Magn) */
   const int chn = (lane >> 2) & 1, sg = lane & 3;
-  float *x = Slot(c, gg) + (chn ? oRawQ : oRawI) + 27;
+  float *x = Slot(c, gg) + (active ? (chn ? oRawQ : oRawI) + 27 : kDummy);
   float b0 = 0, b1 = 0, b2 = 0, a1 = 0, a2 = 0, x1 = 0, x2 = 0, y1 = 0, y2 = 0;
   if (active) {
     const float *kk = c.a.zoom_iir + (cf.zoom - 1) * 20 + 5 * sg;
@@ -2455,8 +2467,10 @@ T41RX_DEV void PhZoomIirPipe(Cta &c, int tid) {
   float *xm = x - kSkew * sg;                         /* this stage's sample at step k is xm[k] */
   const int lo = kSkew * sg - 27;                     /* xm[lo] is the first float of the raw region: early fetches stop there */
   float xn0 = xm[max(0, lo)], xn1 = xm[max(1, lo)], xn2 = xm[max(2, lo)], xn3 = xm[max(3, lo)];
-  /* one step; kEdge: some stages are outside the block (the first and the last 3 kSkew steps) */
-  /* the sum is ((((b0 x + b1 x1) + b2 x2) + a1 y1) + a2 y2) in this order (arm_biquad_cascade_df1_f32); its first
+  /* one step; kEdge: some stages are outside the block (the first and the last 3 kSkew steps), the result is stored at
+     once; else: every stage is inside the block (the state moves are plain register renames) and the store is the
+     result of kLate = 2 steps ago.
+     The sum is ((((b0 x + b1 x1) + b2 x2) + a1 y1) + a2 y2) in this order (arm_biquad_cascade_df1_f32); its first
      three terms do not involve the recurrence and are formed one step ahead (pre), beside the previous step's
      y-chain */
 #define T41RX_ZOOM_STEP(kEdge)                                                     \
@@ -2464,19 +2478,21 @@ T41RX_DEV void PhZoomIirPipe(Cta &c, int tid) {
     const float xin = xn0;                                                         \
     float acc = pre + a1 * y1;                                                     \
     acc = acc + a2 * y2;                                                           \
-    /* away from the edges every stage is inside the block: the state moves are plain register renames; lanes     \
-       without a receiver (or at zoom x1) compute on whatever they read and never store */                       \
-    bool live = true;                                                              \
     if (kEdge) {                                                                   \
       const int n = k - kSkew * sg;                                                \
-      live = n >= 0 && n < kBlock;                                                 \
-    }                                                                              \
-    if (live) {                                                                    \
+      if (n >= 0 && n < kBlock) {                                                  \
+        x2 = x1;                                                                   \
+        x1 = xin;                                                                  \
+        y2 = y1;                                                                   \
+        y1 = acc;                                                                  \
+        xm[k] = acc;                                                               \
+      }                                                                            \
+    } else {                                                                       \
+      xm[k - kLate] = y2;                                                          \
       x2 = x1;                                                                     \
       x1 = xin;                                                                    \
       y2 = y1;                                                                     \
       y1 = acc;                                                                    \
-      if (active) xm[k] = acc;                                                     \
     }                                                                              \
     pre = b0 * xn1;                                                                \
     pre = pre + b1 * x1;                                                           \
@@ -2488,19 +2504,23 @@ T41RX_DEV void PhZoomIirPipe(Cta &c, int tid) {
   pre = pre + b1 * x1;
   pre = pre + b2 * x2;
   /* a warp-level barrier every kGroup steps keeps the compiler from moving a fetch above the predecessor's store it
-     has to see (that store is kSkew - kAhead steps older than the fetch); inside such a group any order is fine */
-  static_assert((3 * kSkew) % kGroup == 4 && kBlock % kGroup == 0, "groups");
+     has to see (that store is kSkew - kAhead - kLate steps older than the fetch); inside such a group any order is
+     fine */
+  static_assert(kEdgeSteps >= 3 * kSkew + kLate && kEdgeSteps % 4 == 0 && (kBlock - kEdgeSteps) % kGroup == 0, "groups");
   int k = 0;
-  for (; k < 40;) {                                   /* 3 kSkew = 36 edge steps, rounded up to whole groups of the main loop */
+  for (; k < kEdgeSteps;) {                           /* until every stage has been inside the block for kLate steps */
     for (int u_ = 0; u_ < 4; ++u_, ++k) T41RX_ZOOM_STEP(true)
     __syncwarp();
   }
 #pragma unroll 1
-  for (; k < kBlock;) {
+  for (; k < kBlock;) {                               /* (its first two stores repeat what the edge steps stored) */
 #pragma unroll
     for (int u_ = 0; u_ < kGroup; ++u_, ++k) T41RX_ZOOM_STEP(false)
     __syncwarp();
   }
+  xm[kBlock - 2] = y2;                                /* the two results the main loop still owes */
+  xm[kBlock - 1] = y1;
+  __syncwarp();
   for (; k < kBlock + 3 * kSkew;) {
     for (int u_ = 0; u_ < 4; ++u_, ++k) T41RX_ZOOM_STEP(true)
     __syncwarp();

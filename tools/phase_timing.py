@@ -19,11 +19,12 @@ NAMES = ["Load", "DcWarm", "DcMain", "DcVerify", "DcFix", "NcoPrep", "Mix", "Dec
          "FftA0", "FftA1", "FftA2", "Mask", "FftB0", "FftB1", "FftB2", "AgcPre", "Max1", "Max2", "Max3", "Max4", "Max5",
          "Max6", "Max7", "AgcSerial", "AgcPost", "DemodPar", "DemodSer", "EqBands", "EqSum", "NrStageIn", "NrNotch", "NrStageOut",
          "CwFilter", "Interp1b", "Interp2", "BlockEnd"]
+FRONT_TAIL = ["SerialStore", "SerialRing+CodecGain"]      # the split chain's front kernel (FLAGS without 32) after Max7
 ROW_NAMES = ["ZoomIir", "SpecWin", "SpecFft0", "SpecFft1", "SpecFft2", "SpecRow"]
 
 
 def main():
-    S, T = 1024, 16
+    S, T = int(os.environ.get("PHASE_TIMING_S", "1024")), 16
     rows = int(os.environ.get("ROWS", "0"))
     params, sigs = bench.workload(T)
     eng = rx.Receiver(S)
@@ -42,7 +43,9 @@ def main():
         eng.synchronize()
         L.t41rx_debug_phase_cycles(buf, 1)
     v = np.array(buf[:], dtype=np.float64).reshape(64, 2) / T
-    names = NAMES[:5] + (ROW_NAMES if rows else []) + NAMES[5:]
+    flags = int(os.environ.get("FLAGS", "2"))
+    body = NAMES[5:] if (flags & 32) else NAMES[5:NAMES.index("Max7") + 1] + FRONT_TAIL
+    names = NAMES[:5] + (ROW_NAMES if rows else []) + body
     tot = v[:, 0].sum()
     print("cycles per block-group (CTA 0), total %.0f, kernel %.3f ms" % (tot, eng.last_kernel_ms()))
     order = sorted(range(len(names)), key=lambda i: -v[i, 0])

@@ -21,7 +21,7 @@ NAMES = ["Load+TailLoad", "RowDcSeedFast", "DcWarm", "DcMain", "DcVerify", "DcFi
 
 def main():
     zoom = int(sys.argv[1]) if len(sys.argv) > 1 else 1
-    S, T = 1024, 8
+    S, T = int(os.environ.get("ROWS_TIMING_S", "1024")), 8
     p = cases.P(mode=cases.USB, spectrum_zoom=zoom)
     iq1 = synth.tone(5, T, 1000.0)
     iq = torch.from_numpy(np.broadcast_to(iq1, (S,) + iq1.shape).copy()).cuda()
