@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(kNT, 8 / kG) t41rx_fused_rx_kernel(const Launc
   c.row = 0;
   c.row_idx = 0;
   c.rows_only = 0;
-  c.casc_warp = 0;
+  c.dc_carried = 0;
   const int tid = threadIdx.x;
   PhCtaInit(c, tid);
   __syncthreads();
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(kNT, 8 / kG) t41rx_exact_front_kernel(const La
   c.row = 0;
   c.row_idx = 0;
   c.rows_only = 0;
-  c.casc_warp = 0;
+  c.dc_carried = 0;
   const int tid = threadIdx.x;
   PhCtaInit(c, tid);
   __syncthreads();
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(kNT, 8 / kG) t41rx_exact_back_kernel(const Lau
   c.row = 0;
   c.row_idx = 0;
   c.rows_only = 0;
-  c.casc_warp = 0;
+  c.dc_carried = 0;
   const int tid = threadIdx.x;
   PhCtaInit(c, tid);
   __syncthreads();
@@ -305,15 +305,10 @@ __global__ void __launch_bounds__(kNT, 8 / kG) t41rx_rows_kernel(const LaunchArg
   c.row = 1;
   c.rows_only = 1;
   const int tid = threadIdx.x;
-  /* The cascade is one warp's 2084-step recurrence (12 instructions on a 12-clock chain per step) while the CTA's other
-     warps wait.  Two CTAs share an SM; were both cascades on the same warp scheduler (warp slot mod 4), they would
-     alternate and take twice as long: the CTA in the upper warp slots gives the cascade to its second warp. */
-  __shared__ unsigned first_warp_slot;
-  if (tid == 0) asm("mov.u32 %0, %%warpid;" : "=r"(first_warp_slot));
   PhCtaInit(c, tid);
   __syncthreads();
-  c.casc_warp = (int)((first_warp_slot / (kNT / 32)) & 3u);
   /* the row-producing blocks of this launch: absolute index a multiple of row_every */
+  c.dc_carried = 0;
   for (int t = (a.row_every - a.t0 % a.row_every) % a.row_every; t < a.n_blocks; t += a.row_every) {
     c.t = t;
     c.row_idx = (a.t0 + t) / a.row_every;
@@ -342,6 +337,7 @@ __global__ void __launch_bounds__(kNT, 8 / kG) t41rx_rows_kernel(const LaunchArg
 #endif
     T41RX_ROWS_SCHEDULE_FAST(T41RX_KPHASE)
 #undef T41RX_KPHASE
+    c.dc_carried = a.row_every == 1;       /* the next block continues where this one ended */
   }
 }
 
@@ -359,7 +355,7 @@ __global__ void __launch_bounds__(kNT) t41rx_row_byproducts_kernel(const LaunchA
   c.ng = min(kG, a.n_streams - c.s0);
   c.row = 1;
   c.rows_only = 1;
-  c.casc_warp = 0;
+  c.dc_carried = 0;
   const int tid = threadIdx.x;
   PhCtaInit(c, tid);
   __syncthreads();

@@ -178,7 +178,7 @@ struct Cta {
   int row;     /* this block produces a spectrum row */
   int row_idx;
   int rows_only;   /* 1 in t41rx_rows_kernel */
-  int casc_warp;   /* rows kernel: the warp of the CTA that runs the ZoomFFT cascade */
+  int dc_carried;  /* rows kernel: the slot holds the DC-block state the previous row block ended in (every block a row) */
 };
 
 T41RX_DEV float *Slot(const Cta &c, int g) { return c.smem + g * kSlot; }
@@ -852,12 +852,18 @@ T41RX_DEV void PhSpecRow(Cta &c, int tid) {
   const float2 *buf = reinterpret_cast<const float2 *>(s + vSpecFft);
   const size_t row_base = ((size_t)(Sid(c, g)) * c.a.n_rows + c.row_idx) * kSpecRes;
   const float lpf = 0.7f;
+  /* the smoothing state lives in HBM: all eight reads in flight before the first is used (the stores below would
+     otherwise order them one trip to memory after the other) */
+  float olds[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) olds[j] = st.spec_old[u + 64 * j];
+#pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int x = u + 64 * j;
     const int bin = (x + 256) & 511;
     const float2 v = buf[OctRev3((unsigned)bin)];
     const float pw = v.x * v.x + v.y * v.y;
-    const float old = st.spec_old[x];
+    const float old = olds[j];
     float shown;
     if (cf.zoom == 0) {
       /* spec_help = LPFcoeff * new + (1.0 - LPFcoeff) * old: the second product and the sum
@@ -2293,7 +2299,7 @@ constexpr int vRowTail = oOla;                    /* 256 floats: last Q samples 
 
 /* stage the 256 samples PhRowDcSeed filters (coalesced instead of 256 dependent global loads) */
 T41RX_DEV void PhRowTailLoad(Cta &c, int tid) {
-  if (c.a.t0 + c.t == 0) return;
+  if (c.a.t0 + c.t == 0 || c.dc_carried) return;
   const int g = tid >> 6, u = tid & 63;
   if (g >= c.ng) return;
   float *s = Slot(c, g);
@@ -2303,6 +2309,7 @@ T41RX_DEV void PhRowTailLoad(Cta &c, int tid) {
 T41RX_DEV void PhRowDcSeedFast(Cta &c, int tid) {
   const int g = SerialStream(c, tid);
   if (g < 0) return;
+  if (c.dc_carried) return;      /* the block before this one was a row block of this launch: PhDcVerify / PhDcFix left the state */
   float *s = Slot(c, g);
   const StreamState &st = c.a.st[Sid(c, g)];
   if (c.a.t0 + c.t == 0) {       /* first block of the call (a later launch of a call cut over time finds block t0 - 1 in the buffer) */
@@ -2447,8 +2454,8 @@ T41RX_DEV void PhZoomIirPipe(Cta &c, int tid) {
   /* the stretch inactive lanes work on: dead in the rows kernel between PhDcFix and PhSpecWindow */
   constexpr int kDummy = oD1I + 80;
   static_assert(kDummy - 27 - 3 * kSkew >= oD1I && kDummy + kBlock + 3 * kSkew + kAhead + 4 <= oD1H, "dummy stretch inside the slot");
-  if ((tid >> 5) != c.casc_warp) return;
-  const int lane = tid & 31, g = lane >> 3;
+  if (tid >= 32) return;
+  const int lane = tid, g = lane >> 3;
   const bool have = g < c.ng;
   const int gg = have ? g : 0;
   const StreamCfg &cf = c.a.cfg[Sid(c, gg)];
@@ -2544,7 +2551,7 @@ T41RX_DEV void PhZoomDecimate(Cta &c, int tid) {
   const int M = 1 << cf.zoom, zs = cf.zoom_samples, ptr = st.zoom_ptr;
   const float f0 = cf.zoom_fir[0], f1 = cf.zoom_fir[1], f2 = cf.zoom_fir[2], f3 = cf.zoom_fir[3];
   for (int e = u; e < 2 * zs; e += 64) {
-    const int chn = e / zs, k = e % zs;
+    const int chn = e >= zs, k = e - (chn ? zs : 0);        /* e < 2 zs */
     const float *y = s + (chn ? oRawQ : oRawI) + 27;
     const int n = k * M;
     const float h0 = (n >= 3) ? y[n - 3] : st.zoom_fir_hist[chn][n], h1 = (n >= 2) ? y[n - 2] : st.zoom_fir_hist[chn][n + 1],
