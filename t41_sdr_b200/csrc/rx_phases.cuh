@@ -52,7 +52,9 @@ namespace t41rx {
 constexpr int kG = T41RX_G;           /* receivers per CTA */
 constexpr int kNT = 64 * kG;          /* threads per CTA: 64 per receiver in the FFT phases */
 constexpr int kDcChunks = 64;         /* time-parallel chunks of the 4096-step DC-block chain: both warps of a receiver */
-constexpr int kDcChunkLen = 65;       /* chunk c starts at c*65 (odd stride: the lanes of a warp hit 32 different banks) */
+constexpr int kDcHalf = kDcChunks / 2;   /* chunks 0..31 cut the I block, 32..63 the Q block: no chunk reaches across sample 2048 */
+constexpr int kDcChunkLen = 65;       /* a chunk starts 65 after its neighbour (odd stride: the lanes of a warp hit 32 different
+                                         banks); the last chunk of a channel is the short one */
 #ifndef T41RX_DC_SPEC_WARM
 #define T41RX_DC_SPEC_WARM 192
 #endif
@@ -61,7 +63,8 @@ constexpr int kDcSpecWarm = T41RX_DC_SPEC_WARM;      /* warm-up of a chunk's spe
                                          against the previous chunk's end state and redone serially on a mismatch) */
 constexpr int kDcWarm = 256;          /* warm-up where nothing can verify it (the rows-only kernel's block-start state):
                                          0.854^256 ~ 3e-18 */
-static_assert(kDcChunks * kDcChunkLen >= 2 * kBlock && (kDcChunks - 1) * kDcChunkLen < 2 * kBlock, "chunking");
+static_assert(kDcHalf * kDcChunkLen >= kBlock && (kDcHalf - 1) * kDcChunkLen < kBlock, "chunking");
+static_assert(kDcSpecWarm <= kDcWarm && kDcSpecWarm % 2 == 0, "bridge size");
 
 /* ---- shared-memory slot layout, in floats ---- */
 constexpr int kRawLen = 2076;                     /* 27 history + 2048 new (+1 pad) */
@@ -115,7 +118,11 @@ enum { mDcD1 = 0, mDcD2 = 1, mNcoMode = 2, mDcBad = 3, mSid = 4 /* int: the rece
 /* the chunks' speculative start states and end states, 64 x 2 each, during the DC phases only: the dec1 output region
    (its history is restored by PhDec1, the spectrum scratch of a row block is written after PhDcFix) */
 constexpr int vDcSpec = oD1I, vDcEnd = oD1I + 2 * kDcChunks;
-static_assert(4 * kDcChunks <= kD1Len, "DC chunk states fit the dec1 region");
+/* behind them, until PhDcFix: the samples either side of the seam of the sequence, I[2048 - W ..] then Q[.. W - 1], as one run
+   (PhLoad writes it beside the raw tile): the warm-up of the first Q chunks reads its I part and its Q part from here
+   in one piece */
+constexpr int vDcBridge = oD1I + 4 * kDcChunks;
+static_assert(vDcBridge + 2 * kDcWarm <= oD1I + 2 * kD1Len, "DC chunk states and the bridge fit the dec1 region");
 
 struct LaunchArgs {
   const float *iq;
@@ -431,6 +438,14 @@ T41RX_DEV void PhLoad(Cta &c, int tid) {
         s[oRawQ + 27 + 2 * j] = v[gg][k].y;
         s[oRawI + 27 + 2 * j + 1] = v[gg][k].z;
         s[oRawQ + 27 + 2 * j + 1] = v[gg][k].w;
+        if (2 * j >= kBlock - kDcSpecWarm) {       /* the DC bridge (vDcBridge): kDcSpecWarm is even */
+          s[vDcBridge + 2 * j - (kBlock - kDcSpecWarm)] = v[gg][k].x;
+          s[vDcBridge + 2 * j + 1 - (kBlock - kDcSpecWarm)] = v[gg][k].z;
+        }
+        if (2 * j < kDcSpecWarm) {
+          s[vDcBridge + kDcSpecWarm + 2 * j] = v[gg][k].y;
+          s[vDcBridge + kDcSpecWarm + 2 * j + 1] = v[gg][k].w;
+        }
       }
     }
   }
@@ -516,24 +531,16 @@ T41RX_DEV void DcSegment(float *x, int n, const DcCoef &k, const DcPost &p, bool
   }
 }
 
-template <bool kStore>
-T41RX_DEV void DcRun(float *s, const DcPost p, int begin, int end, float &d1_io, float &d2_io) {
-  const DcCoef k = DcCoefs();
-  float d1 = d1_io;
-  float lx = 0.0f, ly = 0.0f;          /* last (scaled) input and output: define d2 */
-  /* the sequence is the I block, then the Q block (B6): at most one piece of each */
-  const int i_end = end < kBlock ? end : kBlock, q_begin = begin > kBlock ? begin : kBlock;
-#ifndef T41RX_HOST_EMUL
-#pragma unroll 1                          /* one copy of the loop body: two would spill (and a spill is an L2 access here) */
-#endif
-  for (int seg = 0; seg < 2; ++seg) {
-    float *x = seg ? s + oRawQ + 27 + (q_begin - kBlock) : s + oRawI + 27 + begin;
-    const int n = seg ? end - q_begin : i_end - begin;
-    if (n > 0) DcSegment<kStore>(x, n, k, p, seg == 0 && p.mirrored, d1, lx, ly);
-  }
-  d1_io = d1;
-  if (end > begin) d2_io = DcD2(lx, ly);
+/* chunk ch of the sequence: [DcChunkBegin, DcChunkEnd), all of it in one channel */
+T41RX_DEV int DcChunkBegin(int ch) {
+  return ch < kDcHalf ? ch * kDcChunkLen : kBlock + (ch - kDcHalf) * kDcChunkLen;
 }
+T41RX_DEV int DcChunkEnd(int ch) {
+  const int e = DcChunkBegin(ch) + kDcChunkLen, lim = ch < kDcHalf ? kBlock : 2 * kBlock;
+  return e < lim ? e : lim;
+}
+/* where sample i of the sequence lives in the slot (I block, then Q block) */
+T41RX_DEV float *DcSample(float *s, int i) { return s + oRawI + 27 + i + (i >= kBlock ? oRawQ - oRawI - kBlock : 0); }
 
 /* RFgain in force while block t of the launch is processed, from the values at launch start: Codec_gain
    (Process.cpp:979-1016 with the clip flags never set) raises it by one every 50 blocks up to 15 */
@@ -561,16 +568,20 @@ T41RX_DEV void PhDcWarm(Cta &c, int tid) {
     return;
   }
   const DcPost p = DcPostOf(c, g);
-  int start = ch * kDcChunkLen - kDcSpecWarm;
-  float d1 = 0.0f, d2 = 0.0f;
+  const int end = DcChunkBegin(ch);
+  int start = end - kDcSpecWarm;
+  float d1 = 0.0f;             /* (the state's second word is +-0 and never read: see DcStep) */
   if (start <= 0) {            /* the warm-up would reach before the block: start from the carried state instead */
     start = 0;
     d1 = s[oMisc + mDcD1];
-    d2 = s[oMisc + mDcD2];
   }
-  DcRun<false>(s, p, start, ch * kDcChunkLen, d1, d2);
+  /* one run of consecutive floats: in the tile, or (a warm-up across the seam) in the bridge */
+  float *x = (start < kBlock && end > kBlock) ? s + vDcBridge + (start - (kBlock - kDcSpecWarm)) : DcSample(s, start);
+  const DcCoef k = DcCoefs();
+  float lx = 0.0f, ly = 0.0f;
+  DcSegment<false>(x, end - start, k, p, false, d1, lx, ly);
   s[vDcSpec + 2 * ch] = d1;
-  s[vDcSpec + 2 * ch + 1] = d2;
+  s[vDcSpec + 2 * ch + 1] = DcD2(lx, ly);
 }
 
 T41RX_DEV void PhDcMain(Cta &c, int tid) {
@@ -578,19 +589,13 @@ T41RX_DEV void PhDcMain(Cta &c, int tid) {
   const int g = tid / kDcChunks, ch = tid % kDcChunks;
   float *s = Slot(c, g);
   const DcPost p = DcPostOf(c, g);
-  float d1, d2;
-  if (ch == 0) {
-    d1 = s[oMisc + mDcD1];
-    d2 = s[oMisc + mDcD2];
-  } else {
-    d1 = s[vDcSpec + 2 * ch];
-    d2 = s[vDcSpec + 2 * ch + 1];
-  }
-  const int begin = ch * kDcChunkLen;
-  const int end = (ch == kDcChunks - 1) ? 2 * kBlock : begin + kDcChunkLen;
-  DcRun<true>(s, p, begin, end, d1, d2);
+  float d1 = (ch == 0) ? s[oMisc + mDcD1] : s[vDcSpec + 2 * ch];
+  const int begin = DcChunkBegin(ch), end = DcChunkEnd(ch);
+  const DcCoef k = DcCoefs();
+  float lx = 0.0f, ly = 0.0f;
+  DcSegment<true>(DcSample(s, begin), end - begin, k, p, ch < kDcHalf && p.mirrored, d1, lx, ly);
   s[vDcEnd + 2 * ch] = d1;
-  s[vDcEnd + 2 * ch + 1] = d2;
+  s[vDcEnd + 2 * ch + 1] = DcD2(lx, ly);
 }
 
 #ifndef T41RX_HOST_EMUL
@@ -642,9 +647,19 @@ T41RX_DEV void PhDcFix(Cta &c, int tid) {
   const size_t src = ((size_t)(Sid(c, g)) * c.a.t_stride + c.t) * (2 * kBlock);
   float d1 = s[vDcEnd + 2 * (bad - 1)];
   float d2 = s[vDcEnd + 2 * (bad - 1) + 1];
-  for (int i = bad * kDcChunkLen; i < 2 * kBlock; ++i)
+  const int from = DcChunkBegin(bad);
+  for (int i = from; i < 2 * kBlock; ++i)
     s[SeqOff(i)] = IqWord(c.a, src + (i < kBlock ? 2 * i : 2 * (i - kBlock) + 1));
-  DcRun<true>(s, p, bad * kDcChunkLen, 2 * kBlock, d1, d2);
+  const DcCoef k = DcCoefs();
+  float lx = 0.0f, ly = 0.0f;
+#ifndef T41RX_HOST_EMUL
+#pragma unroll 1                          /* one copy of the loop body */
+#endif
+  for (int seg = (from < kBlock) ? 0 : 1; seg < 2; ++seg) {      /* the rest of the I block, then the Q block */
+    const int b = seg ? (from > kBlock ? from : kBlock) : from, e = seg ? 2 * kBlock : kBlock;
+    DcSegment<true>(DcSample(s, b), e - b, k, p, seg == 0 && p.mirrored, d1, lx, ly);
+  }
+  d2 = DcD2(lx, ly);
   s[oMisc + mDcD1] = d1;
   s[oMisc + mDcD2] = d2;
 }
