@@ -406,23 +406,25 @@ T41RX_DEV void PhStateOut(Cta &c, int tid) {
 /* P0: HBM -> shared, de-interleave; restore dec1 history              */
 /* ------------------------------------------------------------------ */
 T41RX_DEV void PhLoad(Cta &c, int tid) {
-  constexpr int kPer = (kBlock / 2) / kNT;       /* float4 loads per thread per receiver */
-  static_assert(kPer * kNT == kBlock / 2, "load tiling");
+  /* one complex sample per lane and load: a warp's 32 consecutive I (and Q) samples go to 32 different banks (two
+     samples per lane would put every store on 16 banks) */
+  constexpr int kPer = kBlock / kNT;             /* float2 loads per thread per receiver */
+  static_assert(kPer * kNT == kBlock, "load tiling");
   for (int g0 = 0; g0 < c.ng; g0 += 2) {         /* two receivers' loads in flight at once */
-    float4 v[2][kPer];
+    float2 v[2][kPer];
 #pragma unroll
     for (int gg = 0; gg < 2; ++gg) {
       if (g0 + gg >= c.ng) continue;
       const size_t blk = ((size_t)(Sid(c, g0 + gg)) * c.a.t_stride + c.t) * (2 * kBlock);
       if (c.a.iq16) {
-        const short4 *src = reinterpret_cast<const short4 *>(c.a.iq16 + blk);
+        const short2 *src = reinterpret_cast<const short2 *>(c.a.iq16 + blk);
 #pragma unroll
         for (int k = 0; k < kPer; ++k) {
-          const short4 q = LdgRO(src + tid + kNT * k);
-          v[gg][k] = float4{(float)q.x / 32768.0f, (float)q.y / 32768.0f, (float)q.z / 32768.0f, (float)q.w / 32768.0f};
+          const short2 q = LdgRO(src + tid + kNT * k);
+          v[gg][k] = float2{(float)q.x / 32768.0f, (float)q.y / 32768.0f};
         }
       } else {
-        const float4 *src = reinterpret_cast<const float4 *>(c.a.iq + blk);
+        const float2 *src = reinterpret_cast<const float2 *>(c.a.iq + blk);
 #pragma unroll
         for (int k = 0; k < kPer; ++k) v[gg][k] = LdgRO(src + tid + kNT * k);
       }
@@ -433,19 +435,12 @@ T41RX_DEV void PhLoad(Cta &c, int tid) {
       float *s = Slot(c, g0 + gg);
 #pragma unroll
       for (int k = 0; k < kPer; ++k) {
-        const int j = tid + kNT * k;             /* float4 index: samples 2j, 2j+1 */
-        s[oRawI + 27 + 2 * j] = v[gg][k].x;
-        s[oRawQ + 27 + 2 * j] = v[gg][k].y;
-        s[oRawI + 27 + 2 * j + 1] = v[gg][k].z;
-        s[oRawQ + 27 + 2 * j + 1] = v[gg][k].w;
-        if (2 * j >= kBlock - kDcSpecWarm) {       /* the DC bridge (vDcBridge): kDcSpecWarm is even */
-          s[vDcBridge + 2 * j - (kBlock - kDcSpecWarm)] = v[gg][k].x;
-          s[vDcBridge + 2 * j + 1 - (kBlock - kDcSpecWarm)] = v[gg][k].z;
-        }
-        if (2 * j < kDcSpecWarm) {
-          s[vDcBridge + kDcSpecWarm + 2 * j] = v[gg][k].y;
-          s[vDcBridge + kDcSpecWarm + 2 * j + 1] = v[gg][k].w;
-        }
+        const int n = tid + kNT * k;             /* sample index */
+        s[oRawI + 27 + n] = v[gg][k].x;
+        s[oRawQ + 27 + n] = v[gg][k].y;
+        /* the DC bridge (vDcBridge) */
+        if (n >= kBlock - kDcSpecWarm) s[vDcBridge + n - (kBlock - kDcSpecWarm)] = v[gg][k].x;
+        if (n < kDcSpecWarm) s[vDcBridge + kDcSpecWarm + n] = v[gg][k].y;
       }
     }
   }
