@@ -1274,35 +1274,77 @@ T41RX_DEV void PhAgcPre(Cta &c, int tid) {
   }
 }
 
-/* sliding maximum over 97 entries by doubling: level L holds max over 2^L trailing entries */
-T41RX_DEV void PhAgcMaxLevel(Cta &c, int tid, int level) {
+/* Sliding maximum over 97 entries: rm[i] = max |z| over entries [e - 96, e], e = i + 97, of the 353-entry magnitude
+ * array (97 delayed + 256 new).  Three steps instead of a doubling ladder of seven:
+ *   A  chunks of 8: prefix maxima P[e] and suffix maxima S[e] inside every chunk, and the chunk maximum M[c];
+ *   B  W[c] = max M[c - 11 .. c - 1]: the 11 whole chunks inside every window that ends in chunk c;
+ *   C  with e = 8 c + o: rm = max(S[8 (c - 12) + o], W[c], P[e])  (97 = 12 x 8 + 1: the window starts at offset o of
+ *      chunk c - 12 and ends at offset o of chunk c).
+ * max is exact, so any order gives the reference's value (`if (abs > ring_max)`, DSP_Fn.cpp:509-519). */
+constexpr int kMaxChunk = 8;
+constexpr int kMaxChunks = (kAgcDelay + kDec + kMaxChunk - 1) / kMaxChunk;        /* 45 */
+static_assert(kAgcDelay == 12 * kMaxChunk + 1 && kMaxChunks <= 64, "window = 12 chunks + 1 entry");
+static_assert(vAbs % 4 == 0 && vLvlA % 4 == 0 && vLvlB % 4 == 0 && kSlot % 4 == 0, "16-byte accesses of the chunk arrays");
+constexpr int vMaxW = oD1I, vMaxM = oD1I + 64;     /* the dec1 output region is dead between PhDec2 and the equaliser */
+T41RX_DEV void PhAgcMaxA(Cta &c, int tid) {
+  const int g = tid >> 6, u = tid & 63;
+  if (g >= c.ng || u >= kMaxChunks) return;
+  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+  if (!UsesFilter(cf.mode) || cf.agc_mode == 0) return;
+  float *s = Slot(c, g);
+  const int n = kAgcDelay + kDec;   /* 353 */
+  float a[kMaxChunk], pm[kMaxChunk], sm[kMaxChunk];
+  {
+    /* (the last chunk reads past entry 352: still inside the slot, masked below) */
+    const float4 lo = *reinterpret_cast<const float4 *>(s + vAbs + kMaxChunk * u);
+    const float4 hi = *reinterpret_cast<const float4 *>(s + vAbs + kMaxChunk * u + 4);
+    a[0] = lo.x; a[1] = lo.y; a[2] = lo.z; a[3] = lo.w;
+    a[4] = hi.x; a[5] = hi.y; a[6] = hi.z; a[7] = hi.w;
+  }
+#pragma unroll
+  for (int j = 0; j < kMaxChunk; ++j) {
+    /* the reference's `if (abs > ring_max)` never lets a NaN magnitude (NFM discriminator on exact silence: 0/0)
+       become the maximum: NaNs count as 0 here */
+    a[j] = (kMaxChunk * u + j < n && a[j] == a[j]) ? a[j] : 0.0f;
+  }
+  pm[0] = a[0];
+#pragma unroll
+  for (int j = 1; j < kMaxChunk; ++j) pm[j] = fmaxf(pm[j - 1], a[j]);
+  sm[kMaxChunk - 1] = a[kMaxChunk - 1];
+#pragma unroll
+  for (int j = kMaxChunk - 2; j >= 0; --j) sm[j] = fmaxf(sm[j + 1], a[j]);
+  if (kMaxChunk * u + kMaxChunk <= n) {
+    *reinterpret_cast<float4 *>(s + vLvlA + kMaxChunk * u) = float4{pm[0], pm[1], pm[2], pm[3]};
+    *reinterpret_cast<float4 *>(s + vLvlA + kMaxChunk * u + 4) = float4{pm[4], pm[5], pm[6], pm[7]};
+    *reinterpret_cast<float4 *>(s + vLvlB + kMaxChunk * u) = float4{sm[0], sm[1], sm[2], sm[3]};
+    *reinterpret_cast<float4 *>(s + vLvlB + kMaxChunk * u + 4) = float4{sm[4], sm[5], sm[6], sm[7]};
+  } else {                           /* the last, partial chunk: its prefix maxima only (no window starts in it) */
+#pragma unroll
+    for (int j = 0; j < kMaxChunk; ++j)
+      if (kMaxChunk * u + j < n) s[vLvlA + kMaxChunk * u + j] = pm[j];
+  }
+  s[vMaxM + u] = pm[kMaxChunk - 1];
+}
+T41RX_DEV void PhAgcMaxB(Cta &c, int tid) {
+  const int g = tid >> 6, u = tid & 63;
+  if (g >= c.ng || u < 12 || u >= kMaxChunks) return;
+  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+  if (!UsesFilter(cf.mode) || cf.agc_mode == 0) return;
+  float *s = Slot(c, g);
+  float w = s[vMaxM + u - 11];
+#pragma unroll
+  for (int j = 10; j >= 1; --j) w = fmaxf(w, s[vMaxM + u - j]);
+  s[vMaxW + u] = w;
+}
+T41RX_DEV void PhAgcMaxC(Cta &c, int tid) {
   const int g = tid >> 6, u = tid & 63;
   if (g >= c.ng) return;
   const StreamCfg &cf = c.a.cfg[Sid(c, g)];
   if (!UsesFilter(cf.mode) || cf.agc_mode == 0) return;
   float *s = Slot(c, g);
-  const int n = kAgcDelay + kDec;   /* 353 */
-  if (level <= 6) {
-    const float *src = s + (level == 1 ? vAbs : ((level & 1) ? vLvlB : vLvlA));
-    float *dst = s + ((level & 1) ? vLvlA : vLvlB);
-    const int d = 1 << (level - 1);
-    if (level == 1) {
-      /* the reference's `if (abs > ring_max)` never lets a NaN magnitude (NFM discriminator on
-         exact silence: 0/0) become the maximum: NaNs count as 0 here */
-      for (int e = u; e < n; e += 64) {
-        const float a = src[e], b = (e >= 1) ? src[e - 1] : 0.0f;
-        dst[e] = fmaxf((a == a) ? a : 0.0f, (b == b) ? b : 0.0f);
-      }
-    } else {
-      for (int e = u; e < n; e += 64) dst[e] = (e >= d) ? fmaxf(src[e], src[e - d]) : src[e];
-    }
-  } else {
-    /* level 6 result lives in vLvlB; window [i+1, i+97] = [e-96, e] with e = i + 97 */
-    const float *m6 = s + vLvlB;
-    for (int i = u; i < kDec; i += 64) {
-      const int e = i + kAgcDelay;
-      s[vRm + i] = fmaxf(m6[e], m6[e - 33]);
-    }
+  for (int i = u; i < kDec; i += 64) {
+    const int e = i + kAgcDelay;
+    s[vRm + i] = fmaxf(fmaxf(s[vLvlB + e - 12 * kMaxChunk], s[vMaxW + e / kMaxChunk]), s[vLvlA + e]);
   }
 }
 
@@ -2796,13 +2838,9 @@ T41RX_DEV void PhSpecFrameWrite(Cta &c, int tid) {
   RX_PHASE(PhFftPass(c, tid, 1, 1));                                     \
   RX_PHASE(PhFftPass(c, tid, 1, 2));                                     \
   RX_PHASE(PhAgcPre(c, tid));                                            \
-  RX_PHASE(PhAgcMaxLevel(c, tid, 1));                                    \
-  RX_PHASE(PhAgcMaxLevel(c, tid, 2));                                    \
-  RX_PHASE(PhAgcMaxLevel(c, tid, 3));                                    \
-  RX_PHASE(PhAgcMaxLevel(c, tid, 4));                                    \
-  RX_PHASE(PhAgcMaxLevel(c, tid, 5));                                    \
-  RX_PHASE(PhAgcMaxLevel(c, tid, 6));                                    \
-  RX_PHASE(PhAgcMaxLevel(c, tid, 7));                                    \
+  RX_PHASE(PhAgcMaxA(c, tid));                                           \
+  RX_PHASE(PhAgcMaxB(c, tid));                                           \
+  RX_PHASE(PhAgcMaxC(c, tid));                                           \
   RX_PHASE(PhAgcSerial(c, tid));                                         \
   RX_PHASE(PhAgcPost(c, tid));                                           \
   RX_PHASE(PhDemodParallel(c, tid); PhInterp1(c, tid));                  \
@@ -2849,13 +2887,9 @@ T41RX_DEV void PhSpecFrameWrite(Cta &c, int tid) {
   RX_PHASE(PhFftPass(c, tid, 1, 1));                                     \
   RX_PHASE(PhFftPass(c, tid, 1, 2));                                     \
   RX_PHASE(PhAgcPre(c, tid));                                            \
-  RX_PHASE(PhAgcMaxLevel(c, tid, 1));                                    \
-  RX_PHASE(PhAgcMaxLevel(c, tid, 2));                                    \
-  RX_PHASE(PhAgcMaxLevel(c, tid, 3));                                    \
-  RX_PHASE(PhAgcMaxLevel(c, tid, 4));                                    \
-  RX_PHASE(PhAgcMaxLevel(c, tid, 5));                                    \
-  RX_PHASE(PhAgcMaxLevel(c, tid, 6));                                    \
-  RX_PHASE(PhAgcMaxLevel(c, tid, 7));                                    \
+  RX_PHASE(PhAgcMaxA(c, tid));                                           \
+  RX_PHASE(PhAgcMaxB(c, tid));                                           \
+  RX_PHASE(PhAgcMaxC(c, tid));                                           \
   RX_PHASE(PhSerialStore(c, tid));                                       \
   RX_PHASE(PhSerialRing(c, tid); PhCodecGain(c, tid));
 

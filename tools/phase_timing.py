@@ -16,10 +16,9 @@ import rx_driver  # noqa: E402
 from t41_sdr_b200 import rx  # noqa: E402
 
 NAMES = ["Load", "DcWarm", "DcMain", "DcVerify", "DcFix", "NcoPrep", "Mix", "Dec1", "Dec2", "PostDec2", "NfmAsm", "NfmAsm2",
-         "FftA0", "FftA1", "FftA2", "Mask", "FftB0", "FftB1", "FftB2", "AgcPre", "Max1", "Max2", "Max3", "Max4", "Max5",
-         "Max6", "Max7", "AgcSerial", "AgcPost", "DemodPar", "DemodSer", "EqBands", "EqSum", "NrStageIn", "NrNotch", "NrStageOut",
+         "FftA0", "FftA1", "FftA2", "Mask", "FftB0", "FftB1", "FftB2", "AgcPre", "MaxA", "MaxB", "MaxC", "AgcSerial", "AgcPost", "DemodPar", "DemodSer", "EqBands", "EqSum", "NrStageIn", "NrNotch", "NrStageOut",
          "CwFilter", "Interp1b", "Interp2", "BlockEnd"]
-FRONT_TAIL = ["SerialStore", "SerialRing+CodecGain"]      # the split chain's front kernel (FLAGS without 32) after Max7
+FRONT_TAIL = ["SerialStore", "SerialRing+CodecGain"]      # the split chain's front kernel (FLAGS without 32) after MaxC
 ROW_NAMES = ["ZoomIir", "SpecWin", "SpecFft0", "SpecFft1", "SpecFft2", "SpecRow"]
 
 
@@ -44,7 +43,7 @@ def main():
         L.t41rx_debug_phase_cycles(buf, 1)
     v = np.array(buf[:], dtype=np.float64).reshape(64, 2) / T
     flags = int(os.environ.get("FLAGS", "2"))
-    body = NAMES[5:] if (flags & 32) else NAMES[5:NAMES.index("Max7") + 1] + FRONT_TAIL
+    body = NAMES[5:] if (flags & 32) else NAMES[5:NAMES.index("MaxC") + 1] + FRONT_TAIL
     names = NAMES[:5] + (ROW_NAMES if rows else []) + body
     tot = v[:, 0].sum()
     print("cycles per block-group (CTA 0), total %.0f, kernel %.3f ms" % (tot, eng.last_kernel_ms()))
