@@ -115,6 +115,9 @@ constexpr int vSpecFft = oD1I;                    /* 512 complex = 1024 floats <
 
 /* misc scalar indices */
 enum { mDcD1 = 0, mDcD2 = 1, mNcoMode = 2, mDcBad = 3, mSid = 4 /* int: the receiver this slot serves */ };
+constexpr int mCfg = 8;               /* from here: a copy of the receiver's StreamCfg (PhCtaInit) */
+static_assert(sizeof(StreamCfg) % 8 == 0 && mCfg * 4 + sizeof(StreamCfg) <= 160 * 4 && (oMisc + mCfg) % 2 == 0 && kSlot % 2 == 0,
+              "the configuration record fits the scalar area, 8-byte aligned");
 /* the chunks' speculative start states and end states, 64 x 2 each, during the DC phases only: the dec1 output region
    (its history is restored by PhDec1, the spectrum scratch of a row block is written after PhDcFix) */
 constexpr int vDcSpec = oD1I, vDcEnd = oD1I + 2 * kDcChunks;
@@ -200,6 +203,19 @@ T41RX_DEV void PhCtaInit(Cta &c, int tid) {
   if (tid < c.ng)
     reinterpret_cast<int *>(c.smem + tid * kSlot)[oMisc + mSid] =
         c.a.stream_ids ? LdgRO(c.a.stream_ids + c.s0 + tid) : c.a.stream_base + c.s0 + tid;
+  /* the receivers' configuration records, beside the scalars: nearly every phase opens with a look at its receiver's
+     mode or switches, and with next to no L1 beside the shared memory each such look was a trip to L2 (600 - 800 clocks
+     in front of phases that take 1000 - 5000) */
+  constexpr int kW = (int)(sizeof(StreamCfg) / sizeof(uint32_t));
+  for (int i = tid; i < c.ng * kW; i += kNT) {
+    const int g = i / kW, w = i - g * kW;
+    const int sid = c.a.stream_ids ? LdgRO(c.a.stream_ids + c.s0 + g) : c.a.stream_base + c.s0 + g;
+    reinterpret_cast<uint32_t *>(c.smem + g * kSlot + oMisc + mCfg)[w] = LdgRO(reinterpret_cast<const uint32_t *>(c.a.cfg + sid) + w);
+  }
+}
+/* receiver g's configuration (the copy PhCtaInit left in the slot) */
+T41RX_DEV const StreamCfg &CfgOf(const Cta &c, int g) {
+  return *reinterpret_cast<const StreamCfg *>(c.smem + g * kSlot + oMisc + mCfg);
 }
 
 /* one word of a receiver's I/Q (float index `w` inside the [receiver][block][2048][2] array, block-relative base
@@ -350,7 +366,7 @@ T41RX_DEV void PhStateIn(Cta &c, int tid) {
   for (int g = 0; g < c.ng; ++g) {
     float *s = Slot(c, g);
     const StreamState &st = c.a.st[Sid(c, g)];
-    const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+    const StreamCfg &cf = CfgOf(c, g);
     const FilterSet &fs = c.a.fsets[cf.filter_id];
     for (int i = tid; i < 512; i += kNT) s[oOla + i] = st.ola_prev[i >> 8][i & 255];
     for (int i = tid; i < 154; i += kNT) {
@@ -547,7 +563,7 @@ T41RX_DEV int RfGainAtBlock(int rf_gain0, uint32_t timer0, int t) {
 }
 
 T41RX_DEV DcPost DcPostOf(const Cta &c, int g) {
-  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+  const StreamCfg &cf = CfgOf(c, g);
   const StreamState &st = c.a.st[Sid(c, g)];
   /* rows_only: the state in HBM is the one at launch start (the throughput kernel advances it) */
   const int rg = c.rows_only ? RfGainAtBlock(st.rf_gain, st.codec_timer, c.t) : st.rf_gain;
@@ -671,7 +687,7 @@ T41RX_DEV void PhDcFix(Cta &c, int tid) {
 T41RX_DEV void PhZoomIir(Cta &c, int tid) {
   if (!c.row || tid >= c.ng * 2) return;
   const int g = tid >> 1, chn = tid & 1;
-  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+  const StreamCfg &cf = CfgOf(c, g);
   if (cf.zoom == 0) return;
   StreamState &st = c.a.st[Sid(c, g)];
   const float *s = Slot(c, g);
@@ -733,7 +749,7 @@ T41RX_DEV void PhZoomIir(Cta &c, int tid) {
   if (!c.row) return;
   const int g = tid >> 6, lane = tid & 63;
   if (g >= c.ng || lane >= 32) return;               /* first warp of the receiver's 64-thread group */
-  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+  const StreamCfg &cf = CfgOf(c, g);
   if (cf.zoom == 0) return;                          /* warp-uniform */
   StreamState &st = c.a.st[Sid(c, g)];
   const float *s = Slot(c, g);
@@ -818,7 +834,7 @@ T41RX_DEV void PhSpecWindow(Cta &c, int tid) {
   const int g = tid >> 6, u = tid & 63;
   if (g >= c.ng) return;
   float *s = Slot(c, g);
-  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+  const StreamCfg &cf = CfgOf(c, g);
   const StreamState &st = c.a.st[Sid(c, g)];
   float2 *buf = reinterpret_cast<float2 *>(s + vSpecFft);
   const IqFix fix = IqFixOf(cf);
@@ -857,7 +873,7 @@ T41RX_DEV void PhSpecRow(Cta &c, int tid) {
   const int g = tid >> 6, u = tid & 63;
   if (g >= c.ng) return;
   float *s = Slot(c, g);
-  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+  const StreamCfg &cf = CfgOf(c, g);
   StreamState &st = c.a.st[Sid(c, g)];
   const float2 *buf = reinterpret_cast<const float2 *>(s + vSpecFft);
   const size_t row_base = ((size_t)(Sid(c, g)) * c.a.n_rows + c.row_idx) * kSpecRes;
@@ -917,7 +933,7 @@ T41RX_DEV void PhNcoPrep(Cta &c, int tid) {
   const int g = tid >> 6, u = tid & 63;
   if (g >= c.ng) return;
   float *s = Slot(c, g);
-  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+  const StreamCfg &cf = CfgOf(c, g);
   const StreamState &st = c.a.st[Sid(c, g)];
   const bool exact = (c.a.flags & 1u) || !st.nco_closed || (st.nco_epoch_seen != cf.nco_epoch);
   if (u == 0) s[oMisc + mNcoMode] = exact ? 1.0f : 0.0f;
@@ -940,7 +956,7 @@ T41RX_DEV void MixStore(float *s, int n, float vi, float vq, double oq, double o
 T41RX_DEV void PhMix(Cta &c, int tid) {
   for (int g = 0; g < c.ng; ++g) {
     float *s = Slot(c, g);
-    const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+    const StreamCfg &cf = CfgOf(c, g);
     if (s[oMisc + mNcoMode] != 0.0f) {
       /* exact path: the FP64 oscillator recurrence, one lane per receiver */
       if (tid != g) continue;
@@ -1018,7 +1034,7 @@ T41RX_DEV void PhNcoAdvance(Cta &c, int tid) {
   if (tid >= c.ng) return;
   float *s = Slot(c, tid);
   if (s[oMisc + mNcoMode] != 0.0f) return;
-  const StreamCfg &cf = c.a.cfg[Sid(c, tid)];
+  const StreamCfg &cf = CfgOf(c, tid);
   StreamState &st = c.a.st[Sid(c, tid)];
   double ph = st.nco_phase + cf.nco_block_delta;
   const double two_pi = 6.283185307179586476925286766559;
@@ -1078,7 +1094,7 @@ T41RX_DEV void PhDec2(Cta &c, int tid) {
   const int g = tid >> 6, u = tid & 63;
   if (g >= c.ng) return;
   float *s = Slot(c, g);
-  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+  const StreamCfg &cf = CfgOf(c, g);
   const int mode = cf.mode;
   const float vol_scale = cf.vol_scale;
   const bool first_block = c.a.st[Sid(c, g)].first_block != 0;
@@ -1134,7 +1150,7 @@ T41RX_DEV void PhDec2(Cta &c, int tid) {
 T41RX_DEV void PhPostDec2(Cta &c, int tid) {
   for (int g = 0; g < c.ng; ++g) {
     float *s = Slot(c, g);
-    const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+    const StreamCfg &cf = CfgOf(c, g);
     StreamState &st = c.a.st[Sid(c, g)];
     for (int h = tid; h < 90; h += kNT) {
       const int ch = h / 45, i = h % 45;
@@ -1170,7 +1186,7 @@ T41RX_DEV void PhPostDec2(Cta &c, int tid) {
 T41RX_DEV void PhNfmAssemble(Cta &c, int tid) {
   for (int g = 0; g < c.ng; ++g) {
     float *s = Slot(c, g);
-    const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+    const StreamCfg &cf = CfgOf(c, g);
     if (cf.mode != kModeNfm) continue;
     StreamState &st = c.a.st[Sid(c, g)];
     float2 *fa = reinterpret_cast<float2 *>(s + vFftA);
@@ -1183,7 +1199,7 @@ T41RX_DEV void PhNfmAssemble(Cta &c, int tid) {
 T41RX_DEV void PhNfmAssemble2(Cta &c, int tid) {
   for (int g = 0; g < c.ng; ++g) {
     float *s = Slot(c, g);
-    const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+    const StreamCfg &cf = CfgOf(c, g);
     if (cf.mode != kModeNfm) continue;
     float2 *fa = reinterpret_cast<float2 *>(s + vFftA);
     for (int o = tid; o < kDec; o += kNT) {
@@ -1203,7 +1219,7 @@ T41RX_DEV bool UsesFilter(int mode) { return mode != kModePsk31; }
 T41RX_DEV void PhFftPass(Cta &c, int tid, int which, int pass) {
   const int g = tid >> 6, u = tid & 63;
   if (g >= c.ng) return;
-  if (!UsesFilter(c.a.cfg[Sid(c, g)].mode)) return;
+  if (!UsesFilter(CfgOf(c, g).mode)) return;
   Radix8Butterfly(reinterpret_cast<float2 *>(Slot(c, g) + (which ? vFftB : vFftA)), c.a.twiddle, pass, u);
 }
 
@@ -1211,7 +1227,7 @@ T41RX_DEV void PhFftPass(Cta &c, int tid, int which, int pass) {
 T41RX_DEV void PhMask(Cta &c, int tid) {
   const int g = tid >> 6, u = tid & 63;
   if (g >= c.ng) return;
-  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+  const StreamCfg &cf = CfgOf(c, g);
   if (!UsesFilter(cf.mode)) return;
   float *s = Slot(c, g);
   const float2 *fa = reinterpret_cast<const float2 *>(s + vFftA);
@@ -1241,7 +1257,7 @@ T41RX_DEV void PhMask(Cta &c, int tid) {
 T41RX_DEV void PhAgcPre(Cta &c, int tid) {
   const int g = tid >> 6, u = tid & 63;
   if (g >= c.ng) return;
-  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+  const StreamCfg &cf = CfgOf(c, g);
   if (!UsesFilter(cf.mode)) return;
   float *s = Slot(c, g);
   const float2 *fb = reinterpret_cast<const float2 *>(s + vFftB);
@@ -1289,7 +1305,7 @@ constexpr int vMaxW = oD1I, vMaxM = oD1I + 64;     /* the dec1 output region is 
 T41RX_DEV void PhAgcMaxA(Cta &c, int tid) {
   const int g = tid >> 6, u = tid & 63;
   if (g >= c.ng || u >= kMaxChunks) return;
-  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+  const StreamCfg &cf = CfgOf(c, g);
   if (!UsesFilter(cf.mode) || cf.agc_mode == 0) return;
   float *s = Slot(c, g);
   const int n = kAgcDelay + kDec;   /* 353 */
@@ -1328,7 +1344,7 @@ T41RX_DEV void PhAgcMaxA(Cta &c, int tid) {
 T41RX_DEV void PhAgcMaxB(Cta &c, int tid) {
   const int g = tid >> 6, u = tid & 63;
   if (g >= c.ng || u < 12 || u >= kMaxChunks) return;
-  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+  const StreamCfg &cf = CfgOf(c, g);
   if (!UsesFilter(cf.mode) || cf.agc_mode == 0) return;
   float *s = Slot(c, g);
   float w = s[vMaxM + u - 11];
@@ -1339,7 +1355,7 @@ T41RX_DEV void PhAgcMaxB(Cta &c, int tid) {
 T41RX_DEV void PhAgcMaxC(Cta &c, int tid) {
   const int g = tid >> 6, u = tid & 63;
   if (g >= c.ng) return;
-  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+  const StreamCfg &cf = CfgOf(c, g);
   if (!UsesFilter(cf.mode) || cf.agc_mode == 0) return;
   float *s = Slot(c, g);
   for (int i = u; i < kDec; i += 64) {
@@ -1355,7 +1371,7 @@ T41RX_DEV void PhAgcMaxC(Cta &c, int tid) {
 T41RX_DEV void PhAgcSerial(Cta &c, int tid) {
   const int g = SerialStream(c, tid);
   if (g < 0) return;
-  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+  const StreamCfg &cf = CfgOf(c, g);
   if (!UsesFilter(cf.mode) || cf.agc_mode == 0) return;
   float *s = Slot(c, g);
   StreamState &st = c.a.st[Sid(c, g)];
@@ -1464,7 +1480,7 @@ T41RX_DEV void PhAgcSerial(Cta &c, int tid) {
 T41RX_DEV void PhAgcPost(Cta &c, int tid) {
   const int g = tid >> 6, u = tid & 63;
   if (g >= c.ng) return;
-  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+  const StreamCfg &cf = CfgOf(c, g);
   if (!UsesFilter(cf.mode) || cf.agc_mode == 0) return;
   float *s = Slot(c, g);
   const AgcConsts &a = cf.agc;
@@ -1495,7 +1511,7 @@ T41RX_DEV void PhAgcPost(Cta &c, int tid) {
 T41RX_DEV void PhDemodParallel(Cta &c, int tid) {
   const int g = tid >> 6, u = tid & 63;
   if (g >= c.ng) return;
-  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+  const StreamCfg &cf = CfgOf(c, g);
   if (!UsesFilter(cf.mode)) return;
   float *s = Slot(c, g);
   const float2 *dem = reinterpret_cast<const float2 *>(s + vDem);
@@ -1514,7 +1530,7 @@ T41RX_DEV void PhDemodParallel(Cta &c, int tid) {
 T41RX_DEV void PhDemodSerial(Cta &c, int tid) {
   const int g = SerialStream(c, tid);
   if (g < 0) return;
-  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+  const StreamCfg &cf = CfgOf(c, g);
   float *s = Slot(c, g);
   StreamState &st = c.a.st[Sid(c, g)];
   const float2 *dem = reinterpret_cast<const float2 *>(s + vDem);
@@ -1647,7 +1663,7 @@ T41RX_DEV void PhDemodSerial(Cta &c, int tid) {
 T41RX_DEV void PhSerialStore(Cta &c, int tid) {
   const int g = tid % kG, u = tid / kG;           /* u: 0..63 */
   if (g < c.ng) {
-    const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+    const StreamCfg &cf = CfgOf(c, g);
     const float *s = Slot(c, g);
     const size_t n = (size_t)c.a.n_streams;
     float4 *dst = c.a.ser_in + ((size_t)c.t * kDec) * n + (size_t)(c.s0 + g);
@@ -1675,7 +1691,7 @@ T41RX_DEV void PhSerialStore(Cta &c, int tid) {
 T41RX_DEV void PhSerialRing(Cta &c, int tid) {
   const int g = tid >> 6, u = tid & 63;
   if (g >= c.ng) return;
-  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+  const StreamCfg &cf = CfgOf(c, g);
   if (!UsesFilter(cf.mode) || cf.agc_mode == 0) return;
   float *s = Slot(c, g);
   const float2 *zext = reinterpret_cast<const float2 *>(s + vZext);
@@ -1968,7 +1984,7 @@ T41RX_DEV void PhBackStateIn(Cta &c, int tid) {
   for (int g = 0; g < c.ng; ++g) {
     float *s = Slot(c, g);
     const StreamState &st = c.a.st[Sid(c, g)];
-    const FilterSet &fs = c.a.fsets[c.a.cfg[Sid(c, g)].filter_id];
+    const FilterSet &fs = c.a.fsets[CfgOf(c, g).filter_id];
     for (int i = tid; i < 154; i += kNT) {
       float v;
       if (i < kTapDec2) v = fs.dec1[i];
@@ -2066,7 +2082,7 @@ T41RX_DEV void PhEqBands(Cta &c, int tid) {
 T41RX_DEV void PhEqSum(Cta &c, int tid) {
   const int g = tid >> 6, u = tid & 63;
   if (g >= c.ng) return;
-  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+  const StreamCfg &cf = CfgOf(c, g);
   if (!cf.eq_on) return;
   float *s = Slot(c, g);
 #pragma unroll
@@ -2129,7 +2145,7 @@ T41RX_DEV void XanrPass(float *aud, float *d, float *w, StreamState &st, bool no
 T41RX_DEV void PhNrStage(Cta &c, int tid, int dir) {
   const int g = tid >> 6, u = tid & 63;
   if (g >= c.ng) return;
-  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+  const StreamCfg &cf = CfgOf(c, g);
   if (!cf.nr_lms && !cf.anr_notch) return;
   float *s = Slot(c, g);
   StreamState &st = c.a.st[Sid(c, g)];
@@ -2144,7 +2160,7 @@ T41RX_DEV void PhNrStage(Cta &c, int tid, int dir) {
 T41RX_DEV void PhNrNotch(Cta &c, int tid) {
   const int g = SerialStream(c, tid);
   if (g < 0) return;
-  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+  const StreamCfg &cf = CfgOf(c, g);
   if (!cf.nr_lms && !cf.anr_notch) return;
   float *s = Slot(c, g);
   float *aud = s + vAud + 23;
@@ -2213,7 +2229,7 @@ T41RX_DEV void CwFilterLane(float *aud, const float *coef, float *st) {
 T41RX_DEV void PhCwFilter(Cta &c, int tid) {
   const int g = SerialStream(c, tid);
   if (g < 0) return;
-  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+  const StreamCfg &cf = CfgOf(c, g);
   if (cf.cw_filter < 0) return;
   CwFilterLane(Slot(c, g) + vAud + 23, c.a.cw_coeffs + 30 * cf.cw_filter, c.a.st[Sid(c, g)].cw_state[cf.cw_filter]);
 }
@@ -2257,7 +2273,7 @@ T41RX_DEV void PhInterp2(Cta &c, int tid) {
   const int g = tid >> 6, u = tid & 63;
   if (g >= c.ng) return;
   float *s = Slot(c, g);
-  const float volume = c.a.cfg[Sid(c, g)].volume;
+  const float volume = CfgOf(c, g).volume;
   float4 *dst = reinterpret_cast<float4 *>(c.a.audio + ((size_t)(Sid(c, g)) * c.a.t_stride + c.t) * kBlock);
   int16_t *dst16 = c.a.audio16 ? c.a.audio16 + ((size_t)(Sid(c, g)) * c.a.t_stride + c.t) * kBlock : nullptr;
   for (int h = u; h < 23; h += 64) s[oIntH + h] = s[vAud + kDec + h];   /* int1 history for the next block */
@@ -2333,7 +2349,7 @@ T41RX_DEV void PhRowDcSeed(Cta &c, int tid) {
     return;
   }
   const DcCoef k = DcCoefs();
-  const float rfg = c.a.cfg[Sid(c, g)].rf_gain_value;
+  const float rfg = CfgOf(c, g).rf_gain_value;
   const size_t q = ((size_t)Sid(c, g) * c.a.t_stride + (c.t - 1)) * (2 * kBlock) + 2 * (kBlock - kDcWarm) + 1;
   float d1 = 0.0f, lx = 0.0f, ly = 0.0f;
   for (int i = 0; i < kDcWarm; ++i) {
@@ -2370,7 +2386,7 @@ T41RX_DEV void PhRowDcSeedFast(Cta &c, int tid) {
     return;
   }
   const DcCoef k = DcCoefs();
-  const float rfg = c.a.cfg[Sid(c, g)].rf_gain_value;
+  const float rfg = CfgOf(c, g).rf_gain_value;
   float d1 = 0.0f, lx = 0.0f, ly = 0.0f;
   for (int i0 = 0; i0 < kDcWarm; i0 += 8) {
     float x[8];
@@ -2387,7 +2403,7 @@ T41RX_DEV void PhRowDcSeedFast(Cta &c, int tid) {
 T41RX_DEV void PhZoomShift(Cta &c, int tid) {
   const int g = tid >> 6, u = tid & 63;
   if (g >= c.ng) return;
-  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+  const StreamCfg &cf = CfgOf(c, g);
   if (cf.zoom == 0) return;
   float *s = Slot(c, g);
   const IqFix fix = IqFixOf(cf);
@@ -2407,7 +2423,7 @@ T41RX_DEV void PhZoomShift(Cta &c, int tid) {
 T41RX_DEV void PhZoomIirScan(Cta &c, int tid) {
   const int g = tid >> 6, u = tid & 63;
   if (g >= c.ng) return;
-  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+  const StreamCfg &cf = CfgOf(c, g);
   if (cf.zoom == 0) return;                          /* warp-uniform */
   StreamState &st = c.a.st[Sid(c, g)];
   const int chn = u >> 5, lane = u & 31;
@@ -2510,7 +2526,7 @@ T41RX_DEV void PhZoomIirPipe(Cta &c, int tid) {
   const int lane = tid, g = lane >> 3;
   const bool have = g < c.ng;
   const int gg = have ? g : 0;
-  const StreamCfg &cf = c.a.cfg[Sid(c, gg)];
+  const StreamCfg &cf = CfgOf(c, gg);
   StreamState &st = c.a.st[Sid(c, gg)];
   const bool active = have && cf.zoom != 0;
   if (!__any_sync(0xffffffffu, active)) return;       /* every receiver of the CTA at zoom x1: no cascade (CalcZoom1Magn) */
@@ -2596,7 +2612,7 @@ T41RX_DEV void PhZoomIirPipe(Cta &c, int tid) {
 T41RX_DEV void PhZoomDecimate(Cta &c, int tid) {
   const int g = tid >> 6, u = tid & 63;
   if (g >= c.ng) return;
-  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+  const StreamCfg &cf = CfgOf(c, g);
   if (cf.zoom == 0) return;
   StreamState &st = c.a.st[Sid(c, g)];
   const float *s = Slot(c, g);
@@ -2620,7 +2636,7 @@ T41RX_DEV void PhZoomDecimate(Cta &c, int tid) {
 T41RX_DEV void PhZoomDecimateEnd(Cta &c, int tid) {
   const int g = tid >> 6, u = tid & 63;
   if (g >= c.ng) return;
-  const StreamCfg &cf = c.a.cfg[Sid(c, g)];
+  const StreamCfg &cf = CfgOf(c, g);
   if (cf.zoom == 0) return;
   StreamState &st = c.a.st[Sid(c, g)];
   const float *s = Slot(c, g);
