@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(kNT, 8 / kG) t41rx_fused_rx_kernel(const Launc
   c.row = 0;
   c.row_idx = 0;
   c.rows_only = 0;
+  c.casc_warp = 0;
   c.dc_carried = 0;
   const int tid = threadIdx.x;
   PhCtaInit(c, tid);
@@ -101,6 +102,7 @@ __global__ void __launch_bounds__(kNT, 8 / kG) t41rx_exact_front_kernel(const La
   c.row = 0;
   c.row_idx = 0;
   c.rows_only = 0;
+  c.casc_warp = 0;
   c.dc_carried = 0;
   const int tid = threadIdx.x;
   PhCtaInit(c, tid);
@@ -278,6 +280,7 @@ __global__ void __launch_bounds__(kNT, 8 / kG) t41rx_exact_back_kernel(const Lau
   c.row = 0;
   c.row_idx = 0;
   c.rows_only = 0;
+  c.casc_warp = 0;
   c.dc_carried = 0;
   const int tid = threadIdx.x;
   PhCtaInit(c, tid);
@@ -291,55 +294,6 @@ __global__ void __launch_bounds__(kNT, 8 / kG) t41rx_exact_back_kernel(const Lau
   PhBackStateOut(c, tid);
 }
 #undef T41RX_KPHASE
-
-/* display spectrum + waterfall rows of the row-producing blocks, for the receivers the throughput kernel
-   serves; launched before it on the same stream (reads the launch-start state, writes only the zoom /
-   spectrum state and the row outputs) */
-__global__ void __launch_bounds__(kNT, 8 / kG) t41rx_rows_kernel(const LaunchArgs a) {
-  extern __shared__ __align__(16) float smem[];
-  Cta c;
-  c.a = a;
-  c.smem = smem;
-  c.s0 = blockIdx.x * kG;
-  c.ng = min(kG, a.n_streams - c.s0);
-  c.row = 1;
-  c.rows_only = 1;
-  const int tid = threadIdx.x;
-  PhCtaInit(c, tid);
-  __syncthreads();
-  /* the row-producing blocks of this launch: absolute index a multiple of row_every */
-  c.dc_carried = 0;
-  for (int t = (a.row_every - a.t0 % a.row_every) % a.row_every; t < a.n_blocks; t += a.row_every) {
-    c.t = t;
-    c.row_idx = (a.t0 + t) / a.row_every;
-#ifdef T41RX_PHASE_TIMING
-    /* developer build only: cycles per phase of CTA 0, slots 64.. of g_phase_cycles */
-    int phase_no = 32;
-#define T41RX_KPHASE(stmt)                                                                   \
-  do {                                                                                       \
-    const long long t0_ = clock64();                                                         \
-    stmt;                                                                                    \
-    const long long t1_ = clock64();                                                         \
-    __syncthreads();                                                                         \
-    const long long t2_ = clock64();                                                         \
-    if (blockIdx.x == 0 && tid == 0) {                                                       \
-      g_phase_cycles[2 * phase_no] += (unsigned long long)(t2_ - t0_);                       \
-      g_phase_cycles[2 * phase_no + 1] += (unsigned long long)(t1_ - t0_);                   \
-    }                                                                                        \
-    ++phase_no;                                                                              \
-  } while (0)
-#else
-#define T41RX_KPHASE(stmt) \
-  do {                     \
-    stmt;                  \
-    __syncthreads();       \
-  } while (0)
-#endif
-    T41RX_ROWS_SCHEDULE_FAST(T41RX_KPHASE)
-#undef T41RX_KPHASE
-    c.dc_carried = a.row_every == 1;       /* the next block continues where this one ended */
-  }
-}
 
 /* by-products of the row-producing blocks, launched after the chain (and rows) kernels on the same stream:
    audio spectrum + S-meter average (Process.cpp:550-570,791-805) from the masked spectra the chain kernels left in
@@ -355,6 +309,7 @@ __global__ void __launch_bounds__(kNT) t41rx_row_byproducts_kernel(const LaunchA
   c.ng = min(kG, a.n_streams - c.s0);
   c.row = 1;
   c.rows_only = 1;
+  c.casc_warp = 0;
   c.dc_carried = 0;
   const int tid = threadIdx.x;
   PhCtaInit(c, tid);
@@ -647,8 +602,7 @@ int t41rx_create(t41rx_ctx **out, int n_streams, int device) {
                            (int)(kSmemFloats * sizeof(float))) != cudaSuccess ||
       cudaFuncSetAttribute(t41rx_exact_back_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)(kSmemFloats * sizeof(float))) != cudaSuccess ||
-      cudaFuncSetAttribute(t41rx_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)(kSmemFloats * sizeof(float))) != cudaSuccess ||
+      ConfigureRowsKernel() != cudaSuccess ||
       cudaFuncSetAttribute(t41rx_row_byproducts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)(kSmemFloats * sizeof(float))) != cudaSuccess)
     return bail(Fail(T41RX_ECUDA, "t41rx_create: kernel image for this GPU missing (built for sm_100a)%s"));
@@ -1006,8 +960,7 @@ static int LaunchRange(t41rx_ctx *ctx, const void *iq_any, void *audio_any, bool
     f.stream_ids = (p_len > 0) ? ctx->d_fast_ids[v] + f_off : nullptr;     /* nothing for the other kernel in range: contiguous */
     if (first == 0 && count == ctx->n_streams && !ctx->h_fast_grouped[v].empty()) f.stream_ids = ctx->d_fast_grouped[v];
     if (has_row && (a.spec_rows || a.wf_rows)) {
-      t41rx_rows_kernel<<<(f_len + kG - 1) / kG, kNT, kSmemFloats * sizeof(float), st>>>(f);
-      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(LaunchRowsKernel(f, st));
       ctx->launches += 1;
     }
     cudaEvent_t *kev = ctx->kev[ctx->kev_count % kKernelEventRing];
@@ -1290,6 +1243,7 @@ int t41rx_process_q15(t41rx_ctx *ctx, const int16_t *iq_q15, int16_t *audio_q15,
 #ifdef T41RX_PHASE_TIMING
 int t41rx_debug_phase_cycles(unsigned long long *out128, int reset) {
   if (cudaMemcpyFromSymbol(out128, g_phase_cycles, sizeof(unsigned long long) * 128) != cudaSuccess) return -1;
+  if (RowsPhaseCycles(out128 + 64, reset) != cudaSuccess) return -1;       /* slots 32.. : the rows-only kernel (rx_rows.cu) */
   if (reset) {
     unsigned long long z[128] = {0};
     cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z));
@@ -1303,7 +1257,9 @@ int64_t t41rx_kernel_launches(const t41rx_ctx *ctx) { return ctx ? ctx->launches
 int64_t t41rx_dc_refilter_count(void) {
   unsigned long long v = 0;
   if (cudaMemcpyFromSymbol(&v, g_dc_refilter_count, sizeof(v)) != cudaSuccess) return -1;
-  return (int64_t)v;
+  const long long rows = RowsDcRefilterCount();                              /* the rows-only kernel counts in its own unit */
+  if (rows < 0) return -1;
+  return (int64_t)v + rows;
 }
 
 int t41rx_stream_kernel_times(t41rx_ctx *ctx, float *ms, int max_n) {

@@ -64,12 +64,18 @@ constexpr int kDcSpecWarm = T41RX_DC_SPEC_WARM;      /* warm-up of a chunk's spe
 constexpr int kDcWarm = 256;          /* warm-up where nothing can verify it (the rows-only kernel's block-start state):
                                          0.854^256 ~ 3e-18 */
 static_assert(kDcHalf * kDcChunkLen >= kBlock && (kDcHalf - 1) * kDcChunkLen < kBlock, "chunking");
-static_assert(kDcSpecWarm <= kDcWarm && kDcSpecWarm % 2 == 0, "bridge size");
+static_assert(kDcSpecWarm <= kDcWarm && kDcSpecWarm > kDcChunkLen, "bridge size");
+/* the warm-ups that reach across the seam of the sequence (sample 2048: the I block ends, the Q block begins) are those of
+   the Q chunks 1 .. (W - 1) / 65; together they read the samples [kDcBridgeLo, kDcBridgeHi) of the sequence */
+constexpr int kDcBridgeLo = kBlock - kDcSpecWarm + kDcChunkLen;
+constexpr int kDcBridgeHi = kBlock + ((kDcSpecWarm - 1) / kDcChunkLen) * kDcChunkLen;
+constexpr int kDcBridgeLen = kDcBridgeHi - kDcBridgeLo;                 /* 257 at W = 192 */
 
 /* ---- shared-memory slot layout, in floats ---- */
 constexpr int kRawLen = 2076;                     /* 27 history + 2048 new (+1 pad) */
 constexpr int oRawI = 0;
 constexpr int oRawQ = oRawI + kRawLen;            /* 2076 */
+#ifndef T41RX_ROWS_LAYOUT
 constexpr int oD1I = oRawQ + kRawLen;             /* 4152 : 45 history + 512 new */
 constexpr int kD1Len = 560;
 constexpr int oD1Q = oD1I + kD1Len;
@@ -82,7 +88,23 @@ constexpr int oD1H = oNco + 512;                  /* 6836 : dec1 history 2 x 27 
 constexpr int oD2H = oD1H + 56;                   /* 6892 : dec2 history 2 x 45 (-> 92) */
 constexpr int oIntH = oD2H + 92;                  /* 6984 : int1 23 (-> 24) | int2 7 (-> 8) */
 constexpr int oMisc = oIntH + 32;                 /* 7016 : scalars */
-constexpr int kSlotRaw = oMisc + 160;
+constexpr int kMiscLen = 160;
+constexpr int kSlotRaw = oMisc + kMiscLen;
+#else
+/* The rows-only kernel's slot (rx_rows.cu is compiled with T41RX_ROWS_LAYOUT): the raw tile, the DC-block scratch, the
+   scalars: 19.1 KB instead of 28.8, so that THREE of its CTAs share an SM (its cascade phase is one warp's 2093-step
+   chain while the CTA's other warps wait: rows in flight per SM are what its throughput is made of).  The regions of
+   the audio chain are aliased onto the scratch: no phase of this kernel touches them (PhLoad's copy of the dec1 history
+   reads 54 floats of the scalar area and puts them in front of the tile, where nothing looks). */
+constexpr int oD1I = oRawQ + kRawLen;             /* 4152 : chunk states (256) + bridge (257) */
+constexpr int kD1Len = (4 * kDcChunks + kDcBridgeLen + 2) / 2;
+constexpr int oD1Q = oD1I, oOla = oD1I, oTaps = oD1I, oAgc = oD1I, oNco = oD1I, oD2H = oD1I, oIntH = oD1I;
+constexpr int kTapDec1 = 0, kTapDec2 = 28, kTapInt1 = 74, kTapInt2 = 122;
+constexpr int oMisc = oD1I + 2 * kD1Len;
+constexpr int oD1H = oMisc;
+constexpr int kMiscLen = 96;
+constexpr int kSlotRaw = oMisc + kMiscLen;
+#endif
 constexpr int kSlot = ((kSlotRaw - 8 + 31) / 32) * 32 + 8;   /* == 8 (mod 32): distinct banks per slot */
 static_assert(kSlot % 32 == 8 && kSlot >= kSlotRaw, "slot stride");
 static_assert((oNco % 4) == 0, "double2 alignment");
@@ -111,21 +133,28 @@ constexpr int vSamSin = 1056;                     /* SAM: arm_sin_f32's 513-entr
 constexpr int vEqBand = 1056;
 static_assert(vEqBand + 12 * kDec <= 2 * kRawLen, "equaliser bands fit the raw region");
 /* spectrum scratch (row blocks, before dec1): the D1 region */
+#ifndef T41RX_ROWS_LAYOUT
 constexpr int vSpecFft = oD1I;                    /* 512 complex = 1024 floats <= 1120 */
+#else
+/* rows-only layout: the top of the Q tile (a zoomed receiver's tile is dead behind the decimator; one at zoom x1 reads
+   samples 0..511 of both tiles for this buffer: PhSpecWindow) */
+constexpr int vSpecFft = 2 * kRawLen - 2 * kSpecRes;
+static_assert(vSpecFft % 4 == 0 && vSpecFft >= oRawQ + 27 + kSpecRes, "spectrum scratch inside the Q tile, clear of its first 512 samples");
+#endif
 
 /* misc scalar indices */
 enum { mDcD1 = 0, mDcD2 = 1, mNcoMode = 2, mDcBad = 3, mSid = 4 /* int: the receiver this slot serves */ };
 constexpr int mCfg = 8;               /* from here: a copy of the receiver's StreamCfg (PhCtaInit) */
-static_assert(sizeof(StreamCfg) % 8 == 0 && mCfg * 4 + sizeof(StreamCfg) <= 160 * 4 && (oMisc + mCfg) % 2 == 0 && kSlot % 2 == 0,
+static_assert(sizeof(StreamCfg) % 8 == 0 && mCfg * 4 + sizeof(StreamCfg) <= kMiscLen * 4 && (oMisc + mCfg) % 2 == 0 && kSlot % 2 == 0,
               "the configuration record fits the scalar area, 8-byte aligned");
 /* the chunks' speculative start states and end states, 64 x 2 each, during the DC phases only: the dec1 output region
    (its history is restored by PhDec1, the spectrum scratch of a row block is written after PhDcFix) */
 constexpr int vDcSpec = oD1I, vDcEnd = oD1I + 2 * kDcChunks;
-/* behind them, until PhDcFix: the samples either side of the seam of the sequence, I[2048 - W ..] then Q[.. W - 1], as one run
-   (PhLoad writes it beside the raw tile): the warm-up of the first Q chunks reads its I part and its Q part from here
-   in one piece */
+/* behind them, until PhDcFix: the samples either side of the seam of the sequence, I[kDcBridgeLo ..] then
+   Q[.. kDcBridgeHi - 2049], as one run (PhLoad writes it beside the raw tile): the warm-up of the first Q chunks reads its
+   I part and its Q part from here in one piece */
 constexpr int vDcBridge = oD1I + 4 * kDcChunks;
-static_assert(vDcBridge + 2 * kDcWarm <= oD1I + 2 * kD1Len, "DC chunk states and the bridge fit the dec1 region");
+static_assert(vDcBridge + kDcBridgeLen <= oD1I + 2 * kD1Len, "DC chunk states and the bridge fit the dec1 region");
 
 struct LaunchArgs {
   const float *iq;
@@ -188,6 +217,7 @@ struct Cta {
   int row;     /* this block produces a spectrum row */
   int row_idx;
   int rows_only;   /* 1 in t41rx_rows_kernel */
+  int casc_warp;   /* rows kernel: the warp of the CTA that runs the ZoomFFT cascade */
   int dc_carried;  /* rows kernel: the slot holds the DC-block state the previous row block ended in (every block a row) */
 };
 
@@ -455,8 +485,8 @@ T41RX_DEV void PhLoad(Cta &c, int tid) {
         s[oRawI + 27 + n] = v[gg][k].x;
         s[oRawQ + 27 + n] = v[gg][k].y;
         /* the DC bridge (vDcBridge) */
-        if (n >= kBlock - kDcSpecWarm) s[vDcBridge + n - (kBlock - kDcSpecWarm)] = v[gg][k].x;
-        if (n < kDcSpecWarm) s[vDcBridge + kDcSpecWarm + n] = v[gg][k].y;
+        if (n >= kDcBridgeLo) s[vDcBridge + n - kDcBridgeLo] = v[gg][k].x;
+        if (n < kDcBridgeHi - kBlock) s[vDcBridge + kBlock - kDcBridgeLo + n] = v[gg][k].y;
       }
     }
   }
@@ -587,7 +617,7 @@ T41RX_DEV void PhDcWarm(Cta &c, int tid) {
     d1 = s[oMisc + mDcD1];
   }
   /* one run of consecutive floats: in the tile, or (a warm-up across the seam) in the bridge */
-  float *x = (start < kBlock && end > kBlock) ? s + vDcBridge + (start - (kBlock - kDcSpecWarm)) : DcSample(s, start);
+  float *x = (start < kBlock && end > kBlock) ? s + vDcBridge + (start - kDcBridgeLo) : DcSample(s, start);
   const DcCoef k = DcCoefs();
   float lx = 0.0f, ly = 0.0f;
   DcSegment<false>(x, end - start, k, p, false, d1, lx, ly);
@@ -829,12 +859,16 @@ T41RX_DEV void PhZoomIir(Cta &c, int tid) {
 #endif
 
 /* window the 512 samples into the spectrum FFT buffer */
-T41RX_DEV void PhSpecWindow(Cta &c, int tid) {
+/* part: 0 = every receiver; 1 = only those at zoom x1 (their input is the raw tile), 2 = only the zoomed ones (the
+   rows-only kernel runs part 1 before the ZoomFFT cascade, whose idle lanes then have the x1 receivers' dead tiles to
+   work on, and part 2 behind it) */
+T41RX_DEV void PhSpecWindow(Cta &c, int tid, int part = 0) {
   if (!c.row) return;
   const int g = tid >> 6, u = tid & 63;
   if (g >= c.ng) return;
   float *s = Slot(c, g);
   const StreamCfg &cf = CfgOf(c, g);
+  if ((part == 1 && cf.zoom != 0) || (part == 2 && cf.zoom == 0)) return;
   const StreamState &st = c.a.st[Sid(c, g)];
   float2 *buf = reinterpret_cast<float2 *>(s + vSpecFft);
   const IqFix fix = IqFixOf(cf);
@@ -2363,7 +2397,12 @@ T41RX_DEV void PhRowDcSeed(Cta &c, int tid) {
 
 #ifndef T41RX_HOST_EMUL
 /* ---- device-only throughput forms of the two serial pieces of the rows-only kernel ---- */
+#ifndef T41RX_ROWS_LAYOUT
 constexpr int vRowTail = oOla;                    /* 256 floats: last Q samples of the previous block */
+#else
+constexpr int vRowTail = vDcSpec;                 /* (consumed by the seed before PhDcWarm writes the chunk states) */
+static_assert(kDcWarm <= 4 * kDcChunks, "the tail fits the chunk-state area");
+#endif
 
 /* stage the 256 samples PhRowDcSeed filters (coalesced instead of 256 dependent global loads) */
 T41RX_DEV void PhRowTailLoad(Cta &c, int tid) {
@@ -2519,11 +2558,12 @@ T41RX_DEV void PhZoomIirPipe(Cta &c, int tid) {
   constexpr int kSkew = 15, kAhead = 4, kGroup = 8, kLate = 2, kEdgeSteps = 48;
   static_assert(kGroup <= kSkew - kAhead - kLate, "a stage never fetches what its predecessor has not written yet");
   static_assert(kSlot % 32 == 8 && (oRawQ - oRawI) % 32 == 28 && kSkew % 2 == 1, "bank map of the cascade lanes");
-  /* the stretch inactive lanes work on: dead in the rows kernel between PhDcFix and PhSpecWindow */
-  constexpr int kDummy = oD1I + 80;
-  static_assert(kDummy - 27 - 3 * kSkew >= oD1I && kDummy + kBlock + 3 * kSkew + kAhead + 4 <= oD1H, "dummy stretch inside the slot");
-  if (tid >= 32) return;
-  const int lane = tid, g = lane >> 3;
+  /* the stretch inactive lanes work on: their own slot's raw tile (no receiver in the slot, or one at zoom x1 whose
+     spectrum input has been taken from the tile already: PhSpecWindow part 1 runs before this phase) */
+  constexpr int kDummy = oRawI + 27 + 3 * kSkew;
+  static_assert(kDummy + kBlock + 3 * kSkew + kAhead + 4 <= 2 * kRawLen, "dummy stretch inside the raw tile");
+  if ((tid >> 5) != c.casc_warp) return;
+  const int lane = tid & 31, g = lane >> 3;
   const bool have = g < c.ng;
   const int gg = have ? g : 0;
   const StreamCfg &cf = CfgOf(c, gg);
@@ -2531,7 +2571,7 @@ T41RX_DEV void PhZoomIirPipe(Cta &c, int tid) {
   const bool active = have && cf.zoom != 0;
   if (!__any_sync(0xffffffffu, active)) return;       /* every receiver of the CTA at zoom x1: no cascade (CalcZoom1Magn) */
   const int chn = (lane >> 2) & 1, sg = lane & 3;
-  float *x = Slot(c, gg) + (active ? (chn ? oRawQ : oRawI) + 27 : kDummy);
+  float *x = Slot(c, g) + (active ? (chn ? oRawQ : oRawI) + 27 : kDummy);    /* (slot g exists even without a receiver) */
   float b0 = 0, b1 = 0, b2 = 0, a1 = 0, a2 = 0, x1 = 0, x2 = 0, y1 = 0, y2 = 0;
   if (active) {
     const float *kk = c.a.zoom_iir + (cf.zoom - 1) * 20 + 5 * sg;
@@ -2654,7 +2694,7 @@ T41RX_DEV void PhZoomDecimateEnd(Cta &c, int tid) {
   RX_PHASE(PhDcMain(c, tid));                                            \
   RX_PHASE(PhDcVerify(c, tid));                                          \
   RX_PHASE(PhDcFix(c, tid));                                             \
-  RX_PHASE(PhZoomShift(c, tid));                                         \
+  RX_PHASE(PhZoomShift(c, tid); PhSpecWindow(c, tid, 1));                \
   if (c.a.flags & 4u) {                                                  \
     RX_PHASE(PhZoomIirScan(c, tid));                                     \
   } else {                                                               \
@@ -2662,7 +2702,7 @@ T41RX_DEV void PhZoomDecimateEnd(Cta &c, int tid) {
   }                                                                      \
   RX_PHASE(PhZoomDecimate(c, tid));                                      \
   RX_PHASE(PhZoomDecimateEnd(c, tid));                                   \
-  RX_PHASE(PhSpecWindow(c, tid));                                        \
+  RX_PHASE(PhSpecWindow(c, tid, 2));                                     \
   RX_PHASE(PhSpecFftPass(c, tid, 0));                                    \
   RX_PHASE(PhSpecFftPass(c, tid, 1));                                    \
   RX_PHASE(PhSpecFftPass(c, tid, 2));                                    \

@@ -134,6 +134,7 @@ int emul_process(Emul *e, const float *iq, float *audio, int n_blocks, int row_e
       c.row = 0;
       c.row_idx = 0;
       c.rows_only = 0;
+      c.casc_warp = 0;
       c.dc_carried = 0;
       for (int i = 0; i < kSmemFloats; ++i) smem[i] = NAN;
       for (int tid = 0; tid < kNT; ++tid) PhCtaInit(c, tid);
@@ -172,6 +173,7 @@ int emul_process(Emul *e, const float *iq, float *audio, int n_blocks, int row_e
     c.row = 0;
     c.row_idx = 0;
     c.rows_only = 0;
+    c.casc_warp = 0;
     c.dc_carried = 0;
     /* poison: shared memory is uninitialised at CTA start on the GPU */
     for (int i = 0; i < kSmemFloats; ++i) smem[i] = NAN;
