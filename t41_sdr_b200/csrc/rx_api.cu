@@ -960,7 +960,7 @@ static int LaunchRange(t41rx_ctx *ctx, const void *iq_any, void *audio_any, bool
     f.stream_ids = (p_len > 0) ? ctx->d_fast_ids[v] + f_off : nullptr;     /* nothing for the other kernel in range: contiguous */
     if (first == 0 && count == ctx->n_streams && !ctx->h_fast_grouped[v].empty()) f.stream_ids = ctx->d_fast_grouped[v];
     if (has_row && (a.spec_rows || a.wf_rows)) {
-      CUDA_TRY(LaunchRowsKernel(f, st));
+      CUDA_TRY(LaunchRowsKernel(f, ctx->n_sms, st));
       ctx->launches += 1;
     }
     cudaEvent_t *kev = ctx->kev[ctx->kev_count % kKernelEventRing];

@@ -14,7 +14,7 @@ cudaError_t LaunchStreamKernel(const LaunchArgs &a, int n_sms, cudaStream_t st);
 int StreamKernelMaxReceiversPerCta();
 
 cudaError_t ConfigureRowsKernel();
-cudaError_t LaunchRowsKernel(const LaunchArgs &a, cudaStream_t st);
+cudaError_t LaunchRowsKernel(const LaunchArgs &a, int n_sms, cudaStream_t st);
 long long RowsDcRefilterCount();                                        /* < 0: error */
 cudaError_t RowsPhaseCycles(unsigned long long *out64, int reset);     /* developer builds (T41RX_PHASE_TIMING) */
 

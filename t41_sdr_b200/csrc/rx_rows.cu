@@ -25,8 +25,7 @@ __device__ unsigned long long g_rows_phase_cycles[64];
 /* display spectrum + waterfall rows of the row-producing blocks, for the receivers the throughput kernel
    serves; launched before it on the same stream (reads the launch-start state, writes only the zoom /
    spectrum state and the row outputs) */
-__global__ void __launch_bounds__(kNT, kRowsCtasPerSm) t41rx_rows_kernel(const LaunchArgs a) {
-  extern __shared__ __align__(16) float smem[];
+__device__ __forceinline__ void RowsKernelBody(const LaunchArgs &a, float *smem) {
   Cta c;
   c.a = a;
   c.smem = smem;
@@ -83,13 +82,28 @@ __global__ void __launch_bounds__(kNT, kRowsCtasPerSm) t41rx_rows_kernel(const L
   }
 }
 
+__global__ void __launch_bounds__(kNT, kRowsCtasPerSm) t41rx_rows_kernel(const LaunchArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  RowsKernelBody(a, smem);
+}
+/* the same kernel with the registers of two CTAs per SM (no spills): for launches whose CTAs are all resident at two per SM
+   anyway (a bank's one row per step: C2's 256 CTAs) */
+__global__ void __launch_bounds__(kNT, 2) t41rx_rows_wide_kernel(const LaunchArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  RowsKernelBody(a, smem);
+}
+
 cudaError_t ConfigureRowsKernel() {
-  return cudaFuncSetAttribute(t41rx_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemFloats * sizeof(float)));
+  cudaError_t e = cudaFuncSetAttribute(t41rx_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemFloats * sizeof(float)));
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(t41rx_rows_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemFloats * sizeof(float)));
 }
 
 /* rows of a.n_streams receivers (a.stream_ids / a.stream_base) on stream st */
-cudaError_t LaunchRowsKernel(const LaunchArgs &a, cudaStream_t st) {
-  t41rx_rows_kernel<<<(a.n_streams + kG - 1) / kG, kNT, kSmemFloats * sizeof(float), st>>>(a);
+cudaError_t LaunchRowsKernel(const LaunchArgs &a, int n_sms, cudaStream_t st) {
+  const int grid = (a.n_streams + kG - 1) / kG;
+  if (grid <= 2 * n_sms) t41rx_rows_wide_kernel<<<grid, kNT, kSmemFloats * sizeof(float), st>>>(a);
+  else t41rx_rows_kernel<<<grid, kNT, kSmemFloats * sizeof(float), st>>>(a);
   return cudaGetLastError();
 }
 
