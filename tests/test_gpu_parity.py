@@ -420,6 +420,32 @@ def test_c4_full_size_16384_spectrum_rows():
         assert np.array_equal(out["wf"][k::D], np.broadcast_to(w["wf"], out["wf"][k::D].shape))
 
 
+def test_rows_kernel_full_bank_rows_bit_identical_and_call_chunking():
+    """The rows-only kernel (default flags) on a bank large enough for three of its CTAs to share every SM: CTAs
+    that mix zoom x1 with zoomed receivers (the cascade's idle lanes run on the x1 receivers' dead tiles), every
+    block a row (DC-block state carried from block to block), a partial last CTA, and the same run cut into two
+    calls (the second call's first block is seeded from the buffer instead).  Rows and waterfall identical to the
+    oracle's for every distinct waveform and across all replicas."""
+    S, T, D = 8190, 6, 10
+    base_p = [cases.P(spectrum_zoom=k % 5, current_scale=1 + (k // 5)) for k in range(D)]
+    base_iq = [synth.two_tone(700 + k, T, f1=46500.0 - 300 * k, f2=50500.0) for k in range(D)]
+    params = [rx_driver.to_rx_params(base_p[s % D]) for s in range(S)]
+    iq = np.stack([base_iq[s % D] for s in range(S)])
+    with _receiver(S) as eng:
+        eng.set_params_each(params)
+        one = eng.process(iq, row_every=1)
+    with _receiver(S) as eng:
+        eng.set_params_each(params)
+        a = eng.process(np.ascontiguousarray(iq[:, :2]), row_every=1)
+        b = eng.process(np.ascontiguousarray(iq[:, 2:]), row_every=1)
+    for key in ("spec", "wf"):
+        assert np.array_equal(np.concatenate([a[key], b[key]], axis=1), one[key])
+    for k in range(D):
+        w = O.OracleStream(base_p[k]).process(base_iq[k], 1)
+        assert np.array_equal(one["spec"][k::D], np.broadcast_to(w["spec"], one["spec"][k::D].shape)), k
+        assert np.array_equal(one["wf"][k::D], np.broadcast_to(w["wf"], one["wf"][k::D].shape)), k
+
+
 def test_c3_full_size_8192_nfm_sam_state_transitions():
     S, T, D = 8192, 24, 8
     case = cases.c3_nfm_sam_agc(n=D, T=T)
