@@ -2548,7 +2548,7 @@ T41RX_DEV void PhZoomIirPipe(Cta &c, int tid) {
   /* ONE warp serves the CTA's receivers, eight lanes each.  Lane (receiver g, channel c, stage s) touches bank
      8 g + 28 c - kSkew s (mod 32) at every step: with an ODD skew these are 32 different banks (an even one leaves
      only the multiples of 4: a 4-way conflict on every load and store of the loop).
-     Where the time of a step goes (tools/ubench/casc_loop.cu, one warp, clocks per step): the y-chain alone 12.2, with
+     Where the time of a step goes (tools/microbench/casc_loop.cu, one warp, clocks per step): the y-chain alone 12.2, with
      the three input terms 14.4, with the fetch 14.5, with the store of the step's own result 18.0, and 20.8 if that
      store is predicated (the form of the first two rounds).  The result of a step is the last link of the chain: a
      store of it sits in the issue order right where the next step's multiply wants to go.  So the main loop stores

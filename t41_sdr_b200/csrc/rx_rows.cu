@@ -36,7 +36,7 @@ __device__ __forceinline__ void RowsKernelBody(const LaunchArgs &a, float *smem)
   const int tid = threadIdx.x;
   /* The cascade phase is ONE warp per CTA issuing about an instruction per clock for 2093 steps: the cascade warps of
      the CTAs that share an SM must sit on different warp schedulers (hardware warp slot mod 4), or they take turns.
-     The slots of co-resident 8-warp CTAs start at 0, 9, 16 (tools/ubench/warp_slots.cu): warp 0 of the first and of
+     The slots of co-resident 8-warp CTAs start at 0, 9, 16 (tools/microbench/warp_slots.cu): warp 0 of the first and of
      the third CTA would share scheduler 0.  Each CTA gives the cascade to its warp on scheduler (first slot / 8). */
   __shared__ unsigned warp_slot[kNT / 32];
   if ((tid & 31) == 0) asm("mov.u32 %0, %%warpid;" : "=r"(warp_slot[tid >> 5]));

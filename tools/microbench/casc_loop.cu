@@ -1,6 +1,6 @@
 // Developer microbenchmark: the ZoomFFT cascade loop of PhZoomIirPipe (one warp, shared-memory hand-over between the
 // stages) in variants, clocks per step.
-// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 --fmad=false -o tools/ubench/_bin/casc_loop tools/ubench/casc_loop.cu
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 --fmad=false -o tools/microbench/_bin/casc_loop tools/microbench/casc_loop.cu
 #include <cstdio>
 #include <cuda_runtime.h>
 

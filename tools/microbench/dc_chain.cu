@@ -1,6 +1,6 @@
 // Developer microbenchmark: the DC-block recurrence (y = b0 x + d1; d1 = b1 x + a1 y) of one warp in stages: registers only,
 // with shared-memory loads, with the loads batched ahead.  Clocks per step.
-// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 --fmad=false -o tools/ubench/_bin/dc_chain tools/ubench/dc_chain.cu
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 --fmad=false -o tools/microbench/_bin/dc_chain tools/microbench/dc_chain.cu
 #include <cstdio>
 #include <cuda_runtime.h>
 #include "rx_phases.cuh"

@@ -1,7 +1,7 @@
 // Developer microbenchmark: the DC-block speculation phases (PhDcWarm / PhDcMain of rx_phases.cuh) alone, one CTA of the
 // product's shape (4 receivers x 64 chunk lanes), clocks per warp.  Variants by -DT41RX_DC_BATCH=..., -DWARPS=... (how many of
 // the CTA's 8 warps run), -DCTAS=... (CTAs on the SM).
-// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 --fmad=false -I t41_sdr_b200/csrc -I include -o tools/ubench/_bin/dc_loop tools/ubench/dc_loop.cu
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 --fmad=false -I t41_sdr_b200/csrc -I include -o tools/microbench/_bin/dc_loop tools/microbench/dc_loop.cu
 #include <cstdio>
 #include <cuda_runtime.h>
 #include "rx_phases.cuh"

@@ -1,6 +1,6 @@
 // Developer microbenchmark: per-SM throughput of the FP64 operations and conversions the bit-exact mixer uses
 // (one CTA of 1024 threads per SM, independent chains).
-// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 --fmad=false -o tools/ubench/_bin/fp64_rates tools/ubench/fp64_rates.cu
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 --fmad=false -o tools/microbench/_bin/fp64_rates tools/microbench/fp64_rates.cu
 #include <cstdio>
 #include <cuda_runtime.h>
 template <int kMode>

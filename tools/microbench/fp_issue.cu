@@ -1,5 +1,5 @@
 // Developer microbenchmark: how fast can ONE warp issue independent FP32 instructions (FMUL / FADD / FFMA, register operands)?
-// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 --fmad=false -o /tmp/fp_issue tools/ubench/fp_issue.cu
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 --fmad=false -o /tmp/fp_issue tools/microbench/fp_issue.cu
 #include <cstdio>
 #include <cuda_runtime.h>
 

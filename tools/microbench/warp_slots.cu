@@ -1,5 +1,5 @@
 // Developer microbenchmark: which hardware warp slots (%warpid) do the warps of two co-resident 256-thread CTAs get?
-// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/ubench/_bin/warp_slots tools/ubench/warp_slots.cu
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/microbench/_bin/warp_slots tools/microbench/warp_slots.cu
 #include <cstdio>
 #include <cuda_runtime.h>
 __global__ void __launch_bounds__(256, 2) k(unsigned *out) {
