@@ -67,6 +67,20 @@ T41RX_HD void Dft8(float *r, float *i) {
  * `b` in [0,64) enumerates the butterflies of the pass; buf is 512 interleaved complex.
  * tw: 512 (cos, sin) pairs of 2*pi*k/512.
  */
+/* Where element i of a 512-point buffer lives in the phase kernels' shared memory.  With the elements in natural order
+ * every pass but the first collides on the banks: pass 1's lanes are four groups 512 bytes apart (4 wavefronts where 2
+ * would do), pass 2's lanes each walk a contiguous 64 bytes (16 where 2 would do; ncu: the butterflies' loads and stores
+ * were 2/3 of the bit-exact front kernel's bank conflicts).  The low four bits of the index (the 16 eight-byte columns of
+ * a 128-byte row) are XORed with bits of the row number so that in every pass the 16 lanes of a half-warp fall into 16
+ * different columns:
+ *   pass 0  i = b + 64 m        a half-warp is 16 consecutive elements of one row: any XOR keeps them apart;
+ *   pass 1  i = 64 q + 8 m + j  lanes (q, j), q = 0..1 | 2..3: bit 3 ^= q & 1 parts the two q of a half-warp;
+ *   pass 2  i = 8 b + m         lanes b: column = 8 (b & 1) + m; low three bits ^= (b >> 1) & 7 parts the eight pairs.
+ * Both are bits of i >> 4 (bit 6 of i is q & 1 in pass 1 and bit 2 of b >> 1 in pass 2). */
+T41RX_HD int FftPhys(int i) { return i ^ (((i >> 4) & 7) | (((i >> 6) & 1) << 3)); }
+
+/* kSwz: the buffer is in FftPhys order (shared memory of the phase kernels); else natural order (host) */
+template <bool kSwz = false>
 T41RX_HD void Radix8Butterfly(float2 *buf, const float2 *tw, int pass, int b) {
   int n2, j, i0, stride;
   if (pass == 0) { n2 = 64; j = b; i0 = b; stride = 1; }
@@ -75,12 +89,12 @@ T41RX_HD void Radix8Butterfly(float2 *buf, const float2 *tw, int pass, int b) {
   float r[8], im[8];
 #pragma unroll
   for (int m = 0; m < 8; ++m) {
-    const float2 x = buf[i0 + m * n2];
+    const float2 x = buf[kSwz ? FftPhys(i0 + m * n2) : i0 + m * n2];
     r[m] = x.x;
     im[m] = x.y;
   }
   Dft8(r, im);
-  buf[i0] = float2{r[0], im[0]};
+  buf[kSwz ? FftPhys(i0) : i0] = float2{r[0], im[0]};
 #pragma unroll
   for (int k = 1; k < 8; ++k) {
     float re = r[k], ie = im[k];
@@ -91,7 +105,7 @@ T41RX_HD void Radix8Butterfly(float2 *buf, const float2 *tw, int pass, int b) {
       re = rc + is;
       ie = ic - rs;
     }
-    buf[i0 + k * n2] = float2{re, ie};
+    buf[kSwz ? FftPhys(i0 + k * n2) : i0 + k * n2] = float2{re, ie};
   }
 }
 

@@ -890,7 +890,7 @@ T41RX_DEV void PhSpecWindow(Cta &c, int tid, int part = 0) {
       re = (float)((double)a * w);
       im = (float)((double)b * w);
     }
-    buf[i] = float2{re, im};
+    buf[FftPhys(i)] = float2{re, im};
   }
 }
 
@@ -898,7 +898,7 @@ T41RX_DEV void PhSpecFftPass(Cta &c, int tid, int pass) {
   if (!c.row) return;
   const int g = tid >> 6, u = tid & 63;
   if (g >= c.ng) return;
-  Radix8Butterfly(reinterpret_cast<float2 *>(Slot(c, g) + vSpecFft), c.a.twiddle, pass, u);
+  Radix8Butterfly<true>(reinterpret_cast<float2 *>(Slot(c, g) + vSpecFft), c.a.twiddle, pass, u);
 }
 
 /* |X|^2 with half swap -> smoothing -> log -> pixel -> spectrum and waterfall rows */
@@ -921,7 +921,7 @@ T41RX_DEV void PhSpecRow(Cta &c, int tid) {
   for (int j = 0; j < 8; ++j) {
     const int x = u + 64 * j;
     const int bin = (x + 256) & 511;
-    const float2 v = buf[OctRev3((unsigned)bin)];
+    const float2 v = buf[FftPhys((int)OctRev3((unsigned)bin))];
     const float pw = v.x * v.x + v.y * v.y;
     const float old = olds[j];
     float shown;
@@ -1167,13 +1167,13 @@ T41RX_DEV void PhDec2(Cta &c, int tid) {
     if (mode == kModePsk31) {
       s[vAud + 23 + o] = acc[0][r];                /* Process.cpp:376-387,745: raw decimated I */
     } else if (mode == kModeNfm) {
-      fa[kDec + o] = float2{acc[0][r], acc[1][r]}; /* Process.cpp:272-275 */
+      fa[FftPhys(kDec + o)] = float2{acc[0][r], acc[1][r]}; /* Process.cpp:272-275 */
     } else {
       const float li = acc[0][r] * vol_scale, lq = acc[1][r] * vol_scale;
       float2 prev = float2{s[oOla + o], s[oOla + 256 + o]};
       if (first_block) prev = float2{0.0f, 0.0f};
-      fa[o] = prev;
-      fa[kDec + o] = float2{li, lq};
+      fa[FftPhys(o)] = prev;
+      fa[FftPhys(kDec + o)] = float2{li, lq};
       s[oOla + o] = li;
       s[oOla + 256 + o] = lq;
     }
@@ -1196,7 +1196,7 @@ T41RX_DEV void PhPostDec2(Cta &c, int tid) {
       /* fmdemod_quadri_K is a double literal (Demod.h:7): K * num / den runs in double */
       const double kq = 0.340447550238101026565118445432744920253753662109375;
       for (int o = tid; o < kDec; o += kNT) {
-      const float2 now = fa[kDec + o];
+      const float2 now = fa[FftPhys(kDec + o)];
       const float den = now.x * now.x + now.y * now.y;
       float out;
       if (o == 0) {
@@ -1204,7 +1204,7 @@ T41RX_DEV void PhPostDec2(Cta &c, int tid) {
         const float num = now.x * (now.y - lq) - now.y * (now.x - li);
         out = (float)(kq * (double)num / (double)den);
       } else {
-        const float2 last = fa[kDec + o - 1];
+        const float2 last = fa[FftPhys(kDec + o - 1)];
         const float num = now.y * last.x - now.x * last.y;
         out = (float)(kq * (double)num / (double)den);
         out = (1.0f < out) ? 1.0f : out;           /* limiter skips index 0 (B5) */
@@ -1225,8 +1225,8 @@ T41RX_DEV void PhNfmAssemble(Cta &c, int tid) {
     StreamState &st = c.a.st[Sid(c, g)];
     float2 *fa = reinterpret_cast<float2 *>(s + vFftA);
     if (tid == 0) {                                /* "last sample" = complex sample 127 (B4) */
-      st.nfm_last_i = fa[kDec + 127].x;
-      st.nfm_last_q = fa[kDec + 127].y;
+      st.nfm_last_i = fa[FftPhys(kDec + 127)].x;
+      st.nfm_last_q = fa[FftPhys(kDec + 127)].y;
     }
   }
 }
@@ -1238,8 +1238,8 @@ T41RX_DEV void PhNfmAssemble2(Cta &c, int tid) {
     float2 *fa = reinterpret_cast<float2 *>(s + vFftA);
     for (int o = tid; o < kDec; o += kNT) {
       const float a = s[vAmTmp + o];
-      fa[o] = float2{s[oOla + o], 0.0f};
-      fa[kDec + o] = float2{a, 0.0f};
+      fa[FftPhys(o)] = float2{s[oOla + o], 0.0f};
+      fa[FftPhys(kDec + o)] = float2{a, 0.0f};
       s[oOla + o] = a;
     }
   }
@@ -1254,7 +1254,7 @@ T41RX_DEV void PhFftPass(Cta &c, int tid, int which, int pass) {
   const int g = tid >> 6, u = tid & 63;
   if (g >= c.ng) return;
   if (!UsesFilter(CfgOf(c, g).mode)) return;
-  Radix8Butterfly(reinterpret_cast<float2 *>(Slot(c, g) + (which ? vFftB : vFftA)), c.a.twiddle, pass, u);
+  Radix8Butterfly<true>(reinterpret_cast<float2 *>(Slot(c, g) + (which ? vFftB : vFftA)), c.a.twiddle, pass, u);
 }
 
 /* digit-reverse the forward result, multiply by the mask, conjugate for the inverse */
@@ -1274,10 +1274,10 @@ T41RX_DEV void PhMask(Cta &c, int tid) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int k = u + 64 * j;
-    const float2 x = fa[OctRev3((unsigned)k)];
+    const float2 x = fa[FftPhys((int)OctRev3((unsigned)k))];
     const float2 h = LdgRO(mask + k);
     const float rr = x.x * h.x, ii = x.y * h.y, ri = x.x * h.y, ir = x.y * h.x;
-    fb[k] = float2{rr - ii, -(ri + ir)};
+    fb[FftPhys(k)] = float2{rr - ii, -(ri + ir)};
     /* row-producing block: keep the masked spectrum for the audio-spectrum by-product (Process.cpp:550-553) */
     if (arow) arow[k] = float2{rr - ii, ri + ir};
   }
@@ -1301,7 +1301,7 @@ T41RX_DEV void PhAgcPre(Cta &c, int tid) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int i = u + 64 * j;
-    const float2 v = fb[OctRev3((unsigned)(kDec + i))];
+    const float2 v = fb[FftPhys((int)OctRev3((unsigned)(kDec + i)))];
     z[j] = float2{v.x * inv, -v.y * inv};
   }
   if (cf.agc_mode == 0) {
