@@ -2083,7 +2083,7 @@ T41RX_DEV void PhEqBands(Cta &c, int tid) {
   const int g = tid >> 6, u = tid & 63;
   if (g >= c.ng || u >= 14) return;
   const int sid = Sid(c, g);
-  if (!c.a.cfg[sid].eq_on) return;
+  if (!CfgOf(c, g).eq_on) return;
   float *s = Slot(c, g);
   StreamState &st = c.a.st[sid];
   const float *k = c.a.eq_coeffs + 20 * u;
@@ -2218,7 +2218,7 @@ T41RX_DEV void PhNrSpectral(Cta &c, int tid) {
   const int g = SerialStream(c, tid);
   if (g < 0) return;
   const int sid = Sid(c, g);
-  const StreamCfg &cf = c.a.cfg[sid];
+  const StreamCfg &cf = CfgOf(c, g);
   if ((!cf.nr_kim && !cf.nr_spectral) || !c.a.nr) return;
   float *s = Slot(c, g);
   if (cf.nr_kim) KimNrLane(c.a.nr[sid], cf, c.a.nr_tab, c.a.twiddle, s + vAud + 23, s + vNrBuf, s + vNrTmp, s + vNrOut);
@@ -2229,7 +2229,7 @@ T41RX_DEV void PhNoiseBlank(Cta &c, int tid) {
   const int g = SerialStream(c, tid);
   if (g < 0) return;
   const int sid = Sid(c, g);
-  if (!c.a.cfg[sid].nb_on || !c.a.nr) return;
+  if (!CfgOf(c, g).nb_on || !c.a.nr) return;
   float *s = Slot(c, g);
   NoiseBlankLane(c.a.nr[sid], s + vAud + 23, s + vNrBuf, s + vNrTmp);
 }
@@ -2726,7 +2726,7 @@ T41RX_DEV void PhAudioSquares(Cta &c, int tid) {
   const int g = tid >> 6, u = tid & 63;
   if (g >= c.ng) return;
   const int sid = Sid(c, g);
-  if (!AudioSpecUpdates(c.a.cfg[sid].mode)) return;
+  if (!AudioSpecUpdates(CfgOf(c, g).mode)) return;
   float *s = Slot(c, g);
   const float *src = reinterpret_cast<const float *>(c.a.aspec + ((size_t)sid * c.a.n_rows + c.row_idx) * kFft);
   float m = 0.0f;
@@ -2744,7 +2744,7 @@ T41RX_DEV void PhAudioPixels(Cta &c, int tid) {
   const int g = tid >> 6, u = tid & 63;
   if (g >= c.ng) return;
   const int sid = Sid(c, g);
-  const int mode = c.a.cfg[sid].mode;
+  const int mode = CfgOf(c, g).mode;
   StreamState &st = c.a.st[sid];
   const float *sq = Slot(c, g);
   int32_t *out = c.a.audio_ypixel ? c.a.audio_ypixel + ((size_t)sid * c.a.n_rows + c.row_idx) * kAudioSpecPixels : nullptr;
@@ -2798,7 +2798,7 @@ T41RX_DEV void PhSpecFrameMax(Cta &c, int tid) {
   const int g = tid >> 6, u = tid & 63;
   if (g >= c.ng) return;
   const int sid = Sid(c, g);
-  const StreamCfg &cf = c.a.cfg[sid];
+  const StreamCfg &cf = CfgOf(c, g);
   if (cf.zoom == 0) return;
   const int16_t *row = c.a.spec_rows + ((size_t)sid * c.a.n_rows + c.row_idx) * kSpecRes;
   int m = 0;
@@ -2813,7 +2813,7 @@ T41RX_DEV void PhSpecFrameWrite(Cta &c, int tid) {
   const int g = tid >> 6, u = tid & 63;
   if (g >= c.ng) return;
   const int sid = Sid(c, g);
-  const StreamCfg &cf = c.a.cfg[sid];
+  const StreamCfg &cf = CfgOf(c, g);
   uint8_t *f = c.a.spec_frames + ((size_t)sid * c.a.n_rows + c.row_idx) * kSpecFrameBytes;
   if (cf.zoom == 0) {                       /* CalcZoom1Magn sends nothing */
     for (int i = u; i < kSpecFrameBytes; i += 64) f[i] = 0;
