@@ -1779,55 +1779,50 @@ struct SerAgc {
     st.agc_ring_max = rm;
     st.agc_hang_counter = hc; st.agc_state = state; st.agc_decay_type = dtype; st.agc_action = action;
   }
-  /* one sample: delayed |z| and the window maximum in, volts out */
+  /* one sample: delayed |z| and the window maximum in, volts out.
+     The reference's ladder of ifs (DSP_Fn.cpp:521-626) written as selects: the lanes of the serial kernel's AGC warp are 32
+     receivers in whatever states their signals put them, and as branches the ladder ran once per state present in the
+     warp (tools/microbench/ser_stages.cu: 419 clocks per sample with the lanes in different states, the slowest stage of
+     the pipeline).  Every candidate value is formed by the same operations on the same operands as in its branch. */
   T41RX_DEV float Step(float abs_out, float r) {
     fast = k_fbm * abs_out + k_omfbm * fast;
     hang = k_hbm * abs_out + k_omhbm * hang;
     rm = r;
-    if (hc > 0) --hc;
+    hc = (hc > 0) ? hc - 1 : hc;
     const float d = rm - v;
-    if (rm >= v) {                       /* every state: attack; 2,3,4 remember the level they left */
-      if (state >= 2) save = v;
-      state = 0;
-      v += d * k_attack;
-    } else if (state == 3) {
-      const float step = d * k_decay;
-      v = (float)((double)v + (double)step * .05);   /* double product and sum */
-    } else if (state == 0) {
-      if (v > k_pop * fast) {
-        state = 1;
-        v += d * k_fdecay;
-      } else if (k_henable && (hang > k_hlevel)) {
-        state = 2;
-        hc = k_hload;
-        dtype = 1;
-      } else {
-        state = 3;
-        v += d * k_decay;
-        dtype = 0;
-      }
-    } else if (state == 1) {
-      if (v > save) {
-        v += d * k_fdecay;
-      } else if (hc > 0) {
-        state = 2;
-      } else if (dtype == 0) {
-        state = 3;
-        v += d * k_decay;
-      } else {
-        state = 4;
-        v += d * k_hdecay;
-      }
-    } else if (state == 2) {
-      if (hc == 0) {
-        state = 4;
-        v += d * k_hdecay;
-      }
-    } else {
-      v += d * k_hdecay;
-    }
-    action = (v < k_minv) ? 0 : 1;
-    v = (v < k_minv) ? k_minv : v;
+    const float v_att = v + d * k_attack;
+    const float v_fd = v + d * k_fdecay;
+    const float v_dk = v + d * k_decay;
+    const float v_hd = v + d * k_hdecay;
+    const float step3 = d * k_decay;
+    const float v_d3 = (float)((double)v + (double)step3 * .05);   /* state 3: double product and sum */
+    const bool att = rm >= v;                        /* every state: attack; 2,3,4 remember the level they left */
+    const bool pop = v > k_pop * fast;
+    const bool hangc = (k_henable != 0) && (hang > k_hlevel);
+    const bool above = v > save;
+    const bool hc_pos = hc > 0;
+    const int s = state;
+    /* state 0 without attack: 1 (fast decay) | 2 (hang) | 3 (decay) */
+    const int n0 = pop ? 1 : (hangc ? 2 : 3);
+    const float v0 = pop ? v_fd : (hangc ? v : v_dk);
+    /* state 1 without attack: stay | 2 | 3 | 4 */
+    const int n1 = above ? 1 : (hc_pos ? 2 : (dtype == 0 ? 3 : 4));
+    const float v1 = above ? v_fd : (hc_pos ? v : (dtype == 0 ? v_dk : v_hd));
+    /* state 2: until the hang counter runs out; state 4: hang decay */
+    const int n2 = hc_pos ? 2 : 4;
+    const float v2 = hc_pos ? v : v_hd;
+    int ns = (s == 3) ? 3 : (s == 0) ? n0 : (s == 1) ? n1 : (s == 2) ? n2 : s;
+    float nv = (s == 3) ? v_d3 : (s == 0) ? v0 : (s == 1) ? v1 : (s == 2) ? v2 : v_hd;
+    const bool to_hang = !att && s == 0 && !pop && hangc;
+    const bool to_decay = !att && s == 0 && !pop && !hangc;
+    hc = to_hang ? k_hload : hc;
+    dtype = to_hang ? 1 : (to_decay ? 0 : dtype);
+    save = (att && s >= 2) ? v : save;
+    ns = att ? 0 : ns;
+    nv = att ? v_att : nv;
+    state = ns;
+    action = (nv < k_minv) ? 0 : 1;
+    v = (nv < k_minv) ? k_minv : nv;
     return v;
   }
 };
