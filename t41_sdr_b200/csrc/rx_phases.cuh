@@ -329,16 +329,20 @@ T41RX_DEV float Atan2Approx(float y, float x) {   /* Demod.cpp:148-197 (TPI quir
 
 /* arm_sin_f32 / arm_cos_f32 tail: linear interpolation in the 513-entry table */
 T41RX_DEV float TableTurns(const float *tab, float in) {
-  int32_t n = (int32_t)in;
-  if (in < 0.0f) n--;
-  in = in - (float)n;
+  /* arm_sin_f32: n = (int32_t) in; if (in < 0) n--; in -= (float) n.  floorf gives the same float except at the negative
+     integers, where the reference is left with in = 1.0 -> findex = 512 -> wrapped to entry 0 with fraction 0: the same
+     table entry and fraction as in = 0.  One rounding instruction instead of a conversion to integer and back on the
+     serial chain of the SAM PLL; likewise for the fraction below (0 <= findex <= 512: floorf(findex) = (float) index) */
+  in = in - floorf(in);
   float findex = 512.0f * in;
   uint32_t index = (uint32_t)findex & 0xFFFFu;
+  float findex_floor = floorf(findex);
   if (index >= 512u) {
     index = 0;
     findex -= 512.0f;
+    findex_floor = 0.0f;
   }
-  const float fract = findex - (float)index;
+  const float fract = findex - findex_floor;
   const float a = tab[index];                     /* the table sits in shared memory (vSamSin) */
   const float b = tab[index + 1];
   const float wa = (1.0f - fract) * a;
