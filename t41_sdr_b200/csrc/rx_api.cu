@@ -362,6 +362,7 @@ constexpr int kKernelEventRing = 32;
 constexpr int kProcessChunks = 16;  /* most chunks of the host-buffer entry point's copy / compute pipeline (cut over time) */
 constexpr int kReceiverChunks = 8;  /* chunks when a short call is cut over receivers */
 constexpr size_t kSerialScratchBytes = (size_t)2048 << 20;  /* most hand-over scratch of the split bit-exact chain */
+constexpr int kPipeMinBlocks = 16;          /* launches this long run their bit-exact chain as a pipeline of chunks (LaunchExact) */
 
 struct t41rx_ctx {
   int device = 0;
@@ -372,7 +373,7 @@ struct t41rx_ctx {
   /* the serial kernel of the split bit-exact chain is a bundle of latency-bound chains (one warp trio per 32
      receivers): in a mixed bank it runs on this stream beside the throughput kernel of the other receivers */
   cudaStream_t aux = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join_b = nullptr;   /* front done -> serial; serial done -> back (alternating) */
   cudaEvent_t ev_in[kProcessChunks] = {}, ev_done[kProcessChunks] = {};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool ev_valid = false;
@@ -556,6 +557,7 @@ void t41rx_destroy(t41rx_ctx *ctx) {
   }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->ev_join_b) cudaEventDestroy(ctx->ev_join_b);
   if (ctx->aux) cudaStreamDestroy(ctx->aux);
   if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
   if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
@@ -593,6 +595,7 @@ int t41rx_create(t41rx_ctx **out, int n_streams, int device) {
       cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_join_b, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_ext, cudaEventDisableTiming) != cudaSuccess)
     return bail(Fail(T41RX_ECUDA, "t41rx_create: stream/event creation failed%s"));
@@ -803,12 +806,27 @@ static int LaunchExact(t41rx_ctx *ctx, const LaunchArgs &p, cudaStream_t st, con
     ctx->launches += 1;
     return overlap();
   }
+  /* The launch is cut over time into chunks (scratch bounded; a launch of kPipeMinBlocks blocks or more into at least
+     two) and the chunks are pipelined over two scratch halves:
+         st :  F0  F1  [the other receivers' kernels]  B0  F2  B1  F3  B2 ...
+         aux:      S0  S1 .........................        S2      S3 ...
+     S(c) waits for F(c) and follows S(c - 1); B(c) waits for S(c).  The serial kernel is three latency-bound warps per 32
+     receivers: beside a front kernel, the throughput kernel or a back kernel it costs them little, alone it leaves the
+     GPU idle.  Hazards: F, S and B own disjoint parts of the receiver state; F(c + 2) re-uses the scratch half of chunk c,
+     and B(c), which has waited for S(c), precedes it on st. */
   const size_t per_block = (size_t)n * kDec * (sizeof(float4) + sizeof(float));
-  int chunk = (int)std::min<size_t>((size_t)p.n_blocks, std::max<size_t>(1, kSerialScratchBytes / per_block));
+  const bool pipe = p.n_blocks >= kPipeMinBlocks;
+  const size_t budget = pipe ? kSerialScratchBytes / 2 : kSerialScratchBytes;
+  int chunk = (int)std::min<size_t>((size_t)p.n_blocks, std::max<size_t>(1, budget / per_block));
+  if (pipe) chunk = std::min(chunk, (p.n_blocks + 1) / 2);
+  const int n_chunks = (p.n_blocks + chunk - 1) / chunk;
+  const int halves = n_chunks > 1 ? 2 : 1;
+  const size_t in_elems = (size_t)n * chunk * kDec, out_elems = (size_t)n * chunk * kDec;
   int rc;
-  if ((rc = Grow(&ctx->d_ser_in, &ctx->cap_ser_in, (size_t)n * chunk * kDec * sizeof(float4)))) return rc;
-  if ((rc = Grow(&ctx->d_ser_out, &ctx->cap_ser_out, (size_t)n * chunk * kDec * sizeof(float)))) return rc;
-  for (int c0 = 0; c0 < p.n_blocks; c0 += chunk) {
+  if ((rc = Grow(&ctx->d_ser_in, &ctx->cap_ser_in, halves * in_elems * sizeof(float4)))) return rc;
+  if ((rc = Grow(&ctx->d_ser_out, &ctx->cap_ser_out, halves * out_elems * sizeof(float)))) return rc;
+  auto args_of = [&](int c) {
+    const int c0 = c * chunk;
     LaunchArgs q = p;
     q.iq = p.iq ? p.iq + (size_t)c0 * 2 * kBlock : nullptr;
     q.audio = p.audio ? p.audio + (size_t)c0 * kBlock : nullptr;
@@ -818,58 +836,38 @@ static int LaunchExact(t41rx_ctx *ctx, const LaunchArgs &p, cudaStream_t st, con
     q.psk_chars = p.psk_chars ? p.psk_chars + c0 : nullptr;
     q.t0 = p.t0 + c0;
     q.n_blocks = std::min(chunk, p.n_blocks - c0);
-    q.ser_in = (float4 *)ctx->d_ser_in;
-    q.ser_out = (float *)ctx->d_ser_out;
-#ifdef T41RX_DEV_KNOBS
-    static cudaEvent_t dev_ev[6];
-    if (!dev_ev[0]) for (auto &e : dev_ev) cudaEventCreate(&e);
-    cudaEventRecord(dev_ev[0], st);
-#endif
+    q.ser_in = (float4 *)ctx->d_ser_in + (size_t)(c & (halves - 1)) * in_elems;
+    q.ser_out = (float *)ctx->d_ser_out + (size_t)(c & (halves - 1)) * out_elems;
+    return q;
+  };
+  auto front_and_serial = [&](int c) -> int {
+    const LaunchArgs q = args_of(c);
     t41rx_exact_front_kernel<<<grid, kNT, kSmemFloats * sizeof(float), st>>>(q);
     CUDA_TRY(cudaGetLastError());
-#ifdef T41RX_DEV_KNOBS
-    cudaEventRecord(dev_ev[1], st);
-#endif
-    if (c0 == 0) {
-      /* first chunk: the serial kernel on the side stream, the other receivers' kernels (overlap) on st beside it */
-      CUDA_TRY(cudaEventRecord(ctx->ev_fork, st));
-      CUDA_TRY(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
-      t41rx_exact_serial_kernel<<<(n + kSerialLanes - 1) / kSerialLanes, kSerialThreads, 0, ctx->aux>>>(q);
-      CUDA_TRY(cudaGetLastError());
-      CUDA_TRY(cudaEventRecord(ctx->ev_join, ctx->aux));
-#ifdef T41RX_DEV_KNOBS
-      cudaEventRecord(dev_ev[5], ctx->aux);
-#endif
-      if ((rc = overlap())) return rc;
-#ifdef T41RX_DEV_KNOBS
-      cudaEventRecord(dev_ev[2], st);
-#endif
-      CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_join, 0));
-#ifdef T41RX_DEV_KNOBS
-      cudaEventRecord(dev_ev[3], st);
-#endif
-    } else {
-      t41rx_exact_serial_kernel<<<(n + kSerialLanes - 1) / kSerialLanes, kSerialThreads, 0, st>>>(q);
-      CUDA_TRY(cudaGetLastError());
-    }
+    CUDA_TRY(cudaEventRecord(ctx->ev_fork, st));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
+    t41rx_exact_serial_kernel<<<(n + kSerialLanes - 1) / kSerialLanes, kSerialThreads, 0, ctx->aux>>>(q);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord((c & 1) ? ctx->ev_join_b : ctx->ev_join, ctx->aux));
+    ctx->launches += 2;
+    return T41RX_OK;
+  };
+  auto back = [&](int c) -> int {
+    const LaunchArgs q = args_of(c);
+    CUDA_TRY(cudaStreamWaitEvent(st, (c & 1) ? ctx->ev_join_b : ctx->ev_join, 0));
     t41rx_exact_back_kernel<<<grid, kNT, kSmemFloats * sizeof(float), st>>>(q);
     CUDA_TRY(cudaGetLastError());
-#ifdef T41RX_DEV_KNOBS
-    if (c0 == 0 && getenv("T41RX_DEV_TIMELINE")) {          /* developer builds only: where the step's time goes */
-      cudaEventRecord(dev_ev[4], st);
-      cudaEventSynchronize(dev_ev[4]);
-      float f, o, j, b, js;
-      cudaEventElapsedTime(&f, dev_ev[0], dev_ev[1]);
-      cudaEventElapsedTime(&o, dev_ev[1], dev_ev[2]);
-      cudaEventElapsedTime(&j, dev_ev[2], dev_ev[3]);
-      cudaEventElapsedTime(&b, dev_ev[3], dev_ev[4]);
-      cudaEventElapsedTime(&js, dev_ev[1], dev_ev[5]);
-      fprintf(stderr, "[exact timeline] front %.3f ms | other kernels on st %.3f | wait for serial %.3f (serial done at +%.3f) | back %.3f\n", f, o, j, js, b);
-    }
-#endif
-    ctx->launches += 3;
+    ctx->launches += 1;
+    return T41RX_OK;
+  };
+  if ((rc = front_and_serial(0))) return rc;
+  for (int c = 1; c < n_chunks; ++c) {
+    if ((rc = front_and_serial(c))) return rc;
+    if (c == 1 && (rc = overlap())) return rc;
+    if ((rc = back(c - 1))) return rc;
   }
-  return T41RX_OK;
+  if (n_chunks == 1 && (rc = overlap())) return rc;
+  return back(n_chunks - 1);
 }
 
 /* enqueue the kernels for a span of the call on stream st (buffer pointers are those of the whole call) */
