@@ -362,6 +362,10 @@ constexpr int kKernelEventRing = 32;
 constexpr int kProcessChunks = 16;  /* most chunks of the host-buffer entry point's copy / compute pipeline (cut over time) */
 constexpr int kReceiverChunks = 8;  /* chunks when a short call is cut over receivers */
 constexpr size_t kSerialScratchBytes = (size_t)2048 << 20;  /* most hand-over scratch of the split bit-exact chain */
+#ifndef T41RX_PIPE_CHUNKS
+#define T41RX_PIPE_CHUNKS 2
+#endif
+constexpr int kPipeChunks = T41RX_PIPE_CHUNKS;   /* chunks a long launch is cut into (not below kPipeMinBlocks / 2 blocks each) */
 constexpr int kPipeMinBlocks = 16;          /* launches this long run their bit-exact chain as a pipeline of chunks (LaunchExact) */
 
 struct t41rx_ctx {
@@ -818,7 +822,7 @@ static int LaunchExact(t41rx_ctx *ctx, const LaunchArgs &p, cudaStream_t st, con
   const bool pipe = p.n_blocks >= kPipeMinBlocks;
   const size_t budget = pipe ? kSerialScratchBytes / 2 : kSerialScratchBytes;
   int chunk = (int)std::min<size_t>((size_t)p.n_blocks, std::max<size_t>(1, budget / per_block));
-  if (pipe) chunk = std::min(chunk, (p.n_blocks + 1) / 2);
+  if (pipe) chunk = std::min(chunk, std::max(kPipeMinBlocks / 2, (p.n_blocks + kPipeChunks - 1) / kPipeChunks));
   const int n_chunks = (p.n_blocks + chunk - 1) / chunk;
   const int halves = n_chunks > 1 ? 2 : 1;
   const size_t in_elems = (size_t)n * chunk * kDec, out_elems = (size_t)n * chunk * kDec;
